@@ -1,0 +1,1222 @@
+/*
+ * oracle/twin.c -- TEST INFRASTRUCTURE ONLY. Not part of the product; nothing under
+ * gg_b200/ may include, link or dlopen this file.
+ *
+ * CPU restatement of gg's Vello-style tile pipeline (the "CPU twin" the reference itself
+ * uses as the oracle for its GPU shaders). Every function cites the reference file:line it
+ * restates (paths relative to gogpu/gg). Arithmetic is float32 with the same operation
+ * order as the Go source; transcendental calls go through float64 libm and are rounded to
+ * float32 exactly where the Go code does (util.go:36-37,104-105). Must be compiled with
+ * -ffp-contract=off (Go/amd64 does not fuse multiply-add).
+ *
+ * Parity pin: tests/test_oracle_golden.py checks this file against the reference's own
+ * golden PNGs (testdata/golden/vello-gpu-pipeline, copied to tests/golden/) at the
+ * thresholds of tilecompute/rasterizer_test.go:39-135 and against the known-answer vectors
+ * of scene_encode_test.go / coarse_test.go / fine_ptcl_test.go / fine_clip_test.go.
+ */
+#include "twin.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define TILE_W 16
+#define TILE_H 16
+static const float TILE_SCALE = 1.0f / 16.0f;        /* types.go:7-11 */
+static const float ONE_MINUS_ULP = 0.99999994f;      /* util.go:17 */
+static const float ROBUST_EPSILON = 2e-7f;           /* util.go:20 */
+
+/* ------------------------------------------------------------------ util.go */
+typedef struct { float x, y; } vec2;
+static inline vec2 v2(float x, float y) { vec2 v = {x, y}; return v; }
+static inline vec2 vadd(vec2 a, vec2 b) { return v2(a.x + b.x, a.y + b.y); }
+static inline vec2 vsub(vec2 a, vec2 b) { return v2(a.x - b.x, a.y - b.y); }
+static inline vec2 vmul(vec2 a, float s) { return v2(a.x * s, a.y * s); }
+static inline float vdot(vec2 a, vec2 b) { return a.x * b.x + a.y * b.y; }
+static inline float vlen_sq(vec2 a) { return vdot(a, a); }
+static inline int veq(vec2 a, vec2 b) { return a.x == b.x && a.y == b.y; }
+
+/* Go's math.Hypot (math/hypot.go): p*sqrt(1+q*q) after ordering; restated so that the
+ * float64 value matches Go's rather than glibc's correctly rounded hypot. */
+static double go_hypot(double p, double q) {
+    if (isinf(p) || isinf(q)) return INFINITY;
+    if (isnan(p) || isnan(q)) return NAN;
+    p = fabs(p); q = fabs(q);
+    if (p < q) { double t = p; p = q; q = t; }
+    if (p == 0) return 0;
+    q = q / p;
+    return p * sqrt(1 + q * q);
+}
+static inline float vlength(vec2 v) { return (float)go_hypot((double)v.x, (double)v.y); }       /* util.go:36 */
+static inline float vatan2(vec2 v) { return (float)atan2((double)v.y, (double)v.x); }            /* util.go:37 */
+
+static inline float floor32(float x) { return (float)floor((double)x); }
+static inline float ceil32(float x) { return (float)ceil((double)x); }
+static inline float round32(float x) { return (float)round((double)x); }   /* half away from zero, as math.Round */
+static inline float abs32(float x) { return fabsf(x); }
+static inline float min32(float a, float b) { if (a != a) return b; if (b != b) return a; return a < b ? a : b; } /* util.go:62 */
+static inline float max32(float a, float b) { if (a != a) return b; if (b != b) return a; return a > b ? a : b; } /* util.go:76 */
+static inline float clamp32(float x, float lo, float hi) { if (x < lo) return lo; if (x > hi) return hi; return x; }
+static inline float copysign32(float x, float y) { return copysignf(x, y); }
+static inline float sin32(float x) { return (float)sin((double)x); }
+static inline float cos32(float x) { return (float)cos((double)x); }
+static inline float pow32(float base, int e) { float r = 1.0f; for (int i = 0; i < e; i++) r *= base; return r; }
+static inline float signum32(float x) {               /* util.go:118-130 */
+    if (x > 0) return 1; if (x < 0) return -1;
+    return signbit(x) ? -1.0f : 1.0f;
+}
+/* Go float32->uint32 / int32 conversions on amd64 (CVTTSS2SQ then truncate / CVTTSS2SL). */
+static inline uint32_t f2u(float f) { return (uint32_t)(int64_t)f; }
+static inline int32_t f2i(float f) { return (int32_t)f; }
+
+static uint32_t span(float a, float b) {              /* util.go:41-55 */
+    float mx = a, mn = a;
+    if (b > mx) mx = b;
+    if (b < mn) mn = b;
+    float r = ceil32(mx) - floor32(mn);
+    if (r < 1.0f) r = 1.0f;
+    return f2u(r);
+}
+
+/* growable line buffer with a hard cap (counts past the cap so callers can size) */
+typedef struct { ot_line_soup *out; uint32_t n, cap; } line_sink;
+static void sink_push(line_sink *s, vec2 a, vec2 b) {
+    if (s->n < s->cap) {
+        ot_line_soup *l = &s->out[s->n];
+        l->path_ix = 0; l->p0[0] = a.x; l->p0[1] = a.y; l->p1[0] = b.x; l->p1[1] = b.y;
+    }
+    s->n++;
+}
+
+/* ------------------------------------------------------------------ euler.go */
+static const float TANGENT_THRESH = 1e-6f;            /* euler.go:11 */
+typedef struct { float th0, th1, chord_len, err; } cubic_params;
+typedef struct { float th0, k0, k1, ch; } euler_params;
+
+static cubic_params cubic_params_from_points_derivs(vec2 p0, vec2 p1, vec2 q0, vec2 q1, float dt) { /* euler.go:39-90 */
+    vec2 chord = vsub(p1, p0);
+    float chord_sq = vlen_sq(chord);
+    float chord_len = (float)sqrt((double)chord_sq);
+    cubic_params cp;
+    if (chord_sq < TANGENT_THRESH * TANGENT_THRESH) {
+        float chord_err = (float)sqrt((double)((float)(9.0 / 32.0) * (vlen_sq(q0) + vlen_sq(q1)))) * dt;
+        cp.th0 = 0; cp.th1 = 0; cp.chord_len = TANGENT_THRESH; cp.err = chord_err;
+        return cp;
+    }
+    float scale = dt / chord_sq;
+    vec2 h0 = v2(q0.x * chord.x + q0.y * chord.y, q0.y * chord.x - q0.x * chord.y);
+    float th0 = vatan2(h0);
+    float d0 = vlength(h0) * scale;
+    vec2 h1 = v2(q1.x * chord.x + q1.y * chord.y, q1.x * chord.y - q1.y * chord.x);
+    float th1 = vatan2(h1);
+    float d1 = vlength(h1) * scale;
+    float cth0 = cos32(th0), cth1 = cos32(th1);
+    float err;
+    if (cth0 * cth1 < 0) {
+        err = 2.0f;
+    } else {
+        const float two_thirds = (float)(2.0 / 3.0);
+        float e0 = two_thirds / max32(1.0f + cth0, 1e-9f);
+        float e1 = two_thirds / max32(1.0f + cth1, 1e-9f);
+        float s0 = sin32(th0), s1 = sin32(th1);
+        float s01 = cth0 * s1 + cth1 * s0;
+        float amin = 0.15f * (2 * e0 * s0 + 2 * e1 * s1 - e0 * e1 * s01);
+        float a = 0.15f * (2 * d0 * s0 + 2 * d1 * s1 - d0 * d1 * s01);
+        float aerr = abs32(a - amin);
+        float symm = abs32(th0 + th1);
+        float asymm = abs32(th0 - th1);
+        float dist = (float)go_hypot((double)(d0 - e0), (double)(d1 - e1));
+        float ctr = 4.625e-6f * pow32(symm, 5) + 7.5e-3f * asymm * symm * symm;
+        float halo_symm = 5e-3f * symm * dist;
+        float halo_asymm = 7e-2f * asymm * dist;
+        err = ctr + 1.55f * aerr + halo_symm + halo_asymm;
+    }
+    err *= chord_len;
+    cp.th0 = th0; cp.th1 = th1; cp.chord_len = chord_len; cp.err = err;
+    return cp;
+}
+
+static euler_params euler_params_from_angles(float th0, float th1) {   /* euler.go:93-119 */
+    float k0 = th0 + th1;
+    float dth = th1 - th0;
+    float d2 = dth * dth;
+    float k2 = k0 * k0;
+    float a = 6.0f;
+    a -= d2 * (float)(1.0 / 70.0);
+    a -= (d2 * d2) * (float)(1.0 / 10780.0);
+    a += (d2 * d2 * d2) * (float)2.769178184818219e-07;
+    float b = -0.1f + d2 * (float)(1.0 / 4200.0) + d2 * d2 * (float)1.6959677820260655e-05;
+    float c = (float)(-1.0 / 1400.0) + d2 * (float)6.84915970574303e-05 - k2 * (float)7.936475029053326e-06;
+    a += (b + c * k2) * k2;
+    float k1 = dth * a;
+    float ch = 1.0f;
+    ch -= d2 * (float)(1.0 / 40.0);
+    ch += (d2 * d2) * (float)0.00034226190482569864;
+    ch -= (d2 * d2 * d2) * (float)1.9349474568904524e-06;
+    float b2 = (float)(-1.0 / 24.0) + d2 * (float)0.0024702380951963226 - d2 * d2 * (float)3.7297408997537985e-05;
+    float c2 = (float)(1.0 / 1920.0) - d2 * (float)4.87350869747975e-05 - k2 * (float)3.1001936068463107e-06;
+    ch += (b2 + c2 * k2) * k2;
+    euler_params ep = {th0, k0, k1, ch};
+    return ep;
+}
+
+static void integ_euler_10(float k0, float k1, float *uo, float *vo) {   /* euler.go:149-186 */
+    float t1_1 = k0;
+    float t1_2 = 0.5f * k1;
+    float t2_2 = t1_1 * t1_1;
+    float t2_3 = 2.0f * (t1_1 * t1_2);
+    float t2_4 = t1_2 * t1_2;
+    float t3_4 = t2_2 * t1_2 + t2_3 * t1_1;
+    float t3_6 = t2_4 * t1_2;
+    float t4_4 = t2_2 * t2_2;
+    float t4_5 = 2.0f * (t2_2 * t2_3);
+    float t4_6 = 2.0f * (t2_2 * t2_4) + t2_3 * t2_3;
+    float t4_7 = 2.0f * (t2_3 * t2_4);
+    float t4_8 = t2_4 * t2_4;
+    float t5_6 = t4_4 * t1_2 + t4_5 * t1_1;
+    float t5_8 = t4_6 * t1_2 + t4_7 * t1_1;
+    float t6_6 = t4_4 * t2_2;
+    float t6_7 = t4_4 * t2_3 + t4_5 * t2_2;
+    float t6_8 = t4_4 * t2_4 + t4_5 * t2_3 + t4_6 * t2_2;
+    float t7_8 = t6_6 * t1_2 + t6_7 * t1_1;
+    float t8_8 = t6_6 * t2_2;
+    float u = 1.0f;
+    u -= (float)(1.0 / 24.0) * t2_2 + (float)(1.0 / 160.0) * t2_4;
+    u += (float)(1.0 / 1920.0) * t4_4 + (float)(1.0 / 10752.0) * t4_6 + (float)(1.0 / 55296.0) * t4_8;
+    u -= (float)(1.0 / 322560.0) * t6_6 + (float)(1.0 / 1658880.0) * t6_8;
+    u += (float)(1.0 / 92897280.0) * t8_8;
+    float v = (float)(1.0 / 12.0) * t1_2;
+    v -= (float)(1.0 / 480.0) * t3_4 + (float)(1.0 / 2688.0) * t3_6;
+    v += (float)(1.0 / 53760.0) * t5_6 + (float)(1.0 / 276480.0) * t5_8;
+    v -= (float)(1.0 / 11612160.0) * t7_8;
+    *uo = u; *vo = v;
+}
+
+static inline float ep_eval_th(const euler_params *ep, float t) {   /* euler.go:121-123 */
+    return (ep->k0 + 0.5f * ep->k1 * (t - 1.0f)) * t - ep->th0;
+}
+static vec2 ep_eval(const euler_params *ep, float t) {              /* euler.go:125-131 */
+    float thm = ep_eval_th(ep, t * 0.5f);
+    float u, v;
+    integ_euler_10((ep->k0 + ep->k1 * (0.5f * t - 0.5f)) * t, ep->k1 * t * t, &u, &v);
+    float s = t / ep->ch * sin32(thm);
+    float c = t / ep->ch * cos32(thm);
+    return v2(u * c - v * s, -v * c - u * s);
+}
+static vec2 ep_eval_with_offset(const euler_params *ep, float t, float offset) { /* euler.go:133-137 */
+    float th = ep_eval_th(ep, t);
+    vec2 ov = v2(offset * sin32(th), offset * cos32(th));
+    return vadd(ep_eval(ep, t), ov);
+}
+static vec2 es_eval_with_offset(vec2 p0, vec2 p1, const euler_params *ep, float t, float off) { /* euler.go:139-146 */
+    vec2 chord = vsub(p1, p0);
+    vec2 pt = ep_eval_with_offset(ep, t, off);
+    return v2(p0.x + chord.x * pt.x - chord.y * pt.y, p0.y + chord.x * pt.y + chord.y * pt.x);
+}
+
+/* ------------------------------------------------------------------ flatten.go */
+static const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f, FLATTEN_TOL = 0.25f;
+
+static void eval_cubic_and_deriv(vec2 p0, vec2 p1, vec2 p2, vec2 p3, float t, vec2 *po, vec2 *qo) { /* flatten.go:46-56 */
+    float m = 1.0f - t;
+    float mm = m * m, mt = m * t, tt = t * t;
+    *po = vadd(vmul(p0, mm * m), vmul(vadd(vadd(vmul(p1, 3 * mm), vmul(p2, 3 * mt)), vmul(p3, tt)), t));
+    *qo = vadd(vadd(vmul(vsub(p1, p0), mm), vmul(vsub(p2, p1), 2 * mt)), vmul(vsub(p3, p2), tt));
+}
+static inline float cube_signed_sqrt(float x) { return x * (float)sqrt((double)abs32(x)); } /* flatten.go:195 */
+static unsigned trailing_zeros32(uint32_t x) { if (x == 0) return 32; unsigned n = 0; while ((x & 1) == 0) { n++; x >>= 1; } return n; }
+
+static void flatten_euler_fill(vec2 p0, vec2 p1, vec2 p2, vec2 p3, line_sink *lines) {   /* flatten.go:60-184 */
+    if (veq(p0, p1) && veq(p0, p2) && veq(p0, p3)) return;
+    uint32_t t0u = 0;
+    float dt = 1.0f;
+    vec2 last_p = p0;
+    vec2 last_q = vsub(p1, p0);
+    if (vlen_sq(last_q) < DERIV_THRESH * DERIV_THRESH) {
+        vec2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &last_q);
+    }
+    float last_t = 0.0f;
+    vec2 lp0 = p0;
+    for (;;) {
+        float t0 = (float)t0u * dt;
+        if (t0 == 1.0f) break;
+        float t1 = t0 + dt;
+        vec2 this_p0 = last_p, this_q0 = last_q, this_p1, this_q1;
+        eval_cubic_and_deriv(p0, p1, p2, p3, t1, &this_p1, &this_q1);
+        if (vlen_sq(this_q1) < DERIV_THRESH * DERIV_THRESH) {
+            vec2 new_p1, new_q1;
+            eval_cubic_and_deriv(p0, p1, p2, p3, t1 - DERIV_EPS, &new_p1, &new_q1);
+            this_q1 = new_q1;
+            if (t1 < 1.0f) { this_p1 = new_p1; t1 -= DERIV_EPS; }
+        }
+        float actual_dt = t1 - last_t;
+        cubic_params cp = cubic_params_from_points_derivs(this_p0, this_p1, this_q0, this_q1, actual_dt);
+        if (cp.err <= FLATTEN_TOL || dt <= SUBDIV_LIMIT) {
+            euler_params ep = euler_params_from_angles(cp.th0, cp.th1);
+            float k0_minus_half_k1 = ep.k0 - 0.5f * ep.k1;
+            float k1 = ep.k1;
+            float scale_mul = 0.5f * (float)(M_SQRT2 / 2.0) *
+                              (float)sqrt((double)(cp.chord_len / (ep.ch * FLATTEN_TOL)));
+            const float k1_thresh = 1e-3f;
+            float n_frac;
+            int robust; /* 1 = LowK1, 2 = LowDist */
+            float a = 0, b = 0, integral = 0, int0 = 0;
+            if (abs32(k1) < k1_thresh) {
+                float k = k0_minus_half_k1 + 0.5f * k1;
+                n_frac = (float)sqrt((double)abs32(k));
+                robust = 1;
+            } else {
+                a = k1;
+                b = k0_minus_half_k1;
+                int0 = cube_signed_sqrt(b);
+                float int1 = cube_signed_sqrt(a + b);
+                integral = int1 - int0;
+                n_frac = (float)(2.0 / 3.0) * integral / a;
+                robust = 2;
+            }
+            float n = (float)ceil((double)(n_frac * scale_mul));
+            if (n < 1) n = 1;
+            if (n > 100) n = 100;
+            /* NaN n (degenerate input): Go's int(NaN) on amd64 is INT64_MIN -> empty loop. */
+            int n_int = (n != n) ? 0 : (int)n;
+            for (int i = 0; i < n_int; i++) {
+                vec2 lp1;
+                if (i == n_int - 1 && t1 == 1.0f) {
+                    lp1 = p3;
+                } else {
+                    float t = (float)(i + 1) / n;
+                    float s;
+                    if (robust == 1) {
+                        s = t;
+                    } else {
+                        float c = (float)cbrt((double)(integral * t + int0));
+                        float inv = c * abs32(c);
+                        s = (inv - b) / a;
+                    }
+                    lp1 = es_eval_with_offset(this_p0, this_p1, &ep, s, 0.0f);
+                }
+                sink_push(lines, lp0, lp1);
+                lp0 = lp1;
+            }
+            last_p = this_p1; last_q = this_q1; last_t = t1;
+            t0u++;
+            unsigned shift = trailing_zeros32(t0u);
+            t0u >>= shift;
+            dt *= (float)((uint32_t)1 << shift);
+        } else {
+            if (t0u < 0xFFFFFFFFu / 2) t0u *= 2;
+            dt *= 0.5f;
+        }
+    }
+}
+
+uint32_t ot_flatten_fill(const float *cubics, uint32_t n, ot_line_soup *out, uint32_t cap) {   /* flatten.go:32-43 */
+    line_sink s = {out, 0, cap};
+    for (uint32_t i = 0; i < n; i++) {
+        const float *c = cubics + 8 * (size_t)i;
+        flatten_euler_fill(v2(c[0], c[1]), v2(c[2], c[3]), v2(c[4], c[5]), v2(c[6], c[7]), &s);
+    }
+    return s.n;
+}
+
+/* internal/gpu/path_convert.go:29-112 (convertPathToPathDef geometry part).
+ * Lines from LineTo are appended immediately; cubics of a subpath are flushed (flattened)
+ * at MoveTo / Close / end, exactly as the reference orders them. */
+uint32_t ot_flatten_path(const uint8_t *verbs, uint32_t n_verbs, const double *coords,
+                         int auto_close, ot_line_soup *out, uint32_t cap) {
+    line_sink s = {out, 0, cap};
+    float *cub = NULL; uint32_t ncub = 0, capcub = 0;
+    vec2 current = v2(0, 0), start = v2(0, 0);
+    int has_move = 0;
+    const double *c = coords;
+#define FLUSH_CUBICS() do { for (uint32_t k_ = 0; k_ < ncub; k_++) { const float *q_ = cub + 8 * (size_t)k_; \
+        flatten_euler_fill(v2(q_[0], q_[1]), v2(q_[2], q_[3]), v2(q_[4], q_[5]), v2(q_[6], q_[7]), &s); } ncub = 0; } while (0)
+#define PUSH_CUBIC(a0, a1, a2, a3) do { if (ncub == capcub) { capcub = capcub ? capcub * 2 : 16; cub = (float *)realloc(cub, sizeof(float) * 8 * capcub); } \
+        float *q_ = cub + 8 * (size_t)ncub++; q_[0] = (a0).x; q_[1] = (a0).y; q_[2] = (a1).x; q_[3] = (a1).y; q_[4] = (a2).x; q_[5] = (a2).y; q_[6] = (a3).x; q_[7] = (a3).y; } while (0)
+    for (uint32_t i = 0; i < n_verbs; i++) {
+        switch (verbs[i]) {
+        case 0: /* MoveTo */
+            FLUSH_CUBICS();
+            if (auto_close && has_move && !veq(current, start)) sink_push(&s, current, start);
+            current = v2((float)c[0], (float)c[1]); start = current; has_move = 1; c += 2;
+            break;
+        case 1: { /* LineTo */
+            vec2 pt = v2((float)c[0], (float)c[1]); c += 2;
+            if (!has_move) break;
+            if (!veq(pt, current)) sink_push(&s, current, pt);
+            current = pt;
+        } break;
+        case 2: { /* QuadTo: elevated to cubic, path_convert.go:60-72 */
+            vec2 ctrl = v2((float)c[0], (float)c[1]), end = v2((float)c[2], (float)c[3]); c += 4;
+            if (!has_move) break;
+            const float k = (float)(2.0 / 3.0);
+            vec2 c1 = v2(current.x + k * (ctrl.x - current.x), current.y + k * (ctrl.y - current.y));
+            vec2 c2 = v2(end.x + k * (ctrl.x - end.x), end.y + k * (ctrl.y - end.y));
+            PUSH_CUBIC(current, c1, c2, end);
+            current = end;
+        } break;
+        case 3: { /* CubicTo */
+            vec2 c1 = v2((float)c[0], (float)c[1]), c2 = v2((float)c[2], (float)c[3]), end = v2((float)c[4], (float)c[5]); c += 6;
+            if (!has_move) break;
+            PUSH_CUBIC(current, c1, c2, end);
+            current = end;
+        } break;
+        case 4: /* Close */
+            FLUSH_CUBICS();
+            if (has_move && !veq(current, start)) sink_push(&s, current, start);
+            current = start;
+            break;
+        default: break;
+        }
+    }
+    FLUSH_CUBICS();
+    if (auto_close && has_move && !veq(current, start)) sink_push(&s, current, start);
+    free(cub);
+#undef FLUSH_CUBICS
+#undef PUSH_CUBIC
+    return s.n;
+}
+
+/* ------------------------------------------------------------------ pathtag.go / draw_leaf.go */
+void ot_path_monoid_new(uint32_t tag_word, ot_path_monoid *m) {   /* pathtag.go:26-63 */
+    uint32_t point_count = tag_word & 0x03030303u;
+    m->path_seg_ix = (uint32_t)__builtin_popcount((point_count * 7) & 0x04040404u);
+    m->trans_ix = (uint32_t)__builtin_popcount(tag_word & 0x20202020u);
+    uint32_t n_points = point_count + ((tag_word >> 2) & 0x01010101u);
+    uint32_t a = n_points + (n_points & (((tag_word >> 3) & 0x01010101u) * 15));
+    a += a >> 8;
+    a += a >> 16;
+    m->path_seg_offset = a & 0xff;
+    m->path_ix = (uint32_t)__builtin_popcount(tag_word & 0x10101010u);
+    m->style_ix = (uint32_t)__builtin_popcount(tag_word & 0x40404040u);
+}
+static void pm_combine(ot_path_monoid *a, const ot_path_monoid *b) {   /* pathtag.go:66-74 */
+    a->trans_ix += b->trans_ix; a->path_seg_ix += b->path_seg_ix; a->path_seg_offset += b->path_seg_offset;
+    a->style_ix += b->style_ix; a->path_ix += b->path_ix;
+}
+void ot_draw_monoid_new(uint32_t tag, ot_draw_monoid *m) {   /* draw_leaf.go:29-41 */
+    m->path_ix = tag != 0 ? 1 : 0;
+    m->clip_ix = tag & 1;
+    m->scene_offset = (tag >> 2) & 0x7;
+    m->info_offset = (tag >> 6) & 0xf;
+}
+static void dm_combine(ot_draw_monoid *a, const ot_draw_monoid *b) {
+    a->path_ix += b->path_ix; a->clip_ix += b->clip_ix; a->scene_offset += b->scene_offset; a->info_offset += b->info_offset;
+}
+
+/* ------------------------------------------------------------------ path_count.go */
+typedef struct {
+    vec2 xy0, xy1, s0, s1;
+    int is_down, is_positive_slope;
+    uint32_t count_x, count;
+    float dx, dy, a, b, sign, x0, y0;
+} dda;
+
+/* Shared DDA set-up: path_count.go:19-69 == path_tiling.go:28-71 */
+static void dda_setup(const ot_line_soup *line, dda *d) {
+    vec2 p0 = v2(line->p0[0], line->p0[1]), p1 = v2(line->p1[0], line->p1[1]);
+    d->is_down = p1.y >= p0.y;
+    if (d->is_down) { d->xy0 = p0; d->xy1 = p1; } else { d->xy0 = p1; d->xy1 = p0; }
+    d->s0 = vmul(d->xy0, TILE_SCALE);
+    d->s1 = vmul(d->xy1, TILE_SCALE);
+    d->count_x = span(d->s0.x, d->s1.x) - 1;
+    d->count = d->count_x + span(d->s0.y, d->s1.y);
+    d->dx = abs32(d->s1.x - d->s0.x);
+    d->dy = d->s1.y - d->s0.y;
+}
+static void dda_finish(dda *d) {
+    float idxdy = 1.0f / (d->dx + d->dy);
+    float a = d->dx * idxdy;
+    d->is_positive_slope = d->s1.x >= d->s0.x;
+    d->sign = d->is_positive_slope ? 1.0f : -1.0f;
+    float xt0 = floor32(d->s0.x * d->sign);
+    float c = d->s0.x * d->sign - xt0;
+    d->y0 = floor32(d->s0.y);
+    float ytop = (d->s0.y == d->s1.y) ? ceil32(d->s0.y) : d->y0 + 1.0f;
+    d->b = min32((d->dy * c + d->dx * (ytop - d->s0.y)) * idxdy, ONE_MINUS_ULP);
+    float robust_err = floor32(a * (float)(d->count - 1) + d->b) - (float)d->count_x;
+    if (robust_err != 0.0f) a -= copysign32(ROBUST_EPSILON, robust_err);
+    d->a = a;
+    d->x0 = d->is_positive_slope ? xt0 * d->sign : xt0 * d->sign - 1.0f;
+}
+
+uint32_t ot_path_count(const ot_line_soup *lines, uint32_t n_lines, const ot_path *paths,
+                       ot_tile *tile, ot_segment_count *seg_counts) {   /* path_count.go:11-205 */
+    uint32_t bump_seg_counts = 0;
+    for (uint32_t line_ix = 0; line_ix < n_lines; line_ix++) {
+        const ot_line_soup *line = &lines[line_ix];
+        dda d; dda_setup(line, &d);
+        if (d.dx + d.dy == 0.0f) continue;
+        if (d.dy == 0.0f && floor32(d.s0.y) == d.s0.y) continue;
+        dda_finish(&d);
+        float a = d.a, b = d.b, sign = d.sign, x0 = d.x0, y0 = d.y0;
+        vec2 s0 = d.s0, s1 = d.s1;
+        uint32_t count = d.count;
+        const ot_path *path = &paths[line->path_ix];
+        int32_t bboxi[4] = {(int32_t)path->bbox[0], (int32_t)path->bbox[1], (int32_t)path->bbox[2], (int32_t)path->bbox[3]};
+        float xmin = min32(s0.x, s1.x);
+        int32_t stride = bboxi[2] - bboxi[0];
+        if (s0.y >= (float)bboxi[3] || s1.y < (float)bboxi[1] || xmin >= (float)bboxi[2] || stride == 0) continue;
+        uint32_t imin = 0;
+        if (s0.y < (float)bboxi[1]) {
+            float iminf = round32(((float)bboxi[1] - y0 + b - a) / (1.0f - a)) - 1.0f;
+            if (y0 + iminf - floor32(a * iminf + b) < (float)bboxi[1]) iminf += 1.0f;
+            imin = f2u(iminf);
+        }
+        uint32_t imax = count;
+        if (s1.y > (float)bboxi[3]) {
+            float imaxf = round32(((float)bboxi[3] - y0 + b - a) / (1.0f - a)) - 1.0f;
+            if (y0 + imaxf - floor32(a * imaxf + b) < (float)bboxi[3]) imaxf += 1.0f;
+            imax = f2u(imaxf);
+        }
+        int32_t delta = d.is_down ? -1 : 1;
+        int32_t ymin = 0, ymax = 0;
+        if (max32(s0.x, s1.x) < (float)bboxi[0]) {
+            ymin = f2i(ceil32(s0.y));
+            ymax = f2i(ceil32(s1.y));
+            imax = imin;
+        } else {
+            float fudge = d.is_positive_slope ? 0.0f : 1.0f;
+            if (xmin < (float)bboxi[0]) {
+                float f = round32((sign * ((float)bboxi[0] - x0) - b + fudge) / a);
+                if ((x0 + sign * floor32(a * f + b) < (float)bboxi[0]) == d.is_positive_slope) f += 1.0f;
+                int32_t ynext = f2i(y0 + f - floor32(a * f + b) + 1.0f);
+                if (d.is_positive_slope) {
+                    if (f2u(f) > imin) {
+                        float y_off = (y0 != s0.y) ? 1.0f : 0.0f;
+                        ymin = f2i(y0 + y_off);
+                        ymax = ynext;
+                        imin = f2u(f);
+                    }
+                } else if (f2u(f) < imax) {
+                    ymin = ynext;
+                    ymax = f2i(ceil32(s1.y));
+                    imax = f2u(f);
+                }
+            }
+            if (max32(s0.x, s1.x) > (float)bboxi[2]) {
+                float f = round32((sign * ((float)bboxi[2] - x0) - b + fudge) / a);
+                if ((x0 + sign * floor32(a * f + b) < (float)bboxi[2]) == d.is_positive_slope) f += 1.0f;
+                if (d.is_positive_slope) { uint32_t fu = f2u(f); if (fu < imax) imax = fu; }
+                else { uint32_t fu = f2u(f); if (fu > imin) imin = fu; }
+            }
+        }
+        if (imin > imax) imax = imin;
+        if (ymin < bboxi[1]) ymin = bboxi[1];
+        if (ymax > bboxi[3]) ymax = bboxi[3];
+        for (int32_t y = ymin; y < ymax; y++) {
+            int32_t base = (int32_t)path->tiles + (y - bboxi[1]) * stride;
+            tile[base].backdrop += delta;
+        }
+        float last_z = floor32(a * (float)(imin - 1) + b);
+        uint32_t seg_base = bump_seg_counts;
+        bump_seg_counts += imax - imin;
+        for (uint32_t i = imin; i < imax; i++) {
+            float zf = a * (float)i + b;
+            float z = floor32(zf);
+            int32_t y = f2i(y0 + (float)i - z);
+            int32_t x = f2i(x0 + sign * z);
+            int32_t base = (int32_t)path->tiles + (y - bboxi[1]) * stride - bboxi[0];
+            int top_edge = (i == 0) ? (y0 == s0.y) : (last_z == z);
+            if (top_edge && x + 1 < bboxi[2]) {
+                int32_t x_bump = x + 1 > bboxi[0] ? x + 1 : bboxi[0];
+                tile[base + x_bump].backdrop += delta;
+            }
+            uint32_t seg_within_slice = tile[base + x].seg_count_or_ix;
+            tile[base + x].seg_count_or_ix++;
+            if (seg_counts) {
+                seg_counts[seg_base + i - imin].line_ix = line_ix;
+                seg_counts[seg_base + i - imin].counts = (seg_within_slice << 16) | i;
+            }
+            last_z = z;
+        }
+    }
+    return bump_seg_counts;
+}
+
+/* ------------------------------------------------------------------ path_tiling.go */
+void ot_path_tiling(const ot_segment_count *seg_counts, uint32_t n_seg_counts,
+                    const ot_line_soup *lines, const ot_path *paths, const ot_tile *tiles,
+                    ot_path_segment *segments) {   /* path_tiling.go:11-199 */
+    for (uint32_t seg_ix = 0; seg_ix < n_seg_counts; seg_ix++) {
+        ot_segment_count sc = seg_counts[seg_ix];
+        const ot_line_soup *line = &lines[sc.line_ix];
+        uint32_t seg_within_slice = sc.counts >> 16;
+        uint32_t seg_within_line = sc.counts & 0xffff;
+        dda d; dda_setup(line, &d); dda_finish(&d);
+        float a = d.a, b = d.b, sign = d.sign, x0 = d.x0, y0 = d.y0;
+        vec2 xy0 = d.xy0, xy1 = d.xy1;
+        uint32_t count = d.count;
+        float z = floor32(a * (float)seg_within_line + b);
+        int32_t x = f2i(x0) + f2i(sign * z);                       /* split truncation, path_tiling.go:74 */
+        int32_t y = f2i(y0 + (float)seg_within_line - z);
+        const ot_path *path = &paths[line->path_ix];
+        int32_t bboxi[4] = {(int32_t)path->bbox[0], (int32_t)path->bbox[1], (int32_t)path->bbox[2], (int32_t)path->bbox[3]};
+        int32_t stride = bboxi[2] - bboxi[0];
+        int32_t tile_ix = (int32_t)path->tiles + (y - bboxi[1]) * stride + x - bboxi[0];
+        ot_tile tile = tiles[tile_ix];
+        uint32_t seg_start = ~tile.seg_count_or_ix;
+        if ((int32_t)seg_start < 0) continue;
+        vec2 tile_xy = v2((float)x * (float)TILE_W, (float)y * (float)TILE_H);
+        vec2 tile_xy1 = vadd(tile_xy, v2((float)TILE_W, (float)TILE_H));
+        if (seg_within_line > 0) {
+            float z_prev = floor32(a * (float)(seg_within_line - 1) + b);
+            if (z == z_prev) {
+                float xt = xy0.x + (xy1.x - xy0.x) * (tile_xy.y - xy0.y) / (xy1.y - xy0.y);
+                xt = clamp32(xt, tile_xy.x + 1e-3f, tile_xy1.x);
+                xy0 = v2(xt, tile_xy.y);
+            } else {
+                float x_clip = d.is_positive_slope ? tile_xy.x : tile_xy1.x;
+                float yt = xy0.y + (xy1.y - xy0.y) * (x_clip - xy0.x) / (xy1.x - xy0.x);
+                yt = clamp32(yt, tile_xy.y + 1e-3f, tile_xy1.y);
+                xy0 = v2(x_clip, yt);
+            }
+        }
+        if (seg_within_line < count - 1) {
+            float z_next = floor32(a * (float)(seg_within_line + 1) + b);
+            if (z == z_next) {
+                float xt = xy0.x + (xy1.x - xy0.x) * (tile_xy1.y - xy0.y) / (xy1.y - xy0.y);
+                xt = clamp32(xt, tile_xy.x + 1e-3f, tile_xy1.x);
+                xy1 = v2(xt, tile_xy1.y);
+            } else {
+                float x_clip = d.is_positive_slope ? tile_xy1.x : tile_xy.x;
+                float yt = xy0.y + (xy1.y - xy0.y) * (x_clip - xy0.x) / (xy1.x - xy0.x);
+                yt = clamp32(yt, tile_xy.y + 1e-3f, tile_xy1.y);
+                xy1 = v2(x_clip, yt);
+            }
+        }
+        float y_edge = 1e9f;
+        vec2 p0o = vsub(xy0, tile_xy), p1o = vsub(xy1, tile_xy);
+        const float epsilon = 1e-6f;
+        if (p0o.x == 0.0f) {
+            if (p1o.x == 0.0f) {
+                p0o.x = epsilon;
+                if (p0o.y == 0.0f) { p1o.x = epsilon; p1o.y = (float)TILE_H; }
+                else { p1o.x = 2.0f * epsilon; p1o.y = p0o.y; }
+            } else if (p0o.y == 0.0f) {
+                p0o.x = epsilon;
+            } else {
+                y_edge = p0o.y;
+            }
+        } else if (p1o.x == 0.0f) {
+            if (p1o.y == 0.0f) p1o.x = epsilon; else y_edge = p1o.y;
+        }
+        if (p0o.x == floor32(p0o.x) && p0o.x != 0.0f) p0o.x -= epsilon;
+        if (p1o.x == floor32(p1o.x) && p1o.x != 0.0f) p1o.x -= epsilon;
+        if (!d.is_down) { vec2 t = p0o; p0o = p1o; p1o = t; }
+        ot_path_segment *o = &segments[seg_start + seg_within_slice];
+        o->p0[0] = p0o.x; o->p0[1] = p0o.y; o->p1[0] = p1o.x; o->p1[1] = p1o.y; o->y_edge = y_edge;
+    }
+}
+
+/* ------------------------------------------------------------------ coarse.go:169-223 / rasterizer.go:425-487 */
+void ot_line_bbox(const ot_line_soup *lines, uint32_t n, int w, int h, uint32_t bbox[4]) {
+    float min_x = 3.40282346638528859811704183484516925440e+38f, min_y = min_x, max_x = -min_x, max_y = -min_x;
+    for (uint32_t i = 0; i < n; i++) {
+        const float *pts[2] = {lines[i].p0, lines[i].p1};
+        for (int k = 0; k < 2; k++) {
+            const float *p = pts[k];
+            if (p[0] < min_x) min_x = p[0];
+            if (p[0] > max_x) max_x = p[0];
+            if (p[1] < min_y) min_y = p[1];
+            if (p[1] > max_y) max_y = p[1];
+        }
+    }
+    if (min_x < 0) min_x = 0;
+    if (min_y < 0) min_y = 0;
+    if (max_x > (float)w) max_x = (float)w;
+    if (max_y > (float)h) max_y = (float)h;
+    /* Go: uint32(math.Floor(float64(minX / 16))) -- float64->uint32 goes through int64 on amd64 */
+    uint32_t x0 = (uint32_t)(int64_t)floor((double)(min_x / (float)TILE_W));
+    uint32_t y0 = (uint32_t)(int64_t)floor((double)(min_y / (float)TILE_H));
+    uint32_t x1 = (uint32_t)(int64_t)ceil((double)(max_x / (float)TILE_W));
+    uint32_t y1 = (uint32_t)(int64_t)ceil((double)(max_y / (float)TILE_H));
+    uint32_t gx = (uint32_t)ceil((double)w / (double)TILE_W), gy = (uint32_t)ceil((double)h / (double)TILE_H);
+    if (x1 > gx) x1 = gx;
+    if (y1 > gy) y1 = gy;
+    bbox[0] = x0; bbox[1] = y0; bbox[2] = x1; bbox[3] = y1;
+}
+
+/* ------------------------------------------------------------------ fine.go:219-289 */
+static void fill_path(float *area, const ot_path_segment *segs, uint32_t n_segs, int32_t backdrop, int even_odd) {
+    float backdrop_f = (float)backdrop;
+    for (int i = 0; i < TILE_W * TILE_H; i++) area[i] = backdrop_f;
+    for (uint32_t s = 0; s < n_segs; s++) {
+        const ot_path_segment *seg = &segs[s];
+        float delta0 = seg->p1[0] - seg->p0[0], delta1 = seg->p1[1] - seg->p0[1];
+        for (int yi = 0; yi < TILE_H; yi++) {
+            float y = seg->p0[1] - (float)yi;
+            float y0 = clamp32(y, 0.0f, 1.0f);
+            float y1 = clamp32(y + delta1, 0.0f, 1.0f);
+            float dy = y0 - y1;
+            float y_edge = signum32(delta0) * clamp32((float)yi - seg->y_edge + 1.0f, 0.0f, 1.0f);
+            if (dy != 0.0f) {
+                float vec_y_recip = 1.0f / delta1;
+                float t0 = (y0 - y) * vec_y_recip;
+                float t1 = (y1 - y) * vec_y_recip;
+                float startx = seg->p0[0];
+                float x0 = startx + t0 * delta0;
+                float x1 = startx + t1 * delta0;
+                float xmin0 = min32(x0, x1);
+                float xmax0 = max32(x0, x1);
+                for (int i = 0; i < TILE_W; i++) {
+                    float i_f = (float)i;
+                    float xmin = min32(xmin0 - i_f, 1.0f) - 1.0e-6f;
+                    float xmax = xmax0 - i_f;
+                    float b = min32(xmax, 1.0f);
+                    float c = max32(b, 0.0f);
+                    float d = max32(xmin, 0.0f);
+                    float a = (b + 0.5f * (d * d - c * c) - xmin) / (xmax - xmin);
+                    area[yi * TILE_W + i] += y_edge + a * dy;
+                }
+            } else if (y_edge != 0.0f) {
+                for (int i = 0; i < TILE_W; i++) area[yi * TILE_W + i] += y_edge;
+            }
+        }
+    }
+    if (even_odd) {
+        for (int i = 0; i < TILE_W * TILE_H; i++) area[i] = abs32(area[i] - 2.0f * round32(0.5f * area[i]));
+    } else {
+        for (int i = 0; i < TILE_W * TILE_H; i++) area[i] = min32(abs32(area[i]), 1.0f);
+    }
+}
+
+/* ------------------------------------------------------------------ rasterizer.go:27-170 */
+void ot_rasterize(const ot_line_soup *lines, uint32_t n_lines, int even_odd, int w, int h, float *alpha) {
+    memset(alpha, 0, sizeof(float) * (size_t)w * h);
+    if (n_lines == 0) return;
+    ot_path path; path.tiles = 0;
+    ot_line_bbox(lines, n_lines, w, h, path.bbox);
+    int tiles_x = (int)(path.bbox[2] - path.bbox[0]), tiles_y = (int)(path.bbox[3] - path.bbox[1]);
+    int tile_count = tiles_x * tiles_y;
+    if (tile_count == 0) return;
+    ot_tile *tiles = (ot_tile *)calloc((size_t)tile_count, sizeof(ot_tile));
+    ot_line_soup *ll = (ot_line_soup *)malloc(sizeof(ot_line_soup) * n_lines);
+    uint32_t max_sc = 0;
+    for (uint32_t i = 0; i < n_lines; i++) {
+        ll[i] = lines[i]; ll[i].path_ix = 0;
+        dda d; dda_setup(&ll[i], &d); max_sc += d.count;
+    }
+    ot_segment_count *sc = (ot_segment_count *)calloc(max_sc ? max_sc : 1, sizeof(ot_segment_count));
+    uint32_t n_sc = ot_path_count(ll, n_lines, &path, tiles, sc);
+    uint32_t next = 0;
+    for (int i = 0; i < tile_count; i++) {
+        uint32_t n = tiles[i].seg_count_or_ix;
+        if (n != 0) { tiles[i].seg_count_or_ix = ~next; next += n; }
+    }
+    uint32_t total = next;
+    ot_path_segment *segs = (ot_path_segment *)calloc(total ? total : 1, sizeof(ot_path_segment));
+    ot_path_tiling(sc, n_sc, ll, &path, tiles, segs);
+    for (int y = 0; y < tiles_y; y++) {
+        int32_t sum = 0;
+        for (int x = 0; x < tiles_x; x++) { sum += tiles[y * tiles_x + x].backdrop; tiles[y * tiles_x + x].backdrop = sum; }
+    }
+    float area[TILE_W * TILE_H];
+    for (int ty = 0; ty < tiles_y; ty++) for (int tx = 0; tx < tiles_x; tx++) {
+        int tix = ty * tiles_x + tx;
+        uint32_t seg_start = ~tiles[tix].seg_count_or_ix, n_ts = 0;
+        const ot_path_segment *ts = NULL;
+        if ((int32_t)seg_start >= 0) {
+            uint32_t seg_end = total;
+            for (int nx = tix + 1; nx < tile_count; nx++) {
+                uint32_t ns = ~tiles[nx].seg_count_or_ix;
+                if ((int32_t)ns >= 0) { seg_end = ns; break; }
+            }
+            if (seg_start < seg_end) { ts = segs + seg_start; n_ts = seg_end - seg_start; }
+        }
+        fill_path(area, ts, n_ts, tiles[tix].backdrop, even_odd);
+        int gx = ((int)path.bbox[0] + tx) * TILE_W, gy = ((int)path.bbox[1] + ty) * TILE_H;
+        for (int ly = 0; ly < TILE_H; ly++) {
+            int py = gy + ly; if (py >= h) break;
+            for (int lx = 0; lx < TILE_W; lx++) {
+                int px = gx + lx; if (px >= w) break;
+                alpha[py * w + px] = area[ly * TILE_W + lx];
+            }
+        }
+    }
+    free(tiles); free(ll); free(sc); free(segs);
+}
+
+/* compositor.go:24-59 */
+static void blend_source_over(const uint8_t src[4], float alpha, uint8_t dst[4]) {
+    if (alpha <= 0) return;
+    if (alpha > 1.0f) alpha = 1.0f;
+    float src_a = alpha * (float)src[3] / 255.0f;
+    float sr = (float)src[0] / 255.0f * src_a, sg = (float)src[1] / 255.0f * src_a, sb = (float)src[2] / 255.0f * src_a;
+    float dr = (float)dst[0] / 255.0f, dg = (float)dst[1] / 255.0f, db = (float)dst[2] / 255.0f, da = (float)dst[3] / 255.0f;
+    float inv = 1.0f - src_a;
+    float or_ = sr + dr * inv, og = sg + dg * inv, ob = sb + db * inv, oa = src_a + da * inv;
+    dst[0] = (uint8_t)(or_ * 255.0f + 0.5f); dst[1] = (uint8_t)(og * 255.0f + 0.5f);
+    dst[2] = (uint8_t)(ob * 255.0f + 0.5f); dst[3] = (uint8_t)(oa * 255.0f + 0.5f);
+}
+
+/* rasterizer.go:176-224 RasterizeScene */
+void ot_rasterize_scene(const uint8_t bg[4], const ot_element *elems, uint32_t n_elems,
+                        const ot_line_soup *lines, int w, int h, uint8_t *out) {
+    for (int i = 0; i < w * h; i++) memcpy(out + 4 * (size_t)i, bg, 4);
+    float *alpha = (float *)malloc(sizeof(float) * (size_t)w * h);
+    for (uint32_t e = 0; e < n_elems; e++) {
+        if (elems[e].type != OT_ELEM_DRAW || elems[e].line_count == 0) continue;
+        ot_rasterize(lines + elems[e].line_start, elems[e].line_count, (int)elems[e].even_odd, w, h, alpha);
+        for (int i = 0; i < w * h; i++) {
+            if (alpha[i] <= 0) continue;
+            blend_source_over(elems[e].color, alpha[i], out + 4 * (size_t)i);
+        }
+    }
+    free(alpha);
+}
+
+/* ------------------------------------------------------------------ scene_encode.go + scans */
+typedef struct { uint32_t *d; uint32_t n, cap; } u32vec;
+static void u32_push(u32vec *v, uint32_t x) {
+    if (v->n == v->cap) { v->cap = v->cap ? v->cap * 2 : 64; v->d = (uint32_t *)realloc(v->d, sizeof(uint32_t) * v->cap); }
+    v->d[v->n++] = x;
+}
+static inline uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+enum { DRAWTAG_COLOR = 0x44, DRAWTAG_BEGIN_CLIP = 0x9, DRAWTAG_END_CLIP = 0x21 };          /* scene_encode.go:70-76 */
+enum { PTAG_LINETO = 0x9, PTAG_PATH = 0x10, PTAG_TRANSFORM = 0x20, PTAG_STYLE = 0x40 };      /* scene_encode.go:78-86 */
+enum { CMD_END = 0, CMD_FILL = 1, CMD_SOLID = 3, CMD_COLOR = 5, CMD_BEGIN_CLIP = 10, CMD_END_CLIP = 11 }; /* ptcl.go:17-24 */
+
+/* scene_encode.go:312-347 encodePath */
+static void encode_path(u32vec *raw_tags, u32vec *path_data, u32vec *transforms, u32vec *styles,
+                        const ot_line_soup *lines, uint32_t n, int even_odd) {
+    u32_push(raw_tags, PTAG_TRANSFORM);
+    const float ident[6] = {1, 0, 0, 1, 0, 0};
+    for (int i = 0; i < 6; i++) u32_push(transforms, f32_bits(ident[i]));
+    u32_push(raw_tags, PTAG_STYLE);
+    u32_push(styles, even_odd ? 0x02u : 0u);
+    int needs_move = 1; float last[2] = {0, 0};
+    for (uint32_t i = 0; i < n; i++) {
+        if (needs_move || lines[i].p0[0] != last[0] || lines[i].p0[1] != last[1]) {
+            u32_push(raw_tags, PTAG_LINETO);
+            u32_push(path_data, f32_bits(lines[i].p0[0])); u32_push(path_data, f32_bits(lines[i].p0[1]));
+            needs_move = 0;
+        }
+        u32_push(raw_tags, PTAG_LINETO);
+        u32_push(path_data, f32_bits(lines[i].p1[0])); u32_push(path_data, f32_bits(lines[i].p1[1]));
+        last[0] = lines[i].p1[0]; last[1] = lines[i].p1[1];
+    }
+    u32_push(raw_tags, PTAG_PATH);
+}
+
+/* scene_encode.go:162-168 colour packing */
+static uint32_t pack_color(const uint8_t c[4]) {
+    float a = (float)c[3] / 255.0f;
+    uint32_t r = f2u((float)c[0] * a + 0.5f), g = f2u((float)c[1] * a + 0.5f), b = f2u((float)c[2] * a + 0.5f);
+    return r | (g << 8) | (b << 16) | ((uint32_t)c[3] << 24);
+}
+
+typedef struct { uint32_t *cmds; uint32_t n, cap; } ptcl;
+static void ptcl_push(ptcl *p, uint32_t w) {
+    if (p->n == p->cap) { p->cap = p->cap ? p->cap * 2 : 64; p->cmds = (uint32_t *)realloc(p->cmds, sizeof(uint32_t) * p->cap); }
+    p->cmds[p->n++] = w;
+}
+typedef struct { uint32_t clip_depth, clip_zero_depth, blend_depth, max_blend_depth; } tile_clip_state;  /* coarse.go:313-320 */
+
+/* coarse.go:651-679 tileSegRange */
+static void tile_seg_range(ot_tile tile, int local_idx, int tile_count, const ot_tile *path_tiles, uint32_t total,
+                           uint32_t *count, uint32_t *start) {
+    uint32_t seg_start = ~tile.seg_count_or_ix;
+    if ((int32_t)seg_start < 0) { *count = 0; *start = 0; return; }
+    uint32_t seg_end = total;
+    for (int nx = local_idx + 1; nx < tile_count; nx++) {
+        uint32_t ns = ~path_tiles[nx].seg_count_or_ix;
+        if ((int32_t)ns >= 0) { seg_end = ns; break; }
+    }
+    if (seg_end <= seg_start) { *count = 0; *start = seg_start; return; }
+    *count = seg_end - seg_start; *start = seg_start;
+}
+
+ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_line_soup *lines_in, int w, int h) {
+    ot_coarse *out = (ot_coarse *)calloc(1, sizeof(ot_coarse));
+    /* --- EncodeSceneDef (scene_encode.go:240-308) --- */
+    u32vec raw_tags = {0}, path_data = {0}, draw_tags = {0}, draw_data = {0}, transforms = {0}, styles = {0};
+    uint32_t n_paths = 0, n_draw = 0, n_clips = 0;
+    for (uint32_t e = 0; e < n_elems; e++) {
+        const ot_element *el = &elems[e];
+        switch (el->type) {
+        case OT_ELEM_DRAW:
+            encode_path(&raw_tags, &path_data, &transforms, &styles, lines_in + el->line_start, el->line_count, (int)el->even_odd);
+            u32_push(&draw_tags, DRAWTAG_COLOR);
+            u32_push(&draw_data, pack_color(el->color));
+            n_paths++; n_draw++;
+            break;
+        case OT_ELEM_BEGIN_CLIP:
+            encode_path(&raw_tags, &path_data, &transforms, &styles, lines_in + el->line_start, el->line_count, 0);
+            u32_push(&draw_tags, DRAWTAG_BEGIN_CLIP);
+            u32_push(&draw_data, el->blend); u32_push(&draw_data, f32_bits(el->alpha));
+            n_paths++; n_draw++; n_clips++;
+            break;
+        case OT_ELEM_END_CLIP:
+            u32_push(&raw_tags, PTAG_PATH);
+            u32_push(&draw_tags, DRAWTAG_END_CLIP);
+            n_paths++; n_draw++; n_clips++;
+            break;
+        }
+    }
+    /* packPathTags (scene_encode.go:189-198) + PackScene (:280-356) */
+    uint32_t n_tag_words = (raw_tags.n + 3) / 4;
+    uint32_t padded = ((n_tag_words + 255) / 256) * 256;
+    if (padded == 0) padded = 256;
+    ot_layout L; memset(&L, 0, sizeof L);
+    L.n_draw_objects = n_draw; L.n_paths = n_paths; L.n_clips = n_clips;
+    uint32_t off = 0;
+    L.path_tag_base = off; off += padded;
+    L.path_data_base = off; off += path_data.n;
+    L.draw_tag_base = off; off += draw_tags.n;
+    L.draw_data_base = off; off += draw_data.n;
+    L.transform_base = off; off += transforms.n;
+    L.style_base = off; off += styles.n;
+    uint32_t *scene = (uint32_t *)calloc(off ? off : 1, sizeof(uint32_t));
+    for (uint32_t i = 0; i < raw_tags.n; i++) scene[L.path_tag_base + i / 4] |= (raw_tags.d[i] & 0xff) << ((i % 4) * 8);
+    if (path_data.n) memcpy(scene + L.path_data_base, path_data.d, 4 * (size_t)path_data.n);
+    if (draw_tags.n) memcpy(scene + L.draw_tag_base, draw_tags.d, 4 * (size_t)draw_tags.n);
+    if (draw_data.n) memcpy(scene + L.draw_data_base, draw_data.d, 4 * (size_t)draw_data.n);
+    if (transforms.n) memcpy(scene + L.transform_base, transforms.d, 4 * (size_t)transforms.n);
+    if (styles.n) memcpy(scene + L.style_base, styles.d, 4 * (size_t)styles.n);
+    out->scene = scene; out->n_scene_words = off; out->layout = L;
+    free(raw_tags.d); free(path_data.d); free(draw_tags.d); free(draw_data.d); free(transforms.d); free(styles.d);
+
+    /* --- pathtagReduce + pathtagScan (pathtag.go:76-121): exclusive scan per tag word --- */
+    out->n_tag_words = padded;
+    out->tag_monoids = (ot_path_monoid *)calloc(padded, sizeof(ot_path_monoid));
+    {
+        ot_path_monoid m; memset(&m, 0, sizeof m);
+        for (uint32_t i = 0; i < padded; i++) {
+            out->tag_monoids[i] = m;
+            ot_path_monoid t; ot_path_monoid_new(scene[L.path_tag_base + i], &t);
+            pm_combine(&m, &t);
+        }
+    }
+    /* --- drawReduce + drawLeafScan (draw_leaf.go:54-151) --- */
+    ot_draw_monoid *dm = (ot_draw_monoid *)calloc(n_draw ? n_draw : 1, sizeof(ot_draw_monoid));
+    ot_draw_monoid pre; memset(&pre, 0, sizeof pre);
+    for (uint32_t i = 0; i < n_draw; i++) {
+        dm[i] = pre;
+        ot_draw_monoid t; ot_draw_monoid_new(scene[L.draw_tag_base + i], &t);
+        dm_combine(&pre, &t);
+    }
+    uint32_t n_info = pre.info_offset;
+    uint32_t *info = (uint32_t *)calloc(n_info ? n_info : 1, sizeof(uint32_t));
+    typedef struct { uint32_t ix; int32_t path_ix; } clip_inp;
+    clip_inp *clip_inps = (clip_inp *)calloc(n_clips ? n_clips : 1, sizeof(clip_inp));
+    for (uint32_t i = 0; i < n_draw; i++) {
+        uint32_t tag = scene[L.draw_tag_base + i];
+        if (tag == DRAWTAG_COLOR) {
+            uint32_t so = L.draw_data_base + dm[i].scene_offset;
+            if (so < off && dm[i].info_offset < n_info) info[dm[i].info_offset] = scene[so];
+        } else if (tag == DRAWTAG_BEGIN_CLIP) {
+            if (dm[i].clip_ix < n_clips) { clip_inps[dm[i].clip_ix].ix = i; clip_inps[dm[i].clip_ix].path_ix = (int32_t)dm[i].path_ix; }
+        } else if (tag == DRAWTAG_END_CLIP) {
+            if (dm[i].clip_ix < n_clips) { clip_inps[dm[i].clip_ix].ix = i; clip_inps[dm[i].clip_ix].path_ix = ~(int32_t)i; }
+        }
+    }
+    /* --- clipLeafScan (clip_leaf.go:27-56) --- */
+    if (n_clips > 0) {
+        int *stack = (int *)malloc(sizeof(int) * n_clips); int sp = 0;
+        for (uint32_t i = 0; i < n_clips; i++) {
+            if (clip_inps[i].path_ix >= 0) { stack[sp++] = (int)i; }
+            else {
+                if (sp == 0) continue;
+                int parent = stack[--sp];
+                uint32_t end_idx = (uint32_t)(~clip_inps[i].path_ix);
+                if (end_idx < n_draw && clip_inps[parent].ix < n_draw) {
+                    dm[end_idx].path_ix = (uint32_t)clip_inps[parent].path_ix;
+                    dm[end_idx].scene_offset = dm[clip_inps[parent].ix].scene_offset;
+                }
+            }
+        }
+        free(stack);
+    }
+    free(clip_inps);
+    out->draw_monoids = dm; out->info = info; out->n_info = n_info;
+
+    /* --- allLines with PathIx (rasterizer.go:363-384) --- */
+    uint32_t n_lines = 0;
+    for (uint32_t e = 0; e < n_elems; e++) if (elems[e].type != OT_ELEM_END_CLIP) n_lines += elems[e].line_count;
+    ot_line_soup *all = (ot_line_soup *)malloc(sizeof(ot_line_soup) * (n_lines ? n_lines : 1));
+    uint32_t *path_line_start = (uint32_t *)calloc(n_paths + 1, sizeof(uint32_t));
+    {
+        uint32_t k = 0, pix = 0;
+        for (uint32_t e = 0; e < n_elems; e++) {
+            path_line_start[pix] = k;
+            if (elems[e].type != OT_ELEM_END_CLIP)
+                for (uint32_t i = 0; i < elems[e].line_count; i++) { all[k] = lines_in[elems[e].line_start + i]; all[k].path_ix = pix; k++; }
+            pix++;
+        }
+        path_line_start[n_paths] = k;
+    }
+
+    /* --- CoarseRasterize (coarse.go:59-154) --- */
+    int wt = (w + TILE_W - 1) / TILE_W, ht = (h + TILE_H - 1) / TILE_H;
+    out->width_in_tiles = wt; out->height_in_tiles = ht;
+    int n_grid = wt * ht;
+    ptcl *ptcls = (ptcl *)calloc((size_t)(n_grid ? n_grid : 1), sizeof(ptcl));
+    for (int i = 0; i < n_grid; i++) ptcl_push(&ptcls[i], 0);   /* word 0 = blend_offset (ptcl.go:72-78) */
+    out->n_paths = n_paths;
+    out->paths = (ot_path *)calloc(n_paths ? n_paths : 1, sizeof(ot_path));
+    out->path_seg_base = (uint32_t *)calloc(n_paths ? n_paths : 1, sizeof(uint32_t));
+    out->path_total_segs = (uint32_t *)calloc(n_paths ? n_paths : 1, sizeof(uint32_t));
+    ot_tile *tiles = NULL; uint32_t n_tiles = 0, cap_tiles = 0;
+    ot_path_segment *segs = NULL; uint32_t n_segs = 0, cap_segs = 0;
+
+    if (n_draw != 0 && n_paths != 0 && n_lines != 0) {
+        uint32_t cur_tile_off = 0, global_seg_off = 0;
+        for (uint32_t pix = 0; pix < n_paths; pix++) {
+            const ot_line_soup *pl = all + path_line_start[pix];
+            uint32_t npl = path_line_start[pix + 1] - path_line_start[pix];
+            out->path_seg_base[pix] = global_seg_off;
+            if (npl == 0) { out->paths[pix].tiles = cur_tile_off; continue; }
+            ot_path path; path.tiles = cur_tile_off;
+            ot_line_bbox(pl, npl, w, h, path.bbox);
+            int bw = (int)(path.bbox[2] - path.bbox[0]), bh = (int)(path.bbox[3] - path.bbox[1]);
+            uint32_t tile_count = (uint32_t)(bw * bh);
+            out->paths[pix] = path;
+            if (tile_count == 0) continue;
+            if (n_tiles + tile_count > cap_tiles) { cap_tiles = (n_tiles + tile_count) * 2; tiles = (ot_tile *)realloc(tiles, sizeof(ot_tile) * cap_tiles); }
+            ot_tile *pt = tiles + n_tiles;
+            memset(pt, 0, sizeof(ot_tile) * tile_count);
+            n_tiles += tile_count; cur_tile_off += tile_count;
+            /* runPathStages (coarse.go:229-302) */
+            ot_line_soup *ll = (ot_line_soup *)malloc(sizeof(ot_line_soup) * npl);
+            uint32_t max_sc = 0;
+            for (uint32_t i = 0; i < npl; i++) { ll[i] = pl[i]; ll[i].path_ix = 0; dda d; dda_setup(&ll[i], &d); max_sc += d.count; }
+            ot_segment_count *sc = (ot_segment_count *)calloc(max_sc ? max_sc : 1, sizeof(ot_segment_count));
+            ot_path local = path; local.tiles = 0;
+            uint32_t n_sc = ot_path_count(ll, npl, &local, pt, sc);
+            uint32_t next = 0;
+            for (uint32_t i = 0; i < tile_count; i++) { uint32_t n = pt[i].seg_count_or_ix; if (n != 0) { pt[i].seg_count_or_ix = ~next; next += n; } }
+            if (n_segs + next > cap_segs) { cap_segs = (n_segs + next) * 2 + 16; segs = (ot_path_segment *)realloc(segs, sizeof(ot_path_segment) * cap_segs); }
+            memset(segs + n_segs, 0, sizeof(ot_path_segment) * next);
+            ot_path_tiling(sc, n_sc, ll, &local, pt, segs + n_segs);
+            for (int y = 0; y < bh; y++) { int32_t sum = 0; for (int x = 0; x < bw; x++) { sum += pt[y * bw + x].backdrop; pt[y * bw + x].backdrop = sum; } }
+            out->path_total_segs[pix] = next;
+            n_segs += next; global_seg_off += next;
+            free(ll); free(sc);
+        }
+
+        /* generatePTCLs (coarse.go:322-376) */
+        tile_clip_state *cs_all = (tile_clip_state *)calloc((size_t)n_grid, sizeof(tile_clip_state));
+        /* extractPathFillRules (coarse.go:683-705): style i for path i (reference quirk kept) */
+        uint32_t style_count = L.transform_base - L.style_base;   /* uint32 wrap, as in the reference */
+        for (uint32_t draw_ix = 0; draw_ix < n_draw; draw_ix++) {
+            uint32_t tag = scene[L.draw_tag_base + draw_ix];
+            ot_draw_monoid m = dm[draw_ix];
+            uint32_t pix = m.path_ix;
+            if (pix >= n_paths) continue;
+            ot_path path = out->paths[pix];
+            int bw = (int)(path.bbox[2] - path.bbox[0]), bh = (int)(path.bbox[3] - path.bbox[1]);
+            if (tag == DRAWTAG_COLOR) {
+                uint32_t rgba = m.info_offset < n_info ? info[m.info_offset] : 0;
+                int even_odd = 0;
+                if (pix < style_count && L.style_base + pix < off) even_odd = (scene[L.style_base + pix] & 0x02) != 0;
+                uint32_t gsb = out->path_seg_base[pix], total = out->path_total_segs[pix];
+                if (bw == 0 || bh == 0) continue;
+                for (int ty = 0; ty < bh; ty++) for (int tx = 0; tx < bw; tx++) {   /* emitDrawToTilesClipAware :380-432 */
+                    int gtx = (int)path.bbox[0] + tx, gty = (int)path.bbox[1] + ty;
+                    if (gtx < 0 || gtx >= wt || gty < 0 || gty >= ht) continue;
+                    int g = gty * wt + gtx;
+                    if (cs_all[g].clip_zero_depth > 0) continue;
+                    int li = ty * bw + tx;
+                    uint32_t tix = path.tiles + (uint32_t)li;
+                    if (tix >= n_tiles) continue;
+                    ot_tile t = tiles[tix];
+                    uint32_t cnt, st;
+                    tile_seg_range(t, li, bw * bh, tiles + path.tiles, total, &cnt, &st);
+                    if (cnt > 0) {
+                        ptcl_push(&ptcls[g], CMD_FILL); ptcl_push(&ptcls[g], (cnt << 1) | (uint32_t)even_odd);
+                        ptcl_push(&ptcls[g], gsb + st); ptcl_push(&ptcls[g], (uint32_t)t.backdrop);
+                        ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
+                    } else if (t.backdrop != 0) {
+                        ptcl_push(&ptcls[g], CMD_SOLID);
+                        ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
+                    }
+                }
+            } else if (tag == DRAWTAG_BEGIN_CLIP) {   /* emitBeginClipToTiles :442-507 */
+                for (int ty = 0; ty < bh; ty++) for (int tx = 0; tx < bw; tx++) {
+                    int gtx = (int)path.bbox[0] + tx, gty = (int)path.bbox[1] + ty;
+                    if (gtx < 0 || gtx >= wt || gty < 0 || gty >= ht) continue;
+                    int g = gty * wt + gtx;
+                    tile_clip_state *cs = &cs_all[g];
+                    if (cs->clip_zero_depth > 0) { cs->clip_depth++; continue; }
+                    uint32_t tix = path.tiles + (uint32_t)(ty * bw + tx);
+                    int has_seg = 0, has_bd = 0;
+                    if (tix < n_tiles) { has_seg = tiles[tix].seg_count_or_ix != 0; has_bd = tiles[tix].backdrop != 0; }
+                    if (!has_seg && !has_bd) {
+                        cs->clip_zero_depth = cs->clip_depth + 1;
+                    } else {
+                        ptcl_push(&ptcls[g], CMD_BEGIN_CLIP);
+                        cs->blend_depth++;
+                        if (cs->blend_depth > cs->max_blend_depth) cs->max_blend_depth = cs->blend_depth;
+                    }
+                    cs->clip_depth++;
+                }
+                for (int ty = 0; ty < ht; ty++) for (int tx = 0; tx < wt; tx++) {
+                    if ((uint32_t)tx >= path.bbox[0] && (uint32_t)tx < path.bbox[2] && (uint32_t)ty >= path.bbox[1] && (uint32_t)ty < path.bbox[3]) continue;
+                    tile_clip_state *cs = &cs_all[ty * wt + tx];
+                    if (cs->clip_zero_depth == 0) cs->clip_zero_depth = cs->clip_depth + 1;
+                    cs->clip_depth++;
+                }
+            } else if (tag == DRAWTAG_END_CLIP) {   /* :360-372 + emitEndClipToTiles :517-563 + endClipForTile :566-625 */
+                uint32_t blend = 0; float alpha = 0;
+                uint32_t so = L.draw_data_base + m.scene_offset;
+                if (so + 1 < off) { blend = scene[so]; alpha = bits_f32(scene[so + 1]); }
+                for (int ty = 0; ty < bh; ty++) for (int tx = 0; tx < bw; tx++) {
+                    int gtx = (int)path.bbox[0] + tx, gty = (int)path.bbox[1] + ty;
+                    if (gtx < 0 || gtx >= wt || gty < 0 || gty >= ht) continue;
+                    int g = gty * wt + gtx;
+                    tile_clip_state *cs = &cs_all[g];
+                    cs->clip_depth--;
+                    if (cs->clip_zero_depth == cs->clip_depth + 1) { cs->clip_zero_depth = 0; continue; }
+                    if (cs->clip_zero_depth > 0) continue;
+                    int li = ty * bw + tx;
+                    uint32_t tix = path.tiles + (uint32_t)li;
+                    if (tix < n_tiles) {
+                        ot_tile t = tiles[tix];
+                        uint32_t cnt, st;
+                        tile_seg_range(t, li, bw * bh, tiles + path.tiles, out->path_total_segs[pix], &cnt, &st);
+                        if (cnt > 0) {
+                            ptcl_push(&ptcls[g], CMD_FILL); ptcl_push(&ptcls[g], (cnt << 1));
+                            ptcl_push(&ptcls[g], out->path_seg_base[pix] + st); ptcl_push(&ptcls[g], (uint32_t)t.backdrop);
+                        } else {
+                            ptcl_push(&ptcls[g], CMD_SOLID);
+                        }
+                        ptcl_push(&ptcls[g], CMD_END_CLIP); ptcl_push(&ptcls[g], blend); ptcl_push(&ptcls[g], f32_bits(alpha));
+                    }
+                    cs->blend_depth--;
+                }
+                for (int ty = 0; ty < ht; ty++) for (int tx = 0; tx < wt; tx++) {
+                    if ((uint32_t)tx >= path.bbox[0] && (uint32_t)tx < path.bbox[2] && (uint32_t)ty >= path.bbox[1] && (uint32_t)ty < path.bbox[3]) continue;
+                    tile_clip_state *cs = &cs_all[ty * wt + tx];
+                    cs->clip_depth--;
+                    if (cs->clip_zero_depth == cs->clip_depth + 1) cs->clip_zero_depth = 0;
+                }
+            }
+        }
+        free(cs_all);
+    }
+    /* WriteEnd on every tile (coarse.go:148-151) and flatten to one array */
+    out->ptcl_offsets = (uint32_t *)calloc((size_t)n_grid + 1, sizeof(uint32_t));
+    uint32_t total_words = 0;
+    for (int i = 0; i < n_grid; i++) { ptcl_push(&ptcls[i], CMD_END); out->ptcl_offsets[i] = total_words; total_words += ptcls[i].n; }
+    out->ptcl_offsets[n_grid] = total_words;
+    out->ptcl_words = (uint32_t *)malloc(sizeof(uint32_t) * (total_words ? total_words : 1));
+    for (int i = 0; i < n_grid; i++) { memcpy(out->ptcl_words + out->ptcl_offsets[i], ptcls[i].cmds, 4 * (size_t)ptcls[i].n); free(ptcls[i].cmds); }
+    free(ptcls);
+    out->tiles = tiles; out->n_tiles = n_tiles; out->segments = segs; out->n_segments = n_segs;
+    free(all); free(path_line_start);
+    return out;
+}
+
+void ot_coarse_free(ot_coarse *c) {
+    if (!c) return;
+    free(c->paths); free(c->tiles); free(c->segments); free(c->path_seg_base); free(c->path_total_segs);
+    free(c->ptcl_offsets); free(c->ptcl_words); free(c->scene); free(c->tag_monoids); free(c->draw_monoids); free(c->info);
+    free(c);
+}
+
+/* ------------------------------------------------------------------ fine.go:40-187 */
+void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment *segs, uint32_t n_segs,
+                  const float bg[4], float *rgba_out) {
+    enum { PC = TILE_W * TILE_H, SPLIT = 4 };
+    float (*rgba)[4] = (float (*)[4])rgba_out;
+    for (int i = 0; i < PC; i++) memcpy(rgba[i], bg, 16);
+    if (!cmds) return;
+    float area[PC];
+    for (int i = 0; i < PC; i++) area[i] = 0;
+    /* blend stack: first 4 levels "registers", deeper levels spill (fine.go:58-62) */
+    float (*stack)[PC][4] = NULL; uint32_t stack_cap = 0;
+    uint32_t clip_depth = 0;
+    uint32_t off = 1;   /* CmdStartOffset, ptcl.go:98 */
+    for (;;) {
+        uint32_t tag = off < n_words ? cmds[off] : CMD_END;
+        if (off < n_words) off++;
+        switch (tag) {
+        case CMD_END: goto done;
+        case CMD_FILL: {
+            uint32_t packed = cmds[off], seg_index = cmds[off + 1]; int32_t backdrop = (int32_t)cmds[off + 2];
+            off += 3;
+            uint32_t seg_end = seg_index + (packed >> 1);
+            if (seg_end > n_segs) seg_end = n_segs;
+            uint32_t cnt = seg_end > seg_index ? seg_end - seg_index : 0;
+            fill_path(area, segs + seg_index, cnt, backdrop, (int)(packed & 1));
+        } break;
+        case CMD_SOLID:
+            for (int i = 0; i < PC; i++) area[i] = 1.0f;
+            break;
+        case CMD_COLOR: {
+            uint32_t c = cmds[off++];
+            float r = (float)(c & 0xff) / 255.0f, g = (float)((c >> 8) & 0xff) / 255.0f;
+            float b = (float)((c >> 16) & 0xff) / 255.0f, a = (float)((c >> 24) & 0xff) / 255.0f;
+            for (int i = 0; i < PC; i++) {
+                float cov = area[i];
+                float fr = r * cov, fg = g * cov, fb = b * cov, fa = a * cov;
+                float inv = 1.0f - fa;
+                rgba[i][0] = rgba[i][0] * inv + fr; rgba[i][1] = rgba[i][1] * inv + fg;
+                rgba[i][2] = rgba[i][2] * inv + fb; rgba[i][3] = rgba[i][3] * inv + fa;
+            }
+        } break;
+        case CMD_BEGIN_CLIP:
+            if (clip_depth >= stack_cap) { stack_cap = stack_cap ? stack_cap * 2 : 8; stack = realloc(stack, sizeof(*stack) * stack_cap); }
+            memcpy(stack[clip_depth], rgba, sizeof(*stack));
+            clip_depth++;
+            for (int i = 0; i < PC; i++) rgba[i][0] = rgba[i][1] = rgba[i][2] = rgba[i][3] = 0;
+            break;
+        case CMD_END_CLIP: {
+            float alpha = bits_f32(cmds[off + 1]);   /* cmds[off] = blend: ignored by the reference (fine.go:164) */
+            off += 2;
+            if (clip_depth == 0) continue;
+            clip_depth--;
+            float (*saved)[4] = stack[clip_depth];
+            for (int i = 0; i < PC; i++) {
+                float scale = area[i] * alpha;
+                float fr = rgba[i][0] * scale, fg = rgba[i][1] * scale, fb = rgba[i][2] * scale, fa = rgba[i][3] * scale;
+                float inv = 1.0f - fa;
+                rgba[i][0] = saved[i][0] * inv + fr; rgba[i][1] = saved[i][1] * inv + fg;
+                rgba[i][2] = saved[i][2] * inv + fb; rgba[i][3] = saved[i][3] * inv + fa;
+            }
+        } break;
+        default: goto done;
+        }
+    }
+done:
+    free(stack);
+    (void)SPLIT;
+}
+
+/* fine.go:190-217 */
+static void premul_to_straight_u8(const float pm[4], uint8_t out[4]) {
+    float a = pm[3];
+    if (a <= 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+    if (a > 1.0f) a = 1.0f;
+    float r = pm[0] / a; if (r > 1.0f) r = 1.0f;
+    float g = pm[1] / a; if (g > 1.0f) g = 1.0f;
+    float b = pm[2] / a; if (b > 1.0f) b = 1.0f;
+    out[0] = (uint8_t)(r * 255.0f + 0.5f); out[1] = (uint8_t)(g * 255.0f + 0.5f);
+    out[2] = (uint8_t)(b * 255.0f + 0.5f); out[3] = (uint8_t)(a * 255.0f + 0.5f);
+}
+
+void ot_fine_frame(const ot_coarse *c, const uint8_t bg[4], int w, int h, uint8_t *out_straight, uint8_t *out_premul) {
+    float bg_a = (float)bg[3] / 255.0f;   /* rasterizer.go:236-243 */
+    float bgf[4] = {(float)bg[0] / 255.0f * bg_a, (float)bg[1] / 255.0f * bg_a, (float)bg[2] / 255.0f * bg_a, bg_a};
+    float px[TILE_W * TILE_H * 4];
+    for (int ty = 0; ty < c->height_in_tiles; ty++) for (int tx = 0; tx < c->width_in_tiles; tx++) {
+        int t = ty * c->width_in_tiles + tx;
+        ot_fine_tile(c->ptcl_words + c->ptcl_offsets[t], c->ptcl_offsets[t + 1] - c->ptcl_offsets[t],
+                     c->segments, c->n_segments, bgf, px);
+        for (int ly = 0; ly < TILE_H; ly++) {
+            int py = ty * TILE_H + ly; if (py >= h) break;
+            for (int lx = 0; lx < TILE_W; lx++) {
+                int pxx = tx * TILE_W + lx; if (pxx >= w) break;
+                const float *p = px + 4 * (ly * TILE_W + lx);
+                size_t o = 4 * ((size_t)py * w + pxx);
+                if (out_straight) premul_to_straight_u8(p, out_straight + o);
+                if (out_premul) {   /* fine.wgsl:305-323 */
+                    for (int k = 0; k < 4; k++) { float v = clamp32(p[k], 0.0f, 1.0f); out_premul[o + k] = (uint8_t)f2u(v * 255.0f + 0.5f); }
+                }
+            }
+        }
+    }
+}
