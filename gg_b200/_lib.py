@@ -1,0 +1,193 @@
+"""ctypes binding of libggcuda.so (include/ggcuda.h). No CPU fallback: if the library is
+missing or no B200 is present, every entry point raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libggcuda.so")
+
+OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
+COMPOSITE_OVER, KEEP_SCENE = 1, 2
+(BUF_SCENE, BUF_TAG_MONOIDS, BUF_DRAW_MONOIDS, BUF_INFO, BUF_CLIP_INPS, BUF_LINES, BUF_PATHS, BUF_TILES,
+ BUF_SEG_START, BUF_SEGMENTS, BUF_PTCL_OFF, BUF_PTCL, BUF_HIT_CNT, BUF_LAYOUT) = range(14)
+
+# every symbol include/ggcuda.h declares (tests check the .so exports exactly these)
+SYMBOLS = [
+    "ggcuda_create", "ggcuda_destroy", "ggcuda_last_error", "ggcuda_set_stream", "ggcuda_begin", "ggcuda_set_background",
+    "ggcuda_set_band", "ggcuda_fill_path", "ggcuda_stroke_path", "ggcuda_push_clip", "ggcuda_push_layer", "ggcuda_pop",
+    "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_get_stats", "ggcuda_set_timing",
+    "ggcuda_debug_read",
+]
+
+LINE = np.dtype([("path_ix", "<u4"), ("p0", "<f4", 2), ("p1", "<f4", 2)])
+PATH = np.dtype([("bbox", "<u4", 4), ("tiles", "<u4")])
+TILE = np.dtype([("backdrop", "<i4"), ("seg_count", "<u4")])
+SEGMENT = np.dtype([("p0", "<f4", 2), ("p1", "<f4", 2), ("y_edge", "<f4")])
+PATH_MONOID = np.dtype([(n, "<u4") for n in ("trans_ix", "path_seg_ix", "path_seg_offset", "style_ix", "path_ix")])
+DRAW_MONOID = np.dtype([(n, "<u4") for n in ("path_ix", "clip_ix", "scene_offset", "info_offset")])
+CLIP_INP = np.dtype([("ix", "<u4"), ("path_ix", "<i4")])
+LAYOUT = np.dtype([(n, "<u4") for n in ("n_tag_bytes", "n_tag_words", "n_draws", "n_paths", "n_clips", "path_tag_base",
+                                         "path_data_base", "draw_tag_base", "draw_data_base", "transform_base", "style_base",
+                                         "clip_aux_base", "n_scene_words")])
+
+
+class Stats(C.Structure):
+    _fields_ = [(n, C.c_uint32) for n in ("n_draws", "n_paths", "n_clips", "n_tag_bytes", "n_lines", "n_path_tiles",
+                                          "n_seg_counts", "n_segments", "n_hits", "n_ptcl_words", "n_spill", "passes",
+                                          "kernel_launches")] + \
+               [("scene_bytes", C.c_uint64), ("device_bytes", C.c_uint64)] + \
+               [(n, C.c_float) for n in ("ms_front", "ms_binning", "ms_coarse", "ms_fine")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class GGCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"ggcuda error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libggcuda.so and declare prototypes. Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -m gg_b200.build` (there is no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    vp, u32, sz = C.c_void_p, C.c_uint32, C.c_size_t
+    L.ggcuda_create.argtypes = [C.c_int, u32, C.POINTER(vp)]
+    L.ggcuda_destroy.argtypes = [vp]
+    L.ggcuda_destroy.restype = None
+    L.ggcuda_last_error.argtypes = [vp]
+    L.ggcuda_last_error.restype = C.c_char_p
+    L.ggcuda_set_stream.argtypes = [vp, vp]
+    L.ggcuda_begin.argtypes = [vp, u32, u32]
+    L.ggcuda_set_background.argtypes = [vp, vp]
+    L.ggcuda_set_band.argtypes = [vp, u32, u32]
+    L.ggcuda_fill_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_int]
+    L.ggcuda_stroke_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_double, C.c_int, C.c_int, C.c_double]
+    L.ggcuda_push_clip.argtypes = [vp, vp, u32, vp, u32]
+    L.ggcuda_push_layer.argtypes = [vp, u32, C.c_float]
+    L.ggcuda_pop.argtypes = [vp]
+    L.ggcuda_add_encoding.argtypes = [vp, vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
+    L.ggcuda_flush.argtypes = [vp, vp, sz, u32]
+    L.ggcuda_upload.argtypes = [vp]
+    L.ggcuda_render_device.argtypes = [vp, vp, sz, u32]
+    L.ggcuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    L.ggcuda_set_timing.argtypes = [vp, C.c_int]
+    L.ggcuda_debug_read.argtypes = [vp, C.c_int, vp, sz]
+    L.ggcuda_debug_read.restype = C.c_longlong
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+class Context:
+    """Thin object wrapper over a ggcuda_ctx."""
+
+    def __init__(self, device=0):
+        self.L = load()
+        h = C.c_void_p()
+        rc = self.L.ggcuda_create(device, 0, C.byref(h))
+        if rc != 0:
+            raise GGCudaError(rc, (self.L.ggcuda_last_error(None) or b"").decode())
+        self.h = h
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise GGCudaError(rc, (self.L.ggcuda_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.ggcuda_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.L.ggcuda_set_stream(self.h, C.c_void_p(stream_ptr)))
+
+    def begin(self, w, h):
+        self._ck(self.L.ggcuda_begin(self.h, w, h))
+
+    def set_background(self, rgba_premul):
+        a = np.asarray(rgba_premul, dtype=np.uint8)
+        self._ck(self.L.ggcuda_set_background(self.h, _p(a)))
+
+    def set_band(self, y0, y1):
+        self._ck(self.L.ggcuda_set_band(self.h, y0, y1))
+
+    def fill_path(self, verbs, coords, rgba_straight, fill_rule=0):
+        v = np.ascontiguousarray(verbs, dtype=np.uint8)
+        c = np.ascontiguousarray(coords, dtype=np.float64).ravel()
+        col = np.asarray(rgba_straight, dtype=np.uint8)
+        self._ck(self.L.ggcuda_fill_path(self.h, _p(v), v.size, _p(c), c.size, _p(col), int(fill_rule)))
+
+    def stroke_path(self, verbs, coords, rgba_straight, width, cap=0, join=0, miter_limit=4.0):
+        v = np.ascontiguousarray(verbs, dtype=np.uint8)
+        c = np.ascontiguousarray(coords, dtype=np.float64).ravel()
+        col = np.asarray(rgba_straight, dtype=np.uint8)
+        self._ck(self.L.ggcuda_stroke_path(self.h, _p(v), v.size, _p(c), c.size, _p(col), float(width), int(cap), int(join),
+                                           float(miter_limit)))
+
+    def push_clip(self, verbs, coords):
+        v = np.ascontiguousarray(verbs, dtype=np.uint8)
+        c = np.ascontiguousarray(coords, dtype=np.float64).ravel()
+        self._ck(self.L.ggcuda_push_clip(self.h, _p(v), v.size, _p(c), c.size))
+
+    def push_layer(self, blend_mode, alpha):
+        self._ck(self.L.ggcuda_push_layer(self.h, int(blend_mode), float(alpha)))
+
+    def pop(self):
+        self._ck(self.L.ggcuda_pop(self.h))
+
+    def add_encoding(self, tags, path_data, draw_data, transforms, brushes):
+        t = np.ascontiguousarray(tags, dtype=np.uint8)
+        pd = np.ascontiguousarray(path_data, dtype=np.float32)
+        dd = np.ascontiguousarray(draw_data, dtype=np.uint32)
+        tr = np.ascontiguousarray(transforms, dtype=np.float32).ravel()
+        br = np.ascontiguousarray(brushes, dtype=np.float64).ravel()
+        self._ck(self.L.ggcuda_add_encoding(self.h, _p(t), t.size, _p(pd), pd.size, _p(dd), dd.size, _p(tr), tr.size,
+                                            _p(br), br.size // 4))
+
+    def flush(self, dst, stride=None, flags=0):
+        """dst: (H, W, 4) uint8 premultiplied RGBA (GPURenderTarget.Data)."""
+        assert dst.dtype == np.uint8 and dst.flags.c_contiguous
+        stride = stride or dst.strides[0]
+        self._ck(self.L.ggcuda_flush(self.h, _p(dst), stride, flags))
+
+    def upload(self):
+        self._ck(self.L.ggcuda_upload(self.h))
+
+    def render_device(self, dptr, stride, flags=0):
+        self._ck(self.L.ggcuda_render_device(self.h, C.c_void_p(dptr), stride, flags))
+
+    def set_timing(self, on):
+        self._ck(self.L.ggcuda_set_timing(self.h, int(on)))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self.L.ggcuda_get_stats(self.h, C.byref(s)))
+        return s.as_dict()
+
+    def debug_read(self, which, dtype):
+        n = self.L.ggcuda_debug_read(self.h, which, None, 0)
+        if n < 0:
+            self._ck(int(n))
+        dt = np.dtype(dtype)
+        out = np.zeros(n // dt.itemsize, dtype=dt)
+        if n:
+            m = self.L.ggcuda_debug_read(self.h, which, _p(out), n)
+            if m < 0:
+                self._ck(int(m))
+        return out

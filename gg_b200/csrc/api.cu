@@ -1,0 +1,506 @@
+// gg_b200/csrc/api.cu -- C ABI of libggcuda.so (declared in include/ggcuda.h): context,
+// device buffers, scene upload, pipeline execution with grow-and-retry sizing, read-back.
+//
+// Replaces, behind gg.GPUAccelerator: VelloAccelerator.flushLocked/dispatchComputeScene
+// (internal/gpu/vello_accelerator.go:335-386, 512-630) and VelloComputeDispatcher
+// (internal/gpu/vello_compute.go:734-793 buffer sizing, :1112-1225 dispatch + WaitIdle).
+// Unlike the reference (18 buffers sized by worst-case formulas, zero-filled by upload,
+// every intermediate read back for diagnostics), buffers persist across frames, are sized
+// by what the previous pass measured (GGBump), and nothing but the bump block and the
+// finished band leaves the device.
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <string>
+
+#include "../../include/ggcuda.h"
+#include "host_scene.h"
+#include "pipeline.cuh"
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    HostScene scene;
+    HostScene::Layout layout{};
+    uint32_t width = 0, height = 0, band_y0 = 0, band_y1 = 0;
+    bool band_set = false;
+    uint8_t bg[4] = {0, 0, 0, 0};
+    bool uploaded = false;
+    // host staging
+    uint32_t* h_scene = nullptr; size_t h_scene_words = 0;
+    GGBump* h_bump = nullptr;
+    uint8_t* h_frame = nullptr; size_t h_frame_bytes = 0;
+    // device
+    DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, lines, path_bbox, paths, path_row_off,
+        tiles, seg_start, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl, spill_off, spill, bump,
+        scan_partials, frame_d;
+    uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0;
+    ggcuda_stats stats{};
+    bool timing = false;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    GGConfig cfg{};
+    GGBump last_bump{};
+};
+
+thread_local std::string g_create_err;
+
+int fail(Ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_err = msg;
+    return code;
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e_ = (call);                                                                       \
+        if (e_ != cudaSuccess) return fail(c, GGCUDA_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+int ensure(Ctx* c, DevBuf& b, size_t bytes) {
+    if (bytes <= b.bytes) return 0;
+    size_t want = bytes + bytes / 4 + 256;
+    if (b.p) { CK(cudaStreamSynchronize(c->stream)); CK(cudaFree(b.p)); b.p = nullptr; b.bytes = 0; }
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, GGCUDA_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    b.bytes = want;
+    return 0;
+}
+size_t total_device_bytes(Ctx* c) {
+    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off,
+                     &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
+                     &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl, &c->spill_off, &c->spill,
+                     &c->bump, &c->scan_partials, &c->frame_d};
+    size_t t = 0;
+    for (DevBuf* b : all) t += b->bytes;
+    return t;
+}
+void free_all(Ctx* c) {
+    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off,
+                     &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
+                     &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl, &c->spill_off, &c->spill,
+                     &c->bump, &c->scan_partials, &c->frame_d};
+    for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->bytes = 0; }
+}
+
+uint32_t band_tiles(const Ctx* c) {
+    uint32_t wt = (c->width + GG_TILE_W - 1) / GG_TILE_W;
+    return wt * (c->band_y1 - c->band_y0);
+}
+
+// Upload the accumulated scene (one pinned staging buffer, one H2D copy) and size the
+// scene-proportional buffers.
+int upload(Ctx* c) {
+    CK(cudaSetDevice(c->device));
+    if (c->width == 0 || c->height == 0) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_begin was not called");
+    c->scene.close_open_clips();
+    size_t words = c->scene.packed_words();
+    if (words > c->h_scene_words) {
+        if (c->h_scene) { CK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->h_scene); c->h_scene = nullptr; }
+        size_t want = words + words / 4 + 1024;
+        CK(cudaHostAlloc((void**)&c->h_scene, want * 4, cudaHostAllocDefault));
+        c->h_scene_words = want;
+    }
+    uint32_t ht = (c->height + GG_TILE_H - 1) / GG_TILE_H;
+    if (!c->band_set) { c->band_y0 = 0; c->band_y1 = ht; }
+    if (c->band_y1 > ht) c->band_y1 = ht;
+    if (c->band_y0 > c->band_y1) c->band_y0 = c->band_y1;
+    c->scene.pack(c->h_scene, &c->layout, band_tiles(c));
+    const HostScene::Layout& L = c->layout;
+    int r;
+    if ((r = ensure(c, c->scene_d, words * 4))) return r;
+    CK(cudaMemcpyAsync(c->scene_d.p, c->h_scene, words * 4, cudaMemcpyHostToDevice, c->stream));
+    c->stats.scene_bytes = words * 4;
+    size_t nd = std::max<size_t>(L.n_draws, 1), np = std::max<size_t>(L.n_paths, 1), bt = std::max<size_t>(band_tiles(c), 1);
+    if ((r = ensure(c, c->tag_monoids, sizeof(GGPathMonoid) * L.n_tag_words))) return r;
+    if ((r = ensure(c, c->draw_monoids, sizeof(GGDrawMonoid) * nd))) return r;
+    if ((r = ensure(c, c->info, 4 * nd))) return r;
+    if ((r = ensure(c, c->clip_inps, sizeof(GGClipInp) * std::max<size_t>(L.n_clips, 1)))) return r;
+    if ((r = ensure(c, c->draw_recs, sizeof(GGDrawRec) * nd))) return r;
+    if ((r = ensure(c, c->line_count, 4 * std::max<size_t>(L.n_tag_bytes, 1)))) return r;
+    if ((r = ensure(c, c->line_off, 4 * std::max<size_t>(L.n_tag_bytes, 1)))) return r;
+    if ((r = ensure(c, c->path_bbox, 16 * np))) return r;
+    if ((r = ensure(c, c->paths, sizeof(GGPath) * np))) return r;
+    if ((r = ensure(c, c->path_row_off, 4 * np))) return r;
+    if ((r = ensure(c, c->tile_hits, 8 * bt))) return r;
+    if ((r = ensure(c, c->hit_off, 4 * bt))) return r;
+    if ((r = ensure(c, c->hit_cnt, 4 * bt))) return r;
+    if ((r = ensure(c, c->hit_cursor, 4 * bt))) return r;
+    if ((r = ensure(c, c->ptcl_off, 4 * bt))) return r;
+    if ((r = ensure(c, c->spill_off, 4 * bt))) return r;
+    if ((r = ensure(c, c->bump, sizeof(GGBump)))) return r;
+    if ((r = ensure(c, c->scan_partials, 32 * GG_SCAN_BLOCKS))) return r;
+    // first guesses for the data-dependent buffers; the retry loop corrects them
+    c->lines_cap = std::max<uint32_t>(c->lines_cap, 16u * c->scene.n_seg_tags + 1024u);
+    c->tiles_cap = std::max<uint32_t>(c->tiles_cap, 64u * L.n_paths + 4096u);
+    c->rows_cap = 0xffffffffu;
+    c->seg_counts_cap = std::max<uint32_t>(c->seg_counts_cap, 2u * c->lines_cap);
+    c->segments_cap = std::max<uint32_t>(c->segments_cap, 2u * c->lines_cap);
+    c->hits_cap = std::max<uint32_t>(c->hits_cap, c->tiles_cap);
+    c->ptcl_cap = std::max<uint32_t>(c->ptcl_cap, 6u * c->hits_cap + 2u * (uint32_t)bt);
+    c->uploaded = true;
+    return 0;
+}
+
+int size_dynamic(Ctx* c) {
+    int r;
+    if ((r = ensure(c, c->lines, sizeof(GGLine) * (size_t)c->lines_cap))) return r;
+    if ((r = ensure(c, c->tiles, sizeof(GGTile) * (size_t)c->tiles_cap))) return r;
+    if ((r = ensure(c, c->seg_start, 4 * (size_t)c->tiles_cap))) return r;
+    if ((r = ensure(c, c->seg_counts, sizeof(GGSegCount) * (size_t)c->seg_counts_cap))) return r;
+    if ((r = ensure(c, c->segments, sizeof(GGSegment) * (size_t)c->segments_cap))) return r;
+    if ((r = ensure(c, c->hits, 4 * (size_t)c->hits_cap))) return r;
+    if ((r = ensure(c, c->ptcl, 4 * (size_t)c->ptcl_cap))) return r;
+    if ((r = ensure(c, c->spill, sizeof(float4) * 256 * (size_t)std::max<uint32_t>(c->spill_cap, 1)))) return r;
+    return 0;
+}
+
+void fill_config(Ctx* c, uint32_t flags) {
+    GGConfig& g = c->cfg;
+    const HostScene::Layout& L = c->layout;
+    g.width = c->width; g.height = c->height;
+    g.width_in_tiles = (c->width + GG_TILE_W - 1) / GG_TILE_W;
+    g.height_in_tiles = (c->height + GG_TILE_H - 1) / GG_TILE_H;
+    g.band_y0 = c->band_y0; g.band_y1 = c->band_y1;
+    g.n_tag_bytes = L.n_tag_bytes; g.n_tag_words = L.n_tag_words;
+    g.n_draws = L.n_draws; g.n_paths = L.n_paths; g.n_clips = L.n_clips;
+    g.path_tag_base = L.path_tag_base; g.path_data_base = L.path_data_base; g.draw_tag_base = L.draw_tag_base;
+    g.draw_data_base = L.draw_data_base; g.transform_base = L.transform_base; g.style_base = L.style_base;
+    g.clip_parent_base = L.clip_aux_base; g.n_scene_words = L.n_scene_words;
+    g.lines_cap = c->lines_cap; g.tiles_cap = c->tiles_cap; g.rows_cap = c->rows_cap; g.seg_counts_cap = c->seg_counts_cap;
+    g.segments_cap = c->segments_cap; g.hits_cap = c->hits_cap; g.ptcl_cap = c->ptcl_cap; g.spill_cap = c->spill_cap;
+    for (int i = 0; i < 4; i++) g.bg[i] = (float)c->bg[i] / 255.0f;
+    g.flags = (flags & GGCUDA_COMPOSITE_OVER) ? GG_FLAG_BG_FROM_DST : 0u;
+}
+
+GGBuffers buffers(Ctx* c) {
+    GGBuffers b;
+    b.scene = (uint32_t*)c->scene_d.p; b.tag_monoids = (GGPathMonoid*)c->tag_monoids.p; b.draw_monoids = (GGDrawMonoid*)c->draw_monoids.p;
+    b.info = (uint32_t*)c->info.p; b.clip_inps = (GGClipInp*)c->clip_inps.p; b.draw_recs = (GGDrawRec*)c->draw_recs.p;
+    b.line_count = (uint32_t*)c->line_count.p; b.line_off = (uint32_t*)c->line_off.p; b.lines = (GGLine*)c->lines.p;
+    b.path_bbox_ord = (uint32_t*)c->path_bbox.p; b.paths = (GGPath*)c->paths.p; b.path_row_off = (uint32_t*)c->path_row_off.p;
+    b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
+    b.segments = (GGSegment*)c->segments.p; b.tile_hits = (unsigned long long*)c->tile_hits.p; b.hit_off = (uint32_t*)c->hit_off.p;
+    b.hit_cnt = (uint32_t*)c->hit_cnt.p; b.hit_cursor = (uint32_t*)c->hit_cursor.p; b.hits = (uint32_t*)c->hits.p;
+    b.ptcl_off = (uint32_t*)c->ptcl_off.p; b.ptcl = (uint32_t*)c->ptcl.p; b.spill_off = (uint32_t*)c->spill_off.p;
+    b.spill = (float4*)c->spill.p; b.bump = (GGBump*)c->bump.p; b.scan_partials = c->scan_partials.p;
+    return b;
+}
+
+// Run the pipeline into dst_device (band-relative). Re-runs with larger buffers while a stage overflowed.
+int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
+    CK(cudaSetDevice(c->device));
+    if (!c->uploaded) { int r = upload(c); if (r) return r; }
+    c->stats.passes = 0; c->stats.kernel_launches = 0;
+    for (int attempt = 0; attempt < 12; attempt++) {
+        int r = size_dynamic(c);
+        if (r) return r;
+        fill_config(c, flags);
+        GGBuffers b = buffers(c);
+        if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+        gg_launch_front(c->cfg, b, c->stream);
+        if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+        gg_launch_binning(c->cfg, b, c->stream);
+        if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+        gg_launch_coarse(c->cfg, b, c->stream);
+        if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
+        CK(cudaMemcpyAsync(c->h_bump, c->bump.p, sizeof(GGBump), cudaMemcpyDeviceToHost, c->stream));
+        // fine is launched optimistically; if a stage overflowed its inputs are in-bounds garbage and the pass is redone
+        gg_launch_fine(c->cfg, b, dst_device, stride, c->stream);
+        if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
+        c->stats.passes++;
+        c->stats.kernel_launches += 16 + 7 + 5 + 1;
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaGetLastError());
+        GGBump bm = *c->h_bump;
+        c->last_bump = bm;
+        bool grow = false;
+        auto need = [&](uint32_t& cap, uint64_t required) { if (required > cap) { cap = (uint32_t)std::min<uint64_t>(required + required / 4 + 1024, 0xfffffff0u); grow = true; } };
+        need(c->lines_cap, bm.lines);
+        need(c->tiles_cap, bm.path_tiles);
+        need(c->seg_counts_cap, bm.seg_counts);
+        need(c->segments_cap, bm.segments);
+        need(c->hits_cap, bm.hits);
+        need(c->ptcl_cap, bm.ptcl_words);
+        need(c->spill_cap, bm.spill);
+        if (!grow && bm.failed == 0) {
+            ggcuda_stats& s = c->stats;
+            s.n_draws = c->layout.n_draws; s.n_paths = c->layout.n_paths; s.n_clips = c->layout.n_clips; s.n_tag_bytes = c->layout.n_tag_bytes;
+            s.n_lines = bm.lines; s.n_path_tiles = bm.path_tiles; s.n_seg_counts = bm.seg_counts; s.n_segments = bm.segments;
+            s.n_hits = bm.hits; s.n_ptcl_words = bm.ptcl_words; s.n_spill = bm.spill;
+            s.device_bytes = total_device_bytes(c);
+            if (c->timing) {
+                cudaEventElapsedTime(&s.ms_front, c->ev[0], c->ev[1]);
+                cudaEventElapsedTime(&s.ms_binning, c->ev[1], c->ev[2]);
+                cudaEventElapsedTime(&s.ms_coarse, c->ev[2], c->ev[3]);
+                cudaEventElapsedTime(&s.ms_fine, c->ev[3], c->ev[4]);
+            }
+            return 0;
+        }
+        if (!grow) return fail(c, GGCUDA_ERR_CUDA, "pipeline reported overflow without a growable buffer (failed mask " + std::to_string(bm.failed) + ")");
+    }
+    return fail(c, GGCUDA_ERR_NOMEM, "pipeline buffers did not converge");
+}
+
+}  // namespace
+
+extern "C" {
+
+int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
+    (void)flags;
+    Ctx* c = nullptr;
+    if (!out) return fail(nullptr, GGCUDA_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(nullptr, GGCUDA_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
+    if (device < 0 || device >= n) return fail(nullptr, GGCUDA_ERR_INVALID, "device index out of range");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, GGCUDA_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10) return fail(nullptr, GGCUDA_ERR_UNSUPPORTED, "libggcuda is built for sm_100a (B200) only; found compute " + std::to_string(prop.major) + "." + std::to_string(prop.minor));
+    c = new (std::nothrow) Ctx();
+    if (!c) return fail(nullptr, GGCUDA_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaHostAlloc((void**)&c->h_bump, sizeof(GGBump), cudaHostAllocDefault) != cudaSuccess) {
+        g_create_err = std::string("context set-up failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete c;
+        return GGCUDA_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+    for (auto& ev : c->ev) cudaEventCreate(&ev);
+    *out = reinterpret_cast<ggcuda_ctx*>(c);
+    return 0;
+}
+
+void ggcuda_destroy(ggcuda_ctx* h) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_all(c);
+    if (c->h_scene) cudaFreeHost(c->h_scene);
+    if (c->h_bump) cudaFreeHost(c->h_bump);
+    if (c->h_frame) cudaFreeHost(c->h_frame);
+    for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+const char* ggcuda_last_error(ggcuda_ctx* h) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    return c ? c->err.c_str() : g_create_err.c_str();
+}
+
+int ggcuda_set_stream(ggcuda_ctx* h, void* s) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    c->stream = s ? reinterpret_cast<cudaStream_t>(s) : c->own_stream;
+    return 0;
+}
+
+int ggcuda_begin(ggcuda_ctx* h, uint32_t width, uint32_t height) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    if (width == 0 || height == 0 || width > 65536 || height > 65536) return fail(c, GGCUDA_ERR_INVALID, "bad target size");
+    c->width = width; c->height = height;
+    c->scene.clear(width, height);
+    c->uploaded = false;
+    return 0;
+}
+
+int ggcuda_set_background(ggcuda_ctx* h, const uint8_t rgba[4]) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !rgba) return GGCUDA_ERR_INVALID;
+    memcpy(c->bg, rgba, 4);
+    return 0;
+}
+
+int ggcuda_set_band(ggcuda_ctx* h, uint32_t y0, uint32_t y1) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    if (y1 < y0) return fail(c, GGCUDA_ERR_INVALID, "band rows reversed");
+    c->band_y0 = y0; c->band_y1 = y1; c->band_set = true;
+    c->uploaded = false;
+    return 0;
+}
+
+static const float ID6[6] = {1, 0, 0, 0, 1, 0};
+
+int ggcuda_fill_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
+                     const uint8_t rgba[4], int fill_rule) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !rgba) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    if (n_verbs == 0) return 0;   // vello_accelerator.go:216-219: empty paths are dropped
+    c->scene.begin_path(ID6, fill_rule == GGCUDA_FILL_EVENODD);
+    c->scene.add_verbs(verbs, n_verbs, coords, n_coords);
+    c->scene.end_path();
+    c->scene.draw_color(gg_pack_color_straight(rgba));
+    c->uploaded = false;
+    return 0;
+}
+
+int ggcuda_stroke_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
+                       const uint8_t rgba[4], double width, int cap, int join, double miter_limit) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !rgba) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    if (n_verbs == 0) return 0;
+    std::vector<uint8_t> v(verbs, verbs + n_verbs);
+    std::vector<float> cf(n_coords);
+    for (uint32_t i = 0; i < n_coords; i++) cf[i] = (float)coords[i];
+    StrokeStyleHost st = {width, miter_limit, cap, join};
+    c->scene.begin_path(ID6, false);
+    gg_stroke_to_fill(v, cf, st, &c->scene);
+    c->scene.end_path();
+    c->scene.draw_color(gg_pack_color_straight(rgba));
+    c->uploaded = false;
+    return 0;
+}
+
+int ggcuda_push_clip(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    c->scene.begin_path(ID6, false);
+    if (n_verbs) c->scene.add_verbs(verbs, n_verbs, coords, n_coords);
+    c->scene.end_path();
+    c->scene.begin_clip(0x8003u, 1.0f, 0);
+    c->uploaded = false;
+    return 0;
+}
+
+int ggcuda_push_layer(ggcuda_ctx* h, uint32_t blend_mode, float alpha) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    HostScene& s = c->scene;
+    s.begin_path(ID6, false);
+    s.move_to(0, 0); s.line_to((float)c->width, 0); s.line_to((float)c->width, (float)c->height); s.line_to(0, (float)c->height); s.close();
+    s.end_path();
+    s.begin_clip(gg_blend_word(blend_mode), alpha, 1);
+    c->uploaded = false;
+    return 0;
+}
+
+int ggcuda_pop(ggcuda_ctx* h) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    if (c->scene.clip_stack.empty()) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_pop: nothing to pop");
+    c->scene.end_clip(c->scene.clip_kind.back());
+    c->uploaded = false;
+    return 0;
+}
+
+int ggcuda_add_encoding(ggcuda_ctx* h, const uint8_t* tags, size_t n_tags, const float* path_data, size_t n_path_data,
+                        const uint32_t* draw_data, size_t n_draw_data, const float* transforms, size_t n_transforms,
+                        const double* brushes, size_t n_brushes) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    if (c->width == 0) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_begin was not called");
+    std::string msg;
+    int r = c->scene.add_encoding(tags, n_tags, path_data, n_path_data, draw_data, n_draw_data, transforms, n_transforms / 6, brushes, n_brushes, &msg);
+    c->uploaded = false;
+    if (r) return fail(c, r, msg);
+    return 0;
+}
+
+int ggcuda_upload(ggcuda_ctx* h) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    return upload(c);
+}
+
+int ggcuda_render_device(ggcuda_ctx* h, void* dst_device, size_t stride, uint32_t flags) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !dst_device) return c ? fail(c, GGCUDA_ERR_INVALID, "dst_device is NULL") : GGCUDA_ERR_INVALID;
+    if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
+    int r = render(c, (uint8_t*)dst_device, stride, flags);
+    if (r == 0 && !(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+    return r;
+}
+
+int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !dst) return c ? fail(c, GGCUDA_ERR_INVALID, "dst is NULL") : GGCUDA_ERR_INVALID;
+    if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
+    CK(cudaSetDevice(c->device));
+    if (!c->uploaded) { int r = upload(c); if (r) return r; }
+    uint32_t row0 = c->band_y0 * GG_TILE_H, row1 = std::min(c->band_y1 * GG_TILE_H, c->height);
+    if (row1 <= row0) return 0;
+    size_t rows = row1 - row0, tight = (size_t)c->width * 4, bytes = rows * tight;
+    int r;
+    if ((r = ensure(c, c->frame_d, bytes))) return r;
+    if (bytes > c->h_frame_bytes) {
+        if (c->h_frame) { CK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->h_frame); c->h_frame = nullptr; }
+        CK(cudaHostAlloc((void**)&c->h_frame, bytes, cudaHostAllocDefault));
+        c->h_frame_bytes = bytes;
+    }
+    if (flags & GGCUDA_COMPOSITE_OVER) {   // bring the existing target pixels to the device as fine's starting colour
+        for (size_t y = 0; y < rows; y++) memcpy(c->h_frame + y * tight, dst + (row0 + y) * stride, tight);
+        CK(cudaMemcpyAsync(c->frame_d.p, c->h_frame, bytes, cudaMemcpyHostToDevice, c->stream));
+    }
+    r = render(c, (uint8_t*)c->frame_d.p, tight, flags);
+    if (r) return r;
+    CK(cudaMemcpyAsync(c->h_frame, c->frame_d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (stride == tight) memcpy(dst + (size_t)row0 * stride, c->h_frame, bytes);
+    else for (size_t y = 0; y < rows; y++) memcpy(dst + (row0 + y) * stride, c->h_frame + y * tight, tight);
+    if (!(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+    return 0;
+}
+
+int ggcuda_get_stats(ggcuda_ctx* h, ggcuda_stats* out) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !out) return GGCUDA_ERR_INVALID;
+    *out = c->stats;
+    return 0;
+}
+
+int ggcuda_set_timing(ggcuda_ctx* h, int enabled) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    c->timing = enabled != 0;
+    return 0;
+}
+
+long long ggcuda_debug_read(ggcuda_ctx* h, int which, void* dst, size_t cap) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    const GGBump& bm = c->last_bump;
+    const HostScene::Layout& L = c->layout;
+    uint32_t bt = band_tiles(c);
+    const void* src = nullptr; size_t bytes = 0;
+    switch (which) {
+    case GGCUDA_BUF_SCENE: src = c->scene_d.p; bytes = 4 * (size_t)L.n_scene_words; break;
+    case GGCUDA_BUF_TAG_MONOIDS: src = c->tag_monoids.p; bytes = sizeof(GGPathMonoid) * (size_t)L.n_tag_words; break;
+    case GGCUDA_BUF_DRAW_MONOIDS: src = c->draw_monoids.p; bytes = sizeof(GGDrawMonoid) * (size_t)L.n_draws; break;
+    case GGCUDA_BUF_INFO: src = c->info.p; bytes = 4 * (size_t)L.n_draws; break;
+    case GGCUDA_BUF_CLIP_INPS: src = c->clip_inps.p; bytes = sizeof(GGClipInp) * (size_t)L.n_clips; break;
+    case GGCUDA_BUF_LINES: src = c->lines.p; bytes = sizeof(GGLine) * (size_t)bm.lines; break;
+    case GGCUDA_BUF_PATHS: src = c->paths.p; bytes = sizeof(GGPath) * (size_t)L.n_paths; break;
+    case GGCUDA_BUF_TILES: src = c->tiles.p; bytes = sizeof(GGTile) * (size_t)bm.path_tiles; break;
+    case GGCUDA_BUF_SEG_START: src = c->seg_start.p; bytes = 4 * (size_t)bm.path_tiles; break;
+    case GGCUDA_BUF_SEGMENTS: src = c->segments.p; bytes = sizeof(GGSegment) * (size_t)bm.segments; break;
+    case GGCUDA_BUF_PTCL_OFF: src = c->ptcl_off.p; bytes = 4 * (size_t)bt; break;
+    case GGCUDA_BUF_PTCL: src = c->ptcl.p; bytes = 4 * (size_t)bm.ptcl_words; break;
+    case GGCUDA_BUF_HIT_CNT: src = c->hit_cnt.p; bytes = 4 * (size_t)bt; break;
+    case GGCUDA_BUF_LAYOUT: {
+        if (!dst || cap < sizeof(L)) return (long long)sizeof(L);
+        memcpy(dst, &L, sizeof(L));
+        return (long long)sizeof(L);
+    }
+    default: return fail(c, GGCUDA_ERR_INVALID, "unknown debug buffer");
+    }
+    if (!dst || cap < bytes) return (long long)bytes;
+    if (bytes == 0) return 0;
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail(c, GGCUDA_ERR_CUDA, std::string("debug read: ") + cudaGetErrorString(cudaGetLastError()));
+    return (long long)bytes;
+}
+
+}  // extern "C"

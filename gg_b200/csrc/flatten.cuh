@@ -1,0 +1,254 @@
+// gg_b200/csrc/flatten.cuh -- Euler-spiral cubic flattening on the device.
+//
+// Behavioural spec: gg internal/gpu/tilecompute/flatten.go:60-184 (flattenEulerFill),
+// euler.go:39-224 and the quad elevation of internal/gpu/path_convert.go:60-72.
+// One thread owns one curve; the subdivision loop is run twice (count, then emit) so that
+// LineSoup lands in tag order without atomics. float32 arithmetic in the reference's
+// operation order (TU compiled with -fmad=false); transcendental calls go through float64
+// and are rounded to float32 at the same places the Go code does (util.go:36-37,104-105).
+#pragma once
+#include "common.cuh"
+
+struct V2 { float x, y; };
+__device__ __forceinline__ V2 mk(float x, float y) { V2 v; v.x = x; v.y = y; return v; }
+__device__ __forceinline__ V2 vadd(V2 a, V2 b) { return mk(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ V2 vsub(V2 a, V2 b) { return mk(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ V2 vmul(V2 a, float s) { return mk(a.x * s, a.y * s); }
+__device__ __forceinline__ float vlen_sq(V2 a) { return a.x * a.x + a.y * a.y; }
+__device__ __forceinline__ bool veq(V2 a, V2 b) { return a.x == b.x && a.y == b.y; }
+
+// Go math.Hypot: p*sqrt(1+q*q) on ordered magnitudes (not the correctly rounded libm hypot).
+__device__ __forceinline__ double go_hypot(double p, double q) {
+    if (isinf(p) || isinf(q)) return CUDART_INF;
+    if (isnan(p) || isnan(q)) return CUDART_NAN;
+    p = fabs(p); q = fabs(q);
+    if (p < q) { double t = p; p = q; q = t; }
+    if (p == 0) return 0;
+    q = q / p;
+    return p * sqrt(1 + q * q);
+}
+__device__ __forceinline__ float sin32(float x) { return (float)sin((double)x); }
+__device__ __forceinline__ float cos32(float x) { return (float)cos((double)x); }
+__device__ __forceinline__ float sqrt32(float x) { return (float)sqrt((double)x); }
+__device__ __forceinline__ float pow5(float b) { float r = 1.0f; r *= b; r *= b; r *= b; r *= b; r *= b; return r; }
+
+struct CubicParams { float th0, th1, chord_len, err; };
+struct EulerParams { float th0, k0, k1, ch; };
+
+__device__ inline CubicParams cubic_params_from_points_derivs(V2 p0, V2 p1, V2 q0, V2 q1, float dt) {   // euler.go:39-90
+    const float TANGENT_THRESH = 1e-6f;
+    V2 chord = vsub(p1, p0);
+    float chord_sq = vlen_sq(chord);
+    float chord_len = sqrt32(chord_sq);
+    CubicParams cp;
+    if (chord_sq < TANGENT_THRESH * TANGENT_THRESH) {
+        float chord_err = sqrt32((float)(9.0 / 32.0) * (vlen_sq(q0) + vlen_sq(q1))) * dt;
+        cp.th0 = 0; cp.th1 = 0; cp.chord_len = TANGENT_THRESH; cp.err = chord_err;
+        return cp;
+    }
+    float scale = dt / chord_sq;
+    V2 h0 = mk(q0.x * chord.x + q0.y * chord.y, q0.y * chord.x - q0.x * chord.y);
+    float th0 = (float)atan2((double)h0.y, (double)h0.x);
+    float d0 = (float)go_hypot((double)h0.x, (double)h0.y) * scale;
+    V2 h1 = mk(q1.x * chord.x + q1.y * chord.y, q1.x * chord.y - q1.y * chord.x);
+    float th1 = (float)atan2((double)h1.y, (double)h1.x);
+    float d1 = (float)go_hypot((double)h1.x, (double)h1.y) * scale;
+    float cth0 = cos32(th0), cth1 = cos32(th1);
+    float err;
+    if (cth0 * cth1 < 0) {
+        err = 2.0f;
+    } else {
+        const float two_thirds = (float)(2.0 / 3.0);
+        float e0 = two_thirds / f_max(1.0f + cth0, 1e-9f);
+        float e1 = two_thirds / f_max(1.0f + cth1, 1e-9f);
+        float s0 = sin32(th0), s1 = sin32(th1);
+        float s01 = cth0 * s1 + cth1 * s0;
+        float amin = 0.15f * (2 * e0 * s0 + 2 * e1 * s1 - e0 * e1 * s01);
+        float a = 0.15f * (2 * d0 * s0 + 2 * d1 * s1 - d0 * d1 * s01);
+        float aerr = fabsf(a - amin);
+        float symm = fabsf(th0 + th1);
+        float asymm = fabsf(th0 - th1);
+        float dist = (float)go_hypot((double)(d0 - e0), (double)(d1 - e1));
+        float ctr = 4.625e-6f * pow5(symm) + 7.5e-3f * asymm * symm * symm;
+        float halo_symm = 5e-3f * symm * dist;
+        float halo_asymm = 7e-2f * asymm * dist;
+        err = ctr + 1.55f * aerr + halo_symm + halo_asymm;
+    }
+    err *= chord_len;
+    cp.th0 = th0; cp.th1 = th1; cp.chord_len = chord_len; cp.err = err;
+    return cp;
+}
+
+__device__ inline EulerParams euler_params_from_angles(float th0, float th1) {   // euler.go:93-119
+    float k0 = th0 + th1;
+    float dth = th1 - th0;
+    float d2 = dth * dth;
+    float k2 = k0 * k0;
+    float a = 6.0f;
+    a -= d2 * (float)(1.0 / 70.0);
+    a -= (d2 * d2) * (float)(1.0 / 10780.0);
+    a += (d2 * d2 * d2) * (float)2.769178184818219e-07;
+    float b = -0.1f + d2 * (float)(1.0 / 4200.0) + d2 * d2 * (float)1.6959677820260655e-05;
+    float c = (float)(-1.0 / 1400.0) + d2 * (float)6.84915970574303e-05 - k2 * (float)7.936475029053326e-06;
+    a += (b + c * k2) * k2;
+    float k1 = dth * a;
+    float ch = 1.0f;
+    ch -= d2 * (float)(1.0 / 40.0);
+    ch += (d2 * d2) * (float)0.00034226190482569864;
+    ch -= (d2 * d2 * d2) * (float)1.9349474568904524e-06;
+    float b2 = (float)(-1.0 / 24.0) + d2 * (float)0.0024702380951963226 - d2 * d2 * (float)3.7297408997537985e-05;
+    float c2 = (float)(1.0 / 1920.0) - d2 * (float)4.87350869747975e-05 - k2 * (float)3.1001936068463107e-06;
+    ch += (b2 + c2 * k2) * k2;
+    EulerParams ep; ep.th0 = th0; ep.k0 = k0; ep.k1 = k1; ep.ch = ch;
+    return ep;
+}
+
+__device__ inline void integ_euler_10(float k0, float k1, float* uo, float* vo) {   // euler.go:149-186
+    float t1_1 = k0;
+    float t1_2 = 0.5f * k1;
+    float t2_2 = t1_1 * t1_1;
+    float t2_3 = 2.0f * (t1_1 * t1_2);
+    float t2_4 = t1_2 * t1_2;
+    float t3_4 = t2_2 * t1_2 + t2_3 * t1_1;
+    float t3_6 = t2_4 * t1_2;
+    float t4_4 = t2_2 * t2_2;
+    float t4_5 = 2.0f * (t2_2 * t2_3);
+    float t4_6 = 2.0f * (t2_2 * t2_4) + t2_3 * t2_3;
+    float t4_7 = 2.0f * (t2_3 * t2_4);
+    float t4_8 = t2_4 * t2_4;
+    float t5_6 = t4_4 * t1_2 + t4_5 * t1_1;
+    float t5_8 = t4_6 * t1_2 + t4_7 * t1_1;
+    float t6_6 = t4_4 * t2_2;
+    float t6_7 = t4_4 * t2_3 + t4_5 * t2_2;
+    float t6_8 = t4_4 * t2_4 + t4_5 * t2_3 + t4_6 * t2_2;
+    float t7_8 = t6_6 * t1_2 + t6_7 * t1_1;
+    float t8_8 = t6_6 * t2_2;
+    float u = 1.0f;
+    u -= (float)(1.0 / 24.0) * t2_2 + (float)(1.0 / 160.0) * t2_4;
+    u += (float)(1.0 / 1920.0) * t4_4 + (float)(1.0 / 10752.0) * t4_6 + (float)(1.0 / 55296.0) * t4_8;
+    u -= (float)(1.0 / 322560.0) * t6_6 + (float)(1.0 / 1658880.0) * t6_8;
+    u += (float)(1.0 / 92897280.0) * t8_8;
+    float v = (float)(1.0 / 12.0) * t1_2;
+    v -= (float)(1.0 / 480.0) * t3_4 + (float)(1.0 / 2688.0) * t3_6;
+    v += (float)(1.0 / 53760.0) * t5_6 + (float)(1.0 / 276480.0) * t5_8;
+    v -= (float)(1.0 / 11612160.0) * t7_8;
+    *uo = u; *vo = v;
+}
+
+// euler.go:121-146 with offset == 0 (fill): the offset vector is (0*sin, 0*cos) == +/-0 and
+// cannot change a finite sum, so it is not evaluated.
+__device__ inline V2 euler_seg_eval(V2 p0, V2 p1, const EulerParams& ep, float t) {
+    float thm = (ep.k0 + 0.5f * ep.k1 * (t * 0.5f - 1.0f)) * (t * 0.5f) - ep.th0;
+    float u, v;
+    integ_euler_10((ep.k0 + ep.k1 * (0.5f * t - 0.5f)) * t, ep.k1 * t * t, &u, &v);
+    float s = t / ep.ch * sin32(thm);
+    float c = t / ep.ch * cos32(thm);
+    V2 pt = mk(u * c - v * s, -v * c - u * s);
+    V2 chord = vsub(p1, p0);
+    return mk(p0.x + chord.x * pt.x - chord.y * pt.y, p0.y + chord.x * pt.y + chord.y * pt.x);
+}
+
+__device__ __forceinline__ void eval_cubic_and_deriv(V2 p0, V2 p1, V2 p2, V2 p3, float t, V2* po, V2* qo) {   // flatten.go:46-56
+    float m = 1.0f - t;
+    float mm = m * m, mt = m * t, tt = t * t;
+    *po = vadd(vmul(p0, mm * m), vmul(vadd(vadd(vmul(p1, 3 * mm), vmul(p2, 3 * mt)), vmul(p3, tt)), t));
+    *qo = vadd(vadd(vmul(vsub(p1, p0), mm), vmul(vsub(p2, p1), 2 * mt)), vmul(vsub(p3, p2), tt));
+}
+__device__ __forceinline__ float cube_signed_sqrt(float x) { return x * sqrt32(fabsf(x)); }   // flatten.go:195
+
+// Runs the adaptive subdivision. EMIT=false: returns the number of lines. EMIT=true: writes them
+// to out[0..] (path_ix set) and folds their endpoints into bb (minx, miny, maxx, maxy).
+template <bool EMIT>
+__device__ inline uint32_t flatten_cubic(V2 p0, V2 p1, V2 p2, V2 p3, uint32_t path_ix, GGLine* out, uint32_t out_cap_left, float* bb) {
+    const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f, FLATTEN_TOL = 0.25f;
+    if (veq(p0, p1) && veq(p0, p2) && veq(p0, p3)) return 0;
+    uint32_t n_out = 0;
+    uint32_t t0u = 0;
+    float dt = 1.0f;
+    V2 last_p = p0;
+    V2 last_q = vsub(p1, p0);
+    if (vlen_sq(last_q) < DERIV_THRESH * DERIV_THRESH) {
+        V2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &last_q);
+    }
+    float last_t = 0.0f;
+    V2 lp0 = p0;
+    for (;;) {
+        float t0 = (float)t0u * dt;
+        if (t0 == 1.0f) break;
+        float t1 = t0 + dt;
+        V2 this_p0 = last_p, this_q0 = last_q, this_p1, this_q1;
+        eval_cubic_and_deriv(p0, p1, p2, p3, t1, &this_p1, &this_q1);
+        if (vlen_sq(this_q1) < DERIV_THRESH * DERIV_THRESH) {
+            V2 new_p1, new_q1;
+            eval_cubic_and_deriv(p0, p1, p2, p3, t1 - DERIV_EPS, &new_p1, &new_q1);
+            this_q1 = new_q1;
+            if (t1 < 1.0f) { this_p1 = new_p1; t1 -= DERIV_EPS; }
+        }
+        float actual_dt = t1 - last_t;
+        CubicParams cp = cubic_params_from_points_derivs(this_p0, this_p1, this_q0, this_q1, actual_dt);
+        if (cp.err <= FLATTEN_TOL || dt <= SUBDIV_LIMIT) {
+            EulerParams ep = euler_params_from_angles(cp.th0, cp.th1);
+            float k0_minus_half_k1 = ep.k0 - 0.5f * ep.k1;
+            float k1 = ep.k1;
+            float scale_mul = 0.5f * (float)(1.41421356237309504880168872420969808 / 2.0) * sqrt32(cp.chord_len / (ep.ch * FLATTEN_TOL));
+            float n_frac;
+            bool low_k1;
+            float a = 0, b = 0, integral = 0, int0 = 0;
+            if (fabsf(k1) < 1e-3f) {
+                float k = k0_minus_half_k1 + 0.5f * k1;
+                n_frac = sqrt32(fabsf(k));
+                low_k1 = true;
+            } else {
+                a = k1;
+                b = k0_minus_half_k1;
+                int0 = cube_signed_sqrt(b);
+                float int1 = cube_signed_sqrt(a + b);
+                integral = int1 - int0;
+                n_frac = (float)(2.0 / 3.0) * integral / a;
+                low_k1 = false;
+            }
+            float n = ceilf(n_frac * scale_mul);
+            if (n < 1) n = 1;
+            if (n > 100) n = 100;
+            int n_int = (n != n) ? 0 : (int)n;
+            if (EMIT) {
+                for (int i = 0; i < n_int; i++) {
+                    V2 lp1;
+                    if (i == n_int - 1 && t1 == 1.0f) {
+                        lp1 = p3;
+                    } else {
+                        float t = (float)(i + 1) / n;
+                        float s;
+                        if (low_k1) {
+                            s = t;
+                        } else {
+                            float c = (float)cbrt((double)(integral * t + int0));
+                            float inv = c * fabsf(c);
+                            s = (inv - b) / a;
+                        }
+                        lp1 = euler_seg_eval(this_p0, this_p1, ep, s);
+                    }
+                    if (n_out < out_cap_left) {
+                        GGLine l; l.path_ix = path_ix; l.p0x = lp0.x; l.p0y = lp0.y; l.p1x = lp1.x; l.p1y = lp1.y;
+                        out[n_out] = l;
+                    }
+                    bb[0] = fminf(bb[0], lp1.x); bb[1] = fminf(bb[1], lp1.y);
+                    bb[2] = fmaxf(bb[2], lp1.x); bb[3] = fmaxf(bb[3], lp1.y);
+                    n_out++;
+                    lp0 = lp1;
+                }
+            } else {
+                n_out += (uint32_t)n_int;
+            }
+            last_p = this_p1; last_q = this_q1; last_t = t1;
+            t0u++;
+            uint32_t shift = (uint32_t)(__ffs((int)t0u) - 1);   // trailing zeros; t0u != 0 here
+            t0u >>= shift;
+            dt *= (float)(1u << shift);
+        } else {
+            if (t0u < 0xFFFFFFFFu / 2) t0u *= 2;
+            dt *= 0.5f;
+        }
+    }
+    return n_out;
+}

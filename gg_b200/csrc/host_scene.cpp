@@ -1,0 +1,478 @@
+// gg_b200/csrc/host_scene.cpp -- see host_scene.h.
+#include "host_scene.h"
+
+#include <math.h>
+#include <string.h>
+
+#include "../../include/ggcuda.h"
+
+enum { PT_LINETO = 0x09, PT_QUADTO = 0x0A, PT_CUBICTO = 0x0B, PT_MOVETO = 0x0C, PT_PATH = 0x10, PT_TRANSFORM = 0x20, PT_STYLE = 0x40 };
+enum { DT_COLOR = 0x44, DT_BEGIN_CLIP = 0x9, DT_END_CLIP = 0x21 };
+
+// scene.Tag values, scene/tag.go:25-110
+enum {
+    ST_TRANSFORM = 0x01, ST_SET_AA = 0x02, ST_BEGIN_PATH = 0x10, ST_MOVE_TO = 0x11, ST_LINE_TO = 0x12, ST_QUAD_TO = 0x13,
+    ST_CUBIC_TO = 0x14, ST_CLOSE_PATH = 0x16, ST_END_PATH = 0x17, ST_FILL = 0x20, ST_STROKE = 0x21, ST_FILL_ROUND_RECT = 0x22,
+    ST_PUSH_LAYER = 0x30, ST_POP_LAYER = 0x31, ST_BEGIN_CLIP = 0x40, ST_END_CLIP = 0x41, ST_BRUSH = 0x50, ST_IMAGE = 0x51, ST_TEXT = 0x60
+};
+
+static const float IDENTITY[6] = {1, 0, 0, 0, 1, 0};   // scene.Affine: x' = A x + B y + C, y' = D x + E y + F
+
+uint8_t gg_clamp_u8(double v) {   // path_convert.go:131-140
+    double x = v * 255.0 + 0.5;
+    if (x < 0) return 0;
+    if (x > 255) return 255;
+    return (uint8_t)x;
+}
+uint32_t gg_pack_color_straight(const uint8_t c[4]) {   // scene_encode.go:162-168 (float32, +0.5)
+    float a = (float)c[3] / 255.0f;
+    uint32_t r = (uint32_t)(int64_t)((float)c[0] * a + 0.5f);
+    uint32_t g = (uint32_t)(int64_t)((float)c[1] * a + 0.5f);
+    uint32_t b = (uint32_t)(int64_t)((float)c[2] * a + 0.5f);
+    return r | (g << 8) | (b << 16) | ((uint32_t)c[3] << 24);
+}
+uint32_t gg_blend_word(uint32_t m) {   // scene/encoding.go:17-48 -> (mix << 8) | compose
+    if (m < 16) return (m << 8) | 3u;  // Normal..Luminosity mix with SrcOver compose
+    if (m <= 28) return m - 16;        // Clear..Plus compose with Normal mix
+    return 3u;
+}
+
+void HostScene::clear(uint32_t w, uint32_t h) {
+    width = w; height = h;
+    tags.clear(); path_data.clear(); draw_tags.clear(); draw_data.clear(); styles.clear(); transforms.clear();
+    clip_aux.clear(); clip_stack.clear(); clip_kind.clear();
+    n_paths = n_clips = n_seg_tags = 0;
+    have_transform = false; in_path = false; has_move = false;
+}
+
+void HostScene::begin_path(const float t[6], bool even_odd) {
+    if (!have_transform || memcmp(t, last_transform, sizeof(float) * 6) != 0) {
+        tags.push_back(PT_TRANSFORM);
+        transforms.insert(transforms.end(), t, t + 6);
+        memcpy(last_transform, t, sizeof(float) * 6);
+        have_transform = true;
+    }
+    tags.push_back(PT_STYLE);
+    styles.push_back(even_odd ? 0x02u : 0u);   // scene_encode.go:110-114
+    in_path = true; has_move = false;
+}
+void HostScene::move_to(float x, float y) {
+    // An open subpath is closed implicitly, as every CPU filler in gg does (the Vello
+    // path of the reference leaves it open, path_convert.go:44-49).
+    if (has_move && (cur[0] != start[0] || cur[1] != start[1])) line_to(start[0], start[1]);
+    tags.push_back(PT_MOVETO);
+    path_data.push_back(x); path_data.push_back(y);
+    cur[0] = start[0] = x; cur[1] = start[1] = y; has_move = true;
+}
+void HostScene::line_to(float x, float y) {
+    if (!has_move) return;   // path_convert.go:52-54
+    tags.push_back(PT_LINETO);
+    path_data.push_back(x); path_data.push_back(y);
+    cur[0] = x; cur[1] = y; n_seg_tags++;
+}
+void HostScene::quad_to(float cx, float cy, float x, float y) {
+    if (!has_move) return;
+    tags.push_back(PT_QUADTO);
+    path_data.push_back(cx); path_data.push_back(cy); path_data.push_back(x); path_data.push_back(y);
+    cur[0] = x; cur[1] = y; n_seg_tags++;
+}
+void HostScene::cubic_to(float c1x, float c1y, float c2x, float c2y, float x, float y) {
+    if (!has_move) return;
+    tags.push_back(PT_CUBICTO);
+    path_data.push_back(c1x); path_data.push_back(c1y); path_data.push_back(c2x); path_data.push_back(c2y);
+    path_data.push_back(x); path_data.push_back(y);
+    cur[0] = x; cur[1] = y; n_seg_tags++;
+}
+void HostScene::close() {   // path_convert.go:86-92
+    if (has_move && (cur[0] != start[0] || cur[1] != start[1])) line_to(start[0], start[1]);
+    cur[0] = start[0]; cur[1] = start[1];
+}
+void HostScene::end_path() {
+    if (has_move && (cur[0] != start[0] || cur[1] != start[1])) line_to(start[0], start[1]);
+    tags.push_back(PT_PATH);
+    n_paths++;
+    in_path = false; has_move = false;
+}
+void HostScene::add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* c, uint32_t n_coords) {
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n_verbs; i++) {
+        switch (verbs[i]) {
+        case GGCUDA_VERB_MOVE: if (k + 2 > n_coords) return; move_to((float)c[k], (float)c[k + 1]); k += 2; break;
+        case GGCUDA_VERB_LINE: if (k + 2 > n_coords) return; line_to((float)c[k], (float)c[k + 1]); k += 2; break;
+        case GGCUDA_VERB_QUAD: if (k + 4 > n_coords) return; quad_to((float)c[k], (float)c[k + 1], (float)c[k + 2], (float)c[k + 3]); k += 4; break;
+        case GGCUDA_VERB_CUBIC: if (k + 6 > n_coords) return;
+            cubic_to((float)c[k], (float)c[k + 1], (float)c[k + 2], (float)c[k + 3], (float)c[k + 4], (float)c[k + 5]); k += 6; break;
+        case GGCUDA_VERB_CLOSE: close(); break;
+        default: break;
+        }
+    }
+}
+
+void HostScene::draw_color(uint32_t rgba_premul) {
+    draw_tags.push_back(DT_COLOR);
+    draw_data.push_back(rgba_premul);
+    clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
+    clip_aux.push_back(0);
+}
+void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
+    int32_t d = (int32_t)draw_tags.size();
+    draw_tags.push_back(DT_BEGIN_CLIP);
+    draw_data.push_back(blend_word);
+    uint32_t ab; memcpy(&ab, &alpha, 4);
+    draw_data.push_back(ab);
+    clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
+    clip_aux.push_back(-1);   // link patched by end_clip
+    clip_stack.push_back(d); clip_kind.push_back(kind);
+    n_clips++;
+}
+bool HostScene::end_clip(uint8_t kind) {
+    if (clip_stack.empty() || clip_kind.back() != kind) return false;
+    int32_t b = clip_stack.back();
+    clip_stack.pop_back(); clip_kind.pop_back();
+    int32_t d = (int32_t)draw_tags.size();
+    // EndClip: dummy path marker so that path index == draw index (scene_encode.go:258-268);
+    // we also give it a style word so that styles[path_ix] is valid for every path.
+    tags.push_back(PT_STYLE); styles.push_back(0);
+    tags.push_back(PT_PATH); n_paths++;
+    draw_tags.push_back(DT_END_CLIP);
+    clip_aux.push_back(b);    // "parent" of an EndClip = its BeginClip
+    clip_aux.push_back(b);
+    clip_aux[2 * (size_t)b + 1] = d;
+    n_clips++;
+    return true;
+}
+void HostScene::close_open_clips() {
+    while (!clip_stack.empty()) end_clip(clip_kind.back());
+}
+
+size_t HostScene::packed_words() const {
+    size_t tw = (tags.size() + 3) / 4;
+    size_t padded = (tw + 255) / 256 * 256;
+    if (padded == 0) padded = 256;
+    return padded + path_data.size() + draw_tags.size() + draw_data.size() + transforms.size() + styles.size() + clip_aux.size() + 8;
+}
+void HostScene::pack(uint32_t* out, Layout* L, uint32_t band_tiles) const {   // scene_encode.go:280-356
+    uint32_t tw = (uint32_t)((tags.size() + 3) / 4);
+    uint32_t padded = (tw + 255) / 256 * 256;
+    if (padded == 0) padded = 256;
+    uint32_t off = 0;
+    L->n_tag_bytes = (uint32_t)tags.size(); L->n_tag_words = padded;
+    L->n_draws = (uint32_t)draw_tags.size(); L->n_paths = n_paths; L->n_clips = n_clips;
+    L->path_tag_base = off; off += padded;
+    L->path_data_base = off; off += (uint32_t)path_data.size();
+    L->draw_tag_base = off; off += (uint32_t)draw_tags.size();
+    L->draw_data_base = off; off += (uint32_t)draw_data.size();
+    L->transform_base = off; off += (uint32_t)transforms.size();
+    L->style_base = off; off += (uint32_t)styles.size();
+    L->clip_aux_base = off; off += (uint32_t)clip_aux.size();
+    L->n_scene_words = off;
+    memset(out, 0, sizeof(uint32_t) * padded);
+    memcpy(out, tags.data(), tags.size());   // little endian: byte i -> bits 8*(i%4) of word i/4 (packPathTags)
+    if (!path_data.empty()) memcpy(out + L->path_data_base, path_data.data(), 4 * path_data.size());
+    if (!draw_tags.empty()) memcpy(out + L->draw_tag_base, draw_tags.data(), 4 * draw_tags.size());
+    if (!draw_data.empty()) memcpy(out + L->draw_data_base, draw_data.data(), 4 * draw_data.size());
+    if (!transforms.empty()) memcpy(out + L->transform_base, transforms.data(), 4 * transforms.size());
+    if (!styles.empty()) memcpy(out + L->style_base, styles.data(), 4 * styles.size());
+    if (!clip_aux.empty()) memcpy(out + L->clip_aux_base, clip_aux.data(), 4 * clip_aux.size());
+    uint32_t* tail = out + off;   // device-resident element counts for the scan primitive
+    tail[0] = padded; tail[1] = L->n_draws; tail[2] = L->n_tag_bytes; tail[3] = n_paths; tail[4] = band_tiles;
+    tail[5] = tail[6] = tail[7] = 0;
+}
+
+// ------------------------------------------------------------------ scene.Encoding ingest
+static void emit_round_rect(HostScene* s, float x0, float y0, float x1, float y1, float rx, float ry) {
+    // scene/path.go rounded rectangle with kappa arcs; TagFillRoundRect is SDF-rendered by the
+    // CPU oracle (scene/renderer.go:986-1071) -- exact-area rendering of the same outline here.
+    const float k = 0.5522847498f;
+    float w = x1 - x0, h = y1 - y0;
+    if (rx > w * 0.5f) rx = w * 0.5f;
+    if (ry > h * 0.5f) ry = h * 0.5f;
+    if (rx <= 0 || ry <= 0) {
+        s->move_to(x0, y0); s->line_to(x1, y0); s->line_to(x1, y1); s->line_to(x0, y1); s->close();
+        return;
+    }
+    float kx = rx * k, ky = ry * k;
+    s->move_to(x0 + rx, y0);
+    s->line_to(x1 - rx, y0);
+    s->cubic_to(x1 - rx + kx, y0, x1, y0 + ry - ky, x1, y0 + ry);
+    s->line_to(x1, y1 - ry);
+    s->cubic_to(x1, y1 - ry + ky, x1 - rx + kx, y1, x1 - rx, y1);
+    s->line_to(x0 + rx, y1);
+    s->cubic_to(x0 + rx - kx, y1, x0, y1 - ry + ky, x0, y1 - ry);
+    s->line_to(x0, y0 + ry);
+    s->cubic_to(x0, y0 + ry - ky, x0 + rx - kx, y0, x0 + rx, y0);
+    s->close();
+}
+
+static uint32_t brush_color(const double* brushes, size_t n_brushes, uint32_t ix) {
+    uint8_t c[4] = {0, 0, 0, 0};   // missing brush: zero Brush{} -> transparent
+    if (ix < n_brushes) {
+        const double* b = brushes + 4 * (size_t)ix;
+        c[0] = gg_clamp_u8(b[0]); c[1] = gg_clamp_u8(b[1]); c[2] = gg_clamp_u8(b[2]); c[3] = gg_clamp_u8(b[3]);
+    }
+    return gg_pack_color_straight(c);
+}
+
+int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, size_t n_pd, const uint32_t* dd, size_t n_dd,
+                            const float* tr, size_t n_tr, const double* brushes, size_t n_brushes, std::string* msg) {
+    size_t pi = 0, di = 0, ti = 0;
+    float cur_t[6]; memcpy(cur_t, IDENTITY, sizeof cur_t);
+    std::vector<uint8_t> pv; std::vector<float> pc;   // current path: verbs + untransformed coords
+    bool path_active = false;
+    auto emit_path = [&](bool even_odd) {
+        begin_path(cur_t, even_odd);
+        size_t k = 0;
+        for (uint8_t v : pv) {
+            switch (v) {
+            case GGCUDA_VERB_MOVE: move_to(pc[k], pc[k + 1]); k += 2; break;
+            case GGCUDA_VERB_LINE: line_to(pc[k], pc[k + 1]); k += 2; break;
+            case GGCUDA_VERB_QUAD: quad_to(pc[k], pc[k + 1], pc[k + 2], pc[k + 3]); k += 4; break;
+            case GGCUDA_VERB_CUBIC: cubic_to(pc[k], pc[k + 1], pc[k + 2], pc[k + 3], pc[k + 4], pc[k + 5]); k += 6; break;
+            case GGCUDA_VERB_CLOSE: close(); break;
+            }
+        }
+        end_path();
+    };
+    for (size_t i = 0; i < n_tags; i++) {
+        switch (tg[i]) {
+        case ST_TRANSFORM:
+            if (ti + 1 > n_tr) { *msg = "encoding: transform stream underrun"; return GGCUDA_ERR_INVALID; }
+            memcpy(cur_t, tr + 6 * ti, sizeof cur_t); ti++;
+            break;
+        case ST_SET_AA: di += 1; break;   // anti-aliasing is always on in this path
+        case ST_BEGIN_PATH: pv.clear(); pc.clear(); path_active = true; break;
+        case ST_MOVE_TO: case ST_LINE_TO:
+            if (pi + 2 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
+            if (path_active) { pv.push_back(tg[i] == ST_MOVE_TO ? GGCUDA_VERB_MOVE : GGCUDA_VERB_LINE); pc.insert(pc.end(), pd + pi, pd + pi + 2); }
+            pi += 2; break;
+        case ST_QUAD_TO:
+            if (pi + 4 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
+            if (path_active) { pv.push_back(GGCUDA_VERB_QUAD); pc.insert(pc.end(), pd + pi, pd + pi + 4); }
+            pi += 4; break;
+        case ST_CUBIC_TO:
+            if (pi + 6 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
+            if (path_active) { pv.push_back(GGCUDA_VERB_CUBIC); pc.insert(pc.end(), pd + pi, pd + pi + 6); }
+            pi += 6; break;
+        case ST_CLOSE_PATH: if (path_active) pv.push_back(GGCUDA_VERB_CLOSE); break;
+        case ST_END_PATH: break;
+        case ST_FILL: {
+            if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
+            uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
+            if (path_active && !pv.empty()) { emit_path(style == 1); draw_color(brush_color(brushes, n_brushes, bix)); }
+            path_active = false;
+        } break;
+        case ST_STROKE: {
+            if (di + 5 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
+            uint32_t bix = dd[di]; float w, ml; memcpy(&w, dd + di + 1, 4); memcpy(&ml, dd + di + 2, 4);
+            uint32_t cap = dd[di + 3], join = dd[di + 4]; di += 5;
+            if (path_active && !pv.empty()) {
+                // CPU scene tiles transform the points, then stroke with the raw width
+                // (scene/renderer.go:655-684, 707-713): do the same, in device space.
+                std::vector<float> dev(pc.size());
+                for (size_t k = 0; k + 1 < pc.size(); k += 2) {
+                    dev[k] = cur_t[0] * pc[k] + cur_t[1] * pc[k + 1] + cur_t[2];
+                    dev[k + 1] = cur_t[3] * pc[k] + cur_t[4] * pc[k + 1] + cur_t[5];
+                }
+                StrokeStyleHost st = {(double)w, (double)ml, (int)cap, (int)join};
+                begin_path(IDENTITY, false);
+                gg_stroke_to_fill(pv, dev, st, this);
+                end_path();
+                draw_color(brush_color(brushes, n_brushes, bix));
+            }
+            path_active = false;
+        } break;
+        case ST_FILL_ROUND_RECT: {
+            if (di + 2 > n_dd || pi + 6 > n_pd) { *msg = "encoding: round-rect underrun"; return GGCUDA_ERR_INVALID; }
+            uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
+            const float* r = pd + pi; pi += 6;
+            begin_path(cur_t, style == 1);
+            emit_round_rect(this, r[0], r[1], r[2], r[3], r[4], r[5]);
+            end_path();
+            draw_color(brush_color(brushes, n_brushes, bix));
+        } break;
+        case ST_PUSH_LAYER: {
+            if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
+            uint32_t blend = dd[di]; float alpha; memcpy(&alpha, dd + di + 1, 4); di += 2;
+            // a layer is a clip over the whole canvas that carries the blend mode and alpha
+            begin_path(IDENTITY, false);
+            move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
+            end_path();
+            begin_clip(gg_blend_word(blend), alpha, 1);
+        } break;
+        case ST_POP_LAYER:
+            while (!clip_stack.empty() && clip_kind.back() == 0) end_clip(0);   // unbalanced clips inside the layer
+            end_clip(1);
+            break;
+        case ST_BEGIN_CLIP:
+            if (path_active && !pv.empty()) emit_path(false);
+            else { begin_path(IDENTITY, false); end_path(); }   // empty clip path clips everything (renderer.go:747-753)
+            begin_clip(0x8003u, 1.0f, 0);
+            path_active = false;
+            break;
+        case ST_END_CLIP: end_clip(0); break;
+        case ST_BRUSH: pi += 4; break;
+        case ST_IMAGE: *msg = "encoding: TagImage is not supported by the CUDA path"; return GGCUDA_ERR_UNSUPPORTED;
+        case ST_TEXT: *msg = "encoding: TagText must be resolved to outlines before the CUDA path"; return GGCUDA_ERR_UNSUPPORTED;
+        default: *msg = "encoding: unknown tag"; return GGCUDA_ERR_INVALID;
+        }
+    }
+    close_open_clips();   // renderer.go:789-797
+    return 0;
+}
+
+// ------------------------------------------------------------------ stroke outline (host)
+// Polyline stroker: curves are subdivided to `tol`, each subpath becomes one closed outline
+// (left side forward, cap, right side backward, cap) or two loops for closed subpaths; joins
+// are added on both sides (the inner ones overlap harmlessly under NonZero).
+namespace {
+struct P2 { double x, y; };
+const double STROKE_TOL = 0.1;
+
+void flatten_quad(std::vector<P2>& o, P2 a, P2 b, P2 c) {
+    double ddx = a.x - 2 * b.x + c.x, ddy = a.y - 2 * b.y + c.y;
+    int n = (int)ceil(sqrt(sqrt(ddx * ddx + ddy * ddy) / (4 * STROKE_TOL)));
+    if (n < 1) n = 1; if (n > 256) n = 256;
+    for (int i = 1; i <= n; i++) {
+        double t = (double)i / n, m = 1 - t;
+        o.push_back({m * m * a.x + 2 * m * t * b.x + t * t * c.x, m * m * a.y + 2 * m * t * b.y + t * t * c.y});
+    }
+}
+void flatten_cubic(std::vector<P2>& o, P2 a, P2 b, P2 c, P2 d) {
+    double d1x = a.x - 2 * b.x + c.x, d1y = a.y - 2 * b.y + c.y, d2x = b.x - 2 * c.x + d.x, d2y = b.y - 2 * c.y + d.y;
+    double m = fmax(sqrt(d1x * d1x + d1y * d1y), sqrt(d2x * d2x + d2y * d2y));
+    int n = (int)ceil(sqrt(0.75 * m / STROKE_TOL));
+    if (n < 1) n = 1; if (n > 512) n = 512;
+    for (int i = 1; i <= n; i++) {
+        double t = (double)i / n, u = 1 - t;
+        double w0 = u * u * u, w1 = 3 * u * u * t, w2 = 3 * u * t * t, w3 = t * t * t;
+        o.push_back({w0 * a.x + w1 * b.x + w2 * c.x + w3 * d.x, w0 * a.y + w1 * b.y + w2 * c.y + w3 * d.y});
+    }
+}
+void arc_points(std::vector<P2>& o, P2 c, double r, double a0, double a1) {   // a0 -> a1 (signed sweep), excluding start, including end
+    double sweep = a1 - a0;
+    double step = 2 * acos(fmax(0.0, 1 - STROKE_TOL / fmax(r, STROKE_TOL)));
+    if (step < 0.05) step = 0.05;
+    int n = (int)ceil(fabs(sweep) / step);
+    if (n < 1) n = 1;
+    for (int i = 1; i <= n; i++) { double a = a0 + sweep * i / n; o.push_back({c.x + r * cos(a), c.y + r * sin(a)}); }
+}
+// join at vertex v between directions d0 -> d1 on the side with normal sign `side` (+1 = left)
+void add_join(std::vector<P2>& o, P2 v, P2 d0, P2 d1, double hw, int side, int join, double miter_limit) {
+    P2 n0 = {-d0.y * side, d0.x * side}, n1 = {-d1.y * side, d1.x * side};
+    P2 a = {v.x + n0.x * hw, v.y + n0.y * hw}, b = {v.x + n1.x * hw, v.y + n1.y * hw};
+    double cross = d0.x * d1.y - d0.y * d1.x, dot = d0.x * d1.x + d0.y * d1.y;
+    bool outer = cross * side < 0;   // turning away from this side
+    o.push_back(a);
+    if (outer && fabs(cross) > 1e-12) {
+        if (join == GGCUDA_JOIN_ROUND) {
+            double a0 = atan2(n0.y, n0.x), a1 = atan2(n1.y, n1.x);
+            double sw = a1 - a0;
+            while (sw > M_PI) sw -= 2 * M_PI;
+            while (sw < -M_PI) sw += 2 * M_PI;
+            arc_points(o, v, hw, a0, a0 + sw);
+            return;
+        } else if (join == GGCUDA_JOIN_MITER) {
+            double cos_half = sqrt(fmax(0.0, (1 + dot) * 0.5));
+            if (cos_half > 1e-9 && 1.0 / cos_half <= miter_limit) {
+                P2 m = {n0.x + n1.x, n0.y + n1.y};
+                double ml = sqrt(m.x * m.x + m.y * m.y);
+                if (ml > 1e-12) { double k = hw / cos_half / ml; o.push_back({v.x + m.x * k, v.y + m.y * k}); }
+            }
+        }
+    }
+    o.push_back(b);
+}
+void add_cap(std::vector<P2>& o, P2 v, P2 d, double hw, int cap) {   // from left side to right side around the end, d = outgoing direction
+    P2 n = {-d.y, d.x};
+    P2 l = {v.x + n.x * hw, v.y + n.y * hw}, r = {v.x - n.x * hw, v.y - n.y * hw};
+    o.push_back(l);
+    if (cap == GGCUDA_CAP_ROUND) {
+        double a0 = atan2(n.y, n.x);
+        arc_points(o, v, hw, a0, a0 - M_PI);
+        return;
+    } else if (cap == GGCUDA_CAP_SQUARE) {
+        o.push_back({l.x + d.x * hw, l.y + d.y * hw});
+        o.push_back({r.x + d.x * hw, r.y + d.y * hw});
+    }
+    o.push_back(r);
+}
+void emit_loop(HostScene* s, const std::vector<P2>& pts) {
+    if (pts.size() < 3) return;
+    s->move_to((float)pts[0].x, (float)pts[0].y);
+    for (size_t i = 1; i < pts.size(); i++) s->line_to((float)pts[i].x, (float)pts[i].y);
+    s->close();
+}
+void stroke_subpath(std::vector<P2>& pts, bool closed, const StrokeStyleHost& st, HostScene* out) {
+    // drop consecutive duplicates
+    std::vector<P2> p;
+    for (const P2& q : pts) if (p.empty() || fabs(q.x - p.back().x) > 1e-9 || fabs(q.y - p.back().y) > 1e-9) p.push_back(q);
+    if (closed && p.size() > 1 && fabs(p.front().x - p.back().x) < 1e-9 && fabs(p.front().y - p.back().y) < 1e-9) p.pop_back();
+    double hw = st.width * 0.5;
+    if (hw <= 0) return;
+    size_t n = p.size();
+    if (n == 0) return;
+    if (n == 1) {   // degenerate: dot for round / square caps
+        if (st.cap == GGCUDA_CAP_BUTT) return;
+        std::vector<P2> o;
+        if (st.cap == GGCUDA_CAP_ROUND) arc_points(o, p[0], hw, 0, 2 * M_PI);
+        else { o.push_back({p[0].x - hw, p[0].y - hw}); o.push_back({p[0].x + hw, p[0].y - hw}); o.push_back({p[0].x + hw, p[0].y + hw}); o.push_back({p[0].x - hw, p[0].y + hw}); }
+        emit_loop(out, o);
+        return;
+    }
+    size_t ns = closed ? n : n - 1;
+    std::vector<P2> dir(ns);
+    for (size_t i = 0; i < ns; i++) {
+        P2 a = p[i], b = p[(i + 1) % n];
+        double dx = b.x - a.x, dy = b.y - a.y, l = sqrt(dx * dx + dy * dy);
+        dir[i] = {dx / l, dy / l};
+    }
+    if (closed && n >= 3) {
+        std::vector<P2> left, right;
+        for (size_t i = 0; i < n; i++) {
+            P2 d0 = dir[(i + n - 1) % n], d1 = dir[i];
+            add_join(left, p[i], d0, d1, hw, +1, st.join, st.miter_limit);
+            add_join(right, p[i], d0, d1, hw, -1, st.join, st.miter_limit);
+        }
+        emit_loop(out, left);
+        std::vector<P2> rr(right.rbegin(), right.rend());
+        emit_loop(out, rr);
+        return;
+    }
+    std::vector<P2> o, right;
+    // left side forward
+    o.push_back({p[0].x - dir[0].y * hw, p[0].y + dir[0].x * hw});
+    for (size_t i = 1; i + 1 < n; i++) add_join(o, p[i], dir[i - 1], dir[i], hw, +1, st.join, st.miter_limit);
+    add_cap(o, p[n - 1], dir[ns - 1], hw, st.cap);
+    // right side backward
+    for (size_t i = n - 1; i-- > 1;) {
+        std::vector<P2> j;
+        add_join(j, p[i], dir[i - 1], dir[i], hw, -1, st.join, st.miter_limit);
+        o.insert(o.end(), j.rbegin(), j.rend());
+    }
+    P2 back = {-dir[0].x, -dir[0].y};
+    add_cap(o, p[0], back, hw, st.cap);
+    emit_loop(out, o);
+}
+}  // namespace
+
+void gg_stroke_to_fill(const std::vector<uint8_t>& verbs, const std::vector<float>& c, const StrokeStyleHost& st, HostScene* out) {
+    std::vector<P2> pts;
+    bool closed = false, have = false;
+    P2 cur = {0, 0}, start = {0, 0};
+    size_t k = 0;
+    auto flush = [&]() {
+        if (have && !pts.empty()) stroke_subpath(pts, closed, st, out);
+        pts.clear(); closed = false;
+    };
+    auto seg_start = [&]() { if (pts.empty()) pts.push_back(cur); };
+    for (uint8_t v : verbs) {
+        switch (v) {
+        case GGCUDA_VERB_MOVE: flush(); cur = start = {c[k], c[k + 1]}; k += 2; have = true; break;
+        case GGCUDA_VERB_LINE: if (have) { seg_start(); cur = {c[k], c[k + 1]}; pts.push_back(cur); } k += 2; break;
+        case GGCUDA_VERB_QUAD: if (have) { seg_start(); P2 b = {c[k], c[k + 1]}, e = {c[k + 2], c[k + 3]}; flatten_quad(pts, cur, b, e); cur = e; } k += 4; break;
+        case GGCUDA_VERB_CUBIC: if (have) { seg_start(); P2 b = {c[k], c[k + 1]}, d = {c[k + 2], c[k + 3]}, e = {c[k + 4], c[k + 5]}; flatten_cubic(pts, cur, b, d, e); cur = e; } k += 6; break;
+        case GGCUDA_VERB_CLOSE: if (have) { closed = true; flush(); cur = start; } break;
+        }
+    }
+    flush();
+}

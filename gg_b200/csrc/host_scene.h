@@ -1,0 +1,74 @@
+// gg_b200/csrc/host_scene.h -- host-side scene packing for libggcuda.
+//
+// Turns gg's two input forms into the packed, Vello-style scene the device consumes:
+//   * per-draw paths (gg.Path verbs + f64 device-space coords), the GPUAccelerator.FillPath /
+//     StrokePath boundary (accelerator.go:118-128, path_convert.go:29-112), and
+//   * whole scene.Encoding streams (scene/encoding.go:407-444) with the tag semantics of
+//     scene.Renderer.executeEncodingOnTile (scene/renderer.go:619-813).
+// Packed layout == gg's PackedScene (tilecompute/scene_encode.go:52-66, 280-356):
+//   path tags (4 per u32, padded to 256 words) | path data | draw tags | draw data |
+//   transforms | styles, followed by our clip-aux words and five constant words.
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+struct HostScene {
+    uint32_t width = 0, height = 0;
+    std::vector<uint8_t> tags;
+    std::vector<float> path_data;
+    std::vector<uint32_t> draw_tags, draw_data, styles;
+    std::vector<float> transforms;
+    std::vector<int32_t> clip_aux;       // 2 per draw: enclosing BeginClip (-1), link (End for Begin, Begin for End)
+    std::vector<int32_t> clip_stack;     // open BeginClip draw indices
+    std::vector<uint8_t> clip_kind;      // 0 = clip, 1 = layer (parallel to clip_stack)
+    uint32_t n_paths = 0, n_clips = 0, n_seg_tags = 0;
+    float last_transform[6] = {0, 0, 0, 0, 0, 0};
+    bool have_transform = false;
+    // current path state
+    bool in_path = false, has_move = false;
+    float cur[2] = {0, 0}, start[2] = {0, 0};
+
+    void clear(uint32_t w, uint32_t h);
+    uint32_t n_draws() const { return (uint32_t)draw_tags.size(); }
+
+    // path construction (coordinates in the space of `transform`; the device applies it)
+    void begin_path(const float transform[6], bool even_odd);
+    void move_to(float x, float y);
+    void line_to(float x, float y);
+    void quad_to(float cx, float cy, float x, float y);
+    void cubic_to(float c1x, float c1y, float c2x, float c2y, float x, float y);
+    void close();
+    void end_path();                      // auto-closes the open subpath, emits the Path marker
+    void add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords);
+
+    void draw_color(uint32_t rgba_premul);                 // DrawTagColor for the path just ended
+    void begin_clip(uint32_t blend_word, float alpha, uint8_t kind);   // DrawTagBeginClip for the path just ended
+    bool end_clip(uint8_t kind);                           // DrawTagEndClip (+ dummy path); false if nothing to pop
+    void close_open_clips();
+
+    // scene.Encoding ingest; returns 0 or a negative GGCUDA_ERR_* with msg set
+    int add_encoding(const uint8_t* tags_in, size_t n_tags, const float* pd, size_t n_pd, const uint32_t* dd, size_t n_dd,
+                     const float* tr, size_t n_tr, const double* brushes, size_t n_brushes, std::string* msg);
+
+    // packed words + layout
+    struct Layout {
+        uint32_t n_tag_bytes, n_tag_words, n_draws, n_paths, n_clips;
+        uint32_t path_tag_base, path_data_base, draw_tag_base, draw_data_base, transform_base, style_base, clip_aux_base, n_scene_words;
+    };
+    size_t packed_words() const;          // including the constant tail
+    void pack(uint32_t* out, Layout* L, uint32_t band_tiles) const;
+};
+
+// premultiplied RGBA8 packing of a straight RGBA8 colour (scene_encode.go:162-168)
+uint32_t gg_pack_color_straight(const uint8_t c[4]);
+// clampU8 of a float colour channel (path_convert.go:131-140)
+uint8_t gg_clamp_u8(double v);
+// scene.BlendMode -> PTCL blend word: (mix << 8) | compose, Vello/peniko numbering
+uint32_t gg_blend_word(uint32_t scene_blend_mode);
+
+// Stroke outline of a device-space path as a polygon set to be filled NonZero
+// (software.go:1145-1226 fills the expanded stroke with the paint's rule, NonZero).
+struct StrokeStyleHost { double width, miter_limit; int cap, join; };
+void gg_stroke_to_fill(const std::vector<uint8_t>& verbs, const std::vector<float>& coords, const StrokeStyleHost& st, HostScene* out);

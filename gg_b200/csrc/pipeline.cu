@@ -1,0 +1,743 @@
+// gg_b200/csrc/pipeline.cu -- every stage of the ggcuda pipeline before fine rasterisation.
+// Compiled with -fmad=false: the float32 results of these stages feed integer decisions
+// (line counts, tile walks, backdrops) that must match the CPU twin bit-for-bit.
+//
+// Stage map (reference = gogpu/gg internal/gpu/tilecompute, CPU twin of its WGSL kernels):
+//   pathtag scan      pathtag.go:26-121            -> tag_monoids
+//   draw scan + leaf  draw_leaf.go:29-151          -> draw_monoids, info, clip_inps, draw_recs
+//   clip leaf fix-up  clip_leaf.go:27-56           (matching resolved on the host, applied here)
+//   flatten           flatten.go / euler.go / path_convert.go:29-112 -> lines (+ per-path bbox)
+//   path setup        coarse.go:169-223            -> paths (tile bbox, tile offset)
+//   path_count        path_count.go:11-205         -> tiles (backdrop deltas, counts), seg_counts
+//   backdrop          coarse.go:291-299            -> tiles (prefix-summed backdrop) + tile hit histogram
+//   seg alloc         coarse.go:276-285            -> seg_start (global exclusive scan of counts)
+//   path_tiling       path_tiling.go:11-199        -> segments
+//   coarse            coarse.go:322-625, ptcl.go   -> per-tile PTCL
+#include "pipeline.cuh"
+#include "flatten.cuh"
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
+#define GG_GRID(blocks_per_sm) (GG_SM_COUNT * (blocks_per_sm))
+
+// ------------------------------------------------------------------ monoids
+__device__ __forceinline__ GGPathMonoid path_monoid_new(uint32_t tag_word) {   // pathtag.go:26-63
+    GGPathMonoid m;
+    uint32_t point_count = tag_word & 0x03030303u;
+    m.path_seg_ix = __popc((point_count * 7) & 0x04040404u);
+    m.trans_ix = __popc(tag_word & 0x20202020u);
+    uint32_t n_points = point_count + ((tag_word >> 2) & 0x01010101u);
+    uint32_t a = n_points + (n_points & (((tag_word >> 3) & 0x01010101u) * 15));
+    a += a >> 8;
+    a += a >> 16;
+    m.path_seg_offset = a & 0xff;
+    m.path_ix = __popc(tag_word & 0x10101010u);
+    m.style_ix = __popc(tag_word & 0x40404040u);
+    return m;
+}
+__device__ __forceinline__ GGDrawMonoid draw_monoid_new(uint32_t tag) {   // draw_leaf.go:29-41
+    GGDrawMonoid m;
+    m.path_ix = tag != GG_DRAWTAG_NOP ? 1u : 0u;
+    m.clip_ix = tag & 1u;
+    m.scene_offset = (tag >> 2) & 0x7u;
+    m.info_offset = (tag >> 6) & 0xfu;
+    return m;
+}
+
+struct LoadTagMonoid {
+    const uint32_t* tags;
+    __device__ GGPathMonoid operator()(uint32_t i) const { return path_monoid_new(tags[i]); }
+};
+struct StoreTagMonoid {
+    GGPathMonoid* out;
+    __device__ void operator()(uint32_t i, const GGPathMonoid& ex, const GGPathMonoid&) const { out[i] = ex; }
+};
+struct LoadDrawMonoid {
+    const uint32_t* tags;
+    __device__ GGDrawMonoid operator()(uint32_t i) const { return draw_monoid_new(tags[i]); }
+};
+struct StoreDrawMonoid {
+    GGDrawMonoid* out;
+    __device__ void operator()(uint32_t i, const GGDrawMonoid& ex, const GGDrawMonoid&) const { out[i] = ex; }
+};
+
+// draw_leaf.go:112-150 (info + clip inputs) fused with the clip_leaf.go:27-56 fix-up. The
+// Begin/End matching itself is resolved while the host packs the scene (clip aux words:
+// [2d] = enclosing BeginClip or -1, [2d+1] = matching End (for Begin) / Begin (for End)).
+__global__ void draw_leaf_kernel(GGConfig cfg, const uint32_t* __restrict__ scene, GGDrawMonoid* dm,
+                                 uint32_t* info, GGClipInp* clip_inps, GGDrawRec* recs) {
+    for (uint32_t d = blockIdx.x * blockDim.x + threadIdx.x; d < cfg.n_draws; d += gridDim.x * blockDim.x) {
+        uint32_t tag = scene[cfg.draw_tag_base + d];
+        GGDrawMonoid m = dm[d];
+        int32_t parent = (int32_t)scene[cfg.clip_parent_base + 2 * d];
+        uint32_t link = scene[cfg.clip_parent_base + 2 * d + 1];
+        GGDrawRec r; r.tag = tag; r.parent = parent; r.a = 0; r.b = 0;
+        if (tag == GG_DRAWTAG_COLOR) {
+            uint32_t rgba = scene[cfg.draw_data_base + m.scene_offset];
+            info[m.info_offset] = rgba;
+            r.a = rgba;
+            // fill rule: style word of this path (coarse.go:683-705 indexes styles by path_ix;
+            // our encoder emits one style per path marker so the lookup is exact)
+            r.b = (scene[cfg.style_base + m.path_ix] & 0x02u) ? 1u : 0u;
+        } else if (tag == GG_DRAWTAG_BEGIN_CLIP) {
+            if (m.clip_ix < cfg.n_clips) { clip_inps[m.clip_ix].ix = d; clip_inps[m.clip_ix].path_ix = (int32_t)m.path_ix; }
+            r.a = link;
+        } else if (tag == GG_DRAWTAG_END_CLIP) {
+            if (m.clip_ix < cfg.n_clips) { clip_inps[m.clip_ix].ix = d; clip_inps[m.clip_ix].path_ix = ~(int32_t)d; }
+            if (link < cfg.n_draws) {
+                GGDrawMonoid bm = dm[link];          // BeginClip monoids are never rewritten
+                m.path_ix = bm.path_ix;              // clip_leaf.go:48-51
+                m.scene_offset = bm.scene_offset;
+                dm[d] = m;
+                r.parent = (int32_t)link;
+                r.a = scene[cfg.draw_data_base + bm.scene_offset];
+                r.b = scene[cfg.draw_data_base + bm.scene_offset + 1];
+            }
+        }
+        recs[d] = r;
+    }
+}
+
+// ------------------------------------------------------------------ flatten
+struct CurveIn { V2 p0, p1, p2, p3; uint32_t path_ix; uint32_t kind; };   // kind: 0 none, 1 line, 3 cubic
+
+__device__ __forceinline__ V2 xform(const float* t, float x, float y) {   // scene/encoding.go:348-350
+    return mk(t[0] * x + t[1] * y + t[2], t[3] * x + t[4] * y + t[5]);
+}
+
+__device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restrict__ scene,
+                                  const GGPathMonoid* __restrict__ tag_monoids, uint32_t i, CurveIn* c) {
+    uint32_t w = scene[cfg.path_tag_base + (i >> 2)];
+    uint32_t sh = (i & 3u) * 8u;
+    uint32_t tag = (w >> sh) & 0xffu;
+    uint32_t seg = tag & 3u;
+    if (seg == 0) return false;
+    GGPathMonoid m = ScanTraits<GGPathMonoid>::combine(tag_monoids[i >> 2], path_monoid_new(w & ((1u << sh) - 1u)));
+    const float* data = reinterpret_cast<const float*>(scene + cfg.path_data_base) + m.path_seg_offset;
+    float t[6] = {1, 0, 0, 0, 1, 0};
+    if (m.trans_ix > 0) {
+        const float* tp = reinterpret_cast<const float*>(scene + cfg.transform_base) + 6 * (m.trans_ix - 1);
+#pragma unroll
+        for (int k = 0; k < 6; k++) t[k] = tp[k];
+    }
+    c->path_ix = m.path_ix;
+    V2 a = xform(t, data[-2], data[-1]);
+    if (seg == 1) {
+        V2 b = xform(t, data[0], data[1]);
+        c->p0 = a; c->p3 = b; c->kind = 1;
+    } else if (seg == 2) {   // quad -> cubic, path_convert.go:60-72
+        V2 ctrl = xform(t, data[0], data[1]);
+        V2 end = xform(t, data[2], data[3]);
+        const float k = (float)(2.0 / 3.0);
+        c->p0 = a;
+        c->p1 = mk(a.x + k * (ctrl.x - a.x), a.y + k * (ctrl.y - a.y));
+        c->p2 = mk(end.x + k * (ctrl.x - end.x), end.y + k * (ctrl.y - end.y));
+        c->p3 = end; c->kind = 3;
+    } else {
+        c->p0 = a;
+        c->p1 = xform(t, data[0], data[1]);
+        c->p2 = xform(t, data[2], data[3]);
+        c->p3 = xform(t, data[4], data[5]);
+        c->kind = 3;
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(128) flatten_count_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                            const GGPathMonoid* __restrict__ tag_monoids, uint32_t* line_count) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_tag_bytes; i += gridDim.x * blockDim.x) {
+        CurveIn c;
+        uint32_t n = 0;
+        if (load_curve(cfg, scene, tag_monoids, i, &c)) {
+            if (c.kind == 1) n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
+            else n = flatten_cubic<false>(c.p0, c.p1, c.p2, c.p3, c.path_ix, nullptr, 0, nullptr);
+        }
+        line_count[i] = n;
+    }
+}
+
+__global__ void __launch_bounds__(128) flatten_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                           const GGPathMonoid* __restrict__ tag_monoids,
+                                                           const uint32_t* __restrict__ line_count, const uint32_t* __restrict__ line_off,
+                                                           GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_tag_bytes; i += gridDim.x * blockDim.x) {
+        uint32_t n = line_count[i];
+        if (n == 0) continue;
+        uint32_t off = line_off[i];
+        if (off + n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
+        CurveIn c;
+        load_curve(cfg, scene, tag_monoids, i, &c);
+        float bb[4] = {c.p0.x, c.p0.y, c.p0.x, c.p0.y};
+        if (c.kind == 1) {
+            GGLine l; l.path_ix = c.path_ix; l.p0x = c.p0.x; l.p0y = c.p0.y; l.p1x = c.p3.x; l.p1y = c.p3.y;
+            lines[off] = l;
+            bb[0] = fminf(bb[0], c.p3.x); bb[1] = fminf(bb[1], c.p3.y);
+            bb[2] = fmaxf(bb[2], c.p3.x); bb[3] = fmaxf(bb[3], c.p3.y);
+        } else {
+            flatten_cubic<true>(c.p0, c.p1, c.p2, c.p3, c.path_ix, lines + off, n, bb);
+        }
+        uint32_t* pb = path_bbox_ord + 4 * (size_t)c.path_ix;
+        atomicMin(pb + 0, f_ord(bb[0]));
+        atomicMin(pb + 1, f_ord(bb[1]));
+        atomicMax(pb + 2, f_ord(bb[2]));
+        atomicMax(pb + 3, f_ord(bb[3]));
+    }
+}
+
+__global__ void init_frame_kernel(GGConfig cfg, uint32_t* path_bbox_ord, GGBump* bump) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_paths; i += gridDim.x * blockDim.x) {
+        uint32_t* pb = path_bbox_ord + 4 * (size_t)i;
+        pb[0] = 0xffffffffu; pb[1] = 0xffffffffu; pb[2] = 0u; pb[3] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(GGBump) / 4) reinterpret_cast<uint32_t*>(bump)[threadIdx.x] = 0;
+}
+
+struct LoadU32 {
+    const uint32_t* p;
+    __device__ uint32_t operator()(uint32_t i) const { return p[i]; }
+};
+struct StoreU32Ex {
+    uint32_t* p;
+    __device__ void operator()(uint32_t i, const uint32_t& ex, const uint32_t&) const { p[i] = ex; }
+};
+
+// ------------------------------------------------------------------ path setup (coarse.go:169-223)
+// Tile bbox of a path from the order-mapped float bbox, clamped to the canvas and to this
+// device's band of tile rows. Off-canvas / untouched paths come out empty (0 tiles); the
+// reference's uint32 wrap-around for those cases is deliberately not reproduced.
+__device__ inline void path_tile_bbox(const GGConfig& cfg, const uint32_t* pb, uint32_t bbox[4]) {
+    bbox[0] = bbox[1] = bbox[2] = bbox[3] = 0;
+    if (pb[0] == 0xffffffffu && pb[2] == 0u) return;   // no line touched this path
+    float min_x = f_unord(pb[0]), min_y = f_unord(pb[1]), max_x = f_unord(pb[2]), max_y = f_unord(pb[3]);
+    if (!(min_x <= max_x) || !(min_y <= max_y)) return;
+    if (min_x < 0) min_x = 0;
+    if (min_y < 0) min_y = 0;
+    if (max_x > (float)cfg.width) max_x = (float)cfg.width;
+    if (max_y > (float)cfg.height) max_y = (float)cfg.height;
+    if (max_x < min_x || max_y < min_y) return;          // entirely off-canvas
+    int64_t x0 = (int64_t)floor((double)(min_x / (float)GG_TILE_W));
+    int64_t y0 = (int64_t)floor((double)(min_y / (float)GG_TILE_H));
+    int64_t x1 = (int64_t)ceil((double)(max_x / (float)GG_TILE_W));
+    int64_t y1 = (int64_t)ceil((double)(max_y / (float)GG_TILE_H));
+    if (x1 > (int64_t)cfg.width_in_tiles) x1 = cfg.width_in_tiles;
+    if (y1 > (int64_t)cfg.height_in_tiles) y1 = cfg.height_in_tiles;
+    // band clamp (multi-GPU): rows outside [band_y0, band_y1) belong to another device
+    if (y0 < (int64_t)cfg.band_y0) y0 = cfg.band_y0;
+    if (y1 > (int64_t)cfg.band_y1) y1 = cfg.band_y1;
+    if (x1 <= x0 || y1 <= y0) {
+        // keep the reference's bbox for degenerate-but-on-canvas paths (e.g. a vertical
+        // hairline on a tile boundary) when it is representable; tile count is 0 either way
+        if (x1 >= x0 && y1 >= y0) { bbox[0] = (uint32_t)x0; bbox[1] = (uint32_t)y0; bbox[2] = (uint32_t)x1; bbox[3] = (uint32_t)y1; }
+        return;
+    }
+    bbox[0] = (uint32_t)x0; bbox[1] = (uint32_t)y0; bbox[2] = (uint32_t)x1; bbox[3] = (uint32_t)y1;
+}
+struct LoadPathTiles {   // packed: tiles in the low word, rows in the high word
+    GGConfig cfg; const uint32_t* path_bbox_ord;
+    __device__ unsigned long long operator()(uint32_t p) const {
+        uint32_t bb[4];
+        path_tile_bbox(cfg, path_bbox_ord + 4 * (size_t)p, bb);
+        unsigned long long w = bb[2] - bb[0], h = bb[3] - bb[1];
+        unsigned long long t = w * h;
+        return t == 0 ? 0ull : (t | (h << 32));
+    }
+};
+struct StorePath {
+    GGConfig cfg; const uint32_t* path_bbox_ord; GGPath* paths; uint32_t* path_row_off;
+    __device__ void operator()(uint32_t p, const unsigned long long& ex, const unsigned long long&) const {
+        GGPath o;
+        path_tile_bbox(cfg, path_bbox_ord + 4 * (size_t)p, o.bbox);
+        o.tiles = (uint32_t)ex;
+        paths[p] = o;
+        path_row_off[p] = (uint32_t)(ex >> 32);
+    }
+};
+
+__global__ void zero_tiles_kernel(GGConfig cfg, GGTile* tiles, GGBump* bump) {
+    uint32_t n = bump->path_tiles;
+    if (n > cfg.tiles_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, GG_FAIL_TILES); n = cfg.tiles_cap; }
+    uint2* t = reinterpret_cast<uint2*>(tiles);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) t[i] = make_uint2(0, 0);
+}
+
+// ------------------------------------------------------------------ DDA set-up shared by path_count / path_tiling
+struct DDA {
+    V2 xy0, xy1, s0, s1;
+    bool is_down, is_positive_slope;
+    uint32_t count_x, count;
+    float dx, dy, a, b, sign, x0, y0;
+};
+__device__ __forceinline__ void dda_setup(const GGLine& l, DDA& d) {   // path_count.go:19-39
+    const float TILE_SCALE = 1.0f / 16.0f;
+    V2 p0 = mk(l.p0x, l.p0y), p1 = mk(l.p1x, l.p1y);
+    d.is_down = p1.y >= p0.y;
+    if (d.is_down) { d.xy0 = p0; d.xy1 = p1; } else { d.xy0 = p1; d.xy1 = p0; }
+    d.s0 = vmul(d.xy0, TILE_SCALE);
+    d.s1 = vmul(d.xy1, TILE_SCALE);
+    d.count_x = span_u(d.s0.x, d.s1.x) - 1;
+    d.count = d.count_x + span_u(d.s0.y, d.s1.y);
+    d.dx = fabsf(d.s1.x - d.s0.x);
+    d.dy = d.s1.y - d.s0.y;
+}
+__device__ __forceinline__ void dda_finish(DDA& d) {   // path_count.go:40-69
+    const float ONE_MINUS_ULP = 0.99999994f, ROBUST_EPSILON = 2e-7f;
+    float idxdy = 1.0f / (d.dx + d.dy);
+    float a = d.dx * idxdy;
+    d.is_positive_slope = d.s1.x >= d.s0.x;
+    d.sign = d.is_positive_slope ? 1.0f : -1.0f;
+    float xt0 = f_floor(d.s0.x * d.sign);
+    float c = d.s0.x * d.sign - xt0;
+    d.y0 = f_floor(d.s0.y);
+    float ytop = (d.s0.y == d.s1.y) ? f_ceil(d.s0.y) : d.y0 + 1.0f;
+    d.b = f_min((d.dy * c + d.dx * (ytop - d.s0.y)) * idxdy, ONE_MINUS_ULP);
+    float robust_err = f_floor(a * (float)(d.count - 1) + d.b) - (float)d.count_x;
+    if (robust_err != 0.0f) a -= copysignf(ROBUST_EPSILON, robust_err);
+    d.a = a;
+    d.x0 = d.is_positive_slope ? xt0 * d.sign : xt0 * d.sign - 1.0f;
+}
+
+// path_count.go:11-205. One thread per line; tile counters and backdrops are global atomics
+// (the slot a segment gets inside its tile is the value returned by the count atomic).
+__global__ void __launch_bounds__(256) path_count_kernel(GGConfig cfg, const GGLine* __restrict__ lines, const GGPath* __restrict__ paths,
+                                                         GGTile* tiles, GGSegCount* seg_counts, GGBump* bump) {
+    uint32_t n_lines = min(bump->lines, cfg.lines_cap);
+    for (uint32_t line_ix = blockIdx.x * blockDim.x + threadIdx.x; line_ix < n_lines; line_ix += gridDim.x * blockDim.x) {
+        GGLine line = lines[line_ix];
+        DDA d; dda_setup(line, d);
+        if (d.dx + d.dy == 0.0f) continue;
+        if (d.dy == 0.0f && f_floor(d.s0.y) == d.s0.y) continue;
+        dda_finish(d);
+        const float a = d.a, b = d.b, sign = d.sign, x0 = d.x0, y0 = d.y0;
+        const V2 s0 = d.s0, s1 = d.s1;
+        GGPath path = paths[line.path_ix];
+        int32_t bx0 = (int32_t)path.bbox[0], by0 = (int32_t)path.bbox[1], bx1 = (int32_t)path.bbox[2], by1 = (int32_t)path.bbox[3];
+        float xmin = f_min(s0.x, s1.x);
+        int32_t stride = bx1 - bx0;
+        if (s0.y >= (float)by1 || s1.y < (float)by0 || xmin >= (float)bx1 || stride == 0) continue;
+        if (by1 <= by0) continue;   // empty bbox (band-clamped away)
+        uint32_t imin = 0;
+        if (s0.y < (float)by0) {
+            float iminf = f_round(((float)by0 - y0 + b - a) / (1.0f - a)) - 1.0f;
+            if (y0 + iminf - f_floor(a * iminf + b) < (float)by0) iminf += 1.0f;
+            imin = f2u(iminf);
+        }
+        uint32_t imax = d.count;
+        if (s1.y > (float)by1) {
+            float imaxf = f_round(((float)by1 - y0 + b - a) / (1.0f - a)) - 1.0f;
+            if (y0 + imaxf - f_floor(a * imaxf + b) < (float)by1) imaxf += 1.0f;
+            imax = f2u(imaxf);
+        }
+        int32_t delta = d.is_down ? -1 : 1;
+        int32_t ymin = 0, ymax = 0;
+        if (f_max(s0.x, s1.x) < (float)bx0) {
+            ymin = f2i(f_ceil(s0.y));
+            ymax = f2i(f_ceil(s1.y));
+            imax = imin;
+        } else {
+            float fudge = d.is_positive_slope ? 0.0f : 1.0f;
+            if (xmin < (float)bx0) {
+                float f = f_round((sign * ((float)bx0 - x0) - b + fudge) / a);
+                if ((x0 + sign * f_floor(a * f + b) < (float)bx0) == d.is_positive_slope) f += 1.0f;
+                int32_t ynext = f2i(y0 + f - f_floor(a * f + b) + 1.0f);
+                if (d.is_positive_slope) {
+                    if (f2u(f) > imin) {
+                        float y_off = (y0 != s0.y) ? 1.0f : 0.0f;
+                        ymin = f2i(y0 + y_off);
+                        ymax = ynext;
+                        imin = f2u(f);
+                    }
+                } else if (f2u(f) < imax) {
+                    ymin = ynext;
+                    ymax = f2i(f_ceil(s1.y));
+                    imax = f2u(f);
+                }
+            }
+            if (f_max(s0.x, s1.x) > (float)bx1) {
+                float f = f_round((sign * ((float)bx1 - x0) - b + fudge) / a);
+                if ((x0 + sign * f_floor(a * f + b) < (float)bx1) == d.is_positive_slope) f += 1.0f;
+                if (d.is_positive_slope) imax = min(imax, f2u(f));
+                else imin = max(imin, f2u(f));
+            }
+        }
+        imax = max(imin, imax);
+        ymin = max(ymin, by0);
+        ymax = min(ymax, by1);
+        for (int32_t y = ymin; y < ymax; y++) {
+            int32_t base = (int32_t)path.tiles + (y - by0) * stride;
+            atomicAdd(&tiles[base].backdrop, delta);
+        }
+        float last_z = f_floor(a * (float)(imin - 1) + b);
+        uint32_t n_seg = imax - imin;
+        uint32_t seg_base = 0;
+        bool store = false;
+        if (n_seg) {
+            seg_base = atomicAdd(&bump->seg_counts, n_seg);
+            store = (uint64_t)seg_base + n_seg <= cfg.seg_counts_cap;
+            if (!store) atomicOr(&bump->failed, GG_FAIL_SEGCOUNTS);
+        }
+        for (uint32_t i = imin; i < imax; i++) {
+            float zf = a * (float)i + b;
+            float z = f_floor(zf);
+            int32_t y = f2i(y0 + (float)i - z);
+            int32_t x = f2i(x0 + sign * z);
+            int32_t base = (int32_t)path.tiles + (y - by0) * stride - bx0;
+            bool top_edge = (i == 0) ? (y0 == s0.y) : (last_z == z);
+            if (top_edge && x + 1 < bx1) {
+                int32_t x_bump = max(x + 1, bx0);
+                atomicAdd(&tiles[base + x_bump].backdrop, delta);
+            }
+            uint32_t seg_within_slice = atomicAdd(&tiles[base + x].seg_count, 1u);
+            if (store) {
+                GGSegCount sc; sc.line_ix = line_ix; sc.counts = (seg_within_slice << 16) | i;
+                seg_counts[seg_base + i - imin] = sc;
+            }
+            last_z = z;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backdrop prefix sum + tile-hit pass
+// Rows of all per-path tile rectangles are enumerated flat; a group of 8 lanes owns one row
+// and walks it 8 tiles at a time with a shuffle prefix sum (coarse.go:291-299, backdrop.wgsl).
+// PASS 0: write the summed backdrop back and add this path's contribution to the per-tile
+//         hit/word histogram of coarse. PASS 1: scatter draw indices into the per-tile hit lists.
+__device__ __forceinline__ uint32_t find_row_path(const uint32_t* __restrict__ path_row_off, uint32_t n_paths, uint32_t row) {
+    uint32_t lo = 0, hi = n_paths;   // largest p with path_row_off[p] <= row
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (path_row_off[mid] <= row) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+template <int PASS>
+__global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint32_t* __restrict__ scene, const GGPath* __restrict__ paths,
+                                                        const uint32_t* __restrict__ path_row_off, GGTile* tiles,
+                                                        const GGDrawRec* __restrict__ recs,
+                                                        unsigned long long* tile_hits, const uint32_t* __restrict__ hit_off,
+                                                        uint32_t* hit_cursor, uint32_t* hits, GGBump* bump) {
+    cg::thread_block_tile<8> g = cg::tiled_partition<8>(cg::this_thread_block());
+    const uint32_t n_rows = min(bump->path_rows, cfg.rows_cap);
+    if (bump->path_tiles > cfg.tiles_cap) return;
+    const uint32_t groups = gridDim.x * blockDim.x / 8;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / 8; row < n_rows; row += groups) {
+        uint32_t p = find_row_path(path_row_off, cfg.n_paths, row);
+        GGPath path = paths[p];
+        uint32_t bw = path.bbox[2] - path.bbox[0];
+        uint32_t y = row - path_row_off[p];
+        uint32_t base = path.tiles + y * bw;
+        uint32_t gy = path.bbox[1] + y - cfg.band_y0;
+        uint32_t tag = scene[cfg.draw_tag_base + p];   // one path marker per draw object: path p <-> draw p
+        int32_t carry = 0;
+        for (uint32_t x0 = 0; x0 < bw; x0 += 8) {
+            uint32_t x = x0 + g.thread_rank();
+            GGTile t; t.backdrop = 0; t.seg_count = 0;
+            if (x < bw) t = tiles[base + x];
+            int32_t v = t.backdrop;
+            if (PASS == 0) {
+#pragma unroll
+                for (int dlt = 1; dlt < 8; dlt <<= 1) {
+                    int32_t o = g.shfl_up(v, dlt);
+                    if ((int)g.thread_rank() >= dlt) v += o;
+                }
+                v += carry;
+                carry = g.shfl(v, 7);
+            }
+            if (x < bw) {
+                if (PASS == 0 && v != t.backdrop) tiles[base + x].backdrop = v;
+                if (t.seg_count != 0 || v != 0) {
+                    uint32_t T = gy * cfg.width_in_tiles + path.bbox[0] + x;
+                    if (PASS == 0) {
+                        unsigned long long w;
+                        if (tag == GG_DRAWTAG_COLOR) w = 1ull | ((t.seg_count ? 6ull : 3ull) << 32);
+                        else if (tag == GG_DRAWTAG_BEGIN_CLIP) w = 2ull | ((1ull + (t.seg_count ? 7ull : 4ull)) << 32);
+                        else w = 0;
+                        if (w) atomicAdd(&tile_hits[T], w);
+                    } else {
+                        if (tag == GG_DRAWTAG_COLOR) {
+                            uint32_t slot = hit_off[T] + atomicAdd(&hit_cursor[T], 1u);
+                            if (slot < cfg.hits_cap) hits[slot] = p;
+                        } else if (tag == GG_DRAWTAG_BEGIN_CLIP) {
+                            uint32_t slot = hit_off[T] + atomicAdd(&hit_cursor[T], 2u);
+                            if (slot + 1 < cfg.hits_cap) { hits[slot] = p; hits[slot + 1] = recs[p].a; }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+struct LoadTileCount {
+    const GGTile* tiles;
+    __device__ uint32_t operator()(uint32_t i) const { return tiles[i].seg_count; }
+};
+struct LoadTileHits {   // + 2 words per tile: blend-offset word 0 and the CmdEnd terminator (ptcl.go:72-78, coarse.go:148-151)
+    const unsigned long long* h;
+    __device__ unsigned long long operator()(uint32_t i) const { return h[i] + (2ull << 32); }
+};
+struct StoreTileHits {
+    uint32_t* hit_off; uint32_t* hit_cnt; uint32_t* ptcl_off; uint32_t* hit_cursor; uint32_t* spill_off;
+    __device__ void operator()(uint32_t i, const unsigned long long& ex, const unsigned long long& v) const {
+        hit_off[i] = (uint32_t)ex; hit_cnt[i] = (uint32_t)v; ptcl_off[i] = (uint32_t)(ex >> 32);
+        hit_cursor[i] = 0; spill_off[i] = 0xffffffffu;
+    }
+};
+
+// ------------------------------------------------------------------ path_tiling.go:11-199
+__global__ void __launch_bounds__(256) path_tiling_kernel(GGConfig cfg, const GGSegCount* __restrict__ seg_counts, const GGLine* __restrict__ lines,
+                                                          const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
+                                                          const uint32_t* __restrict__ seg_start, GGSegment* segments, GGBump* bump) {
+    uint32_t n = min(bump->seg_counts, cfg.seg_counts_cap);
+    if (bump->segments > cfg.segments_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, GG_FAIL_SEGMENTS); return; }
+    for (uint32_t seg_ix = blockIdx.x * blockDim.x + threadIdx.x; seg_ix < n; seg_ix += gridDim.x * blockDim.x) {
+        GGSegCount sc = seg_counts[seg_ix];
+        GGLine line = lines[sc.line_ix];
+        uint32_t seg_within_slice = sc.counts >> 16;
+        uint32_t seg_within_line = sc.counts & 0xffffu;
+        DDA d; dda_setup(line, d); dda_finish(d);
+        const float a = d.a, b = d.b, sign = d.sign, x0 = d.x0, y0 = d.y0;
+        V2 xy0 = d.xy0, xy1 = d.xy1;
+        float z = f_floor(a * (float)seg_within_line + b);
+        int32_t x = f2i(x0) + f2i(sign * z);                 // split truncation, path_tiling.go:74
+        int32_t y = f2i(y0 + (float)seg_within_line - z);
+        GGPath path = paths[line.path_ix];
+        int32_t bx0 = (int32_t)path.bbox[0], by0 = (int32_t)path.bbox[1], bx1 = (int32_t)path.bbox[2];
+        int32_t stride = bx1 - bx0;
+        int32_t tile_ix = (int32_t)path.tiles + (y - by0) * stride + x - bx0;
+        if (tiles[tile_ix].seg_count == 0) continue;
+        uint32_t out_ix = seg_start[tile_ix] + seg_within_slice;
+        const float TW = (float)GG_TILE_W, TH = (float)GG_TILE_H;
+        V2 tile_xy = mk((float)x * TW, (float)y * TH);
+        V2 tile_xy1 = mk(tile_xy.x + TW, tile_xy.y + TH);
+        if (seg_within_line > 0) {
+            float z_prev = f_floor(a * (float)(seg_within_line - 1) + b);
+            if (z == z_prev) {
+                float xt = xy0.x + (xy1.x - xy0.x) * (tile_xy.y - xy0.y) / (xy1.y - xy0.y);
+                xt = f_clamp(xt, tile_xy.x + 1e-3f, tile_xy1.x);
+                xy0 = mk(xt, tile_xy.y);
+            } else {
+                float x_clip = d.is_positive_slope ? tile_xy.x : tile_xy1.x;
+                float yt = xy0.y + (xy1.y - xy0.y) * (x_clip - xy0.x) / (xy1.x - xy0.x);
+                yt = f_clamp(yt, tile_xy.y + 1e-3f, tile_xy1.y);
+                xy0 = mk(x_clip, yt);
+            }
+        }
+        if (seg_within_line < d.count - 1) {
+            float z_next = f_floor(a * (float)(seg_within_line + 1) + b);
+            if (z == z_next) {
+                float xt = xy0.x + (xy1.x - xy0.x) * (tile_xy1.y - xy0.y) / (xy1.y - xy0.y);
+                xt = f_clamp(xt, tile_xy.x + 1e-3f, tile_xy1.x);
+                xy1 = mk(xt, tile_xy1.y);
+            } else {
+                float x_clip = d.is_positive_slope ? tile_xy1.x : tile_xy.x;
+                float yt = xy0.y + (xy1.y - xy0.y) * (x_clip - xy0.x) / (xy1.x - xy0.x);
+                yt = f_clamp(yt, tile_xy.y + 1e-3f, tile_xy1.y);
+                xy1 = mk(x_clip, yt);
+            }
+        }
+        float y_edge = 1e9f;
+        V2 p0o = vsub(xy0, tile_xy), p1o = vsub(xy1, tile_xy);
+        const float epsilon = 1e-6f;
+        if (p0o.x == 0.0f) {
+            if (p1o.x == 0.0f) {
+                p0o.x = epsilon;
+                if (p0o.y == 0.0f) { p1o.x = epsilon; p1o.y = TH; }
+                else { p1o.x = 2.0f * epsilon; p1o.y = p0o.y; }
+            } else if (p0o.y == 0.0f) {
+                p0o.x = epsilon;
+            } else {
+                y_edge = p0o.y;
+            }
+        } else if (p1o.x == 0.0f) {
+            if (p1o.y == 0.0f) p1o.x = epsilon; else y_edge = p1o.y;
+        }
+        if (p0o.x == f_floor(p0o.x) && p0o.x != 0.0f) p0o.x -= epsilon;
+        if (p1o.x == f_floor(p1o.x) && p1o.x != 0.0f) p1o.x -= epsilon;
+        if (!d.is_down) { V2 t = p0o; p0o = p1o; p1o = t; }
+        if (out_ix < cfg.segments_cap) {
+            GGSegment s; s.p0x = p0o.x; s.p0y = p0o.y; s.p1x = p1o.x; s.p1y = p1o.y; s.y_edge = y_edge;
+            segments[out_ix] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ coarse (coarse.go:322-625)
+// One warp per tile. The tile's hit list (draw indices, scattered by atomics) is sorted in
+// shared memory so commands come out in scene order; the clip state machine of the
+// reference (clipDepth / clipZeroDepth) collapses to a single "innermost emitted clip"
+// register because a draw is live in a tile iff every enclosing clip emitted there.
+#define COARSE_WARPS 8
+#define COARSE_CAP 1024   // hits per tile sorted in shared memory; longer lists are sorted in place by lane 0
+
+__device__ inline void heap_sort_global(uint32_t* a, uint32_t n) {
+    for (uint32_t start = n / 2; start-- > 0;) {
+        uint32_t root = start;
+        for (;;) { uint32_t c = 2 * root + 1; if (c >= n) break; if (c + 1 < n && a[c] < a[c + 1]) c++; if (a[root] >= a[c]) break; uint32_t t = a[root]; a[root] = a[c]; a[c] = t; root = c; }
+    }
+    for (uint32_t end = n; end-- > 1;) {
+        uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+        uint32_t root = 0;
+        for (;;) { uint32_t c = 2 * root + 1; if (c >= end) break; if (c + 1 < end && a[c] < a[c + 1]) c++; if (a[root] >= a[c]) break; uint32_t t2 = a[root]; a[root] = a[c]; a[c] = t2; root = c; }
+    }
+}
+
+__global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg, const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
+                                                                   const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
+                                                                   const GGDrawMonoid* __restrict__ dm,
+                                                                   const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ hit_cnt,
+                                                                   uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl,
+                                                                   uint32_t* spill_off, GGBump* bump) {
+    __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
+    const bool overflow = bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap;
+    if (overflow) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, (bump->hits > cfg.hits_cap ? GG_FAIL_HITS : 0u) | (bump->ptcl_words > cfg.ptcl_cap ? GG_FAIL_PTCL : 0u)); return; }
+    uint32_t* sb = sort_buf[warp];
+    for (uint32_t T = blockIdx.x * COARSE_WARPS + warp; T < n_tiles; T += gridDim.x * COARSE_WARPS) {
+        const uint32_t n = hit_cnt[T];
+        uint32_t* list = hits + hit_off[T];
+        uint32_t pos = ptcl_off[T];
+        if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
+        pos += 1;
+        if (n == 0) { if (lane == 0) ptcl[pos] = GG_CMD_END; continue; }
+        const uint32_t* sorted;
+        if (n <= COARSE_CAP) {
+            uint32_t np2 = 32; while (np2 < n) np2 <<= 1;
+            for (uint32_t i = lane; i < np2; i += 32) sb[i] = i < n ? list[i] : 0xffffffffu;
+            __syncwarp();
+            for (uint32_t k = 2; k <= np2; k <<= 1)
+                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+                    for (uint32_t i = lane; i < np2; i += 32) {
+                        uint32_t ixj = i ^ j;
+                        if (ixj > i) {
+                            uint32_t a = sb[i], b = sb[ixj];
+                            bool up = (i & k) == 0;
+                            if ((a > b) == up) { sb[i] = b; sb[ixj] = a; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            sorted = sb;
+        } else {
+            if (lane == 0) heap_sort_global(list, n);
+            __syncwarp();
+            sorted = list;
+        }
+        const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
+        int32_t top = -1;
+        uint32_t depth = 0, max_depth = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            uint32_t i = base + lane;
+            // parallel gather of everything the state machine and the emitters need
+            GGDrawRec r; r.tag = 0; r.parent = -1; r.a = 0; r.b = 0;
+            uint32_t d = 0; GGTile t; t.backdrop = 0; t.seg_count = 0; uint32_t sstart = 0; int32_t begin_parent = -1;
+            if (i < n) {
+                d = sorted[i];
+                r = recs[d];
+                GGPath path = paths[dm[d].path_ix];
+                uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
+                t = tiles[ti];
+                sstart = seg_start[ti];
+                if (r.tag == GG_DRAWTAG_END_CLIP) begin_parent = recs[r.parent].parent;
+            }
+            // sequential, warp-uniform replay of the clip state over the (up to) 32 gathered hits
+            bool emit = false;
+            uint32_t cnt = min(32u, n - base);
+            for (uint32_t j = 0; j < cnt; j++) {
+                uint32_t jt = __shfl_sync(0xffffffffu, r.tag, j);
+                int32_t jp = __shfl_sync(0xffffffffu, r.parent, j);
+                uint32_t jd = __shfl_sync(0xffffffffu, d, j);
+                int32_t jbp = __shfl_sync(0xffffffffu, begin_parent, j);
+                bool e = false;
+                if (jt == GG_DRAWTAG_COLOR) {
+                    e = jp == top;
+                } else if (jt == GG_DRAWTAG_BEGIN_CLIP) {
+                    if (jp == top) { e = true; top = (int32_t)jd; depth++; max_depth = max(max_depth, depth); }
+                } else if (jt == GG_DRAWTAG_END_CLIP) {
+                    if (top == jp) { e = true; top = jbp; depth--; }   // jp == index of the matching BeginClip
+                }
+                if (lane == j) emit = e;
+            }
+            // words per hit, warp exclusive scan, parallel emission
+            uint32_t nw = 0;
+            if (emit) {
+                if (r.tag == GG_DRAWTAG_COLOR) nw = t.seg_count ? 6u : 3u;
+                else if (r.tag == GG_DRAWTAG_BEGIN_CLIP) nw = 1u;
+                else nw = t.seg_count ? 7u : 4u;
+            }
+            uint32_t inc = nw;
+#pragma unroll
+            for (int dl = 1; dl < 32; dl <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, dl); if ((int)lane >= dl) inc += o; }
+            uint32_t o = pos + inc - nw;
+            if (emit) {
+                if (r.tag == GG_DRAWTAG_COLOR) {
+                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | r.b; ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
+                    else ptcl[o++] = GG_CMD_SOLID;
+                    ptcl[o++] = GG_CMD_COLOR; ptcl[o++] = r.a;
+                } else if (r.tag == GG_DRAWTAG_BEGIN_CLIP) {
+                    ptcl[o++] = GG_CMD_BEGIN_CLIP;
+                } else {
+                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1); ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
+                    else ptcl[o++] = GG_CMD_SOLID;
+                    ptcl[o++] = GG_CMD_END_CLIP; ptcl[o++] = r.a; ptcl[o++] = r.b;
+                }
+            }
+            pos += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            ptcl[pos] = GG_CMD_END;
+            if (max_depth > GG_BLEND_STACK_SPLIT) {
+                uint32_t lv = max_depth - GG_BLEND_STACK_SPLIT;
+                uint32_t so = atomicAdd(&bump->spill, lv);
+                if (so + lv > cfg.spill_cap) atomicOr(&bump->failed, GG_FAIL_SPILL); else spill_off[T] = so;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ launchers
+void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
+    init_frame_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.path_bbox_ord, b.bump);
+    // a3: pathtag scan. n is host-known here; the scan primitive wants it in device memory, so a
+    // constant slot at the tail of the scene buffer carries it (word n_scene_words).
+    const uint32_t* n_tag_words = b.scene + cfg.n_scene_words + 0;
+    const uint32_t* n_draws = b.scene + cfg.n_scene_words + 1;
+    const uint32_t* n_tag_bytes = b.scene + cfg.n_scene_words + 2;
+    const uint32_t* n_paths = b.scene + cfg.n_scene_words + 3;
+    gg_scan<GGPathMonoid>(s, n_tag_words, cfg.n_tag_words, LoadTagMonoid{b.scene + cfg.path_tag_base}, StoreTagMonoid{b.tag_monoids},
+                          (GGPathMonoid*)b.scan_partials, (GGPathMonoid*)nullptr);
+    // a4 + a5: draw scan, draw leaf, clip leaf fix-up
+    gg_scan<GGDrawMonoid>(s, n_draws, cfg.n_draws, LoadDrawMonoid{b.scene + cfg.draw_tag_base}, StoreDrawMonoid{b.draw_monoids},
+                          (GGDrawMonoid*)b.scan_partials, (GGDrawMonoid*)nullptr);
+    draw_leaf_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.scene, b.draw_monoids, b.info, b.clip_inps, b.draw_recs);
+    // a6: flatten (count, scan, emit)
+    flatten_count_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count);
+    gg_scan<uint32_t>(s, n_tag_bytes, cfg.n_tag_bytes, LoadU32{b.line_count}, StoreU32Ex{b.line_off}, (uint32_t*)b.scan_partials, &b.bump->lines);
+    flatten_emit_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
+    // a7: per-path tile bbox + tile / row offsets (one packed scan)
+    gg_scan<unsigned long long>(s, n_paths, cfg.n_paths, LoadPathTiles{cfg, b.path_bbox_ord}, StorePath{cfg, b.path_bbox_ord, b.paths, b.path_row_off},
+                                (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->path_tiles));
+}
+
+void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
+    zero_tiles_kernel<<<GG_GRID(4), 256, 0, s>>>(cfg, b.tiles, b.bump);
+    uint32_t band_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
+    cudaMemsetAsync(b.tile_hits, 0, sizeof(unsigned long long) * band_tiles, s);
+    path_count_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.lines, b.paths, b.tiles, b.seg_counts, b.bump);
+    tile_rows_kernel<0><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, nullptr, nullptr, nullptr, b.bump);
+    gg_scan<uint32_t>(s, &b.bump->path_tiles, cfg.tiles_cap, LoadTileCount{b.tiles}, StoreU32Ex{b.seg_start}, (uint32_t*)b.scan_partials, &b.bump->segments);
+    path_tiling_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.seg_counts, b.lines, b.paths, b.tiles, b.seg_start, b.segments, b.bump);
+}
+
+void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
+    const uint32_t* n_band_tiles = b.scene + cfg.n_scene_words + 4;
+    uint32_t band_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
+    gg_scan<unsigned long long>(s, n_band_tiles, band_tiles, LoadTileHits{b.tile_hits},
+                                StoreTileHits{b.hit_off, b.hit_cnt, b.ptcl_off, b.hit_cursor, b.spill_off},
+                                (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->hits));
+    tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.bump);
+    coarse_kernel<<<GG_GRID(4), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
+                                                           b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl, b.spill_off, b.bump);
+}

@@ -1,0 +1,47 @@
+// gg_b200/csrc/pipeline.cuh -- device buffer table shared by the host API and the stage launchers.
+#pragma once
+#include "common.cuh"
+
+// All device pointers of one context. Capacities live in GGConfig (passed by value to kernels).
+struct GGBuffers {
+    // inputs
+    uint32_t* scene;            // packed scene (tags | path data | draw tags | draw data | transforms | styles | clip aux)
+    // scans
+    GGPathMonoid* tag_monoids;  // [n_tag_words]  exclusive
+    GGDrawMonoid* draw_monoids; // [n_draws]      exclusive (+ clip_leaf fix-up)
+    uint32_t* info;             // [n_draws]      draw_leaf info (packed colours)
+    GGClipInp* clip_inps;       // [n_clips]
+    GGDrawRec* draw_recs;       // [n_draws]
+    // flatten
+    uint32_t* line_count;       // [n_tag_bytes]
+    uint32_t* line_off;         // [n_tag_bytes]
+    GGLine* lines;              // [lines_cap]
+    uint32_t* path_bbox_ord;    // [4*n_paths] order-mapped float min/max
+    // binning
+    GGPath* paths;              // [n_paths]
+    uint32_t* path_row_off;     // [n_paths]
+    GGTile* tiles;              // [tiles_cap]
+    uint32_t* seg_start;        // [tiles_cap]
+    GGSegCount* seg_counts;     // [seg_counts_cap]
+    GGSegment* segments;        // [segments_cap]
+    // coarse
+    unsigned long long* tile_hits;  // [band_tiles] (hits | words<<32) histogram
+    uint32_t* hit_off;          // [band_tiles]
+    uint32_t* hit_cnt;          // [band_tiles]
+    uint32_t* hit_cursor;       // [band_tiles]
+    uint32_t* hits;             // [hits_cap] draw indices
+    uint32_t* ptcl_off;         // [band_tiles]
+    uint32_t* ptcl;             // [ptcl_cap]
+    uint32_t* spill_off;        // [band_tiles] blend spill offsets (tile-levels), 0xffffffff = none
+    float4* spill;              // [spill_cap * 256]
+    // misc
+    GGBump* bump;
+    void* scan_partials;        // GG_SCAN_BLOCKS * 32 bytes
+};
+
+// stage launchers (pipeline.cu)
+void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);   // scans, flatten, path setup
+void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s); // path_count, backdrop, seg alloc, path_tiling
+void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  // hit lists + PTCL
+// fine (fine.cu). dst: RGBA8 premultiplied, row stride in bytes; covers tile rows [band_y0, band_y1).
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s);

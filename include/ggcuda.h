@@ -1,0 +1,133 @@
+/*
+ * ggcuda.h -- C ABI of libggcuda.so, the B200 (sm_100a) scene rasteriser that plugs in
+ * behind gogpu/gg's GPUAccelerator boundary.
+ *
+ * Every entry point is what the Go side's cgo file (accel_cuda.go, build tag `ggcuda`)
+ * binds; INTEGRATION.md shows that binding. Reference interfaces replaced (gogpu/gg):
+ *   gg.GPUAccelerator                      accelerator.go:104-140
+ *   gg.GPURenderTarget                     accelerator.go:61-92
+ *   internal/gpu.VelloAccelerator          vello_accelerator.go:197-386 (accumulate + Flush)
+ *   internal/gpu.VelloComputeDispatcher    vello_compute.go:1112-1225 (9 WGSL passes + readback)
+ *   scene.GPUSceneRenderer / scene.Encoding scene/gpu_renderer.go:73-213, scene/encoding.go:407-444
+ *
+ * Conventions: plain pointers and sizes, no ownership transfer (inputs are copied before the
+ * call returns, as cgo requires), int status (0 = ok, negative = GGCUDA_ERR_*), the message
+ * for the last failure via ggcuda_last_error(). Calls on one context must be serialised by
+ * the caller (the reference accelerator holds one mutex, vello_accelerator.go:37,202); any
+ * OS thread may make them (the library binds its device on every call).
+ */
+#ifndef GGCUDA_H
+#define GGCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define GGCUDA_API __attribute__((visibility("default")))
+#else
+#define GGCUDA_API
+#endif
+
+typedef struct ggcuda_ctx ggcuda_ctx;
+
+enum {
+    GGCUDA_OK = 0,
+    GGCUDA_ERR_CUDA = -1,        /* CUDA runtime failure; maps to a Go error (gg falls back to CPU) */
+    GGCUDA_ERR_INVALID = -2,     /* bad argument */
+    GGCUDA_ERR_UNSUPPORTED = -3, /* content this path cannot render (== gg.ErrFallbackToCPU, accelerator.go:16) */
+    GGCUDA_ERR_NOMEM = -4
+};
+
+/* gg.PathVerb (path.go): MoveTo 0, LineTo 1, QuadTo 2, CubicTo 3, Close 4 */
+enum { GGCUDA_VERB_MOVE = 0, GGCUDA_VERB_LINE = 1, GGCUDA_VERB_QUAD = 2, GGCUDA_VERB_CUBIC = 3, GGCUDA_VERB_CLOSE = 4 };
+/* gg.FillRule: NonZero 0, EvenOdd 1 */
+enum { GGCUDA_FILL_NONZERO = 0, GGCUDA_FILL_EVENODD = 1 };
+/* gg.LineCap / gg.LineJoin (paint.go): Butt 0, Round 1, Square 2 / Miter 0, Round 1, Bevel 2 */
+enum { GGCUDA_CAP_BUTT = 0, GGCUDA_CAP_ROUND = 1, GGCUDA_CAP_SQUARE = 2 };
+enum { GGCUDA_JOIN_MITER = 0, GGCUDA_JOIN_ROUND = 1, GGCUDA_JOIN_BEVEL = 2 };
+
+/* flags for ggcuda_flush / ggcuda_render_device */
+enum {
+    GGCUDA_COMPOSITE_OVER = 1,  /* start from the pixels already in dst (VelloAccelerator.compositeOver,
+                                   vello_accelerator.go:388-442) instead of the background colour */
+    GGCUDA_KEEP_SCENE = 2       /* do not clear the accumulated scene after rendering */
+};
+
+/* ---- lifetime: GPUAccelerator.Init / Close (accelerator.go:108-112) ---- */
+GGCUDA_API int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out);
+GGCUDA_API void ggcuda_destroy(ggcuda_ctx* ctx);
+GGCUDA_API const char* ggcuda_last_error(ggcuda_ctx* ctx);        /* ctx may be NULL for create failures */
+/* Use an externally owned cudaStream_t (e.g. the caller's current stream); NULL restores the context's own. */
+GGCUDA_API int ggcuda_set_stream(ggcuda_ctx* ctx, void* cuda_stream);
+
+/* ---- frame set-up ---- */
+/* Start accumulating a scene for a width x height target (GPURenderTarget.Width/Height). */
+GGCUDA_API int ggcuda_begin(ggcuda_ctx* ctx, uint32_t width, uint32_t height);
+/* Background (premultiplied RGBA8) used where GGCUDA_COMPOSITE_OVER is not set. Default transparent. */
+GGCUDA_API int ggcuda_set_background(ggcuda_ctx* ctx, const uint8_t rgba_premul[4]);
+/* Multi-GPU banding: this context renders only tile rows [y0, y1) (16-px rows). Default: whole canvas. */
+GGCUDA_API int ggcuda_set_band(ggcuda_ctx* ctx, uint32_t tile_row0, uint32_t tile_row1);
+
+/* ---- per-draw accumulation: GPUAccelerator.FillPath / StrokePath (accelerator.go:118-128),
+ *      VelloAccelerator.FillPath/StrokePath (vello_accelerator.go:197-268).
+ *      Paths are in device space (the CTM was applied by gg, context.go:1815,1870);
+ *      colour is straight-alpha RGBA8 as extractColorU8 produces (path_convert.go:116-128). ---- */
+GGCUDA_API int ggcuda_fill_path(ggcuda_ctx* ctx, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
+                     const uint8_t rgba_straight[4], int fill_rule);
+GGCUDA_API int ggcuda_stroke_path(ggcuda_ctx* ctx, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
+                       const uint8_t rgba_straight[4], double width, int cap, int join, double miter_limit);
+/* Clip / layer brackets for callers that own a clip stack (scene.Encoding's TagBeginClip /
+ * TagPushLayer reach the library through ggcuda_add_encoding; these are the same operations
+ * exposed per call). blend_mode is scene.BlendMode (scene/encoding.go:17-48). */
+GGCUDA_API int ggcuda_push_clip(ggcuda_ctx* ctx, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords);
+GGCUDA_API int ggcuda_push_layer(ggcuda_ctx* ctx, uint32_t blend_mode, float alpha);
+GGCUDA_API int ggcuda_pop(ggcuda_ctx* ctx);
+
+/* ---- whole-encoding accumulation: the streams of scene.Encoding (scene/encoding.go:407-444),
+ *      consumed with the tag semantics of scene.Renderer.executeEncodingOnTile
+ *      (scene/renderer.go:619-813). brushes: 4 doubles (straight RGBA) per brush.
+ *      Returns GGCUDA_ERR_UNSUPPORTED for TagImage / TagText (caller falls back). ---- */
+GGCUDA_API int ggcuda_add_encoding(ggcuda_ctx* ctx, const uint8_t* tags, size_t n_tags, const float* path_data, size_t n_path_data,
+                        const uint32_t* draw_data, size_t n_draw_data, const float* transforms, size_t n_transforms,
+                        const double* brushes_rgba, size_t n_brushes);
+
+/* ---- render: GPUAccelerator.Flush (accelerator.go:139, vello_accelerator.go:335-386) ---- */
+/* Upload the scene, run the pipeline, read the band back into dst (premultiplied RGBA8,
+ * GPURenderTarget.Data/Stride). dst addresses row 0 of the CANVAS; only the band's rows are written. */
+GGCUDA_API int ggcuda_flush(ggcuda_ctx* ctx, uint8_t* dst, size_t stride_bytes, uint32_t flags);
+/* Split form used by benchmarks and multi-GPU callers: upload once, render into device memory.
+ * dst_device addresses the first row of this context's BAND. */
+GGCUDA_API int ggcuda_upload(ggcuda_ctx* ctx);
+GGCUDA_API int ggcuda_render_device(ggcuda_ctx* ctx, void* dst_device, size_t stride_bytes, uint32_t flags);
+
+/* ---- introspection ---- */
+typedef struct {
+    uint32_t n_draws, n_paths, n_clips, n_tag_bytes;
+    uint32_t n_lines, n_path_tiles, n_seg_counts, n_segments, n_hits, n_ptcl_words, n_spill;
+    uint32_t passes;              /* pipeline executions of the last render (> 1 when a buffer had to grow) */
+    uint32_t kernel_launches;     /* kernels launched by the last render */
+    uint64_t scene_bytes;         /* host->device bytes of the last upload */
+    uint64_t device_bytes;        /* device memory currently held */
+    float ms_front, ms_binning, ms_coarse, ms_fine;   /* CUDA-event stage times of the last render (timing enabled) */
+} ggcuda_stats;
+GGCUDA_API int ggcuda_get_stats(ggcuda_ctx* ctx, ggcuda_stats* out);
+GGCUDA_API int ggcuda_set_timing(ggcuda_ctx* ctx, int enabled);
+
+/* Copy an intermediate buffer of the last render to host memory (parity tests). Returns bytes
+ * written, or the required size when dst == NULL / cap too small (negative on error). */
+enum {
+    GGCUDA_BUF_SCENE = 0, GGCUDA_BUF_TAG_MONOIDS = 1, GGCUDA_BUF_DRAW_MONOIDS = 2, GGCUDA_BUF_INFO = 3,
+    GGCUDA_BUF_CLIP_INPS = 4, GGCUDA_BUF_LINES = 5, GGCUDA_BUF_PATHS = 6, GGCUDA_BUF_TILES = 7,
+    GGCUDA_BUF_SEG_START = 8, GGCUDA_BUF_SEGMENTS = 9, GGCUDA_BUF_PTCL_OFF = 10, GGCUDA_BUF_PTCL = 11,
+    GGCUDA_BUF_HIT_CNT = 12, GGCUDA_BUF_LAYOUT = 13
+};
+GGCUDA_API long long ggcuda_debug_read(ggcuda_ctx* ctx, int which, void* dst, size_t cap_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
