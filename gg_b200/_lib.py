@@ -18,7 +18,7 @@ SYMBOLS = [
     "ggcuda_create", "ggcuda_destroy", "ggcuda_last_error", "ggcuda_set_stream", "ggcuda_begin", "ggcuda_set_background",
     "ggcuda_set_band", "ggcuda_fill_path", "ggcuda_stroke_path", "ggcuda_push_clip", "ggcuda_push_layer", "ggcuda_pop",
     "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_get_stats", "ggcuda_set_timing",
-    "ggcuda_debug_read",
+    "ggcuda_debug_read", "ggcuda_pack_host",
 ]
 
 LINE = np.dtype([("path_ix", "<u4"), ("p0", "<f4", 2), ("p1", "<f4", 2)])
@@ -84,6 +84,8 @@ def load():
     L.ggcuda_set_timing.argtypes = [vp, C.c_int]
     L.ggcuda_debug_read.argtypes = [vp, C.c_int, vp, sz]
     L.ggcuda_debug_read.restype = C.c_longlong
+    L.ggcuda_pack_host.argtypes = [vp, vp, sz, vp]
+    L.ggcuda_pack_host.restype = C.c_longlong
     _lib = L
     return L
 
@@ -171,6 +173,18 @@ class Context:
 
     def render_device(self, dptr, stride, flags=0):
         self._ck(self.L.ggcuda_render_device(self.h, C.c_void_p(dptr), stride, flags))
+
+    def pack_host(self):
+        """(packed scene words, LAYOUT record) exactly as ggcuda_upload would send them; works on host-only contexts."""
+        n = self.L.ggcuda_pack_host(self.h, None, 0, None)
+        if n < 0:
+            self._ck(int(n))
+        words = np.zeros(n, dtype=np.uint32)
+        lay = np.zeros(1, dtype=LAYOUT)
+        m = self.L.ggcuda_pack_host(self.h, _p(words), n, _p(lay))
+        if m < 0:
+            self._ck(int(m))
+        return words[:int(lay[0]["n_scene_words"])], lay[0]
 
     def set_timing(self, on):
         self._ck(self.L.ggcuda_set_timing(self.h, int(on)))

@@ -1,0 +1,185 @@
+"""Host-side mirror of gg's accelerator boundary over libggcuda's C ABI.
+
+The reference is Go; this image has no Go toolchain, so the host layer the parity tests and the
+bench drive is this Python mirror (same names, argument meaning and error behaviour as
+gogpu/gg accelerator.go:104-140 and internal/gpu/vello_accelerator.go). The Go binding a gg
+maintainer would add is in INTEGRATION.md. There is no CPU fallback here: operations this path
+cannot render raise ErrFallbackToCPU exactly where the reference returns gg.ErrFallbackToCPU,
+and it is the *caller* (gg.Context in the reference) that falls back.
+"""
+import numpy as np
+
+from . import _lib
+from ._lib import GGCudaError
+
+
+class ErrFallbackToCPU(Exception):
+    """accelerator.go:14-16."""
+
+
+# accelerator.go:19-45 AcceleratedOp
+AccelFill, AccelStroke, AccelScene, AccelText, AccelImage, AccelGradient, AccelCircleSDF, AccelRRectSDF = (1 << i for i in range(8))
+
+# gg.PathVerb
+MoveTo, LineTo, QuadTo, CubicTo, Close = 0, 1, 2, 3, 4
+FillRuleNonZero, FillRuleEvenOdd = 0, 1
+LineCapButt, LineCapRound, LineCapSquare = 0, 1, 2
+LineJoinMiter, LineJoinRound, LineJoinBevel = 0, 1, 2
+
+
+class Path:
+    """gg.Path (path.go): SOA verbs + float64 coords, device space at the accelerator boundary."""
+
+    def __init__(self):
+        self.verbs = []
+        self.coords = []
+
+    def MoveTo(self, x, y):
+        self.verbs.append(MoveTo); self.coords += [x, y]; return self
+
+    def LineTo(self, x, y):
+        self.verbs.append(LineTo); self.coords += [x, y]; return self
+
+    def QuadraticTo(self, cx, cy, x, y):
+        self.verbs.append(QuadTo); self.coords += [cx, cy, x, y]; return self
+
+    def CubicTo(self, c1x, c1y, c2x, c2y, x, y):
+        self.verbs.append(CubicTo); self.coords += [c1x, c1y, c2x, c2y, x, y]; return self
+
+    def Close(self):
+        self.verbs.append(Close); return self
+
+    def Circle(self, cx, cy, r):
+        """path.go:304-315: four kappa cubics."""
+        k = r * 0.5522847498307936
+        self.MoveTo(cx + r, cy)
+        self.CubicTo(cx + r, cy + k, cx + k, cy + r, cx, cy + r)
+        self.CubicTo(cx - k, cy + r, cx - r, cy + k, cx - r, cy)
+        self.CubicTo(cx - r, cy - k, cx - k, cy - r, cx, cy - r)
+        self.CubicTo(cx + k, cy - r, cx + r, cy - k, cx + r, cy)
+        return self.Close()
+
+    def Rectangle(self, x, y, w, h):
+        return self.MoveTo(x, y).LineTo(x + w, y).LineTo(x + w, y + h).LineTo(x, y + h).Close()
+
+    def NumVerbs(self):
+        return len(self.verbs)
+
+
+class Paint:
+    """The subset of gg.Paint the accelerator reads (paint.go; path_convert.go:116-128)."""
+
+    def __init__(self, color=(0, 0, 0, 1), fill_rule=FillRuleNonZero, line_width=1.0, line_cap=LineCapButt,
+                 line_join=LineJoinMiter, miter_limit=4.0, dashed=False):
+        self.color = color            # straight RGBA in [0, 1] (gg.RGBA)
+        self.FillRule = fill_rule
+        self.line_width = line_width
+        self.line_cap = line_cap
+        self.line_join = line_join
+        self.miter_limit = miter_limit
+        self.dashed = dashed
+
+    def IsDashed(self):
+        return self.dashed
+
+    def color_u8(self):
+        """extractColorU8 (path_convert.go:116-140): clampU8(v*255+0.5), straight alpha."""
+        return tuple(int(min(255.0, max(0.0, v * 255.0 + 0.5))) for v in self.color)
+
+
+class GPURenderTarget:
+    """accelerator.go:61-92, CPU read-back mode: Data is premultiplied RGBA8, Stride bytes per row."""
+
+    def __init__(self, width, height, data=None):
+        self.Width, self.Height = width, height
+        self.Data = data if data is not None else np.zeros((height, width, 4), dtype=np.uint8)
+        self.Stride = self.Data.strides[0]
+
+
+class CUDAAccelerator:
+    """gg.GPUAccelerator implemented by libggcuda (accumulate in FillPath/StrokePath, render in Flush --
+    the contract of VelloAccelerator, vello_accelerator.go:197-386), plus the whole-encoding entry
+    `RenderEncoding` that scene.Renderer.renderGPU would type-assert (SURVEY section 0 finding 2)."""
+
+    def __init__(self, device=0):
+        self.device = device
+        self.ctx = None
+        self._target = None
+        self._pending = 0
+
+    # -- GPUAccelerator
+    def Name(self):
+        return "ggcuda-b200"
+
+    def Init(self):
+        self.ctx = _lib.Context(self.device)   # raises if the library or a B200 is missing
+
+    def Close(self):
+        if self.ctx is not None:
+            self.ctx.close()
+            self.ctx = None
+
+    def CanAccelerate(self, op):
+        # False for the SDF shape ops so that gg offers the exact original path (shape routing)
+        return bool(op & (AccelFill | AccelStroke | AccelScene))
+
+    def CanCompute(self):   # ComputePipelineAware, accelerator.go:444-447
+        return self.ctx is not None
+
+    def _bind(self, target):
+        if self._target is not target:
+            if self._pending:
+                self.Flush(self._target)   # vello_accelerator.go:209-214: target change flushes
+            self._target = target
+            self.ctx.begin(target.Width, target.Height)
+
+    def FillPath(self, target, path, paint):
+        if self.ctx is None:
+            raise ErrFallbackToCPU("accelerator not initialised")
+        if path is None or path.NumVerbs() == 0:
+            return
+        self._bind(target)
+        self.ctx.fill_path(path.verbs, path.coords, paint.color_u8(), paint.FillRule)
+        self._pending += 1
+
+    def StrokePath(self, target, path, paint):
+        if self.ctx is None or paint.IsDashed():
+            raise ErrFallbackToCPU("dashed strokes are expanded on the CPU")   # vello_accelerator.go:239-241
+        if path is None or path.NumVerbs() == 0:
+            return
+        self._bind(target)
+        self.ctx.stroke_path(path.verbs, path.coords, paint.color_u8(), paint.line_width, paint.line_cap, paint.line_join,
+                             paint.miter_limit)
+        self._pending += 1
+
+    def FillShape(self, target, shape, paint):
+        raise ErrFallbackToCPU("shapes are routed through FillPath")
+
+    def StrokeShape(self, target, shape, paint):
+        raise ErrFallbackToCPU("shapes are routed through StrokePath")
+
+    def Flush(self, target):
+        if self.ctx is None or not self._pending:
+            return
+        try:
+            # content rendered earlier (CPU or a previous flush) is kept: composite over the target
+            self.ctx.flush(target.Data, target.Stride, _lib.COMPOSITE_OVER)
+        finally:
+            self._pending = 0
+            self._target = None
+
+    # -- scene.EncodingAccelerator (proposed optional interface)
+    def RenderEncoding(self, target, enc, composite_over=False):
+        """Render a whole scene.Encoding (fills, strokes, clips, layers with blend modes)."""
+        if self.ctx is None:
+            raise ErrFallbackToCPU("accelerator not initialised")
+        if self._pending:
+            self.Flush(self._target)
+        self.ctx.begin(target.Width, target.Height)
+        try:
+            self.ctx.add_encoding(*enc.streams())
+        except GGCudaError as e:
+            if e.code == _lib.ERR_UNSUPPORTED:
+                raise ErrFallbackToCPU(str(e))
+            raise
+        self.ctx.flush(target.Data, target.Stride, _lib.COMPOSITE_OVER if composite_over else 0)

@@ -28,6 +28,7 @@ struct DevBuf {
 
 struct Ctx {
     int device = 0;
+    bool host_only = false;   // device < 0: scene accumulation and packing only, no CUDA call is ever made
     cudaStream_t own_stream = nullptr, stream = nullptr;
     std::string err;
     HostScene scene;
@@ -98,6 +99,7 @@ uint32_t band_tiles(const Ctx* c) {
 // Upload the accumulated scene (one pinned staging buffer, one H2D copy) and size the
 // scene-proportional buffers.
 int upload(Ctx* c) {
+    if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
     if (c->width == 0 || c->height == 0) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_begin was not called");
     c->scene.close_open_clips();
@@ -196,6 +198,7 @@ GGBuffers buffers(Ctx* c) {
 
 // Run the pipeline into dst_device (band-relative). Re-runs with larger buffers while a stage overflowed.
 int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
+    if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
     if (!c->uploaded) { int r = upload(c); if (r) return r; }
     c->stats.passes = 0; c->stats.kernel_launches = 0;
@@ -258,6 +261,13 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
     Ctx* c = nullptr;
     if (!out) return fail(nullptr, GGCUDA_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    if (device < 0) {   // host-only context (scene packing for tests and the CPU baseline)
+        c = new (std::nothrow) Ctx();
+        if (!c) return fail(nullptr, GGCUDA_ERR_NOMEM, "out of host memory");
+        c->host_only = true; c->device = -1;
+        *out = reinterpret_cast<ggcuda_ctx*>(c);
+        return 0;
+    }
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
     if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(nullptr, GGCUDA_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e)); }
@@ -283,6 +293,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
 void ggcuda_destroy(ggcuda_ctx* h) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return;
+    if (c->host_only) { delete c; return; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_all(c);
@@ -297,6 +308,21 @@ void ggcuda_destroy(ggcuda_ctx* h) {
 const char* ggcuda_last_error(ggcuda_ctx* h) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     return c ? c->err.c_str() : g_create_err.c_str();
+}
+
+long long ggcuda_pack_host(ggcuda_ctx* h, uint32_t* dst, size_t cap_words, uint32_t layout13[13]) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    if (c->width == 0) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_begin was not called");
+    c->scene.close_open_clips();
+    size_t words = c->scene.packed_words();
+    if (!dst || cap_words < words) return (long long)words;
+    uint32_t ht = (c->height + GG_TILE_H - 1) / GG_TILE_H;
+    uint32_t y0 = c->band_set ? c->band_y0 : 0, y1 = c->band_set ? std::min(c->band_y1, ht) : ht;
+    HostScene::Layout L;
+    c->scene.pack(dst, &L, ((c->width + GG_TILE_W - 1) / GG_TILE_W) * (y1 > y0 ? y1 - y0 : 0));
+    if (layout13) memcpy(layout13, &L, sizeof(uint32_t) * 13);
+    return (long long)words;
 }
 
 int ggcuda_set_stream(ggcuda_ctx* h, void* s) {
@@ -378,11 +404,7 @@ int ggcuda_push_clip(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, cons
 int ggcuda_push_layer(ggcuda_ctx* h, uint32_t blend_mode, float alpha) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
-    HostScene& s = c->scene;
-    s.begin_path(ID6, false);
-    s.move_to(0, 0); s.line_to((float)c->width, 0); s.line_to((float)c->width, (float)c->height); s.line_to(0, (float)c->height); s.close();
-    s.end_path();
-    s.begin_clip(gg_blend_word(blend_mode), alpha, 1);
+    c->scene.begin_layer(gg_blend_word(blend_mode), alpha);
     c->uploaded = false;
     return 0;
 }
@@ -428,6 +450,7 @@ int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || !dst) return c ? fail(c, GGCUDA_ERR_INVALID, "dst is NULL") : GGCUDA_ERR_INVALID;
     if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
+    if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
     if (!c->uploaded) { int r = upload(c); if (r) return r; }
     uint32_t row0 = c->band_y0 * GG_TILE_H, row1 = std::min(c->band_y1 * GG_TILE_H, c->height);

@@ -65,7 +65,9 @@ __device__ __forceinline__ float4 unpack_rgba8(uint32_t c) {
 
 __global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
-                                                               float4* spill, uint8_t* dst, size_t stride) {
+                                                               float4* spill, const GGBump* __restrict__ bump, uint8_t* dst, size_t stride) {
+    // a stage overflowed its buffer: PTCL / segments are incomplete, the host re-runs the pass with larger buffers
+    if (bump->failed || bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap || bump->segments > cfg.segments_cap) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t warp_global = blockIdx.x * FINE_WARPS + (threadIdx.x >> 5);
     const uint32_t n_warps = gridDim.x * FINE_WARPS;
@@ -199,5 +201,5 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     uint32_t max_blocks = GG_SM_COUNT * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks == 0) return;
-    fine_kernel<<<blocks, FINE_WARPS * 32, 0, s>>>(cfg, b.ptcl_off, b.ptcl, b.segments, b.spill_off, b.spill, dst, stride);
+    fine_kernel<<<blocks, FINE_WARPS * 32, 0, s>>>(cfg, b.ptcl_off, b.ptcl, b.segments, b.spill_off, b.spill, b.bump, dst, stride);
 }

@@ -41,6 +41,7 @@ void HostScene::clear(uint32_t w, uint32_t h) {
     width = w; height = h;
     tags.clear(); path_data.clear(); draw_tags.clear(); draw_data.clear(); styles.clear(); transforms.clear();
     clip_aux.clear(); clip_stack.clear(); clip_kind.clear();
+    bounds_stack.clear(); layer_rect_off.clear(); layer_blend.clear();
     n_paths = n_clips = n_seg_tags = 0;
     have_transform = false; in_path = false; has_move = false;
 }
@@ -55,6 +56,16 @@ void HostScene::begin_path(const float t[6], bool even_odd) {
     tags.push_back(PT_STYLE);
     styles.push_back(even_odd ? 0x02u : 0u);   // scene_encode.go:110-114
     in_path = true; has_move = false;
+    memcpy(path_t, t, sizeof path_t);
+    path_bb[0] = path_bb[1] = 3.0e38f; path_bb[2] = path_bb[3] = -3.0e38f;
+}
+void HostScene::note_point(float x, float y) {
+    if (clip_stack.empty()) return;   // bounds only matter inside a clip / layer
+    float dx = path_t[0] * x + path_t[1] * y + path_t[2], dy = path_t[3] * x + path_t[4] * y + path_t[5];
+    if (dx < path_bb[0]) path_bb[0] = dx;
+    if (dy < path_bb[1]) path_bb[1] = dy;
+    if (dx > path_bb[2]) path_bb[2] = dx;
+    if (dy > path_bb[3]) path_bb[3] = dy;
 }
 void HostScene::move_to(float x, float y) {
     // An open subpath is closed implicitly, as every CPU filler in gg does (the Vello
@@ -62,18 +73,21 @@ void HostScene::move_to(float x, float y) {
     if (has_move && (cur[0] != start[0] || cur[1] != start[1])) line_to(start[0], start[1]);
     tags.push_back(PT_MOVETO);
     path_data.push_back(x); path_data.push_back(y);
+    note_point(x, y);
     cur[0] = start[0] = x; cur[1] = start[1] = y; has_move = true;
 }
 void HostScene::line_to(float x, float y) {
     if (!has_move) return;   // path_convert.go:52-54
     tags.push_back(PT_LINETO);
     path_data.push_back(x); path_data.push_back(y);
+    note_point(x, y);
     cur[0] = x; cur[1] = y; n_seg_tags++;
 }
 void HostScene::quad_to(float cx, float cy, float x, float y) {
     if (!has_move) return;
     tags.push_back(PT_QUADTO);
     path_data.push_back(cx); path_data.push_back(cy); path_data.push_back(x); path_data.push_back(y);
+    note_point(cx, cy); note_point(x, y);
     cur[0] = x; cur[1] = y; n_seg_tags++;
 }
 void HostScene::cubic_to(float c1x, float c1y, float c2x, float c2y, float x, float y) {
@@ -81,6 +95,7 @@ void HostScene::cubic_to(float c1x, float c1y, float c2x, float c2y, float x, fl
     tags.push_back(PT_CUBICTO);
     path_data.push_back(c1x); path_data.push_back(c1y); path_data.push_back(c2x); path_data.push_back(c2y);
     path_data.push_back(x); path_data.push_back(y);
+    note_point(c1x, c1y); note_point(c2x, c2y); note_point(x, y);
     cur[0] = x; cur[1] = y; n_seg_tags++;
 }
 void HostScene::close() {   // path_convert.go:86-92
@@ -113,6 +128,13 @@ void HostScene::draw_color(uint32_t rgba_premul) {
     draw_data.push_back(rgba_premul);
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(0);
+    if (!clip_stack.empty() && path_bb[0] <= path_bb[2]) {   // content bounds of the innermost open clip / layer
+        float* b = &bounds_stack[bounds_stack.size() - 4];
+        if (path_bb[0] < b[0]) b[0] = path_bb[0];
+        if (path_bb[1] < b[1]) b[1] = path_bb[1];
+        if (path_bb[2] > b[2]) b[2] = path_bb[2];
+        if (path_bb[3] > b[3]) b[3] = path_bb[3];
+    }
 }
 void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     int32_t d = (int32_t)draw_tags.size();
@@ -123,12 +145,54 @@ void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(-1);   // link patched by end_clip
     clip_stack.push_back(d); clip_kind.push_back(kind);
+    const float empty[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
+    bounds_stack.insert(bounds_stack.end(), empty, empty + 4);
+    layer_rect_off.push_back(SIZE_MAX); layer_blend.push_back(blend_word);
     n_clips++;
+}
+void HostScene::begin_layer(uint32_t blend_word, float alpha) {
+    // a layer is a clip rectangle that carries the blend mode and alpha; it starts as the whole
+    // canvas and may be shrunk to the layer's content bounds by end_clip
+    begin_path(IDENTITY, false);
+    size_t off = path_data.size();
+    move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
+    end_path();
+    begin_clip(blend_word, alpha, 1);
+    layer_rect_off.back() = off;
 }
 bool HostScene::end_clip(uint8_t kind) {
     if (clip_stack.empty() || clip_kind.back() != kind) return false;
     int32_t b = clip_stack.back();
     clip_stack.pop_back(); clip_kind.pop_back();
+    float cb[4]; memcpy(cb, &bounds_stack[bounds_stack.size() - 4], sizeof cb);
+    bounds_stack.resize(bounds_stack.size() - 4);
+    size_t rect_off = layer_rect_off.back(); uint32_t bw = layer_blend.back();
+    layer_rect_off.pop_back(); layer_blend.pop_back();
+    if (kind == 1 && rect_off != SIZE_MAX) {
+        // Layer rectangle: full canvas for compose modes that change the backdrop where the layer is
+        // transparent (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop); otherwise the tile-aligned bounds
+        // of the layer's content (an empty layer collapses to nothing and coarse culls it).
+        uint32_t mix = bw >> 8, compose = bw & 0xffu;
+        bool erases = mix == 0 && (compose == 0 || compose == 1 || compose == 5 || compose == 6 || compose == 7 || compose == 10);
+        if (!erases) {
+            float x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+            if (cb[0] <= cb[2]) {
+                x0 = floorf(fmaxf(cb[0], 0.0f) / 16.0f) * 16.0f; y0 = floorf(fmaxf(cb[1], 0.0f) / 16.0f) * 16.0f;
+                x1 = fminf(ceilf(fminf(cb[2], (float)width) / 16.0f) * 16.0f, (float)width);
+                y1 = fminf(ceilf(fminf(cb[3], (float)height) / 16.0f) * 16.0f, (float)height);
+                if (x1 <= x0 || y1 <= y0) x0 = y0 = x1 = y1 = 0;
+            }
+            float* r = &path_data[rect_off];   // move(x0,y0) line(x1,y0) line(x1,y1) line(x0,y1) line(x0,y0)
+            r[0] = x0; r[1] = y0; r[2] = x1; r[3] = y0; r[4] = x1; r[5] = y1; r[6] = x0; r[7] = y1; r[8] = x0; r[9] = y0;
+        }
+    }
+    if (!bounds_stack.empty() && cb[0] <= cb[2]) {   // a child's content is also the parent's content
+        float* pb = &bounds_stack[bounds_stack.size() - 4];
+        if (cb[0] < pb[0]) pb[0] = cb[0];
+        if (cb[1] < pb[1]) pb[1] = cb[1];
+        if (cb[2] > pb[2]) pb[2] = cb[2];
+        if (cb[3] > pb[3]) pb[3] = cb[3];
+    }
     int32_t d = (int32_t)draw_tags.size();
     // EndClip: dummy path marker so that path index == draw index (scene_encode.go:258-268);
     // we also give it a style word so that styles[path_ix] is valid for every path.
@@ -293,11 +357,7 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         case ST_PUSH_LAYER: {
             if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
             uint32_t blend = dd[di]; float alpha; memcpy(&alpha, dd + di + 1, 4); di += 2;
-            // a layer is a clip over the whole canvas that carries the blend mode and alpha
-            begin_path(IDENTITY, false);
-            move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
-            end_path();
-            begin_clip(gg_blend_word(blend), alpha, 1);
+            begin_layer(gg_blend_word(blend), alpha);
         } break;
         case ST_POP_LAYER:
             while (!clip_stack.empty() && clip_kind.back() == 0) end_clip(0);   // unbalanced clips inside the layer
@@ -325,28 +385,28 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
 // (left side forward, cap, right side backward, cap) or two loops for closed subpaths; joins
 // are added on both sides (the inner ones overlap harmlessly under NonZero).
 namespace {
-struct P2 { double x, y; };
-const double STROKE_TOL = 0.1;
+struct P2 { double x, y; bool smooth = false; };   // smooth: interior vertex of a flattened curve (no join style)
+const double STROKE_TOL = 0.25;   // same tolerance as the fill flattener (flatten.go:19)
 
-void flatten_quad(std::vector<P2>& o, P2 a, P2 b, P2 c) {
-    double ddx = a.x - 2 * b.x + c.x, ddy = a.y - 2 * b.y + c.y;
-    int n = (int)ceil(sqrt(sqrt(ddx * ddx + ddy * ddy) / (4 * STROKE_TOL)));
-    if (n < 1) n = 1; if (n > 256) n = 256;
-    for (int i = 1; i <= n; i++) {
-        double t = (double)i / n, m = 1 - t;
-        o.push_back({m * m * a.x + 2 * m * t * b.x + t * t * c.x, m * m * a.y + 2 * m * t * b.y + t * t * c.y});
-    }
+// adaptive de Casteljau subdivision: stop when the control points are within tol of the chord
+void flatten_cubic_rec(std::vector<P2>& o, P2 a, P2 b, P2 c, P2 d, int depth) {
+    double ux = 3 * b.x - 2 * a.x - d.x, uy = 3 * b.y - 2 * a.y - d.y;
+    double vx = 3 * c.x - 2 * d.x - a.x, vy = 3 * c.y - 2 * d.y - a.y;
+    double m = fmax(ux * ux, vx * vx) + fmax(uy * uy, vy * vy);
+    if (m <= 16 * STROKE_TOL * STROKE_TOL || depth >= 16) { P2 e = d; e.smooth = true; o.push_back(e); return; }
+    P2 ab = {(a.x + b.x) / 2, (a.y + b.y) / 2}, bc = {(b.x + c.x) / 2, (b.y + c.y) / 2}, cd = {(c.x + d.x) / 2, (c.y + d.y) / 2};
+    P2 abc = {(ab.x + bc.x) / 2, (ab.y + bc.y) / 2}, bcd = {(bc.x + cd.x) / 2, (bc.y + cd.y) / 2};
+    P2 mid = {(abc.x + bcd.x) / 2, (abc.y + bcd.y) / 2};
+    flatten_cubic_rec(o, a, ab, abc, mid, depth + 1);
+    flatten_cubic_rec(o, mid, bcd, cd, d, depth + 1);
 }
 void flatten_cubic(std::vector<P2>& o, P2 a, P2 b, P2 c, P2 d) {
-    double d1x = a.x - 2 * b.x + c.x, d1y = a.y - 2 * b.y + c.y, d2x = b.x - 2 * c.x + d.x, d2y = b.y - 2 * c.y + d.y;
-    double m = fmax(sqrt(d1x * d1x + d1y * d1y), sqrt(d2x * d2x + d2y * d2y));
-    int n = (int)ceil(sqrt(0.75 * m / STROKE_TOL));
-    if (n < 1) n = 1; if (n > 512) n = 512;
-    for (int i = 1; i <= n; i++) {
-        double t = (double)i / n, u = 1 - t;
-        double w0 = u * u * u, w1 = 3 * u * u * t, w2 = 3 * u * t * t, w3 = t * t * t;
-        o.push_back({w0 * a.x + w1 * b.x + w2 * c.x + w3 * d.x, w0 * a.y + w1 * b.y + w2 * c.y + w3 * d.y});
-    }
+    flatten_cubic_rec(o, a, b, c, d, 0);
+    o.back().smooth = false;   // the segment's end point is a real path vertex
+}
+void flatten_quad(std::vector<P2>& o, P2 a, P2 b, P2 c) {
+    P2 c1 = {a.x + 2.0 / 3.0 * (b.x - a.x), a.y + 2.0 / 3.0 * (b.y - a.y)}, c2 = {c.x + 2.0 / 3.0 * (b.x - c.x), c.y + 2.0 / 3.0 * (b.y - c.y)};
+    flatten_cubic(o, a, c1, c2, c);
 }
 void arc_points(std::vector<P2>& o, P2 c, double r, double a0, double a1) {   // a0 -> a1 (signed sweep), excluding start, including end
     double sweep = a1 - a0;
@@ -359,6 +419,10 @@ void arc_points(std::vector<P2>& o, P2 c, double r, double a0, double a1) {   //
 // join at vertex v between directions d0 -> d1 on the side with normal sign `side` (+1 = left)
 void add_join(std::vector<P2>& o, P2 v, P2 d0, P2 d1, double hw, int side, int join, double miter_limit) {
     P2 n0 = {-d0.y * side, d0.x * side}, n1 = {-d1.y * side, d1.x * side};
+    if (v.smooth) {   // flattened-curve interior vertex: one point on the bisector (turning angle is small)
+        double mx = n0.x + n1.x, my = n0.y + n1.y, ml2 = mx * mx + my * my;
+        if (ml2 > 1.0) { double k = 2.0 * hw / ml2; o.push_back({v.x + mx * k, v.y + my * k}); return; }
+    }
     P2 a = {v.x + n0.x * hw, v.y + n0.y * hw}, b = {v.x + n1.x * hw, v.y + n1.y * hw};
     double cross = d0.x * d1.y - d0.y * d1.x, dot = d0.x * d1.x + d0.y * d1.y;
     bool outer = cross * side < 0;   // turning away from this side

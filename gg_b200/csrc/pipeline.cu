@@ -300,6 +300,7 @@ __device__ __forceinline__ void dda_finish(DDA& d) {   // path_count.go:40-69
 // (the slot a segment gets inside its tile is the value returned by the count atomic).
 __global__ void __launch_bounds__(256) path_count_kernel(GGConfig cfg, const GGLine* __restrict__ lines, const GGPath* __restrict__ paths,
                                                          GGTile* tiles, GGSegCount* seg_counts, GGBump* bump) {
+    if (bump->failed) return;   // an upstream buffer overflowed: this pass is redone with larger buffers
     uint32_t n_lines = min(bump->lines, cfg.lines_cap);
     for (uint32_t line_ix = blockIdx.x * blockDim.x + threadIdx.x; line_ix < n_lines; line_ix += gridDim.x * blockDim.x) {
         GGLine line = lines[line_ix];
@@ -418,7 +419,8 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
                                                         uint32_t* hit_cursor, uint32_t* hits, GGBump* bump) {
     cg::thread_block_tile<8> g = cg::tiled_partition<8>(cg::this_thread_block());
     const uint32_t n_rows = min(bump->path_rows, cfg.rows_cap);
-    if (bump->path_tiles > cfg.tiles_cap) return;
+    if (bump->failed || bump->path_tiles > cfg.tiles_cap) return;
+    if (PASS == 1 && bump->hits > cfg.hits_cap) return;
     const uint32_t groups = gridDim.x * blockDim.x / 8;
     for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) / 8; row < n_rows; row += groups) {
         uint32_t p = find_row_path(path_row_off, cfg.n_paths, row);
@@ -489,6 +491,7 @@ __global__ void __launch_bounds__(256) path_tiling_kernel(GGConfig cfg, const GG
                                                           const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
                                                           const uint32_t* __restrict__ seg_start, GGSegment* segments, GGBump* bump) {
     uint32_t n = min(bump->seg_counts, cfg.seg_counts_cap);
+    if (bump->failed) return;
     if (bump->segments > cfg.segments_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, GG_FAIL_SEGMENTS); return; }
     for (uint32_t seg_ix = blockIdx.x * blockDim.x + threadIdx.x; seg_ix < n; seg_ix += gridDim.x * blockDim.x) {
         GGSegCount sc = seg_counts[seg_ix];
@@ -591,6 +594,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
     __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
+    if (bump->failed) return;
     const bool overflow = bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap;
     if (overflow) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, (bump->hits > cfg.hits_cap ? GG_FAIL_HITS : 0u) | (bump->ptcl_words > cfg.ptcl_cap ? GG_FAIL_PTCL : 0u)); return; }
     uint32_t* sb = sort_buf[warp];

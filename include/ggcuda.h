@@ -127,6 +127,12 @@ enum {
 };
 GGCUDA_API long long ggcuda_debug_read(ggcuda_ctx* ctx, int which, void* dst, size_t cap_bytes);
 
+/* Host-only scene packing. ggcuda_create(device = -1) gives a context that accumulates scenes but
+ * owns no device (every render call fails with GGCUDA_ERR_UNSUPPORTED: there is no CPU fallback).
+ * ggcuda_pack_host writes the packed scene exactly as ggcuda_upload would send it (layout13: the 13
+ * words of the packed layout) and returns its size in words (also when dst is NULL / too small). */
+GGCUDA_API long long ggcuda_pack_host(ggcuda_ctx* ctx, uint32_t* dst, size_t cap_words, uint32_t layout13[13]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -756,7 +756,7 @@ void ot_rasterize_scene(const uint8_t bg[4], const ot_element *elems, uint32_t n
     for (int i = 0; i < w * h; i++) memcpy(out + 4 * (size_t)i, bg, 4);
     float *alpha = (float *)malloc(sizeof(float) * (size_t)w * h);
     for (uint32_t e = 0; e < n_elems; e++) {
-        if (elems[e].type != OT_ELEM_DRAW || elems[e].line_count == 0) continue;
+        if (OT_ELEM_TYPE(elems[e].type) != OT_ELEM_DRAW || elems[e].line_count == 0) continue;
         ot_rasterize(lines + elems[e].line_start, elems[e].line_count, (int)elems[e].even_odd, w, h, alpha);
         for (int i = 0; i < w * h; i++) {
             if (alpha[i] <= 0) continue;
@@ -829,6 +829,8 @@ static void tile_seg_range(ot_tile tile, int local_idx, int tile_count, const ot
     *count = seg_end - seg_start; *start = seg_start;
 }
 
+int ot_style_per_path = 0;
+
 ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_line_soup *lines_in, int w, int h) {
     ot_coarse *out = (ot_coarse *)calloc(1, sizeof(ot_coarse));
     /* --- EncodeSceneDef (scene_encode.go:240-308) --- */
@@ -836,11 +838,11 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
     uint32_t n_paths = 0, n_draw = 0, n_clips = 0;
     for (uint32_t e = 0; e < n_elems; e++) {
         const ot_element *el = &elems[e];
-        switch (el->type) {
+        switch (OT_ELEM_TYPE(el->type)) {
         case OT_ELEM_DRAW:
             encode_path(&raw_tags, &path_data, &transforms, &styles, lines_in + el->line_start, el->line_count, (int)el->even_odd);
             u32_push(&draw_tags, DRAWTAG_COLOR);
-            u32_push(&draw_data, pack_color(el->color));
+            u32_push(&draw_data, (el->type & OT_ELEM_PACKED) ? el->packed_rgba : pack_color(el->color));
             n_paths++; n_draw++;
             break;
         case OT_ELEM_BEGIN_CLIP:
@@ -850,6 +852,9 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
             n_paths++; n_draw++; n_clips++;
             break;
         case OT_ELEM_END_CLIP:
+            /* reference quirk: no style word for the dummy path, so styles[path_ix] (coarse.go:683-705) is
+             * shifted after the first clip pair. ot_style_per_path != 0 emits one (ggcuda's encoder does). */
+            if (ot_style_per_path) { u32_push(&raw_tags, PTAG_STYLE); u32_push(&styles, 0); }
             u32_push(&raw_tags, PTAG_PATH);
             u32_push(&draw_tags, DRAWTAG_END_CLIP);
             n_paths++; n_draw++; n_clips++;
@@ -935,14 +940,14 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
 
     /* --- allLines with PathIx (rasterizer.go:363-384) --- */
     uint32_t n_lines = 0;
-    for (uint32_t e = 0; e < n_elems; e++) if (elems[e].type != OT_ELEM_END_CLIP) n_lines += elems[e].line_count;
+    for (uint32_t e = 0; e < n_elems; e++) if (OT_ELEM_TYPE(elems[e].type) != OT_ELEM_END_CLIP) n_lines += elems[e].line_count;
     ot_line_soup *all = (ot_line_soup *)malloc(sizeof(ot_line_soup) * (n_lines ? n_lines : 1));
     uint32_t *path_line_start = (uint32_t *)calloc(n_paths + 1, sizeof(uint32_t));
     {
         uint32_t k = 0, pix = 0;
         for (uint32_t e = 0; e < n_elems; e++) {
             path_line_start[pix] = k;
-            if (elems[e].type != OT_ELEM_END_CLIP)
+            if (OT_ELEM_TYPE(elems[e].type) != OT_ELEM_END_CLIP)
                 for (uint32_t i = 0; i < elems[e].line_count; i++) { all[k] = lines_in[elems[e].line_start + i]; all[k].path_ix = pix; k++; }
             pix++;
         }

@@ -36,7 +36,10 @@ typedef struct {
     uint32_t even_odd;    /* fill rule (draw) */
     uint32_t blend;       /* begin clip */
     float    alpha;       /* begin clip */
+    uint32_t packed_rgba; /* draw: premultiplied packed colour, used instead of `color` when OT_ELEM_PACKED is set in type */
 } ot_element;
+#define OT_ELEM_PACKED 0x100u
+#define OT_ELEM_TYPE(t) ((t) & 0xffu)
 
 /* scene_encode.go:52-62 */
 typedef struct {
@@ -80,6 +83,7 @@ void ot_rasterize_scene(const uint8_t bg[4], const ot_element *elems, uint32_t n
                         const ot_line_soup *lines, int w, int h, uint8_t *out);
 
 /* ---- full PTCL pipeline (rasterizer.go:321-422, coarse.go, fine.go) ---- */
+extern int ot_style_per_path;   /* 0 = reference behaviour (default), 1 = one style word per path marker */
 ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems,
                          const ot_line_soup *lines, int w, int h);
 void ot_coarse_free(ot_coarse *c);
@@ -98,6 +102,19 @@ void ot_path_tiling(const ot_segment_count *seg_counts, uint32_t n_seg_counts,
                     const ot_line_soup *lines, const ot_path *paths, const ot_tile *tiles,
                     ot_path_segment *segments);
 void ot_line_bbox(const ot_line_soup *lines, uint32_t n, int w, int h, uint32_t bbox[4]);
+
+/* ---- whole pipeline from ggcuda's packed scene (the a2 format: Vello path tags incl. 0x0C MoveTo,
+ *      quads/cubics, real transforms). CPU restatement of the product's device stages a6..a13:
+ *      flatten every curve (transform in f32 as scene/encoding.go:348-350, quad elevation as
+ *      path_convert.go:60-72, FlattenFill), then ot_coarse_run + fine on `threads` host threads.
+ *      layout: the 13 words of gg_b200/csrc/host_scene.h HostScene::Layout. out_premul: w*h*4. ---- */
+typedef struct { double t_flatten, t_coarse, t_fine; uint32_t n_lines, n_segments, n_ptcl_words; } ot_timing;
+int ot_render_packed(const uint32_t *scene, const uint32_t *layout13, int w, int h, const uint8_t bg_premul[4],
+                     int threads, uint8_t *out_premul, ot_timing *timing);
+/* flatten stage alone: lines (path_ix set) for every path of the packed scene; returns count (cap as ot_flatten_fill) */
+uint32_t ot_flatten_packed(const uint32_t *scene, const uint32_t *layout13, ot_line_soup *out, uint32_t cap);
+/* multi-threaded ot_fine_frame */
+void ot_fine_frame_mt(const ot_coarse *c, const float bg_premul[4], int w, int h, int threads, uint8_t *out_premul);
 
 #ifdef __cplusplus
 }

@@ -21,7 +21,7 @@ SEGMENT = np.dtype([("p0", "<f4", 2), ("p1", "<f4", 2), ("y_edge", "<f4")])     
 PATH_MONOID = np.dtype([(n, "<u4") for n in ("trans_ix", "path_seg_ix", "path_seg_offset", "style_ix", "path_ix")])
 DRAW_MONOID = np.dtype([(n, "<u4") for n in ("path_ix", "clip_ix", "scene_offset", "info_offset")])
 ELEMENT = np.dtype([("type", "<u4"), ("line_start", "<u4"), ("line_count", "<u4"), ("color", "u1", 4),
-                    ("even_odd", "<u4"), ("blend", "<u4"), ("alpha", "<f4")])
+                    ("even_odd", "<u4"), ("blend", "<u4"), ("alpha", "<f4"), ("packed_rgba", "<u4")])
 ELEM_DRAW, ELEM_BEGIN_CLIP, ELEM_END_CLIP = 0, 1, 2
 
 
@@ -238,3 +238,44 @@ def polygon_lines(verts):
             continue
         out.append((0, p0, p1))
     return np.array(out, dtype=LINE)
+
+
+# ---- ggcuda packed-scene entry points (oracle/packed.c) ----
+class _Timing(C.Structure):
+    _fields_ = [("t_flatten", C.c_double), ("t_coarse", C.c_double), ("t_fine", C.c_double),
+                ("n_lines", C.c_uint32), ("n_segments", C.c_uint32), ("n_ptcl_words", C.c_uint32)]
+
+
+def _layout13(layout):
+    """layout: numpy record with gg_b200._lib.LAYOUT fields, or a 13-sequence."""
+    if hasattr(layout, "dtype") and layout.dtype.names:
+        return np.array([int(layout[n]) for n in layout.dtype.names], dtype=np.uint32)
+    return np.asarray(layout, dtype=np.uint32)
+
+
+def flatten_packed(scene_words, layout):
+    L = lib()
+    L.ot_flatten_packed.restype = C.c_uint32
+    L.ot_flatten_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    sw = np.ascontiguousarray(scene_words, dtype=np.uint32)
+    l13 = _layout13(layout)
+    cap = 1 << 16
+    while True:
+        out = np.zeros(cap, dtype=LINE)
+        n = L.ot_flatten_packed(_p(sw), _p(l13), _p(out), cap)
+        if n <= cap:
+            return out[:n].copy()
+        cap = n
+
+
+def render_packed(scene_words, layout, w, h, bg_premul=(0, 0, 0, 0), threads=1):
+    """Whole CPU pipeline from ggcuda's packed scene -> ((h, w, 4) premultiplied RGBA8, timing dict)."""
+    L = lib()
+    L.ot_render_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.POINTER(_Timing)]
+    sw = np.ascontiguousarray(scene_words, dtype=np.uint32)
+    l13 = _layout13(layout)
+    bg = np.asarray(bg_premul, dtype=np.uint8)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    tm = _Timing()
+    L.ot_render_packed(_p(sw), _p(l13), w, h, _p(bg), int(threads), _p(out), C.byref(tm))
+    return out, {n: getattr(tm, n) for n, _ in _Timing._fields_}
