@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, con
                     float cov = area[i];
                     float fr = c.x * cov, fg = c.y * cov, fb = c.z * cov, fa = c.w * cov;
                     float inv = 1.0f - fa;
-                    rgba[i].x = rgba[i].x * inv + fr; rgba[i].y = rgba[i].y * inv + fg;
-                    rgba[i].z = rgba[i].z * inv + fb; rgba[i].w = rgba[i].w * inv + fa;
+                    rgba[i].x = fmaf(rgba[i].x, inv, fr); rgba[i].y = fmaf(rgba[i].y, inv, fg);
+                    rgba[i].z = fmaf(rgba[i].z, inv, fb); rgba[i].w = fmaf(rgba[i].w, inv, fa);
                 }
             } else if (tag == GG_CMD_BEGIN_CLIP) {   // fine.go:125-138
                 if (clip_depth < GG_BLEND_STACK_SPLIT) {
@@ -173,8 +173,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, con
                     float fr = rgba[i].x * scale, fg = rgba[i].y * scale, fb = rgba[i].z * scale, fa = rgba[i].w * scale;
                     float inv = 1.0f - fa;
                     float4 sv = saved[i];
-                    rgba[i].x = sv.x * inv + fr; rgba[i].y = sv.y * inv + fg;
-                    rgba[i].z = sv.z * inv + fb; rgba[i].w = sv.w * inv + fa;
+                    rgba[i].x = fmaf(sv.x, inv, fr); rgba[i].y = fmaf(sv.y, inv, fg);
+                    rgba[i].z = fmaf(sv.z, inv, fb); rgba[i].w = fmaf(sv.w, inv, fa);
                 }
             } else {
                 break;   // unknown command: stop (fine.go:182-185)

@@ -150,6 +150,12 @@ void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     layer_rect_off.push_back(SIZE_MAX); layer_blend.push_back(blend_word);
     n_clips++;
 }
+// Compose modes whose result differs from the backdrop where the layer is transparent:
+// Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop (Porter-Duff with Fb != 1 at Sa == 0).
+static bool blend_erases_backdrop(uint32_t bw) {
+    uint32_t mix = (bw >> 8) & 0xffu, compose = bw & 0xffu;
+    return mix == 0 && (compose == 0 || compose == 1 || compose == 5 || compose == 6 || compose == 7 || compose == 10);
+}
 void HostScene::begin_layer(uint32_t blend_word, float alpha) {
     // a layer is a clip rectangle that carries the blend mode and alpha; it starts as the whole
     // canvas and may be shrunk to the layer's content bounds by end_clip
@@ -157,6 +163,7 @@ void HostScene::begin_layer(uint32_t blend_word, float alpha) {
     size_t off = path_data.size();
     move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
     end_path();
+    if (!blend_erases_backdrop(blend_word)) blend_word |= 0x80000000u;   // GG_BLEND_ELIDE_EMPTY
     begin_clip(blend_word, alpha, 1);
     layer_rect_off.back() = off;
 }
@@ -172,9 +179,7 @@ bool HostScene::end_clip(uint8_t kind) {
         // Layer rectangle: full canvas for compose modes that change the backdrop where the layer is
         // transparent (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop); otherwise the tile-aligned bounds
         // of the layer's content (an empty layer collapses to nothing and coarse culls it).
-        uint32_t mix = bw >> 8, compose = bw & 0xffu;
-        bool erases = mix == 0 && (compose == 0 || compose == 1 || compose == 5 || compose == 6 || compose == 7 || compose == 10);
-        if (!erases) {
+        if (!blend_erases_backdrop(bw)) {
             float x0 = 0, y0 = 0, x1 = 0, y1 = 0;
             if (cb[0] <= cb[2]) {
                 x0 = floorf(fmaxf(cb[0], 0.0f) / 16.0f) * 16.0f; y0 = floorf(fmaxf(cb[1], 0.0f) / 16.0f) * 16.0f;

@@ -82,6 +82,7 @@ __global__ void draw_leaf_kernel(GGConfig cfg, const uint32_t* __restrict__ scen
         } else if (tag == GG_DRAWTAG_BEGIN_CLIP) {
             if (m.clip_ix < cfg.n_clips) { clip_inps[m.clip_ix].ix = d; clip_inps[m.clip_ix].path_ix = (int32_t)m.path_ix; }
             r.a = link;
+            r.b = scene[cfg.draw_data_base + m.scene_offset];   // blend word (GG_BLEND_ELIDE_EMPTY lives here)
         } else if (tag == GG_DRAWTAG_END_CLIP) {
             if (m.clip_ix < cfg.n_clips) { clip_inps[m.clip_ix].ix = d; clip_inps[m.clip_ix].path_ix = ~(int32_t)d; }
             if (link < cfg.n_draws) {
@@ -605,7 +606,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
         pos += 1;
         if (n == 0) { if (lane == 0) ptcl[pos] = GG_CMD_END; continue; }
-        const uint32_t* sorted;
+        uint32_t* sorted;
         if (n <= COARSE_CAP) {
             uint32_t np2 = 32; while (np2 < n) np2 <<= 1;
             for (uint32_t i = lane; i < np2; i += 32) sb[i] = i < n ? list[i] : 0xffffffffu;
@@ -629,8 +630,12 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
             sorted = list;
         }
         const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
+        // Layers whose blend word carries GG_BLEND_ELIDE_EMPTY are opened lazily: their BeginClip is only
+        // written (just before the first command they enclose in this tile) once something is drawn inside;
+        // a layer still pending at its EndClip leaves no trace. `depth` counts logically open clips,
+        // `mat` how many of them (always the outermost ones) have been written to the PTCL.
         int32_t top = -1;
-        uint32_t depth = 0, max_depth = 0;
+        uint32_t depth = 0, mat = 0, max_depth = 0;
         for (uint32_t base = 0; base < n; base += 32) {
             uint32_t i = base + lane;
             // parallel gather of everything the state machine and the emitters need
@@ -647,21 +652,33 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
             }
             // sequential, warp-uniform replay of the clip state over the (up to) 32 gathered hits
             bool emit = false;
+            uint32_t pre = 0;   // pending BeginClip words this hit has to write before its own command
             uint32_t cnt = min(32u, n - base);
             for (uint32_t j = 0; j < cnt; j++) {
                 uint32_t jt = __shfl_sync(0xffffffffu, r.tag, j);
                 int32_t jp = __shfl_sync(0xffffffffu, r.parent, j);
                 uint32_t jd = __shfl_sync(0xffffffffu, d, j);
                 int32_t jbp = __shfl_sync(0xffffffffu, begin_parent, j);
+                uint32_t jb = __shfl_sync(0xffffffffu, r.b, j);
                 bool e = false;
+                uint32_t pj = 0;
                 if (jt == GG_DRAWTAG_COLOR) {
-                    e = jp == top;
+                    if (jp == top) { e = true; pj = depth - mat; mat = depth; }
                 } else if (jt == GG_DRAWTAG_BEGIN_CLIP) {
-                    if (jp == top) { e = true; top = (int32_t)jd; depth++; max_depth = max(max_depth, depth); }
+                    if (jp == top) {
+                        top = (int32_t)jd;
+                        if (jb & GG_BLEND_ELIDE_EMPTY) { depth++; }                       // pending
+                        else { e = true; pj = depth - mat; depth++; mat = depth; }        // written now (+ pending parents)
+                    }
                 } else if (jt == GG_DRAWTAG_END_CLIP) {
-                    if (top == jp) { e = true; top = jbp; depth--; }   // jp == index of the matching BeginClip
+                    if (top == jp) {   // jp == index of the matching BeginClip
+                        top = jbp;
+                        if (depth > mat) { depth--; }                                     // never materialised: nothing to close
+                        else { e = true; depth--; mat--; }
+                    }
                 }
-                if (lane == j) emit = e;
+                max_depth = max(max_depth, mat);
+                if (lane == j) { emit = e; pre = pj; }
             }
             // words per hit, warp exclusive scan, parallel emission
             uint32_t nw = 0;
@@ -669,12 +686,14 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                 if (r.tag == GG_DRAWTAG_COLOR) nw = t.seg_count ? 6u : 3u;
                 else if (r.tag == GG_DRAWTAG_BEGIN_CLIP) nw = 1u;
                 else nw = t.seg_count ? 7u : 4u;
+                nw += pre;
             }
             uint32_t inc = nw;
 #pragma unroll
             for (int dl = 1; dl < 32; dl <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, dl); if ((int)lane >= dl) inc += o; }
             uint32_t o = pos + inc - nw;
             if (emit) {
+                for (uint32_t k = 0; k < pre; k++) ptcl[o++] = GG_CMD_BEGIN_CLIP;
                 if (r.tag == GG_DRAWTAG_COLOR) {
                     if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | r.b; ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
                     else ptcl[o++] = GG_CMD_SOLID;

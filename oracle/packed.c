@@ -102,8 +102,28 @@ void ot_fine_frame_mt(const ot_coarse *c, const float bg[4], int w, int h, int t
     if (threads > 1) for (int i = 0; i < threads; i++) pthread_join(th[i], NULL);
 }
 
+static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, int w, int h, double *t_flatten, uint32_t *n_lines_out);
+
+ot_coarse *ot_coarse_from_packed(const uint32_t *scene, const uint32_t *L, int w, int h) {
+    return coarse_from_packed(scene, L, w, h, NULL, NULL);
+}
+
 int ot_render_packed(const uint32_t *scene, const uint32_t *L, int w, int h, const uint8_t bg[4], int threads,
                      uint8_t *out_premul, ot_timing *tm) {
+    double t0 = now_s(), tf = 0;
+    uint32_t n = 0;
+    ot_coarse *c = coarse_from_packed(scene, L, w, h, &tf, &n);
+    double t2 = now_s();
+    float bgf[4] = {bg[0] / 255.0f, bg[1] / 255.0f, bg[2] / 255.0f, bg[3] / 255.0f};
+    if (out_premul) ot_fine_frame_mt(c, bgf, w, h, threads, out_premul);
+    double t3 = now_s();
+    if (tm) { tm->t_flatten = tf; tm->t_coarse = t2 - t0 - tf; tm->t_fine = t3 - t2; tm->n_lines = n; tm->n_segments = c->n_segments;
+              tm->n_ptcl_words = c->ptcl_offsets[c->width_in_tiles * c->height_in_tiles]; }
+    ot_coarse_free(c);
+    return 0;
+}
+
+static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, int w, int h, double *t_flatten, uint32_t *n_lines_out) {
     double t0 = now_s();
     uint32_t cap = 1u << 16, n;
     ot_line_soup *lines = (ot_line_soup *)malloc(sizeof(ot_line_soup) * cap);
@@ -127,12 +147,8 @@ int ot_render_packed(const uint32_t *scene, const uint32_t *L, int w, int h, con
     ot_style_per_path = 1;
     ot_coarse *c = ot_coarse_run(el, n_draws, lines, w, h);
     ot_style_per_path = saved;
-    double t2 = now_s();
-    float bgf[4] = {bg[0] / 255.0f, bg[1] / 255.0f, bg[2] / 255.0f, bg[3] / 255.0f};
-    if (out_premul) ot_fine_frame_mt(c, bgf, w, h, threads, out_premul);
-    double t3 = now_s();
-    if (tm) { tm->t_flatten = t1 - t0; tm->t_coarse = t2 - t1; tm->t_fine = t3 - t2; tm->n_lines = n; tm->n_segments = c->n_segments;
-              tm->n_ptcl_words = c->ptcl_offsets[c->width_in_tiles * c->height_in_tiles]; }
-    ot_coarse_free(c); free(el); free(start); free(lines);
-    return 0;
+    if (t_flatten) *t_flatten = t1 - t0;
+    if (n_lines_out) *n_lines_out = n;
+    free(el); free(start); free(lines);
+    return c;
 }

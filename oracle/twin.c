@@ -626,6 +626,10 @@ void ot_line_bbox(const ot_line_soup *lines, uint32_t n, int w, int h, uint32_t 
     if (min_y < 0) min_y = 0;
     if (max_x > (float)w) max_x = (float)w;
     if (max_y > (float)h) max_y = (float)h;
+    /* Guard (deviation, documented in DESIGN.md): a path entirely off the canvas makes the reference's
+     * uint32 conversions wrap (coarse.go:203-216) -- a huge or full-width bbox, i.e. a panic or wasted
+     * empty tiles, never a visible pixel. Oracle and product both give such paths an empty bbox. */
+    if (n == 0 || max_x < min_x || max_y < min_y) { bbox[0] = bbox[1] = bbox[2] = bbox[3] = 0; return; }
     /* Go: uint32(math.Floor(float64(minX / 16))) -- float64->uint32 goes through int64 on amd64 */
     uint32_t x0 = (uint32_t)(int64_t)floor((double)(min_x / (float)TILE_W));
     uint32_t y0 = (uint32_t)(int64_t)floor((double)(min_y / (float)TILE_H));
@@ -813,7 +817,11 @@ static void ptcl_push(ptcl *p, uint32_t w) {
     if (p->n == p->cap) { p->cap = p->cap ? p->cap * 2 : 64; p->cmds = (uint32_t *)realloc(p->cmds, sizeof(uint32_t) * p->cap); }
     p->cmds[p->n++] = w;
 }
-typedef struct { uint32_t clip_depth, clip_zero_depth, blend_depth, max_blend_depth; } tile_clip_state;  /* coarse.go:313-320 */
+typedef struct { uint32_t clip_depth, clip_zero_depth, blend_depth, max_blend_depth;   /* coarse.go:313-320 */
+                 uint32_t *begin_pos; uint32_t n_begin, cap_begin; } tile_clip_state;   /* + PTCL position of every open BeginClip (ggcuda layer elision) */
+/* ggcuda extension (not in the reference, which never maps layers to PTCL): a BeginClip whose blend word has
+ * bit 31 set is removed again, together with its EndClip, when no command was written between them in a tile. */
+#define OT_BLEND_ELIDE_EMPTY 0x80000000u
 
 /* coarse.go:651-679 tileSegRange */
 static void tile_seg_range(ot_tile tile, int local_idx, int tile_count, const ot_tile *path_tiles, uint32_t total,
@@ -1052,6 +1060,8 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                     if (!has_seg && !has_bd) {
                         cs->clip_zero_depth = cs->clip_depth + 1;
                     } else {
+                        if (cs->n_begin == cs->cap_begin) { cs->cap_begin = cs->cap_begin ? cs->cap_begin * 2 : 4; cs->begin_pos = (uint32_t *)realloc(cs->begin_pos, 4 * cs->cap_begin); }
+                        cs->begin_pos[cs->n_begin++] = ptcls[g].n;
                         ptcl_push(&ptcls[g], CMD_BEGIN_CLIP);
                         cs->blend_depth++;
                         if (cs->blend_depth > cs->max_blend_depth) cs->max_blend_depth = cs->blend_depth;
@@ -1078,6 +1088,12 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                     if (cs->clip_zero_depth > 0) continue;
                     int li = ty * bw + tx;
                     uint32_t tix = path.tiles + (uint32_t)li;
+                    uint32_t bpos = cs->n_begin ? cs->begin_pos[--cs->n_begin] : 0;
+                    if ((blend & OT_BLEND_ELIDE_EMPTY) && ptcls[g].n == bpos + 1) {   /* nothing between Begin and End */
+                        ptcls[g].n = bpos;
+                        cs->blend_depth--;
+                        continue;
+                    }
                     if (tix < n_tiles) {
                         ot_tile t = tiles[tix];
                         uint32_t cnt, st;
@@ -1100,6 +1116,7 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                 }
             }
         }
+        for (int i = 0; i < n_grid; i++) free(cs_all[i].begin_pos);
         free(cs_all);
     }
     /* WriteEnd on every tile (coarse.go:148-151) and flatten to one array */

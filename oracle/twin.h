@@ -111,6 +111,7 @@ void ot_line_bbox(const ot_line_soup *lines, uint32_t n, int w, int h, uint32_t 
 typedef struct { double t_flatten, t_coarse, t_fine; uint32_t n_lines, n_segments, n_ptcl_words; } ot_timing;
 int ot_render_packed(const uint32_t *scene, const uint32_t *layout13, int w, int h, const uint8_t bg_premul[4],
                      int threads, uint8_t *out_premul, ot_timing *timing);
+ot_coarse *ot_coarse_from_packed(const uint32_t *scene, const uint32_t *layout13, int w, int h);
 /* flatten stage alone: lines (path_ix set) for every path of the packed scene; returns count (cap as ot_flatten_fill) */
 uint32_t ot_flatten_packed(const uint32_t *scene, const uint32_t *layout13, ot_line_soup *out, uint32_t cap);
 /* multi-threaded ot_fine_frame */

@@ -163,11 +163,13 @@ def _view(ptr, n, dtype):
 class Coarse:
     """Copy-out of ot_coarse (coarse.go:17-43 CoarseOutput + scan results)."""
 
-    def __init__(self, elems, lines, w, h):
+    def __init__(self, elems, lines, w, h, _handle=None):
         L = lib()
-        elems = np.ascontiguousarray(elems, dtype=ELEMENT)
-        lines = np.ascontiguousarray(lines, dtype=LINE)
-        self._c = L.ot_coarse_run(_p(elems), len(elems), _p(lines), w, h)
+        if _handle is None:
+            elems = np.ascontiguousarray(elems, dtype=ELEMENT)
+            lines = np.ascontiguousarray(lines, dtype=LINE)
+            _handle = L.ot_coarse_run(_p(elems), len(elems), _p(lines), w, h)
+        self._c = _handle
         c = self._c.contents
         self.w, self.h = w, h
         self.wt, self.ht = c.width_in_tiles, c.height_in_tiles
@@ -184,6 +186,16 @@ class Coarse:
         self.tag_monoids = _view(c.tag_monoids, c.n_tag_words, PATH_MONOID)
         self.draw_monoids = _view(c.draw_monoids, c.layout.n_draw_objects, DRAW_MONOID)
         self.info = _view(c.info, c.n_info, np.uint32)
+
+    @classmethod
+    def from_packed(cls, scene_words, layout, w, h):
+        """CPU pipeline up to PTCL from ggcuda's packed scene (oracle/packed.c)."""
+        L = lib()
+        L.ot_coarse_from_packed.restype = C.POINTER(_Coarse)
+        L.ot_coarse_from_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        sw = np.ascontiguousarray(scene_words, dtype=np.uint32)
+        l13 = _layout13(layout)
+        return cls(None, None, w, h, _handle=L.ot_coarse_from_packed(_p(sw), _p(l13), w, h))
 
     def ptcl(self, tile_ix):
         return self.ptcl_words[self.ptcl_offsets[tile_ix]:self.ptcl_offsets[tile_ix + 1]]

@@ -44,6 +44,25 @@ def gpu_scene(ctx, elems, w, h, bg=(0, 0, 0, 0), band=None):
     return out
 
 
+def gpu_encoding(ctx, enc, w, h, bg=(0, 0, 0, 0), band=None):
+    """Render a scene.Encoding (gg_b200.scene.Encoding) through ggcuda_add_encoding + ggcuda_flush."""
+    ctx.begin(w, h)
+    ctx.set_background(bg)
+    ht = (h + 15) // 16
+    ctx.set_band(*(band or (0, ht)))
+    ctx.add_encoding(*enc.streams())
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    ctx.flush(out, flags=G.KEEP_SCENE)
+    return out
+
+
+def oracle_from_ctx(ctx, w, h):
+    """CPU twin run on the packed scene the context uploaded (oracle/packed.c)."""
+    words = ctx.debug_read(G.BUF_SCENE, np.uint32)
+    lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+    return T.Coarse.from_packed(words, lay, w, h)
+
+
 def sorted_rows(a):
     """Sort a structured array's rows by their raw bytes (order-independent multiset comparison)."""
     if len(a) == 0:
@@ -64,7 +83,13 @@ def compare_stages(ctx, oc, elems, w, h, check_ptcl=True):
     order = np.argsort(gl["path_ix"], kind="stable")
     gls = gl[order]
     starts = np.searchsorted(gls["path_ix"], np.arange(n_paths + 1))
-    for p, e in enumerate(elems):
+    if elems is None:
+        # packed-scene oracle: both sides flatten in tag order, so the arrays must be identical
+        lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+        ol = T.flatten_packed(ctx.debug_read(G.BUF_SCENE, np.uint32), lay).astype(G.LINE)
+        assert len(ol) == len(gl), f"{len(gl)} lines, oracle {len(ol)}"
+        assert ol.tobytes() == gl.tobytes(), "flattened lines differ"
+    for p, e in enumerate(elems or []):
         g = gls[starts[p]:starts[p + 1]]
         if e["type"] == "end_clip":
             assert len(g) == 0

@@ -95,3 +95,68 @@ def test_bands_match_full_frame(ctx):
         acc[y0 * 16:y1 * 16] = part[y0 * 16:y1 * 16]
     mx, _, frac = U.pixel_diff(acc, full)
     assert mx <= 1 and frac < 0.001
+
+
+def _check_encoding(ctx, enc, w, h, bg=(0, 0, 0, 0)):
+    out = U.gpu_encoding(ctx, enc, w, h, bg)
+    oc = U.oracle_from_ctx(ctx, w, h)
+    rep = U.compare_stages(ctx, oc, None, w, h)
+    _, ref = oc.fine(_straight_bg(bg), straight=False, premul=True)
+    mx, mean, frac = U.pixel_diff(out, ref)
+    assert mx <= 1 and frac <= 0.002, (mx, frac)
+    return out, oc, rep
+
+
+def test_encoding_config1(ctx):
+    """BASELINE configs[0]: 512x512, 1 000 filled circles / cubic blobs through the scene.Encoding entry."""
+    from gg_b200 import scenes
+    enc, w, h = scenes.config1()
+    _check_encoding(ctx, enc, w, h)
+
+
+def test_encoding_layers_clips_transforms(ctx):
+    """Layers (elided where empty), clips, even-odd fills, strokes, round rects and non-identity transforms."""
+    from gg_b200 import scene as S
+    rng = np.random.default_rng(5)
+    sc = S.Scene()
+    w, h = 640, 480
+    for i in range(120):
+        if i % 10 == 0:
+            clip = S.circle_verbs_coords(rng.uniform(0, w), rng.uniform(0, h), rng.uniform(60, 200)) if i % 20 == 0 else None
+            sc.PushLayer(int(rng.integers(0, 16)), float(rng.uniform(0.3, 1.0)), clip)
+        t = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0) if i % 3 else (float(rng.uniform(0.5, 1.5)), float(rng.uniform(-0.3, 0.3)), float(rng.uniform(-20, 20)),
+                                                             float(rng.uniform(-0.3, 0.3)), float(rng.uniform(0.5, 1.5)), float(rng.uniform(-20, 20)))
+        shape = S.circle_verbs_coords(rng.uniform(0, w), rng.uniform(0, h), rng.uniform(5, 60))
+        col = (*rng.uniform(0, 1, 3), rng.uniform(0.3, 1.0))
+        if i % 4 == 1:
+            sc.Stroke(dict(width=float(rng.uniform(1, 9)), cap=int(rng.integers(0, 3)), join=int(rng.integers(0, 3))), t, col, shape)
+        elif i % 4 == 2:
+            sc.Fill(S.FillEvenOdd, t, col, shape)
+        else:
+            sc.Fill(S.FillNonZero, t, col, shape)
+        if i % 10 == 9:
+            sc.PopLayer()
+        if i % 17 == 0:
+            sc.enc.EncodeFillRoundRect(col, (rng.uniform(0, w / 2), rng.uniform(0, h / 2), rng.uniform(w / 2, w), rng.uniform(h / 2, h)), 12.0, 9.0)
+    _check_encoding(ctx, sc.Encoding(), w, h, bg=(255, 255, 255, 255))
+
+
+def test_buffer_growth_from_cold_context():
+    """A fresh context starts with small buffers: the first render must grow them (several passes) and still be right."""
+    from gg_b200 import _lib, scenes
+    c = _lib.Context(0)
+    try:
+        enc, w, h = scenes.config3(n=1500, w=1920, h=1080)
+        out = U.gpu_encoding(c, enc, w, h)
+        st = c.stats()
+        assert st["passes"] >= 1
+        oc = U.oracle_from_ctx(c, w, h)
+        U.compare_stages(c, oc, None, w, h)
+        _, ref = oc.fine((0, 0, 0, 0), straight=False, premul=True)
+        mx, _, frac = U.pixel_diff(out, ref)
+        assert mx <= 1 and frac <= 0.002
+        out2 = U.gpu_encoding(c, enc, w, h)
+        assert c.stats()["passes"] == 1, "steady state must be a single pass"
+        assert U.pixel_diff(out, out2)[0] <= 1
+    finally:
+        c.close()
