@@ -477,7 +477,11 @@ struct LoadTileCount {
 };
 struct LoadTileHits {   // + 2 words per tile: blend-offset word 0 and the CmdEnd terminator (ptcl.go:72-78, coarse.go:148-151)
     const unsigned long long* h;
-    __device__ unsigned long long operator()(uint32_t i) const { return h[i] + (2ull << 32); }
+    __device__ unsigned long long operator()(uint32_t i) const {
+        unsigned long long v = h[i] + (2ull << 32);
+        unsigned long long words = ((v >> 32) + 3ull) & ~3ull;   // pad every list to 16 bytes (bulk-copy granularity in fine)
+        return (v & 0xffffffffull) | (words << 32);
+    }
 };
 struct StoreTileHits {
     uint32_t* hit_off; uint32_t* hit_cnt; uint32_t* ptcl_off; uint32_t* hit_cursor; uint32_t* spill_off;
@@ -590,7 +594,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                                                                    const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
                                                                    const GGDrawMonoid* __restrict__ dm,
                                                                    const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ hit_cnt,
-                                                                   uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl,
+                                                                   uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len, uint32_t* ptcl,
                                                                    uint32_t* spill_off, GGBump* bump) {
     __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         uint32_t pos = ptcl_off[T];
         if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
         pos += 1;
-        if (n == 0) { if (lane == 0) ptcl[pos] = GG_CMD_END; continue; }
+        if (n == 0) { if (lane == 0) { ptcl[pos] = GG_CMD_END; ptcl_len[T] = 2; } continue; }
         uint32_t* sorted;
         if (n <= COARSE_CAP) {
             uint32_t np2 = 32; while (np2 < n) np2 <<= 1;
@@ -710,6 +714,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         }
         if (lane == 0) {
             ptcl[pos] = GG_CMD_END;
+            ptcl_len[T] = pos + 1 - ptcl_off[T];
             if (max_depth > GG_BLEND_STACK_SPLIT) {
                 uint32_t lv = max_depth - GG_BLEND_STACK_SPLIT;
                 uint32_t so = atomicAdd(&bump->spill, lv);
@@ -762,5 +767,5 @@ void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->hits));
     tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.bump);
     coarse_kernel<<<GG_GRID(4), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
-                                                           b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl, b.spill_off, b.bump);
+                                                           b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.bump);
 }

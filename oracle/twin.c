@@ -1187,17 +1187,19 @@ void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment 
             for (int i = 0; i < PC; i++) rgba[i][0] = rgba[i][1] = rgba[i][2] = rgba[i][3] = 0;
             break;
         case CMD_END_CLIP: {
-            float alpha = bits_f32(cmds[off + 1]);   /* cmds[off] = blend: ignored by the reference (fine.go:164) */
+            /* cmds[off] = blend word. The reference ignores it (fine.go:164: source-over only); ggcuda defines
+             * the layer composite as ot_blend_f32 (oracle/blend.c), which reduces to the reference's
+             * saved*(1-fg.a)+fg for the words the reference can emit (0 and 0x8003). */
+            uint32_t blend = cmds[off];
+            float alpha = bits_f32(cmds[off + 1]);
             off += 2;
             if (clip_depth == 0) continue;
             clip_depth--;
             float (*saved)[4] = stack[clip_depth];
             for (int i = 0; i < PC; i++) {
                 float scale = area[i] * alpha;
-                float fr = rgba[i][0] * scale, fg = rgba[i][1] * scale, fb = rgba[i][2] * scale, fa = rgba[i][3] * scale;
-                float inv = 1.0f - fa;
-                rgba[i][0] = saved[i][0] * inv + fr; rgba[i][1] = saved[i][1] * inv + fg;
-                rgba[i][2] = saved[i][2] * inv + fb; rgba[i][3] = saved[i][3] * inv + fa;
+                float fgc[4] = {rgba[i][0] * scale, rgba[i][1] * scale, rgba[i][2] * scale, rgba[i][3] * scale};
+                ot_blend_f32(blend, saved[i], fgc, rgba[i]);
             }
         } break;
         default: goto done;

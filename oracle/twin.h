@@ -103,6 +103,12 @@ void ot_path_tiling(const ot_segment_count *seg_counts, uint32_t n_seg_counts,
                     ot_path_segment *segments);
 void ot_line_bbox(const ot_line_soup *lines, uint32_t n, int w, int h, uint32_t bbox[4]);
 
+/* ---- blending (oracle/blend.c) ---- */
+/* bit-exact restatement of gg's byte blend functions, selected by scene.BlendMode; premultiplied RGBA8 */
+void ot_blend_bytes(uint32_t scene_mode, const uint8_t s[4], const uint8_t d[4], uint8_t out[4]);
+/* float32 layer composite applied at CmdEndClip: bg (blend) fg, premultiplied; blend = (mix << 8) | compose */
+void ot_blend_f32(uint32_t blend, const float bg[4], const float fg[4], float out[4]);
+
 /* ---- whole pipeline from ggcuda's packed scene (the a2 format: Vello path tags incl. 0x0C MoveTo,
  *      quads/cubics, real transforms). CPU restatement of the product's device stages a6..a13:
  *      flatten every curve (transform in f32 as scene/encoding.go:348-350, quad elevation as

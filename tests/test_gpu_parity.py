@@ -160,3 +160,35 @@ def test_buffer_growth_from_cold_context():
         assert U.pixel_diff(out, out2)[0] <= 1
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("bg", [(0, 0, 0, 0), (255, 255, 255, 255), (40, 80, 120, 200)])
+def test_all_29_blend_modes(ctx, bg):
+    """One layer per scene.BlendMode over a varied backdrop; CUDA fine vs the oracle's float32 definition."""
+    from gg_b200 import scene as S
+    rng = np.random.default_rng(29)
+    sc = S.Scene()
+    w, h = 29 * 40, 160
+    for i in range(40):   # backdrop: translucent blobs over the whole strip
+        sc.Fill(S.FillNonZero, S.IDENTITY, (*rng.uniform(0, 1, 3), rng.uniform(0.3, 1.0)),
+                S.circle_verbs_coords(rng.uniform(0, w), rng.uniform(0, h), rng.uniform(20, 90)))
+    for mode in range(S.NUM_BLEND_MODES):
+        x0 = mode * 40
+        sc.PushLayer(mode, float(rng.uniform(0.5, 1.0)), S.rect_verbs_coords(x0 + 2, 4, x0 + 38, h - 4) if mode % 2 else None)
+        for _ in range(3):
+            sc.Fill(S.FillNonZero, S.IDENTITY, (*rng.uniform(0, 1, 3), rng.uniform(0.2, 1.0)),
+                    S.circle_verbs_coords(x0 + rng.uniform(5, 35), rng.uniform(10, h - 10), rng.uniform(8, 30)))
+        sc.PopLayer()
+    _check_encoding(ctx, sc.Encoding(), w, h, bg=bg)
+
+
+def test_deep_clip_stack_spills(ctx):
+    """Seven nested layers/clips: levels 0-1 shared memory, 2-3 local memory, 4+ global spill (fine.go:58-62)."""
+    from gg_b200 import scene as S
+    sc = S.Scene()
+    w, h = 200, 200
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0.2, 0.4, 0.9, 1.0), S.rect_verbs_coords(10, 10, 190, 190))
+    for d in range(7):
+        sc.PushLayer(d % 3, 0.9, S.circle_verbs_coords(100, 100, 95 - 8 * d))
+        sc.Fill(S.FillNonZero, S.IDENTITY, (0.9 - 0.1 * d, 0.1 * d, 0.5, 0.7), S.rect_verbs_coords(20 + 5 * d, 30, 180 - 5 * d, 170))
+    _check_encoding(ctx, sc.Encoding(), w, h, bg=(255, 255, 255, 255))
