@@ -1,0 +1,192 @@
+"""CPU tests (no GPU): the C-ABI library loads and exports every declared symbol, host-side scene packing
+(host-only context, no compute), and the multi-rank band assembly over gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from gg_b200 import _lib, scene as S, scenes
+from oracle import twin as T
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "ggcuda.h")).read()
+    declared = set(re.findall(r"GGCUDA_API\s+[\w\s\*]+?\b(ggcuda_\w+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l and "ggcuda_" in l}
+    assert exported == declared, exported ^ declared   # nothing else leaks out of the shared object
+
+
+def test_no_cpu_fallback():
+    """A host-only context packs scenes but refuses to render; there is no software path in the product."""
+    c = _lib.Context(-1)
+    c.begin(64, 64)
+    c.fill_path([0, 1, 1, 4], [1, 1, 30, 1, 15, 30], (255, 0, 0, 255))
+    with pytest.raises(_lib.GGCudaError) as e:
+        c.flush(np.zeros((64, 64, 4), np.uint8))
+    assert e.value.code == _lib.ERR_UNSUPPORTED
+    src = "".join(open(os.path.join(ROOT, "gg_b200", f)).read() for f in os.listdir(os.path.join(ROOT, "gg_b200")) if f.endswith(".py"))
+    assert "oracle" not in src.replace("oracle/", "")   # the package never imports the test oracle
+
+
+def _pack(build):
+    c = _lib.Context(-1)
+    c.begin(256, 128)
+    build(c)
+    words, lay = c.pack_host()
+    c.close()
+    return words, lay
+
+
+def _tags(words, lay):
+    return words[lay["path_tag_base"]:lay["path_tag_base"] + lay["n_tag_words"]].view(np.uint8)[:lay["n_tag_bytes"]]
+
+
+def test_packed_layout_and_autoclose():
+    """PackedScene layout (scene_encode.go:280-356) and the ingest rules: one Transform when it changes, one Style and
+    one Path marker per draw, MoveTo tag 0x0C, open subpaths closed, zero-length closes dropped."""
+    def build(c):
+        c.fill_path([0, 1, 1], [10, 10, 50, 10, 30, 40], (255, 0, 0, 255), 0)           # open triangle -> closing line added
+        c.fill_path([0, 1, 1, 1, 4], [60, 10, 90, 10, 90, 40, 60, 10], (0, 255, 0, 128), 1)   # explicit return to start + Close
+    words, lay = _pack(build)
+    assert lay["n_tag_words"] % 256 == 0 and lay["path_tag_base"] == 0
+    assert lay["path_data_base"] == lay["n_tag_words"]
+    assert (lay["n_draws"], lay["n_paths"], lay["n_clips"]) == (2, 2, 0)
+    assert list(_tags(words, lay)) == [0x20, 0x40, 0x0C, 0x09, 0x09, 0x09, 0x10, 0x40, 0x0C, 0x09, 0x09, 0x09, 0x10]
+    pd = words[lay["path_data_base"]:lay["draw_tag_base"]].view(np.float32)
+    assert list(pd[:8]) == [10, 10, 50, 10, 30, 40, 10, 10]
+    assert list(words[lay["draw_tag_base"]:lay["draw_data_base"]]) == [0x44, 0x44]
+    a = np.float32(128) / np.float32(255)
+    assert int(words[lay["draw_data_base"]]) == 0xFF0000FF
+    assert int(words[lay["draw_data_base"] + 1]) == (int(np.float32(255) * a + np.float32(0.5)) << 8) | (128 << 24)
+    assert list(words[lay["style_base"]:lay["style_base"] + 2]) == [0, 2]                 # even-odd = bit 1
+    assert list(words[lay["transform_base"]:lay["style_base"]].view(np.float32)) == [1, 0, 0, 0, 1, 0]
+    # monoids of the packed tags agree with the oracle's restatement of pathtag.go
+    m = T.path_monoid(int(words[0]))
+    assert (int(m["trans_ix"]), int(m["style_ix"]), int(m["path_seg_ix"]), int(m["path_seg_offset"])) == (1, 1, 1, 4)
+
+
+def test_clip_and_layer_pairing():
+    def build(c):
+        c.push_layer(S.BlendMultiply, 0.5)
+        c.push_clip([0, 1, 1, 4], [0, 0, 100, 0, 50, 100])
+        c.fill_path([0, 1, 1, 4], [10, 10, 50, 10, 30, 40], (255, 0, 0, 255))
+        c.pop()
+        c.pop()
+        c.push_layer(S.BlendClear, 1.0)
+        # left open on purpose: packing closes it (scene/renderer.go:789-797)
+    words, lay = _pack(build)
+    assert (lay["n_draws"], lay["n_clips"]) == (7, 6)
+    dt = list(words[lay["draw_tag_base"]:lay["draw_data_base"]])
+    assert dt == [0x9, 0x9, 0x44, 0x21, 0x21, 0x9, 0x21]
+    aux = words[lay["clip_aux_base"]:lay["clip_aux_base"] + 14].view(np.int32).reshape(7, 2)
+    assert list(aux[:, 0]) == [-1, 0, 1, 1, 0, -1, 5]          # enclosing clip (EndClip: its own BeginClip)
+    assert aux[0, 1] == 4 and aux[1, 1] == 3 and aux[5, 1] == 6  # Begin -> End links
+    dd = words[lay["draw_data_base"]:lay["transform_base"]]
+    assert dd[0] == ((S.BlendMultiply << 8) | 3) | 0x80000000   # mix mode, SrcOver compose, elidable when empty
+    assert dd[1] == np.float32(0.5).view(np.uint32)
+    assert dd[2] == 0x8003                                       # plain clip
+    assert dd[5] == 0                                            # Clear compose: must cover the canvas, not elidable
+    # the Multiply layer's rectangle was shrunk to the tile-aligned bounds of its content (10..50 x 10..40)
+    pd = words[lay["path_data_base"]:lay["draw_tag_base"]].view(np.float32)
+    assert list(pd[:10]) == [0, 0, 64, 0, 64, 48, 0, 48, 0, 0]
+
+
+def test_encoding_ingest_matches_per_draw_calls():
+    """scene.Encoding streams (tags 0x01..0x41) produce the same packed scene as the equivalent per-draw calls."""
+    sc = S.Scene()
+    shape = S.circle_verbs_coords(40, 40, 20)
+    sc.Fill(S.FillEvenOdd, S.IDENTITY, (1.0, 0.5, 0.0, 0.5), shape)
+    sc.PushClip(S.rect_verbs_coords(0, 0, 50, 50))
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0.0, 0.0, 1.0, 1.0), shape)
+    sc.PopClip()
+    c = _lib.Context(-1)
+    c.begin(256, 128)
+    c.add_encoding(*sc.Encoding().streams())
+    w1, l1 = c.pack_host()
+    c.begin(256, 128)
+    col = lambda rgba: tuple(int(min(255.0, v * 255.0 + 0.5)) for v in rgba)
+    c.fill_path(*shape, col((1.0, 0.5, 0.0, 0.5)), 1)
+    c.push_clip(*S.rect_verbs_coords(0, 0, 50, 50))
+    c.fill_path(*shape, col((0.0, 0.0, 1.0, 1.0)), 0)
+    c.pop()
+    w2, l2 = c.pack_host()
+    assert l1 == l2 and (w1 == w2).all()
+
+
+def test_unsupported_tags_are_reported():
+    c = _lib.Context(-1)
+    c.begin(64, 64)
+    with pytest.raises(_lib.GGCudaError) as e:
+        c.add_encoding(np.array([S.TagImage], np.uint8), [], [0], [1, 0, 0, 0, 1, 0], [])
+    assert e.value.code == _lib.ERR_UNSUPPORTED     # the Go binding maps this to gg.ErrFallbackToCPU
+    with pytest.raises(_lib.GGCudaError) as e:
+        c.add_encoding(np.array([S.TagFill], np.uint8), [], [], [], [])
+    assert e.value.code == _lib.ERR_INVALID         # stream underrun
+
+
+def test_stroke_outline_area():
+    """Host stroke expansion: the outline's area (through the oracle) is length x width (+ caps) within 2 %."""
+    for cap, extra in ((0, 0.0), (2, 1.0), (1, np.pi / 4)):
+        c = _lib.Context(-1)
+        c.begin(128, 64)
+        c.stroke_path([0, 1], [20, 32, 100, 32], (255, 255, 255, 255), 10.0, cap, 0, 4.0)
+        words, lay = c.pack_host()
+        img, _ = T.render_packed(words, lay, 128, 64)
+        area = img[..., 3].astype(np.float64).sum() / 255
+        want = 80 * 10 + extra * 10 * 10
+        assert abs(area - want) / want < 0.02, (cap, area, want)
+
+
+def test_config_generators_are_deterministic():
+    a = scenes.config1()[0].streams()
+    b = scenes.config1()[0].streams()
+    assert all((x == y).all() for x, y in zip(a, b))
+    enc, w, h = scenes.config3(n=200, w=640, h=480)
+    tags = enc.streams()[0]
+    assert (tags == S.TagPushLayer).sum() == (tags == S.TagPopLayer).sum() >= 4
+    assert (tags == S.TagStroke).sum() > 0 and (tags == S.TagBeginClip).sum() == (tags == S.TagEndClip).sum()
+
+
+def test_bands_assemble_over_gloo(tmp_path):
+    """world_size-2 gloo run of the band decomposition: each rank produces its band (here with the oracle, since
+    there is no GPU and no fallback) and one all_gather_into_tensor assembles the frame on every rank."""
+    script = tmp_path / "rank.py"
+    script.write_text(f'''
+import os, sys
+sys.path.insert(0, {ROOT!r})
+import numpy as np, torch, torch.distributed as dist
+from gg_b200 import _lib, bands, scenes
+from oracle import twin as T
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+enc, w, h = scenes.config3(n=300, w=320, h=200)
+c = _lib.Context(-1); c.begin(w, h); c.add_encoding(*enc.streams()); words, lay = c.pack_host()
+full, _ = T.render_packed(words, lay, w, h)
+y0, y1 = bands.band_rows(h, world, rank)
+frame = bands.alloc_frame(w, h, world, "cpu")
+band = bands.band_view(frame, h, world, rank)
+rows = full[y0 * 16:min(y1 * 16, h)]
+band[:rows.shape[0]] = torch.from_numpy(rows.copy())
+bands.assemble(frame, h, world, rank)
+assert (frame[:h].numpy() == full).all(), "assembled frame differs"
+assert frame.shape[0] == bands.padded_height(h, world) and frame.shape[0] % (16 * world) == 0
+dist.destroy_process_group()
+print("rank", rank, "ok")
+''')
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", str(script)], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("ok") == 2
