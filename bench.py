@@ -164,7 +164,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from gg_b200 import _lib, scenes
+    from gg_b200 import _lib, bands, scenes
     from gg_b200.accelerator import CUDAAccelerator, GPURenderTarget
 
     torch.cuda.set_device(local_rank)
@@ -174,28 +174,25 @@ def main():
 
     enc, w, h = scenes.config3(bands=world)
     streams = enc.streams()
-    ht = (h + 15) // 16
-    rows_per = ht // world
-    y0, y1 = rank * rows_per, (rank + 1) * rows_per if rank < world - 1 else ht
-    assert ht % world == 0, "bands must be equal for all_gather_into_tensor"
+    y0, y1 = bands.band_rows(h, world, rank)
 
     ctx = _lib.Context(local_rank)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()          # kernels, events and the all-gather all go through this stream
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_timing(True)
     ctx.begin(w, h)
     ctx.add_encoding(*streams)
     ctx.set_band(y0, y1)
     ctx.upload()
-    frame = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")   # full canvas on every rank (all-gather target)
-    band = frame[y0 * 16:min(y1 * 16, h)]
+    frame = bands.alloc_frame(w, h, world, "cuda")   # full canvas on every rank (all-gather target)
+    band = bands.band_view(frame, h, world, rank)     # fine writes its band straight into the gather buffer
     stride = w * 4
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def step():
         ctx.render_device(band.data_ptr(), stride, _lib.KEEP_SCENE)
-        if world > 1:
-            dist.all_gather_into_tensor(frame.view(-1), band.reshape(-1))
+        bands.assemble(frame, h, world, rank)
 
     for _ in range(args.warmup):
         step()

@@ -113,9 +113,8 @@ __device__ __forceinline__ float sep_mix(uint32_t mix, float s, float d) {
 // bg (blend) fg for a mix mode 1..15 (always composed SrcOver)
 __device__ __noinline__ float4 blend_mix_px(uint32_t mix, float4 bg, float4 fg) {
     float sa = fg.w, da = bg.w;
-    if (sa <= 0.0f) return bg;
-    if (da <= 0.0f) return fg;
-    float csr = fg.x / sa, csg = fg.y / sa, csb = fg.z / sa, cdr = bg.x / da, cdg = bg.y / da, cdb = bg.z / da, br, bgc, bb;
+    float isa = 1.0f / sa, ida = 1.0f / da;   // callers guarantee sa > 0 and da > 0
+    float csr = fg.x * isa, csg = fg.y * isa, csb = fg.z * isa, cdr = bg.x * ida, cdg = bg.y * ida, cdb = bg.z * ida, br, bgc, bb;
     if (mix >= 12) {
         if (mix == 12) { br = csr; bgc = csg; bb = csb; set_sat(br, bgc, bb, max3f(cdr, cdg, cdb) - min3f(cdr, cdg, cdb)); set_lum(br, bgc, bb, lum3(cdr, cdg, cdb)); }
         else if (mix == 13) { br = cdr; bgc = cdg; bb = cdb; set_sat(br, bgc, bb, max3f(csr, csg, csb) - min3f(csr, csg, csb)); set_lum(br, bgc, bb, lum3(cdr, cdg, cdb)); }
@@ -132,29 +131,24 @@ __device__ __noinline__ float4 blend_mix_px(uint32_t mix, float4 bg, float4 fg) 
     o.w = sa + da * (1.0f - sa);
     return o;
 }
-// Porter-Duff compose (Normal mix): Fa * S + Fb * D
-__device__ __forceinline__ float4 blend_compose_px(uint32_t compose, float4 bg, float4 fg) {
-    float sa = fg.w, da = bg.w, fa, fb;
-    switch (compose) {
-    case 0: fa = 0; fb = 0; break;
-    case 1: fa = 1; fb = 0; break;
-    case 2: fa = 0; fb = 1; break;
-    case 4: fa = 1 - da; fb = 1; break;
-    case 5: fa = da; fb = 0; break;
-    case 6: fa = 0; fb = sa; break;
-    case 7: fa = 1 - da; fb = 0; break;
-    case 8: fa = 0; fb = 1 - sa; break;
-    case 9: fa = da; fb = 1 - sa; break;
-    case 10: fa = 1 - da; fb = sa; break;
-    case 11: fa = 1 - da; fb = 1 - sa; break;
-    case 12: fa = 1; fb = 1; break;
-    default: fa = 1; fb = 1 - sa; break;
-    }
-    float4 o = make_float4(fa * fg.x + fb * bg.x, fa * fg.y + fb * bg.y, fa * fg.z + fb * bg.z, fa * fg.w + fb * bg.w);
-    if (compose == 12) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
-    return o;
-}
-
+// Porter-Duff compose (Normal mix): Fa * S + Fb * D with Fa = a0 + a1 * Da and Fb = b0 + b1 * Sa
+// (porter_duff.go:117-216); one table row per compose mode keeps the per-pixel code branch free.
+__constant__ float4 COMPOSE_COEF[14] = {
+    {0, 0, 0, 0},    // Clear
+    {1, 0, 0, 0},    // Copy
+    {0, 0, 1, 0},    // Dest
+    {1, 0, 1, -1},   // SrcOver
+    {1, -1, 1, 0},   // DestOver
+    {0, 1, 0, 0},    // SrcIn
+    {0, 0, 0, 1},    // DestIn
+    {1, -1, 0, 0},   // SrcOut
+    {0, 0, 1, -1},   // DestOut
+    {0, 1, 1, -1},   // SrcAtop
+    {1, -1, 0, 1},   // DestAtop
+    {1, -1, 1, -1},  // Xor
+    {1, 0, 1, 0},    // Plus (clamped)
+    {1, 0, 1, -1},   // PlusLighter: not produced by gg, treated as SrcOver
+};
 // ---------------------------------------------------------------- PTCL streaming through shared memory (TMA)
 // Each warp streams its tile's command list through a private two-slot ring in shared memory: 1-D bulk
 // async copies (cp.async.bulk, SASS UBLKCP) complete on a per-slot mbarrier, the next chunk is in flight
@@ -211,16 +205,18 @@ struct PtclStream {
         issue(0);
         issue(1);
     }
-    __device__ __forceinline__ uint32_t word(uint32_t i) {
-        while (i >= loaded_end) {   // first touch of a new chunk: wait for it, then refill the slot behind us
+    // Make words [.., i] available: wait for the chunk(s) they live in and refill the slot behind us.
+    // Called once per command (the longest command is 4 words), so the decode loop has a single copy of it.
+    __device__ __forceinline__ void ensure(uint32_t i) {
+        while (i >= loaded_end && loaded_end < issued * PTCL_CHUNK) {
             uint32_t chunk = loaded_end / PTCL_CHUNK, slot = chunk & 1u;
             mbar_wait(bars + slot, (parity >> slot) & 1u);
             parity ^= 1u << slot;
             loaded_end += PTCL_CHUNK;
             if (chunk >= 1) { __syncwarp(); issue(chunk + 1); }
         }
-        return ring[i & (2 * PTCL_CHUNK - 1)];
     }
+    __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
 };
 
 // Area of one CmdFill (fine.go:219-276 fillPath) for the 8 pixels of this lane.
@@ -323,7 +319,7 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
+__global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
                                                                float4* spill, const GGBump* __restrict__ bump, uint8_t* dst, size_t stride) {
@@ -353,11 +349,10 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    // Blend stack (fine.go:58-62: 4 levels "in registers", deeper levels spill). Levels 0-1 live in shared
-    // memory ([level][pixel][lane] so that 128-bit accesses are conflict free), levels 2-3 in local memory,
-    // deeper ones in the global spill buffer: a local-memory stack alone pushed ~10 GB of write-through
-    // traffic to L2 per 4K frame of the benchmark scene (73 layer composites per tile).
-    float4 stack[GG_BLEND_STACK_SPLIT - 2][PX];
+    // Blend stack (fine.go:58-62 keeps 4 levels "in registers" and spills deeper ones; where a level lives is
+    // invisible in the output). Levels 0-1 live in shared memory ([level][pixel][lane]: conflict-free 128-bit
+    // accesses), deeper levels in the global spill buffer coarse sized for this tile. A local-memory stack
+    // pushed ~10 GB of write-through traffic to L2 per 4K frame of the benchmark scene (73 composites per tile).
 
     for (uint32_t T = warp_global; T < n_tiles; T += n_warps) {
         const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
@@ -384,26 +379,27 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, con
         uint32_t cmd = 1;   // word 0 = blend offset (ptcl.go:98)
         const uint32_t sp_off = spill_off[T];
         for (;;) {
-            uint32_t tag = ps.word(cmd++);
-            if (tag == GG_CMD_END) break;
+            ps.ensure(cmd + 3);
+            const uint32_t tag = ps.word(cmd);
             if (tag == GG_CMD_FILL) {
-                uint32_t packed = ps.word(cmd), seg_ix = ps.word(cmd + 1);
-                float backdrop = (float)(int32_t)ps.word(cmd + 2);
-                cmd += 3;
-                uint32_t n = packed >> 1;
-                fill_area(area, acc, suf, segments + seg_ix, n, backdrop, lane);
-                if (packed & 1u) {
+                const uint32_t packed = ps.word(cmd + 1), seg_ix = ps.word(cmd + 2);
+                const float backdrop = (float)(int32_t)ps.word(cmd + 3);
+                cmd += 4;
+                fill_area(area, acc, suf, segments + seg_ix, packed >> 1, backdrop, lane);
+                const bool even_odd = packed & 1u;
 #pragma unroll
-                    for (int i = 0; i < PX; i++) area[i] = fabsf(area[i] - 2.0f * roundf(0.5f * area[i]));   // fine.go:281
-                } else {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) area[i] = fminf(fabsf(area[i]), 1.0f);                      // fine.go:286
+                for (int i = 0; i < PX; i++) {
+                    float a = area[i];
+                    area[i] = even_odd ? fabsf(a - 2.0f * roundf(0.5f * a))    // fine.go:281
+                                       : fminf(fabsf(a), 1.0f);                // fine.go:286
                 }
             } else if (tag == GG_CMD_SOLID) {
+                cmd += 1;
 #pragma unroll
                 for (int i = 0; i < PX; i++) area[i] = 1.0f;
             } else if (tag == GG_CMD_COLOR) {
-                float4 c = unpack_rgba8(ps.word(cmd++));
+                const float4 c = unpack_rgba8(ps.word(cmd + 1));
+                cmd += 2;
 #pragma unroll
                 for (int i = 0; i < PX; i++) {   // fine.go:104-123
                     float cov = area[i];
@@ -413,66 +409,58 @@ __global__ void __launch_bounds__(FINE_WARPS * 32) fine_kernel(GGConfig cfg, con
                     rgba[i].z = fmaf(rgba[i].z, inv, fb); rgba[i].w = fmaf(rgba[i].w, inv, fa);
                 }
             } else if (tag == GG_CMD_BEGIN_CLIP) {   // fine.go:125-138
-                if (clip_depth < 2) {
+                cmd += 1;
+                float4* slot; uint32_t step;
+                if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
+                else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
+                if (clip_depth < GG_BLEND_STACK_SPLIT || sp_off != 0xffffffffu) {
 #pragma unroll
-                    for (int i = 0; i < PX; i++) sstk[clip_depth][i][lane] = rgba[i];
-                } else if (clip_depth < GG_BLEND_STACK_SPLIT) {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) stack[clip_depth - 2][i] = rgba[i];
-                } else if (sp_off != 0xffffffffu) {
-                    float4* sp = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX);
-#pragma unroll
-                    for (int i = 0; i < PX; i++) sp[i] = rgba[i];
+                    for (int i = 0; i < PX; i++) { slot[i * step] = rgba[i]; }
                 }
                 clip_depth++;
 #pragma unroll
                 for (int i = 0; i < PX; i++) rgba[i] = make_float4(0, 0, 0, 0);
             } else if (tag == GG_CMD_END_CLIP) {     // fine.go:140-180
-                const uint32_t blend = ps.word(cmd) & 0x7fffffffu;
-                float alpha = __uint_as_float(ps.word(cmd + 1));
-                cmd += 2;
+                const uint32_t blend = ps.word(cmd + 1) & 0x7fffffffu;
+                const float alpha = __uint_as_float(ps.word(cmd + 2));
+                cmd += 3;
                 if (clip_depth == 0) continue;
                 clip_depth--;
+                const float4* slot; uint32_t step;
+                if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
+                else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
                 float4 svd[PX];
-                if (clip_depth < 2) {
 #pragma unroll
-                    for (int i = 0; i < PX; i++) svd[i] = sstk[clip_depth][i][lane];
-                } else if (clip_depth < GG_BLEND_STACK_SPLIT) {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) svd[i] = stack[clip_depth - 2][i];
-                } else {
-                    const float4* sp = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX);
-#pragma unroll
-                    for (int i = 0; i < PX; i++) svd[i] = sp[i];
+                for (int i = 0; i < PX; i++) {
+                    svd[i] = slot[i * step];
+                    float scale = area[i] * alpha;   // fg = rgba * area * alpha, in place
+                    rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
                 }
                 const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
-                if ((mix == 0u || mix == 0x80u) && compose == 3u) {   // Normal / clip, SrcOver: fine.go:168-179
+                if (mix != 0u && mix < 16u) {
+                    // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source); only
+                    // pixels where both are visible take the (un-premultiply, mix, re-compose) path
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
-                        float scale = area[i] * alpha;
-                        float fr = rgba[i].x * scale, fg = rgba[i].y * scale, fb = rgba[i].z * scale, fa = rgba[i].w * scale;
-                        float inv = 1.0f - fa;
-                        float4 sv = svd[i];
-                        rgba[i].x = fmaf(sv.x, inv, fr); rgba[i].y = fmaf(sv.y, inv, fg);
-                        rgba[i].z = fmaf(sv.z, inv, fb); rgba[i].w = fmaf(sv.w, inv, fa);
-                    }
-                } else if (mix != 0u && mix < 16u) {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) {
-                        float scale = area[i] * alpha;
-                        float4 f = make_float4(rgba[i].x * scale, rgba[i].y * scale, rgba[i].z * scale, rgba[i].w * scale);
-                        rgba[i] = blend_mix_px(mix, svd[i], f);
+                        if (rgba[i].w <= 0.0f) rgba[i] = svd[i];
+                        else if (svd[i].w > 0.0f) rgba[i] = blend_mix_px(mix, svd[i], rgba[i]);
                     }
                 } else {
+                    // Porter-Duff: Fa * S + Fb * D. Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}.
+                    const float4 k = COMPOSE_COEF[min(compose, 13u)];
+                    const bool plus = compose == 12u;
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
-                        float scale = area[i] * alpha;
-                        float4 f = make_float4(rgba[i].x * scale, rgba[i].y * scale, rgba[i].z * scale, rgba[i].w * scale);
-                        rgba[i] = blend_compose_px(compose, svd[i], f);
+                        float fa = k.x + k.y * svd[i].w, fb = k.z + k.w * rgba[i].w;
+                        float4 o;
+                        o.x = fmaf(fb, svd[i].x, fa * rgba[i].x); o.y = fmaf(fb, svd[i].y, fa * rgba[i].y);
+                        o.z = fmaf(fb, svd[i].z, fa * rgba[i].z); o.w = fmaf(fb, svd[i].w, fa * rgba[i].w);
+                        if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
+                        rgba[i] = o;
                     }
                 }
             } else {
-                break;   // unknown command: stop (fine.go:182-185)
+                break;   // CmdEnd, or an unknown command: stop (fine.go:182-185)
             }
         }
         if (row_in) {

@@ -197,7 +197,8 @@ void ot_blend_f32(uint32_t blend, const float bg[4], const float fg[4], float ou
     if (mix != 0 && mix < 16) {   /* mix modes always compose SrcOver: Co = (1-Da) S + (1-Sa) D + Sa Da B */
         if (sa <= 0.0f) { for (int k = 0; k < 4; k++) out[k] = bg[k]; return; }
         if (da <= 0.0f) { for (int k = 0; k < 4; k++) out[k] = fg[k]; return; }
-        float cs[3] = {fg[0] / sa, fg[1] / sa, fg[2] / sa}, cd[3] = {bg[0] / da, bg[1] / da, bg[2] / da}, b[3];
+        float isa = 1.0f / sa, ida = 1.0f / da;
+        float cs[3] = {fg[0] * isa, fg[1] * isa, fg[2] * isa}, cd[3] = {bg[0] * ida, bg[1] * ida, bg[2] * ida}, b[3];
         if (mix >= 12) hsl_blend((int)mix - 12, cs[0], cs[1], cs[2], cd[0], cd[1], cd[2], &b[0], &b[1], &b[2]);
         else for (int k = 0; k < 3; k++) b[k] = sep_f32(mix, cs[k], cd[k]);
         float sada = sa * da;
