@@ -383,8 +383,10 @@ int ggcuda_stroke_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, co
     std::vector<float> cf(n_coords);
     for (uint32_t i = 0; i < n_coords; i++) cf[i] = (float)coords[i];
     StrokeStyleHost st = {width, miter_limit, cap, join};
+    StrokeSink sink;
+    gg_stroke_to_fill(v, cf, st, &sink);
     c->scene.begin_path(ID6, false);
-    gg_stroke_to_fill(v, cf, st, &c->scene);
+    c->scene.append_stroke(sink);
     c->scene.end_path();
     c->scene.draw_color(gg_pack_color_straight(rgba));
     c->uploaded = false;

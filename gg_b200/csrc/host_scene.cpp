@@ -4,6 +4,13 @@
 #include <math.h>
 #include <string.h>
 
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <thread>
+
 #include "../../include/ggcuda.h"
 
 enum { PT_LINETO = 0x09, PT_QUADTO = 0x0A, PT_CUBICTO = 0x0B, PT_MOVETO = 0x0C, PT_PATH = 0x10, PT_TRANSFORM = 0x20, PT_STYLE = 0x40 };
@@ -120,6 +127,20 @@ void HostScene::add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* 
         case GGCUDA_VERB_CLOSE: close(); break;
         default: break;
         }
+    }
+}
+
+void HostScene::append_stroke(const StrokeSink& k) {
+    // the outline loops are complete subpaths in device space (the path was begun with the identity transform)
+    tags.insert(tags.end(), k.tags.begin(), k.tags.end());
+    path_data.insert(path_data.end(), k.data.begin(), k.data.end());
+    n_seg_tags += k.n_seg;
+    has_move = false;
+    if (!clip_stack.empty() && k.bb[0] <= k.bb[2]) {
+        if (k.bb[0] < path_bb[0]) path_bb[0] = k.bb[0];
+        if (k.bb[1] < path_bb[1]) path_bb[1] = k.bb[1];
+        if (k.bb[2] > path_bb[2]) path_bb[2] = k.bb[2];
+        if (k.bb[3] > path_bb[3]) path_bb[3] = k.bb[3];
     }
 }
 
@@ -284,6 +305,68 @@ static uint32_t brush_color(const double* brushes, size_t n_brushes, uint32_t ix
 
 int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, size_t n_pd, const uint32_t* dd, size_t n_dd,
                             const float* tr, size_t n_tr, const double* brushes, size_t n_brushes, std::string* msg) {
+    // Strokes are expanded on the host (the reference's stroke expander is host code too).
+    // Pass 1 collects every TagStroke as a job, the jobs run on all host cores, pass 2 is the ordinary
+    // sequential walk that appends each finished outline in scene order.
+    struct StrokeJob { std::vector<uint8_t> verbs; std::vector<float> dev; StrokeStyleHost st; StrokeSink out; };
+    std::vector<StrokeJob> jobs;
+    auto t_begin = std::chrono::steady_clock::now();
+    {
+        size_t pi = 0, di = 0, ti = 0;
+        float t[6]; memcpy(t, IDENTITY, sizeof t);
+        std::vector<uint8_t> pv; std::vector<float> pc; bool active = false;
+        for (size_t i = 0; i < n_tags; i++) {
+            switch (tg[i]) {
+            case ST_TRANSFORM: if (ti + 1 <= n_tr) memcpy(t, tr + 6 * ti, sizeof t); ti++; break;
+            case ST_SET_AA: di += 1; break;
+            case ST_BEGIN_PATH: pv.clear(); pc.clear(); active = true; break;
+            case ST_MOVE_TO: case ST_LINE_TO: if (active && pi + 2 <= n_pd) { pv.push_back(tg[i] == ST_MOVE_TO ? GGCUDA_VERB_MOVE : GGCUDA_VERB_LINE); pc.insert(pc.end(), pd + pi, pd + pi + 2); } pi += 2; break;
+            case ST_QUAD_TO: if (active && pi + 4 <= n_pd) { pv.push_back(GGCUDA_VERB_QUAD); pc.insert(pc.end(), pd + pi, pd + pi + 4); } pi += 4; break;
+            case ST_CUBIC_TO: if (active && pi + 6 <= n_pd) { pv.push_back(GGCUDA_VERB_CUBIC); pc.insert(pc.end(), pd + pi, pd + pi + 6); } pi += 6; break;
+            case ST_CLOSE_PATH: if (active) pv.push_back(GGCUDA_VERB_CLOSE); break;
+            case ST_FILL: di += 2; active = false; break;
+            case ST_STROKE:
+                if (di + 5 <= n_dd && active && !pv.empty()) {
+                    jobs.emplace_back();
+                    StrokeJob& j = jobs.back();
+                    float w, ml; memcpy(&w, dd + di + 1, 4); memcpy(&ml, dd + di + 2, 4);
+                    j.st = {(double)w, (double)ml, (int)dd[di + 3], (int)dd[di + 4]};
+                    j.verbs = pv;
+                    // CPU scene tiles transform the points, then stroke with the raw width
+                    // (scene/renderer.go:655-684, 707-713): do the same, in device space.
+                    j.dev.resize(pc.size());
+                    for (size_t k = 0; k + 1 < pc.size(); k += 2) {
+                        j.dev[k] = t[0] * pc[k] + t[1] * pc[k + 1] + t[2];
+                        j.dev[k + 1] = t[3] * pc[k] + t[4] * pc[k + 1] + t[5];
+                    }
+                }
+                di += 5; active = false; break;
+            case ST_FILL_ROUND_RECT: di += 2; pi += 6; break;
+            case ST_PUSH_LAYER: di += 2; break;
+            case ST_BEGIN_CLIP: active = false; break;
+            case ST_BRUSH: pi += 4; break;
+            default: break;
+            }
+        }
+        auto t_collect = std::chrono::steady_clock::now();
+        unsigned nt = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 32u);
+        nt = (unsigned)std::min<size_t>(nt, jobs.size() / 32 + 1);
+        auto work = [&](unsigned tix) { for (size_t j = tix; j < jobs.size(); j += nt) gg_stroke_to_fill(jobs[j].verbs, jobs[j].dev, jobs[j].st, &jobs[j].out); };
+        if (nt <= 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (unsigned k = 1; k < nt; k++) th.emplace_back(work, k);
+            work(0);
+            for (auto& x : th) x.join();
+        }
+        if (getenv("GGCUDA_TRACE")) {
+            auto t_done = std::chrono::steady_clock::now();
+            fprintf(stderr, "[ggcuda] ingest: collect %.2f ms, %zu stroke jobs on %u threads %.2f ms\n",
+                    std::chrono::duration<double, std::milli>(t_collect - t_begin).count(), jobs.size(), nt,
+                    std::chrono::duration<double, std::milli>(t_done - t_collect).count());
+        }
+    }
+    size_t next_job = 0;
     size_t pi = 0, di = 0, ti = 0;
     float cur_t[6]; memcpy(cur_t, IDENTITY, sizeof cur_t);
     std::vector<uint8_t> pv; std::vector<float> pc;   // current path: verbs + untransformed coords
@@ -332,19 +415,10 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         } break;
         case ST_STROKE: {
             if (di + 5 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
-            uint32_t bix = dd[di]; float w, ml; memcpy(&w, dd + di + 1, 4); memcpy(&ml, dd + di + 2, 4);
-            uint32_t cap = dd[di + 3], join = dd[di + 4]; di += 5;
-            if (path_active && !pv.empty()) {
-                // CPU scene tiles transform the points, then stroke with the raw width
-                // (scene/renderer.go:655-684, 707-713): do the same, in device space.
-                std::vector<float> dev(pc.size());
-                for (size_t k = 0; k + 1 < pc.size(); k += 2) {
-                    dev[k] = cur_t[0] * pc[k] + cur_t[1] * pc[k + 1] + cur_t[2];
-                    dev[k + 1] = cur_t[3] * pc[k] + cur_t[4] * pc[k + 1] + cur_t[5];
-                }
-                StrokeStyleHost st = {(double)w, (double)ml, (int)cap, (int)join};
+            uint32_t bix = dd[di]; di += 5;
+            if (path_active && !pv.empty() && next_job < jobs.size()) {
                 begin_path(IDENTITY, false);
-                gg_stroke_to_fill(pv, dev, st, this);
+                append_stroke(jobs[next_job++].out);
                 end_path();
                 draw_color(brush_color(brushes, n_brushes, bix));
             }
@@ -390,7 +464,7 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
 // (left side forward, cap, right side backward, cap) or two loops for closed subpaths; joins
 // are added on both sides (the inner ones overlap harmlessly under NonZero).
 namespace {
-struct P2 { double x, y; bool smooth = false; };   // smooth: interior vertex of a flattened curve (no join style)
+struct P2 { double x, y; bool smooth; P2() : x(0), y(0), smooth(false) {} P2(double x_, double y_, bool s_ = false) : x(x_), y(y_), smooth(s_) {} };   // smooth: interior vertex of a flattened curve (no join style)
 const double STROKE_TOL = 0.25;   // same tolerance as the fill flattener (flatten.go:19)
 
 // adaptive de Casteljau subdivision: stop when the control points are within tol of the chord
@@ -465,15 +539,33 @@ void add_cap(std::vector<P2>& o, P2 v, P2 d, double hw, int cap) {   // from lef
     }
     o.push_back(r);
 }
-void emit_loop(HostScene* s, const std::vector<P2>& pts) {
+void emit_loop(StrokeSink* s, const std::vector<P2>& pts) {
     if (pts.size() < 3) return;
-    s->move_to((float)pts[0].x, (float)pts[0].y);
-    for (size_t i = 1; i < pts.size(); i++) s->line_to((float)pts[i].x, (float)pts[i].y);
-    s->close();
+    size_t n = pts.size();
+    s->tags.push_back(PT_MOVETO);
+    s->tags.insert(s->tags.end(), n - 1, (uint8_t)PT_LINETO);
+    size_t base = s->data.size();
+    s->data.resize(base + 2 * n);
+    float* d = s->data.data() + base;
+    for (size_t i = 0; i < n; i++) {
+        float x = (float)pts[i].x, y = (float)pts[i].y;
+        d[2 * i] = x; d[2 * i + 1] = y;
+        if (x < s->bb[0]) s->bb[0] = x;
+        if (y < s->bb[1]) s->bb[1] = y;
+        if (x > s->bb[2]) s->bb[2] = x;
+        if (y > s->bb[3]) s->bb[3] = y;
+    }
+    s->n_seg += (uint32_t)(n - 1);
+    if (d[0] != d[2 * n - 2] || d[1] != d[2 * n - 1]) {   // close the loop (HostScene::close)
+        s->tags.push_back(PT_LINETO); s->data.push_back(d[0]); s->data.push_back(s->data[base + 1]); s->n_seg++;
+    }
 }
-void stroke_subpath(std::vector<P2>& pts, bool closed, const StrokeStyleHost& st, HostScene* out) {
+void stroke_subpath(std::vector<P2>& pts, bool closed, const StrokeStyleHost& st, StrokeSink* out) {
     // drop consecutive duplicates
-    std::vector<P2> p;
+    static thread_local std::vector<P2> tls_p, tls_dir, tls_o, tls_left, tls_right;
+    std::vector<P2>&p = tls_p, &dir = tls_dir, &o = tls_o, &left = tls_left, &right = tls_right;   // one TLS lookup each
+    if (p.capacity() < 4096) { p.reserve(4096); dir.reserve(4096); o.reserve(16384); left.reserve(8192); right.reserve(8192); }
+    p.clear();
     for (const P2& q : pts) if (p.empty() || fabs(q.x - p.back().x) > 1e-9 || fabs(q.y - p.back().y) > 1e-9) p.push_back(q);
     if (closed && p.size() > 1 && fabs(p.front().x - p.back().x) < 1e-9 && fabs(p.front().y - p.back().y) < 1e-9) p.pop_back();
     double hw = st.width * 0.5;
@@ -482,50 +574,50 @@ void stroke_subpath(std::vector<P2>& pts, bool closed, const StrokeStyleHost& st
     if (n == 0) return;
     if (n == 1) {   // degenerate: dot for round / square caps
         if (st.cap == GGCUDA_CAP_BUTT) return;
-        std::vector<P2> o;
+        o.clear();
         if (st.cap == GGCUDA_CAP_ROUND) arc_points(o, p[0], hw, 0, 2 * M_PI);
         else { o.push_back({p[0].x - hw, p[0].y - hw}); o.push_back({p[0].x + hw, p[0].y - hw}); o.push_back({p[0].x + hw, p[0].y + hw}); o.push_back({p[0].x - hw, p[0].y + hw}); }
         emit_loop(out, o);
         return;
     }
     size_t ns = closed ? n : n - 1;
-    std::vector<P2> dir(ns);
+    dir.resize(ns);
     for (size_t i = 0; i < ns; i++) {
         P2 a = p[i], b = p[(i + 1) % n];
         double dx = b.x - a.x, dy = b.y - a.y, l = sqrt(dx * dx + dy * dy);
         dir[i] = {dx / l, dy / l};
     }
     if (closed && n >= 3) {
-        std::vector<P2> left, right;
+        left.clear(); right.clear();
         for (size_t i = 0; i < n; i++) {
             P2 d0 = dir[(i + n - 1) % n], d1 = dir[i];
             add_join(left, p[i], d0, d1, hw, +1, st.join, st.miter_limit);
             add_join(right, p[i], d0, d1, hw, -1, st.join, st.miter_limit);
         }
         emit_loop(out, left);
-        std::vector<P2> rr(right.rbegin(), right.rend());
-        emit_loop(out, rr);
+        std::reverse(right.begin(), right.end());
+        emit_loop(out, right);
         return;
     }
-    std::vector<P2> o, right;
+    o.clear(); right.clear();
     // left side forward
     o.push_back({p[0].x - dir[0].y * hw, p[0].y + dir[0].x * hw});
     for (size_t i = 1; i + 1 < n; i++) add_join(o, p[i], dir[i - 1], dir[i], hw, +1, st.join, st.miter_limit);
     add_cap(o, p[n - 1], dir[ns - 1], hw, st.cap);
-    // right side backward
-    for (size_t i = n - 1; i-- > 1;) {
-        std::vector<P2> j;
-        add_join(j, p[i], dir[i - 1], dir[i], hw, -1, st.join, st.miter_limit);
-        o.insert(o.end(), j.rbegin(), j.rend());
-    }
+    // right side: built forward, appended backward
+    for (size_t i = 1; i + 1 < n; i++) add_join(right, p[i], dir[i - 1], dir[i], hw, -1, st.join, st.miter_limit);
+    o.insert(o.end(), right.rbegin(), right.rend());
     P2 back = {-dir[0].x, -dir[0].y};
     add_cap(o, p[0], back, hw, st.cap);
     emit_loop(out, o);
 }
 }  // namespace
 
-void gg_stroke_to_fill(const std::vector<uint8_t>& verbs, const std::vector<float>& c, const StrokeStyleHost& st, HostScene* out) {
-    std::vector<P2> pts;
+void gg_stroke_to_fill(const std::vector<uint8_t>& verbs, const std::vector<float>& c, const StrokeStyleHost& st, StrokeSink* out) {
+    static thread_local std::vector<P2> tls_pts;
+    std::vector<P2>& pts = tls_pts;
+    if (pts.capacity() < 4096) pts.reserve(4096);
+    pts.clear();
     bool closed = false, have = false;
     P2 cur = {0, 0}, start = {0, 0};
     size_t k = 0;

@@ -14,6 +14,14 @@
 #include <string>
 #include <vector>
 
+// Output of the host stroke expander: closed outline loops as MoveTo/LineTo tags + coordinates (device space).
+struct StrokeSink {
+    std::vector<uint8_t> tags;
+    std::vector<float> data;
+    uint32_t n_seg = 0;
+    float bb[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
+};
+
 struct HostScene {
     uint32_t width = 0, height = 0;
     std::vector<uint8_t> tags;
@@ -52,6 +60,7 @@ struct HostScene {
     void end_path();                      // auto-closes the open subpath, emits the Path marker
     void add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords);
 
+    void append_stroke(const StrokeSink& k);               // outline loops of an expanded stroke into the current path
     void draw_color(uint32_t rgba_premul);                 // DrawTagColor for the path just ended
     void begin_clip(uint32_t blend_word, float alpha, uint8_t kind);   // DrawTagBeginClip for the path just ended
     void begin_layer(uint32_t blend_word, float alpha);   // PushLayer: clip rectangle carrying blend + alpha
@@ -81,4 +90,4 @@ uint32_t gg_blend_word(uint32_t scene_blend_mode);
 // Stroke outline of a device-space path as a polygon set to be filled NonZero
 // (software.go:1145-1226 fills the expanded stroke with the paint's rule, NonZero).
 struct StrokeStyleHost { double width, miter_limit; int cap, join; };
-void gg_stroke_to_fill(const std::vector<uint8_t>& verbs, const std::vector<float>& coords, const StrokeStyleHost& st, HostScene* out);
+void gg_stroke_to_fill(const std::vector<uint8_t>& verbs, const std::vector<float>& coords, const StrokeStyleHost& st, StrokeSink* out);

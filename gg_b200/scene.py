@@ -86,10 +86,15 @@ class Encoding:
         self.tags.append(TagEndClip)
 
     def streams(self):
-        """(tags u8, pathData f32, drawData u32, transforms f32[n*6], brushes f64[n*4]) as numpy arrays."""
-        return (np.frombuffer(bytes(self.tags), dtype=np.uint8), np.asarray(self.path_data, dtype=np.float32),
-                np.asarray(self.draw_data, dtype=np.uint32), np.asarray(self.transforms, dtype=np.float32).reshape(-1),
-                np.asarray(self.brushes, dtype=np.float64).reshape(-1))
+        """(tags u8, pathData f32, drawData u32, transforms f32[n*6], brushes f64[n*4]) as numpy arrays -- the Go
+        Encoding holds exactly these slices; they are materialised once per encoding state, not per render."""
+        key = (len(self.tags), len(self.path_data), len(self.draw_data), len(self.transforms), len(self.brushes))
+        if getattr(self, "_cache_key", None) != key:
+            self._cache = (np.frombuffer(bytes(self.tags), dtype=np.uint8), np.asarray(self.path_data, dtype=np.float32),
+                           np.asarray(self.draw_data, dtype=np.uint32), np.asarray(self.transforms, dtype=np.float32).reshape(-1),
+                           np.asarray(self.brushes, dtype=np.float64).reshape(-1))
+            self._cache_key = key
+        return self._cache
 
 
 class ArrayEncoding:
