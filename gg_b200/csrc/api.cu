@@ -11,7 +11,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <string>
 
@@ -42,10 +45,13 @@ struct Ctx {
     GGBump* h_bump = nullptr;
     uint8_t* h_frame = nullptr; size_t h_frame_bytes = 0;
     // device
-    DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, lines, path_bbox, paths, path_row_off,
+    DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, curve_list, lines, path_bbox, paths, path_row_off,
         tiles, seg_start, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, spill_off, spill, bump,
         scan_partials, frame_d;
     uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0;
+    // Read-back target seen on consecutive flushes (gg keeps one pixmap per context): page-locked in place
+    // from its second use so the band is DMA'd straight into it, without the staging copy.
+    uint8_t* last_dst = nullptr; size_t last_dst_bytes = 0; bool dst_registered = false;
     ggcuda_stats stats{};
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -75,7 +81,7 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes) {
     return 0;
 }
 size_t total_device_bytes(Ctx* c) {
-    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off,
+    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list,
                      &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
                      &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
@@ -84,7 +90,7 @@ size_t total_device_bytes(Ctx* c) {
     return t;
 }
 void free_all(Ctx* c) {
-    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off,
+    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list,
                      &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
                      &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
@@ -128,6 +134,7 @@ int upload(Ctx* c) {
     if ((r = ensure(c, c->draw_recs, sizeof(GGDrawRec) * nd))) return r;
     if ((r = ensure(c, c->line_count, 4 * std::max<size_t>(L.n_tag_bytes, 1)))) return r;
     if ((r = ensure(c, c->line_off, 4 * std::max<size_t>(L.n_tag_bytes, 1)))) return r;
+    if ((r = ensure(c, c->curve_list, 4 * std::max<size_t>(L.n_tag_bytes, 1)))) return r;
     if ((r = ensure(c, c->path_bbox, 16 * np))) return r;
     if ((r = ensure(c, c->paths, sizeof(GGPath) * np))) return r;
     if ((r = ensure(c, c->path_row_off, 4 * np))) return r;
@@ -187,7 +194,7 @@ GGBuffers buffers(Ctx* c) {
     GGBuffers b;
     b.scene = (uint32_t*)c->scene_d.p; b.tag_monoids = (GGPathMonoid*)c->tag_monoids.p; b.draw_monoids = (GGDrawMonoid*)c->draw_monoids.p;
     b.info = (uint32_t*)c->info.p; b.clip_inps = (GGClipInp*)c->clip_inps.p; b.draw_recs = (GGDrawRec*)c->draw_recs.p;
-    b.line_count = (uint32_t*)c->line_count.p; b.line_off = (uint32_t*)c->line_off.p; b.lines = (GGLine*)c->lines.p;
+    b.line_count = (uint32_t*)c->line_count.p; b.line_off = (uint32_t*)c->line_off.p; b.curve_list = (uint32_t*)c->curve_list.p; b.lines = (GGLine*)c->lines.p;
     b.path_bbox_ord = (uint32_t*)c->path_bbox.p; b.paths = (GGPath*)c->paths.p; b.path_row_off = (uint32_t*)c->path_row_off.p;
     b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
     b.segments = (GGSegment*)c->segments.p; b.tile_hits = (unsigned long long*)c->tile_hits.p; b.hit_off = (uint32_t*)c->hit_off.p;
@@ -220,7 +227,7 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
         gg_launch_fine(c->cfg, b, dst_device, stride, c->stream);
         if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
         c->stats.passes++;
-        c->stats.kernel_launches += 16 + 7 + 5 + 1;
+        c->stats.kernel_launches += 18 + 7 + 5 + 1;
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
         GGBump bm = *c->h_bump;
@@ -297,6 +304,7 @@ void ggcuda_destroy(ggcuda_ctx* h) {
     if (c->host_only) { delete c; return; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->dst_registered) cudaHostUnregister(c->last_dst);
     free_all(c);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_bump) cudaFreeHost(c->h_bump);
@@ -449,13 +457,18 @@ int ggcuda_render_device(ggcuda_ctx* h, void* dst_device, size_t stride, uint32_
     return r;
 }
 
+static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
 int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
+    const bool trace = getenv("GGCUDA_TRACE") != nullptr;
+    double t0 = trace ? now_ms() : 0, t1 = 0, t2 = 0;
     if (!c || !dst) return c ? fail(c, GGCUDA_ERR_INVALID, "dst is NULL") : GGCUDA_ERR_INVALID;
     if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
     if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
     if (!c->uploaded) { int r = upload(c); if (r) return r; }
+    if (trace) t1 = now_ms();
     uint32_t row0 = c->band_y0 * GG_TILE_H, row1 = std::min(c->band_y1 * GG_TILE_H, c->height);
     if (row1 <= row0) return 0;
     size_t rows = row1 - row0, tight = (size_t)c->width * 4, bytes = rows * tight;
@@ -472,10 +485,27 @@ int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
     }
     r = render(c, (uint8_t*)c->frame_d.p, tight, flags);
     if (r) return r;
-    CK(cudaMemcpyAsync(c->h_frame, c->frame_d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (stride == tight) memcpy(dst + (size_t)row0 * stride, c->h_frame, bytes);
-    else for (size_t y = 0; y < rows; y++) memcpy(dst + (row0 + y) * stride, c->h_frame + y * tight, tight);
+    if (trace) t2 = now_ms();
+    uint8_t* band_dst = dst + (size_t)row0 * stride;
+    size_t band_bytes = (rows - 1) * stride + tight;
+    if (band_dst == c->last_dst && band_bytes == c->last_dst_bytes) {
+        if (!c->dst_registered && cudaHostRegister(band_dst, band_bytes, cudaHostRegisterDefault) == cudaSuccess) c->dst_registered = true;
+        else if (!c->dst_registered) cudaGetLastError();
+    } else {
+        if (c->dst_registered) { cudaHostUnregister(c->last_dst); c->dst_registered = false; }
+        c->last_dst = band_dst; c->last_dst_bytes = band_bytes;
+    }
+    if (c->dst_registered) {
+        CK(cudaMemcpy2DAsync(band_dst, stride, c->frame_d.p, tight, tight, rows, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+    } else {
+        CK(cudaMemcpyAsync(c->h_frame, c->frame_d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        if (stride == tight) memcpy(band_dst, c->h_frame, bytes);
+        else for (size_t y = 0; y < rows; y++) memcpy(band_dst + y * stride, c->h_frame + y * tight, tight);
+    }
+    if (trace) fprintf(stderr, "[ggcuda] flush: pack+upload %.2f ms, pipeline %.2f ms (%u passes), read-back %.2f ms (%s)\n", t1 - t0, t2 - t1,
+                       c->stats.passes, now_ms() - t2, c->dst_registered ? "direct" : "staged");
     if (!(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
     return 0;
 }

@@ -68,7 +68,8 @@ struct GGBump {
     uint32_t segments;     // 24: scan total of tile segment counts
     uint32_t spill;        // 28: blend-spill tile-levels (clip depth > 4)
     uint32_t failed;       // 32: bitmask of stages whose capacity was exceeded
-    uint32_t pad[7];
+    uint32_t curves;       // 36: curve tags compacted by flatten_classify
+    uint32_t pad[6];
 };
 #define GG_FAIL_LINES 1u
 #define GG_FAIL_TILES 2u

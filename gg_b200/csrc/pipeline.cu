@@ -144,24 +144,85 @@ __device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restric
     return true;
 }
 
-__global__ void __launch_bounds__(128) flatten_count_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
-                                                            const GGPathMonoid* __restrict__ tag_monoids, uint32_t* line_count) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_tag_bytes; i += gridDim.x * blockDim.x) {
-        CurveIn c;
-        uint32_t n = 0;
-        if (load_curve(cfg, scene, tag_monoids, i, &c)) {
-            if (c.kind == 1) n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
-            else n = flatten_cubic<false>(c.p0, c.p1, c.p2, c.p3, c.path_ix, nullptr, 0, nullptr);
+// Flatten runs as: classify (every tag byte: lines are counted on the spot, curve tags are compacted into a
+// dense list), curve_count (dense: one thread per curve runs the Euler subdivision), scan of the per-tag line
+// counts, line_emit (every tag byte, trivial) and curve_emit (dense). In the first version one thread per tag
+// byte ran everything and a warp of LineTo tags waited for its one cubic: 5 of 32 lanes active (ncu).
+__device__ __forceinline__ void fold_bbox(uint32_t* path_bbox_ord, uint32_t path_ix, const float* bb) {
+    uint32_t* pb = path_bbox_ord + 4 * (size_t)path_ix;
+    atomicMin(pb + 0, f_ord(bb[0]));
+    atomicMin(pb + 1, f_ord(bb[1]));
+    atomicMax(pb + 2, f_ord(bb[2]));
+    atomicMax(pb + 3, f_ord(bb[3]));
+}
+
+__global__ void __launch_bounds__(256) flatten_classify_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                               const GGPathMonoid* __restrict__ tag_monoids, uint32_t* line_count,
+                                                               uint32_t* curve_list, GGBump* bump) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t n_round = (cfg.n_tag_bytes + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
+        bool is_curve = false;
+        if (i < cfg.n_tag_bytes) {
+            uint32_t w = scene[cfg.path_tag_base + (i >> 2)];
+            uint32_t seg = (w >> ((i & 3u) * 8u)) & 3u;
+            uint32_t n = 0;
+            if (seg == 1) {
+                CurveIn c;
+                load_curve(cfg, scene, tag_monoids, i, &c);
+                n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
+            }
+            is_curve = seg >= 2;
+            if (!is_curve) line_count[i] = n;
         }
-        line_count[i] = n;
+        uint32_t m = __ballot_sync(0xffffffffu, is_curve);
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&bump->curves, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (is_curve) curve_list[base + __popc(m & ((1u << lane) - 1u))] = i;
+        }
     }
 }
 
-__global__ void __launch_bounds__(128) flatten_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
-                                                           const GGPathMonoid* __restrict__ tag_monoids,
-                                                           const uint32_t* __restrict__ line_count, const uint32_t* __restrict__ line_off,
-                                                           GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
+__global__ void __launch_bounds__(128) flatten_curve_count_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                                  const GGPathMonoid* __restrict__ tag_monoids,
+                                                                  const uint32_t* __restrict__ curve_list, uint32_t* line_count, const GGBump* bump) {
+    const uint32_t n = bump->curves;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        uint32_t i = curve_list[k];
+        CurveIn c;
+        load_curve(cfg, scene, tag_monoids, i, &c);
+        line_count[i] = flatten_cubic<false>(c.p0, c.p1, c.p2, c.p3, c.path_ix, nullptr, 0, nullptr);
+    }
+}
+
+__global__ void __launch_bounds__(256) flatten_line_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                                const GGPathMonoid* __restrict__ tag_monoids,
+                                                                const uint32_t* __restrict__ line_count, const uint32_t* __restrict__ line_off,
+                                                                GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cfg.n_tag_bytes; i += gridDim.x * blockDim.x) {
+        uint32_t w = scene[cfg.path_tag_base + (i >> 2)];
+        if (((w >> ((i & 3u) * 8u)) & 3u) != 1u || line_count[i] == 0) continue;
+        uint32_t off = line_off[i];
+        if (off + 1 > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
+        CurveIn c;
+        load_curve(cfg, scene, tag_monoids, i, &c);
+        GGLine l; l.path_ix = c.path_ix; l.p0x = c.p0.x; l.p0y = c.p0.y; l.p1x = c.p3.x; l.p1y = c.p3.y;
+        lines[off] = l;
+        float bb[4] = {fminf(c.p0.x, c.p3.x), fminf(c.p0.y, c.p3.y), fmaxf(c.p0.x, c.p3.x), fmaxf(c.p0.y, c.p3.y)};
+        fold_bbox(path_bbox_ord, c.path_ix, bb);
+    }
+}
+
+__global__ void __launch_bounds__(128) flatten_curve_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                                 const GGPathMonoid* __restrict__ tag_monoids,
+                                                                 const uint32_t* __restrict__ curve_list,
+                                                                 const uint32_t* __restrict__ line_count, const uint32_t* __restrict__ line_off,
+                                                                 GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
+    const uint32_t n_curves = bump->curves;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_curves; k += gridDim.x * blockDim.x) {
+        uint32_t i = curve_list[k];
         uint32_t n = line_count[i];
         if (n == 0) continue;
         uint32_t off = line_off[i];
@@ -169,19 +230,8 @@ __global__ void __launch_bounds__(128) flatten_emit_kernel(GGConfig cfg, const u
         CurveIn c;
         load_curve(cfg, scene, tag_monoids, i, &c);
         float bb[4] = {c.p0.x, c.p0.y, c.p0.x, c.p0.y};
-        if (c.kind == 1) {
-            GGLine l; l.path_ix = c.path_ix; l.p0x = c.p0.x; l.p0y = c.p0.y; l.p1x = c.p3.x; l.p1y = c.p3.y;
-            lines[off] = l;
-            bb[0] = fminf(bb[0], c.p3.x); bb[1] = fminf(bb[1], c.p3.y);
-            bb[2] = fmaxf(bb[2], c.p3.x); bb[3] = fmaxf(bb[3], c.p3.y);
-        } else {
-            flatten_cubic<true>(c.p0, c.p1, c.p2, c.p3, c.path_ix, lines + off, n, bb);
-        }
-        uint32_t* pb = path_bbox_ord + 4 * (size_t)c.path_ix;
-        atomicMin(pb + 0, f_ord(bb[0]));
-        atomicMin(pb + 1, f_ord(bb[1]));
-        atomicMax(pb + 2, f_ord(bb[2]));
-        atomicMax(pb + 3, f_ord(bb[3]));
+        flatten_cubic<true>(c.p0, c.p1, c.p2, c.p3, c.path_ix, lines + off, n, bb);
+        fold_bbox(path_bbox_ord, c.path_ix, bb);
     }
 }
 
@@ -741,9 +791,11 @@ void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
                           (GGDrawMonoid*)b.scan_partials, (GGDrawMonoid*)nullptr);
     draw_leaf_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.scene, b.draw_monoids, b.info, b.clip_inps, b.draw_recs);
     // a6: flatten (count, scan, emit)
-    flatten_count_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count);
+    flatten_classify_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.curve_list, b.bump);
+    flatten_curve_count_kernel<<<GG_GRID(4), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.bump);
     gg_scan<uint32_t>(s, n_tag_bytes, cfg.n_tag_bytes, LoadU32{b.line_count}, StoreU32Ex{b.line_off}, (uint32_t*)b.scan_partials, &b.bump->lines);
-    flatten_emit_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
+    flatten_line_emit_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
+    flatten_curve_emit_kernel<<<GG_GRID(4), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
     // a7: per-path tile bbox + tile / row offsets (one packed scan)
     gg_scan<unsigned long long>(s, n_paths, cfg.n_paths, LoadPathTiles{cfg, b.path_bbox_ord}, StorePath{cfg, b.path_bbox_ord, b.paths, b.path_row_off},
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->path_tiles));
