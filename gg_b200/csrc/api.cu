@@ -46,7 +46,7 @@ struct Ctx {
     uint8_t* h_frame = nullptr; size_t h_frame_bytes = 0;
     // device
     DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, curve_list, lines, path_bbox, paths, path_row_off,
-        tiles, seg_start, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, spill_off, spill, bump,
+        tiles, seg_start, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, restart_pt, spill_off, spill, bump,
         scan_partials, frame_d;
     uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0;
     // Read-back target seen on consecutive flushes (gg keeps one pixmap per context): page-locked in place
@@ -83,7 +83,7 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes) {
 size_t total_device_bytes(Ctx* c) {
     DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list,
                      &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
-                     &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->spill_off, &c->spill,
+                     &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->restart_pt, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
     size_t t = 0;
     for (DevBuf* b : all) t += b->bytes;
@@ -92,7 +92,7 @@ size_t total_device_bytes(Ctx* c) {
 void free_all(Ctx* c) {
     DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list,
                      &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
-                     &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->spill_off, &c->spill,
+                     &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->restart_pt, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
     for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->bytes = 0; }
 }
@@ -144,6 +144,7 @@ int upload(Ctx* c) {
     if ((r = ensure(c, c->hit_cursor, 4 * bt))) return r;
     if ((r = ensure(c, c->ptcl_off, 4 * bt))) return r;
     if ((r = ensure(c, c->ptcl_len, 4 * bt))) return r;
+    if ((r = ensure(c, c->restart_pt, 8 * bt))) return r;
     if ((r = ensure(c, c->spill_off, 4 * bt))) return r;
     if ((r = ensure(c, c->bump, sizeof(GGBump)))) return r;
     if ((r = ensure(c, c->scan_partials, 32 * GG_SCAN_BLOCKS))) return r;
@@ -199,7 +200,7 @@ GGBuffers buffers(Ctx* c) {
     b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
     b.segments = (GGSegment*)c->segments.p; b.tile_hits = (unsigned long long*)c->tile_hits.p; b.hit_off = (uint32_t*)c->hit_off.p;
     b.hit_cnt = (uint32_t*)c->hit_cnt.p; b.hit_cursor = (uint32_t*)c->hit_cursor.p; b.hits = (uint32_t*)c->hits.p;
-    b.ptcl_off = (uint32_t*)c->ptcl_off.p; b.ptcl_len = (uint32_t*)c->ptcl_len.p; b.ptcl = (uint32_t*)c->ptcl.p; b.spill_off = (uint32_t*)c->spill_off.p;
+    b.ptcl_off = (uint32_t*)c->ptcl_off.p; b.ptcl_len = (uint32_t*)c->ptcl_len.p; b.restart_pt = (uint32_t*)c->restart_pt.p; b.ptcl = (uint32_t*)c->ptcl.p; b.spill_off = (uint32_t*)c->spill_off.p;
     b.spill = (float4*)c->spill.p; b.bump = (GGBump*)c->bump.p; b.scan_partials = c->scan_partials.p;
     return b;
 }

@@ -56,6 +56,10 @@ struct GGDrawRec { uint32_t tag; int32_t parent; uint32_t a; uint32_t b; };
 // Bit 31 is ours: the layer may be dropped from a tile's PTCL when it would enclose no command there
 // (set by the host for PushLayer blend modes that leave the backdrop unchanged where the layer is empty).
 #define GG_BLEND_ELIDE_EMPTY 0x80000000u
+// Bit 30, also ours: an "implicit" layer -- no clip geometry, coverage 1 everywhere (a PushLayer without a clip
+// shape whose blend mode cannot change the backdrop where the layer is empty). It owns no tiles; its Begin/End
+// reach a tile's command list only through the draws it encloses. Always set together with bit 31.
+#define GG_BLEND_IMPLICIT 0x40000000u
 
 // Bump allocators / required sizes, written by the device, read back once per frame.
 struct GGBump {

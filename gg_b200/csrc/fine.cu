@@ -192,7 +192,7 @@ struct PtclStream {
             bulk_load(ring + (chunk & 1u) * PTCL_CHUNK, src + w0, words * 4u, bars + (chunk & 1u));
         }
     }
-    __device__ __forceinline__ void begin(const uint32_t* s, uint32_t n) {
+    __device__ __forceinline__ void begin(const uint32_t* s, uint32_t n, uint32_t first_chunk = 0) {
         // drain a chunk that was prefetched for the previous tile but never needed
         while (loaded_end < issued * PTCL_CHUNK) {
             uint32_t slot = (loaded_end / PTCL_CHUNK) & 1u;
@@ -200,10 +200,10 @@ struct PtclStream {
             parity ^= 1u << slot;
             loaded_end += PTCL_CHUNK;
         }
-        src = s; len = n; loaded_end = 0; issued = 0;
+        src = s; len = n; loaded_end = first_chunk * PTCL_CHUNK; issued = first_chunk;
         __syncwarp();
-        issue(0);
-        issue(1);
+        issue(first_chunk);
+        issue(first_chunk + 1);
     }
     // Make words [.., i] available: wait for the chunk(s) they live in and refill the slot behind us.
     // Called once per command (the longest command is 4 words), so the decode loop has a single copy of it.
@@ -213,7 +213,7 @@ struct PtclStream {
             mbar_wait(bars + slot, (parity >> slot) & 1u);
             parity ^= 1u << slot;
             loaded_end += PTCL_CHUNK;
-            if (chunk >= 1) { __syncwarp(); issue(chunk + 1); }
+            if (chunk + 1 >= issued) { __syncwarp(); issue(chunk + 1); }
         }
     }
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
@@ -320,7 +320,7 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
 }
 
 __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
-                                                               const uint32_t* __restrict__ ptcl,
+                                                               const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
                                                                float4* spill, const GGBump* __restrict__ bump, uint8_t* dst, size_t stride) {
     // a stage overflowed its buffer: PTCL / segments are incomplete, the host re-runs the pass with larger buffers
@@ -361,7 +361,14 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
         uint8_t* out = dst + (size_t)(py - cfg.band_y0 * GG_TILE_H) * stride + (size_t)px * 4;
         float4 rgba[PX];
         float area[PX];
-        if (cfg.flags & GG_FLAG_BG_FROM_DST) {
+        // coarse found the last command of this tile that overwrites every pixel whatever came before (an opaque
+        // solid colour or a backdrop-wiping layer at clip depth 0): start right after it, from that colour
+        const uint32_t restart = restart_pt[2 * T];
+        if (restart) {
+            const float4 c0 = unpack_rgba8(restart_pt[2 * T + 1]);
+#pragma unroll
+            for (int i = 0; i < PX; i++) rgba[i] = c0;
+        } else if (cfg.flags & GG_FLAG_BG_FROM_DST) {
 #pragma unroll
             for (int i = 0; i < PX; i++) {
                 uint32_t c = 0;
@@ -375,8 +382,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
 #pragma unroll
         for (int i = 0; i < PX; i++) area[i] = 0.0f;
         uint32_t clip_depth = 0;
-        ps.begin(ptcl + ptcl_off[T], ptcl_len[T]);
-        uint32_t cmd = 1;   // word 0 = blend offset (ptcl.go:98)
+        uint32_t cmd = restart ? restart : 1u;   // word 0 = blend offset (ptcl.go:98)
+        ps.begin(ptcl + ptcl_off[T], ptcl_len[T], cmd / PTCL_CHUNK);
         const uint32_t sp_off = spill_off[T];
         for (;;) {
             ps.ensure(cmd + 3);
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
 #pragma unroll
                 for (int i = 0; i < PX; i++) rgba[i] = make_float4(0, 0, 0, 0);
             } else if (tag == GG_CMD_END_CLIP) {     // fine.go:140-180
-                const uint32_t blend = ps.word(cmd + 1) & 0x7fffffffu;
+                const uint32_t blend = ps.word(cmd + 1) & 0x3fffffffu;   // bits 30-31 are coarse's layer flags
                 const float alpha = __uint_as_float(ps.word(cmd + 2));
                 cmd += 3;
                 if (clip_depth == 0) continue;
@@ -486,5 +493,5 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     if (blocks == 0) return;
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
-    fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.segments, b.spill_off, b.spill, b.bump, dst, stride);
+    fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride);
 }

@@ -48,7 +48,6 @@ void HostScene::clear(uint32_t w, uint32_t h) {
     width = w; height = h;
     tags.clear(); path_data.clear(); draw_tags.clear(); draw_data.clear(); styles.clear(); transforms.clear();
     clip_aux.clear(); clip_stack.clear(); clip_kind.clear();
-    bounds_stack.clear(); layer_rect_off.clear(); layer_blend.clear();
     n_paths = n_clips = n_seg_tags = 0;
     have_transform = false; in_path = false; has_move = false;
 }
@@ -66,14 +65,7 @@ void HostScene::begin_path(const float t[6], bool even_odd) {
     memcpy(path_t, t, sizeof path_t);
     path_bb[0] = path_bb[1] = 3.0e38f; path_bb[2] = path_bb[3] = -3.0e38f;
 }
-void HostScene::note_point(float x, float y) {
-    if (clip_stack.empty()) return;   // bounds only matter inside a clip / layer
-    float dx = path_t[0] * x + path_t[1] * y + path_t[2], dy = path_t[3] * x + path_t[4] * y + path_t[5];
-    if (dx < path_bb[0]) path_bb[0] = dx;
-    if (dy < path_bb[1]) path_bb[1] = dy;
-    if (dx > path_bb[2]) path_bb[2] = dx;
-    if (dy > path_bb[3]) path_bb[3] = dy;
-}
+void HostScene::note_point(float, float) {}   // (content bounds are no longer needed: layers are implicit)
 void HostScene::move_to(float x, float y) {
     // An open subpath is closed implicitly, as every CPU filler in gg does (the Vello
     // path of the reference leaves it open, path_convert.go:44-49).
@@ -136,12 +128,6 @@ void HostScene::append_stroke(const StrokeSink& k) {
     path_data.insert(path_data.end(), k.data.begin(), k.data.end());
     n_seg_tags += k.n_seg;
     has_move = false;
-    if (!clip_stack.empty() && k.bb[0] <= k.bb[2]) {
-        if (k.bb[0] < path_bb[0]) path_bb[0] = k.bb[0];
-        if (k.bb[1] < path_bb[1]) path_bb[1] = k.bb[1];
-        if (k.bb[2] > path_bb[2]) path_bb[2] = k.bb[2];
-        if (k.bb[3] > path_bb[3]) path_bb[3] = k.bb[3];
-    }
 }
 
 void HostScene::draw_color(uint32_t rgba_premul) {
@@ -149,13 +135,6 @@ void HostScene::draw_color(uint32_t rgba_premul) {
     draw_data.push_back(rgba_premul);
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(0);
-    if (!clip_stack.empty() && path_bb[0] <= path_bb[2]) {   // content bounds of the innermost open clip / layer
-        float* b = &bounds_stack[bounds_stack.size() - 4];
-        if (path_bb[0] < b[0]) b[0] = path_bb[0];
-        if (path_bb[1] < b[1]) b[1] = path_bb[1];
-        if (path_bb[2] > b[2]) b[2] = path_bb[2];
-        if (path_bb[3] > b[3]) b[3] = path_bb[3];
-    }
 }
 void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     int32_t d = (int32_t)draw_tags.size();
@@ -166,9 +145,6 @@ void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(-1);   // link patched by end_clip
     clip_stack.push_back(d); clip_kind.push_back(kind);
-    const float empty[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
-    bounds_stack.insert(bounds_stack.end(), empty, empty + 4);
-    layer_rect_off.push_back(SIZE_MAX); layer_blend.push_back(blend_word);
     n_clips++;
 }
 // Compose modes whose result differs from the backdrop where the layer is transparent:
@@ -178,47 +154,23 @@ static bool blend_erases_backdrop(uint32_t bw) {
     return mix == 0 && (compose == 0 || compose == 1 || compose == 5 || compose == 6 || compose == 7 || compose == 10);
 }
 void HostScene::begin_layer(uint32_t blend_word, float alpha) {
-    // a layer is a clip rectangle that carries the blend mode and alpha; it starts as the whole
-    // canvas and may be shrunk to the layer's content bounds by end_clip
+    // A layer is a BeginClip/EndClip pair carrying the blend mode and alpha. If the mode cannot change the backdrop
+    // where the layer is empty, the layer is "implicit": no clip geometry (an empty path), coverage 1 everywhere,
+    // present in a tile only where something is drawn inside it (GG_BLEND_IMPLICIT | GG_BLEND_ELIDE_EMPTY).
+    // The six wiping compose modes act on the whole canvas, so they get an explicit full-canvas rectangle.
     begin_path(IDENTITY, false);
-    size_t off = path_data.size();
-    move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
+    if (blend_erases_backdrop(blend_word)) {
+        move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
+    } else {
+        blend_word |= 0xC0000000u;
+    }
     end_path();
-    if (!blend_erases_backdrop(blend_word)) blend_word |= 0x80000000u;   // GG_BLEND_ELIDE_EMPTY
     begin_clip(blend_word, alpha, 1);
-    layer_rect_off.back() = off;
 }
 bool HostScene::end_clip(uint8_t kind) {
     if (clip_stack.empty() || clip_kind.back() != kind) return false;
     int32_t b = clip_stack.back();
     clip_stack.pop_back(); clip_kind.pop_back();
-    float cb[4]; memcpy(cb, &bounds_stack[bounds_stack.size() - 4], sizeof cb);
-    bounds_stack.resize(bounds_stack.size() - 4);
-    size_t rect_off = layer_rect_off.back(); uint32_t bw = layer_blend.back();
-    layer_rect_off.pop_back(); layer_blend.pop_back();
-    if (kind == 1 && rect_off != SIZE_MAX) {
-        // Layer rectangle: full canvas for compose modes that change the backdrop where the layer is
-        // transparent (Clear, Copy, SrcIn, DestIn, SrcOut, DestAtop); otherwise the tile-aligned bounds
-        // of the layer's content (an empty layer collapses to nothing and coarse culls it).
-        if (!blend_erases_backdrop(bw)) {
-            float x0 = 0, y0 = 0, x1 = 0, y1 = 0;
-            if (cb[0] <= cb[2]) {
-                x0 = floorf(fmaxf(cb[0], 0.0f) / 16.0f) * 16.0f; y0 = floorf(fmaxf(cb[1], 0.0f) / 16.0f) * 16.0f;
-                x1 = fminf(ceilf(fminf(cb[2], (float)width) / 16.0f) * 16.0f, (float)width);
-                y1 = fminf(ceilf(fminf(cb[3], (float)height) / 16.0f) * 16.0f, (float)height);
-                if (x1 <= x0 || y1 <= y0) x0 = y0 = x1 = y1 = 0;
-            }
-            float* r = &path_data[rect_off];   // move(x0,y0) line(x1,y0) line(x1,y1) line(x0,y1) line(x0,y0)
-            r[0] = x0; r[1] = y0; r[2] = x1; r[3] = y0; r[4] = x1; r[5] = y1; r[6] = x0; r[7] = y1; r[8] = x0; r[9] = y0;
-        }
-    }
-    if (!bounds_stack.empty() && cb[0] <= cb[2]) {   // a child's content is also the parent's content
-        float* pb = &bounds_stack[bounds_stack.size() - 4];
-        if (cb[0] < pb[0]) pb[0] = cb[0];
-        if (cb[1] < pb[1]) pb[1] = cb[1];
-        if (cb[2] > pb[2]) pb[2] = cb[2];
-        if (cb[3] > pb[3]) pb[3] = cb[3];
-    }
     int32_t d = (int32_t)draw_tags.size();
     // EndClip: dummy path marker so that path index == draw index (scene_encode.go:258-268);
     // we also give it a style word so that styles[path_ix] is valid for every path.

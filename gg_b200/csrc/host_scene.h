@@ -39,12 +39,6 @@ struct HostScene {
     float cur[2] = {0, 0}, start[2] = {0, 0};
     float path_t[6] = {1, 0, 0, 0, 1, 0};
     float path_bb[4] = {0, 0, 0, 0};     // device-space control-point bbox of the path being built
-    // Content bounds of every open clip / layer (device space, 4 floats each). A layer is encoded as
-    // a clip rectangle; when its blend mode leaves the backdrop untouched where the layer is empty,
-    // the rectangle is shrunk to the (tile-aligned) bounds of what was drawn inside it at end_clip.
-    std::vector<float> bounds_stack;
-    std::vector<size_t> layer_rect_off;  // index into path_data of the layer rectangle's 8 coordinates (or SIZE_MAX)
-    std::vector<uint32_t> layer_blend;
     void note_point(float x, float y);
 
     void clear(uint32_t w, uint32_t h);

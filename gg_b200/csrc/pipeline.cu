@@ -500,19 +500,25 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
                 if (PASS == 0 && v != t.backdrop) tiles[base + x].backdrop = v;
                 if (t.seg_count != 0 || v != 0) {
                     uint32_t T = gy * cfg.width_in_tiles + path.bbox[0] + x;
+                    // Implicit layers (GG_BLEND_IMPLICIT: no geometry, full coverage) have no tiles of their own: every
+                    // hit of something they enclose also drops their Begin/End pair into this tile's list (coarse
+                    // removes the duplicates after sorting).
+                    uint32_t n_imp = 0;
+                    for (int32_t a = recs[p].parent; a >= 0; a = recs[a].parent) n_imp += (recs[a].b & GG_BLEND_IMPLICIT) ? 1u : 0u;
                     if (PASS == 0) {
                         unsigned long long w;
                         if (tag == GG_DRAWTAG_COLOR) w = 1ull | ((t.seg_count ? 6ull : 3ull) << 32);
                         else if (tag == GG_DRAWTAG_BEGIN_CLIP) w = 2ull | ((1ull + (t.seg_count ? 7ull : 4ull)) << 32);
                         else w = 0;
-                        if (w) atomicAdd(&tile_hits[T], w);
-                    } else {
-                        if (tag == GG_DRAWTAG_COLOR) {
-                            uint32_t slot = hit_off[T] + atomicAdd(&hit_cursor[T], 1u);
-                            if (slot < cfg.hits_cap) hits[slot] = p;
-                        } else if (tag == GG_DRAWTAG_BEGIN_CLIP) {
-                            uint32_t slot = hit_off[T] + atomicAdd(&hit_cursor[T], 2u);
-                            if (slot + 1 < cfg.hits_cap) { hits[slot] = p; hits[slot + 1] = recs[p].a; }
+                        if (w) atomicAdd(&tile_hits[T], w + n_imp * (2ull | (5ull << 32)));
+                    } else if (tag == GG_DRAWTAG_COLOR || tag == GG_DRAWTAG_BEGIN_CLIP) {
+                        uint32_t own = tag == GG_DRAWTAG_COLOR ? 1u : 2u;
+                        uint32_t slot = hit_off[T] + atomicAdd(&hit_cursor[T], own + 2u * n_imp);
+                        if (slot + own + 2u * n_imp <= cfg.hits_cap) {
+                            hits[slot++] = p;
+                            if (own == 2u) hits[slot++] = recs[p].a;
+                            for (int32_t a = recs[p].parent; a >= 0; a = recs[a].parent)
+                                if (recs[a].b & GG_BLEND_IMPLICIT) { hits[slot++] = (uint32_t)a; hits[slot++] = recs[a].a; }
                         }
                     }
                 }
@@ -645,7 +651,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                                                                    const GGDrawMonoid* __restrict__ dm,
                                                                    const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ hit_cnt,
                                                                    uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len, uint32_t* ptcl,
-                                                                   uint32_t* spill_off, GGBump* bump) {
+                                                                   uint32_t* spill_off, uint32_t* restart_pt, GGBump* bump) {
     __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
@@ -659,7 +665,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         uint32_t pos = ptcl_off[T];
         if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
         pos += 1;
-        if (n == 0) { if (lane == 0) { ptcl[pos] = GG_CMD_END; ptcl_len[T] = 2; } continue; }
+        if (n == 0) { if (lane == 0) { ptcl[pos] = GG_CMD_END; ptcl_len[T] = 2; restart_pt[2 * T] = 0; restart_pt[2 * T + 1] = 0; } continue; }
         uint32_t* sorted;
         if (n <= COARSE_CAP) {
             uint32_t np2 = 32; while (np2 < n) np2 <<= 1;
@@ -690,19 +696,39 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         // `mat` how many of them (always the outermost ones) have been written to the PTCL.
         int32_t top = -1;
         uint32_t depth = 0, mat = 0, max_depth = 0;
+        // Restart point for fine: the PTCL position after the last command at clip depth 0 that fixes every pixel
+        // of the tile regardless of what came before -- an opaque CmdSolid+CmdColor, or a full-coverage layer whose
+        // compose mode wipes the backdrop (Clear always; Copy/SrcIn/DestIn/SrcOut/DestAtop when nothing was drawn
+        // inside). The PTCL itself is complete (it must match the reference word for word); fine merely starts there.
+        uint32_t pos_u = pos - ptcl_off[T], restart = 0, restart_rgba = 0, d0_begin_pos = 0xffffffffu;
         for (uint32_t base = 0; base < n; base += 32) {
             uint32_t i = base + lane;
             // parallel gather of everything the state machine and the emitters need
             GGDrawRec r; r.tag = 0; r.parent = -1; r.a = 0; r.b = 0;
             uint32_t d = 0; GGTile t; t.backdrop = 0; t.seg_count = 0; uint32_t sstart = 0; int32_t begin_parent = -1;
-            if (i < n) {
+            if (i < n && !(i > 0 && sorted[i] == sorted[i - 1])) {   // implicit-layer hits arrive once per enclosed hit: keep the first
                 d = sorted[i];
                 r = recs[d];
-                GGPath path = paths[dm[d].path_ix];
-                uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
-                t = tiles[ti];
-                sstart = seg_start[ti];
+                const bool implicit = (r.tag == GG_DRAWTAG_BEGIN_CLIP && (r.b & GG_BLEND_IMPLICIT)) ||
+                                      (r.tag == GG_DRAWTAG_END_CLIP && (r.a & GG_BLEND_IMPLICIT));
+                if (implicit) {
+                    t.backdrop = 1; t.seg_count = 0;   // full coverage, no geometry: CmdSolid at its EndClip
+                } else {
+                    GGPath path = paths[dm[d].path_ix];
+                    uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
+                    t = tiles[ti];
+                    sstart = seg_start[ti];
+                }
                 if (r.tag == GG_DRAWTAG_END_CLIP) begin_parent = recs[r.parent].parent;
+            }
+            // per-hit flags for the restart bookkeeping: bit 0 = tile has segments for this path,
+            // bits 1-2: 1 = opaque colour, 2 = End of a wiping layer (if empty), 3 = End of a Clear layer
+            uint32_t hflags = t.seg_count ? 1u : 0u;
+            if (r.tag == GG_DRAWTAG_COLOR) { if ((r.a >> 24) == 255u) hflags |= 1u << 1; }
+            else if (r.tag == GG_DRAWTAG_END_CLIP) {
+                uint32_t mixm = (r.a >> 8) & 0xffu, comp = r.a & 0xffu;
+                if (mixm == 0u && comp == 0u) hflags |= 3u << 1;
+                else if (mixm == 0u && (comp == 1u || comp == 5u || comp == 6u || comp == 7u || comp == 10u)) hflags |= 2u << 1;
             }
             // sequential, warp-uniform replay of the clip state over the (up to) 32 gathered hits
             bool emit = false;
@@ -714,21 +740,38 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                 uint32_t jd = __shfl_sync(0xffffffffu, d, j);
                 int32_t jbp = __shfl_sync(0xffffffffu, begin_parent, j);
                 uint32_t jb = __shfl_sync(0xffffffffu, r.b, j);
+                uint32_t jf = __shfl_sync(0xffffffffu, hflags, j);
+                uint32_t ja = __shfl_sync(0xffffffffu, r.a, j);
                 bool e = false;
                 uint32_t pj = 0;
                 if (jt == GG_DRAWTAG_COLOR) {
-                    if (jp == top) { e = true; pj = depth - mat; mat = depth; }
+                    if (jp == top) {
+                        e = true; pj = depth - mat; mat = depth;
+                        uint32_t words = pj + ((jf & 1u) ? 6u : 3u);
+                        if (depth == 0 && jf == (1u << 1)) { restart = pos_u + words; restart_rgba = ja; }   // opaque, no segments
+                        pos_u += words;
+                    }
                 } else if (jt == GG_DRAWTAG_BEGIN_CLIP) {
                     if (jp == top) {
                         top = (int32_t)jd;
                         if (jb & GG_BLEND_ELIDE_EMPTY) { depth++; }                       // pending
-                        else { e = true; pj = depth - mat; depth++; mat = depth; }        // written now (+ pending parents)
+                        else {                                                              // written now (+ pending parents)
+                            e = true; pj = depth - mat;
+                            pos_u += pj + 1u;
+                            if (depth == 0) d0_begin_pos = pos_u;
+                            depth++; mat = depth;
+                        }
                     }
                 } else if (jt == GG_DRAWTAG_END_CLIP) {
                     if (top == jp) {   // jp == index of the matching BeginClip
                         top = jbp;
                         if (depth > mat) { depth--; }                                     // never materialised: nothing to close
-                        else { e = true; depth--; mat--; }
+                        else {
+                            e = true; depth--; mat--;
+                            uint32_t words = (jf & 1u) ? 7u : 4u, kind = jf >> 1;
+                            if (depth == 0 && !(jf & 1u) && (kind == 3u || (kind == 2u && pos_u == d0_begin_pos))) { restart = pos_u + words; restart_rgba = 0; }
+                            pos_u += words;
+                        }
                     }
                 }
                 max_depth = max(max_depth, mat);
@@ -765,6 +808,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         if (lane == 0) {
             ptcl[pos] = GG_CMD_END;
             ptcl_len[T] = pos + 1 - ptcl_off[T];
+            restart_pt[2 * T] = restart; restart_pt[2 * T + 1] = restart_rgba;
             if (max_depth > GG_BLEND_STACK_SPLIT) {
                 uint32_t lv = max_depth - GG_BLEND_STACK_SPLIT;
                 uint32_t so = atomicAdd(&bump->spill, lv);
@@ -819,5 +863,5 @@ void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->hits));
     tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.bump);
     coarse_kernel<<<GG_GRID(4), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
-                                                           b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.bump);
+                                                           b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.restart_pt, b.bump);
 }

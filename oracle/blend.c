@@ -186,7 +186,7 @@ static float sep_f32(uint32_t mix, float s, float d) {
 
 /* bg, fg: premultiplied RGBA float32. out = bg (blend) fg. */
 void ot_blend_f32(uint32_t blend, const float bg[4], const float fg[4], float out[4]) {
-    blend &= 0x7fffffffu;
+    blend &= 0x3fffffffu;   /* bits 30-31: coarse's layer flags */
     uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
     float sa = fg[3], da = bg[3];
     if ((mix == 0 || mix == 0x80u) && compose == 3u) {   /* Normal or Clip with SrcOver: fine.go:168-179 */

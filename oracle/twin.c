@@ -822,6 +822,9 @@ typedef struct { uint32_t clip_depth, clip_zero_depth, blend_depth, max_blend_de
 /* ggcuda extension (not in the reference, which never maps layers to PTCL): a BeginClip whose blend word has
  * bit 31 set is removed again, together with its EndClip, when no command was written between them in a tile. */
 #define OT_BLEND_ELIDE_EMPTY 0x80000000u
+/* Bit 30: "implicit" layer -- no clip geometry, coverage 1 in every tile of the canvas (ggcuda's encoding of a
+ * PushLayer without clip shape); BeginClip everywhere (retracted where nothing is drawn), CmdSolid + CmdEndClip. */
+#define OT_BLEND_IMPLICIT 0x40000000u
 
 /* coarse.go:651-679 tileSegRange */
 static void tile_seg_range(ot_tile tile, int local_idx, int tile_count, const ot_tile *path_tiles, uint32_t total,
@@ -1047,6 +1050,17 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                         ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
                     }
                 }
+            } else if (tag == DRAWTAG_BEGIN_CLIP && (scene[L.draw_data_base + m.scene_offset] & OT_BLEND_IMPLICIT)) {
+                for (int g = 0; g < n_grid; g++) {   /* implicit layer: every tile is "inside with full coverage" */
+                    tile_clip_state *cs = &cs_all[g];
+                    if (cs->clip_zero_depth > 0) { cs->clip_depth++; continue; }
+                    if (cs->n_begin == cs->cap_begin) { cs->cap_begin = cs->cap_begin ? cs->cap_begin * 2 : 4; cs->begin_pos = (uint32_t *)realloc(cs->begin_pos, 4 * cs->cap_begin); }
+                    cs->begin_pos[cs->n_begin++] = ptcls[g].n;
+                    ptcl_push(&ptcls[g], CMD_BEGIN_CLIP);
+                    cs->blend_depth++;
+                    if (cs->blend_depth > cs->max_blend_depth) cs->max_blend_depth = cs->blend_depth;
+                    cs->clip_depth++;
+                }
             } else if (tag == DRAWTAG_BEGIN_CLIP) {   /* emitBeginClipToTiles :442-507 */
                 for (int ty = 0; ty < bh; ty++) for (int tx = 0; tx < bw; tx++) {
                     int gtx = (int)path.bbox[0] + tx, gty = (int)path.bbox[1] + ty;
@@ -1078,6 +1092,20 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                 uint32_t blend = 0; float alpha = 0;
                 uint32_t so = L.draw_data_base + m.scene_offset;
                 if (so + 1 < off) { blend = scene[so]; alpha = bits_f32(scene[so + 1]); }
+                if (blend & OT_BLEND_IMPLICIT) {
+                    for (int g = 0; g < n_grid; g++) {
+                        tile_clip_state *cs = &cs_all[g];
+                        cs->clip_depth--;
+                        if (cs->clip_zero_depth == cs->clip_depth + 1) { cs->clip_zero_depth = 0; continue; }
+                        if (cs->clip_zero_depth > 0) continue;
+                        uint32_t bpos = cs->n_begin ? cs->begin_pos[--cs->n_begin] : 0;
+                        if ((blend & OT_BLEND_ELIDE_EMPTY) && ptcls[g].n == bpos + 1) { ptcls[g].n = bpos; cs->blend_depth--; continue; }
+                        ptcl_push(&ptcls[g], CMD_SOLID);
+                        ptcl_push(&ptcls[g], CMD_END_CLIP); ptcl_push(&ptcls[g], blend); ptcl_push(&ptcls[g], f32_bits(alpha));
+                        cs->blend_depth--;
+                    }
+                    continue;
+                }
                 for (int ty = 0; ty < bh; ty++) for (int tx = 0; tx < bw; tx++) {
                     int gtx = (int)path.bbox[0] + tx, gty = (int)path.bbox[1] + ty;
                     if (gtx < 0 || gtx >= wt || gty < 0 || gty >= ht) continue;

@@ -94,13 +94,15 @@ def test_clip_and_layer_pairing():
     assert list(aux[:, 0]) == [-1, 0, 1, 1, 0, -1, 5]          # enclosing clip (EndClip: its own BeginClip)
     assert aux[0, 1] == 4 and aux[1, 1] == 3 and aux[5, 1] == 6  # Begin -> End links
     dd = words[lay["draw_data_base"]:lay["transform_base"]]
-    assert dd[0] == ((S.BlendMultiply << 8) | 3) | 0x80000000   # mix mode, SrcOver compose, elidable when empty
+    assert dd[0] == ((S.BlendMultiply << 8) | 3) | 0xC0000000   # mix mode, SrcOver compose; implicit + elidable layer
     assert dd[1] == np.float32(0.5).view(np.uint32)
     assert dd[2] == 0x8003                                       # plain clip
     assert dd[5] == 0                                            # Clear compose: must cover the canvas, not elidable
-    # the Multiply layer's rectangle was shrunk to the tile-aligned bounds of its content (10..50 x 10..40)
+    # the Multiply layer is implicit: its path is empty (the first path data belongs to the clip triangle);
+    # the Clear layer keeps an explicit full-canvas rectangle
     pd = words[lay["path_data_base"]:lay["draw_tag_base"]].view(np.float32)
-    assert list(pd[:10]) == [0, 0, 64, 0, 64, 48, 0, 48, 0, 0]
+    assert list(pd[:6]) == [0, 0, 100, 0, 50, 100]
+    assert list(pd[-10:]) == [0, 0, 256, 0, 256, 128, 0, 128, 0, 0]
 
 
 def test_encoding_ingest_matches_per_draw_calls():

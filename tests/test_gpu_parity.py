@@ -192,3 +192,32 @@ def test_deep_clip_stack_spills(ctx):
         sc.PushLayer(d % 3, 0.9, S.circle_verbs_coords(100, 100, 95 - 8 * d))
         sc.Fill(S.FillNonZero, S.IDENTITY, (0.9 - 0.1 * d, 0.1 * d, 0.5, 0.7), S.rect_verbs_coords(20 + 5 * d, 30, 180 - 5 * d, 170))
     _check_encoding(ctx, sc.Encoding(), w, h, bg=(255, 255, 255, 255))
+
+
+def test_fine_restart_points(ctx):
+    """Opaque full-tile fills and backdrop-wiping layers let fine skip the head of a tile's PTCL (coarse records the
+    restart point); pixels must be what the full replay (oracle) gives, PTCL unchanged."""
+    from gg_b200 import scene as S
+    rng = np.random.default_rng(77)
+    w, h = 320, 240
+
+    def blobs(sc, n):
+        for _ in range(n):
+            sc.Fill(S.FillNonZero, S.IDENTITY, (*rng.uniform(0, 1, 3), rng.uniform(0.3, 1.0)),
+                    S.circle_verbs_coords(rng.uniform(0, w), rng.uniform(0, h), rng.uniform(10, 80)))
+    sc = S.Scene()
+    blobs(sc, 30)
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0.2, 0.3, 0.4, 1.0), S.rect_verbs_coords(0, 0, w, 128))       # opaque: restart (solid tiles)
+    blobs(sc, 10)
+    sc.PushLayer(S.BlendCopy, 1.0); sc.PopLayer()                                                        # empty Copy layer wipes everything
+    blobs(sc, 10)
+    sc.PushLayer(S.BlendClear, 0.8); blobs(sc, 5); sc.PopLayer()                                         # Clear wipes whatever it holds
+    blobs(sc, 10)
+    sc.PushLayer(S.BlendSourceIn, 1.0); blobs(sc, 3); sc.PopLayer()                                      # not empty: no restart, real SrcIn
+    blobs(sc, 5)
+    sc.PushLayer(S.BlendNormal, 1.0, S.circle_verbs_coords(160, 120, 100))
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0.9, 0.1, 0.1, 1.0), S.rect_verbs_coords(0, 0, w, h))           # opaque but inside a clip: no restart
+    sc.PopLayer()
+    blobs(sc, 5)
+    for bg in ((0, 0, 0, 0), (255, 255, 255, 255)):
+        _check_encoding(ctx, sc.Encoding(), w, h, bg=bg)
