@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(_HERE, "libggcuda.so")
 OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
 COMPOSITE_OVER, KEEP_SCENE = 1, 2
 (BUF_SCENE, BUF_TAG_MONOIDS, BUF_DRAW_MONOIDS, BUF_INFO, BUF_CLIP_INPS, BUF_LINES, BUF_PATHS, BUF_TILES,
- BUF_SEG_START, BUF_SEGMENTS, BUF_PTCL_OFF, BUF_PTCL, BUF_HIT_CNT, BUF_LAYOUT) = range(14)
+ BUF_SEG_START, BUF_SEGMENTS, BUF_PTCL_OFF, BUF_PTCL, BUF_HIT_CNT, BUF_LAYOUT, BUF_RESTART) = range(15)
 
 # every symbol include/ggcuda.h declares (tests check the .so exports exactly these)
 SYMBOLS = [

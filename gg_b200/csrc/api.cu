@@ -17,6 +17,7 @@
 #include <chrono>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/ggcuda.h"
 #include "host_scene.h"
@@ -546,6 +547,7 @@ long long ggcuda_debug_read(ggcuda_ctx* h, int which, void* dst, size_t cap) {
     case GGCUDA_BUF_PTCL_OFF: src = c->ptcl_off.p; bytes = 4 * (size_t)bt; break;
     case GGCUDA_BUF_PTCL: src = c->ptcl.p; bytes = 4 * (size_t)bm.ptcl_words; break;
     case GGCUDA_BUF_HIT_CNT: src = c->hit_cnt.p; bytes = 4 * (size_t)bt; break;
+    case GGCUDA_BUF_RESTART: src = c->restart_pt.p; bytes = 8 * (size_t)bt; break;
     case GGCUDA_BUF_LAYOUT: {
         if (!dst || cap < sizeof(L)) return (long long)sizeof(L);
         memcpy(dst, &L, sizeof(L));
@@ -557,6 +559,13 @@ long long ggcuda_debug_read(ggcuda_ctx* h, int which, void* dst, size_t cap) {
     if (bytes == 0) return 0;
     if (cudaSetDevice(c->device) != cudaSuccess || cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) != cudaSuccess)
         return fail(c, GGCUDA_ERR_CUDA, std::string("debug read: ") + cudaGetErrorString(cudaGetLastError()));
+    if (which == GGCUDA_BUF_SEG_START) {   // the device array holds range ENDS after path_tiling; report starts (coarse.go:276-285)
+        std::vector<GGTile> t(bm.path_tiles);
+        if (cudaMemcpy(t.data(), c->tiles.p, sizeof(GGTile) * t.size(), cudaMemcpyDeviceToHost) != cudaSuccess)
+            return fail(c, GGCUDA_ERR_CUDA, "debug read: tiles");
+        uint32_t* s = (uint32_t*)dst;
+        for (size_t i = 0; i < t.size(); i++) s[i] -= t[i].seg_count;
+    }
     return (long long)bytes;
 }
 

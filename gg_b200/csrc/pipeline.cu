@@ -438,7 +438,12 @@ __global__ void __launch_bounds__(256) path_count_kernel(GGConfig cfg, const GGL
                 int32_t x_bump = max(x + 1, bx0);
                 atomicAdd(&tiles[base + x_bump].backdrop, delta);
             }
-            uint32_t seg_within_slice = atomicAdd(&tiles[base + x].seg_count, 1u);
+            // The count needs no return value here (a fire-and-forget RED, not a scoreboard-stalling ATOM): the slot a
+            // segment takes inside its tile is claimed later by path_tiling, one thread per segment, where the
+            // returning atomic's latency hides behind millions of independent threads (it stalled this kernel for
+            // 97 cycles per issue when the reference's seg_within_slice was taken here, path_count.go:192-194).
+            atomicAdd(&tiles[base + x].seg_count, 1u);
+            const uint32_t seg_within_slice = 0;
             if (store) {
                 GGSegCount sc; sc.line_ix = line_ix; sc.counts = (seg_within_slice << 16) | i;
                 seg_counts[seg_base + i - imin] = sc;
@@ -550,14 +555,13 @@ struct StoreTileHits {
 // ------------------------------------------------------------------ path_tiling.go:11-199
 __global__ void __launch_bounds__(256) path_tiling_kernel(GGConfig cfg, const GGSegCount* __restrict__ seg_counts, const GGLine* __restrict__ lines,
                                                           const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
-                                                          const uint32_t* __restrict__ seg_start, GGSegment* segments, GGBump* bump) {
+                                                          uint32_t* seg_start, GGSegment* segments, GGBump* bump) {
     uint32_t n = min(bump->seg_counts, cfg.seg_counts_cap);
     if (bump->failed) return;
     if (bump->segments > cfg.segments_cap) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, GG_FAIL_SEGMENTS); return; }
     for (uint32_t seg_ix = blockIdx.x * blockDim.x + threadIdx.x; seg_ix < n; seg_ix += gridDim.x * blockDim.x) {
         GGSegCount sc = seg_counts[seg_ix];
         GGLine line = lines[sc.line_ix];
-        uint32_t seg_within_slice = sc.counts >> 16;
         uint32_t seg_within_line = sc.counts & 0xffffu;
         DDA d; dda_setup(line, d); dda_finish(d);
         const float a = d.a, b = d.b, sign = d.sign, x0 = d.x0, y0 = d.y0;
@@ -570,7 +574,7 @@ __global__ void __launch_bounds__(256) path_tiling_kernel(GGConfig cfg, const GG
         int32_t stride = bx1 - bx0;
         int32_t tile_ix = (int32_t)path.tiles + (y - by0) * stride + x - bx0;
         if (tiles[tile_ix].seg_count == 0) continue;
-        uint32_t out_ix = seg_start[tile_ix] + seg_within_slice;
+        uint32_t out_ix = atomicAdd(&seg_start[tile_ix], 1u);   // claims the next slot: seg_start[] ends up as the END of each tile's range
         const float TW = (float)GG_TILE_W, TH = (float)GG_TILE_H;
         V2 tile_xy = mk((float)x * TW, (float)y * TH);
         V2 tile_xy1 = mk(tile_xy.x + TW, tile_xy.y + TH);
@@ -717,7 +721,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                     GGPath path = paths[dm[d].path_ix];
                     uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
                     t = tiles[ti];
-                    sstart = seg_start[ti];
+                    sstart = seg_start[ti] - t.seg_count;   // path_tiling advanced seg_start[] to the end of the tile's range
                 }
                 if (r.tag == GG_DRAWTAG_END_CLIP) begin_parent = recs[r.parent].parent;
             }

@@ -123,7 +123,7 @@ enum {
     GGCUDA_BUF_SCENE = 0, GGCUDA_BUF_TAG_MONOIDS = 1, GGCUDA_BUF_DRAW_MONOIDS = 2, GGCUDA_BUF_INFO = 3,
     GGCUDA_BUF_CLIP_INPS = 4, GGCUDA_BUF_LINES = 5, GGCUDA_BUF_PATHS = 6, GGCUDA_BUF_TILES = 7,
     GGCUDA_BUF_SEG_START = 8, GGCUDA_BUF_SEGMENTS = 9, GGCUDA_BUF_PTCL_OFF = 10, GGCUDA_BUF_PTCL = 11,
-    GGCUDA_BUF_HIT_CNT = 12, GGCUDA_BUF_LAYOUT = 13
+    GGCUDA_BUF_HIT_CNT = 12, GGCUDA_BUF_LAYOUT = 13, GGCUDA_BUF_RESTART = 14
 };
 GGCUDA_API long long ggcuda_debug_read(ggcuda_ctx* ctx, int which, void* dst, size_t cap_bytes);
 
