@@ -51,7 +51,7 @@ struct GGDrawRec { uint32_t tag; int32_t parent; uint32_t a; uint32_t b; };
 #define GG_CMD_COLOR 5u
 #define GG_CMD_BEGIN_CLIP 10u
 #define GG_CMD_END_CLIP 11u
-#define GG_BLEND_STACK_SPLIT 2   // clip levels kept on chip by fine (the reference's BlendStackSplit is 4, ptcl.go:31; not observable)
+#define GG_BLEND_STACK_SPLIT 1   // clip levels kept on chip by fine (the reference's BlendStackSplit is 4, ptcl.go:31; not observable)
 // Blend word of BeginClip / CmdEndClip: (mix << 8) | compose in Vello/peniko numbering (0x8003 = plain clip).
 // Bit 31 is ours: the layer may be dropped from a tile's PTCL when it would enclose no command there
 // (set by the host for PushLayer blend modes that leave the backdrop unchanged where the layer is empty).

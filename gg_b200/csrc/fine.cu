@@ -155,7 +155,7 @@ __constant__ float4 COMPOSE_COEF[14] = {
 // while the current one is decoded, and every command word is then a broadcast LDS instead of a dependent,
 // L1-missing global load (the top stall of the first version: 14 % of samples on the tag compare).
 #define PTCL_CHUNK 256   // words per ring slot (1 KiB)
-#define FINE_SMEM_PER_WARP 12368
+#define FINE_SMEM_PER_WARP 8272
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -282,7 +282,7 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
                 float y1 = clamp01(y + sdy);
                 float dy = y0 - y1;
                 if (dy != 0.0f) {
-                    float vec_y_recip = 1.0f / sdy;
+                    float vec_y_recip = __frcp_rn(sdy);
                     float t0 = (y0 - y) * vec_y_recip;
                     float t1 = (y1 - y) * vec_y_recip;
                     float x0 = sx + t0 * sdx;
@@ -298,7 +298,9 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
                         float b = fminf(xmax, 1.0f);
                         float c = fmaxf(b, 0.0f);
                         float d = fmaxf(xmin, 0.0f);
-                        float a = (b + 0.5f * (d * d - c * c) - xmin) / (xmax - xmin);
+                        // numerator evaluated exactly as the reference does (it cancels for near-vertical segments);
+                        // the quotient may be 2 ulp off: far below what survives the 8-bit quantisation
+                        float a = __fdividef(b + 0.5f * (d * d - c * c) - xmin, xmax - xmin);
                         atomicAdd(&acc[rowq * 16 + col], a * dy);
                     }
                     if (c1 < 16) atomicAdd(&suf[rowq * 17 + max(c1, 0)], dy);
@@ -319,7 +321,7 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
+__global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
                                                                float4* spill, const GGBump* __restrict__ bump, uint8_t* dst, size_t stride) {
@@ -332,18 +334,18 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
     const uint32_t row = lane >> 1;
     const uint32_t xb = (lane & 1u) * PX;
     // per-warp slice of dynamic shared memory (FINE_SMEM_PER_WARP bytes, opt-in above 48 KiB):
-    //   [0, 8192)      blend stack levels 0-1: float4 [2][PX][32]
-    //   [8192, 10240)  PTCL ring: u32 [2][PTCL_CHUNK]
-    //   [10240, 11264) area accumulators: float [256]
-    //   [11264, 12352) row suffix table: float [16][17]
-    //   [12352, 12368) two mbarriers
+    //   [0, 4096)      blend stack level 0: float4 [1][PX][32]
+    //   [4096, 6144)   PTCL ring: u32 [2][PTCL_CHUNK]
+    //   [6144, 7168)   area accumulators: float [256]
+    //   [7168, 8256)   row suffix table: float [16][17]
+    //   [8256, 8272)   two mbarriers
     extern __shared__ __align__(128) unsigned char fine_smem[];
     unsigned char* wsm = fine_smem + (size_t)(threadIdx.x >> 5) * FINE_SMEM_PER_WARP;
     float4 (*sstk)[PX][32] = reinterpret_cast<float4 (*)[PX][32]>(wsm);
-    float* acc = reinterpret_cast<float*>(wsm + 10240);
-    float* suf = reinterpret_cast<float*>(wsm + 11264);
+    float* acc = reinterpret_cast<float*>(wsm + 6144);
+    float* suf = reinterpret_cast<float*>(wsm + 7168);
     PtclStream ps;
-    ps.ring = reinterpret_cast<uint32_t*>(wsm + 8192); ps.bars = reinterpret_cast<uint64_t*>(wsm + 12352); ps.parity = 0; ps.issued = 0; ps.loaded_end = 0; ps.lane = threadIdx.x & 31;
+    ps.ring = reinterpret_cast<uint32_t*>(wsm + 4096); ps.bars = reinterpret_cast<uint64_t*>(wsm + 8256); ps.parity = 0; ps.issued = 0; ps.loaded_end = 0; ps.lane = threadIdx.x & 31;
     if ((threadIdx.x & 31) == 0) {
         mbar_init(ps.bars + 0, 1); mbar_init(ps.bars + 1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -436,10 +438,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                 const float4* slot; uint32_t step;
                 if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
                 else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
-                float4 svd[PX];
 #pragma unroll
                 for (int i = 0; i < PX; i++) {
-                    svd[i] = slot[i * step];
                     float scale = area[i] * alpha;   // fg = rgba * area * alpha, in place
                     rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
                 }
@@ -449,8 +449,9 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                     // pixels where both are visible take the (un-premultiply, mix, re-compose) path
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
-                        if (rgba[i].w <= 0.0f) rgba[i] = svd[i];
-                        else if (svd[i].w > 0.0f) rgba[i] = blend_mix_px(mix, svd[i], rgba[i]);
+                        const float4 sv = slot[i * step];
+                        if (rgba[i].w <= 0.0f) rgba[i] = sv;
+                        else if (sv.w > 0.0f) rgba[i] = blend_mix_px(mix, sv, rgba[i]);
                     }
                 } else {
                     // Porter-Duff: Fa * S + Fb * D. Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}.
@@ -458,10 +459,11 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                     const bool plus = compose == 12u;
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
-                        float fa = k.x + k.y * svd[i].w, fb = k.z + k.w * rgba[i].w;
+                        const float4 sv = slot[i * step];
+                        float fa = k.x + k.y * sv.w, fb = k.z + k.w * rgba[i].w;
                         float4 o;
-                        o.x = fmaf(fb, svd[i].x, fa * rgba[i].x); o.y = fmaf(fb, svd[i].y, fa * rgba[i].y);
-                        o.z = fmaf(fb, svd[i].z, fa * rgba[i].z); o.w = fmaf(fb, svd[i].w, fa * rgba[i].w);
+                        o.x = fmaf(fb, sv.x, fa * rgba[i].x); o.y = fmaf(fb, sv.y, fa * rgba[i].y);
+                        o.z = fmaf(fb, sv.z, fa * rgba[i].z); o.w = fmaf(fb, sv.w, fa * rgba[i].w);
                         if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
                         rgba[i] = o;
                     }

@@ -408,6 +408,9 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         }
     }
     close_open_clips();   // renderer.go:789-797
+    if (getenv("GGCUDA_TRACE"))
+        fprintf(stderr, "[ggcuda] ingest: total %.2f ms (%zu tags in, %zu packed tags out)\n",
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), n_tags, tags.size());
     return 0;
 }
 

@@ -161,18 +161,28 @@ __global__ void __launch_bounds__(256) flatten_classify_kernel(GGConfig cfg, con
                                                                uint32_t* curve_list, GGBump* bump) {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t n_round = (cfg.n_tag_bytes + 31u) & ~31u;
+    // Multi-GPU bands: a segment whose control points all lie above or below this device's band of tile rows
+    // cannot touch its tiles (backdrop only propagates along x inside a tile row), so it is dropped here and
+    // the flatten work scales with the band, not with the scene.
+    const bool banded = cfg.band_y0 > 0 || cfg.band_y1 < cfg.height_in_tiles;
+    const float band_lo = (float)(cfg.band_y0 * GG_TILE_H), band_hi = (float)(cfg.band_y1 * GG_TILE_H);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
         bool is_curve = false;
         if (i < cfg.n_tag_bytes) {
             uint32_t w = scene[cfg.path_tag_base + (i >> 2)];
             uint32_t seg = (w >> ((i & 3u) * 8u)) & 3u;
             uint32_t n = 0;
-            if (seg == 1) {
+            is_curve = seg >= 2;
+            if (seg == 1 || (is_curve && banded)) {
                 CurveIn c;
                 load_curve(cfg, scene, tag_monoids, i, &c);
-                n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
+                if (seg == 1) n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
+                if (banded) {
+                    float ymin = fminf(c.p0.y, c.p3.y), ymax = fmaxf(c.p0.y, c.p3.y);
+                    if (is_curve) { ymin = fminf(ymin, fminf(c.p1.y, c.p2.y)); ymax = fmaxf(ymax, fmaxf(c.p1.y, c.p2.y)); }
+                    if (ymax < band_lo || ymin > band_hi) { n = 0; if (is_curve) { is_curve = false; } }
+                }
             }
-            is_curve = seg >= 2;
             if (!is_curve) line_count[i] = n;
         }
         uint32_t m = __ballot_sync(0xffffffffu, is_curve);
