@@ -205,15 +205,19 @@ struct PtclStream {
         issue(first_chunk);
         issue(first_chunk + 1);
     }
-    // Make words [.., i] available: wait for the chunk(s) they live in and refill the slot behind us.
-    // Called once per command (the longest command is 4 words), so the decode loop has a single copy of it.
-    __device__ __forceinline__ void ensure(uint32_t i) {
-        while (i >= loaded_end && loaded_end < issued * PTCL_CHUNK) {
-            uint32_t chunk = loaded_end / PTCL_CHUNK, slot = chunk & 1u;
+    // Called once per command with the index of its first word (the longest command is 4 words). The ring holds
+    // the chunk the command starts in and the next one; the slot of the chunk BEHIND the command start is refilled
+    // with the chunk after next. A command may straddle a chunk boundary, so nothing is refilled on the strength
+    // of its later words (refilling when word cmd+3 entered a new chunk overwrote words cmd..cmd+2: long lists,
+    // > 1024 hits in a tile, came out wrong).
+    __device__ __forceinline__ void ensure(uint32_t cmd) {
+        const uint32_t cur = cmd / PTCL_CHUNK;
+        while (issued < cur + 2 && issued * PTCL_CHUNK < len) { __syncwarp(); issue(issued); }
+        while (cmd + 3 >= loaded_end && loaded_end < issued * PTCL_CHUNK) {
+            uint32_t slot = (loaded_end / PTCL_CHUNK) & 1u;
             mbar_wait(bars + slot, (parity >> slot) & 1u);
             parity ^= 1u << slot;
             loaded_end += PTCL_CHUNK;
-            if (chunk + 1 >= issued) { __syncwarp(); issue(chunk + 1); }
         }
     }
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
@@ -388,7 +392,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
         ps.begin(ptcl + ptcl_off[T], ptcl_len[T], cmd / PTCL_CHUNK);
         const uint32_t sp_off = spill_off[T];
         for (;;) {
-            ps.ensure(cmd + 3);
+            ps.ensure(cmd);
             const uint32_t tag = ps.word(cmd);
             if (tag == GG_CMD_FILL) {
                 const uint32_t packed = ps.word(cmd + 1), seg_ix = ps.word(cmd + 2);

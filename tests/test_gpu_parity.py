@@ -221,3 +221,14 @@ def test_fine_restart_points(ctx):
     blobs(sc, 5)
     for bg in ((0, 0, 0, 0), (255, 255, 255, 255)):
         _check_encoding(ctx, sc.Encoding(), w, h, bg=bg)
+
+
+def test_long_hit_lists(ctx):
+    """More than 1024 draws over one tile: coarse sorts such lists in place in global memory instead of shared memory."""
+    rng = np.random.default_rng(3)
+    elems = []
+    for i in range(1500):
+        x0, y0 = rng.uniform(0, 20, 2)
+        v, c = U.polygon_path(np.array([(x0, y0), (x0 + rng.uniform(5, 40), y0), (x0 + rng.uniform(5, 40), y0 + rng.uniform(5, 40))], dtype=np.float32))
+        elems.append(dict(type="draw", verbs=v, coords=c, color=tuple(int(q) for q in rng.integers(0, 256, 3)) + (40,)))
+    _check(ctx, elems, 64, 64, bg=(255, 255, 255, 255))
