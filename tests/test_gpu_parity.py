@@ -232,3 +232,15 @@ def test_long_hit_lists(ctx):
         v, c = U.polygon_path(np.array([(x0, y0), (x0 + rng.uniform(5, 40), y0), (x0 + rng.uniform(5, 40), y0 + rng.uniform(5, 40))], dtype=np.float32))
         elems.append(dict(type="draw", verbs=v, coords=c, color=tuple(int(q) for q in rng.integers(0, 256, 3)) + (40,)))
     _check(ctx, elems, 64, 64, bg=(255, 255, 255, 255))
+
+
+@pytest.mark.parametrize("name", ["polygon", "float-rect-aa", "star-aa"])
+def test_cuda_vs_gg_cpu_aaa_goldens(ctx, name):
+    """CUDA coverage against gg's CPU filler on the Skia-AAA golden paths (see test_cpu_oracle.test_exact_area_vs_gg_cpu_aaa
+    for why max |d| is large on snapped edges): same statistics as the CPU twin, i.e. the gap is the algorithm's, not CUDA's."""
+    import test_cpu_oracle as O
+    cov_g = O.skia_golden_coverage(name)
+    v, c = U.polygon_path(np.array(O.SKIA_AAA[name], dtype=np.float32))
+    out = U.gpu_scene(ctx, [dict(type="draw", verbs=v, coords=c, color=(255, 255, 255, 255))], 100, 100)
+    d = np.abs(out[..., 3].astype(np.float64) - cov_g)
+    assert d.mean() <= 0.7 and (d <= 2.5).mean() >= 0.97 and d.max() <= 61
