@@ -12,6 +12,7 @@ its band. `value` is device time (CUDA events, max over ranks); `e2e` is the sam
 public host API with host buffers (scene ingest + H2D + pipeline + D2H inside the timed region).
 """
 import argparse
+import faulthandler
 import json
 import os
 import subprocess
@@ -162,6 +163,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    # Watchdog: a wedged collective or driver call must not hold a GPU box until the caller's limit; dump every
+    # thread's stack and exit instead.
+    faulthandler.dump_traceback_later(int(os.environ.get("GG_BENCH_WATCHDOG_S", "900")), exit=True)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

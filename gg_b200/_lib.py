@@ -33,6 +33,9 @@ LAYOUT = np.dtype([(n, "<u4") for n in ("n_tag_bytes", "n_tag_words", "n_draws",
                                          "clip_aux_base", "n_scene_words")])
 
 
+CREATE_HOST_STROKES = 1   # ggcuda_create flag (diagnostic host polyline stroker)
+
+
 class Stats(C.Structure):
     _fields_ = [(n, C.c_uint32) for n in ("n_draws", "n_paths", "n_clips", "n_tag_bytes", "n_lines", "n_path_tiles",
                                           "n_seg_counts", "n_segments", "n_hits", "n_ptcl_words", "n_spill", "passes",
@@ -97,10 +100,10 @@ def _p(a):
 class Context:
     """Thin object wrapper over a ggcuda_ctx."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, flags=0):
         self.L = load()
         h = C.c_void_p()
-        rc = self.L.ggcuda_create(device, 0, C.byref(h))
+        rc = self.L.ggcuda_create(device, flags, C.byref(h))
         if rc != 0:
             raise GGCudaError(rc, (self.L.ggcuda_last_error(None) or b"").decode())
         self.h = h

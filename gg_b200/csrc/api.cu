@@ -267,7 +267,6 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
 extern "C" {
 
 int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
-    (void)flags;
     Ctx* c = nullptr;
     if (!out) return fail(nullptr, GGCUDA_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -275,6 +274,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
         c = new (std::nothrow) Ctx();
         if (!c) return fail(nullptr, GGCUDA_ERR_NOMEM, "out of host memory");
         c->host_only = true; c->device = -1;
+        c->scene.host_strokes = (flags & GGCUDA_CREATE_HOST_STROKES) != 0;
         *out = reinterpret_cast<ggcuda_ctx*>(c);
         return 0;
     }
@@ -288,6 +288,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
     c = new (std::nothrow) Ctx();
     if (!c) return fail(nullptr, GGCUDA_ERR_NOMEM, "out of host memory");
     c->device = device;
+    c->scene.host_strokes = (flags & GGCUDA_CREATE_HOST_STROKES) != 0;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void**)&c->h_bump, sizeof(GGBump), cudaHostAllocDefault) != cudaSuccess) {
         g_create_err = std::string("context set-up failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -389,15 +390,19 @@ int ggcuda_stroke_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, co
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !rgba) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
     if (n_verbs == 0) return 0;
-    std::vector<uint8_t> v(verbs, verbs + n_verbs);
     std::vector<float> cf(n_coords);
     for (uint32_t i = 0; i < n_coords; i++) cf[i] = (float)coords[i];
     StrokeStyleHost st = {width, miter_limit, cap, join};
-    StrokeSink sink;
-    gg_stroke_to_fill(v, cf, st, &sink);
-    c->scene.begin_path(ID6, false);
-    c->scene.append_stroke(sink);
-    c->scene.end_path();
+    if (c->scene.host_strokes) {
+        std::vector<uint8_t> v(verbs, verbs + n_verbs);
+        StrokeSink sink;
+        gg_stroke_to_fill(v, cf, st, &sink);
+        c->scene.begin_path(ID6, false);
+        c->scene.append_stroke(sink);
+        c->scene.end_path();
+    } else {
+        c->scene.stroke_path(ID6, verbs, n_verbs, cf.data(), cf.size(), st);
+    }
     c->scene.draw_color(gg_pack_color_straight(rgba));
     c->uploaded = false;
     return 0;

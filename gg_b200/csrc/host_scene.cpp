@@ -13,7 +13,9 @@
 
 #include "../../include/ggcuda.h"
 
-enum { PT_LINETO = 0x09, PT_QUADTO = 0x0A, PT_CUBICTO = 0x0B, PT_MOVETO = 0x0C, PT_PATH = 0x10, PT_TRANSFORM = 0x20, PT_STYLE = 0x40 };
+enum { PT_LINETO = 0x09, PT_QUADTO = 0x0A, PT_CUBICTO = 0x0B, PT_MOVETO = 0x0C, PT_PATH = 0x10, PT_TRANSFORM = 0x20, PT_STYLE = 0x40,
+       PT_MARKER = 0x80, PT_MARKER_MOVE = 0x8C };   // stroke markers, see stroke.cuh
+enum { STYLE_STROKE = 0x01, STYLE_EVEN_ODD = 0x02 };
 enum { DT_COLOR = 0x44, DT_BEGIN_CLIP = 0x9, DT_END_CLIP = 0x21 };
 
 // scene.Tag values, scene/tag.go:25-110
@@ -60,7 +62,8 @@ void HostScene::begin_path(const float t[6], bool even_odd) {
         have_transform = true;
     }
     tags.push_back(PT_STYLE);
-    styles.push_back(even_odd ? 0x02u : 0u);   // scene_encode.go:110-114
+    styles.push_back(even_odd ? 0x02u : 0u);   // scene_encode.go:110-114 (+ two stroke words, unused for fills)
+    styles.push_back(0); styles.push_back(0);
     in_path = true; has_move = false;
     memcpy(path_t, t, sizeof path_t);
     path_bb[0] = path_bb[1] = 3.0e38f; path_bb[2] = path_bb[3] = -3.0e38f;
@@ -122,6 +125,73 @@ void HostScene::add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* 
     }
 }
 
+// Centre line of a stroked path for the device-side expander. Per subpath: MoveTo, the segments (those whose points
+// all coincide are dropped, so every segment has a tangent), then a marker: a copy of the first segment flagged
+// PT_MARKER -- the last segment reads the tangent of its join from it when the subpath is closed; for an open
+// subpath a PT_MARKER_MOVE back to the first point precedes it and the marker segment draws the start cap.
+void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const StrokeStyleHost& st) {
+    begin_path(t, false);
+    float w = (float)st.width, ml = (float)st.miter_limit;
+    if (!(w > 0.0f)) { end_path(); return; }
+    uint32_t fl = STYLE_STROKE | ((uint32_t)(st.join & 3) << 2) | ((uint32_t)(st.cap & 3) << 4);
+    uint32_t wb, mb; memcpy(&wb, &w, 4); memcpy(&mb, &ml, 4);
+    styles[styles.size() - 3] = fl; styles[styles.size() - 2] = wb; styles[styles.size() - 1] = mb;
+    struct Seg { uint8_t tag; uint8_t n; float p[6]; };
+    static thread_local std::vector<Seg> segs;
+    segs.clear();
+    bool have = false, implicit = false;   // implicit: current point left behind by a Close, not set by a MoveTo
+    float sx = 0, sy = 0, cx = 0, cy = 0;
+    auto flush = [&](bool closed) {
+        if (!have) return;
+        have = false;
+        if (segs.empty() && implicit) return;
+        if (closed && !segs.empty() && (cx != sx || cy != sy)) { Seg s{PT_LINETO, 2, {sx, sy}}; segs.push_back(s); }
+        if (segs.empty()) {   // a dot: round and square caps draw it (software.go strokes a zero-length subpath the same way)
+            if (st.cap == GGCUDA_CAP_BUTT) return;
+            Seg s{PT_LINETO, 2, {sx + 1.0f / 1024.0f, sy}}; segs.push_back(s);
+            closed = false;
+        }
+        tags.push_back(PT_MOVETO); path_data.push_back(sx); path_data.push_back(sy);
+        for (const Seg& s : segs) { tags.push_back(s.tag); path_data.insert(path_data.end(), s.p, s.p + s.n); }
+        if (!closed) { tags.push_back(PT_MARKER_MOVE); path_data.push_back(sx); path_data.push_back(sy); }
+        tags.push_back((uint8_t)(segs[0].tag | PT_MARKER)); path_data.insert(path_data.end(), segs[0].p, segs[0].p + segs[0].n);
+        n_seg_tags += (uint32_t)segs.size() + 1;
+        segs.clear();
+    };
+    size_t k = 0;
+    for (size_t i = 0; i < n_verbs; i++) {
+        switch (verbs[i]) {
+        case GGCUDA_VERB_MOVE:
+            if (k + 2 > n_coords) { i = n_verbs; break; }
+            flush(false);
+            sx = cx = c[k]; sy = cy = c[k + 1]; k += 2; have = true; implicit = false; break;
+        case GGCUDA_VERB_LINE:
+            if (k + 2 > n_coords) { i = n_verbs; break; }
+            if (have && (c[k] != cx || c[k + 1] != cy)) { Seg s{PT_LINETO, 2, {c[k], c[k + 1]}}; segs.push_back(s); cx = c[k]; cy = c[k + 1]; }
+            k += 2; break;
+        case GGCUDA_VERB_QUAD:
+            if (k + 4 > n_coords) { i = n_verbs; break; }
+            if (have && (c[k] != cx || c[k + 1] != cy || c[k + 2] != cx || c[k + 3] != cy)) {
+                Seg s{PT_QUADTO, 4, {c[k], c[k + 1], c[k + 2], c[k + 3]}}; segs.push_back(s); cx = c[k + 2]; cy = c[k + 3];
+            }
+            k += 4; break;
+        case GGCUDA_VERB_CUBIC:
+            if (k + 6 > n_coords) { i = n_verbs; break; }
+            if (have && (c[k] != cx || c[k + 1] != cy || c[k + 2] != cx || c[k + 3] != cy || c[k + 4] != cx || c[k + 5] != cy)) {
+                Seg s{PT_CUBICTO, 6, {c[k], c[k + 1], c[k + 2], c[k + 3], c[k + 4], c[k + 5]}}; segs.push_back(s); cx = c[k + 4]; cy = c[k + 5];
+            }
+            k += 6; break;
+        case GGCUDA_VERB_CLOSE:
+            if (have) { float x0 = sx, y0 = sy; flush(true); sx = cx = x0; sy = cy = y0; have = true; implicit = true; }   // path.go: Close moves back to the start
+            break;
+        default: break;
+        }
+    }
+    flush(false);
+    has_move = false;
+    end_path();
+}
+
 void HostScene::append_stroke(const StrokeSink& k) {
     // the outline loops are complete subpaths in device space (the path was begun with the identity transform)
     tags.insert(tags.end(), k.tags.begin(), k.tags.end());
@@ -174,7 +244,7 @@ bool HostScene::end_clip(uint8_t kind) {
     int32_t d = (int32_t)draw_tags.size();
     // EndClip: dummy path marker so that path index == draw index (scene_encode.go:258-268);
     // we also give it a style word so that styles[path_ix] is valid for every path.
-    tags.push_back(PT_STYLE); styles.push_back(0);
+    tags.push_back(PT_STYLE); styles.push_back(0); styles.push_back(0); styles.push_back(0);
     tags.push_back(PT_PATH); n_paths++;
     draw_tags.push_back(DT_END_CLIP);
     clip_aux.push_back(b);    // "parent" of an EndClip = its BeginClip
@@ -263,7 +333,7 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
     struct StrokeJob { std::vector<uint8_t> verbs; std::vector<float> dev; StrokeStyleHost st; StrokeSink out; };
     std::vector<StrokeJob> jobs;
     auto t_begin = std::chrono::steady_clock::now();
-    {
+    if (host_strokes) {
         size_t pi = 0, di = 0, ti = 0;
         float t[6]; memcpy(t, IDENTITY, sizeof t);
         std::vector<uint8_t> pv; std::vector<float> pc; bool active = false;
@@ -367,13 +437,19 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         } break;
         case ST_STROKE: {
             if (di + 5 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
-            uint32_t bix = dd[di]; di += 5;
-            if (path_active && !pv.empty() && next_job < jobs.size()) {
-                begin_path(IDENTITY, false);
-                append_stroke(jobs[next_job++].out);
-                end_path();
+            uint32_t bix = dd[di];
+            if (path_active && !pv.empty()) {
+                if (host_strokes) {
+                    if (next_job < jobs.size()) { begin_path(IDENTITY, false); append_stroke(jobs[next_job++].out); end_path(); }
+                    else { begin_path(IDENTITY, false); end_path(); }
+                } else {
+                    float w, ml; memcpy(&w, dd + di + 1, 4); memcpy(&ml, dd + di + 2, 4);
+                    StrokeStyleHost st = {(double)w, (double)ml, (int)dd[di + 3], (int)dd[di + 4]};
+                    stroke_path(cur_t, pv.data(), pv.size(), pc.data(), pc.size(), st);
+                }
                 draw_color(brush_color(brushes, n_brushes, bix));
             }
+            di += 5;
             path_active = false;
         } break;
         case ST_FILL_ROUND_RECT: {

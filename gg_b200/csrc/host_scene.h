@@ -22,11 +22,13 @@ struct StrokeSink {
     float bb[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
 };
 
+struct StrokeStyleHost;
 struct HostScene {
     uint32_t width = 0, height = 0;
     std::vector<uint8_t> tags;
     std::vector<float> path_data;
-    std::vector<uint32_t> draw_tags, draw_data, styles;
+    std::vector<uint32_t> draw_tags, draw_data, styles;   // styles: 3 words per path {flags, width bits, miter-limit bits}
+    bool host_strokes = false;           // diagnostic: expand strokes with the host polyline stroker instead of on the device
     std::vector<float> transforms;
     std::vector<int32_t> clip_aux;       // 2 per draw: enclosing BeginClip (-1), link (End for Begin, Begin for End)
     std::vector<int32_t> clip_stack;     // open BeginClip draw indices
@@ -46,6 +48,10 @@ struct HostScene {
 
     // path construction (coordinates in the space of `transform`; the device applies it)
     void begin_path(const float transform[6], bool even_odd);
+    // Stroked path: the centre line travels to the device (which expands it, stroke.cuh); coordinates in the space of
+    // `transform`, width in device units (scene/renderer.go:655-713 strokes the transformed points with the raw width).
+    void stroke_path(const float transform[6], const uint8_t* verbs, size_t n_verbs, const float* coords, size_t n_coords,
+                     const struct StrokeStyleHost& st);
     void move_to(float x, float y);
     void line_to(float x, float y);
     void quad_to(float cx, float cy, float x, float y);

@@ -14,7 +14,7 @@
 //   path_tiling       path_tiling.go:11-199        -> segments
 //   coarse            coarse.go:322-625, ptcl.go   -> per-tile PTCL
 #include "pipeline.cuh"
-#include "flatten.cuh"
+#include "stroke.cuh"
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
@@ -78,7 +78,7 @@ __global__ void draw_leaf_kernel(GGConfig cfg, const uint32_t* __restrict__ scen
             r.a = rgba;
             // fill rule: style word of this path (coarse.go:683-705 indexes styles by path_ix;
             // our encoder emits one style per path marker so the lookup is exact)
-            r.b = (scene[cfg.style_base + m.path_ix] & 0x02u) ? 1u : 0u;
+            r.b = (scene[cfg.style_base + GG_STYLE_WORDS * m.path_ix] & 0x02u) ? 1u : 0u;
         } else if (tag == GG_DRAWTAG_BEGIN_CLIP) {
             if (m.clip_ix < cfg.n_clips) { clip_inps[m.clip_ix].ix = d; clip_inps[m.clip_ix].path_ix = (int32_t)m.path_ix; }
             r.a = link;
@@ -100,20 +100,41 @@ __global__ void draw_leaf_kernel(GGConfig cfg, const uint32_t* __restrict__ scen
 }
 
 // ------------------------------------------------------------------ flatten
-struct CurveIn { V2 p0, p1, p2, p3; uint32_t path_ix; uint32_t kind; };   // kind: 0 none, 1 line, 3 cubic
+struct CurveIn { V2 p0, p1, p2, p3; uint32_t path_ix; uint32_t kind; uint32_t tag; uint32_t style_ix; };   // kind: 0 none, 1 line, 3 cubic
 
 __device__ __forceinline__ V2 xform(const float* t, float x, float y) {   // scene/encoding.go:348-350
     return mk(t[0] * x + t[1] * y + t[2], t[3] * x + t[4] * y + t[5]);
 }
 
-__device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restrict__ scene,
-                                  const GGPathMonoid* __restrict__ tag_monoids, uint32_t i, CurveIn* c) {
+__device__ __forceinline__ uint32_t tag_byte(const GGConfig& cfg, const uint32_t* __restrict__ scene, uint32_t i) {
+    return (scene[cfg.path_tag_base + (i >> 2)] >> ((i & 3u) * 8u)) & 0xffu;
+}
+// Exclusive PathMonoid at tag byte i: the scanned per-word monoid + the bytes of the word before i.
+__device__ __forceinline__ GGPathMonoid tag_monoid_at(const GGConfig& cfg, const uint32_t* __restrict__ scene,
+                                                      const GGPathMonoid* __restrict__ tag_monoids, uint32_t i) {
     uint32_t w = scene[cfg.path_tag_base + (i >> 2)];
     uint32_t sh = (i & 3u) * 8u;
-    uint32_t tag = (w >> sh) & 0xffu;
+    return ScanTraits<GGPathMonoid>::combine(tag_monoids[i >> 2], path_monoid_new(w & ((1u << sh) - 1u)));
+}
+// Style of the path a tag byte belongs to (style_ix = number of style tags up to it). False for fills.
+__device__ __forceinline__ bool load_stroke_style(const GGConfig& cfg, const uint32_t* __restrict__ scene, uint32_t style_ix, StrokeStyle* st) {
+    if (style_ix == 0) return false;
+    const uint32_t* s = scene + cfg.style_base + GG_STYLE_WORDS * (style_ix - 1);
+    uint32_t f = s[0];
+    if (!(f & GG_STYLE_STROKE)) return false;
+    st->hw = 0.5f * __uint_as_float(s[1]);
+    st->miter_limit = __uint_as_float(s[2]);
+    st->join = (f >> 2) & 3u;
+    st->cap = (f >> 4) & 3u;
+    return true;
+}
+
+__device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restrict__ scene,
+                                  const GGPathMonoid* __restrict__ tag_monoids, uint32_t i, CurveIn* c) {
+    uint32_t tag = tag_byte(cfg, scene, i);
     uint32_t seg = tag & 3u;
     if (seg == 0) return false;
-    GGPathMonoid m = ScanTraits<GGPathMonoid>::combine(tag_monoids[i >> 2], path_monoid_new(w & ((1u << sh) - 1u)));
+    GGPathMonoid m = tag_monoid_at(cfg, scene, tag_monoids, i);
     const float* data = reinterpret_cast<const float*>(scene + cfg.path_data_base) + m.path_seg_offset;
     float t[6] = {1, 0, 0, 0, 1, 0};
     if (m.trans_ix > 0) {
@@ -121,7 +142,7 @@ __device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restric
 #pragma unroll
         for (int k = 0; k < 6; k++) t[k] = tp[k];
     }
-    c->path_ix = m.path_ix;
+    c->path_ix = m.path_ix; c->tag = tag; c->style_ix = m.style_ix;
     V2 a = xform(t, data[-2], data[-1]);
     if (seg == 1) {
         V2 b = xform(t, data[0], data[1]);
@@ -142,6 +163,31 @@ __device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restric
         c->kind = 3;
     }
     return true;
+}
+
+// The outline lines one stroked segment (tag byte i) is responsible for; see stroke.cuh.
+template <bool EMIT>
+__device__ inline uint32_t stroke_segment(const GGConfig& cfg, const uint32_t* __restrict__ scene, const GGPathMonoid* __restrict__ tag_monoids,
+                                          uint32_t i, const CurveIn& c, const StrokeStyle& st, GGLine* out, uint32_t cap, float* bb) {
+    LineOut o; o.out = out; o.n = 0; o.cap = cap; o.path_ix = c.path_ix;
+    o.bb[0] = o.bb[1] = 3.0e38f; o.bb[2] = o.bb[3] = -3.0e38f;
+    V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+    if (c.tag & GG_PTAG_MARKER) {
+        // copy of the subpath's first segment: it only exists so that the last segment can read its start tangent
+        // (closed subpath) or, after a marker MoveTo, to draw the start cap of an open subpath
+        if (i > 0 && tag_byte(cfg, scene, i - 1) == GG_PTAG_MARKER_MOVE) stroke_cap<EMIT>(o, c.p0, mk(-ns.x, -ns.y), st);
+    } else {
+        V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+        if (c.kind == 1) stroke_piece<EMIT>(o, stroke_vertex(c.p0, ns), stroke_vertex(c.p3, ne), st.hw);
+        else stroke_cubic<EMIT>(o, c.p0, c.p1, c.p2, c.p3, ns, ne, st.hw);
+        CurveIn nx;
+        if (i + 1 < cfg.n_tag_bytes && load_curve(cfg, scene, tag_monoids, i + 1, &nx))
+            stroke_join<EMIT>(o, c.p3, ne, stroke_normal(seg_start_tangent(nx.p0, nx.p1, nx.p2, nx.p3, nx.kind), st.hw), st);
+        else
+            stroke_cap<EMIT>(o, c.p3, ne, st);
+    }
+    if (EMIT) { bb[0] = o.bb[0]; bb[1] = o.bb[1]; bb[2] = o.bb[2]; bb[3] = o.bb[3]; }
+    return o.n;
 }
 
 // Flatten runs as: classify (every tag byte: lines are counted on the spot, curve tags are compacted into a
@@ -167,20 +213,27 @@ __global__ void __launch_bounds__(256) flatten_classify_kernel(GGConfig cfg, con
     const bool banded = cfg.band_y0 > 0 || cfg.band_y1 < cfg.height_in_tiles;
     const float band_lo = (float)(cfg.band_y0 * GG_TILE_H), band_hi = (float)(cfg.band_y1 * GG_TILE_H);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += gridDim.x * blockDim.x) {
-        bool is_curve = false;
+        bool is_curve = false;   // goes to the dense work list: curves, and every segment of a stroked path
         if (i < cfg.n_tag_bytes) {
-            uint32_t w = scene[cfg.path_tag_base + (i >> 2)];
-            uint32_t seg = (w >> ((i & 3u) * 8u)) & 3u;
+            uint32_t seg = tag_byte(cfg, scene, i) & 3u;
             uint32_t n = 0;
-            is_curve = seg >= 2;
-            if (seg == 1 || (is_curve && banded)) {
-                CurveIn c;
-                load_curve(cfg, scene, tag_monoids, i, &c);
-                if (seg == 1) n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
-                if (banded) {
-                    float ymin = fminf(c.p0.y, c.p3.y), ymax = fmaxf(c.p0.y, c.p3.y);
-                    if (is_curve) { ymin = fminf(ymin, fminf(c.p1.y, c.p2.y)); ymax = fmaxf(ymax, fmaxf(c.p1.y, c.p2.y)); }
-                    if (ymax < band_lo || ymin > band_hi) { n = 0; if (is_curve) { is_curve = false; } }
+            if (seg != 0) {
+                StrokeStyle st;
+                const bool stroke = load_stroke_style(cfg, scene, tag_monoid_at(cfg, scene, tag_monoids, i).style_ix, &st);
+                is_curve = seg >= 2 || stroke;
+                if (seg == 1 || banded) {
+                    CurveIn c;
+                    load_curve(cfg, scene, tag_monoids, i, &c);
+                    if (seg == 1 && !stroke) n = veq(c.p0, c.p3) ? 0u : 1u;   // path_convert.go:55
+                    if (banded) {
+                        float ymin = fminf(c.p0.y, c.p3.y), ymax = fmaxf(c.p0.y, c.p3.y);
+                        if (seg >= 2) { ymin = fminf(ymin, fminf(c.p1.y, c.p2.y)); ymax = fmaxf(ymax, fmaxf(c.p1.y, c.p2.y)); }
+                        if (stroke) {   // the outline reaches a half width (miter tips, square caps: a bit more) beyond the centre line
+                            float margin = st.hw * fmaxf(st.join == 0u ? st.miter_limit : 1.0f, 1.5f);
+                            ymin -= margin; ymax += margin;
+                        }
+                        if (ymax < band_lo || ymin > band_hi) { n = 0; is_curve = false; }
+                    }
                 }
             }
             if (!is_curve) line_count[i] = n;
@@ -203,7 +256,9 @@ __global__ void __launch_bounds__(128) flatten_curve_count_kernel(GGConfig cfg, 
         uint32_t i = curve_list[k];
         CurveIn c;
         load_curve(cfg, scene, tag_monoids, i, &c);
-        line_count[i] = flatten_cubic<false>(c.p0, c.p1, c.p2, c.p3, c.path_ix, nullptr, 0, nullptr);
+        StrokeStyle st;
+        if (load_stroke_style(cfg, scene, c.style_ix, &st)) line_count[i] = stroke_segment<false>(cfg, scene, tag_monoids, i, c, st, nullptr, 0, nullptr);
+        else line_count[i] = flatten_cubic<false>(c.p0, c.p1, c.p2, c.p3, c.path_ix, nullptr, 0, nullptr);
     }
 }
 
@@ -218,6 +273,8 @@ __global__ void __launch_bounds__(256) flatten_line_emit_kernel(GGConfig cfg, co
         if (off + 1 > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
         CurveIn c;
         load_curve(cfg, scene, tag_monoids, i, &c);
+        StrokeStyle st;
+        if (load_stroke_style(cfg, scene, c.style_ix, &st)) continue;   // stroked segments are emitted from the work list
         GGLine l; l.path_ix = c.path_ix; l.p0x = c.p0.x; l.p0y = c.p0.y; l.p1x = c.p3.x; l.p1y = c.p3.y;
         lines[off] = l;
         float bb[4] = {fminf(c.p0.x, c.p3.x), fminf(c.p0.y, c.p3.y), fmaxf(c.p0.x, c.p3.x), fmaxf(c.p0.y, c.p3.y)};
@@ -240,7 +297,9 @@ __global__ void __launch_bounds__(128) flatten_curve_emit_kernel(GGConfig cfg, c
         CurveIn c;
         load_curve(cfg, scene, tag_monoids, i, &c);
         float bb[4] = {c.p0.x, c.p0.y, c.p0.x, c.p0.y};
-        flatten_cubic<true>(c.p0, c.p1, c.p2, c.p3, c.path_ix, lines + off, n, bb);
+        StrokeStyle st;
+        if (load_stroke_style(cfg, scene, c.style_ix, &st)) stroke_segment<true>(cfg, scene, tag_monoids, i, c, st, lines + off, n, bb);
+        else flatten_cubic<true>(c.p0, c.p1, c.p2, c.p3, c.path_ix, lines + off, n, bb);
         fold_bbox(path_bbox_ord, c.path_ix, bb);
     }
 }

@@ -57,6 +57,12 @@ enum {
     GGCUDA_KEEP_SCENE = 2       /* do not clear the accumulated scene after rendering */
 };
 
+/* flags for ggcuda_create */
+enum {
+    GGCUDA_CREATE_HOST_STROKES = 1  /* diagnostic: expand strokes with the host polyline stroker (the path the
+                                       reference takes, internal/stroke/expander.go) instead of on the device */
+};
+
 /* ---- lifetime: GPUAccelerator.Init / Close (accelerator.go:108-112) ---- */
 GGCUDA_API int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out);
 GGCUDA_API void ggcuda_destroy(ggcuda_ctx* ctx);

@@ -21,46 +21,66 @@ enum { L_N_TAG_BYTES, L_N_TAG_WORDS, L_N_DRAWS, L_N_PATHS, L_N_CLIPS, L_PATH_TAG
 static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 static inline float bits_f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
+/* control points of the segment at tag i in cubic form, device space (transform, then quad elevation) */
+static int seg_cubic_form(uint8_t tag, const uint32_t *data, uint32_t off, const float *t, float *c) {
+    uint32_t seg = tag & 3u;
+    float p[8];
+    for (uint32_t k = 0; k <= seg; k++) {
+        float x = bits_f(data[off - 2 + 2 * k]), y = bits_f(data[off - 2 + 2 * k + 1]);
+        p[2 * k] = t[0] * x + t[1] * y + t[2];
+        p[2 * k + 1] = t[3] * x + t[4] * y + t[5];
+    }
+    if (seg == 1) {
+        c[0] = p[0]; c[1] = p[1]; c[6] = p[2]; c[7] = p[3];
+        c[2] = c[3] = c[4] = c[5] = 0.0f;
+        return 1;
+    }
+    if (seg == 2) {
+        const float k23 = (float)(2.0 / 3.0);
+        c[0] = p[0]; c[1] = p[1];
+        c[2] = p[0] + k23 * (p[2] - p[0]); c[3] = p[1] + k23 * (p[3] - p[1]);
+        c[4] = p[4] + k23 * (p[2] - p[4]); c[5] = p[5] + k23 * (p[3] - p[5]);
+        c[6] = p[4]; c[7] = p[5];
+    } else {
+        memcpy(c, p, sizeof(float) * 8);
+    }
+    return 3;
+}
+
 uint32_t ot_flatten_packed(const uint32_t *scene, const uint32_t *L, ot_line_soup *out, uint32_t cap) {
     const uint8_t *tags = (const uint8_t *)(scene + L[L_PATH_TAG_BASE]);
     const uint32_t *data = scene + L[L_PATH_DATA_BASE];
     const uint32_t *tr = scene + L[L_TRANSFORM_BASE];
-    uint32_t n = 0, path_ix = 0, off = 0, trans_ix = 0;
+    const uint32_t *styles = scene + L[L_STYLE_BASE];
+    uint32_t n = 0, path_ix = 0, off = 0, trans_ix = 0, style_ix = 0;
     float t[6] = {1, 0, 0, 0, 1, 0};
     for (uint32_t i = 0; i < L[L_N_TAG_BYTES]; i++) {
         uint8_t tag = tags[i];
         if (tag == 0x20) { for (int k = 0; k < 6; k++) t[k] = bits_f(tr[6 * trans_ix + k]); trans_ix++; continue; }
         if (tag == 0x10) { path_ix++; continue; }
-        if (tag == 0x40) continue;
-        if (tag == 0x0C) { off += 2; continue; }
+        if (tag == 0x40) { style_ix++; continue; }
+        if ((tag & 0x7f) == 0x0C) { off += 2; continue; }   /* MoveTo / marker MoveTo */
         uint32_t seg = tag & 3u;
         if (!seg) continue;
-        float p[8];
-        uint32_t npts = seg + 1;
-        for (uint32_t k = 0; k < npts; k++) {
-            float x = bits_f(data[off - 2 + 2 * k]), y = bits_f(data[off - 2 + 2 * k + 1]);
-            p[2 * k] = t[0] * x + t[1] * y + t[2];
-            p[2 * k + 1] = t[3] * x + t[4] * y + t[5];
-        }
+        float c[8];
+        int kind = seg_cubic_form(tag, data, off, t, c);
         off += 2 * seg;
         uint32_t before = n;
-        if (seg == 1) {
-            if (!(p[0] == p[2] && p[1] == p[3])) {
-                if (n < cap) { out[n].p0[0] = p[0]; out[n].p0[1] = p[1]; out[n].p1[0] = p[2]; out[n].p1[1] = p[3]; }
+        const uint32_t *sty = style_ix ? styles + 3 * (style_ix - 1) : NULL;
+        uint32_t room = n < cap ? cap - n : 0;
+        if (sty && (sty[0] & 1u)) {   /* stroked path: gg_b200/csrc/stroke.cuh */
+            int role = 0, next_kind = 0;
+            float nx[8];
+            if (tag & 0x80) role = (i > 0 && tags[i - 1] == 0x8C) ? 2 : 1;
+            else if (i + 1 < L[L_N_TAG_BYTES] && (tags[i + 1] & 3u)) next_kind = seg_cubic_form(tags[i + 1], data, off, t, nx);
+            n += ot_stroke_segment(c, kind, role, nx, next_kind, bits_f(sty[1]), bits_f(sty[2]), (int)((sty[0] >> 2) & 3u),
+                                   (int)((sty[0] >> 4) & 3u), room ? out + n : NULL, room);
+        } else if (kind == 1) {
+            if (!(c[0] == c[6] && c[1] == c[7])) {
+                if (n < cap) { out[n].p0[0] = c[0]; out[n].p0[1] = c[1]; out[n].p1[0] = c[6]; out[n].p1[1] = c[7]; }
                 n++;
             }
         } else {
-            float c[8];
-            if (seg == 2) {
-                const float k23 = (float)(2.0 / 3.0);
-                c[0] = p[0]; c[1] = p[1];
-                c[2] = p[0] + k23 * (p[2] - p[0]); c[3] = p[1] + k23 * (p[3] - p[1]);
-                c[4] = p[4] + k23 * (p[2] - p[4]); c[5] = p[5] + k23 * (p[3] - p[5]);
-                c[6] = p[4]; c[7] = p[5];
-            } else {
-                memcpy(c, p, sizeof c);
-            }
-            uint32_t room = n < cap ? cap - n : 0;
             n += ot_flatten_fill(c, 1, room ? out + n : NULL, room);
         }
         for (uint32_t k = before; k < n && k < cap; k++) out[k].path_ix = path_ix;
@@ -138,7 +158,7 @@ static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, i
     const uint32_t *dtags = scene + L[L_DRAW_TAG_BASE], *ddata = scene + L[L_DRAW_DATA_BASE], *styles = scene + L[L_STYLE_BASE];
     for (uint32_t d = 0; d < n_draws; d++) {
         el[d].line_start = start[d]; el[d].line_count = start[d + 1] - start[d];
-        if (dtags[d] == 0x44) { el[d].type = OT_ELEM_DRAW | OT_ELEM_PACKED; el[d].packed_rgba = ddata[dd]; el[d].even_odd = (styles[d] & 2u) ? 1 : 0; dd += 1; }
+        if (dtags[d] == 0x44) { el[d].type = OT_ELEM_DRAW | OT_ELEM_PACKED; el[d].packed_rgba = ddata[dd]; el[d].even_odd = (styles[3 * d] & 2u) ? 1 : 0; dd += 1; }
         else if (dtags[d] == 0x9) { el[d].type = OT_ELEM_BEGIN_CLIP; el[d].blend = ddata[dd]; el[d].alpha = bits_f(ddata[dd + 1]); dd += 2; }
         else { el[d].type = OT_ELEM_END_CLIP; el[d].line_count = 0; }
     }

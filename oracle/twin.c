@@ -310,6 +310,225 @@ static void flatten_euler_fill(vec2 p0, vec2 p1, vec2 p2, vec2 p3, line_sink *li
     }
 }
 
+/* ------------------------------------------------------------------ stroke expansion (ggcuda's own definition)
+ * PARITY UNPINNED against the reference: gg expands strokes on the host with internal/stroke/expander.go before its
+ * Vello path ever sees them (tilecompute/flatten.go:7-8: "stroke expansion ... is not yet ported"). ggcuda expands
+ * them inside flatten on the device (gg_b200/csrc/stroke.cuh); this is the CPU statement of that definition, written
+ * for a sequential walk, and what tests/ pin is (a) device lines == these lines bit for bit, (b) areas against closed
+ * forms, (c) pixels against the host polyline stroker. Join/cap/miter-limit semantics follow gg (paint.go,
+ * expander.go:442-476); the outline is filled NonZero as software.go:1145-1226 does.
+ *
+ * Construction: per flattened piece of the centre line a quad between its two offset vertices (offsets on the Euler
+ * spiral's own normals, euler.go:133-146); a quad with a backward edge becomes rectangle + outer bevels + inner
+ * detours through the centre; joins decorate the outer side and pass through the centre on the inner side. Every
+ * piece is positively oriented, so winding numbers never cancel. */
+typedef struct { float hw, miter_limit; int join, cap; } stroke_style;
+typedef struct { vec2 p, n, l, r; } stroke_vtx;
+
+static inline float vcross(vec2 a, vec2 b) { return a.x * b.y - a.y * b.x; }
+static void sk_put(line_sink *s, vec2 a, vec2 b) { if (!veq(a, b)) sink_push(s, a, b); }
+static vec2 sk_normal(vec2 t, float hw) {
+    float len = (float)sqrt((double)(t.x * t.x + t.y * t.y));
+    float k = len > 0.0f ? hw / len : 0.0f;
+    return v2(-t.y * k, t.x * k);
+}
+static stroke_vtx sk_vtx(vec2 p, vec2 n) { stroke_vtx v = {p, n, vadd(p, n), vsub(p, n)}; return v; }
+static vec2 sk_start_tangent(const vec2 *c, int kind) {
+    if (kind == 1) return vsub(c[3], c[0]);
+    if (!veq(c[1], c[0])) return vsub(c[1], c[0]);
+    if (!veq(c[2], c[0])) return vsub(c[2], c[0]);
+    return vsub(c[3], c[0]);
+}
+static vec2 sk_end_tangent(const vec2 *c, int kind) {
+    if (kind == 1) return vsub(c[3], c[0]);
+    if (!veq(c[3], c[2])) return vsub(c[3], c[2]);
+    if (!veq(c[3], c[1])) return vsub(c[3], c[1]);
+    return vsub(c[3], c[0]);
+}
+static vec2 sk_arc(line_sink *s, vec2 c, vec2 v0, float sweep, float hw, vec2 from) {
+    float cc = 1.0f - 0.25f / hw;
+    if (cc < -1.0f) cc = -1.0f;
+    float step = 2.0f * (float)acos((double)cc);
+    float nf = (float)ceil((double)(abs32(sweep) / step));
+    if (!(nf >= 1.0f)) nf = 1.0f;
+    if (nf > 1024.0f) nf = 1024.0f;
+    int n = (int)nf;
+    vec2 last = from;
+    for (int k = 1; k < n; k++) {
+        float a = sweep * (float)k / nf;
+        float cs = cos32(a), sn = sin32(a);
+        vec2 p = v2(c.x + (v0.x * cs - v0.y * sn), c.y + (v0.x * sn + v0.y * cs));
+        sk_put(s, last, p);
+        last = p;
+    }
+    return last;
+}
+static void sk_piece(line_sink *s, const stroke_vtx *a, const stroke_vtx *b, float hw) {
+    vec2 e = vsub(b->p, a->p);
+    float dl = vdot(vsub(b->l, a->l), e), dr = vdot(vsub(b->r, a->r), e);
+    if ((dl > 0.0f && dr > 0.0f) || (e.x == 0.0f && e.y == 0.0f)) { sk_put(s, a->l, b->l); sk_put(s, b->r, a->r); return; }
+    vec2 n = sk_normal(e, hw);
+    vec2 a0 = vadd(a->p, n), b0 = vsub(a->p, n), a1 = vadd(b->p, n), b1 = vsub(b->p, n);
+    if (vcross(a->n, n) > 0.0f) { sk_put(s, a->l, a->p); sk_put(s, a->p, a0); sk_put(s, b0, a->r); }
+    else { sk_put(s, a->l, a0); sk_put(s, b0, a->p); sk_put(s, a->p, a->r); }
+    sk_put(s, a0, a1);
+    sk_put(s, b1, b0);
+    if (vcross(n, b->n) > 0.0f) { sk_put(s, a1, b->p); sk_put(s, b->p, b->l); sk_put(s, b->r, b1); }
+    else { sk_put(s, a1, b->l); sk_put(s, b->r, b->p); sk_put(s, b->p, b1); }
+}
+static void sk_join(line_sink *s, vec2 p, vec2 n0, vec2 n1, const stroke_style *st) {
+    if (veq(n0, n1)) return;
+    float cr = vcross(n0, n1), dt = vdot(n0, n1);
+    vec2 u0, u1;
+    if (cr > 0.0f) {   /* turning towards the left side: left is inner, right is outer */
+        sk_put(s, vadd(p, n0), p); sk_put(s, p, vadd(p, n1));
+        u0 = v2(-n1.x, -n1.y); u1 = v2(-n0.x, -n0.y);
+    } else {
+        sk_put(s, vsub(p, n1), p); sk_put(s, p, vsub(p, n0));
+        u0 = n0; u1 = n1;
+    }
+    vec2 from = vadd(p, u0), to = vadd(p, u1);
+    float hw2 = st->hw * st->hw;
+    if (st->join == 1) {
+        float sweep = (float)atan2((double)vcross(u0, u1), (double)vdot(u0, u1));
+        vec2 last = sk_arc(s, p, u0, sweep, st->hw, from);
+        sk_put(s, last, to);
+    } else if (st->join == 0 && 2.0f * hw2 < st->miter_limit * st->miter_limit * (hw2 + dt) && hw2 + dt > 0.0f) {   /* expander.go:455-456 */
+        float k = hw2 / (hw2 + dt);
+        vec2 m = v2(p.x + (u0.x + u1.x) * k, p.y + (u0.y + u1.y) * k);
+        sk_put(s, from, m); sk_put(s, m, to);
+    } else {
+        sk_put(s, from, to);
+    }
+}
+static void sk_cap(line_sink *s, vec2 p, vec2 nf, const stroke_style *st) {
+    vec2 a = vadd(p, nf), b = vsub(p, nf);
+    if (st->cap == 1) {
+        vec2 last = sk_arc(s, p, nf, -3.14159265358979323846f, st->hw, a);
+        sk_put(s, last, b);
+    } else if (st->cap == 2) {
+        vec2 d = v2(nf.y, -nf.x);
+        vec2 a2 = vadd(a, d), b2 = vadd(b, d);
+        sk_put(s, a, a2); sk_put(s, a2, b2); sk_put(s, b2, b);
+    } else {
+        sk_put(s, a, b);
+    }
+}
+/* the subdivision loop of flatten_euler_fill with one offset vertex per subdivision point and the line count of each
+ * Euler segment raised by sqrt(1 + hw * max curvature) */
+static void sk_cubic(line_sink *lines, vec2 p0, vec2 p1, vec2 p2, vec2 p3, vec2 n_start, vec2 n_end, float hw) {
+    uint32_t t0u = 0;
+    float dt = 1.0f;
+    vec2 last_p = p0;
+    vec2 last_q = vsub(p1, p0);
+    if (vlen_sq(last_q) < DERIV_THRESH * DERIV_THRESH) { vec2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &last_q); }
+    float last_t = 0.0f;
+    stroke_vtx va = sk_vtx(p0, n_start);
+    for (;;) {
+        float t0 = (float)t0u * dt;
+        if (t0 == 1.0f) break;
+        float t1 = t0 + dt;
+        vec2 this_p0 = last_p, this_q0 = last_q, this_p1, this_q1;
+        eval_cubic_and_deriv(p0, p1, p2, p3, t1, &this_p1, &this_q1);
+        if (vlen_sq(this_q1) < DERIV_THRESH * DERIV_THRESH) {
+            vec2 new_p1, new_q1;
+            eval_cubic_and_deriv(p0, p1, p2, p3, t1 - DERIV_EPS, &new_p1, &new_q1);
+            this_q1 = new_q1;
+            if (t1 < 1.0f) { this_p1 = new_p1; t1 -= DERIV_EPS; }
+        }
+        float actual_dt = t1 - last_t;
+        cubic_params cp = cubic_params_from_points_derivs(this_p0, this_p1, this_q0, this_q1, actual_dt);
+        if (cp.err <= FLATTEN_TOL || dt <= SUBDIV_LIMIT) {
+            euler_params ep = euler_params_from_angles(cp.th0, cp.th1);
+            float kb = ep.k0 - 0.5f * ep.k1;
+            float k1 = ep.k1;
+            float scale_mul = 0.5f * (float)(M_SQRT2 / 2.0) * (float)sqrt((double)(cp.chord_len / (ep.ch * FLATTEN_TOL)));
+            float k_abs = max32(abs32(kb), abs32(kb + k1));
+            float widen = (float)sqrt((double)(1.0f + hw * k_abs * ep.ch / cp.chord_len));
+            float n_frac, a = 0, b = 0, integral = 0, int0 = 0;
+            int low_k1;
+            if (abs32(k1) < 1e-3f) {
+                float k = kb + 0.5f * k1;
+                n_frac = (float)sqrt((double)abs32(k));
+                low_k1 = 1;
+            } else {
+                a = k1; b = kb;
+                int0 = cube_signed_sqrt(b);
+                float int1 = cube_signed_sqrt(a + b);
+                integral = int1 - int0;
+                n_frac = (float)(2.0 / 3.0) * integral / a;
+                low_k1 = 0;
+            }
+            float n = (float)ceil((double)(n_frac * scale_mul * widen));
+            if (n < 1) n = 1;
+            if (n > 100) n = 100;
+            int n_int = (n != n) ? 0 : (int)n;
+            vec2 chord = vsub(this_p1, this_p0);
+            float nscale = hw / cp.chord_len;
+            int tiny = vlen_sq(chord) < 1e-12f;
+            for (int i = 0; i < n_int; i++) {
+                stroke_vtx vb;
+                if (i == n_int - 1 && t1 == 1.0f) {
+                    vb = sk_vtx(p3, n_end);
+                } else {
+                    float t = (float)(i + 1) / n;
+                    float sp;
+                    if (low_k1) sp = t;
+                    else {
+                        float c = (float)cbrt((double)(integral * t + int0));
+                        float inv = c * abs32(c);
+                        sp = (inv - b) / a;
+                    }
+                    vec2 pc = es_eval_with_offset(this_p0, this_p1, &ep, sp, 0.0f);
+                    vec2 nn = va.n;
+                    if (!tiny) {
+                        float th = ep_eval_th(&ep, sp);
+                        float sx = sin32(th), sy = cos32(th);
+                        nn = v2((chord.x * sx - chord.y * sy) * nscale, (chord.x * sy + chord.y * sx) * nscale);
+                    }
+                    vb = sk_vtx(pc, nn);
+                }
+                sk_piece(lines, &va, &vb, hw);
+                va = vb;
+            }
+            last_p = this_p1; last_q = this_q1; last_t = t1;
+            t0u++;
+            unsigned shift = trailing_zeros32(t0u);
+            t0u >>= shift;
+            dt *= (float)((uint32_t)1 << shift);
+        } else {
+            if (t0u < 0xFFFFFFFFu / 2) t0u *= 2;
+            dt *= 0.5f;
+        }
+    }
+    if (!veq(va.p, p3) || !veq(va.n, n_end)) { stroke_vtx vb = sk_vtx(p3, n_end); sk_piece(lines, &va, &vb, hw); }
+}
+
+/* One segment's share of the outline. seg / next: 4 points in cubic form (kind 1: line from [0] to [3]); role 0 = a
+ * real segment (next_kind 0: the subpath ends here with a cap), 1 = marker copy after a closed subpath (draws nothing),
+ * 2 = marker copy after the marker MoveTo of an open subpath (draws the start cap). */
+uint32_t ot_stroke_segment(const float *seg, int kind, int role, const float *next, int next_kind,
+                           float width, float miter_limit, int join, int cap, ot_line_soup *out, uint32_t out_cap) {
+    line_sink s = {out, 0, out_cap};
+    stroke_style st = {0.5f * width, miter_limit, join, cap};
+    vec2 c[4] = {v2(seg[0], seg[1]), v2(seg[2], seg[3]), v2(seg[4], seg[5]), v2(seg[6], seg[7])};
+    vec2 ns = sk_normal(sk_start_tangent(c, kind), st.hw);
+    if (role != 0) {
+        if (role == 2) sk_cap(&s, c[0], v2(-ns.x, -ns.y), &st);
+        return s.n;
+    }
+    vec2 ne = sk_normal(sk_end_tangent(c, kind), st.hw);
+    if (kind == 1) { stroke_vtx a = sk_vtx(c[0], ns), b = sk_vtx(c[3], ne); sk_piece(&s, &a, &b, st.hw); }
+    else sk_cubic(&s, c[0], c[1], c[2], c[3], ns, ne, st.hw);
+    if (next_kind != 0) {
+        vec2 d[4] = {v2(next[0], next[1]), v2(next[2], next[3]), v2(next[4], next[5]), v2(next[6], next[7])};
+        sk_join(&s, c[3], ne, sk_normal(sk_start_tangent(d, next_kind), st.hw), &st);
+    } else {
+        sk_cap(&s, c[3], ne, &st);
+    }
+    return s.n;
+}
+
 uint32_t ot_flatten_fill(const float *cubics, uint32_t n, ot_line_soup *out, uint32_t cap) {   /* flatten.go:32-43 */
     line_sink s = {out, 0, cap};
     for (uint32_t i = 0; i < n; i++) {

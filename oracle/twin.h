@@ -71,6 +71,10 @@ uint32_t ot_flatten_fill(const float *cubics, uint32_t n, ot_line_soup *out, uin
 uint32_t ot_flatten_path(const uint8_t *verbs, uint32_t n_verbs, const double *coords,
                          int auto_close, ot_line_soup *out, uint32_t cap);
 
+/* stroke expansion of one centre-line segment (ggcuda's definition, see twin.c; parity unpinned against gg) */
+uint32_t ot_stroke_segment(const float *seg, int kind, int role, const float *next, int next_kind,
+                           float width, float miter_limit, int join, int cap, ot_line_soup *out, uint32_t out_cap);
+
 /* ---- monoids (pathtag.go:26-63, draw_leaf.go:29-41) ---- */
 void ot_path_monoid_new(uint32_t tag_word, ot_path_monoid *out);
 void ot_draw_monoid_new(uint32_t tag, ot_draw_monoid *out);

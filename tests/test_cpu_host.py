@@ -70,7 +70,7 @@ def test_packed_layout_and_autoclose():
     a = np.float32(128) / np.float32(255)
     assert int(words[lay["draw_data_base"]]) == 0xFF0000FF
     assert int(words[lay["draw_data_base"] + 1]) == (int(np.float32(255) * a + np.float32(0.5)) << 8) | (128 << 24)
-    assert list(words[lay["style_base"]:lay["style_base"] + 2]) == [0, 2]                 # even-odd = bit 1
+    assert list(words[lay["style_base"]:lay["style_base"] + 6]) == [0, 0, 0, 2, 0, 0]     # 3 words per path; even-odd = bit 1
     assert list(words[lay["transform_base"]:lay["style_base"]].view(np.float32)) == [1, 0, 0, 0, 1, 0]
     # monoids of the packed tags agree with the oracle's restatement of pathtag.go
     m = T.path_monoid(int(words[0]))
@@ -139,7 +139,7 @@ def test_unsupported_tags_are_reported():
 
 
 def test_stroke_outline_area():
-    """Host stroke expansion: the outline's area (through the oracle) is length x width (+ caps) within 2 %."""
+    """Stroke of a straight line (expanded by the oracle's statement of the device stroker): length x width (+ caps) within 2 %."""
     for cap, extra in ((0, 0.0), (2, 1.0), (1, np.pi / 4)):
         c = _lib.Context(-1)
         c.begin(128, 64)
@@ -192,3 +192,83 @@ print("rank", rank, "ok")
                         "--master-port", "29541", str(script)], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("ok") == 2
+
+
+def _stroke_alpha(v, c, width, cap, join, w, h, flags=0, miter=4.0):
+    ctx = _lib.Context(-1, flags)
+    ctx.begin(w, h)
+    ctx.stroke_path(v, c, (255, 255, 255, 255), width, cap, join, miter)
+    words, lay = ctx.pack_host()
+    img, _ = T.render_packed(words, lay, w, h)
+    return img[..., 3].astype(np.float64) / 255
+
+
+def test_stroke_centre_line_encoding():
+    """Stroked paths travel as centre lines: 3-word style, degenerate segments dropped, marker copy of the first segment
+    (after a marker MoveTo when the subpath is open), dots only for round / square caps."""
+    def build(c):
+        c.stroke_path([0, 1, 1, 3], [10, 10, 10, 10, 50, 10, 50, 10, 50, 10, 50, 10], (255, 255, 255, 255), 4.0, 1, 2, 7.0)   # open; a repeated point and a null cubic
+        c.stroke_path([0, 1, 1, 4], [10, 30, 50, 30, 30, 60], (255, 255, 255, 255), 2.0, 0, 0, 4.0)                            # closed: closing line added
+        c.stroke_path([0, 0, 1], [5, 5, 80, 80, 90, 80], (255, 255, 255, 255), 2.0, 0, 0, 4.0)                                 # lone MoveTo + butt cap: nothing
+        c.stroke_path([0], [70, 20], (255, 255, 255, 255), 6.0, 2, 0, 4.0)                                                     # dot with a square cap
+    words, lay = _pack(build)
+    assert list(_tags(words, lay)) == [0x20, 0x40, 0x0C, 0x09, 0x8C, 0x89, 0x10,
+                                       0x40, 0x0C, 0x09, 0x09, 0x09, 0x89, 0x10,
+                                       0x40, 0x0C, 0x09, 0x8C, 0x89, 0x10,
+                                       0x40, 0x0C, 0x09, 0x8C, 0x89, 0x10]
+    st = words[lay["style_base"]:lay["style_base"] + 12]
+    assert int(st[0]) == 1 | (2 << 2) | (1 << 4) and st[1:3].view(np.float32).tolist() == [4.0, 7.0]
+    assert int(st[3]) == 1 and int(st[9]) == 1 | (2 << 4)
+    pd = words[lay["path_data_base"]:lay["draw_tag_base"]].view(np.float32)
+    assert list(pd[:8]) == [10, 10, 50, 10, 10, 10, 50, 10]      # MoveTo, LineTo, marker MoveTo, marker copy of the LineTo
+
+
+def test_stroke_areas_closed_forms():
+    """Oracle statement of the stroke expander against closed forms: circles (also with the offset beyond the radius: no
+    hole), joins, caps."""
+    k = 0.5522847498307936
+    for r, wd in ((40, 10), (40, 1), (3, 12), (1, 20), (10, 20)):
+        kk = r * k
+        c = [64 + r, 64, 64 + r, 64 + kk, 64 + kk, 64 + r, 64, 64 + r, 64 - kk, 64 + r, 64 - r, 64 + kk, 64 - r, 64,
+             64 - r, 64 - kk, 64 - kk, 64 - r, 64, 64 - r, 64 + kk, 64 - r, 64 + r, 64 - kk, 64 + r, 64]
+        a = _stroke_alpha([0, 3, 3, 3, 3, 4], c, wd, 0, 1, 128, 128)
+        want = np.pi * ((r + wd / 2) ** 2 - max(r - wd / 2, 0) ** 2)
+        assert abs(a.sum() - want) / want < 0.012, (r, wd, a.sum(), want)
+        if r < wd / 2:
+            assert a[64, 64] == 1.0          # the centre is inside the stroke
+    # right-angle corner, width 10: two 50 x 10 arms overlapping in a 5 x 5 square + the outer join
+    v, c = [0, 1, 1], [20, 20, 70, 20, 70, 70]
+    base = 2 * 50 * 10 - 25
+    for join, extra in ((2, 12.5), (0, 25.0), (1, np.pi * 25 / 4)):
+        a = _stroke_alpha(v, c, 10, 0, join, 100, 100)
+        assert abs(a.sum() - (base + extra)) < 1.0, (join, a.sum(), base + extra)
+    a = _stroke_alpha(v, c, 10, 0, 0, 100, 100, miter=1.0)      # miter limit exceeded -> bevel
+    assert abs(a.sum() - (base + 12.5)) < 1.0
+
+
+def test_stroke_against_distance_field():
+    """Round joins + round caps: the stroke is the set of points within half a width of the curve. Random cubics with cusps
+    and loops, widths up to 24 px: no pixel clearly inside is uncovered, none clearly outside is covered."""
+    rng = np.random.default_rng(0)
+    w = h = 96
+    ys, xs = np.mgrid[0:h, 0:w]
+    P = np.stack([xs + 0.5, ys + 0.5], -1).reshape(-1, 1, 2)
+    for it in range(12):
+        n = int(rng.integers(1, 4))
+        closed = bool(rng.random() < 0.5)
+        c = rng.uniform(8, 88, 2 + 6 * n)
+        wd = float(rng.uniform(0.5, 24))
+        pts, cur = [], c[0:2]
+        t = np.linspace(0, 1, 200)[:, None]
+        for s in range(n):
+            p1, p2, p3 = c[2 + 6 * s:4 + 6 * s], c[4 + 6 * s:6 + 6 * s], c[6 + 6 * s:8 + 6 * s]
+            pts.append((1 - t) ** 3 * cur + 3 * (1 - t) ** 2 * t * p1 + 3 * (1 - t) * t * t * p2 + t ** 3 * p3)
+            cur = p3
+        pts = np.concatenate(pts + ([pts[0][:1]] if closed else []))
+        a0, ab = pts[:-1][None], (pts[1:] - pts[:-1])[None]
+        l2 = np.maximum((ab ** 2).sum(-1), 1e-30)
+        tt = np.clip(((P - a0) * ab).sum(-1) / l2, 0, 1)
+        dist = np.sqrt((((a0 + ab * tt[..., None]) - P) ** 2).sum(-1)).min(1).reshape(h, w)
+        a = _stroke_alpha([0] + [3] * n + ([4] if closed else []), c, wd, 1, 1, w, h)
+        assert not ((dist < wd / 2 - 0.9) & (a < 0.98)).any(), it
+        assert not ((dist > wd / 2 + 0.9) & (a > 0.02)).any(), it

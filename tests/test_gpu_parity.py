@@ -244,3 +244,104 @@ def test_cuda_vs_gg_cpu_aaa_goldens(ctx, name):
     out = U.gpu_scene(ctx, [dict(type="draw", verbs=v, coords=c, color=(255, 255, 255, 255))], 100, 100)
     d = np.abs(out[..., 3].astype(np.float64) - cov_g)
     assert d.mean() <= 0.7 and (d <= 2.5).mean() >= 0.97 and d.max() <= 61
+
+
+# ---- device-side stroke expansion (gg_b200/csrc/stroke.cuh) against its CPU statement (oracle/twin.c ot_stroke_segment) ----
+def _stroke_scene(seed, w, h, n, transforms=False):
+    from gg_b200 import scene as S
+    rng = np.random.default_rng(seed)
+    sc = S.Scene()
+    for i in range(n):
+        kind = i % 6
+        cx, cy = rng.uniform(0, w), rng.uniform(0, h)
+        box = rng.uniform(8, 160)
+        closed = bool(rng.random() < 0.5)
+        if kind == 0:     # polyline
+            m = int(rng.integers(1, 7))
+            pts = np.stack([cx + rng.uniform(-box, box, m + 1), cy + rng.uniform(-box, box, m + 1)], 1)
+            verbs, coords = [S.MOVE] + [S.LINE] * m, list(pts.ravel())
+        elif kind == 1:   # cubics, possibly with cusps and loops
+            m = int(rng.integers(1, 5))
+            verbs, coords = [S.MOVE] + [S.CUBIC] * m, list(np.concatenate([[cx, cy], (np.array([cx, cy]) + rng.uniform(-box, box, (3 * m, 2))).ravel()]))
+        elif kind == 2:   # quads
+            m = int(rng.integers(1, 5))
+            verbs, coords = [S.MOVE] + [S.QUAD] * m, list(np.concatenate([[cx, cy], (np.array([cx, cy]) + rng.uniform(-box, box, (2 * m, 2))).ravel()]))
+        elif kind == 3:   # small circle under a wide stroke (offset > radius of curvature everywhere)
+            verbs, coords = S.circle_verbs_coords(cx, cy, rng.uniform(0.5, 6))
+            closed = False
+        elif kind == 4:   # two subpaths, degenerate pieces: repeated points, a zero-length curve, a lone MoveTo (dot)
+            verbs = [S.MOVE, S.LINE, S.LINE, S.CUBIC, S.MOVE, S.MOVE, S.LINE, S.QUAD]
+            a, b = (cx, cy), (cx + box, cy + box / 3)
+            coords = [*a, *a, *b, *b, *b, *b, cx - 9, cy - 9, cx + 5, cy - box, cx + 5, cy, cx + 5, cy, cx + box / 2, cy]
+        else:             # mixed
+            verbs = [S.MOVE, S.LINE, S.CUBIC, S.QUAD, S.LINE]
+            coords = list(np.concatenate([[cx, cy], (np.array([cx, cy]) + rng.uniform(-box, box, (7, 2))).ravel()]))
+        if closed:
+            verbs = list(verbs) + [S.CLOSE]
+        t = S.IDENTITY
+        if transforms and i % 3 == 0:
+            t = (float(rng.uniform(0.5, 1.5)), float(rng.uniform(-0.4, 0.4)), float(rng.uniform(-20, 20)),
+                 float(rng.uniform(-0.4, 0.4)), float(rng.uniform(0.5, 1.5)), float(rng.uniform(-20, 20)))
+        col = (*rng.uniform(0, 1, 3), rng.uniform(0.3, 1.0))
+        sc.Stroke(dict(width=float(rng.choice([0.3, 1.0, 2.5, 7.0, 12.0, 30.0])), miter_limit=float(rng.choice([1.0, 4.0, 10.0])),
+                       cap=int(rng.integers(0, 3)), join=int(rng.integers(0, 3))), t, col, (verbs, [float(v) for v in coords]))
+        if i % 5 == 0:    # fills in between: the two kinds share the work list
+            sc.Fill(S.FillNonZero, t, col, S.circle_verbs_coords(rng.uniform(0, w), rng.uniform(0, h), rng.uniform(4, 40)))
+    return sc.Encoding()
+
+
+@pytest.mark.parametrize("seed,w,h,n,tr", [(21, 512, 384, 240, False), (22, 700, 500, 400, True), (23, 128, 96, 60, True)])
+def test_strokes_device_expansion(ctx, seed, w, h, n, tr):
+    """Stroked paths (all caps / joins / miter limits, open and closed, cusps, degenerate pieces, transforms): the lines the
+    device writes are the oracle's, bit for bit and in order; every later stage follows as for fills."""
+    _check_encoding(ctx, _stroke_scene(seed, w, h, n, tr), w, h)
+
+
+def test_strokes_per_draw_api_and_bands(ctx):
+    """GPUAccelerator.StrokePath entry (ggcuda_stroke_path) and band culling of stroked segments."""
+    w, h = 400, 320
+    rng = np.random.default_rng(31)
+
+    def build():
+        ctx.begin(w, h)
+        for i in range(80):
+            m = int(rng.integers(1, 4))
+            c = rng.uniform(0, [w, h] * (1 + 3 * m))
+            ctx.stroke_path([0] + [3] * m + ([4] if i % 2 else []), c, tuple(int(q) for q in rng.integers(60, 256, 4)),
+                            float(rng.uniform(0.5, 20)), int(i % 3), int((i // 3) % 3), 4.0)
+    build()
+    full = np.zeros((h, w, 4), np.uint8)
+    ctx.set_band(0, (h + 15) // 16)
+    ctx.flush(full, flags=G.KEEP_SCENE)
+    oc = U.oracle_from_ctx(ctx, w, h)
+    U.compare_stages(ctx, oc, None, w, h)
+    _, ref = oc.fine((0, 0, 0, 0), straight=False, premul=True)
+    mx, _, frac = U.pixel_diff(full, ref)
+    assert mx <= 1 and frac <= 0.002
+    parts = np.zeros_like(full)
+    for y0, y1 in ((0, 7), (7, 13), (13, 20)):
+        ctx.set_band(y0, y1)
+        ctx.flush(parts, flags=G.KEEP_SCENE)
+    assert (parts == full).all()
+
+
+def test_strokes_device_vs_host_stroker(ctx):
+    """Same scene through the diagnostic host polyline stroker (GGCUDA_CREATE_HOST_STROKES): the two outlines are
+    different constructions of the same stroke, so pixels agree except along edges (flattening differs) and where the
+    host stroker is wrong (it leaves holes / spikes where the offset exceeds the radius of curvature)."""
+    from gg_b200 import scene as S
+    rng = np.random.default_rng(41)
+    sc = S.Scene()
+    w, h = 512, 512
+    for i in range(60):
+        pts = rng.uniform(0, w, (5, 2))
+        sc.Stroke(dict(width=float(rng.uniform(1, 10)), cap=int(i % 3), join=int((i // 3) % 3)), S.IDENTITY, (1, 1, 1, 1),
+                  ([S.MOVE] + [S.LINE] * 4 + ([S.CLOSE] if i % 2 else []), [float(v) for v in pts.ravel()]))
+    a = U.gpu_encoding(ctx, sc.Encoding(), w, h)
+    hc = G.Context(0, G.CREATE_HOST_STROKES)
+    try:
+        b = U.gpu_encoding(hc, sc.Encoding(), w, h)
+    finally:
+        hc.close()
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    assert d.mean() < 0.02 and (d > 8).mean() < 1e-3, (d.max(), d.mean())   # round joins / caps are tessellated differently
