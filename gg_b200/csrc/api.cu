@@ -22,6 +22,7 @@
 #include "../../include/ggcuda.h"
 #include "host_scene.h"
 #include "pipeline.cuh"
+#include "flatten.cuh"
 
 namespace {
 
@@ -46,10 +47,10 @@ struct Ctx {
     GGBump* h_bump = nullptr;
     uint8_t* h_frame = nullptr; size_t h_frame_bytes = 0;
     // device
-    DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, curve_list, lines, path_bbox, paths, path_row_off,
+    DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, curve_list, esegs, lines, path_bbox, paths, path_row_off,
         tiles, seg_start, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, restart_pt, spill_off, spill, bump,
         scan_partials, frame_d;
-    uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0;
+    uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0, esegs_cap = 0;
     // Read-back target seen on consecutive flushes (gg keeps one pixmap per context): page-locked in place
     // from its second use so the band is DMA'd straight into it, without the staging copy.
     uint8_t* last_dst = nullptr; size_t last_dst_bytes = 0; bool dst_registered = false;
@@ -82,7 +83,7 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes) {
     return 0;
 }
 size_t total_device_bytes(Ctx* c) {
-    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list,
+    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list, &c->esegs,
                      &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
                      &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->restart_pt, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
@@ -91,7 +92,7 @@ size_t total_device_bytes(Ctx* c) {
     return t;
 }
 void free_all(Ctx* c) {
-    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list,
+    DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list, &c->esegs,
                      &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
                      &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->restart_pt, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
@@ -151,6 +152,7 @@ int upload(Ctx* c) {
     if ((r = ensure(c, c->scan_partials, 32 * GG_SCAN_BLOCKS))) return r;
     // first guesses for the data-dependent buffers; the retry loop corrects them
     c->lines_cap = std::max<uint32_t>(c->lines_cap, 16u * c->scene.n_seg_tags + 1024u);
+    c->esegs_cap = std::max<uint32_t>(c->esegs_cap, 4u * c->scene.n_seg_tags + 1024u);
     c->tiles_cap = std::max<uint32_t>(c->tiles_cap, 64u * L.n_paths + 4096u);
     c->rows_cap = 0xffffffffu;
     c->seg_counts_cap = std::max<uint32_t>(c->seg_counts_cap, 2u * c->lines_cap);
@@ -164,6 +166,7 @@ int upload(Ctx* c) {
 int size_dynamic(Ctx* c) {
     int r;
     if ((r = ensure(c, c->lines, sizeof(GGLine) * (size_t)c->lines_cap))) return r;
+    if ((r = ensure(c, c->esegs, sizeof(GGESeg) * (size_t)c->esegs_cap))) return r;
     if ((r = ensure(c, c->tiles, sizeof(GGTile) * (size_t)c->tiles_cap))) return r;
     if ((r = ensure(c, c->seg_start, 4 * (size_t)c->tiles_cap))) return r;
     if ((r = ensure(c, c->seg_counts, sizeof(GGSegCount) * (size_t)c->seg_counts_cap))) return r;
@@ -187,7 +190,7 @@ void fill_config(Ctx* c, uint32_t flags) {
     g.draw_data_base = L.draw_data_base; g.transform_base = L.transform_base; g.style_base = L.style_base;
     g.clip_parent_base = L.clip_aux_base; g.n_scene_words = L.n_scene_words;
     g.lines_cap = c->lines_cap; g.tiles_cap = c->tiles_cap; g.rows_cap = c->rows_cap; g.seg_counts_cap = c->seg_counts_cap;
-    g.segments_cap = c->segments_cap; g.hits_cap = c->hits_cap; g.ptcl_cap = c->ptcl_cap; g.spill_cap = c->spill_cap;
+    g.segments_cap = c->segments_cap; g.hits_cap = c->hits_cap; g.ptcl_cap = c->ptcl_cap; g.spill_cap = c->spill_cap; g.esegs_cap = c->esegs_cap;
     for (int i = 0; i < 4; i++) g.bg[i] = (float)c->bg[i] / 255.0f;
     g.flags = (flags & GGCUDA_COMPOSITE_OVER) ? GG_FLAG_BG_FROM_DST : 0u;
 }
@@ -196,7 +199,7 @@ GGBuffers buffers(Ctx* c) {
     GGBuffers b;
     b.scene = (uint32_t*)c->scene_d.p; b.tag_monoids = (GGPathMonoid*)c->tag_monoids.p; b.draw_monoids = (GGDrawMonoid*)c->draw_monoids.p;
     b.info = (uint32_t*)c->info.p; b.clip_inps = (GGClipInp*)c->clip_inps.p; b.draw_recs = (GGDrawRec*)c->draw_recs.p;
-    b.line_count = (uint32_t*)c->line_count.p; b.line_off = (uint32_t*)c->line_off.p; b.curve_list = (uint32_t*)c->curve_list.p; b.lines = (GGLine*)c->lines.p;
+    b.line_count = (uint32_t*)c->line_count.p; b.line_off = (uint32_t*)c->line_off.p; b.curve_list = (uint32_t*)c->curve_list.p; b.esegs = (GGESeg*)c->esegs.p; b.lines = (GGLine*)c->lines.p;
     b.path_bbox_ord = (uint32_t*)c->path_bbox.p; b.paths = (GGPath*)c->paths.p; b.path_row_off = (uint32_t*)c->path_row_off.p;
     b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
     b.segments = (GGSegment*)c->segments.p; b.tile_hits = (unsigned long long*)c->tile_hits.p; b.hit_off = (uint32_t*)c->hit_off.p;
@@ -229,7 +232,7 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
         gg_launch_fine(c->cfg, b, dst_device, stride, c->stream);
         if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
         c->stats.passes++;
-        c->stats.kernel_launches += 18 + 7 + 5 + 1;
+        c->stats.kernel_launches += 18 + 7 + 5 + 1;   // front (4 scans x 3 + 6) + binning + coarse + fine
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
         GGBump bm = *c->h_bump;
@@ -237,6 +240,7 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
         bool grow = false;
         auto need = [&](uint32_t& cap, uint64_t required) { if (required > cap) { cap = (uint32_t)std::min<uint64_t>(required + required / 4 + 1024, 0xfffffff0u); grow = true; } };
         need(c->lines_cap, bm.lines);
+        need(c->esegs_cap, bm.esegs);
         need(c->tiles_cap, bm.path_tiles);
         need(c->seg_counts_cap, bm.seg_counts);
         need(c->segments_cap, bm.segments);

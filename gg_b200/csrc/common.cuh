@@ -73,7 +73,8 @@ struct GGBump {
     uint32_t spill;        // 28: blend-spill tile-levels (clip depth > 4)
     uint32_t failed;       // 32: bitmask of stages whose capacity was exceeded
     uint32_t curves;       // 36: curve tags compacted by flatten_classify
-    uint32_t pad[6];
+    uint32_t esegs;        // 40: Euler-segment records written by flatten_subdivide
+    uint32_t pad[5];
 };
 #define GG_FAIL_LINES 1u
 #define GG_FAIL_TILES 2u
@@ -82,6 +83,7 @@ struct GGBump {
 #define GG_FAIL_HITS 16u
 #define GG_FAIL_PTCL 32u
 #define GG_FAIL_SPILL 64u
+#define GG_FAIL_ESEGS 128u
 
 // Per-frame configuration (kernel argument, by value).
 struct GGConfig {
@@ -93,7 +95,7 @@ struct GGConfig {
     uint32_t path_tag_base, path_data_base, draw_tag_base, draw_data_base, transform_base, style_base; // word offsets
     uint32_t clip_parent_base;              // word offset of the host-resolved clip-parent array (n_draws words)
     uint32_t n_scene_words;
-    uint32_t lines_cap, tiles_cap, rows_cap, seg_counts_cap, segments_cap, hits_cap, ptcl_cap, spill_cap;
+    uint32_t lines_cap, tiles_cap, rows_cap, seg_counts_cap, segments_cap, hits_cap, ptcl_cap, spill_cap, esegs_cap;
     float bg[4];                            // premultiplied background
     uint32_t flags;
 };

@@ -156,13 +156,34 @@ __device__ __forceinline__ void eval_cubic_and_deriv(V2 p0, V2 p1, V2 p2, V2 p3,
 }
 __device__ __forceinline__ float cube_signed_sqrt(float x) { return x * sqrt32(fabsf(x)); }   // flatten.go:195
 
-// Runs the adaptive subdivision. EMIT=false: returns the number of lines. EMIT=true: writes them
-// to out[0..] (path_ix set) and folds their endpoints into bb (minx, miny, maxx, maxy).
-template <bool EMIT>
-__device__ inline uint32_t flatten_cubic(V2 p0, V2 p1, V2 p2, V2 p3, uint32_t path_ix, GGLine* out, uint32_t out_cap_left, float* bb) {
+// One accepted Euler segment of a curve on the flatten work list (or, for stroked paths, one straight piece / one cap
+// marker). The subdivision loop (serial per curve, cheap) only decides these records and how many lines each one
+// owns; the lines themselves -- one Euler-spiral evaluation with float64 transcendentals per point -- are written by
+// one thread per record.
+struct GGESeg {
+    V2 p0, p1;                    // end points of the segment's chord (this_p0, this_p1 of flatten.go:88-96)
+    float th0, k0, k1, ch;        // EulerParams (euler.go:93-119)
+    float chord_len, n;           // CubicParams.chord_len; line count n as the float the reference divides by
+    float a, b, integral, int0;   // inverse-integral parameters (flatten.go:119-129)
+    uint32_t tag_ix;              // tag byte of the owning segment
+    uint32_t path_ix;
+    uint32_t line_rel;            // first line of this record, relative to line_off[tag_ix]
+    uint32_t prev;                // record holding the previous Euler segment of the same curve (0xffffffff: first)
+    uint32_t flags;               // GG_ESEG_*
+};
+#define GG_ESEG_LOW_K1 1u         // s = t (flatten.go:148-149)
+#define GG_ESEG_LAST 2u           // t1 == 1: the last point is the curve's end point itself
+#define GG_ESEG_STROKE 4u         // stroked path: two outline lines per subdivision (stroke.cuh)
+#define GG_ESEG_LINE 8u           // stroked straight segment: one piece, no Euler parameters
+#define GG_ESEG_CAP 16u           // stroke marker after an open subpath: the start cap
+
+// The adaptive subdivision of flatten.go:76-183 without the emission loop: `sink(rec)` is called once per accepted
+// Euler segment with everything but the bookkeeping fields filled in. widen_hw > 0 raises n by
+// sqrt(1 + hw * max curvature) so that the outer parallel curve of a stroke stays within the tolerance too.
+template <typename Sink>
+__device__ inline void subdivide_cubic(V2 p0, V2 p1, V2 p2, V2 p3, float widen_hw, Sink& sink) {
     const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f, FLATTEN_TOL = 0.25f;
-    if (veq(p0, p1) && veq(p0, p2) && veq(p0, p3)) return 0;
-    uint32_t n_out = 0;
+    if (veq(p0, p1) && veq(p0, p2) && veq(p0, p3)) return;
     uint32_t t0u = 0;
     float dt = 1.0f;
     V2 last_p = p0;
@@ -171,7 +192,6 @@ __device__ inline uint32_t flatten_cubic(V2 p0, V2 p1, V2 p2, V2 p3, uint32_t pa
         V2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &last_q);
     }
     float last_t = 0.0f;
-    V2 lp0 = p0;
     for (;;) {
         float t0 = (float)t0u * dt;
         if (t0 == 1.0f) break;
@@ -191,55 +211,35 @@ __device__ inline uint32_t flatten_cubic(V2 p0, V2 p1, V2 p2, V2 p3, uint32_t pa
             float k0_minus_half_k1 = ep.k0 - 0.5f * ep.k1;
             float k1 = ep.k1;
             float scale_mul = 0.5f * (float)(1.41421356237309504880168872420969808 / 2.0) * sqrt32(cp.chord_len / (ep.ch * FLATTEN_TOL));
+            GGESeg r;
+            r.a = 0; r.b = 0; r.integral = 0; r.int0 = 0; r.flags = 0;
             float n_frac;
-            bool low_k1;
-            float a = 0, b = 0, integral = 0, int0 = 0;
             if (fabsf(k1) < 1e-3f) {
                 float k = k0_minus_half_k1 + 0.5f * k1;
                 n_frac = sqrt32(fabsf(k));
-                low_k1 = true;
+                r.flags |= GG_ESEG_LOW_K1;
             } else {
-                a = k1;
-                b = k0_minus_half_k1;
-                int0 = cube_signed_sqrt(b);
-                float int1 = cube_signed_sqrt(a + b);
-                integral = int1 - int0;
-                n_frac = (float)(2.0 / 3.0) * integral / a;
-                low_k1 = false;
+                r.a = k1;
+                r.b = k0_minus_half_k1;
+                r.int0 = cube_signed_sqrt(r.b);
+                float int1 = cube_signed_sqrt(r.a + r.b);
+                r.integral = int1 - r.int0;
+                n_frac = (float)(2.0 / 3.0) * r.integral / r.a;
             }
-            float n = ceilf(n_frac * scale_mul);
+            float nn = n_frac * scale_mul;
+            if (widen_hw > 0.0f) {
+                float k_abs = f_max(fabsf(k0_minus_half_k1), fabsf(k0_minus_half_k1 + k1));
+                nn = nn * sqrt32(1.0f + widen_hw * k_abs * ep.ch / cp.chord_len);
+            }
+            float n = ceilf(nn);
             if (n < 1) n = 1;
             if (n > 100) n = 100;
-            int n_int = (n != n) ? 0 : (int)n;
-            if (EMIT) {
-                for (int i = 0; i < n_int; i++) {
-                    V2 lp1;
-                    if (i == n_int - 1 && t1 == 1.0f) {
-                        lp1 = p3;
-                    } else {
-                        float t = (float)(i + 1) / n;
-                        float s;
-                        if (low_k1) {
-                            s = t;
-                        } else {
-                            float c = (float)cbrt((double)(integral * t + int0));
-                            float inv = c * fabsf(c);
-                            s = (inv - b) / a;
-                        }
-                        lp1 = euler_seg_eval(this_p0, this_p1, ep, s);
-                    }
-                    if (n_out < out_cap_left) {
-                        GGLine l; l.path_ix = path_ix; l.p0x = lp0.x; l.p0y = lp0.y; l.p1x = lp1.x; l.p1y = lp1.y;
-                        out[n_out] = l;
-                    }
-                    bb[0] = fminf(bb[0], lp1.x); bb[1] = fminf(bb[1], lp1.y);
-                    bb[2] = fmaxf(bb[2], lp1.x); bb[3] = fmaxf(bb[3], lp1.y);
-                    n_out++;
-                    lp0 = lp1;
-                }
-            } else {
-                n_out += (uint32_t)n_int;
-            }
+            if (n != n) n = 0;   // NaN (degenerate input): Go's int(NaN) gives an empty loop
+            r.p0 = this_p0; r.p1 = this_p1;
+            r.th0 = ep.th0; r.k0 = ep.k0; r.k1 = ep.k1; r.ch = ep.ch;
+            r.chord_len = cp.chord_len; r.n = n;
+            if (t1 == 1.0f) r.flags |= GG_ESEG_LAST;
+            sink(r);
             last_p = this_p1; last_q = this_q1; last_t = t1;
             t0u++;
             uint32_t shift = (uint32_t)(__ffs((int)t0u) - 1);   // trailing zeros; t0u != 0 here
@@ -250,5 +250,18 @@ __device__ inline uint32_t flatten_cubic(V2 p0, V2 p1, V2 p2, V2 p3, uint32_t pa
             dt *= 0.5f;
         }
     }
-    return n_out;
+}
+
+// Arc-length parameter of subdivision point j (0-based: the point that ends line j), flatten.go:144-157.
+__device__ __forceinline__ float eseg_param(const GGESeg& r, int j) {
+    float t = (float)(j + 1) / r.n;
+    if (r.flags & GG_ESEG_LOW_K1) return t;
+    float c = (float)cbrt((double)(r.integral * t + r.int0));
+    float inv = c * fabsf(c);
+    return (inv - r.b) / r.a;
+}
+__device__ __forceinline__ V2 eseg_point(const GGESeg& r, int j) {
+    if ((r.flags & GG_ESEG_LAST) && j == (int)r.n - 1) return r.p1;   // exact end point (flatten.go:141-142)
+    EulerParams ep; ep.th0 = r.th0; ep.k0 = r.k0; ep.k1 = r.k1; ep.ch = r.ch;
+    return euler_seg_eval(r.p0, r.p1, ep, eseg_param(r, j));
 }

@@ -165,35 +165,13 @@ __device__ inline bool load_curve(const GGConfig& cfg, const uint32_t* __restric
     return true;
 }
 
-// The outline lines one stroked segment (tag byte i) is responsible for; see stroke.cuh.
-template <bool EMIT>
-__device__ inline uint32_t stroke_segment(const GGConfig& cfg, const uint32_t* __restrict__ scene, const GGPathMonoid* __restrict__ tag_monoids,
-                                          uint32_t i, const CurveIn& c, const StrokeStyle& st, GGLine* out, uint32_t cap, float* bb) {
-    LineOut o; o.out = out; o.n = 0; o.cap = cap; o.path_ix = c.path_ix;
-    o.bb[0] = o.bb[1] = 3.0e38f; o.bb[2] = o.bb[3] = -3.0e38f;
-    V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
-    if (c.tag & GG_PTAG_MARKER) {
-        // copy of the subpath's first segment: it only exists so that the last segment can read its start tangent
-        // (closed subpath) or, after a marker MoveTo, to draw the start cap of an open subpath
-        if (i > 0 && tag_byte(cfg, scene, i - 1) == GG_PTAG_MARKER_MOVE) stroke_cap<EMIT>(o, c.p0, mk(-ns.x, -ns.y), st);
-    } else {
-        V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
-        if (c.kind == 1) stroke_piece<EMIT>(o, stroke_vertex(c.p0, ns), stroke_vertex(c.p3, ne), st.hw);
-        else stroke_cubic<EMIT>(o, c.p0, c.p1, c.p2, c.p3, ns, ne, st.hw);
-        CurveIn nx;
-        if (i + 1 < cfg.n_tag_bytes && load_curve(cfg, scene, tag_monoids, i + 1, &nx))
-            stroke_join<EMIT>(o, c.p3, ne, stroke_normal(seg_start_tangent(nx.p0, nx.p1, nx.p2, nx.p3, nx.kind), st.hw), st);
-        else
-            stroke_cap<EMIT>(o, c.p3, ne, st);
-    }
-    if (EMIT) { bb[0] = o.bb[0]; bb[1] = o.bb[1]; bb[2] = o.bb[2]; bb[3] = o.bb[3]; }
-    return o.n;
-}
-
-// Flatten runs as: classify (every tag byte: lines are counted on the spot, curve tags are compacted into a
-// dense list), curve_count (dense: one thread per curve runs the Euler subdivision), scan of the per-tag line
-// counts, line_emit (every tag byte, trivial) and curve_emit (dense). In the first version one thread per tag
-// byte ran everything and a warp of LineTo tags waited for its one cubic: 5 of 32 lanes active (ncu).
+// Flatten runs as: classify (every tag byte: fill lines are counted on the spot; curve tags and every segment of a
+// stroked path are compacted into a dense work list), subdivide (one thread per work item runs the adaptive
+// Euler-spiral subdivision -- serial but cheap -- and leaves one GGESeg record per accepted Euler segment plus the
+// item's line count), scan of the per-tag line counts, line_emit (fill LineTo tags, trivial) and eseg_emit (one
+// thread per RECORD evaluates its points: the float64 transcendentals run ~200 k wide instead of ~45 k curves wide).
+// History (ncu): one thread per tag byte running everything kept 5 of 32 lanes busy; one thread per curve running
+// count and emit serially was latency bound at ~2 warps per scheduler once strokes were expanded here too.
 __device__ __forceinline__ void fold_bbox(uint32_t* path_bbox_ord, uint32_t path_ix, const float* bb) {
     uint32_t* pb = path_bbox_ord + 4 * (size_t)path_ix;
     atomicMin(pb + 0, f_ord(bb[0]));
@@ -248,17 +226,67 @@ __global__ void __launch_bounds__(256) flatten_classify_kernel(GGConfig cfg, con
     }
 }
 
-__global__ void __launch_bounds__(128) flatten_curve_count_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
-                                                                  const GGPathMonoid* __restrict__ tag_monoids,
-                                                                  const uint32_t* __restrict__ curve_list, uint32_t* line_count, const GGBump* bump) {
+struct ESegSink {
+    GGESeg* esegs; uint32_t cap; GGBump* bump;
+    uint32_t tag_ix, path_ix, flags, lines_per_piece, line_rel, prev;
+    __device__ void operator()(GGESeg& r) {
+        uint32_t ix = atomicAdd(&bump->esegs, 1u);
+        r.tag_ix = tag_ix; r.path_ix = path_ix; r.line_rel = line_rel; r.prev = prev; r.flags |= flags;
+        if (ix < cap) esegs[ix] = r; else atomicOr(&bump->failed, GG_FAIL_ESEGS);
+        prev = ix;
+        line_rel += lines_per_piece * (uint32_t)r.n;
+    }
+};
+
+// Lines of the join to the next segment / of the end cap, written (EMIT) or counted after a stroked segment's sides.
+template <bool EMIT>
+__device__ inline void stroke_tail(LineOut& o, const GGConfig& cfg, const uint32_t* __restrict__ scene, const GGPathMonoid* __restrict__ tag_monoids,
+                                   uint32_t i, const CurveIn& c, V2 ne, const StrokeStyle& st) {
+    CurveIn nx;
+    if (i + 1 < cfg.n_tag_bytes && load_curve(cfg, scene, tag_monoids, i + 1, &nx))
+        stroke_join<EMIT>(o, c.p3, ne, stroke_normal(seg_start_tangent(nx.p0, nx.p1, nx.p2, nx.p3, nx.kind), st.hw), st);
+    else
+        stroke_cap<EMIT>(o, c.p3, ne, st);
+}
+
+__global__ void __launch_bounds__(128) flatten_subdivide_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                                const GGPathMonoid* __restrict__ tag_monoids,
+                                                                const uint32_t* __restrict__ curve_list, uint32_t* line_count,
+                                                                GGESeg* esegs, GGBump* bump) {
     const uint32_t n = bump->curves;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         uint32_t i = curve_list[k];
         CurveIn c;
         load_curve(cfg, scene, tag_monoids, i, &c);
+        ESegSink sink; sink.esegs = esegs; sink.cap = cfg.esegs_cap; sink.bump = bump;
+        sink.tag_ix = i; sink.path_ix = c.path_ix; sink.flags = 0; sink.lines_per_piece = 1; sink.line_rel = 0; sink.prev = 0xffffffffu;
         StrokeStyle st;
-        if (load_stroke_style(cfg, scene, c.style_ix, &st)) line_count[i] = stroke_segment<false>(cfg, scene, tag_monoids, i, c, st, nullptr, 0, nullptr);
-        else line_count[i] = flatten_cubic<false>(c.p0, c.p1, c.p2, c.p3, c.path_ix, nullptr, 0, nullptr);
+        if (!load_stroke_style(cfg, scene, c.style_ix, &st)) {
+            subdivide_cubic(c.p0, c.p1, c.p2, c.p3, 0.0f, sink);
+            line_count[i] = sink.line_rel;
+            continue;
+        }
+        LineOut o; o.out = nullptr; o.n = 0; o.cap = 0; o.path_ix = c.path_ix;
+        sink.flags = GG_ESEG_STROKE; sink.lines_per_piece = 2;
+        GGESeg r;
+        r.p0 = c.p0; r.p1 = c.p3; r.th0 = r.k0 = r.k1 = 0; r.ch = 1; r.chord_len = 0; r.a = r.b = r.integral = r.int0 = 0;
+        if (c.tag & GG_PTAG_MARKER) {
+            // copy of the subpath's first segment: it exists so that the last segment can read the tangent of a closing
+            // join; after a marker MoveTo (open subpath) it draws the start cap
+            if (i > 0 && tag_byte(cfg, scene, i - 1) == GG_PTAG_MARKER_MOVE) {
+                V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+                stroke_cap<false>(o, c.p0, mk(-ns.x, -ns.y), st);
+                r.n = 0; r.flags = GG_ESEG_CAP;
+                sink(r);
+            }
+            line_count[i] = o.n;
+            continue;
+        }
+        if (c.kind == 1) { r.n = 1; r.flags = GG_ESEG_LINE | GG_ESEG_LAST; sink(r); }
+        else subdivide_cubic(c.p0, c.p1, c.p2, c.p3, st.hw, sink);
+        V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+        stroke_tail<false>(o, cfg, scene, tag_monoids, i, c, ne, st);
+        line_count[i] = sink.line_rel + o.n;
     }
 }
 
@@ -282,25 +310,62 @@ __global__ void __launch_bounds__(256) flatten_line_emit_kernel(GGConfig cfg, co
     }
 }
 
-__global__ void __launch_bounds__(128) flatten_curve_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
-                                                                 const GGPathMonoid* __restrict__ tag_monoids,
-                                                                 const uint32_t* __restrict__ curve_list,
-                                                                 const uint32_t* __restrict__ line_count, const uint32_t* __restrict__ line_off,
-                                                                 GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
-    const uint32_t n_curves = bump->curves;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_curves; k += gridDim.x * blockDim.x) {
-        uint32_t i = curve_list[k];
-        uint32_t n = line_count[i];
-        if (n == 0) continue;
-        uint32_t off = line_off[i];
-        if (off + n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
+__global__ void __launch_bounds__(128) flatten_eseg_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+                                                                const GGPathMonoid* __restrict__ tag_monoids,
+                                                                const GGESeg* __restrict__ esegs, const uint32_t* __restrict__ line_off,
+                                                                GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
+    if (bump->failed) return;
+    const uint32_t n_rec = min(bump->esegs, cfg.esegs_cap);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_rec; k += gridDim.x * blockDim.x) {
+        const GGESeg r = esegs[k];
+        const uint32_t i = r.tag_ix;
+        const int n = (int)r.n;
+        float bb[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
+        uint32_t base = line_off[i] + r.line_rel;
+        if (!(r.flags & (GG_ESEG_STROKE | GG_ESEG_CAP))) {
+            if ((uint64_t)base + (uint32_t)n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
+            V2 lp0 = r.p0;   // first Euler segment: the curve's start point (last_p == p0)
+            if (r.prev != 0xffffffffu) { const GGESeg pr = esegs[r.prev]; lp0 = eseg_point(pr, (int)pr.n - 1); }
+            for (int j = 0; j < n; j++) {
+                V2 lp1 = eseg_point(r, j);
+                write_line(lines + base + j, r.path_ix, lp0, lp1, bb);
+                lp0 = lp1;
+            }
+            if (n > 0) fold_bbox(path_bbox_ord, r.path_ix, bb);
+            continue;
+        }
+        // ---- stroked path
         CurveIn c;
         load_curve(cfg, scene, tag_monoids, i, &c);
-        float bb[4] = {c.p0.x, c.p0.y, c.p0.x, c.p0.y};
         StrokeStyle st;
-        if (load_stroke_style(cfg, scene, c.style_ix, &st)) stroke_segment<true>(cfg, scene, tag_monoids, i, c, st, lines + off, n, bb);
-        else flatten_cubic<true>(c.p0, c.p1, c.p2, c.p3, c.path_ix, lines + off, n, bb);
-        fold_bbox(path_bbox_ord, c.path_ix, bb);
+        load_stroke_style(cfg, scene, c.style_ix, &st);
+        V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+        V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+        LineOut o; o.n = 0; o.path_ix = r.path_ix;
+        o.bb[0] = o.bb[1] = 3.0e38f; o.bb[2] = o.bb[3] = -3.0e38f;
+        if (r.flags & GG_ESEG_CAP) {
+            o.out = lines + base; o.cap = base < cfg.lines_cap ? cfg.lines_cap - base : 0;
+            stroke_cap<true>(o, c.p0, mk(-ns.x, -ns.y), st);
+            if (o.n > o.cap) atomicOr(&bump->failed, GG_FAIL_LINES);
+            if (o.n) fold_bbox(path_bbox_ord, r.path_ix, o.bb);
+            continue;
+        }
+        if ((uint64_t)base + 2u * (uint32_t)n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
+        StrokeVertex v0 = stroke_vertex(r.p0, ns);
+        if (r.prev != 0xffffffffu) { const GGESeg pr = esegs[r.prev]; v0 = eseg_vertex(pr, (int)pr.n - 1, st.hw, ne, ns); }
+        for (int j = 0; j < n; j++) {
+            StrokeVertex v1 = (r.flags & GG_ESEG_LINE) ? stroke_vertex(r.p1, ne) : eseg_vertex(r, j, st.hw, ne, ns);
+            stroke_piece_emit(lines, base + 2u * (uint32_t)j, cfg.lines_cap, &bump->lines, &bump->failed, r.path_ix, v0, v1, st.hw, bb);
+            v0 = v1;
+        }
+        if (r.flags & GG_ESEG_LAST) {
+            uint32_t tb = base + 2u * (uint32_t)n;
+            o.out = lines + tb; o.cap = tb < cfg.lines_cap ? cfg.lines_cap - tb : 0;
+            stroke_tail<true>(o, cfg, scene, tag_monoids, i, c, ne, st);
+            if (o.n > o.cap) atomicOr(&bump->failed, GG_FAIL_LINES);
+            bb[0] = fminf(bb[0], o.bb[0]); bb[1] = fminf(bb[1], o.bb[1]); bb[2] = fmaxf(bb[2], o.bb[2]); bb[3] = fmaxf(bb[3], o.bb[3]);
+        }
+        if (bb[0] <= bb[2]) fold_bbox(path_bbox_ord, r.path_ix, bb);
     }
 }
 
@@ -909,10 +974,10 @@ void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     draw_leaf_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.scene, b.draw_monoids, b.info, b.clip_inps, b.draw_recs);
     // a6: flatten (count, scan, emit)
     flatten_classify_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.curve_list, b.bump);
-    flatten_curve_count_kernel<<<GG_GRID(4), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.bump);
+    flatten_subdivide_kernel<<<GG_GRID(4), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.esegs, b.bump);
     gg_scan<uint32_t>(s, n_tag_bytes, cfg.n_tag_bytes, LoadU32{b.line_count}, StoreU32Ex{b.line_off}, (uint32_t*)b.scan_partials, &b.bump->lines);
     flatten_line_emit_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
-    flatten_curve_emit_kernel<<<GG_GRID(4), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
+    flatten_eseg_emit_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.esegs, b.line_off, b.lines, b.path_bbox_ord, b.bump);
     // a7: per-path tile bbox + tile / row offsets (one packed scan)
     gg_scan<unsigned long long>(s, n_paths, cfg.n_paths, LoadPathTiles{cfg, b.path_bbox_ord}, StorePath{cfg, b.path_bbox_ord, b.paths, b.path_row_off},
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->path_tiles));

@@ -16,6 +16,7 @@ struct GGBuffers {
     uint32_t* line_count;       // [n_tag_bytes]
     uint32_t* line_off;         // [n_tag_bytes]
     uint32_t* curve_list;       // [n_tag_bytes] tag-byte indices of quad / cubic tags (dense work list)
+    struct GGESeg* esegs;       // [esegs_cap] Euler-segment records (flatten.cuh)
     GGLine* lines;              // [lines_cap]
     uint32_t* path_bbox_ord;    // [4*n_paths] order-mapped float min/max
     // binning

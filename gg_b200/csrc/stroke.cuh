@@ -87,26 +87,48 @@ __device__ inline V2 put_arc(LineOut& o, V2 c, V2 v0, float sweep, float hw, V2 
     return last;
 }
 
-// One side quad between two outline vertices of the same segment.
-template <bool EMIT>
-__device__ inline void stroke_piece(LineOut& o, const StrokeVertex& a, const StrokeVertex& b, float hw) {
+// One side quad between two outline vertices of the same segment: exactly two lines in the curve's own slots
+// (main[0], main[1]; possibly zero length, which path_count ignores). A quad with an edge that would run backwards
+// becomes the piece's rectangle + a bevel on the outer side of each end with the inner side through the centre
+// point: up to eight lines, the surplus appended behind the scan-allocated lines (slots claimed from bump->lines).
+__device__ __forceinline__ void write_line(GGLine* dst, uint32_t path_ix, V2 a, V2 b, float* bb) {
+    GGLine l; l.path_ix = path_ix; l.p0x = a.x; l.p0y = a.y; l.p1x = b.x; l.p1y = b.y;
+    *dst = l;
+    bb[0] = fminf(bb[0], fminf(a.x, b.x)); bb[1] = fminf(bb[1], fminf(a.y, b.y));
+    bb[2] = fmaxf(bb[2], fmaxf(a.x, b.x)); bb[3] = fmaxf(bb[3], fmaxf(a.y, b.y));
+}
+__device__ inline void stroke_piece_emit(GGLine* lines, uint32_t main_ix, uint32_t lines_cap, uint32_t* bump_lines, uint32_t* bump_failed,
+                                         uint32_t path_ix, const StrokeVertex& a, const StrokeVertex& b, float hw, float* bb) {
     V2 e = vsub(b.p, a.p);
     float dl = vdot(vsub(b.l, a.l), e), dr = vdot(vsub(b.r, a.r), e);
     if ((dl > 0.0f && dr > 0.0f) || (e.x == 0.0f && e.y == 0.0f)) {
-        put_line<EMIT>(o, a.l, b.l);
-        put_line<EMIT>(o, b.r, a.r);
+        write_line(lines + main_ix, path_ix, a.l, b.l, bb);
+        write_line(lines + main_ix + 1, path_ix, b.r, a.r, bb);
         return;
     }
-    // An edge of the quad runs backwards: rectangle of the piece + a bevel on the outer side of each end,
-    // the inner side through the centre point.
     V2 n = stroke_normal(e, hw);
     V2 a0 = vadd(a.p, n), b0 = vsub(a.p, n), a1 = vadd(b.p, n), b1 = vsub(b.p, n);
-    if (vcross(a.n, n) > 0.0f) { put_line<EMIT>(o, a.l, a.p); put_line<EMIT>(o, a.p, a0); put_line<EMIT>(o, b0, a.r); }
-    else { put_line<EMIT>(o, a.l, a0); put_line<EMIT>(o, b0, a.p); put_line<EMIT>(o, a.p, a.r); }
-    put_line<EMIT>(o, a0, a1);
-    put_line<EMIT>(o, b1, b0);
-    if (vcross(n, b.n) > 0.0f) { put_line<EMIT>(o, a1, b.p); put_line<EMIT>(o, b.p, b.l); put_line<EMIT>(o, b.r, b1); }
-    else { put_line<EMIT>(o, a1, b.l); put_line<EMIT>(o, b.r, b.p); put_line<EMIT>(o, b.p, b1); }
+    V2 q[16];
+    int k = 0;
+#define GG_Q(u, v) do { if (!veq(u, v)) { q[k++] = u; q[k++] = v; } } while (0)
+    if (vcross(a.n, n) > 0.0f) { GG_Q(a.l, a.p); GG_Q(a.p, a0); GG_Q(b0, a.r); }
+    else { GG_Q(a.l, a0); GG_Q(b0, a.p); GG_Q(a.p, a.r); }
+    GG_Q(a0, a1);
+    GG_Q(b1, b0);
+    if (vcross(n, b.n) > 0.0f) { GG_Q(a1, b.p); GG_Q(b.p, b.l); GG_Q(b.r, b1); }
+    else { GG_Q(a1, b.l); GG_Q(b.r, b.p); GG_Q(b.p, b1); }
+#undef GG_Q
+    int nl = k / 2;
+    for (int i = 0; i < 2; i++) {
+        if (i < nl) write_line(lines + main_ix + i, path_ix, q[2 * i], q[2 * i + 1], bb);
+        else write_line(lines + main_ix + i, path_ix, a.p, a.p, bb);
+    }
+    if (nl > 2) {
+        uint32_t extra = (uint32_t)(nl - 2);
+        uint32_t slot = atomicAdd(bump_lines, extra);
+        if ((uint64_t)slot + extra > lines_cap) { atomicOr(bump_failed, GG_FAIL_LINES); return; }
+        for (int i = 2; i < nl; i++) write_line(lines + slot + (i - 2), path_ix, q[2 * i], q[2 * i + 1], bb);
+    }
 }
 
 // Join at p between the end of one segment (offset n0) and the start of the next (offset n1).
@@ -156,101 +178,17 @@ __device__ inline void stroke_cap(LineOut& o, V2 p, V2 nf, const StrokeStyle& st
     }
 }
 
-// Both sides of a cubic: the subdivision loop of flatten_cubic (flatten.go:60-184) with one offset vertex per
-// subdivision point. The line count of an Euler segment is raised by sqrt(1 + hw * max curvature) so the outer
-// parallel curve stays within the tolerance as well.
-template <bool EMIT>
-__device__ inline void stroke_cubic(LineOut& o, V2 p0, V2 p1, V2 p2, V2 p3, V2 n_start, V2 n_end, float hw) {
-    const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f, FLATTEN_TOL = 0.25f;
-    uint32_t t0u = 0;
-    float dt = 1.0f;
-    V2 last_p = p0;
-    V2 last_q = vsub(p1, p0);
-    if (vlen_sq(last_q) < DERIV_THRESH * DERIV_THRESH) {
-        V2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &last_q);
-    }
-    float last_t = 0.0f;
-    StrokeVertex v0 = stroke_vertex(p0, n_start);
-    for (;;) {
-        float t0 = (float)t0u * dt;
-        if (t0 == 1.0f) break;
-        float t1 = t0 + dt;
-        V2 this_p0 = last_p, this_q0 = last_q, this_p1, this_q1;
-        eval_cubic_and_deriv(p0, p1, p2, p3, t1, &this_p1, &this_q1);
-        if (vlen_sq(this_q1) < DERIV_THRESH * DERIV_THRESH) {
-            V2 new_p1, new_q1;
-            eval_cubic_and_deriv(p0, p1, p2, p3, t1 - DERIV_EPS, &new_p1, &new_q1);
-            this_q1 = new_q1;
-            if (t1 < 1.0f) { this_p1 = new_p1; t1 -= DERIV_EPS; }
-        }
-        float actual_dt = t1 - last_t;
-        CubicParams cp = cubic_params_from_points_derivs(this_p0, this_p1, this_q0, this_q1, actual_dt);
-        if (cp.err <= FLATTEN_TOL || dt <= SUBDIV_LIMIT) {
-            EulerParams ep = euler_params_from_angles(cp.th0, cp.th1);
-            float k0_minus_half_k1 = ep.k0 - 0.5f * ep.k1;
-            float k1 = ep.k1;
-            float scale_mul = 0.5f * (float)(1.41421356237309504880168872420969808 / 2.0) * sqrt32(cp.chord_len / (ep.ch * FLATTEN_TOL));
-            float k_abs = f_max(fabsf(k0_minus_half_k1), fabsf(k0_minus_half_k1 + k1));
-            float widen = sqrt32(1.0f + hw * k_abs * ep.ch / cp.chord_len);
-            float n_frac;
-            bool low_k1;
-            float a = 0, b = 0, integral = 0, int0 = 0;
-            if (fabsf(k1) < 1e-3f) {
-                float k = k0_minus_half_k1 + 0.5f * k1;
-                n_frac = sqrt32(fabsf(k));
-                low_k1 = true;
-            } else {
-                a = k1;
-                b = k0_minus_half_k1;
-                int0 = cube_signed_sqrt(b);
-                float int1 = cube_signed_sqrt(a + b);
-                integral = int1 - int0;
-                n_frac = (float)(2.0 / 3.0) * integral / a;
-                low_k1 = false;
-            }
-            float n = ceilf(n_frac * scale_mul * widen);
-            if (n < 1) n = 1;
-            if (n > 100) n = 100;
-            int n_int = (n != n) ? 0 : (int)n;
-            V2 chord = vsub(this_p1, this_p0);
-            float nscale = hw / cp.chord_len;
-            bool tiny = vlen_sq(chord) < 1e-12f;   // euler.go:44: no usable chord direction, keep the previous offset
-            for (int i = 0; i < n_int; i++) {
-                StrokeVertex v1;
-                if (i == n_int - 1 && t1 == 1.0f) {
-                    v1 = stroke_vertex(p3, n_end);
-                } else {
-                    float t = (float)(i + 1) / n;
-                    float s;
-                    if (low_k1) {
-                        s = t;
-                    } else {
-                        float c = (float)cbrt((double)(integral * t + int0));
-                        float inv = c * fabsf(c);
-                        s = (inv - b) / a;
-                    }
-                    V2 pc = euler_seg_eval(this_p0, this_p1, ep, s);
-                    V2 nn = v0.n;
-                    if (!tiny) {
-                        float th = (ep.k0 + 0.5f * ep.k1 * (s - 1.0f)) * s - ep.th0;   // euler.go:121-123
-                        float sx = sin32(th), sy = cos32(th);                           // euler.go:133-137: offset direction
-                        nn = mk((chord.x * sx - chord.y * sy) * nscale, (chord.x * sy + chord.y * sx) * nscale);
-                    }
-                    v1 = stroke_vertex(pc, nn);
-                }
-                stroke_piece<EMIT>(o, v0, v1, hw);
-                v0 = v1;
-            }
-            last_p = this_p1; last_q = this_q1; last_t = t1;
-            t0u++;
-            uint32_t shift = (uint32_t)(__ffs((int)t0u) - 1);
-            t0u >>= shift;
-            dt *= (float)(1u << shift);
-        } else {
-            if (t0u < 0xFFFFFFFFu / 2) t0u *= 2;
-            dt *= 0.5f;
-        }
-    }
-    // t == 1 is reached through an exact end point only if the last subdivision ended there; close the chain otherwise
-    if (!veq(v0.p, p3) || !veq(v0.n, n_end)) stroke_piece<EMIT>(o, v0, stroke_vertex(p3, n_end), hw);
+// Outline vertex at subdivision point j of an Euler segment: the point and the spiral's own normal there
+// (euler.go:121-137), scaled to the half width.
+__device__ inline StrokeVertex eseg_vertex(const GGESeg& r, int j, float hw, V2 n_end, V2 n_fallback) {
+    if ((r.flags & GG_ESEG_LAST) && j == (int)r.n - 1) return stroke_vertex(r.p1, n_end);
+    EulerParams ep; ep.th0 = r.th0; ep.k0 = r.k0; ep.k1 = r.k1; ep.ch = r.ch;
+    float s = eseg_param(r, j);
+    V2 pc = euler_seg_eval(r.p0, r.p1, ep, s);
+    V2 chord = vsub(r.p1, r.p0);
+    if (vlen_sq(chord) < 1e-12f) return stroke_vertex(pc, n_fallback);   // euler.go:44: no usable chord direction
+    float th = (ep.k0 + 0.5f * ep.k1 * (s - 1.0f)) * s - ep.th0;
+    float sx = sin32(th), sy = cos32(th);
+    float nscale = hw / r.chord_len;
+    return stroke_vertex(pc, mk((chord.x * sx - chord.y * sy) * nscale, (chord.x * sy + chord.y * sx) * nscale));
 }

@@ -480,7 +480,7 @@ static void sk_cubic(line_sink *lines, vec2 p0, vec2 p1, vec2 p2, vec2 p3, vec2 
                         sp = (inv - b) / a;
                     }
                     vec2 pc = es_eval_with_offset(this_p0, this_p1, &ep, sp, 0.0f);
-                    vec2 nn = va.n;
+                    vec2 nn = n_start;   /* no usable chord direction (euler.go:44): the curve's start offset */
                     if (!tiny) {
                         float th = ep_eval_th(&ep, sp);
                         float sx = sin32(th), sy = cos32(th);
@@ -501,7 +501,6 @@ static void sk_cubic(line_sink *lines, vec2 p0, vec2 p1, vec2 p2, vec2 p3, vec2 
             dt *= 0.5f;
         }
     }
-    if (!veq(va.p, p3) || !veq(va.n, n_end)) { stroke_vtx vb = sk_vtx(p3, n_end); sk_piece(lines, &va, &vb, hw); }
 }
 
 /* One segment's share of the outline. seg / next: 4 points in cubic form (kind 1: line from [0] to [3]); role 0 = a
