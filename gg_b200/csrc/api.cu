@@ -418,6 +418,8 @@ int ggcuda_push_clip(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, cons
     c->scene.begin_path(ID6, false);
     if (n_verbs) c->scene.add_verbs(verbs, n_verbs, coords, n_coords);
     c->scene.end_path();
+    std::vector<float> cf(coords, coords + (n_verbs ? n_coords : 0));
+    c->scene.set_next_clip_bounds(ID6, verbs, n_verbs, cf.data(), cf.size());
     c->scene.begin_clip(0x8003u, 1.0f, 0);
     c->uploaded = false;
     return 0;

@@ -49,7 +49,8 @@ uint32_t gg_blend_word(uint32_t m) {   // scene/encoding.go:17-48 -> (mix << 8) 
 void HostScene::clear(uint32_t w, uint32_t h) {
     width = w; height = h;
     tags.clear(); path_data.clear(); draw_tags.clear(); draw_data.clear(); styles.clear(); transforms.clear();
-    clip_aux.clear(); clip_stack.clear(); clip_kind.clear();
+    clip_aux.clear(); clip_stack.clear(); clip_kind.clear(); clip_bb.clear();
+    next_clip_bb[0] = next_clip_bb[1] = -3.0e38f; next_clip_bb[2] = next_clip_bb[3] = 3.0e38f;
     n_paths = n_clips = n_seg_tags = 0;
     have_transform = false; in_path = false; has_move = false;
 }
@@ -125,60 +126,122 @@ void HostScene::add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* 
     }
 }
 
+// Fill path straight from verb bytes + float coordinates: the hot loop of scene ingest. Tags and coordinates are
+// written through raw pointers into space reserved for the worst case (every MoveTo / Close / the path end may add a
+// closing LineTo); the rules are those of move_to / line_to / close / end_path above.
+void HostScene::fill_verbs(const float t[6], bool even_odd, const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords,
+                           const uint8_t* verb_map) {
+    begin_path(t, even_odd);
+    const size_t t0 = tags.size(), d0 = path_data.size();
+    tags.resize(t0 + 2 * n_verbs + 3);
+    path_data.resize(d0 + n_coords + 2 * (n_verbs + 2));
+    uint8_t* tp = tags.data() + t0;
+    float* dp = path_data.data() + d0;
+    bool have = false;
+    float sx = 0, sy = 0, cx = 0, cy = 0;
+    uint32_t nseg = 0;
+    size_t k = 0;
+#define GG_CLOSE_SUBPATH() do { if (have && (cx != sx || cy != sy)) { *tp++ = PT_LINETO; *dp++ = sx; *dp++ = sy; nseg++; } } while (0)
+    for (size_t i = 0; i < n_verbs; i++) {
+        switch (verb_map ? verb_map[verbs[i]] : verbs[i]) {
+        case GGCUDA_VERB_MOVE:
+            if (k + 2 > n_coords) { i = n_verbs; break; }
+            GG_CLOSE_SUBPATH();
+            *tp++ = PT_MOVETO; sx = cx = *dp++ = c[k]; sy = cy = *dp++ = c[k + 1]; k += 2; have = true;
+            break;
+        case GGCUDA_VERB_LINE:
+            if (k + 2 > n_coords) { i = n_verbs; break; }
+            if (have) { *tp++ = PT_LINETO; cx = *dp++ = c[k]; cy = *dp++ = c[k + 1]; nseg++; }
+            k += 2; break;
+        case GGCUDA_VERB_QUAD:
+            if (k + 4 > n_coords) { i = n_verbs; break; }
+            if (have) { *tp++ = PT_QUADTO; memcpy(dp, c + k, 16); dp += 4; cx = c[k + 2]; cy = c[k + 3]; nseg++; }
+            k += 4; break;
+        case GGCUDA_VERB_CUBIC:
+            if (k + 6 > n_coords) { i = n_verbs; break; }
+            if (have) { *tp++ = PT_CUBICTO; memcpy(dp, c + k, 24); dp += 6; cx = c[k + 4]; cy = c[k + 5]; nseg++; }
+            k += 6; break;
+        case GGCUDA_VERB_CLOSE:   // path_convert.go:86-92
+            GG_CLOSE_SUBPATH();
+            cx = sx; cy = sy;
+            break;
+        default: break;
+        }
+    }
+    GG_CLOSE_SUBPATH();
+#undef GG_CLOSE_SUBPATH
+    *tp++ = PT_PATH;
+    tags.resize((size_t)(tp - tags.data()));
+    path_data.resize((size_t)(dp - path_data.data()));
+    n_seg_tags += nseg;
+    n_paths++;
+    in_path = false; has_move = false;
+}
+
 // Centre line of a stroked path for the device-side expander. Per subpath: MoveTo, the segments (those whose points
 // all coincide are dropped, so every segment has a tangent), then a marker: a copy of the first segment flagged
 // PT_MARKER -- the last segment reads the tangent of its join from it when the subpath is closed; for an open
 // subpath a PT_MARKER_MOVE back to the first point precedes it and the marker segment draws the start cap.
-void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const StrokeStyleHost& st) {
+void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const StrokeStyleHost& st,
+                            const uint8_t* verb_map) {
     begin_path(t, false);
     float w = (float)st.width, ml = (float)st.miter_limit;
     if (!(w > 0.0f)) { end_path(); return; }
     uint32_t fl = STYLE_STROKE | ((uint32_t)(st.join & 3) << 2) | ((uint32_t)(st.cap & 3) << 4);
     uint32_t wb, mb; memcpy(&wb, &w, 4); memcpy(&mb, &ml, 4);
     styles[styles.size() - 3] = fl; styles[styles.size() - 2] = wb; styles[styles.size() - 1] = mb;
-    struct Seg { uint8_t tag; uint8_t n; float p[6]; };
-    static thread_local std::vector<Seg> segs;
-    segs.clear();
+    // worst case per verb: its own tag + (at a subpath end) closing line, marker MoveTo and marker copy
+    const size_t t0 = tags.size(), d0 = path_data.size();
+    tags.resize(t0 + 4 * n_verbs + 8);
+    path_data.resize(d0 + n_coords + 12 * (n_verbs + 2));
+    uint8_t* tp = tags.data() + t0;
+    float* dp = path_data.data() + d0;
     bool have = false, implicit = false;   // implicit: current point left behind by a Close, not set by a MoveTo
     float sx = 0, sy = 0, cx = 0, cy = 0;
+    uint8_t* sub_t = nullptr; float* sub_d = nullptr;   // where the open subpath's MoveTo was written
+    uint32_t nseg = 0, sub_seg = 0;
+    auto open_sub = [&]() { if (!sub_t) { sub_t = tp; sub_d = dp; *tp++ = PT_MOVETO; *dp++ = sx; *dp++ = sy; sub_seg = 0; } };
     auto flush = [&](bool closed) {
         if (!have) return;
         have = false;
-        if (segs.empty() && implicit) return;
-        if (closed && !segs.empty() && (cx != sx || cy != sy)) { Seg s{PT_LINETO, 2, {sx, sy}}; segs.push_back(s); }
-        if (segs.empty()) {   // a dot: round and square caps draw it (software.go strokes a zero-length subpath the same way)
-            if (st.cap == GGCUDA_CAP_BUTT) return;
-            Seg s{PT_LINETO, 2, {sx + 1.0f / 1024.0f, sy}}; segs.push_back(s);
+        if (!sub_t) sub_seg = 0;
+        if (sub_seg == 0 && implicit) { if (sub_t) { tp = sub_t; dp = sub_d; sub_t = nullptr; } return; }
+        if (closed && sub_seg && (cx != sx || cy != sy)) { *tp++ = PT_LINETO; *dp++ = sx; *dp++ = sy; sub_seg++; }
+        if (sub_seg == 0) {   // a dot: round and square caps draw it (software.go strokes a zero-length subpath the same way)
+            if (st.cap == GGCUDA_CAP_BUTT) { if (sub_t) { tp = sub_t; dp = sub_d; sub_t = nullptr; } return; }
+            open_sub();
+            *tp++ = PT_LINETO; *dp++ = sx + 1.0f / 1024.0f; *dp++ = sy; sub_seg++;
             closed = false;
         }
-        tags.push_back(PT_MOVETO); path_data.push_back(sx); path_data.push_back(sy);
-        for (const Seg& s : segs) { tags.push_back(s.tag); path_data.insert(path_data.end(), s.p, s.p + s.n); }
-        if (!closed) { tags.push_back(PT_MARKER_MOVE); path_data.push_back(sx); path_data.push_back(sy); }
-        tags.push_back((uint8_t)(segs[0].tag | PT_MARKER)); path_data.insert(path_data.end(), segs[0].p, segs[0].p + segs[0].n);
-        n_seg_tags += (uint32_t)segs.size() + 1;
-        segs.clear();
+        if (!closed) { *tp++ = PT_MARKER_MOVE; *dp++ = sx; *dp++ = sy; }
+        uint8_t first = sub_t[1];
+        uint32_t nf = 2u * (first & 3u);
+        *tp++ = (uint8_t)(first | PT_MARKER);
+        memcpy(dp, sub_d + 2, sizeof(float) * nf); dp += nf;
+        nseg += sub_seg + 1;
+        sub_t = nullptr; sub_seg = 0;
     };
     size_t k = 0;
     for (size_t i = 0; i < n_verbs; i++) {
-        switch (verbs[i]) {
+        switch (verb_map ? verb_map[verbs[i]] : verbs[i]) {
         case GGCUDA_VERB_MOVE:
             if (k + 2 > n_coords) { i = n_verbs; break; }
             flush(false);
             sx = cx = c[k]; sy = cy = c[k + 1]; k += 2; have = true; implicit = false; break;
         case GGCUDA_VERB_LINE:
             if (k + 2 > n_coords) { i = n_verbs; break; }
-            if (have && (c[k] != cx || c[k + 1] != cy)) { Seg s{PT_LINETO, 2, {c[k], c[k + 1]}}; segs.push_back(s); cx = c[k]; cy = c[k + 1]; }
+            if (have && (c[k] != cx || c[k + 1] != cy)) { open_sub(); *tp++ = PT_LINETO; cx = *dp++ = c[k]; cy = *dp++ = c[k + 1]; sub_seg++; }
             k += 2; break;
         case GGCUDA_VERB_QUAD:
             if (k + 4 > n_coords) { i = n_verbs; break; }
             if (have && (c[k] != cx || c[k + 1] != cy || c[k + 2] != cx || c[k + 3] != cy)) {
-                Seg s{PT_QUADTO, 4, {c[k], c[k + 1], c[k + 2], c[k + 3]}}; segs.push_back(s); cx = c[k + 2]; cy = c[k + 3];
+                open_sub(); *tp++ = PT_QUADTO; memcpy(dp, c + k, 16); dp += 4; cx = c[k + 2]; cy = c[k + 3]; sub_seg++;
             }
             k += 4; break;
         case GGCUDA_VERB_CUBIC:
             if (k + 6 > n_coords) { i = n_verbs; break; }
             if (have && (c[k] != cx || c[k + 1] != cy || c[k + 2] != cx || c[k + 3] != cy || c[k + 4] != cx || c[k + 5] != cy)) {
-                Seg s{PT_CUBICTO, 6, {c[k], c[k + 1], c[k + 2], c[k + 3], c[k + 4], c[k + 5]}}; segs.push_back(s); cx = c[k + 4]; cy = c[k + 5];
+                open_sub(); *tp++ = PT_CUBICTO; memcpy(dp, c + k, 24); dp += 6; cx = c[k + 4]; cy = c[k + 5]; sub_seg++;
             }
             k += 6; break;
         case GGCUDA_VERB_CLOSE:
@@ -188,6 +251,9 @@ void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_ver
         }
     }
     flush(false);
+    tags.resize((size_t)(tp - tags.data()));
+    path_data.resize((size_t)(dp - path_data.data()));
+    n_seg_tags += nseg;
     has_move = false;
     end_path();
 }
@@ -198,6 +264,22 @@ void HostScene::append_stroke(const StrokeSink& k) {
     path_data.insert(path_data.end(), k.data.begin(), k.data.end());
     n_seg_tags += k.n_seg;
     has_move = false;
+}
+
+void HostScene::set_next_clip_bounds(const float t[6], const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const uint8_t* verb_map) {
+    float bb[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
+    size_t k = 0;
+    for (size_t i = 0; i < n_verbs; i++) {
+        uint8_t v = verb_map ? verb_map[verbs[i]] : verbs[i];
+        size_t np = v == GGCUDA_VERB_MOVE || v == GGCUDA_VERB_LINE ? 1 : v == GGCUDA_VERB_QUAD ? 2 : v == GGCUDA_VERB_CUBIC ? 3 : 0;
+        if (k + 2 * np > n_coords) break;
+        for (size_t j = 0; j < np; j++, k += 2) {   // control points bound the curve
+            float x = t[0] * c[k] + t[1] * c[k + 1] + t[2], y = t[3] * c[k] + t[4] * c[k + 1] + t[5];
+            bb[0] = std::min(bb[0], x); bb[1] = std::min(bb[1], y); bb[2] = std::max(bb[2], x); bb[3] = std::max(bb[3], y);
+        }
+    }
+    if (!(bb[0] <= bb[2])) { bb[0] = bb[1] = bb[2] = bb[3] = 0; }   // empty clip path: nothing shows
+    memcpy(next_clip_bb, bb, sizeof bb);
 }
 
 void HostScene::draw_color(uint32_t rgba_premul) {
@@ -215,6 +297,15 @@ void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(-1);   // link patched by end_clip
     clip_stack.push_back(d); clip_kind.push_back(kind);
+    // device-space bounds of everything this clip can show: its own bounds (set_next_clip_bounds, else unbounded)
+    // inside its parent's
+    float bb[4] = {next_clip_bb[0], next_clip_bb[1], next_clip_bb[2], next_clip_bb[3]};
+    if (!clip_bb.empty()) {
+        const float* p = &clip_bb[clip_bb.size() - 4];
+        bb[0] = std::max(bb[0], p[0]); bb[1] = std::max(bb[1], p[1]); bb[2] = std::min(bb[2], p[2]); bb[3] = std::min(bb[3], p[3]);
+    }
+    clip_bb.insert(clip_bb.end(), bb, bb + 4);
+    next_clip_bb[0] = next_clip_bb[1] = -3.0e38f; next_clip_bb[2] = next_clip_bb[3] = 3.0e38f;
     n_clips++;
 }
 // Compose modes whose result differs from the backdrop where the layer is transparent:
@@ -230,7 +321,15 @@ void HostScene::begin_layer(uint32_t blend_word, float alpha) {
     // The six wiping compose modes act on the whole canvas, so they get an explicit full-canvas rectangle.
     begin_path(IDENTITY, false);
     if (blend_erases_backdrop(blend_word)) {
-        move_to(0, 0); line_to((float)width, 0); line_to((float)width, (float)height); line_to(0, (float)height); close();
+        // ... the canvas as far as an enclosing clip lets anything show: outside the bounds of that clip's path its
+        // coverage is zero and the layer is invisible, so the rectangle stops there (rounded outwards to whole pixels)
+        float x0 = 0, y0 = 0, x1 = (float)width, y1 = (float)height;
+        if (!clip_bb.empty()) {
+            const float* p = &clip_bb[clip_bb.size() - 4];
+            x0 = std::max(x0, floorf(p[0])); y0 = std::max(y0, floorf(p[1])); x1 = std::min(x1, ceilf(p[2])); y1 = std::min(y1, ceilf(p[3]));
+            if (!(x1 > x0) || !(y1 > y0)) { x1 = x0; y1 = y0; }
+        }
+        move_to(x0, y0); line_to(x1, y0); line_to(x1, y1); line_to(x0, y1); close();
     } else {
         blend_word |= 0xC0000000u;
     }
@@ -240,7 +339,7 @@ void HostScene::begin_layer(uint32_t blend_word, float alpha) {
 bool HostScene::end_clip(uint8_t kind) {
     if (clip_stack.empty() || clip_kind.back() != kind) return false;
     int32_t b = clip_stack.back();
-    clip_stack.pop_back(); clip_kind.pop_back();
+    clip_stack.pop_back(); clip_kind.pop_back(); clip_bb.resize(clip_bb.size() - 4);
     int32_t d = (int32_t)draw_tags.size();
     // EndClip: dummy path marker so that path index == draw index (scene_encode.go:258-268);
     // we also give it a style word so that styles[path_ix] is valid for every path.
@@ -391,22 +490,16 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
     size_t next_job = 0;
     size_t pi = 0, di = 0, ti = 0;
     float cur_t[6]; memcpy(cur_t, IDENTITY, sizeof cur_t);
-    std::vector<uint8_t> pv; std::vector<float> pc;   // current path: verbs + untransformed coords
+    // current path: a view into the input streams (tags [pt0, pt1), coordinates from pp0), consumed by the Fill / Stroke /
+    // BeginClip tag that follows it
+    size_t pt0 = 0, pt1 = 0, pp0 = 0;
     bool path_active = false;
-    auto emit_path = [&](bool even_odd) {
-        begin_path(cur_t, even_odd);
-        size_t k = 0;
-        for (uint8_t v : pv) {
-            switch (v) {
-            case GGCUDA_VERB_MOVE: move_to(pc[k], pc[k + 1]); k += 2; break;
-            case GGCUDA_VERB_LINE: line_to(pc[k], pc[k + 1]); k += 2; break;
-            case GGCUDA_VERB_QUAD: quad_to(pc[k], pc[k + 1], pc[k + 2], pc[k + 3]); k += 4; break;
-            case GGCUDA_VERB_CUBIC: cubic_to(pc[k], pc[k + 1], pc[k + 2], pc[k + 3], pc[k + 4], pc[k + 5]); k += 6; break;
-            case GGCUDA_VERB_CLOSE: close(); break;
-            }
-        }
-        end_path();
-    };
+    tags.reserve(tags.size() + 2 * n_tags + 64);
+    path_data.reserve(path_data.size() + 2 * n_pd + 64);
+    static const struct VerbMap { uint8_t m[256]; VerbMap() { memset(m, 0xff, sizeof m); m[ST_MOVE_TO] = GGCUDA_VERB_MOVE; m[ST_LINE_TO] = GGCUDA_VERB_LINE;
+                                  m[ST_QUAD_TO] = GGCUDA_VERB_QUAD; m[ST_CUBIC_TO] = GGCUDA_VERB_CUBIC; m[ST_CLOSE_PATH] = GGCUDA_VERB_CLOSE; } } verb_map;
+    bool pend_layer = false; uint32_t pend_blend = 0; float pend_alpha = 1.0f;
+    auto flush_layer = [&]() { if (pend_layer) { pend_layer = false; begin_layer(pend_blend, pend_alpha); } };
     for (size_t i = 0; i < n_tags; i++) {
         switch (tg[i]) {
         case ST_TRANSFORM:
@@ -414,38 +507,37 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             memcpy(cur_t, tr + 6 * ti, sizeof cur_t); ti++;
             break;
         case ST_SET_AA: di += 1; break;   // anti-aliasing is always on in this path
-        case ST_BEGIN_PATH: pv.clear(); pc.clear(); path_active = true; break;
+        case ST_BEGIN_PATH: pt0 = pt1 = i + 1; pp0 = pi; path_active = true; break;
         case ST_MOVE_TO: case ST_LINE_TO:
             if (pi + 2 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
-            if (path_active) { pv.push_back(tg[i] == ST_MOVE_TO ? GGCUDA_VERB_MOVE : GGCUDA_VERB_LINE); pc.insert(pc.end(), pd + pi, pd + pi + 2); }
-            pi += 2; break;
+            pi += 2; if (path_active) pt1 = i + 1; break;
         case ST_QUAD_TO:
             if (pi + 4 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
-            if (path_active) { pv.push_back(GGCUDA_VERB_QUAD); pc.insert(pc.end(), pd + pi, pd + pi + 4); }
-            pi += 4; break;
+            pi += 4; if (path_active) pt1 = i + 1; break;
         case ST_CUBIC_TO:
             if (pi + 6 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
-            if (path_active) { pv.push_back(GGCUDA_VERB_CUBIC); pc.insert(pc.end(), pd + pi, pd + pi + 6); }
-            pi += 6; break;
-        case ST_CLOSE_PATH: if (path_active) pv.push_back(GGCUDA_VERB_CLOSE); break;
+            pi += 6; if (path_active) pt1 = i + 1; break;
+        case ST_CLOSE_PATH: if (path_active) pt1 = i + 1; break;
         case ST_END_PATH: break;
         case ST_FILL: {
             if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
+            flush_layer();
             uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
-            if (path_active && !pv.empty()) { emit_path(style == 1); draw_color(brush_color(brushes, n_brushes, bix)); }
+            if (path_active && pt1 > pt0) { fill_verbs(cur_t, style == 1, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, verb_map.m); draw_color(brush_color(brushes, n_brushes, bix)); }
             path_active = false;
         } break;
         case ST_STROKE: {
             if (di + 5 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
+            flush_layer();
             uint32_t bix = dd[di];
-            if (path_active && !pv.empty()) {
+            if (path_active && pt1 > pt0) {
                 if (host_strokes) {
                     if (next_job < jobs.size()) { begin_path(IDENTITY, false); append_stroke(jobs[next_job++].out); end_path(); }
                     else { begin_path(IDENTITY, false); end_path(); }
                 } else {
                     float w, ml; memcpy(&w, dd + di + 1, 4); memcpy(&ml, dd + di + 2, 4);
                     StrokeStyleHost st = {(double)w, (double)ml, (int)dd[di + 3], (int)dd[di + 4]};
-                    stroke_path(cur_t, pv.data(), pv.size(), pc.data(), pc.size(), st);
+                    stroke_path(cur_t, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, st, verb_map.m);
                 }
                 draw_color(brush_color(brushes, n_brushes, bix));
             }
@@ -454,6 +546,7 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         } break;
         case ST_FILL_ROUND_RECT: {
             if (di + 2 > n_dd || pi + 6 > n_pd) { *msg = "encoding: round-rect underrun"; return GGCUDA_ERR_INVALID; }
+            flush_layer();
             uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
             const float* r = pd + pi; pi += 6;
             begin_path(cur_t, style == 1);
@@ -463,26 +556,43 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         } break;
         case ST_PUSH_LAYER: {
             if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
-            uint32_t blend = dd[di]; float alpha; memcpy(&alpha, dd + di + 1, 4); di += 2;
-            begin_layer(gg_blend_word(blend), alpha);
+            flush_layer();
+            uint32_t blend = dd[di]; memcpy(&pend_alpha, dd + di + 1, 4); di += 2;
+            pend_blend = gg_blend_word(blend); pend_layer = true;   // scene.PushLayer may follow up with its clip shape
         } break;
         case ST_POP_LAYER:
+            flush_layer();
             while (!clip_stack.empty() && clip_kind.back() == 0) end_clip(0);   // unbalanced clips inside the layer
-            end_clip(1);
+            if (!clip_stack.empty()) end_clip(clip_kind.back());
             break;
         case ST_BEGIN_CLIP:
-            if (path_active && !pv.empty()) emit_path(false);
-            else { begin_path(IDENTITY, false); end_path(); }   // empty clip path clips everything (renderer.go:747-753)
-            begin_clip(0x8003u, 1.0f, 0);
+            if (path_active && pt1 > pt0) {
+                fill_verbs(cur_t, false, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, verb_map.m);
+                set_next_clip_bounds(cur_t, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, verb_map.m);
+            } else { begin_path(IDENTITY, false); end_path(); next_clip_bb[0] = next_clip_bb[1] = next_clip_bb[2] = next_clip_bb[3] = 0; }   // empty clip path clips everything (renderer.go:747-753)
+            if (pend_layer) {
+                // PushLayer(blend, alpha, clip) (scene/scene.go:307-341: PushLayer, the clip path, BeginClip): ONE clip whose
+                // path is the clip shape and whose blend word / alpha are the layer's -- the layer composites where its clip
+                // lets it (also for the modes that wipe their backdrop), and fine keeps one stack level instead of two.
+                // Where nothing is drawn inside it may be dropped unless the mode wipes.
+                begin_clip(blend_erases_backdrop(pend_blend) ? pend_blend : (pend_blend | 0x80000000u), pend_alpha, 2);
+                pend_layer = false;
+            } else {
+                begin_clip(0x8003u, 1.0f, 0);
+            }
             path_active = false;
             break;
-        case ST_END_CLIP: end_clip(0); break;
+        case ST_END_CLIP:
+            if (!clip_kind.empty() && clip_kind.back() == 2) break;   // the clip of a merged layer: closed by its PopLayer
+            end_clip(0);
+            break;
         case ST_BRUSH: pi += 4; break;
         case ST_IMAGE: *msg = "encoding: TagImage is not supported by the CUDA path"; return GGCUDA_ERR_UNSUPPORTED;
         case ST_TEXT: *msg = "encoding: TagText must be resolved to outlines before the CUDA path"; return GGCUDA_ERR_UNSUPPORTED;
         default: *msg = "encoding: unknown tag"; return GGCUDA_ERR_INVALID;
         }
     }
+    flush_layer();
     close_open_clips();   // renderer.go:789-797
     if (getenv("GGCUDA_TRACE"))
         fprintf(stderr, "[ggcuda] ingest: total %.2f ms (%zu tags in, %zu packed tags out)\n",

@@ -32,7 +32,11 @@ struct HostScene {
     std::vector<float> transforms;
     std::vector<int32_t> clip_aux;       // 2 per draw: enclosing BeginClip (-1), link (End for Begin, Begin for End)
     std::vector<int32_t> clip_stack;     // open BeginClip draw indices
-    std::vector<uint8_t> clip_kind;      // 0 = clip, 1 = layer (parallel to clip_stack)
+    std::vector<uint8_t> clip_kind;      // 0 = clip, 1 = layer, 2 = layer merged with its clip shape (parallel to clip_stack)
+    std::vector<float> clip_bb;          // 4 per open clip: device-space bounds outside which it shows nothing
+    float next_clip_bb[4] = {-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f};   // bounds of the clip path just emitted (consumed by begin_clip)
+    void set_next_clip_bounds(const float transform[6], const uint8_t* verbs, size_t n_verbs, const float* coords, size_t n_coords,
+                              const uint8_t* verb_map = nullptr);
     uint32_t n_paths = 0, n_clips = 0, n_seg_tags = 0;
     float last_transform[6] = {0, 0, 0, 0, 0, 0};
     bool have_transform = false;
@@ -51,7 +55,7 @@ struct HostScene {
     // Stroked path: the centre line travels to the device (which expands it, stroke.cuh); coordinates in the space of
     // `transform`, width in device units (scene/renderer.go:655-713 strokes the transformed points with the raw width).
     void stroke_path(const float transform[6], const uint8_t* verbs, size_t n_verbs, const float* coords, size_t n_coords,
-                     const struct StrokeStyleHost& st);
+                     const struct StrokeStyleHost& st, const uint8_t* verb_map = nullptr);   // verb_map: verbs[] byte -> GGCUDA_VERB_*
     void move_to(float x, float y);
     void line_to(float x, float y);
     void quad_to(float cx, float cy, float x, float y);
@@ -59,6 +63,9 @@ struct HostScene {
     void close();
     void end_path();                      // auto-closes the open subpath, emits the Path marker
     void add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords);
+    // a whole fill path (begin_path .. end_path) from verb bytes + float coordinates, without per-point calls
+    void fill_verbs(const float transform[6], bool even_odd, const uint8_t* verbs, size_t n_verbs, const float* coords, size_t n_coords,
+                    const uint8_t* verb_map = nullptr);
 
     void append_stroke(const StrokeSink& k);               // outline loops of an expanded stroke into the current path
     void draw_color(uint32_t rgba_premul);                 // DrawTagColor for the path just ended

@@ -37,14 +37,12 @@ def config1(seed=1, w=512, h=512, n=1000):
     return sc.Encoding(), w, h
 
 
-def config3(seed=3, w=3840, h=2160, n=10000, layer_every=50, bands=1):
-    """10k random filled + stroked paths; every `layer_every` paths wrapped in a PushLayer cycling the 29
-    scene.BlendModes, 25 % of layers with a circular clip, nesting depth <= 3 plus one 6-deep case.
-    `bands` > 1 stacks that many 4K frames vertically (weak-scaling canvas for N GPUs)."""
+# scene.BlendModes whose layer changes the backdrop even where the layer is empty (Porter-Duff with Fb != 1 at Sa == 0)
+_WIPING = (S.BlendClear, S.BlendCopy, S.BlendSourceIn, S.BlendDestinationIn, S.BlendSourceOut, S.BlendDestinationAtop)
+
+
+def _config3_frame(sc, seed, w, h, n, layer_every, y_off, bound=None):
     rng = np.random.default_rng(seed)
-    H = h * bands
-    n = n * bands
-    sc = S.Scene()
     depth = 0
     mode = 0
     deep_done = False
@@ -54,15 +52,16 @@ def config3(seed=3, w=3840, h=2160, n=10000, layer_every=50, bands=1):
                 sc.PopLayer(); depth -= 1
             if not deep_done and i >= n // 2:
                 for _ in range(6):   # one 6-deep stack to exercise the blend-stack spill (> 4 levels)
-                    sc.PushLayer(mode % S.NUM_BLEND_MODES, float(rng.uniform(0.3, 1.0)), None); mode += 1; depth += 1
+                    sc.PushLayer(mode % S.NUM_BLEND_MODES, float(rng.uniform(0.3, 1.0)), bound if mode % S.NUM_BLEND_MODES in _WIPING else None)
+                    mode += 1; depth += 1
                 deep_done = True
             else:
-                clip = None
+                clip = bound if mode % S.NUM_BLEND_MODES in _WIPING else None
                 if rng.random() < 0.25:
-                    clip = S.circle_verbs_coords(rng.uniform(0, w), rng.uniform(0, H), rng.uniform(200, 900))
+                    clip = S.circle_verbs_coords(rng.uniform(0, w), y_off + rng.uniform(0, h), rng.uniform(200, 900))
                 sc.PushLayer(mode % S.NUM_BLEND_MODES, float(rng.uniform(0.3, 1.0)), clip); mode += 1; depth += 1
         box = rng.uniform(32, 512)
-        cx, cy = rng.uniform(0, w), rng.uniform(0, H)
+        cx, cy = rng.uniform(0, w), y_off + rng.uniform(0, h)
         shape = _blob(rng, cx, cy, box, int(rng.integers(3, 7)))
         col = (*rng.uniform(0, 1, 3), rng.uniform(0.2, 1.0))
         if rng.random() < 0.5:
@@ -73,7 +72,24 @@ def config3(seed=3, w=3840, h=2160, n=10000, layer_every=50, bands=1):
         if deep_done and depth > 3 and i % layer_every == layer_every - 1:
             while depth > 0:
                 sc.PopLayer(); depth -= 1
-    return sc.Encoding(), w, H
+    while depth > 0:
+        sc.PopLayer(); depth -= 1
+
+
+def config3(seed=3, w=3840, h=2160, n=10000, layer_every=50, bands=1):
+    """10k random filled + stroked paths; every `layer_every` paths wrapped in a PushLayer cycling the 29
+    scene.BlendModes, 25 % of layers with a circular clip, nesting depth <= 3 plus one 6-deep case.
+    `bands` > 1: the weak-scaling canvas for N GPUs -- that many such frames (seeds seed, seed + 1, ...) stacked
+    vertically, one per GPU band. A layer without a clip of its own whose blend mode wipes whatever the layer covers gets
+    its frame's rectangle as clip shape, so that it wipes its own frame, as it does on the single 4K canvas."""
+    sc = S.Scene()
+    if bands == 1:
+        _config3_frame(sc, seed, w, h, n, layer_every, 0.0)
+        return sc.Encoding(), w, h
+    for b in range(bands):
+        frame = S.rect_verbs_coords(0.0, float(b * h), float(w), float((b + 1) * h))
+        _config3_frame(sc, seed + b, w, h, n, layer_every, float(b * h), bound=frame)
+    return sc.Encoding(), w, h * bands
 
 
 def config5(seed=5, size=16384, n=1_000_000, min_box=16.0, max_box=256.0):

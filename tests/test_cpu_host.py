@@ -272,3 +272,28 @@ def test_stroke_against_distance_field():
         a = _stroke_alpha([0] + [3] * n + ([4] if closed else []), c, wd, 1, 1, w, h)
         assert not ((dist < wd / 2 - 0.9) & (a < 0.98)).any(), it
         assert not ((dist > wd / 2 + 0.9) & (a > 0.02)).any(), it
+
+
+def test_wiping_layer_stops_at_enclosing_clip():
+    """A layer whose blend mode wipes what it covers (Copy) is a full-canvas rectangle -- inside a clip, only as far as the
+    clip's bounds: same pixels (the clip hides everything beyond), far fewer tiles."""
+    from gg_b200 import scene as S
+    w, h = 128, 64
+    sc = S.Scene()
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0, 1, 0, 1), S.rect_verbs_coords(0, 0, w, h))
+    sc.PushClip(S.rect_verbs_coords(0, 0, 64, h))
+    sc.Fill(S.FillNonZero, S.IDENTITY, (1, 0, 0, 1), S.rect_verbs_coords(0, 0, w, h))    # red, inside the clip group
+    sc.PushLayer(S.BlendCopy, 1.0, None)
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0, 0, 1, 1), S.rect_verbs_coords(16, 16, 48, 48))
+    sc.PopLayer()
+    sc.PopClip()
+    c = _lib.Context(-1)
+    c.begin(w, h)
+    c.add_encoding(*sc.Encoding().streams())
+    words, lay = c.pack_host()
+    pd = words[lay["path_data_base"]:lay["draw_tag_base"]].view(np.float32)
+    assert list(pd[30:38]) == [0, 0, 64, 0, 64, 64, 0, 64]          # the layer's rectangle: the clip's bounds, not the canvas
+    img, _ = T.render_packed(words, lay, w, h)
+    assert (img[:, 64:] == (0, 255, 0, 255)).all()                  # beyond the clip: the green below, untouched
+    assert (img[16:48, 16:48] == (0, 0, 255, 255)).all()            # the layer's content
+    assert (img[:16, :64] == (0, 255, 0, 255)).all()                # Copy wiped the clip group's red: green shows through
