@@ -126,6 +126,99 @@ def config5(seed=5, size=16384, n=1_000_000, min_box=16.0, max_box=256.0):
     return S.ArrayEncoding(tags, pts.reshape(-1), draw.reshape(-1), np.zeros(0, np.float32), brushes), size, size
 
 
+# The in-tree icons of the reference's svg tests (svg/golden_test.go:23-27 folder, svg/stroke_hint_test.go:8-11 terminal):
+# (path data, fill RGBA or None, stroke RGBA or None, stroke width, cap, join), viewBox size
+ICON_FOLDER = ([("M0 0H20V20H0Z", (0x3C / 255, 0x3F / 255, 0x41 / 255, 1.0), None, 0, 0, 0),
+                ("M10.5199 5.57617L10.7285 5.75H11H17C17.6904 5.75 18.25 6.30964 18.25 7V15.1667C18.25 16.0671 17.553 16.75 16.75 16.75"
+                 "H3.25C2.44705 16.75 1.75 16.0671 1.75 15.1667V4.83333C1.75 3.93294 2.44705 3.25 3.25 3.25H7.63795C7.69643 3.25 7.75307 "
+                 "3.2705 7.798 3.30794L10.5199 5.57617Z", None, (0xCE / 255, 0xD0 / 255, 0xD6 / 255, 1.0), 1.0, 0, 0)], 20)
+ICON_TERMINAL = ([("M3 5L7 8L3 11", None, (0x6C / 255, 0x70 / 255, 0x7E / 255, 1.0), 1.0, 1, 1),
+                  ("M9 11H13", None, (0x6C / 255, 0x70 / 255, 0x7E / 255, 1.0), 1.0, 1, 0)], 16)
+
+
+def add_icon(sc, icon, x, y, scale):
+    """What svg.RenderToScene emits for one icon (svg/scene_renderer.go): fills and strokes under a scale + translate; the
+    stroke width is in user units, so it is scaled here (the scene strokes in device units, scene/renderer.go:655-713)."""
+    from .svgpath import parse_path
+    shapes, _ = icon
+    t = (scale, 0.0, x, 0.0, scale, y)
+    for d, fill, stroke, sw, cap, join in shapes:
+        shape = parse_path(d)
+        if fill is not None:
+            sc.Fill(S.FillNonZero, t, fill, shape)
+        if stroke is not None:
+            sc.Stroke(dict(width=float(sw * scale), miter_limit=4.0, cap=cap, join=join), t, stroke, shape)
+
+
+def config2(w=1920, h=1080, cell=16, seed=2):
+    """BASELINE configs[1] stand-in (the named SVG files do not exist in the reference and its brushes
+    are solid): the two in-tree test icons tiled over 1920x1080 at 16-px cells through the RenderToScene shape of calls,
+    every row of icons inside a group-opacity layer. ~8 000 icons, ~24 000 fill + stroke paths."""
+    rng = np.random.default_rng(seed)
+    sc = S.Scene()
+    for row in range(h // cell + 1):
+        sc.PushLayer(S.BlendNormal, float(rng.uniform(0.6, 1.0)), None)
+        for col in range(w // cell):
+            icon = ICON_FOLDER if (row + col) % 2 == 0 else ICON_TERMINAL
+            add_icon(sc, icon, float(col * cell), float(row * cell), cell / icon[1])
+        sc.PopLayer()
+    return sc.Encoding(), w, h
+
+
+def config4(glyphs, w=3840, h=2160, n=50000, seed=4):
+    """BASELINE configs[3]: a text-heavy 4K scene of `n` glyph outlines as paths (the reference resolves TagText to
+    outlines before the GPU path; here they come pre-extracted, tests/golden/make_glyph_outlines.py): rows of printable
+    ASCII in the Go Regular face at 14-48 px, quads, each glyph under its own scale + flip + translate transform;
+    NonZero fills, with 2 000 EvenOdd fills and 2 000 one-pixel stroked outlines mixed in."""
+    rng = np.random.default_rng(seed)
+    upem = float(glyphs["units_per_em"])
+    names = sorted(glyphs["glyphs"])
+    tmpl = {}
+    for ch in names:
+        verbs, coords = [], []
+        for contour in glyphs["glyphs"][ch]["contours"]:
+            for seg in contour:
+                if seg[0] == "M":
+                    verbs.append(S.TagMoveTo); coords += seg[1:]
+                elif seg[0] == "L":
+                    verbs.append(S.TagLineTo); coords += seg[1:]
+                else:
+                    verbs.append(S.TagQuadTo); coords += seg[1:]
+            verbs.append(S.TagClosePath)
+        tmpl[ch] = (np.array([S.TagTransform, S.TagBeginPath] + verbs + [S.TagEndPath], np.uint8), np.array(coords, np.float32),
+                    glyphs["glyphs"][ch]["advance"])
+    tags, pdata, ddata, trs, brushes = [], [], [], [], []
+    x, y, size = 8.0, 40.0, float(rng.uniform(14, 48))
+    special = rng.permutation(n)
+    kind = np.zeros(n, np.uint8)
+    kind[special[:2000]] = 1      # even-odd
+    kind[special[2000:4000]] = 2  # stroked outline
+    for i in range(n):
+        ch = names[int(rng.integers(0, len(names)))]
+        tg, pc, adv = tmpl[ch]
+        s = size / upem
+        if x + adv * s > w - 8:
+            x = 8.0
+            y += size * 1.2
+            size = float(rng.uniform(14, 48))
+            if y > h - 8:
+                y = 40.0
+            s = size / upem
+        tags.append(tg)
+        pdata.append(pc)
+        trs.append((s, 0.0, x, 0.0, -s, y))
+        if kind[i] == 2:
+            tags.append(np.array([S.TagStroke], np.uint8))
+            ddata += [len(brushes), S._f32bits(1.0), S._f32bits(4.0), 0, 0]
+        else:
+            tags.append(np.array([S.TagFill], np.uint8))
+            ddata += [len(brushes), int(kind[i])]
+        brushes.append((*rng.uniform(0, 0.6, 3), 1.0))
+        x += adv * s
+    return S.ArrayEncoding(np.concatenate(tags), np.concatenate(pdata), np.array(ddata, np.uint32), np.array(trs, np.float32),
+                           np.array(brushes, np.float64)), w, h
+
+
 WORKLOADS = {
     "config1_512_1k_fills": config1,
     "config3_4k_10k_paths_blend_layers_clips": config3,

@@ -238,3 +238,66 @@ def random_scene(seed, w, h, n, clips=False, quads=True, max_size=96.0):
         elems.append(dict(type="end_clip"))
         depth -= 1
     return elems
+
+
+def compare_stages_fast(ctx, oc, w, h):
+    """compare_stages for full-size scenes (10^4..10^6 paths): the same bit-exact checks on the packed-scene oracle,
+    vectorised -- lines as a multiset, path bboxes, tile backdrops / occupancy / segment starts, segments as per-tile
+    multisets, PTCL word for word."""
+    lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+    words = ctx.debug_read(G.BUF_SCENE, np.uint32)
+    rep = {}
+    # a6
+    gl = ctx.debug_read(G.BUF_LINES, G.LINE)
+    ol = T.flatten_packed(words, lay).astype(G.LINE)
+
+    def canon(a):
+        return sorted_rows(a[(a["p0"] != a["p1"]).any(axis=1)])
+    ga, oa = canon(gl), canon(ol)
+    assert len(ga) == len(oa), f"{len(ga)} non-degenerate lines, oracle {len(oa)}"
+    assert ga.tobytes() == oa.tobytes(), "flattened / stroked lines differ"
+    rep["lines"] = len(ga)
+    # a7
+    gp = ctx.debug_read(G.BUF_PATHS, G.PATH)
+    assert len(gp) == len(oc.paths)
+    ob, gb = oc.paths["bbox"].astype(np.int64), gp["bbox"].astype(np.int64)
+    live = ((ob[:, 2] - ob[:, 0]) > 0) & ((ob[:, 3] - ob[:, 1]) > 0)
+    assert (ob[live] == gb[live]).all(), "path bboxes differ"
+    assert (gp["tiles"][live] == oc.paths["tiles"][live]).all(), "path tile offsets differ"
+    # a8-a10
+    gt = ctx.debug_read(G.BUF_TILES, G.TILE)
+    gs = ctx.debug_read(G.BUF_SEG_START, np.uint32)
+    assert len(gt) == len(oc.tiles), (len(gt), len(oc.tiles))
+    assert (gt["backdrop"] == oc.tiles["backdrop"]).all(), "backdrop mismatch"
+    has = oc.tiles["seg_count_or_ix"] != 0
+    assert ((gt["seg_count"] != 0) == has).all(), "tile occupancy mismatch"
+    cnt = np.where(live, (ob[:, 2] - ob[:, 0]) * (ob[:, 3] - ob[:, 1]), 0)
+    base_per_tile = np.repeat(oc.path_seg_base.astype(np.uint32), cnt)
+    t0 = np.repeat(oc.paths["tiles"].astype(np.int64), cnt)
+    assert (np.diff(t0) >= 0).all() and len(base_per_tile) == len(oc.tiles)
+    o_start = (~oc.tiles["seg_count_or_ix"]).astype(np.uint32) + base_per_tile
+    assert (gs[has] == o_start[has]).all(), "segment start mismatch"
+    rep["tiles"] = len(gt)
+    # a11: segments sorted inside their tile ranges
+    gseg = ctx.debug_read(G.BUF_SEGMENTS, G.SEGMENT)
+    assert len(gseg) == len(oc.segments), (len(gseg), len(oc.segments))
+    tile_of = np.zeros(len(gseg), np.int64)
+    idx = np.nonzero(has)[0]
+    tile_of[gs[idx]] = 1
+    tile_of = np.cumsum(tile_of)     # ranges are contiguous and ordered by start
+
+    def by_tile(a):
+        v = np.ascontiguousarray(a).view(np.uint8).reshape(len(a), -1)
+        order = np.lexsort(tuple(v.T[::-1]) + (tile_of,))
+        return a[order]
+    assert by_tile(gseg).tobytes() == by_tile(oc.segments.astype(G.SEGMENT)).tobytes(), "segments differ"
+    rep["segments"] = len(gseg)
+    # a12
+    poff = ctx.debug_read(G.BUF_PTCL_OFF, np.uint32).astype(np.int64)
+    pw = ctx.debug_read(G.BUF_PTCL, np.uint32)
+    ng = oc.wt * oc.ht
+    olen = np.diff(oc.ptcl_offsets.astype(np.int64))
+    take = np.repeat(poff[:ng], olen) + (np.arange(int(olen.sum())) - np.repeat(oc.ptcl_offsets[:ng].astype(np.int64), olen))
+    assert (pw[take] == oc.ptcl_words).all(), "PTCL differs"
+    rep["ptcl_words"] = int(olen.sum())
+    return rep

@@ -297,3 +297,52 @@ def test_wiping_layer_stops_at_enclosing_clip():
     assert (img[:, 64:] == (0, 255, 0, 255)).all()                  # beyond the clip: the green below, untouched
     assert (img[16:48, 16:48] == (0, 0, 255, 255)).all()            # the layer's content
     assert (img[:16, :64] == (0, 255, 0, 255)).all()                # Copy wiped the clip group's red: green shows through
+
+
+def test_svg_path_parser():
+    from gg_b200.svgpath import parse_path
+    v, c = parse_path("M3 5L7 8L3 11")
+    assert v == [S.MOVE, S.LINE, S.LINE] and c == [3, 5, 7, 8, 3, 11]
+    v, c = parse_path("m1 1h2v3l-1-1c1 0 2 1 2 2s0 1-1 1q1 1 2 0t2 0z")
+    assert v == [S.MOVE, S.LINE, S.LINE, S.LINE, S.CUBIC, S.CUBIC, S.QUAD, S.QUAD, S.CLOSE]
+    assert c[:8] == [1, 1, 3, 1, 3, 4, 2, 3]
+    assert c[8:14] == [3, 3, 4, 4, 4, 5] and c[14:20] == [4, 6, 4, 6, 3, 6]      # S reflects the previous second control point
+    assert c[20:24] == [4, 7, 5, 6] and c[24:28] == [6, 5, 7, 6]                 # T reflects the previous control point
+    v, c = parse_path("M10.5199 5.57617L10.7285 5.75H11H17C17.6904 5.75 18.25 6.30964 18.25 7V15.1667Z")
+    assert v == [S.MOVE, S.LINE, S.LINE, S.LINE, S.CUBIC, S.LINE, S.CLOSE] and c[4:8] == [11, 5.75, 17, 5.75]
+    with pytest.raises(NotImplementedError):
+        parse_path("M0 0A5 5 0 0 1 10 10")
+
+
+def test_stroke_against_gg_folder_golden():
+    """svg/golden_test.go:21-47: gg's CPU renderer reproduces Skia on this stroke-only icon (diff == 0 asserted there), so
+    the golden IS gg's CPU output. Exact-area coverage of our stroke outline against it: straight edges identical, mean
+    |d| ~ 1.3/255; the few pixels further apart sit on the rounded corners (AAA quantises coverage, gg hints strokes)."""
+    from PIL import Image
+    sc = S.Scene()
+    scenes.add_icon(sc, scenes.ICON_FOLDER, 0.0, 0.0, 1.0)
+    c = _lib.Context(-1)
+    c.begin(20, 20)
+    c.add_encoding(*sc.Encoding().streams())
+    words, lay = c.pack_host()
+    img, _ = T.render_packed(words, lay, 20, 20)
+    g = np.array(Image.open(os.path.join(os.path.dirname(__file__), "golden", "svg", "folder_stroke_20x20.png")).convert("RGBA"))
+    d = np.abs(img.astype(int) - g.astype(int))
+    assert d.mean() <= 1.5 and (d.max(-1) > 16).mean() <= 0.05 and (d.max(-1) <= 2).mean() >= 0.85, (d.mean(), d.max())
+
+
+def test_glyph_fixture_and_text_scene():
+    """The committed glyph outlines (Go Regular, printable ASCII) and the configs[3] generator built on them."""
+    import json
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fixtures", "goregular_ascii.json")))
+    assert g["units_per_em"] == 2048 and len(g["glyphs"]) == 94
+    assert len(g["glyphs"]["O"]["contours"]) == 2 and len(g["glyphs"]["i"]["contours"]) == 2 and len(g["glyphs"]["B"]["contours"]) == 3
+    enc, w, h = scenes.config4(g, n=400, w=640, h=480)
+    c = _lib.Context(-1)
+    c.begin(w, h)
+    c.add_encoding(*enc.streams())
+    words, lay = c.pack_host()
+    assert lay["n_draws"] == 400
+    img, _ = T.render_packed(words, lay, w, h, (255, 255, 255, 255))
+    ink = (img[..., :3].sum(-1) < 3 * 255).mean()
+    assert 0.05 < ink < 0.6        # text, not blobs: a plausible share of inked pixels

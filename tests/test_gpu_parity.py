@@ -345,3 +345,78 @@ def test_strokes_device_vs_host_stroker(ctx):
         hc.close()
     d = np.abs(a.astype(np.int32) - b.astype(np.int32))
     assert d.mean() < 0.02 and (d > 8).mean() < 1e-3, (d.max(), d.mean())   # round joins / caps are tessellated differently
+
+
+# ---- BASELINE.json's configurations at their full sizes ----
+def _full_size(ctx, enc, w, h, bg=(0, 0, 0, 0), threads=None):
+    import os
+    out = U.gpu_encoding(ctx, enc, w, h, bg)
+    oc = U.oracle_from_ctx(ctx, w, h)
+    rep = U.compare_stages_fast(ctx, oc, w, h)
+    from oracle import twin as T
+    ref, _ = T.render_packed(ctx.debug_read(G.BUF_SCENE, np.uint32), ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0], w, h, bg, threads or os.cpu_count())
+    d = np.abs(out.astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() <= 0.002, (d.max(), (d.max(axis=-1) > 0).mean())
+    return out, rep
+
+
+def test_config2_svg_icons_1080p(ctx):
+    """configs[1] stand-in: ~8 000 SVG icons (fills + round / miter strokes under scale transforms, group opacity)."""
+    from gg_b200 import scenes
+    enc, w, h = scenes.config2()
+    _full_size(ctx, enc, w, h, bg=(255, 255, 255, 255))
+
+
+def test_config3_4k_full_size(ctx):
+    """configs[2], the benchmark scene itself: 3840x2160, 10 000 filled + stroked paths, 29 blend modes, layers, clips --
+    every integer stage bit-exact against the oracle, pixels within 1/255."""
+    from gg_b200 import scenes
+    enc, w, h = scenes.config3()
+    _, rep = _full_size(ctx, enc, w, h)
+    assert rep["lines"] > 1_000_000 and rep["segments"] > 2_000_000
+
+
+def test_config4_glyph_outlines_4k(ctx):
+    """configs[3]: 50 000 glyph outlines (quads) under per-glyph transforms, NonZero / EvenOdd fills and stroked outlines."""
+    import json, os
+    from gg_b200 import scenes
+    glyphs = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fixtures", "goregular_ascii.json")))
+    enc, w, h = scenes.config4(glyphs)
+    _full_size(ctx, enc, w, h, bg=(255, 255, 255, 255))
+
+
+def test_config5_16k_one_million_paths(ctx):
+    """configs[4]: 16384x16384, 1 000 000 paths. Too large for the oracle as a whole, so: (a) the oracle renders the
+    top-left 1024x1024 of the same encoding (a smaller canvas only clips) and the CUDA frame must match it there;
+    (b) eight bands rendered one after the other are the full frame; (c) a second render is the same frame."""
+    from gg_b200 import scenes
+    from oracle import twin as T
+    import os
+    enc, w, h = scenes.config5()
+    c5 = G.Context(0)
+    try:
+        full = U.gpu_encoding(c5, enc, w, h)
+        st = c5.stats()
+        assert st["n_draws"] == 1_000_000 and st["n_lines"] > 10_000_000
+        again = np.zeros_like(full)
+        c5.flush(again, flags=G.KEEP_SCENE)
+        d = np.abs(full.astype(np.int16) - again.astype(np.int16))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4          # segment order inside a tile varies between runs
+        parts = np.zeros_like(full)
+        ht = h // 16
+        for b in range(8):
+            c5.set_band(b * ht // 8, (b + 1) * ht // 8)
+            c5.flush(parts, flags=G.KEEP_SCENE)
+        d = np.abs(full.astype(np.int16) - parts.astype(np.int16))
+        assert d.max() <= 1 and (d > 0).mean() < 1e-4
+    finally:
+        c5.close()
+    crop = 1024
+    hc = G.Context(-1)
+    hc.begin(crop, crop)
+    hc.add_encoding(*enc.streams())
+    words, lay = hc.pack_host()
+    hc.close()
+    ref, _ = T.render_packed(words, lay, crop, crop, (0, 0, 0, 0), os.cpu_count())
+    d = np.abs(full[:crop, :crop].astype(np.int32) - ref.astype(np.int32))
+    assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() <= 0.002, (d.max(), (d.max(axis=-1) > 0).mean())
