@@ -769,8 +769,8 @@ __global__ void __launch_bounds__(256) path_tiling_kernel(GGConfig cfg, const GG
 // shared memory so commands come out in scene order; the clip state machine of the
 // reference (clipDepth / clipZeroDepth) collapses to a single "innermost emitted clip"
 // register because a draw is live in a tile iff every enclosing clip emitted there.
-#define COARSE_WARPS 8
-#define COARSE_CAP 1024   // hits per tile sorted in shared memory; longer lists are sorted in place by lane 0
+#define COARSE_WARPS 4
+#define COARSE_CAP 1024   // hits per tile handled in shared memory; longer lists are sorted in place by lane 0 and replayed sequentially
 
 __device__ inline void heap_sort_global(uint32_t* a, uint32_t n) {
     for (uint32_t start = n / 2; start-- > 0;) {
@@ -784,49 +784,14 @@ __device__ inline void heap_sort_global(uint32_t* a, uint32_t n) {
     }
 }
 
-__global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg, const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
-                                                                   const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
-                                                                   const GGDrawMonoid* __restrict__ dm,
-                                                                   const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ hit_cnt,
-                                                                   uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len, uint32_t* ptcl,
-                                                                   uint32_t* spill_off, uint32_t* restart_pt, GGBump* bump) {
-    __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
-    if (bump->failed) return;
-    const bool overflow = bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap;
-    if (overflow) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, (bump->hits > cfg.hits_cap ? GG_FAIL_HITS : 0u) | (bump->ptcl_words > cfg.ptcl_cap ? GG_FAIL_PTCL : 0u)); return; }
-    uint32_t* sb = sort_buf[warp];
-    for (uint32_t T = blockIdx.x * COARSE_WARPS + warp; T < n_tiles; T += gridDim.x * COARSE_WARPS) {
-        const uint32_t n = hit_cnt[T];
-        uint32_t* list = hits + hit_off[T];
-        uint32_t pos = ptcl_off[T];
-        if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
-        pos += 1;
-        if (n == 0) { if (lane == 0) { ptcl[pos] = GG_CMD_END; ptcl_len[T] = 2; restart_pt[2 * T] = 0; restart_pt[2 * T + 1] = 0; } continue; }
-        uint32_t* sorted;
-        if (n <= COARSE_CAP) {
-            uint32_t np2 = 32; while (np2 < n) np2 <<= 1;
-            for (uint32_t i = lane; i < np2; i += 32) sb[i] = i < n ? list[i] : 0xffffffffu;
-            __syncwarp();
-            for (uint32_t k = 2; k <= np2; k <<= 1)
-                for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-                    for (uint32_t i = lane; i < np2; i += 32) {
-                        uint32_t ixj = i ^ j;
-                        if (ixj > i) {
-                            uint32_t a = sb[i], b = sb[ixj];
-                            bool up = (i & k) == 0;
-                            if ((a > b) == up) { sb[i] = b; sb[ixj] = a; }
-                        }
-                    }
-                    __syncwarp();
-                }
-            sorted = sb;
-        } else {
-            if (lane == 0) heap_sort_global(list, n);
-            __syncwarp();
-            sorted = list;
-        }
+// Sequential form of the clip state machine (coarse.go:440-625 with lazy layers), one warp, hits in `sorted`:
+// used for tiles with more than COARSE_CAP hits. The shared-memory path below computes the same PTCL in parallel.
+__device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_t T, uint32_t n, const uint32_t* sorted, uint32_t pos,
+                                                    const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
+                                                    const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
+                                                    const GGDrawMonoid* __restrict__ dm, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len,
+                                                    uint32_t* ptcl, uint32_t* spill_off, uint32_t* restart_pt, GGBump* bump) {
+    const uint32_t lane = threadIdx.x & 31;
         const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
         // Layers whose blend word carries GG_BLEND_ELIDE_EMPTY are opened lazily: their BeginClip is only
         // written (just before the first command they enclose in this tile) once something is drawn inside;
@@ -953,6 +918,233 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                 if (so + lv > cfg.spill_cap) atomicOr(&bump->failed, GG_FAIL_SPILL); else spill_off[T] = so;
             }
         }
+}
+
+// Per-hit state byte of the parallel path
+#define CH_TAG 3u        // 0 colour, 1 BeginClip, 2 EndClip
+#define CH_ELIDE 4u      // BeginClip that may be dropped where nothing is drawn inside (GG_BLEND_ELIDE_EMPTY)
+#define CH_VAL 8u        // colour: drawn; BeginClip: entered; EndClip: its BeginClip was entered
+#define CH_NE 16u        // BeginClip: something inside it is written to this tile's PTCL
+#define CH_NONE 0xffffu  // lpos: no enclosing clip
+#define CH_MISSING 0xfffeu   // lpos: the enclosing clip has no hit in this tile (zero coverage here): the hit is culled
+
+// One warp per tile. The tile's hits (draw indices scattered by tile_rows<1>) are sorted in shared memory so that
+// they are in scene order, then everything the reference's sequential clip state machine decides
+// (coarse.go:440-625: clipDepth / clipZeroDepth / blendDepth) is computed in parallel from one fact: a hit takes part
+// iff its enclosing BeginClip has a hit in this tile and takes part itself. `lpos` links every hit to the position
+// of that BeginClip (an EndClip: to its own BeginClip), liveness is a few rounds of pointer chasing over those links,
+// "this lazily opened layer encloses something" an upward marking, PTCL offsets a warp scan. The first version
+// replayed the state machine hit by hit with seven shuffles per hit: 224 of the kernel's 442 M warp instructions.
+__global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg, const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
+                                                                   const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
+                                                                   const GGDrawMonoid* __restrict__ dm,
+                                                                   const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ hit_cnt,
+                                                                   uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len, uint32_t* ptcl,
+                                                                   uint32_t* spill_off, uint32_t* restart_pt, GGBump* bump) {
+    __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
+    __shared__ uint32_t tmp_buf[COARSE_WARPS][COARSE_CAP];
+    __shared__ uint32_t hist_buf[COARSE_WARPS][256];
+    __shared__ uint16_t lpos_buf[COARSE_WARPS][COARSE_CAP];
+    __shared__ uint8_t st_buf[COARSE_WARPS][COARSE_CAP];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
+    if (bump->failed) return;
+    const bool overflow = bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap;
+    if (overflow) { if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&bump->failed, (bump->hits > cfg.hits_cap ? GG_FAIL_HITS : 0u) | (bump->ptcl_words > cfg.ptcl_cap ? GG_FAIL_PTCL : 0u)); return; }
+    uint32_t* sb = sort_buf[warp];
+    uint32_t* tmp = tmp_buf[warp];
+    uint32_t* hist = hist_buf[warp];
+    const uint32_t key_bits = 32u - (uint32_t)__clz((int)max(cfg.n_draws, 2u) - 1);   // draw indices are < n_draws
+    uint16_t* lpos = lpos_buf[warp];
+    uint8_t* st = st_buf[warp];
+    for (uint32_t T = blockIdx.x * COARSE_WARPS + warp; T < n_tiles; T += gridDim.x * COARSE_WARPS) {
+        const uint32_t n = hit_cnt[T];
+        uint32_t* list = hits + hit_off[T];
+        uint32_t pos = ptcl_off[T];
+        if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
+        pos += 1;
+        if (n == 0) { if (lane == 0) { ptcl[pos] = GG_CMD_END; ptcl_len[T] = 2; restart_pt[2 * T] = 0; restart_pt[2 * T + 1] = 0; } continue; }
+        if (n > COARSE_CAP) {
+            if (lane == 0) heap_sort_global(list, n);
+            __syncwarp();
+            coarse_tile_sequential(cfg, T, n, list, pos, paths, tiles, seg_start, recs, dm, ptcl_off, ptcl_len, ptcl, spill_off, restart_pt, bump);
+            __syncwarp();
+            continue;
+        }
+        // ---- sort: stable LSD radix sort on the draw index, 8 bits per pass (2 passes up to 65 536 draws). Per pass a
+        //      256-bin histogram (shared-memory atomics), an exclusive scan (8 bins per lane) and a stable scatter that
+        //      ranks equal digits inside each group of 32 keys with match_any. The bitonic network this replaces cost
+        //      ~36-45 passes over the padded list: most of the kernel's instructions (ncu, r1b).
+        uint32_t* src = sb;
+        uint32_t* dstb = tmp;
+        for (uint32_t i = lane; i < n; i += 32) src[i] = list[i];
+        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) hist[lane * 8 + k] = 0;
+            __syncwarp();
+            for (uint32_t i = lane; i < n; i += 32) atomicAdd(&hist[(src[i] >> shift) & 255u], 1u);
+            __syncwarp();
+            uint32_t loc[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) { loc[k] = sum; sum += hist[lane * 8 + k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int dl = 1; dl < 32; dl <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, dl); if ((int)lane >= dl) incl += o; }
+            const uint32_t excl = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; k++) hist[lane * 8 + k] = excl + loc[k];
+            __syncwarp();
+            for (uint32_t base = 0; base < n; base += 32) {
+                const uint32_t i = base + lane;
+                const bool valid = i < n;
+                const uint32_t key = valid ? src[i] : 0u;
+                const uint32_t digit = valid ? ((key >> shift) & 255u) : (256u + lane);
+                const uint32_t peers = __match_any_sync(0xffffffffu, digit);
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                uint32_t at = 0;
+                if (valid) at = hist[digit] + rank;
+                __syncwarp();
+                if (valid) {
+                    dstb[at] = key;
+                    if (rank + 1 == (uint32_t)__popc(peers)) hist[digit] = at + 1;   // the last of the group moves the bin on
+                }
+                __syncwarp();
+            }
+            uint32_t* sw = src; src = dstb; dstb = sw;
+        }
+        if (src != sb) { for (uint32_t i = lane; i < n; i += 32) sb[i] = src[i]; }
+        __syncwarp();
+        // ---- A: classify every hit, link it to the hit of its enclosing BeginClip
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t d = sb[i];
+            const bool dup = i > 0 && sb[i - 1] == d;   // implicit-layer hits arrive once per enclosed hit: keep the first
+            const GGDrawRec r = recs[d];
+            uint32_t s8 = r.tag == GG_DRAWTAG_COLOR ? 0u : (r.tag == GG_DRAWTAG_BEGIN_CLIP ? 1u : 2u);
+            if (s8 == 1u && (r.b & GG_BLEND_ELIDE_EMPTY)) s8 |= CH_ELIDE;
+            uint32_t lp = CH_NONE;
+            if (r.parent >= 0) {
+                const uint32_t key = (uint32_t)r.parent;
+                uint32_t lo = 0, hi = n;   // lower bound
+                while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sb[mid] < key) lo = mid + 1; else hi = mid; }
+                lp = (lo < n && sb[lo] == key) ? lo : CH_MISSING;
+            }
+            if (!dup && lp != CH_MISSING) s8 |= CH_VAL;
+            st[i] = (uint8_t)s8;
+            lpos[i] = (uint16_t)lp;
+        }
+        __syncwarp();
+        // ---- B: a hit takes part iff its link does (chains are as long as clips nest: a few rounds)
+        for (;;) {
+            bool changed = false;
+            for (uint32_t i = lane; i < n; i += 32) {
+                const uint32_t s8 = st[i], lp = lpos[i];
+                if ((s8 & CH_VAL) && lp < CH_MISSING && !(st[lp] & CH_VAL)) { st[i] = (uint8_t)(s8 & ~CH_VAL); changed = true; }
+            }
+            __syncwarp();
+            if (!__any_sync(0xffffffffu, changed)) break;
+        }
+        // ---- C: layers opened lazily are written iff they enclose something that is: drawn colours and clips that
+        //         are always written mark every BeginClip above them
+        for (uint32_t i = lane; i < n; i += 32) {
+            const uint32_t s8 = st[i];
+            if (!(s8 & CH_VAL) || (s8 & CH_TAG) == 2u || (s8 & (CH_TAG | CH_ELIDE)) == (1u | CH_ELIDE)) continue;
+            for (uint32_t p = lpos[i]; p < CH_MISSING; p = lpos[p]) {
+                const uint32_t sp = st[p];
+                if (sp & CH_NE) break;   // whoever set it keeps climbing
+                st[p] = (uint8_t)(sp | CH_NE);
+            }
+        }
+        __syncwarp();
+        // ---- D: commands, 32 hits at a time in scene order
+        const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
+        uint32_t pos_u = pos - ptcl_off[T];          // offset of the next command inside this tile's list
+        uint32_t restart = 0, restart_rgba = 0, max_depth = 0;
+        for (uint32_t base = 0; base < n; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t nw = 0, s8 = 0, d = 0, lp = CH_NONE, sstart = 0;
+            GGDrawRec r; r.tag = 0; r.parent = -1; r.a = 0; r.b = 0;
+            GGTile t; t.backdrop = 0; t.seg_count = 0;
+            bool emit = false;
+            if (i < n) {
+                s8 = st[i]; lp = lpos[i];
+                const uint32_t tg = s8 & CH_TAG;
+                if (s8 & CH_VAL) {
+                    if (tg == 0u) emit = true;
+                    else if (tg == 1u) emit = !(s8 & CH_ELIDE) || (s8 & CH_NE);
+                    else if (lp < CH_MISSING) { const uint32_t sbg = st[lp]; emit = !(sbg & CH_ELIDE) || (sbg & CH_NE); }
+                }
+            }
+            if (emit) {
+                d = sb[i];
+                r = recs[d];
+                const uint32_t tg = s8 & CH_TAG;
+                if (tg == 1u) {
+                    nw = 1u;
+                    uint32_t depth = 1;   // written clips above this one + itself
+                    for (uint32_t p = lp; p < CH_MISSING; p = lpos[p]) depth++;
+                    max_depth = max(max_depth, depth);
+                } else {
+                    const bool implicit = tg == 2u && (r.a & GG_BLEND_IMPLICIT);
+                    if (implicit) {
+                        t.backdrop = 1;   // full coverage, no geometry: CmdSolid at its EndClip
+                    } else {
+                        GGPath path = paths[dm[d].path_ix];
+                        uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
+                        t = tiles[ti];
+                        sstart = seg_start[ti] - t.seg_count;   // path_tiling advanced seg_start[] to the end of the tile's range
+                    }
+                    nw = tg == 0u ? (t.seg_count ? 6u : 3u) : (t.seg_count ? 7u : 4u);
+                }
+            }
+            uint32_t inc = nw;
+#pragma unroll
+            for (int dl = 1; dl < 32; dl <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, inc, dl); if ((int)lane >= dl) inc += o; }
+            uint32_t o = pos + inc - nw;
+            if (emit) {
+                const uint32_t tg = s8 & CH_TAG;
+                const uint32_t after = pos_u + inc;   // list offset right after this command
+                if (tg == 0u) {
+                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | r.b; ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
+                    else ptcl[o++] = GG_CMD_SOLID;
+                    ptcl[o++] = GG_CMD_COLOR; ptcl[o++] = r.a;
+                    // restart point for fine: an opaque colour over the whole tile outside every clip
+                    if (lp == CH_NONE && !t.seg_count && (r.a >> 24) == 255u && after > restart) { restart = after; restart_rgba = r.a; }
+                } else if (tg == 1u) {
+                    ptcl[o++] = GG_CMD_BEGIN_CLIP;
+                } else {
+                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1); ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
+                    else ptcl[o++] = GG_CMD_SOLID;
+                    ptcl[o++] = GG_CMD_END_CLIP; ptcl[o++] = r.a; ptcl[o++] = r.b;
+                    // ... or the end of an outermost full-coverage layer whose compose mode wipes the backdrop: Clear always,
+                    // Copy / SrcIn / DestIn / SrcOut / DestAtop when nothing was drawn inside
+                    if (!t.seg_count && lpos[lp] == CH_NONE) {
+                        const uint32_t mixm = (r.a >> 8) & 0xffu, comp = r.a & 0xffu;
+                        const bool wipes_empty = comp == 1u || comp == 5u || comp == 6u || comp == 7u || comp == 10u;
+                        if (mixm == 0u && (comp == 0u || (wipes_empty && !(st[lp] & CH_NE))) && after > restart) { restart = after; restart_rgba = 0; }
+                    }
+                }
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, inc, 31);
+            pos += tot; pos_u += tot;
+        }
+        // the last qualifying command wins
+#pragma unroll
+        for (int dl = 16; dl > 0; dl >>= 1) {
+            uint32_t orr = __shfl_xor_sync(0xffffffffu, restart, dl), oc = __shfl_xor_sync(0xffffffffu, restart_rgba, dl);
+            uint32_t od = __shfl_xor_sync(0xffffffffu, max_depth, dl);
+            if (orr > restart) { restart = orr; restart_rgba = oc; }
+            max_depth = max(max_depth, od);
+        }
+        if (lane == 0) {
+            ptcl[pos] = GG_CMD_END;
+            ptcl_len[T] = pos + 1 - ptcl_off[T];
+            restart_pt[2 * T] = restart; restart_pt[2 * T + 1] = restart_rgba;
+            if (max_depth > GG_BLEND_STACK_SPLIT) {
+                uint32_t lv = max_depth - GG_BLEND_STACK_SPLIT;
+                uint32_t so = atomicAdd(&bump->spill, lv);
+                if (so + lv > cfg.spill_cap) atomicOr(&bump->failed, GG_FAIL_SPILL); else spill_off[T] = so;
+            }
+        }
         __syncwarp();
     }
 }
@@ -1000,6 +1192,6 @@ void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
                                 StoreTileHits{b.hit_off, b.hit_cnt, b.ptcl_off, b.hit_cursor, b.spill_off},
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->hits));
     tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.bump);
-    coarse_kernel<<<GG_GRID(4), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
+    coarse_kernel<<<GG_GRID(8), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
                                                            b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.restart_pt, b.bump);
 }
