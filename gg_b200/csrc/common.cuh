@@ -74,7 +74,9 @@ struct GGBump {
     uint32_t failed;       // 32: bitmask of stages whose capacity was exceeded
     uint32_t curves;       // 36: curve tags compacted by flatten_classify
     uint32_t esegs;        // 40: Euler-segment records written by flatten_subdivide
-    uint32_t pad[5];
+    uint32_t sub_cursor;   // 44: next work-list entry flatten_subdivide hands to a lane
+    uint32_t emit_cursor;  // 48: next Euler-segment record flatten_eseg_emit hands to a lane
+    uint32_t pad[3];
 };
 #define GG_FAIL_LINES 1u
 #define GG_FAIL_TILES 2u

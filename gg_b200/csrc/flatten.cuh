@@ -177,79 +177,87 @@ struct GGESeg {
 #define GG_ESEG_LINE 8u           // stroked straight segment: one piece, no Euler parameters
 #define GG_ESEG_CAP 16u           // stroke marker after an open subpath: the start cap
 
-// The adaptive subdivision of flatten.go:76-183 without the emission loop: `sink(rec)` is called once per accepted
-// Euler segment with everything but the bookkeeping fields filled in. widen_hw > 0 raises n by
-// sqrt(1 + hw * max curvature) so that the outer parallel curve of a stroke stays within the tolerance too.
-template <typename Sink>
-__device__ inline void subdivide_cubic(V2 p0, V2 p1, V2 p2, V2 p3, float widen_hw, Sink& sink) {
+// The adaptive subdivision of flatten.go:76-183 without the emission loop, as a resumable state machine: one call of
+// subdiv_step() tries one interval [t0, t0 + dt] and either halves it (returns 0), accepts it (returns 1 with the
+// Euler segment's record filled in, bookkeeping fields aside) or finds the curve finished (returns 2). A lane of
+// flatten_subdivide_kernel holds one curve at a time and picks up the next one as soon as its own is finished, so the
+// lanes of a warp stay in the same instruction stream whatever the depth their curves subdivide to.
+// widen_hw > 0 raises n by sqrt(1 + hw * max curvature) so that the outer parallel curve of a stroke stays within the
+// tolerance too.
+struct SubdivState {
+    V2 p0, p1, p2, p3, last_p, last_q;
+    uint32_t t0u;
+    float dt, last_t, widen_hw;
+};
+__device__ __forceinline__ bool subdiv_begin(SubdivState& s, V2 p0, V2 p1, V2 p2, V2 p3, float widen_hw) {
+    const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f;
+    if (veq(p0, p1) && veq(p0, p2) && veq(p0, p3)) return false;
+    s.p0 = p0; s.p1 = p1; s.p2 = p2; s.p3 = p3; s.widen_hw = widen_hw;
+    s.t0u = 0; s.dt = 1.0f; s.last_t = 0.0f;
+    s.last_p = p0;
+    s.last_q = vsub(p1, p0);
+    if (vlen_sq(s.last_q) < DERIV_THRESH * DERIV_THRESH) {
+        V2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &s.last_q);
+    }
+    return true;
+}
+__device__ inline int subdiv_step(SubdivState& s, GGESeg& r) {
     const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f, FLATTEN_TOL = 0.25f;
-    if (veq(p0, p1) && veq(p0, p2) && veq(p0, p3)) return;
-    uint32_t t0u = 0;
-    float dt = 1.0f;
-    V2 last_p = p0;
-    V2 last_q = vsub(p1, p0);
-    if (vlen_sq(last_q) < DERIV_THRESH * DERIV_THRESH) {
-        V2 dummy; eval_cubic_and_deriv(p0, p1, p2, p3, DERIV_EPS, &dummy, &last_q);
+    float t0 = (float)s.t0u * s.dt;
+    if (t0 == 1.0f) return 2;
+    float t1 = t0 + s.dt;
+    V2 this_p0 = s.last_p, this_q0 = s.last_q, this_p1, this_q1;
+    eval_cubic_and_deriv(s.p0, s.p1, s.p2, s.p3, t1, &this_p1, &this_q1);
+    if (vlen_sq(this_q1) < DERIV_THRESH * DERIV_THRESH) {
+        V2 new_p1, new_q1;
+        eval_cubic_and_deriv(s.p0, s.p1, s.p2, s.p3, t1 - DERIV_EPS, &new_p1, &new_q1);
+        this_q1 = new_q1;
+        if (t1 < 1.0f) { this_p1 = new_p1; t1 -= DERIV_EPS; }
     }
-    float last_t = 0.0f;
-    for (;;) {
-        float t0 = (float)t0u * dt;
-        if (t0 == 1.0f) break;
-        float t1 = t0 + dt;
-        V2 this_p0 = last_p, this_q0 = last_q, this_p1, this_q1;
-        eval_cubic_and_deriv(p0, p1, p2, p3, t1, &this_p1, &this_q1);
-        if (vlen_sq(this_q1) < DERIV_THRESH * DERIV_THRESH) {
-            V2 new_p1, new_q1;
-            eval_cubic_and_deriv(p0, p1, p2, p3, t1 - DERIV_EPS, &new_p1, &new_q1);
-            this_q1 = new_q1;
-            if (t1 < 1.0f) { this_p1 = new_p1; t1 -= DERIV_EPS; }
-        }
-        float actual_dt = t1 - last_t;
-        CubicParams cp = cubic_params_from_points_derivs(this_p0, this_p1, this_q0, this_q1, actual_dt);
-        if (cp.err <= FLATTEN_TOL || dt <= SUBDIV_LIMIT) {
-            EulerParams ep = euler_params_from_angles(cp.th0, cp.th1);
-            float k0_minus_half_k1 = ep.k0 - 0.5f * ep.k1;
-            float k1 = ep.k1;
-            float scale_mul = 0.5f * (float)(1.41421356237309504880168872420969808 / 2.0) * sqrt32(cp.chord_len / (ep.ch * FLATTEN_TOL));
-            GGESeg r;
-            r.a = 0; r.b = 0; r.integral = 0; r.int0 = 0; r.flags = 0;
-            float n_frac;
-            if (fabsf(k1) < 1e-3f) {
-                float k = k0_minus_half_k1 + 0.5f * k1;
-                n_frac = sqrt32(fabsf(k));
-                r.flags |= GG_ESEG_LOW_K1;
-            } else {
-                r.a = k1;
-                r.b = k0_minus_half_k1;
-                r.int0 = cube_signed_sqrt(r.b);
-                float int1 = cube_signed_sqrt(r.a + r.b);
-                r.integral = int1 - r.int0;
-                n_frac = (float)(2.0 / 3.0) * r.integral / r.a;
-            }
-            float nn = n_frac * scale_mul;
-            if (widen_hw > 0.0f) {
-                float k_abs = f_max(fabsf(k0_minus_half_k1), fabsf(k0_minus_half_k1 + k1));
-                nn = nn * sqrt32(1.0f + widen_hw * k_abs * ep.ch / cp.chord_len);
-            }
-            float n = ceilf(nn);
-            if (n < 1) n = 1;
-            if (n > 100) n = 100;
-            if (n != n) n = 0;   // NaN (degenerate input): Go's int(NaN) gives an empty loop
-            r.p0 = this_p0; r.p1 = this_p1;
-            r.th0 = ep.th0; r.k0 = ep.k0; r.k1 = ep.k1; r.ch = ep.ch;
-            r.chord_len = cp.chord_len; r.n = n;
-            if (t1 == 1.0f) r.flags |= GG_ESEG_LAST;
-            sink(r);
-            last_p = this_p1; last_q = this_q1; last_t = t1;
-            t0u++;
-            uint32_t shift = (uint32_t)(__ffs((int)t0u) - 1);   // trailing zeros; t0u != 0 here
-            t0u >>= shift;
-            dt *= (float)(1u << shift);
-        } else {
-            if (t0u < 0xFFFFFFFFu / 2) t0u *= 2;
-            dt *= 0.5f;
-        }
+    float actual_dt = t1 - s.last_t;
+    CubicParams cp = cubic_params_from_points_derivs(this_p0, this_p1, this_q0, this_q1, actual_dt);
+    if (!(cp.err <= FLATTEN_TOL || s.dt <= SUBDIV_LIMIT)) {
+        if (s.t0u < 0xFFFFFFFFu / 2) s.t0u *= 2;
+        s.dt *= 0.5f;
+        return 0;
     }
+    EulerParams ep = euler_params_from_angles(cp.th0, cp.th1);
+    float k0_minus_half_k1 = ep.k0 - 0.5f * ep.k1;
+    float k1 = ep.k1;
+    float scale_mul = 0.5f * (float)(1.41421356237309504880168872420969808 / 2.0) * sqrt32(cp.chord_len / (ep.ch * FLATTEN_TOL));
+    r.a = 0; r.b = 0; r.integral = 0; r.int0 = 0; r.flags = 0;
+    float n_frac;
+    if (fabsf(k1) < 1e-3f) {
+        float k = k0_minus_half_k1 + 0.5f * k1;
+        n_frac = sqrt32(fabsf(k));
+        r.flags |= GG_ESEG_LOW_K1;
+    } else {
+        r.a = k1;
+        r.b = k0_minus_half_k1;
+        r.int0 = cube_signed_sqrt(r.b);
+        float int1 = cube_signed_sqrt(r.a + r.b);
+        r.integral = int1 - r.int0;
+        n_frac = (float)(2.0 / 3.0) * r.integral / r.a;
+    }
+    float nn = n_frac * scale_mul;
+    if (s.widen_hw > 0.0f) {
+        float k_abs = f_max(fabsf(k0_minus_half_k1), fabsf(k0_minus_half_k1 + k1));
+        nn = nn * sqrt32(1.0f + s.widen_hw * k_abs * ep.ch / cp.chord_len);
+    }
+    float n = ceilf(nn);
+    if (n < 1) n = 1;
+    if (n > 100) n = 100;
+    if (n != n) n = 0;   // NaN (degenerate input): Go's int(NaN) gives an empty loop
+    r.p0 = this_p0; r.p1 = this_p1;
+    r.th0 = ep.th0; r.k0 = ep.k0; r.k1 = ep.k1; r.ch = ep.ch;
+    r.chord_len = cp.chord_len; r.n = n;
+    if (t1 == 1.0f) r.flags |= GG_ESEG_LAST;
+    s.last_p = this_p1; s.last_q = this_q1; s.last_t = t1;
+    s.t0u++;
+    uint32_t shift = (uint32_t)(__ffs((int)s.t0u) - 1);   // trailing zeros; t0u != 0 here
+    s.t0u >>= shift;
+    s.dt *= (float)(1u << shift);
+    return 1;
 }
 
 // Arc-length parameter of subdivision point j (0-based: the point that ends line j), flatten.go:144-157.

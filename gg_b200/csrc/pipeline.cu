@@ -254,39 +254,69 @@ __global__ void __launch_bounds__(128) flatten_subdivide_kernel(GGConfig cfg, co
                                                                 const uint32_t* __restrict__ curve_list, uint32_t* line_count,
                                                                 GGESeg* esegs, GGBump* bump) {
     const uint32_t n = bump->curves;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-        uint32_t i = curve_list[k];
-        CurveIn c;
-        load_curve(cfg, scene, tag_monoids, i, &c);
-        ESegSink sink; sink.esegs = esegs; sink.cap = cfg.esegs_cap; sink.bump = bump;
-        sink.tag_ix = i; sink.path_ix = c.path_ix; sink.flags = 0; sink.lines_per_piece = 1; sink.line_rel = 0; sink.prev = 0xffffffffu;
-        StrokeStyle st;
-        if (!load_stroke_style(cfg, scene, c.style_ix, &st)) {
-            subdivide_cubic(c.p0, c.p1, c.p2, c.p3, 0.0f, sink);
-            line_count[i] = sink.line_rel;
-            continue;
-        }
-        LineOut o; o.out = nullptr; o.n = 0; o.cap = 0; o.path_ix = c.path_ix;
-        sink.flags = GG_ESEG_STROKE; sink.lines_per_piece = 2;
-        GGESeg r;
-        r.p0 = c.p0; r.p1 = c.p3; r.th0 = r.k0 = r.k1 = 0; r.ch = 1; r.chord_len = 0; r.a = r.b = r.integral = r.int0 = 0;
-        if (c.tag & GG_PTAG_MARKER) {
-            // copy of the subpath's first segment: it exists so that the last segment can read the tangent of a closing
-            // join; after a marker MoveTo (open subpath) it draws the start cap
-            if (i > 0 && tag_byte(cfg, scene, i - 1) == GG_PTAG_MARKER_MOVE) {
-                V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
-                stroke_cap<false>(o, c.p0, mk(-ns.x, -ns.y), st);
-                r.n = 0; r.flags = GG_ESEG_CAP;
-                sink(r);
+    // per-lane curve in flight
+    SubdivState ss;
+    ESegSink sink; sink.esegs = esegs; sink.cap = cfg.esegs_cap; sink.bump = bump;
+    CurveIn c;
+    StrokeStyle st;
+    uint32_t i = 0;
+    bool active = false, stroke = false, finish = false, exhausted = false;
+    for (;;) {
+        if (!active) {
+            if (finish) {   // the curve this lane just finished: a stroked one still owes the lines of its join / cap
+                uint32_t lines = sink.line_rel;
+                if (stroke) {
+                    LineOut o; o.out = nullptr; o.n = 0; o.cap = 0; o.path_ix = c.path_ix;
+                    V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+                    stroke_tail<false>(o, cfg, scene, tag_monoids, i, c, ne, st);
+                    lines += o.n;
+                }
+                line_count[i] = lines;
+                finish = false;
             }
-            line_count[i] = o.n;
-            continue;
+            uint32_t k = exhausted ? n : atomicAdd(&bump->sub_cursor, 1u);
+            if (k >= n) {
+                exhausted = true;
+            } else {
+                i = curve_list[k];
+                load_curve(cfg, scene, tag_monoids, i, &c);
+                sink.tag_ix = i; sink.path_ix = c.path_ix; sink.flags = 0; sink.lines_per_piece = 1; sink.line_rel = 0; sink.prev = 0xffffffffu;
+                stroke = load_stroke_style(cfg, scene, c.style_ix, &st);
+                if (!stroke) {
+                    active = subdiv_begin(ss, c.p0, c.p1, c.p2, c.p3, 0.0f);
+                    if (!active) line_count[i] = 0;
+                } else {
+                    sink.flags = GG_ESEG_STROKE; sink.lines_per_piece = 2;
+                    GGESeg r;
+                    r.p0 = c.p0; r.p1 = c.p3; r.th0 = r.k0 = r.k1 = 0; r.ch = 1; r.chord_len = 0; r.a = r.b = r.integral = r.int0 = 0;
+                    if (c.tag & GG_PTAG_MARKER) {
+                        // copy of the subpath's first segment: it exists so that the last segment can read the tangent of a
+                        // closing join; after a marker MoveTo (open subpath) it draws the start cap
+                        LineOut o; o.out = nullptr; o.n = 0; o.cap = 0; o.path_ix = c.path_ix;
+                        if (i > 0 && tag_byte(cfg, scene, i - 1) == GG_PTAG_MARKER_MOVE) {
+                            V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+                            stroke_cap<false>(o, c.p0, mk(-ns.x, -ns.y), st);
+                            r.n = 0; r.flags = GG_ESEG_CAP;
+                            sink(r);
+                        }
+                        line_count[i] = o.n;
+                    } else if (c.kind == 1) {
+                        r.n = 1; r.flags = GG_ESEG_LINE | GG_ESEG_LAST; sink(r);
+                        finish = true;    // join / cap lines are counted on the next round
+                    } else {
+                        active = subdiv_begin(ss, c.p0, c.p1, c.p2, c.p3, st.hw);
+                        finish = !active;
+                    }
+                }
+            }
         }
-        if (c.kind == 1) { r.n = 1; r.flags = GG_ESEG_LINE | GG_ESEG_LAST; sink(r); }
-        else subdivide_cubic(c.p0, c.p1, c.p2, c.p3, st.hw, sink);
-        V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
-        stroke_tail<false>(o, cfg, scene, tag_monoids, i, c, ne, st);
-        line_count[i] = sink.line_rel + o.n;
+        if (__all_sync(0xffffffffu, exhausted && !active && !finish)) break;
+        if (active) {
+            GGESeg r;
+            int res = subdiv_step(ss, r);
+            if (res == 1) sink(r);
+            else if (res == 2) { active = false; finish = true; }
+        }
     }
 }
 
@@ -310,62 +340,111 @@ __global__ void __launch_bounds__(256) flatten_line_emit_kernel(GGConfig cfg, co
     }
 }
 
+// One lane holds one record at a time and takes the next one from a shared cursor when its own is finished; a step
+// evaluates ONE point of an Euler segment (the float64 transcendentals), whichever record and whichever kind of path
+// it belongs to, so the lanes of a warp share that instruction stream. The first step of a record that continues a
+// curve re-evaluates the last point of the previous record (bit-identical: same inputs, same code).
 __global__ void __launch_bounds__(128) flatten_eseg_emit_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
                                                                 const GGPathMonoid* __restrict__ tag_monoids,
                                                                 const GGESeg* __restrict__ esegs, const uint32_t* __restrict__ line_off,
                                                                 GGLine* lines, uint32_t* path_bbox_ord, GGBump* bump) {
     if (bump->failed) return;
     const uint32_t n_rec = min(bump->esegs, cfg.esegs_cap);
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n_rec; k += gridDim.x * blockDim.x) {
-        const GGESeg r = esegs[k];
-        const uint32_t i = r.tag_ix;
-        const int n = (int)r.n;
-        float bb[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
-        uint32_t base = line_off[i] + r.line_rel;
-        if (!(r.flags & (GG_ESEG_STROKE | GG_ESEG_CAP))) {
-            if ((uint64_t)base + (uint32_t)n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
-            V2 lp0 = r.p0;   // first Euler segment: the curve's start point (last_p == p0)
-            if (r.prev != 0xffffffffu) { const GGESeg pr = esegs[r.prev]; lp0 = eseg_point(pr, (int)pr.n - 1); }
-            for (int j = 0; j < n; j++) {
-                V2 lp1 = eseg_point(r, j);
-                write_line(lines + base + j, r.path_ix, lp0, lp1, bb);
-                lp0 = lp1;
+    GGESeg r;
+    CurveIn c;
+    StrokeStyle st;
+    V2 ns = mk(0, 0), ne = mk(0, 0);
+    StrokeVertex v0 = stroke_vertex(mk(0, 0), mk(0, 0));
+    float bb[4] = {3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f};
+    uint32_t base = 0;
+    int j = 0, n = 0;
+    bool active = false, finish = false, exhausted = false, stroke = false;
+    r.flags = 0; r.n = 0; r.prev = 0xffffffffu; r.path_ix = 0; r.tag_ix = 0;
+    st.hw = 0; st.miter_limit = 0; st.join = 0; st.cap = 0;
+    for (;;) {
+        if (!active) {
+            if (finish) {
+                if (stroke && (r.flags & GG_ESEG_LAST)) {   // the join to the next segment / the end cap
+                    LineOut o; o.n = 0; o.path_ix = r.path_ix;
+                    o.bb[0] = o.bb[1] = 3.0e38f; o.bb[2] = o.bb[3] = -3.0e38f;
+                    uint32_t tb = base + 2u * (uint32_t)n;
+                    o.out = lines + tb; o.cap = tb < cfg.lines_cap ? cfg.lines_cap - tb : 0;
+                    stroke_tail<true>(o, cfg, scene, tag_monoids, r.tag_ix, c, ne, st);
+                    if (o.n > o.cap) atomicOr(&bump->failed, GG_FAIL_LINES);
+                    bb[0] = fminf(bb[0], o.bb[0]); bb[1] = fminf(bb[1], o.bb[1]); bb[2] = fmaxf(bb[2], o.bb[2]); bb[3] = fmaxf(bb[3], o.bb[3]);
+                }
+                if (bb[0] <= bb[2]) fold_bbox(path_bbox_ord, r.path_ix, bb);
+                finish = false;
             }
-            if (n > 0) fold_bbox(path_bbox_ord, r.path_ix, bb);
-            continue;
+            uint32_t k = exhausted ? n_rec : atomicAdd(&bump->emit_cursor, 1u);
+            if (k >= n_rec) {
+                exhausted = true;
+            } else {
+                r = esegs[k];
+                n = (int)r.n;
+                base = line_off[r.tag_ix] + r.line_rel;
+                bb[0] = bb[1] = 3.0e38f; bb[2] = bb[3] = -3.0e38f;
+                stroke = (r.flags & (GG_ESEG_STROKE | GG_ESEG_CAP)) != 0;
+                j = r.prev != 0xffffffffu ? -1 : 0;
+                if (!stroke) {
+                    if ((uint64_t)base + (uint32_t)n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); n = 0; }
+                    v0.p = r.p0;   // first Euler segment: the curve's start point (last_p == p0)
+                    active = n > 0;
+                } else {
+                    load_curve(cfg, scene, tag_monoids, r.tag_ix, &c);
+                    load_stroke_style(cfg, scene, c.style_ix, &st);
+                    ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+                    ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
+                    if (r.flags & GG_ESEG_CAP) {
+                        LineOut o; o.n = 0; o.path_ix = r.path_ix;
+                        o.bb[0] = o.bb[1] = 3.0e38f; o.bb[2] = o.bb[3] = -3.0e38f;
+                        o.out = lines + base; o.cap = base < cfg.lines_cap ? cfg.lines_cap - base : 0;
+                        stroke_cap<true>(o, c.p0, mk(-ns.x, -ns.y), st);
+                        if (o.n > o.cap) atomicOr(&bump->failed, GG_FAIL_LINES);
+                        if (o.n) fold_bbox(path_bbox_ord, r.path_ix, o.bb);
+                    } else {
+                        if ((uint64_t)base + 2u * (uint32_t)n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); n = 0; r.flags &= ~GG_ESEG_LAST; }
+                        v0 = stroke_vertex(r.p0, ns);
+                        active = n > 0;
+                        finish = !active;
+                    }
+                }
+            }
         }
-        // ---- stroked path
-        CurveIn c;
-        load_curve(cfg, scene, tag_monoids, i, &c);
-        StrokeStyle st;
-        load_stroke_style(cfg, scene, c.style_ix, &st);
-        V2 ns = stroke_normal(seg_start_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
-        V2 ne = stroke_normal(seg_end_tangent(c.p0, c.p1, c.p2, c.p3, c.kind), st.hw);
-        LineOut o; o.n = 0; o.path_ix = r.path_ix;
-        o.bb[0] = o.bb[1] = 3.0e38f; o.bb[2] = o.bb[3] = -3.0e38f;
-        if (r.flags & GG_ESEG_CAP) {
-            o.out = lines + base; o.cap = base < cfg.lines_cap ? cfg.lines_cap - base : 0;
-            stroke_cap<true>(o, c.p0, mk(-ns.x, -ns.y), st);
-            if (o.n > o.cap) atomicOr(&bump->failed, GG_FAIL_LINES);
-            if (o.n) fold_bbox(path_bbox_ord, r.path_ix, o.bb);
-            continue;
-        }
-        if ((uint64_t)base + 2u * (uint32_t)n > cfg.lines_cap) { atomicOr(&bump->failed, GG_FAIL_LINES); continue; }
-        StrokeVertex v0 = stroke_vertex(r.p0, ns);
-        if (r.prev != 0xffffffffu) { const GGESeg pr = esegs[r.prev]; v0 = eseg_vertex(pr, (int)pr.n - 1, st.hw, ne, ns); }
-        for (int j = 0; j < n; j++) {
-            StrokeVertex v1 = (r.flags & GG_ESEG_LINE) ? stroke_vertex(r.p1, ne) : eseg_vertex(r, j, st.hw, ne, ns);
-            stroke_piece_emit(lines, base + 2u * (uint32_t)j, cfg.lines_cap, &bump->lines, &bump->failed, r.path_ix, v0, v1, st.hw, bb);
+        if (__all_sync(0xffffffffu, exhausted && !active && !finish)) break;
+        if (active) {
+            // ---- one point: of this record, or (first step of a continuing record) the last one of the previous record
+            const bool from_prev = j < 0;
+            GGESeg q = r;
+            if (from_prev) q = esegs[r.prev];
+            const int jj = from_prev ? (int)q.n - 1 : j;
+            StrokeVertex v1;
+            if ((q.flags & (GG_ESEG_LAST | GG_ESEG_LINE)) && jj == (int)q.n - 1) {
+                v1 = stroke_vertex(q.p1, ne);   // exact end point (flatten.go:141-142) with the segment's end offset
+            } else {
+                EulerParams ep; ep.th0 = q.th0; ep.k0 = q.k0; ep.k1 = q.k1; ep.ch = q.ch;
+                const float s = eseg_param(q, jj);
+                v1.p = euler_seg_eval(q.p0, q.p1, ep, s);
+                v1.n = ns;
+                if (stroke) {
+                    V2 chord = vsub(q.p1, q.p0);
+                    if (!(vlen_sq(chord) < 1e-12f)) {   // euler.go:44 otherwise: no usable chord direction, the curve's start offset
+                        float th = (ep.k0 + 0.5f * ep.k1 * (s - 1.0f)) * s - ep.th0;   // euler.go:121-123
+                        float sx = sin32(th), sy = cos32(th);                           // euler.go:133-137: offset direction
+                        float nscale = st.hw / q.chord_len;
+                        v1.n = mk((chord.x * sx - chord.y * sy) * nscale, (chord.x * sy + chord.y * sx) * nscale);
+                    }
+                    v1.l = vadd(v1.p, v1.n); v1.r = vsub(v1.p, v1.n);
+                }
+            }
+            if (!from_prev) {
+                if (!stroke) write_line(lines + base + j, r.path_ix, v0.p, v1.p, bb);
+                else stroke_piece_emit(lines, base + 2u * (uint32_t)j, cfg.lines_cap, &bump->lines, &bump->failed, r.path_ix, v0, v1, st.hw, bb);
+            }
             v0 = v1;
+            j = from_prev ? 0 : j + 1;
+            if (j == n) { active = false; finish = true; }
         }
-        if (r.flags & GG_ESEG_LAST) {
-            uint32_t tb = base + 2u * (uint32_t)n;
-            o.out = lines + tb; o.cap = tb < cfg.lines_cap ? cfg.lines_cap - tb : 0;
-            stroke_tail<true>(o, cfg, scene, tag_monoids, i, c, ne, st);
-            if (o.n > o.cap) atomicOr(&bump->failed, GG_FAIL_LINES);
-            bb[0] = fminf(bb[0], o.bb[0]); bb[1] = fminf(bb[1], o.bb[1]); bb[2] = fmaxf(bb[2], o.bb[2]); bb[3] = fmaxf(bb[3], o.bb[3]);
-        }
-        if (bb[0] <= bb[2]) fold_bbox(path_bbox_ord, r.path_ix, bb);
     }
 }
 
@@ -1166,7 +1245,7 @@ void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     draw_leaf_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.scene, b.draw_monoids, b.info, b.clip_inps, b.draw_recs);
     // a6: flatten (count, scan, emit)
     flatten_classify_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.curve_list, b.bump);
-    flatten_subdivide_kernel<<<GG_GRID(4), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.esegs, b.bump);
+    flatten_subdivide_kernel<<<GG_GRID(2), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.esegs, b.bump);
     gg_scan<uint32_t>(s, n_tag_bytes, cfg.n_tag_bytes, LoadU32{b.line_count}, StoreU32Ex{b.line_off}, (uint32_t*)b.scan_partials, &b.bump->lines);
     flatten_line_emit_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
     flatten_eseg_emit_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.esegs, b.line_off, b.lines, b.path_bbox_ord, b.bump);
