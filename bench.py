@@ -261,7 +261,7 @@ def main():
         gbs = stage_bytes[k] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
         stages[k] = {"ms": float(ms), "algorithmic_bytes": int(stage_bytes[k]), "achieved": gbs, "frac": gbs / peak}
     dom = max(stages, key=lambda k: stages[k]["ms"])
-    dom_kernel = {"front": "flatten_curve_emit_kernel (+ classify/count/scans)", "binning": "path_count_kernel (+ backdrop, tiling)",
+    dom_kernel = {"front": "flatten_subdivide_kernel + flatten_eseg_emit_kernel (+ classify, scans)", "binning": "path_count_kernel (+ backdrop, tiling)",
                   "coarse": "coarse_kernel (+ hit scan/scatter)", "fine": "fine_kernel"}[dom]
 
     # ---- e2e: public host API, host buffers, H2D + D2H inside the timed region

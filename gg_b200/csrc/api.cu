@@ -34,7 +34,8 @@ struct DevBuf {
 struct Ctx {
     int device = 0;
     bool host_only = false;   // device < 0: scene accumulation and packing only, no CUDA call is ever made
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_part[GG_FINE_PARTS] = {}, ev_copied = nullptr;
     std::string err;
     HostScene scene;
     HostScene::Layout layout{};
@@ -48,8 +49,9 @@ struct Ctx {
     uint8_t* h_frame = nullptr; size_t h_frame_bytes = 0;
     // device
     DevBuf scene_d, tag_monoids, draw_monoids, info, clip_inps, draw_recs, line_count, line_off, curve_list, esegs, lines, path_bbox, paths, path_row_off,
-        tiles, seg_start, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, restart_pt, spill_off, spill, bump,
+        tiles, seg_start, imp_mask, imp_seen, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, restart_pt, spill_off, spill, bump,
         scan_partials, frame_d;
+    uint32_t imp_words = 0;
     uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0, esegs_cap = 0;
     // Read-back target seen on consecutive flushes (gg keeps one pixmap per context): page-locked in place
     // from its second use so the band is DMA'd straight into it, without the staging copy.
@@ -84,7 +86,7 @@ int ensure(Ctx* c, DevBuf& b, size_t bytes) {
 }
 size_t total_device_bytes(Ctx* c) {
     DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list, &c->esegs,
-                     &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
+                     &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->imp_mask, &c->imp_seen, &c->seg_counts, &c->segments,
                      &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->restart_pt, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
     size_t t = 0;
@@ -93,7 +95,7 @@ size_t total_device_bytes(Ctx* c) {
 }
 void free_all(Ctx* c) {
     DevBuf* all[] = {&c->scene_d, &c->tag_monoids, &c->draw_monoids, &c->info, &c->clip_inps, &c->draw_recs, &c->line_count, &c->line_off, &c->curve_list, &c->esegs,
-                     &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->seg_counts, &c->segments,
+                     &c->lines, &c->path_bbox, &c->paths, &c->path_row_off, &c->tiles, &c->seg_start, &c->imp_mask, &c->imp_seen, &c->seg_counts, &c->segments,
                      &c->tile_hits, &c->hit_off, &c->hit_cnt, &c->hit_cursor, &c->hits, &c->ptcl_off, &c->ptcl_len, &c->ptcl, &c->restart_pt, &c->spill_off, &c->spill,
                      &c->bump, &c->scan_partials, &c->frame_d};
     for (DevBuf* b : all) { if (b->p) cudaFree(b->p); b->p = nullptr; b->bytes = 0; }
@@ -169,6 +171,12 @@ int size_dynamic(Ctx* c) {
     if ((r = ensure(c, c->esegs, sizeof(GGESeg) * (size_t)c->esegs_cap))) return r;
     if ((r = ensure(c, c->tiles, sizeof(GGTile) * (size_t)c->tiles_cap))) return r;
     if ((r = ensure(c, c->seg_start, 4 * (size_t)c->tiles_cap))) return r;
+    if ((r = ensure(c, c->imp_mask, (size_t)c->tiles_cap))) return r;
+    {   // (implicit layer, tile) bitmap; beyond 256 MiB the hit lists simply keep their duplicates
+        size_t words = ((size_t)band_tiles(c) + 31) / 32, bytes = 4 * words * c->scene.n_implicit;
+        c->imp_words = (c->scene.n_implicit && bytes <= ((size_t)256 << 20)) ? (uint32_t)words : 0u;
+        if (c->imp_words && (r = ensure(c, c->imp_seen, bytes))) return r;
+    }
     if ((r = ensure(c, c->seg_counts, sizeof(GGSegCount) * (size_t)c->seg_counts_cap))) return r;
     if ((r = ensure(c, c->segments, sizeof(GGSegment) * (size_t)c->segments_cap))) return r;
     if ((r = ensure(c, c->hits, 4 * (size_t)c->hits_cap))) return r;
@@ -190,7 +198,7 @@ void fill_config(Ctx* c, uint32_t flags) {
     g.draw_data_base = L.draw_data_base; g.transform_base = L.transform_base; g.style_base = L.style_base;
     g.clip_parent_base = L.clip_aux_base; g.n_scene_words = L.n_scene_words;
     g.lines_cap = c->lines_cap; g.tiles_cap = c->tiles_cap; g.rows_cap = c->rows_cap; g.seg_counts_cap = c->seg_counts_cap;
-    g.segments_cap = c->segments_cap; g.hits_cap = c->hits_cap; g.ptcl_cap = c->ptcl_cap; g.spill_cap = c->spill_cap; g.esegs_cap = c->esegs_cap;
+    g.segments_cap = c->segments_cap; g.hits_cap = c->hits_cap; g.ptcl_cap = c->ptcl_cap; g.spill_cap = c->spill_cap; g.esegs_cap = c->esegs_cap; g.imp_words = c->imp_words; g.n_implicit = c->scene.n_implicit;
     for (int i = 0; i < 4; i++) g.bg[i] = (float)c->bg[i] / 255.0f;
     g.flags = (flags & GGCUDA_COMPOSITE_OVER) ? GG_FLAG_BG_FROM_DST : 0u;
 }
@@ -201,7 +209,7 @@ GGBuffers buffers(Ctx* c) {
     b.info = (uint32_t*)c->info.p; b.clip_inps = (GGClipInp*)c->clip_inps.p; b.draw_recs = (GGDrawRec*)c->draw_recs.p;
     b.line_count = (uint32_t*)c->line_count.p; b.line_off = (uint32_t*)c->line_off.p; b.curve_list = (uint32_t*)c->curve_list.p; b.esegs = (GGESeg*)c->esegs.p; b.lines = (GGLine*)c->lines.p;
     b.path_bbox_ord = (uint32_t*)c->path_bbox.p; b.paths = (GGPath*)c->paths.p; b.path_row_off = (uint32_t*)c->path_row_off.p;
-    b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
+    b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.imp_mask = (uint8_t*)c->imp_mask.p; b.imp_seen = (uint32_t*)c->imp_seen.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
     b.segments = (GGSegment*)c->segments.p; b.tile_hits = (unsigned long long*)c->tile_hits.p; b.hit_off = (uint32_t*)c->hit_off.p;
     b.hit_cnt = (uint32_t*)c->hit_cnt.p; b.hit_cursor = (uint32_t*)c->hit_cursor.p; b.hits = (uint32_t*)c->hits.p;
     b.ptcl_off = (uint32_t*)c->ptcl_off.p; b.ptcl_len = (uint32_t*)c->ptcl_len.p; b.restart_pt = (uint32_t*)c->restart_pt.p; b.ptcl = (uint32_t*)c->ptcl.p; b.spill_off = (uint32_t*)c->spill_off.p;
@@ -210,7 +218,9 @@ GGBuffers buffers(Ctx* c) {
 }
 
 // Run the pipeline into dst_device (band-relative). Re-runs with larger buffers while a stage overflowed.
-int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
+// host_dst != nullptr (page-locked, row pitch host_stride): fine runs in GG_FINE_PARTS row slices and every slice is copied to
+// the host on a second stream while the next one is rasterised.
+int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* host_dst = nullptr, size_t host_stride = 0) {
     if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
     if (!c->uploaded) { int r = upload(c); if (r) return r; }
@@ -229,10 +239,28 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags) {
         if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
         CK(cudaMemcpyAsync(c->h_bump, c->bump.p, sizeof(GGBump), cudaMemcpyDeviceToHost, c->stream));
         // fine is launched optimistically; if a stage overflowed its inputs are in-bounds garbage and the pass is redone
-        gg_launch_fine(c->cfg, b, dst_device, stride, c->stream);
+        const uint32_t band_rows_t = c->band_y1 - c->band_y0;
+        uint32_t parts = (host_dst && band_rows_t >= 4 * GG_FINE_PARTS) ? GG_FINE_PARTS : 1u;
+        for (uint32_t k = 0; k < parts; k++) {
+            uint32_t r0 = (uint32_t)((uint64_t)band_rows_t * k / parts), r1 = (uint32_t)((uint64_t)band_rows_t * (k + 1) / parts);
+            gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, r0, r1, k);
+            if (host_dst) {
+                uint32_t y0 = r0 * GG_TILE_H, y1 = std::min(r1 * GG_TILE_H, std::min(c->band_y1 * GG_TILE_H, c->height) - c->band_y0 * GG_TILE_H);
+                if (y1 > y0) {
+                    CK(cudaEventRecord(c->ev_part[k], c->stream));
+                    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_part[k], 0));
+                    CK(cudaMemcpy2DAsync(host_dst + (size_t)y0 * host_stride, host_stride, dst_device + (size_t)y0 * stride, stride, (size_t)c->width * 4, y1 - y0,
+                                         cudaMemcpyDeviceToHost, c->copy_stream));
+                }
+            }
+        }
+        if (host_dst) {   // the main stream owns the frame buffer again only after the copies
+            CK(cudaEventRecord(c->ev_copied, c->copy_stream));
+            CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+        }
         if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
         c->stats.passes++;
-        c->stats.kernel_launches += 18 + 7 + 5 + 1;   // front (4 scans x 3 + 6) + binning + coarse + fine
+        c->stats.kernel_launches += 18 + 7 + 5 + parts;   // front (4 scans x 3 + 6) + binning + coarse + fine
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
         GGBump bm = *c->h_bump;
@@ -300,7 +328,10 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
         return GGCUDA_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev) cudaEventCreate(&ev);
+    for (auto& ev : c->ev_part) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming);
     *out = reinterpret_cast<ggcuda_ctx*>(c);
     return 0;
 }
@@ -317,6 +348,9 @@ void ggcuda_destroy(ggcuda_ctx* h) {
     if (c->h_bump) cudaFreeHost(c->h_bump);
     if (c->h_frame) cudaFreeHost(c->h_frame);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : c->ev_part) if (ev) cudaEventDestroy(ev);
+    if (c->ev_copied) cudaEventDestroy(c->ev_copied);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -465,7 +499,7 @@ int ggcuda_render_device(ggcuda_ctx* h, void* dst_device, size_t stride, uint32_
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || !dst_device) return c ? fail(c, GGCUDA_ERR_INVALID, "dst_device is NULL") : GGCUDA_ERR_INVALID;
     if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
-    int r = render(c, (uint8_t*)dst_device, stride, flags);
+    int r = render(c, (uint8_t*)dst_device, stride, flags);   // one fine launch, no host copy
     if (r == 0 && !(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
     return r;
 }
@@ -496,9 +530,6 @@ int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
         for (size_t y = 0; y < rows; y++) memcpy(c->h_frame + y * tight, dst + (row0 + y) * stride, tight);
         CK(cudaMemcpyAsync(c->frame_d.p, c->h_frame, bytes, cudaMemcpyHostToDevice, c->stream));
     }
-    r = render(c, (uint8_t*)c->frame_d.p, tight, flags);
-    if (r) return r;
-    if (trace) t2 = now_ms();
     uint8_t* band_dst = dst + (size_t)row0 * stride;
     size_t band_bytes = (rows - 1) * stride + tight;
     if (band_dst == c->last_dst && band_bytes == c->last_dst_bytes) {
@@ -508,17 +539,18 @@ int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
         if (c->dst_registered) { cudaHostUnregister(c->last_dst); c->dst_registered = false; }
         c->last_dst = band_dst; c->last_dst_bytes = band_bytes;
     }
-    if (c->dst_registered) {
-        CK(cudaMemcpy2DAsync(band_dst, stride, c->frame_d.p, tight, tight, rows, cudaMemcpyDeviceToHost, c->stream));
-        CK(cudaStreamSynchronize(c->stream));
-    } else {
+    // a page-locked target is filled slice by slice while fine is still running (render() queues the copies)
+    r = render(c, (uint8_t*)c->frame_d.p, tight, flags, c->dst_registered ? band_dst : nullptr, stride);
+    if (r) return r;
+    if (trace) t2 = now_ms();
+    if (!c->dst_registered) {
         CK(cudaMemcpyAsync(c->h_frame, c->frame_d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         if (stride == tight) memcpy(band_dst, c->h_frame, bytes);
         else for (size_t y = 0; y < rows; y++) memcpy(band_dst + y * stride, c->h_frame + y * tight, tight);
     }
-    if (trace) fprintf(stderr, "[ggcuda] flush: pack+upload %.2f ms, pipeline %.2f ms (%u passes), read-back %.2f ms (%s)\n", t1 - t0, t2 - t1,
-                       c->stats.passes, now_ms() - t2, c->dst_registered ? "direct" : "staged");
+    if (trace) fprintf(stderr, "[ggcuda] flush: pack+upload %.2f ms, pipeline %s %.2f ms (%u passes), %s %.2f ms\n", t1 - t0,
+                       c->dst_registered ? "+ overlapped read-back" : "", t2 - t1, c->stats.passes, c->dst_registered ? "tail" : "staged read-back", now_ms() - t2);
     if (!(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
     return 0;
 }

@@ -14,6 +14,7 @@
 #define GG_SCAN_BLOCKS (GG_SM_COUNT * 4)
 #define GG_SCAN_THREADS 256
 #define GG_SCAN_ITEMS 4
+#define GG_FINE_PARTS 4            // ggcuda_flush runs fine in up to this many row slices so that read-back overlaps it
 
 struct GGLine { uint32_t path_ix; float p0x, p0y, p1x, p1y; };                 // LineSoup, 20 B
 struct GGPath { uint32_t bbox[4]; uint32_t tiles; };                           // Path, 20 B
@@ -76,7 +77,9 @@ struct GGBump {
     uint32_t esegs;        // 40: Euler-segment records written by flatten_subdivide
     uint32_t sub_cursor;   // 44: next work-list entry flatten_subdivide hands to a lane
     uint32_t emit_cursor;  // 48: next Euler-segment record flatten_eseg_emit hands to a lane
-    uint32_t pad[3];
+    uint32_t pad[3];       // 52
+    uint32_t fine_cursor[GG_FINE_PARTS];   // 64: next tile (relative to the part's first) fine hands to a warp, one per launch of a frame
+    uint32_t pad2[8 - GG_FINE_PARTS];
 };
 #define GG_FAIL_LINES 1u
 #define GG_FAIL_TILES 2u
@@ -98,6 +101,7 @@ struct GGConfig {
     uint32_t clip_parent_base;              // word offset of the host-resolved clip-parent array (n_draws words)
     uint32_t n_scene_words;
     uint32_t lines_cap, tiles_cap, rows_cap, seg_counts_cap, segments_cap, hits_cap, ptcl_cap, spill_cap, esegs_cap;
+    uint32_t n_implicit, imp_words;         // implicit layers; words per implicit layer in the (layer, tile) bitmap; 0 = no de-duplication
     float bg[4];                            // premultiplied background
     uint32_t flags;
 };

@@ -328,13 +328,10 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
 __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
-                                                               float4* spill, const GGBump* __restrict__ bump, uint8_t* dst, size_t stride) {
+                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, uint32_t tile0, uint32_t tile1, uint32_t part) {
     // a stage overflowed its buffer: PTCL / segments are incomplete, the host re-runs the pass with larger buffers
     if (bump->failed || bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap || bump->segments > cfg.segments_cap) return;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp_global = blockIdx.x * FINE_WARPS + (threadIdx.x >> 5);
-    const uint32_t n_warps = gridDim.x * FINE_WARPS;
-    const uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
     const uint32_t row = lane >> 1;
     const uint32_t xb = (lane & 1u) * PX;
     // per-warp slice of dynamic shared memory (FINE_SMEM_PER_WARP bytes, opt-in above 48 KiB):
@@ -360,7 +357,13 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
     // accesses), deeper levels in the global spill buffer coarse sized for this tile. A local-memory stack
     // pushed ~10 GB of write-through traffic to L2 per 4K frame of the benchmark scene (73 composites per tile).
 
-    for (uint32_t T = warp_global; T < n_tiles; T += n_warps) {
+    // Tiles are handed out from a shared cursor: their cost varies by orders of magnitude (restart points make most of
+    // them trivial), a static stride left warps idle behind the heavy ones.
+    for (;;) {
+        uint32_t T = 0;
+        if (lane == 0) T = tile0 + atomicAdd(&bump->fine_cursor[part], 1u);
+        T = __shfl_sync(0xffffffffu, T, 0);
+        if (T >= tile1) break;
         const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
         const uint32_t px = tx * GG_TILE_W + xb, py = ty * GG_TILE_H + row;
         const bool row_in = py < cfg.height;
@@ -442,12 +445,16 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
                 const float4* slot; uint32_t step;
                 if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
                 else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
+                const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
+                // Scaling the source by the coverage (fine.go:152-160) equals out = D + cov (blend(S, D) - D) for every mode
+                // whose backdrop factor is 1 under a transparent source; the six compose modes that wipe their backdrop
+                // are blended at full strength and interpolated instead (a pixel the layer's clip does not cover stays).
+                const bool wipe = mix == 0u && (compose == 0u || compose == 1u || compose == 5u || compose == 6u || compose == 7u || compose == 10u);
 #pragma unroll
                 for (int i = 0; i < PX; i++) {
-                    float scale = area[i] * alpha;   // fg = rgba * area * alpha, in place
+                    float scale = wipe ? alpha : area[i] * alpha;   // fg = rgba * area * alpha, in place
                     rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
                 }
-                const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
                 if (mix != 0u && mix < 16u) {
                     // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source); only
                     // pixels where both are visible take the (un-premultiply, mix, re-compose) path
@@ -469,6 +476,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
                         o.x = fmaf(fb, sv.x, fa * rgba[i].x); o.y = fmaf(fb, sv.y, fa * rgba[i].y);
                         o.z = fmaf(fb, sv.z, fa * rgba[i].z); o.w = fmaf(fb, sv.w, fa * rgba[i].w);
                         if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
+                        if (wipe) { const float cv = area[i]; o.x = sv.x + cv * (o.x - sv.x); o.y = sv.y + cv * (o.y - sv.y); o.z = sv.z + cv * (o.z - sv.z); o.w = sv.w + cv * (o.w - sv.w); }
                         rgba[i] = o;
                     }
                 }
@@ -491,13 +499,15 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
     }
 }
 
-void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s) {
-    uint32_t n_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part) {
+    // tile rows [row0, row1) relative to the band; `part` selects the work cursor (each launch of a frame needs its own)
+    uint32_t n_tiles = cfg.width_in_tiles * (row1 - row0);
     uint32_t blocks = (n_tiles + FINE_WARPS - 1) / FINE_WARPS;
     uint32_t max_blocks = GG_SM_COUNT * 16;
     if (blocks > max_blocks) blocks = max_blocks;
     if (blocks == 0) return;
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
-    fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride);
+    fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride,
+                                                      cfg.width_in_tiles * row0, cfg.width_in_tiles * row1, part);
 }

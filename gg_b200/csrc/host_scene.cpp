@@ -51,7 +51,7 @@ void HostScene::clear(uint32_t w, uint32_t h) {
     tags.clear(); path_data.clear(); draw_tags.clear(); draw_data.clear(); styles.clear(); transforms.clear();
     clip_aux.clear(); clip_stack.clear(); clip_kind.clear(); clip_bb.clear();
     next_clip_bb[0] = next_clip_bb[1] = -3.0e38f; next_clip_bb[2] = next_clip_bb[3] = 3.0e38f;
-    n_paths = n_clips = n_seg_tags = 0;
+    n_paths = n_clips = n_seg_tags = n_implicit = 0;
     have_transform = false; in_path = false; has_move = false;
 }
 
@@ -332,6 +332,9 @@ void HostScene::begin_layer(uint32_t blend_word, float alpha) {
         move_to(x0, y0); line_to(x1, y0); line_to(x1, y1); line_to(x0, y1); close();
     } else {
         blend_word |= 0xC0000000u;
+        // ordinal among the implicit layers, in the (otherwise unused) width word of this clip path's style: the device keeps
+        // one bit per (implicit layer, tile) so that a layer enters a tile's hit list once, not once per enclosed draw
+        styles[styles.size() - 2] = n_implicit++;
     }
     end_path();
     begin_clip(blend_word, alpha, 1);

@@ -37,7 +37,7 @@ struct HostScene {
     float next_clip_bb[4] = {-3.0e38f, -3.0e38f, 3.0e38f, 3.0e38f};   // bounds of the clip path just emitted (consumed by begin_clip)
     void set_next_clip_bounds(const float transform[6], const uint8_t* verbs, size_t n_verbs, const float* coords, size_t n_coords,
                               const uint8_t* verb_map = nullptr);
-    uint32_t n_paths = 0, n_clips = 0, n_seg_tags = 0;
+    uint32_t n_paths = 0, n_clips = 0, n_seg_tags = 0, n_implicit = 0;
     float last_transform[6] = {0, 0, 0, 0, 0, 0};
     bool have_transform = false;
     // current path state

@@ -24,6 +24,8 @@ struct GGBuffers {
     uint32_t* path_row_off;     // [n_paths]
     GGTile* tiles;              // [tiles_cap]
     uint32_t* seg_start;        // [tiles_cap]
+    uint8_t* imp_mask;          // [tiles_cap] per path tile: which implicit ancestors it brought into its tile's hit list
+    uint32_t* imp_seen;         // [n_implicit * imp_words] one bit per (implicit layer, band tile)
     GGSegCount* seg_counts;     // [seg_counts_cap]
     GGSegment* segments;        // [segments_cap]
     // coarse
@@ -48,4 +50,4 @@ void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  
 void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s); // path_count, backdrop, seg alloc, path_tiling
 void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  // hit lists + PTCL
 // fine (fine.cu). dst: RGBA8 premultiplied, row stride in bytes; covers tile rows [band_y0, band_y1).
-void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s);
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part);

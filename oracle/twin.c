@@ -1442,10 +1442,17 @@ void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment 
             if (clip_depth == 0) continue;
             clip_depth--;
             float (*saved)[4] = stack[clip_depth];
+            /* Coverage: scaling the source by it (fine.go:152-160) is the same as out = D + cov (blend(S, D) - D) for every
+             * mode whose backdrop factor is 1 under a transparent source; for the six that wipe their backdrop (Clear, Copy,
+             * SrcIn, DestIn, SrcOut, DestAtop) it is not -- a pixel the layer's clip does not cover would be wiped too --
+             * so those are blended at full strength and interpolated. */
+            uint32_t bmix = (blend >> 8) & 0xffu, bcomp = blend & 0xffu;
+            int wipe = bmix == 0 && (bcomp == 0 || bcomp == 1 || bcomp == 5 || bcomp == 6 || bcomp == 7 || bcomp == 10);
             for (int i = 0; i < PC; i++) {
-                float scale = area[i] * alpha;
+                float scale = wipe ? alpha : area[i] * alpha;
                 float fgc[4] = {rgba[i][0] * scale, rgba[i][1] * scale, rgba[i][2] * scale, rgba[i][3] * scale};
                 ot_blend_f32(blend, saved[i], fgc, rgba[i]);
+                if (wipe) for (int k = 0; k < 4; k++) rgba[i][k] = saved[i][k] + area[i] * (rgba[i][k] - saved[i][k]);
             }
         } break;
         default: goto done;

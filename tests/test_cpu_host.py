@@ -346,3 +346,38 @@ def test_glyph_fixture_and_text_scene():
     img, _ = T.render_packed(words, lay, w, h, (255, 255, 255, 255))
     ink = (img[..., :3].sum(-1) < 3 * 255).mean()
     assert 0.05 < ink < 0.6        # text, not blobs: a plausible share of inked pixels
+
+
+def test_push_layer_with_clip_is_one_clip():
+    """scene.PushLayer(blend, alpha, clip) arrives as PushLayer, clip path, BeginClip ... EndClip, PopLayer (scene/scene.go:307-375):
+    one BeginClip/EndClip pair whose path is the clip shape and whose blend word / alpha are the layer's; implicit layers
+    (no clip, non-wiping mode) are numbered in the width word of their empty path's style."""
+    sc = S.Scene()
+    sc.PushLayer(S.BlendMultiply, 0.5, S.rect_verbs_coords(10, 10, 50, 40))      # mix 1, SrcOver
+    sc.Fill(S.FillNonZero, S.IDENTITY, (1, 0, 0, 1), S.rect_verbs_coords(0, 0, 30, 30))
+    sc.PopLayer()
+    sc.PushLayer(S.BlendCopy, 1.0, S.rect_verbs_coords(5, 5, 20, 20))            # wiping mode: never elided
+    sc.PopLayer()
+    sc.PushLayer(S.BlendScreen, 1.0, None)                                       # implicit layer 0
+    sc.PushLayer(S.BlendNormal, 0.7, None)                                       # implicit layer 1
+    sc.Fill(S.FillNonZero, S.IDENTITY, (0, 1, 0, 1), S.rect_verbs_coords(0, 0, 8, 8))
+    sc.PopLayer()
+    sc.PopLayer()
+    c = _lib.Context(-1)
+    c.begin(64, 64)
+    c.add_encoding(*sc.Encoding().streams())
+    words, lay = c.pack_host()
+    dt = list(words[lay["draw_tag_base"]:lay["draw_data_base"]])
+    assert dt == [0x9, 0x44, 0x21, 0x9, 0x21, 0x9, 0x9, 0x44, 0x21, 0x21]
+    dd = words[lay["draw_data_base"]:lay["transform_base"]]
+    assert int(dd[0]) == (1 << 8 | 3) | 0x80000000 and dd[1:2].view(np.float32)[0] == 0.5      # Multiply, droppable where empty
+    assert int(dd[3]) == 1 and dd[4:5].view(np.float32)[0] == 1.0                             # Copy: compose 1, always written
+    assert int(dd[5]) == (2 << 8 | 3) | 0xC0000000 and int(dd[7]) == 3 | 0xC0000000            # implicit layers
+    st = words[lay["style_base"]:lay["clip_aux_base"]].reshape(-1, 3)
+    assert int(st[5, 1]) == 0 and int(st[6, 1]) == 1                                         # their ordinals
+    pd = words[lay["path_data_base"]:lay["draw_tag_base"]].view(np.float32)
+    assert list(pd[:4]) == [10, 10, 50, 10]                                                  # the first clip's path is the clip shape
+    img, _ = T.render_packed(words, lay, 64, 64)
+    assert img[25, 25, 3] == 128 and img[35, 45, 3] == 0 and img[9, 9, 3] == 0              # the red fill shows inside its layer's clip only
+    assert img[12, 12, 3] == 0 and img[20, 20, 3] == 128      # the (empty) Copy layer wiped its clip's 15 x 15 px, not the rest of the tile
+    assert tuple(img[5, 5]) == (0, 179, 0, 179)               # green at the inner implicit layer's alpha
