@@ -193,14 +193,47 @@ def main():
     ctx.add_encoding(*streams)
     ctx.set_band(y0, y1)
     ctx.upload()
-    frame = bands.alloc_frame(w, h, world, "cuda")   # full canvas on every rank (all-gather target)
-    band = bands.band_view(frame, h, world, rank)     # fine writes its band straight into the gather buffer
+    # Full canvas on every rank. N > 1: a symmetric allocation -- fine stores its band into every rank's frame itself
+    # (NVSwitch multicast where offered, else peer stores) and a barrier replaces the all-gather; GG_BANDS=nccl keeps the
+    # all-gather (also the fallback if symmetric memory cannot be set up on this box).
+    sym, assemble_kind = None, "single"
+    if world > 1 and os.environ.get("GG_BANDS", "p2p") != "nccl":
+        try:
+            sym = bands.SymmetricFrame(w, h, world, rank, f"cuda:{local_rank}")
+            if os.environ.get("GG_BANDS") == "p2p_nomc":
+                sym.multicast = False
+            assemble_kind = "fine stores into all frames (multimem.st over NVSwitch multicast) + barrier" if sym.multicast else \
+                "fine stores into all frames (peer memory over NVLink) + barrier"
+        except Exception as e:   # noqa: BLE001
+            if rank == 0:
+                print(f"symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-gather", file=sys.stderr)
+            sym = None
+    if sym is not None:
+        ok = torch.tensor([1], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        frame, band = sym.frame, sym.band()
+    else:
+        frame = bands.alloc_frame(w, h, world, "cuda")
+        band = bands.band_view(frame, h, world, rank)     # fine writes its band straight into the gather buffer
+        if world > 1:
+            assemble_kind = "NCCL all_gather_into_tensor"
     stride = w * 4
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
+    e_mid = torch.cuda.Event(enable_timing=True)
+
     def step():
-        ctx.render_device(band.data_ptr(), stride, _lib.KEEP_SCENE)
-        bands.assemble(frame, h, world, rank)
+        if sym is not None:
+            if sym.multicast:
+                ctx.render_device_multi(band.data_ptr(), [sym.multicast_band], stride, _lib.KEEP_SCENE, multicast=True)
+            else:
+                ctx.render_device_multi(band.data_ptr(), sym.peer_bands, stride, _lib.KEEP_SCENE)
+            e_mid.record(stream)
+            sym.barrier()
+        else:
+            ctx.render_device(band.data_ptr(), stride, _lib.KEEP_SCENE)
+            e_mid.record(stream)
+            bands.assemble(frame, h, world, rank)
 
     for _ in range(args.warmup):
         step()
@@ -214,7 +247,7 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    total_ms, fine_ms, stage_ms = 0.0, 0.0, np.zeros(4)
+    total_ms, fine_ms, stage_ms, own_ms = 0.0, 0.0, np.zeros(4), 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     for _ in range(args.steps):
         flush_buf.fill_(1)          # L2 flush between timed iterations (not timed)
@@ -223,6 +256,7 @@ def main():
         e1.record(stream)
         torch.cuda.synchronize()
         total_ms += e0.elapsed_time(e1)
+        own_ms += e0.elapsed_time(e_mid)
         s = ctx.stats()
         fine_ms += s["ms_fine"]
         stage_ms += [s["ms_front"], s["ms_binning"], s["ms_coarse"], s["ms_fine"]]
@@ -230,9 +264,11 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, own_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    own_max_ms = float(t[1].item()) / args.steps   # slowest rank's own pipeline, before it waits for the others
+    t = t[:1]
     ms_per_step = float(t.item()) / args.steps
     value = w * h / 1e6 / (ms_per_step / 1e3)
 
@@ -261,6 +297,17 @@ def main():
         gbs = stage_bytes[k] / (ms / 1e3) / 1e9 if ms > 0 else 0.0
         stages[k] = {"ms": float(ms), "algorithmic_bytes": int(stage_bytes[k]), "achieved": gbs, "frac": gbs / peak}
     dom = max(stages, key=lambda k: stages[k]["ms"])
+    # DRAM bytes of the dominant stage's main kernel from the committed `ncu --set full` capture of this workload
+    # (profiles/*_traffic.json; null if that kernel was not captured)
+    traffic = None
+    try:
+        tj = json.load(open(sorted(p for p in (os.path.join(ROOT, "profiles", f) for f in os.listdir(os.path.join(ROOT, "profiles")))
+                                   if p.endswith("_traffic.json"))[-1]))
+        kname = {"front": "flatten_subdivide_kernel", "binning": "path_count_kernel", "coarse": "coarse_kernel", "fine": "fine_kernel"}[dom]
+        if world == 1 and kname in tj["kernels"]:
+            traffic = tj["kernels"][kname]["dram_bytes_read"] + tj["kernels"][kname]["dram_bytes_write"]
+    except Exception:
+        traffic = None
     dom_kernel = {"front": "flatten_subdivide_kernel + flatten_eseg_emit_kernel (+ classify, scans)", "binning": "path_count_kernel (+ backdrop, tiling)",
                   "coarse": "coarse_kernel (+ hit scan/scatter)", "fine": "fine_kernel"}[dom]
 
@@ -290,12 +337,13 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "config3_4k_10k_paths_blend_layers_clips", "width": w, "height": h, "bands": world,
+                       "band_assembly": assemble_kind, "rank_pipeline_ms_max": own_max_ms, "rank0_pipeline_ms": own_ms / args.steps,
                        "paths": int(st["n_draws"]), "l2": "flushed between timed iterations (256 MiB write)",
                        "frames_per_s": 1e3 / ms_per_step,
                        "stage_ms": {k: float(v / args.steps) for k, v in zip(("front", "binning", "coarse", "fine"), stage_ms)},
                        "counts": {k: int(st[k]) for k in ("n_lines", "n_path_tiles", "n_segments", "n_hits", "n_ptcl_words")}},
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "stage": dom, "achieved": stages[dom]["achieved"], "peak": peak,
-                         "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes": stages[dom]["algorithmic_bytes"], "kernel_ms": stages[dom]["ms"], "stages": stages,
                          "note": "every stage is issue/latency bound on this scene, not HBM bound; see profiles/"},
             "e2e": {"value": w * h / 1e6 / e2e_s, "unit": "Mpix/s", "ms_per_frame": e2e_s * 1e3,

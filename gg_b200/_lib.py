@@ -17,7 +17,7 @@ COMPOSITE_OVER, KEEP_SCENE = 1, 2
 SYMBOLS = [
     "ggcuda_create", "ggcuda_destroy", "ggcuda_last_error", "ggcuda_set_stream", "ggcuda_begin", "ggcuda_set_background",
     "ggcuda_set_band", "ggcuda_fill_path", "ggcuda_stroke_path", "ggcuda_push_clip", "ggcuda_push_layer", "ggcuda_pop",
-    "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_get_stats", "ggcuda_set_timing",
+    "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_render_device_multi", "ggcuda_get_stats", "ggcuda_set_timing",
     "ggcuda_debug_read", "ggcuda_pack_host",
 ]
 
@@ -83,6 +83,7 @@ def load():
     L.ggcuda_flush.argtypes = [vp, vp, sz, u32]
     L.ggcuda_upload.argtypes = [vp]
     L.ggcuda_render_device.argtypes = [vp, vp, sz, u32]
+    L.ggcuda_render_device_multi.argtypes = [vp, vp, vp, u32, C.c_int, sz, u32]
     L.ggcuda_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.ggcuda_set_timing.argtypes = [vp, C.c_int]
     L.ggcuda_debug_read.argtypes = [vp, C.c_int, vp, sz]
@@ -176,6 +177,11 @@ class Context:
 
     def render_device(self, dptr, stride, flags=0):
         self._ck(self.L.ggcuda_render_device(self.h, C.c_void_p(dptr), stride, flags))
+
+    def render_device_multi(self, dptr, mirrors, stride, flags=0, multicast=False):
+        """Band to `dptr` and to every address in `mirrors` (peer pointers, or one multicast address)."""
+        arr = (C.c_void_p * max(1, len(mirrors)))(*[C.c_void_p(int(m)) for m in mirrors])
+        self._ck(self.L.ggcuda_render_device_multi(self.h, C.c_void_p(dptr), arr, len(mirrors), 1 if multicast else 0, stride, flags))
 
     def pack_host(self):
         """(packed scene words, LAYOUT record) exactly as ggcuda_upload would send them; works on host-only contexts."""

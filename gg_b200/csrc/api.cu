@@ -56,6 +56,7 @@ struct Ctx {
     // Read-back target seen on consecutive flushes (gg keeps one pixmap per context): page-locked in place
     // from its second use so the band is DMA'd straight into it, without the staging copy.
     uint8_t* last_dst = nullptr; size_t last_dst_bytes = 0; bool dst_registered = false;
+    GGFineMirrors mirrors{};   // set for one render by ggcuda_render_device_multi
     ggcuda_stats stats{};
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -243,7 +244,7 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
         uint32_t parts = (host_dst && band_rows_t >= 4 * GG_FINE_PARTS) ? GG_FINE_PARTS : 1u;
         for (uint32_t k = 0; k < parts; k++) {
             uint32_t r0 = (uint32_t)((uint64_t)band_rows_t * k / parts), r1 = (uint32_t)((uint64_t)band_rows_t * (k + 1) / parts);
-            gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, r0, r1, k);
+            gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, r0, r1, k, c->mirrors);
             if (host_dst) {
                 uint32_t y0 = r0 * GG_TILE_H, y1 = std::min(r1 * GG_TILE_H, std::min(c->band_y1 * GG_TILE_H, c->height) - c->band_y0 * GG_TILE_H);
                 if (y1 > y0) {
@@ -500,6 +501,20 @@ int ggcuda_render_device(ggcuda_ctx* h, void* dst_device, size_t stride, uint32_
     if (!c || !dst_device) return c ? fail(c, GGCUDA_ERR_INVALID, "dst_device is NULL") : GGCUDA_ERR_INVALID;
     if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
     int r = render(c, (uint8_t*)dst_device, stride, flags);   // one fine launch, no host copy
+    if (r == 0 && !(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+    return r;
+}
+
+int ggcuda_render_device_multi(ggcuda_ctx* h, void* dst_device, void* const* mirrors, uint32_t n_mirrors, int multicast, size_t stride, uint32_t flags) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !dst_device || (n_mirrors && !mirrors)) return c ? fail(c, GGCUDA_ERR_INVALID, "null destination") : GGCUDA_ERR_INVALID;
+    if (n_mirrors > GG_MAX_MIRRORS || (multicast && n_mirrors != 1)) return fail(c, GGCUDA_ERR_INVALID, "bad mirror list");
+    if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
+    c->mirrors = GGFineMirrors{};
+    for (uint32_t i = 0; i < n_mirrors; i++) c->mirrors.p[i] = (uint8_t*)mirrors[i];
+    c->mirrors.n = n_mirrors; c->mirrors.multicast = multicast ? 1u : 0u;
+    int r = render(c, (uint8_t*)dst_device, stride, flags);
+    c->mirrors = GGFineMirrors{};
     if (r == 0 && !(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
     return r;
 }

@@ -328,7 +328,7 @@ __device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, c
 __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
-                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, uint32_t tile0, uint32_t tile1, uint32_t part) {
+                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, uint32_t tile0, uint32_t tile1, uint32_t part, GGFineMirrors mir) {
     // a stage overflowed its buffer: PTCL / segments are incomplete, the host re-runs the pass with larger buffers
     if (bump->failed || bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap || bump->segments > cfg.segments_cap) return;
     const uint32_t lane = threadIdx.x & 31;
@@ -488,6 +488,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
             uint32_t o[PX];
 #pragma unroll
             for (int i = 0; i < PX; i++) o[i] = pack_rgba8(rgba[i]);
+            const size_t off = (size_t)(py - cfg.band_y0 * GG_TILE_H) * stride + (size_t)px * 4;
             if (px + PX <= cfg.width && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
                 reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
                 reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -495,11 +496,37 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
 #pragma unroll
                 for (int i = 0; i < PX; i++) if (px + i < cfg.width) reinterpret_cast<uint32_t*>(out)[i] = o[i];
             }
+            // Multi-GPU: the band also goes straight into the other devices' frames (peer memory over NVLink / NVSwitch) while
+            // the rest of the band is still being rasterised -- the all-gather of bands, fused into the kernel that makes them.
+            if (mir.multicast) {   // one multimem store per 16 bytes: the switch replicates it to every device of the group
+                uint8_t* m = mir.p[0] + off;
+                if (px + PX <= cfg.width && ((reinterpret_cast<uintptr_t>(m) & 15u) == 0)) {
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m), "f"(__uint_as_float(o[0])), "f"(__uint_as_float(o[1])),
+                                 "f"(__uint_as_float(o[2])), "f"(__uint_as_float(o[3])) : "memory");
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m + 16), "f"(__uint_as_float(o[4])), "f"(__uint_as_float(o[5])),
+                                 "f"(__uint_as_float(o[6])), "f"(__uint_as_float(o[7])) : "memory");
+                } else {
+#pragma unroll
+                    for (int i = 0; i < PX; i++) if (px + i < cfg.width) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(m + 4 * i), "f"(__uint_as_float(o[i])) : "memory");
+                }
+            } else {
+                for (uint32_t k = 0; k < mir.n; k++) {
+                    uint8_t* m = mir.p[k] + off;
+                    if (px + PX <= cfg.width && ((reinterpret_cast<uintptr_t>(m) & 15u) == 0)) {
+                        reinterpret_cast<uint4*>(m)[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        reinterpret_cast<uint4*>(m)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < PX; i++) if (px + i < cfg.width) reinterpret_cast<uint32_t*>(m)[i] = o[i];
+                    }
+                }
+            }
         }
     }
 }
 
-void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part) {
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part,
+                    const GGFineMirrors& mir) {
     // tile rows [row0, row1) relative to the band; `part` selects the work cursor (each launch of a frame needs its own)
     uint32_t n_tiles = cfg.width_in_tiles * (row1 - row0);
     uint32_t blocks = (n_tiles + FINE_WARPS - 1) / FINE_WARPS;
@@ -509,5 +536,5 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
     fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride,
-                                                      cfg.width_in_tiles * row0, cfg.width_in_tiles * row1, part);
+                                                      cfg.width_in_tiles * row0, cfg.width_in_tiles * row1, part, mir);
 }

@@ -50,4 +50,9 @@ void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  
 void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s); // path_count, backdrop, seg alloc, path_tiling
 void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  // hit lists + PTCL
 // fine (fine.cu). dst: RGBA8 premultiplied, row stride in bytes; covers tile rows [band_y0, band_y1).
-void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part);
+// Further destinations of fine's band besides `dst`: the same band inside the frames of the other devices of a
+// multi-GPU group (peer pointers, same row stride), or ONE multicast address that reaches all of them.
+#define GG_MAX_MIRRORS 15
+struct GGFineMirrors { uint8_t* p[GG_MAX_MIRRORS]; uint32_t n; uint32_t multicast; };
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part,
+                    const GGFineMirrors& mir);

@@ -109,6 +109,13 @@ GGCUDA_API int ggcuda_flush(ggcuda_ctx* ctx, uint8_t* dst, size_t stride_bytes, 
  * dst_device addresses the first row of this context's BAND. */
 GGCUDA_API int ggcuda_upload(ggcuda_ctx* ctx);
 GGCUDA_API int ggcuda_render_device(ggcuda_ctx* ctx, void* dst_device, size_t stride_bytes, uint32_t flags);
+/* Multi-GPU form (bands assembled over NVLink): besides dst_device the band is stored, by the fine
+ * rasterisation kernel itself, at n_mirrors further addresses -- the first row of the same band inside the frames of the
+ * other devices (peer-mapped pointers, same stride), or, with multicast != 0, ONE NVSwitch multicast address (n_mirrors
+ * == 1) that reaches every device of the group. The caller synchronises the group afterwards (a barrier, not an
+ * all-gather). There is no counterpart in the reference (single device). */
+GGCUDA_API int ggcuda_render_device_multi(ggcuda_ctx* ctx, void* dst_device, void* const* mirrors, uint32_t n_mirrors, int multicast,
+                                          size_t stride_bytes, uint32_t flags);
 
 /* ---- introspection ---- */
 typedef struct {
