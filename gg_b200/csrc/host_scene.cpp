@@ -67,30 +67,25 @@ void HostScene::begin_path(const float t[6], bool even_odd) {
     styles.push_back(0); styles.push_back(0);
     in_path = true; has_move = false;
     memcpy(path_t, t, sizeof path_t);
-    path_bb[0] = path_bb[1] = 3.0e38f; path_bb[2] = path_bb[3] = -3.0e38f;
 }
-void HostScene::note_point(float, float) {}   // (content bounds are no longer needed: layers are implicit)
 void HostScene::move_to(float x, float y) {
     // An open subpath is closed implicitly, as every CPU filler in gg does (the Vello
     // path of the reference leaves it open, path_convert.go:44-49).
     if (has_move && (cur[0] != start[0] || cur[1] != start[1])) line_to(start[0], start[1]);
     tags.push_back(PT_MOVETO);
     path_data.push_back(x); path_data.push_back(y);
-    note_point(x, y);
     cur[0] = start[0] = x; cur[1] = start[1] = y; has_move = true;
 }
 void HostScene::line_to(float x, float y) {
     if (!has_move) return;   // path_convert.go:52-54
     tags.push_back(PT_LINETO);
     path_data.push_back(x); path_data.push_back(y);
-    note_point(x, y);
     cur[0] = x; cur[1] = y; n_seg_tags++;
 }
 void HostScene::quad_to(float cx, float cy, float x, float y) {
     if (!has_move) return;
     tags.push_back(PT_QUADTO);
     path_data.push_back(cx); path_data.push_back(cy); path_data.push_back(x); path_data.push_back(y);
-    note_point(cx, cy); note_point(x, y);
     cur[0] = x; cur[1] = y; n_seg_tags++;
 }
 void HostScene::cubic_to(float c1x, float c1y, float c2x, float c2y, float x, float y) {
@@ -98,7 +93,6 @@ void HostScene::cubic_to(float c1x, float c1y, float c2x, float c2y, float x, fl
     tags.push_back(PT_CUBICTO);
     path_data.push_back(c1x); path_data.push_back(c1y); path_data.push_back(c2x); path_data.push_back(c2y);
     path_data.push_back(x); path_data.push_back(y);
-    note_point(c1x, c1y); note_point(c2x, c2y); note_point(x, y);
     cur[0] = x; cur[1] = y; n_seg_tags++;
 }
 void HostScene::close() {   // path_convert.go:86-92

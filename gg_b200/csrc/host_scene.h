@@ -44,8 +44,6 @@ struct HostScene {
     bool in_path = false, has_move = false;
     float cur[2] = {0, 0}, start[2] = {0, 0};
     float path_t[6] = {1, 0, 0, 0, 1, 0};
-    float path_bb[4] = {0, 0, 0, 0};     // device-space control-point bbox of the path being built
-    void note_point(float x, float y);
 
     void clear(uint32_t w, uint32_t h);
     uint32_t n_draws() const { return (uint32_t)draw_tags.size(); }
