@@ -381,3 +381,86 @@ def test_push_layer_with_clip_is_one_clip():
     assert img[25, 25, 3] == 128 and img[35, 45, 3] == 0 and img[9, 9, 3] == 0              # the red fill shows inside its layer's clip only
     assert img[12, 12, 3] == 0 and img[20, 20, 3] == 128      # the (empty) Copy layer wiped its clip's 15 x 15 px, not the rest of the tile
     assert tuple(img[5, 5]) == (0, 179, 0, 179)               # green at the inner implicit layer's alpha
+
+
+def test_ingest_survives_malformed_encodings():
+    """Random tag / data streams (short streams, NaNs, unbalanced clips and layers, unknown nesting): add_encoding answers
+    with an error or a well-formed packed scene, never a crash (every stream access is bounds-checked, scene/decoder.go does
+    the same for the CPU renderer)."""
+    rng = np.random.default_rng(1)
+    tags_pool = [0x01, 0x02, 0x10, 0x11, 0x12, 0x13, 0x14, 0x16, 0x17, 0x20, 0x21, 0x22, 0x30, 0x31, 0x40, 0x41, 0x50]
+    c = _lib.Context(-1)
+    ok = err = 0
+    for _ in range(800):
+        tags = rng.choice(tags_pool, int(rng.integers(0, 60))).astype(np.uint8)
+        pd = rng.uniform(-50, 300, int(rng.integers(0, 80))).astype(np.float32)
+        if rng.random() < 0.1 and len(pd):
+            pd[rng.integers(0, len(pd), 3)] = np.nan
+        dd = rng.integers(0, 2 ** 32, int(rng.integers(0, 40)), dtype=np.uint64).astype(np.uint32)
+        tr = rng.uniform(-2, 2, 6 * int(rng.integers(0, 4))).astype(np.float32)
+        br = rng.uniform(0, 1, 4 * int(rng.integers(0, 5)))
+        c.begin(int(rng.integers(1, 300)), int(rng.integers(1, 300)))
+        try:
+            c.add_encoding(tags, pd, dd, tr, br)
+        except _lib.GGCudaError as e:
+            assert e.code in (_lib.ERR_INVALID, _lib.ERR_UNSUPPORTED)
+            err += 1
+            continue
+        words, lay = c.pack_host()
+        assert lay["n_scene_words"] == len(words) and lay["n_draws"] == lay["n_paths"]     # one path marker per draw object
+        ok += 1
+    assert ok > 100 and err > 100
+
+
+def test_random_scenes_pack_and_render():
+    """Structured random scenes with every degenerate the ingest rules name (empty paths, repeated points, collapsed curves,
+    zero-width and huge strokes, unbalanced pops, clips of empty paths): packed scenes the CPU twin renders without incident."""
+    rng = np.random.default_rng(2)
+    c = _lib.Context(-1)
+
+    def rand_path():
+        v, co = [], []
+        for _ in range(int(rng.integers(0, 7))):
+            k = int(rng.choice([S.MOVE, S.LINE, S.LINE, S.QUAD, S.CUBIC, S.CLOSE]))
+            m = {S.MOVE: 2, S.LINE: 2, S.QUAD: 4, S.CUBIC: 6, S.CLOSE: 0}[k]
+            pts = rng.uniform(-20, 90, m)
+            if rng.random() < 0.2 and m >= 2 and len(co) >= 2:
+                pts[:2] = co[-2:]
+            if rng.random() < 0.1 and m:
+                pts[:] = pts[0]
+            v.append(k)
+            co += list(pts)
+        return v, co
+    rendered = 0
+    for _ in range(250):
+        sc, depth = S.Scene(), 0
+        for _ in range(int(rng.integers(1, 12))):
+            r = rng.random()
+            t = S.IDENTITY if rng.random() < 0.7 else tuple(rng.uniform(-1.5, 1.5, 6))
+            col = tuple(rng.uniform(0, 1, 4))
+            if r < 0.35:
+                sc.Fill(int(rng.integers(0, 2)), t, col, rand_path())
+            elif r < 0.7:
+                sc.Stroke(dict(width=float(rng.choice([0, 0.01, 1, 5, 40])), miter_limit=float(rng.choice([0, 1, 4, 100])),
+                               cap=int(rng.integers(0, 3)), join=int(rng.integers(0, 3))), t, col, rand_path())
+            elif r < 0.8:
+                sc.PushLayer(int(rng.integers(0, 29)), float(rng.uniform(0, 1)), rand_path() if rng.random() < 0.5 else None)
+                depth += 1
+            elif r < 0.88 and depth:
+                sc.PopLayer()
+                depth -= 1
+            elif r < 0.94:
+                sc.PushClip(rand_path(), t)
+            else:
+                sc.PopClip()
+        w, h = int(rng.integers(1, 80)), int(rng.integers(1, 80))
+        c.begin(w, h)
+        try:
+            c.add_encoding(*sc.Encoding().streams())
+        except _lib.GGCudaError:
+            continue
+        words, lay = c.pack_host()
+        img, _ = T.render_packed(words, lay, w, h)
+        assert img.shape == (h, w, 4)
+        rendered += 1
+    assert rendered > 200

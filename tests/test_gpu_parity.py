@@ -420,3 +420,55 @@ def test_config5_16k_one_million_paths(ctx):
     ref, _ = T.render_packed(words, lay, crop, crop, (0, 0, 0, 0), os.cpu_count())
     d = np.abs(full[:crop, :crop].astype(np.int32) - ref.astype(np.int32))
     assert d.max() <= 1 and (d.max(axis=-1) > 0).mean() <= 0.002, (d.max(), (d.max(axis=-1) > 0).mean())
+
+
+def test_degenerate_random_scenes(ctx):
+    """The structured random scenes of test_cpu_host.test_random_scenes_pack_and_render (empty paths, repeated points,
+    collapsed curves, zero-width and huge strokes, unbalanced pops, clips of empty paths, all 29 layer modes, transforms)
+    on the device: every stage against the oracle."""
+    from gg_b200 import scene as S
+    rng = np.random.default_rng(2)
+
+    def rand_path():
+        v, co = [], []
+        for _ in range(int(rng.integers(0, 7))):
+            k = int(rng.choice([S.MOVE, S.LINE, S.LINE, S.QUAD, S.CUBIC, S.CLOSE]))
+            m = {S.MOVE: 2, S.LINE: 2, S.QUAD: 4, S.CUBIC: 6, S.CLOSE: 0}[k]
+            pts = rng.uniform(-20, 90, m)
+            if rng.random() < 0.2 and m >= 2 and len(co) >= 2:
+                pts[:2] = co[-2:]
+            if rng.random() < 0.1 and m:
+                pts[:] = pts[0]
+            v.append(k)
+            co += list(pts)
+        return v, co
+    done = 0
+    for _ in range(120):
+        sc, depth = S.Scene(), 0
+        for _ in range(int(rng.integers(1, 12))):
+            r = rng.random()
+            t = S.IDENTITY if rng.random() < 0.7 else tuple(rng.uniform(-1.5, 1.5, 6))
+            col = tuple(rng.uniform(0, 1, 4))
+            if r < 0.35:
+                sc.Fill(int(rng.integers(0, 2)), t, col, rand_path())
+            elif r < 0.7:
+                sc.Stroke(dict(width=float(rng.choice([0, 0.01, 1, 5, 40])), miter_limit=float(rng.choice([0, 1, 4, 100])),
+                               cap=int(rng.integers(0, 3)), join=int(rng.integers(0, 3))), t, col, rand_path())
+            elif r < 0.8:
+                sc.PushLayer(int(rng.integers(0, 29)), float(rng.uniform(0, 1)), rand_path() if rng.random() < 0.5 else None)
+                depth += 1
+            elif r < 0.88 and depth:
+                sc.PopLayer()
+                depth -= 1
+            elif r < 0.94:
+                sc.PushClip(rand_path(), t)
+            else:
+                sc.PopClip()
+        w, h = int(rng.integers(1, 80)), int(rng.integers(1, 80))
+        try:
+            _check_encoding(ctx, sc.Encoding(), w, h)
+        except G.GGCudaError as e:
+            assert e.code in (G.ERR_INVALID, G.ERR_UNSUPPORTED)
+            continue
+        done += 1
+    assert done > 100
