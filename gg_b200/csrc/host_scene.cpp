@@ -390,7 +390,7 @@ void HostScene::pack(uint32_t* out, Layout* L, uint32_t band_tiles) const {   //
 // ------------------------------------------------------------------ scene.Encoding ingest
 static void emit_round_rect(HostScene* s, float x0, float y0, float x1, float y1, float rx, float ry) {
     // scene/path.go rounded rectangle with kappa arcs; TagFillRoundRect is SDF-rendered by the
-    // CPU oracle (scene/renderer.go:986-1071) -- exact-area rendering of the same outline here.
+    // CPU renderer of the reference (scene/renderer.go:986-1071) -- exact-area rendering of the same outline here.
     const float k = 0.5522847498f;
     float w = x1 - x0, h = y1 - y0;
     if (rx > w * 0.5f) rx = w * 0.5f;
