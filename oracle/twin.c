@@ -1433,9 +1433,11 @@ void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment 
             for (int i = 0; i < PC; i++) rgba[i][0] = rgba[i][1] = rgba[i][2] = rgba[i][3] = 0;
             break;
         case CMD_END_CLIP: {
-            /* cmds[off] = blend word. The reference ignores it (fine.go:164: source-over only); ggcuda defines
-             * the layer composite as ot_blend_f32 (oracle/blend.c), which reduces to the reference's
-             * saved*(1-fg.a)+fg for the words the reference can emit (0 and 0x8003). */
+            /* cmds[off] = blend word. The reference carries whatever SceneElement.BlendMode holds (scene_encode.go:233) and
+             * its fine stage ignores it (fine.go:164: source-over only). ggcuda gives the word a meaning -- (mix << 8) |
+             * compose, composite defined by ot_blend_f32 (oracle/blend.c) -- so the reference's own clip vectors, written
+             * with blend 0, correspond to 0x8003 (clip) or 3 (Normal / SrcOver) here, for which ot_blend_f32 is exactly the
+             * reference's saved*(1-fg.a)+fg; 0 itself is BlendClear. */
             uint32_t blend = cmds[off];
             float alpha = bits_f32(cmds[off + 1]);
             off += 2;

@@ -125,6 +125,17 @@ def test_fine_clip_depths():
     assert np.allclose(out[0], [0, 1, 0, 1], atol=1e-5)
 
 
+def test_fine_tile_clip_vector():
+    """fine_ptcl_test.go:150-189 TestFineRasterizeTileClip: Solid, BeginClip, Solid + green, EndClip(alpha .5) over white gives
+    (0.5, 1, 0.5, 1). The reference writes blend word 0 and its fine ignores the word; here the word selects the composite
+    and source-over is 0x8003 (clip) or 3 (Normal layer) -- word 0 is scene.BlendClear."""
+    half = int(np.float32(0.5).view(np.uint32))
+    empty = np.zeros(0, dtype=T.SEGMENT)
+    for blend, want in ((0x8003, [0.5, 1, 0.5, 1]), (3, [0.5, 1, 0.5, 1]), (0, [0, 0, 0, 0])):
+        w = np.array([0, 3, 10, 3, 5, 0xFF00FF00, 11, blend, half, 0], dtype=np.uint32)
+        assert np.allclose(T.fine_tile(w, empty, (1, 1, 1, 1))[0], want, atol=1e-6), hex(blend)
+
+
 def test_clip_scene_zero_depth_and_bbox():
     """clip_integration_test.go:24-326: content outside the clip's bbox or in its empty tiles is suppressed, inside it is kept."""
     clip = T.polygon_lines([(16, 16), (48, 16), (48, 48), (16, 48)])
@@ -218,3 +229,233 @@ def test_exact_area_vs_gg_cpu_aaa(name):
     assert d.mean() <= 0.6
     assert (d <= 2).mean() >= 0.975
     assert d.max() <= 60          # quarter-pixel snapping of a horizontal edge: up to ~0.125 * 255 per edge, 2 edges at a corner
+
+
+# ---- the reference's scene-encoding tests, one for one (tilecompute/scene_encode_test.go) ----
+def _encode(paths):
+    e, l = T.make_elements([dict(lines=T.polygon_lines(p) if isinstance(p, list) else p, color=c, even_odd=eo) for p, c, eo in paths])
+    return T.Coarse(e, l, 100, 100)
+
+
+def _tag_bytes(c):
+    L = c.layout
+    return c.scene[L["path_tag_base"]:L["path_data_base"]].view(np.uint8)
+
+
+def test_encode_scene_single_path():
+    """TestEncodeSceneSinglePath (:14-83) + TestPackScene (:172-237) + TestPackPathTags (:553-595, the four_tags vector)."""
+    c = _encode([([(10, 10), (90, 50), (10, 90)], (255, 0, 0, 255), 0)])
+    L = c.layout
+    assert (L["n_paths"], L["n_draw_objects"]) == (1, 1)
+    assert L["path_tag_base"] == 0 and (L["path_data_base"] - L["path_tag_base"]) % 256 == 0 and L["path_data_base"] >= 256
+    assert list(c.scene[L["draw_tag_base"]:L["draw_data_base"]]) == [0x44]
+    assert list(c.scene[L["draw_data_base"]:L["transform_base"]]) == [0xFF0000FF]
+    assert list(c.scene[L["transform_base"]:L["style_base"]].view(np.float32)) == [1, 0, 0, 1, 0, 0]
+    assert list(c.scene[L["style_base"]:]) == [0]
+    pd = c.scene[L["path_data_base"]:L["draw_tag_base"]]
+    assert L["draw_tag_base"] == L["path_data_base"] + len(pd) and L["draw_data_base"] == L["draw_tag_base"] + 1
+    assert len(c.scene) == L["path_data_base"] + len(pd) + 1 + 1 + 6 + 1             # TestPackScene: total size
+    assert list(pd.view(np.float32)) == [10, 10, 90, 50, 10, 90, 10, 10]          # 4 + 2 + 2 floats for the connected triangle
+    assert int(c.scene[0]) == 0x09094020                                          # Transform, Style, LineTo, LineTo packed 4 per word
+    assert list(_tag_bytes(c)[:7]) == [0x20, 0x40, 0x09, 0x09, 0x09, 0x09, 0x10]   # the first point travels as a LineTo too (scene_encode.go:186-215)
+
+
+def test_encode_scene_multi_path_and_even_odd():
+    """TestEncodeSceneMultiPath (:85-169) and TestEncodeSceneEvenOddStyle (:653-671)."""
+    c = _encode([([(10, 10), (30, 10), (30, 30), (10, 30)], (255, 0, 0, 255), 0),
+                 ([(40, 10), (60, 50), (40, 50)], (0, 255, 0, 255), 0),
+                 ([(70, 10), (90, 10), (90, 30), (70, 30)], (0, 0, 255, 128), 1)])
+    L = c.layout
+    assert (L["n_paths"], L["n_draw_objects"]) == (3, 3)
+    assert list(c.scene[L["draw_tag_base"]:L["draw_data_base"]]) == [0x44] * 3
+    dd = c.scene[L["draw_data_base"]:L["transform_base"]]
+    assert len(dd) == 3
+    blue = int(dd[2])
+    assert (blue & 0xFF, (blue >> 8) & 0xFF, blue >> 24) == (0, 0, 128) and 127 <= (blue >> 16) & 0xFF <= 129
+    assert L["style_base"] - L["transform_base"] == 18
+    assert list(c.scene[L["style_base"]:]) == [0, 0, 2]
+    c = _encode([([(50, 10), (75, 90), (10, 40), (90, 40), (25, 90)], (128, 0, 0, 255), 1)])
+    assert list(c.scene[c.layout["style_base"]:]) == [2]
+
+
+def test_pathtag_and_draw_scans():
+    """TestPathtagReduceScan (:346-415), TestDrawReduceScan (:472-550), TestSceneRoundTrip (:674-733)."""
+    c = _encode([([(10, 10), (50, 50), (10, 50)], (255, 0, 0, 255), 0), ([(60, 10), (90, 10), (90, 40), (60, 40)], (0, 0, 255, 255), 0)])
+    tm = c.tag_monoids
+    assert tuple(tm[0]) == (0, 0, 0, 0, 0)                                        # exclusive prefix starts at the identity
+    for f in ("trans_ix", "path_seg_ix", "path_ix", "style_ix"):
+        assert (np.diff(tm[f].astype(np.int64)) >= 0).all()                       # monotone
+    words = c.scene[c.layout["path_tag_base"]:c.layout["path_data_base"]]
+    last = T.path_monoid(int(words[len(tm) - 1]))
+    total = {f: int(tm[f][-1]) + int(last[f]) for f in tm.dtype.names}
+    assert (total["trans_ix"], total["style_ix"], total["path_ix"]) == (2, 2, 2) and total["path_seg_ix"] == 4 + 5     # every point of a closed polygon is a LineTo tag, the first one included
+    c = _encode([([(10, 10), (50, 50), (10, 50)], (255, 0, 0, 255), 0), ([(60, 10), (90, 10), (90, 40), (60, 40)], (0, 255, 0, 255), 0),
+                 ([(20, 60), (80, 60), (50, 90)], (0, 0, 255, 128), 1)])
+    dm = c.draw_monoids
+    assert len(dm) == 3 and tuple(dm[0]) == (0, 0, 0, 0)
+    assert (int(dm[1]["path_ix"]), int(dm[1]["scene_offset"])) == (1, 1) and (int(dm[2]["path_ix"]), int(dm[2]["scene_offset"])) == (2, 2)
+    dd = c.scene[c.layout["draw_data_base"]:c.layout["transform_base"]]
+    assert len(c.info) == 3 and list(c.info) == list(dd)
+    b = int(c.info[2])
+    assert (b & 0xFF, (b >> 8) & 0xFF, b >> 24) == (0, 0, 128) and 127 <= (b >> 16) & 0xFF <= 129
+    c = _encode([(T.flatten_fill(T.circle_cubics(50, 50, 20)), (255, 128, 0, 255), 0), ([(10, 10), (90, 10), (90, 90), (10, 90)], (0, 128, 255, 200), 1)])
+    assert len(c.draw_monoids) == 2 and len(c.info) == 2 and len(c.tag_monoids) == c.layout["path_data_base"] - c.layout["path_tag_base"]
+
+
+# ---- the reference's coarse tests, one for one (tilecompute/coarse_test.go:172-441) ----
+def _cmds(ptcl):
+    """[(tag, payload words...)] of one tile's PTCL (ptcl.go:17-177 word layout)."""
+    out, o = [], 1
+    size = {0: 1, 1: 4, 3: 1, 5: 2, 10: 1, 11: 3}
+    while o < len(ptcl):
+        t = int(ptcl[o])
+        out.append((t, *[int(w) for w in ptcl[o + 1:o + size[t]]]))
+        o += size[t]
+        if t == 0:
+            break
+    return out
+
+
+def test_coarse_single_triangle_multi_path_allocation():
+    """TestCoarseRasterizeSingleTriangle (:172-214), TestCoarseRasterizeMultiPath (:218-259), TestCoarseTileAllocation (:262-313)."""
+    e, l = T.make_elements([dict(lines=T.polygon_lines([(5, 5), (27, 5), (16, 27)]), color=(255, 0, 0, 255))])
+    c = T.Coarse(e, l, 32, 32)
+    assert (c.wt, c.ht) == (2, 2)
+    with_cmds = [t for t in range(4) if len(c.ptcl(t)) > 2]
+    assert with_cmds and any(any(a[0] in (1, 3) and b[0] == 5 for a, b in zip(_cmds(c.ptcl(t)), _cmds(c.ptcl(t))[1:])) for t in with_cmds)
+    red, blue = T.polygon_lines([(0, 0), (32, 0), (32, 32), (0, 32)]), T.polygon_lines([(0, 0), (16, 0), (16, 16), (0, 16)])
+    e, l = T.make_elements([dict(lines=red, color=(255, 0, 0, 255)), dict(lines=blue, color=(0, 0, 255, 255))])
+    c = T.Coarse(e, l, 32, 32)
+    colors = [cmd[1] for cmd in _cmds(c.ptcl(0)) if cmd[0] == 5]
+    assert colors[:2] == [0xFF0000FF, 0xFFFF0000]                                # scene order: red, then blue
+    e, l = T.make_elements([dict(lines=T.polygon_lines([(2, 2), (10, 2), (10, 10), (2, 10)]), color=(255, 0, 0, 255)),
+                            dict(lines=T.polygon_lines([(5, 5), (25, 5), (25, 25), (5, 25)]), color=(0, 255, 0, 255))])
+    c = T.Coarse(e, l, 32, 32)
+    b0, b1 = c.paths[0]["bbox"], c.paths[1]["bbox"]
+    assert (b0[2] - b0[0]) * (b0[3] - b0[1]) == 1 and (b1[2] - b1[0]) * (b1[3] - b1[1]) >= 4
+    assert c.paths[1]["tiles"] > c.paths[0]["tiles"]
+
+
+def test_coarse_empty_solid_evenodd_nolines():
+    """TestCoarseEmptyTiles (:316-340), TestCoarseBackdropSolid (:344-395), TestCoarseEvenOdd (:399-425), TestCoarseNoLines (:428-441)."""
+    e, l = T.make_elements([dict(lines=T.polygon_lines([(1, 1), (10, 1), (5, 10)]), color=(255, 0, 0, 255))])
+    c = T.Coarse(e, l, 64, 64)
+    assert (c.wt, c.ht) == (4, 4) and list(c.ptcl(3 * 4 + 3)) == [0, 0]           # blend offset + CmdEnd
+    e, l = T.make_elements([dict(lines=T.polygon_lines([(0, 0), (48, 0), (48, 48), (0, 48)]), color=(0, 255, 0, 255))])
+    c = T.Coarse(e, l, 48, 48)
+    assert [cmd[0] for cmd in _cmds(c.ptcl(1 * 3 + 1))] == [3, 5, 0]              # centre tile: CmdSolid, CmdColor, CmdEnd
+    star = [(16, 1), (20, 14), (30, 14), (22, 22), (26, 31), (16, 25), (6, 31), (10, 22), (2, 14), (12, 14)]
+    e, l = T.make_elements([dict(lines=T.polygon_lines(star), color=(128, 0, 0, 255), even_odd=1)])
+    c = T.Coarse(e, l, 32, 32)
+    fills = [cmd for t in range(4) for cmd in _cmds(c.ptcl(t)) if cmd[0] == 1]
+    assert fills and all(f[1] & 1 for f in fills)                                # even-odd flag in every CmdFill
+    e, l = T.make_elements([])
+    c = T.Coarse(e, l, 32, 32)
+    assert all(list(c.ptcl(t)) == [0, 0] for t in range(4))
+
+
+# ---- the reference's clip scenes, one for one (tilecompute/clip_integration_test.go) ----
+def _rect(x0, y0, x1, y1):
+    return T.polygon_lines([(x0, y0), (x1, y0), (x1, y1), (x0, y1)])
+
+
+def _clip(lines, alpha=1.0):
+    return dict(type=T.ELEM_BEGIN_CLIP, lines=lines, blend=0x8003, alpha=alpha)
+
+
+def test_clip_scene_integration_nested_alpha():
+    """TestClipSceneIntegration (:24-75), TestClipSceneNestedClip (:78-149), TestClipSceneAlpha (:152-195): straight-alpha
+    RGBA8 of RasterizeSceneDefPTCL over a white background."""
+    white = (255, 255, 255, 255)
+    e, l = T.make_elements([dict(lines=_rect(0, 0, 64, 64), color=(0, 255, 0, 255)), _clip(_rect(16, 16, 48, 48)),
+                            dict(lines=_rect(0, 0, 64, 64), color=(255, 0, 0, 255)), dict(type=T.ELEM_END_CLIP)])
+    s, _ = T.Coarse(e, l, 64, 64).fine(white)
+    assert tuple(s[32, 32]) == (255, 0, 0, 255) and tuple(s[4, 4]) == (0, 255, 0, 255)
+    e, l = T.make_elements([dict(lines=_rect(0, 0, 64, 64), color=(0, 0, 255, 255)), _clip(_rect(8, 8, 56, 56)),
+                            dict(lines=_rect(0, 0, 64, 64), color=(0, 255, 0, 255)), _clip(_rect(20, 20, 44, 44)),
+                            dict(lines=_rect(0, 0, 64, 64), color=(255, 0, 0, 255)), dict(type=T.ELEM_END_CLIP), dict(type=T.ELEM_END_CLIP)])
+    s, _ = T.Coarse(e, l, 64, 64).fine(white)
+    assert tuple(s[32, 32]) == (255, 0, 0, 255) and tuple(s[12, 12]) == (0, 255, 0, 255) and tuple(s[2, 2]) == (0, 0, 255, 255)
+    e, l = T.make_elements([_clip(_rect(0, 0, 32, 32), alpha=0.5), dict(lines=_rect(0, 0, 32, 32), color=(255, 0, 0, 255)), dict(type=T.ELEM_END_CLIP)])
+    s, _ = T.Coarse(e, l, 32, 32).fine(white)
+    assert tuple(s[16, 16]) == (255, 128, 128, 255)      # white * 0.5 + red * 0.5
+
+
+def test_clip_scene_def_encoding_and_fixup():
+    """TestEncodeSceneDefBasic (:220-281), TestClipLeafScan (:198-218): draw tags Color / BeginClip / Color / EndClip, the clip
+    pair counted as two clip inputs, blend word and alpha bits in the draw data, and the EndClip monoid patched with its
+    BeginClip's path index and scene offset."""
+    e, l = T.make_elements([dict(lines=_rect(0, 0, 64, 64), color=(0, 255, 0, 255)), _clip(_rect(16, 16, 48, 48)),
+                            dict(lines=_rect(0, 0, 64, 64), color=(255, 0, 0, 255)), dict(type=T.ELEM_END_CLIP)])
+    c = T.Coarse(e, l, 64, 64)
+    L = c.layout
+    assert list(c.scene[L["draw_tag_base"]:L["draw_data_base"]]) == [0x44, 0x9, 0x44, 0x21]
+    assert L["n_draw_objects"] == 4 and L["n_clips"] == 2
+    dd = c.scene[L["draw_data_base"]:L["transform_base"]]
+    assert int(dd[1]) == 0x8003 and dd[2:3].view(np.float32)[0] == 1.0
+    dm = c.draw_monoids
+    assert int(dm[3]["path_ix"]) == int(dm[1]["path_ix"]) and int(dm[3]["scene_offset"]) == int(dm[1]["scene_offset"])   # clip_leaf.go:48-51
+
+
+def test_fine_clip_vectors():
+    """fine_clip_test.go:14-160, the PTCLs of TestFineRasterizeClip / NestedClip / DeepClip word for word (their EndClip blend
+    word 0 written as 0x8003, see test_fine_tile_clip_vector): red 50 % in a clip over white -> (1, .498, .498, 1); five nested
+    clips, each over a red solid, blue innermost -> blue."""
+    empty = np.zeros(0, dtype=T.SEGMENT)
+    one = int(np.float32(1.0).view(np.uint32))
+
+    def rgba(r, g, b, a):
+        return r | g << 8 | b << 16 | a << 24
+    w = [0, 3, 5, rgba(255, 255, 255, 255), 10, 3, 5, rgba(128, 0, 0, 128), 11, 0x8003, one, 0]
+    px = T.fine_tile(np.array(w, dtype=np.uint32), empty, (1, 1, 1, 1))[8 * 16 + 8]
+    a = np.float32(128) / np.float32(255)
+    assert np.allclose(px, [1.0, 1 - a, 1 - a, 1.0], atol=1e-6)
+    w = [0] + [3, 5, rgba(255, 0, 0, 255), 10] * 5 + [3, 5, rgba(0, 0, 255, 255)] + [11, 0x8003, one] * 5 + [0]
+    px = T.fine_tile(np.array(w, dtype=np.uint32), empty, (1, 1, 1, 1))[8 * 16 + 8]
+    assert np.allclose(px, [0, 0, 1, 1], atol=1e-6)       # blend-stack depth 5 > BlendStackSplit 4 (ptcl.go:31): spilled levels
+
+
+def test_ptcl_pipeline_matches_per_path_pipeline():
+    """fine_ptcl_test.go:193-410 TestRasterizeScenePTCL{SinglePath,MultiPath,MatchesExisting} and clip_integration_test.go:284-326:
+    the PTCL pipeline and the per-path pipeline (RasterizeScene) agree within 1/255 on the reference's scenes."""
+    scenes_ = [
+        [dict(lines=T.polygon_lines([(10, 10), (54, 32), (10, 54)]), color=(255, 0, 0, 255))],
+        [dict(lines=_rect(0, 0, 32, 32), color=(255, 0, 0, 255)), dict(lines=_rect(8, 8, 24, 24), color=(0, 0, 255, 128))],
+        [dict(lines=T.flatten_fill(T.circle_cubics(32, 32, 25)), color=(0, 200, 0, 255)), dict(lines=T.polygon_lines(STAR), color=(128, 0, 0, 200), even_odd=1)],
+    ]
+    for sc in scenes_:
+        e, l = T.make_elements(sc)
+        a = T.rasterize_scene(WHITE, e, l, 64, 64)
+        b, _ = T.Coarse(e, l, 64, 64).fine(WHITE)
+        assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+
+
+def test_exact_area_vs_gg_cpu_multicontour_folder():
+    """internal/raster/multicontour_golden_test.go:16-110: the stroke-expanded folder outline (two contours, 11 quads) filled
+    NonZero. `multicontour-fill-20x20.png` is gg's CPU output (its test demands diff == 0), `stroke-expanded-fill-20x20.png`
+    Skia's; gg documents 21 pixels differing from Skia by up to 25 on the quad corners and none on straight edges. Exact-area
+    coverage through the same compositing formula (:291-319): straight edges identical to both, the curve-corner pixels within
+    the same band."""
+    from gg_b200 import _lib, scene as S
+    verbs = [0, 1, 1, 1, 1, 1, 2, 1, 2, 1, 2, 1, 2, 1, 2, 1, 4,
+             0, 1, 2, 1, 2, 2, 1, 2, 1, 2, 1, 2, 1, 1, 1, 4]
+    pts = [10.84, 5.1921, 11.0486, 5.3659, 10.7285, 5.75, 10.7285, 5.25, 11, 5.25, 17, 5.25, 18.75, 5.25, 18.75, 7, 18.75, 15.1667,
+           18.75, 17.25, 16.75, 17.25, 3.25, 17.25, 1.25, 17.25, 1.25, 15.1667, 1.25, 4.8333, 1.25, 2.75, 3.25, 2.75, 7.6379, 2.75,
+           7.9095, 2.75, 8.1181, 2.9238, 10.84, 5.1921, 10.1998, 5.9603, 7.4779, 3.6921, 7.5475, 3.75, 7.6379, 3.75, 3.25, 3.75,
+           2.8507, 3.75, 2.5579, 4.052, 2.25, 4.3696, 2.25, 4.8333, 2.25, 15.1667, 2.25, 16.25, 3.25, 16.25, 16.75, 16.25,
+           17.75, 16.25, 17.75, 15.1667, 17.75, 7, 17.75, 6.25, 17, 6.25, 11, 6.25, 10.5475, 6.25, 10.1998, 5.9603]
+    c = _lib.Context(-1)
+    c.begin(20, 20)
+    c.fill_path(verbs, pts, (255, 255, 255, 255), 0)
+    words, lay = c.pack_host()
+    img, _ = T.render_packed(words, lay, 20, 20)
+    cov = img[..., 3].astype(np.uint16)
+    bg, fg = np.array([0x3C, 0x3F, 0x41], np.uint16), np.array([0xCE, 0xD0, 0xD6], np.uint16)
+    scale = cov + 1
+    src = (fg[None, None, :] * scale[..., None]) >> 8
+    srca = (0xFF * scale) >> 8
+    out = np.where(cov[..., None] == 0, bg[None, None, :], (src + ((bg[None, None, :] * ((255 - srca) + 1)[..., None]) >> 8)) & 0xFF).astype(int)
+    for name, max_allowed in (("multicontour-fill-20x20", 32), ("stroke-expanded-fill-20x20", 20)):   # measured: max 29 / 18, mean 1.21 / 0.98
+        g = np.array(Image.open(os.path.join(HERE, "golden", "skia-aaa", name + ".png")).convert("RGBA"))[..., :3].astype(int)
+        d = np.abs(out - g).max(-1)
+        assert d.mean() <= 1.5 and (d <= 2).mean() >= 0.85 and d.max() <= max_allowed, (name, d.mean(), d.max(), (d <= 2).mean())
