@@ -170,6 +170,9 @@ class Context:
         """dst: (H, W, 4) uint8 premultiplied RGBA (GPURenderTarget.Data)."""
         assert dst.dtype == np.uint8 and dst.flags.c_contiguous
         stride = stride or dst.strides[0]
+        # the library page-locks a target it sees twice in a row (cudaHostRegister) and keeps it registered until another
+        # one shows up: the array must not be freed (and its address re-used) meanwhile, so the context holds on to it
+        self._flush_target = dst
         self._ck(self.L.ggcuda_flush(self.h, _p(dst), stride, flags))
 
     def upload(self):

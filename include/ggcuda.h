@@ -105,6 +105,9 @@ GGCUDA_API int ggcuda_add_encoding(ggcuda_ctx* ctx, const uint8_t* tags, size_t 
 /* Upload the scene, run the pipeline, read the band back into dst (premultiplied RGBA8,
  * GPURenderTarget.Data/Stride). dst addresses row 0 of the CANVAS; only the band's rows are written. */
 GGCUDA_API int ggcuda_flush(ggcuda_ctx* ctx, uint8_t* dst, size_t stride_bytes, uint32_t flags);
+/* Lifetime note: a dst seen on two consecutive flushes is page-locked in place (cudaHostRegister) so that the frame is
+ * DMA'd straight into it; it stays registered until a different dst is flushed to or the context is destroyed, and must
+ * stay allocated that long (gg keeps one pixmap per Context, so this is the pixmap's natural lifetime). */
 /* Split form used by benchmarks and multi-GPU callers: upload once, render into device memory.
  * dst_device addresses the first row of this context's BAND. */
 GGCUDA_API int ggcuda_upload(ggcuda_ctx* ctx);
