@@ -117,6 +117,7 @@ class Context:
         if getattr(self, "h", None):
             self.L.ggcuda_destroy(self.h)
             self.h = None
+        self._flush_target = None
 
     __del__ = close
 
@@ -172,8 +173,10 @@ class Context:
         stride = stride or dst.strides[0]
         # the library page-locks a target it sees twice in a row (cudaHostRegister) and keeps it registered until another
         # one shows up: the array must not be freed (and its address re-used) meanwhile, so the context holds on to it
-        self._flush_target = dst
+        prev = getattr(self, "_flush_target", None)   # released only after the call: flush unregisters it when dst differs
         self._ck(self.L.ggcuda_flush(self.h, _p(dst), stride, flags))
+        self._flush_target = dst
+        del prev
 
     def upload(self):
         self._ck(self.L.ggcuda_upload(self.h))
