@@ -3,13 +3,15 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-One "step" is one pass of the hot path (packed scene already in HBM -> flatten -> bin -> coarse/PTCL
--> fine -> RGBA8 band in HBM, then the all-gather of the bands when N > 1) over the synthetic scene
-`config3` (BASELINE.json configs[2]: 3840x2160, 10 000 filled + stroked Bezier paths, 29 blend
-modes, layers, clips). For N GPUs the canvas is N such frames stacked vertically (weak scaling:
-each GPU owns one 4K band of 135 tile rows); every rank holds the whole encoding and renders only
-its band. `value` is device time (CUDA events, max over ranks); `e2e` is the same frame through the
-public host API with host buffers (scene ingest + H2D + pipeline + D2H inside the timed region).
+One "step" is one pass of the hot path (packed scene already in HBM -> flatten incl. stroke expansion -> bin ->
+coarse/PTCL -> fine -> RGBA8 band in HBM, then the assembly of the bands in every rank's frame when N > 1) over the
+synthetic scene `config3` (BASELINE.json configs[2]: 3840x2160, 10 000 filled + stroked Bezier paths, 29 blend modes,
+layers, clips). For N GPUs the canvas is N copies of that frame stacked vertically (weak scaling: each GPU owns one 4K band
+of 135 tile rows); every rank holds the whole encoding and renders only its band. Band assembly: up to 4 GPUs the fine
+kernel stores its band into every rank's frame itself (symmetric memory: NVSwitch multicast / peer pointers) and a barrier
+follows; at 8 GPUs one NCCL all-gather (GG_BANDS=p2p|p2p_nomc|nccl overrides). `value` is device time (CUDA events, max over
+ranks); `e2e` is the same frame through the public host API with host buffers (scene ingest + H2D + pipeline + D2H inside
+the timed region). `--impl reference` times the CPU restatement of the reference's pipeline on the host cores.
 """
 import argparse
 import faulthandler
