@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggcuda.so")
 
 OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
-COMPOSITE_OVER, KEEP_SCENE = 1, 2
+COMPOSITE_OVER, KEEP_SCENE, TARGET_F32 = 1, 2, 4
 (BUF_SCENE, BUF_TAG_MONOIDS, BUF_DRAW_MONOIDS, BUF_INFO, BUF_CLIP_INPS, BUF_LINES, BUF_PATHS, BUF_TILES,
  BUF_SEG_START, BUF_SEGMENTS, BUF_PTCL_OFF, BUF_PTCL, BUF_HIT_CNT, BUF_LAYOUT, BUF_RESTART) = range(15)
 
@@ -18,7 +18,9 @@ SYMBOLS = [
     "ggcuda_create", "ggcuda_destroy", "ggcuda_last_error", "ggcuda_set_stream", "ggcuda_begin", "ggcuda_set_background",
     "ggcuda_set_band", "ggcuda_fill_path", "ggcuda_stroke_path", "ggcuda_push_clip", "ggcuda_push_layer", "ggcuda_pop",
     "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_render_device_multi", "ggcuda_get_stats", "ggcuda_set_timing",
-    "ggcuda_debug_read", "ggcuda_pack_host",
+    "ggcuda_debug_read", "ggcuda_pack_host", "ggcuda_begin_keyed", "ggcuda_set_dirty_rect", "ggcuda_register_target",
+    "ggcuda_unregister_target", "ggcuda_comm_unique_id", "ggcuda_comm_init", "ggcuda_comm_destroy", "ggcuda_all_gather_bands",
+    "ggcuda_sync", "ggcuda_encoding_hash",
 ]
 
 LINE = np.dtype([("path_ix", "<u4"), ("p0", "<f4", 2), ("p1", "<f4", 2)])
@@ -90,12 +92,43 @@ def load():
     L.ggcuda_debug_read.restype = C.c_longlong
     L.ggcuda_pack_host.argtypes = [vp, vp, sz, vp]
     L.ggcuda_pack_host.restype = C.c_longlong
+    L.ggcuda_begin_keyed.argtypes = [vp, u32, u32, C.c_uint64, C.POINTER(C.c_int)]
+    L.ggcuda_set_dirty_rect.argtypes = [vp, u32, u32, u32, u32]
+    L.ggcuda_register_target.argtypes = [vp, vp, sz]
+    L.ggcuda_unregister_target.argtypes = [vp, vp]
+    L.ggcuda_comm_unique_id.argtypes = [vp]
+    L.ggcuda_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.ggcuda_comm_destroy.argtypes = [vp]
+    L.ggcuda_all_gather_bands.argtypes = [vp, vp, sz]
+    L.ggcuda_sync.argtypes = [vp]
+    L.ggcuda_encoding_hash.argtypes = [vp, sz, vp, sz, vp, sz, vp, sz, vp, sz]
+    L.ggcuda_encoding_hash.restype = C.c_uint64
     _lib = L
     return L
 
 
 def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def encoding_hash(tags, path_data, draw_data, transforms, brushes=None):
+    """scene.Encoding.Hash (scene/encoding.go:752-802); with `brushes` the colours are folded in behind it."""
+    t = np.ascontiguousarray(tags, dtype=np.uint8)
+    pd = np.ascontiguousarray(path_data, dtype=np.float32)
+    dd = np.ascontiguousarray(draw_data, dtype=np.uint32)
+    tr = np.ascontiguousarray(transforms, dtype=np.float32).ravel()
+    br = None if brushes is None else np.ascontiguousarray(brushes, dtype=np.float64).ravel()
+    return int(load().ggcuda_encoding_hash(_p(t), t.size, _p(pd), pd.size, _p(dd), dd.size, _p(tr), tr.size,
+                                           _p(br) if br is not None else None, 0 if br is None else br.size // 4))
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (one rank calls this and hands them to the others)."""
+    u = np.zeros(128, dtype=np.uint8)
+    rc = load().ggcuda_comm_unique_id(_p(u))
+    if rc != 0:
+        raise GGCudaError(rc, (load().ggcuda_last_error(None) or b"").decode())
+    return u.tobytes()
 
 
 class Context:
@@ -115,9 +148,9 @@ class Context:
 
     def close(self):
         if getattr(self, "h", None):
-            self.L.ggcuda_destroy(self.h)
+            self.L.ggcuda_destroy(self.h)   # unregisters every page-locked target
             self.h = None
-        self._flush_target = None
+        self._pinned = {}
 
     __del__ = close
 
@@ -126,6 +159,41 @@ class Context:
 
     def begin(self, w, h):
         self._ck(self.L.ggcuda_begin(self.h, w, h))
+
+    def begin_keyed(self, w, h, key):
+        """True if the scene with this key is still resident on the device (nothing may be added then)."""
+        res = C.c_int(0)
+        self._ck(self.L.ggcuda_begin_keyed(self.h, w, h, C.c_uint64(key & 0xFFFFFFFFFFFFFFFF), C.byref(res)))
+        return bool(res.value)
+
+    def set_dirty_rect(self, x0, y0, x1, y1):
+        self._ck(self.L.ggcuda_set_dirty_rect(self.h, x0, y0, x1, y1))
+
+    def register_target(self, arr):
+        """Page-lock a numpy pixel buffer in place (flushes into it are DMA'd directly); the context keeps it alive."""
+        assert arr.dtype == np.uint8 and arr.flags.c_contiguous
+        self._ck(self.L.ggcuda_register_target(self.h, _p(arr), arr.nbytes))
+        if not hasattr(self, "_pinned"):
+            self._pinned = {}
+        self._pinned[arr.ctypes.data] = arr
+
+    def unregister_target(self, arr):
+        self._ck(self.L.ggcuda_unregister_target(self.h, _p(arr)))
+        getattr(self, "_pinned", {}).pop(arr.ctypes.data, None)
+
+    def comm_init(self, n_ranks, rank, uid):
+        u = np.frombuffer(bytes(uid), dtype=np.uint8).copy()
+        assert u.size == 128
+        self._ck(self.L.ggcuda_comm_init(self.h, n_ranks, rank, _p(u)))
+
+    def comm_destroy(self):
+        self._ck(self.L.ggcuda_comm_destroy(self.h))
+
+    def all_gather_bands(self, frame_ptr, band_bytes):
+        self._ck(self.L.ggcuda_all_gather_bands(self.h, C.c_void_p(frame_ptr), band_bytes))
+
+    def sync(self):
+        self._ck(self.L.ggcuda_sync(self.h))
 
     def set_background(self, rgba_premul):
         a = np.asarray(rgba_premul, dtype=np.uint8)
@@ -171,12 +239,7 @@ class Context:
         """dst: (H, W, 4) uint8 premultiplied RGBA (GPURenderTarget.Data)."""
         assert dst.dtype == np.uint8 and dst.flags.c_contiguous
         stride = stride or dst.strides[0]
-        # the library page-locks a target it sees twice in a row (cudaHostRegister) and keeps it registered until another
-        # one shows up: the array must not be freed (and its address re-used) meanwhile, so the context holds on to it
-        prev = getattr(self, "_flush_target", None)   # released only after the call: flush unregisters it when dst differs
         self._ck(self.L.ggcuda_flush(self.h, _p(dst), stride, flags))
-        self._flush_target = dst
-        del prev
 
     def upload(self):
         self._ck(self.L.ggcuda_upload(self.h))

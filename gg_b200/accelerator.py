@@ -106,6 +106,7 @@ class CUDAAccelerator:
         self.ctx = None
         self._target = None
         self._pending = 0
+        self.resident_hits = 0   # RenderEncoding calls served from the resident scene (fine only)
 
     # -- GPUAccelerator
     def Name(self):
@@ -168,18 +169,33 @@ class CUDAAccelerator:
             self._pending = 0
             self._target = None
 
+    def PinTarget(self, target):
+        """Page-lock the target's pixels in place (ggcuda_register_target) so that Flush DMAs straight into them. The Go
+        binding does the same with a runtime.Pinner held for the pixmap's lifetime."""
+        self.ctx.register_target(target.Data)
+
+    def UnpinTarget(self, target):
+        self.ctx.unregister_target(target.Data)
+
     # -- scene.EncodingAccelerator (proposed optional interface)
-    def RenderEncoding(self, target, enc, composite_over=False):
-        """Render a whole scene.Encoding (fills, strokes, clips, layers with blend modes)."""
+    def RenderEncoding(self, target, enc, composite_over=False, dirty=None):
+        """Render a whole scene.Encoding (fills, strokes, clips, layers with blend modes). The scene stays resident on the
+        device under its key (Encoding.Hash, scene/encoding.go:752-802, continued over the brushes): rendering the same
+        encoding again skips ingest, upload, flatten, binning and coarse. dirty = (x0, y0, x1, y1): re-rasterise and read
+        back only the tiles touching that rectangle (scene/renderer.go:395-433)."""
         if self.ctx is None:
             raise ErrFallbackToCPU("accelerator not initialised")
         if self._pending:
             self.Flush(self._target)
-        self.ctx.begin(target.Width, target.Height)
-        try:
-            self.ctx.add_encoding(*enc.streams())
-        except GGCudaError as e:
-            if e.code == _lib.ERR_UNSUPPORTED:
-                raise ErrFallbackToCPU(str(e))
-            raise
+        if self.ctx.begin_keyed(target.Width, target.Height, enc.CacheKey()):
+            self.resident_hits += 1
+        else:
+            try:
+                self.ctx.add_encoding(*enc.streams())
+            except GGCudaError as e:
+                if e.code == _lib.ERR_UNSUPPORTED:
+                    raise ErrFallbackToCPU(str(e))
+                raise
+        if dirty is not None:
+            self.ctx.set_dirty_rect(*dirty)
         self.ctx.flush(target.Data, target.Stride, _lib.COMPOSITE_OVER if composite_over else 0)

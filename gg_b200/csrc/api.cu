@@ -13,8 +13,12 @@
 
 #include <stdlib.h>
 
+#include <dlfcn.h>
+#include <nccl.h>   // types only: the library is resolved at run time (ggcuda_comm_init), libggcuda.so does not link it
+
 #include <algorithm>
 #include <chrono>
+#include <exception>
 #include <new>
 #include <string>
 #include <vector>
@@ -53,9 +57,18 @@ struct Ctx {
         scan_partials, frame_d;
     uint32_t imp_words = 0;
     uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0, esegs_cap = 0;
-    // Read-back target seen on consecutive flushes (gg keeps one pixmap per context): page-locked in place
-    // from its second use so the band is DMA'd straight into it, without the staging copy.
-    uint8_t* last_dst = nullptr; size_t last_dst_bytes = 0; bool dst_registered = false;
+    // Read-back targets the caller asked to page-lock (ggcuda_register_target): a flush whose destination lies inside
+    // one is DMA'd straight into it, slice by slice while fine is still running; any other goes through the staging buffer.
+    struct Pinned { uint8_t* p; size_t bytes; };
+    std::vector<Pinned> pinned;
+    // Resident scene: the key the caller gave the scene whose pipeline results (segments, PTCL) are in the
+    // device buffers; a ggcuda_begin_keyed with the same key, size and band skips ingest, upload and every stage before fine.
+    uint64_t resident_key = 0; bool resident_valid = false, reuse = false, keyed = false; uint64_t pending_key = 0;
+    uint32_t res_w = 0, res_h = 0, res_y0 = 0, res_y1 = 0;
+    bool dirty_set = false; uint32_t dirty[4] = {0, 0, 0, 0};   // pixels: x0, y0, x1, y1 -- fine and read-back cover only these tiles
+    int sm_count = 148;
+    // NCCL communicator for band assembly inside the library (ggcuda_comm_init)
+    ncclComm_t comm = nullptr; int comm_ranks = 0, comm_rank = 0;
     GGFineMirrors mirrors{};   // set for one render by ggcuda_render_device_multi
     ggcuda_stats stats{};
     bool timing = false;
@@ -179,7 +192,8 @@ int size_dynamic(Ctx* c) {
         if (c->imp_words && (r = ensure(c, c->imp_seen, bytes))) return r;
     }
     if ((r = ensure(c, c->seg_counts, sizeof(GGSegCount) * (size_t)c->seg_counts_cap))) return r;
-    if ((r = ensure(c, c->segments, sizeof(GGSegment) * (size_t)c->segments_cap))) return r;
+    // + 4: fine fetches segment slices in 16-byte aligned chunks of 4 segments and may read up to 3 past the last one
+    if ((r = ensure(c, c->segments, sizeof(GGSegment) * ((size_t)c->segments_cap + 4)))) return r;
     if ((r = ensure(c, c->hits, 4 * (size_t)c->hits_cap))) return r;
     if ((r = ensure(c, c->ptcl, 4 * (size_t)c->ptcl_cap))) return r;
     if ((r = ensure(c, c->spill, sizeof(float4) * 256 * (size_t)std::max<uint32_t>(c->spill_cap, 1)))) return r;
@@ -201,7 +215,8 @@ void fill_config(Ctx* c, uint32_t flags) {
     g.lines_cap = c->lines_cap; g.tiles_cap = c->tiles_cap; g.rows_cap = c->rows_cap; g.seg_counts_cap = c->seg_counts_cap;
     g.segments_cap = c->segments_cap; g.hits_cap = c->hits_cap; g.ptcl_cap = c->ptcl_cap; g.spill_cap = c->spill_cap; g.esegs_cap = c->esegs_cap; g.imp_words = c->imp_words; g.n_implicit = c->scene.n_implicit;
     for (int i = 0; i < 4; i++) g.bg[i] = (float)c->bg[i] / 255.0f;
-    g.flags = (flags & GGCUDA_COMPOSITE_OVER) ? GG_FLAG_BG_FROM_DST : 0u;
+    g.flags = ((flags & GGCUDA_COMPOSITE_OVER) ? GG_FLAG_BG_FROM_DST : 0u) | ((flags & GGCUDA_TARGET_F32) ? GG_FLAG_TARGET_F32 : 0u);
+    g.sm_count = (uint32_t)c->sm_count;
 }
 
 GGBuffers buffers(Ctx* c) {
@@ -218,39 +233,62 @@ GGBuffers buffers(Ctx* c) {
     return b;
 }
 
+// Tile rows (relative to the band) and tile-pair columns fine has to cover: the whole band, or the tiles a dirty rectangle touches.
+GGFineRange fine_range(const Ctx* c) {
+    GGFineRange rg;
+    const uint32_t wt = (c->width + GG_TILE_W - 1) / GG_TILE_W;
+    rg.row0 = 0; rg.row1 = c->band_y1 - c->band_y0; rg.px0 = 0; rg.px1 = (wt + 1) / 2;
+    if (c->dirty_set) {
+        uint32_t tx0 = c->dirty[0] / GG_TILE_W, ty0 = c->dirty[1] / GG_TILE_H;
+        uint32_t tx1 = (std::min(c->dirty[2], c->width) + GG_TILE_W - 1) / GG_TILE_W, ty1 = (std::min(c->dirty[3], c->height) + GG_TILE_H - 1) / GG_TILE_H;
+        ty0 = std::max(ty0, c->band_y0); ty1 = std::min(ty1, c->band_y1);
+        if (tx1 <= tx0 || ty1 <= ty0) { rg.row1 = rg.row0; return rg; }
+        rg.row0 = ty0 - c->band_y0; rg.row1 = ty1 - c->band_y0; rg.px0 = tx0 / 2; rg.px1 = (tx1 + 1) / 2;
+    }
+    return rg;
+}
+
 // Run the pipeline into dst_device (band-relative). Re-runs with larger buffers while a stage overflowed.
 // host_dst != nullptr (page-locked, row pitch host_stride): fine runs in GG_FINE_PARTS row slices and every slice is copied to
 // the host on a second stream while the next one is rasterised.
+// A resident scene (ggcuda_begin_keyed found its key) runs fine only: segments and command lists are still in place.
 int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* host_dst = nullptr, size_t host_stride = 0) {
     if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
-    if (!c->uploaded) { int r = upload(c); if (r) return r; }
+    const bool reuse = c->reuse && c->resident_valid;
+    if (!reuse && !c->uploaded) { int r = upload(c); if (r) return r; }
     c->stats.passes = 0; c->stats.kernel_launches = 0;
+    const size_t px_bytes = (flags & GGCUDA_TARGET_F32) ? 16 : 4;
     for (int attempt = 0; attempt < 12; attempt++) {
-        int r = size_dynamic(c);
-        if (r) return r;
+        if (!reuse) { int r = size_dynamic(c); if (r) return r; }
         fill_config(c, flags);
         GGBuffers b = buffers(c);
         if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
-        gg_launch_front(c->cfg, b, c->stream);
+        uint32_t launches = 0;
+        if (!reuse) launches += gg_launch_front(c->cfg, b, c->stream);
         if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
-        gg_launch_binning(c->cfg, b, c->stream);
+        if (!reuse) launches += gg_launch_binning(c->cfg, b, c->stream);
         if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
-        gg_launch_coarse(c->cfg, b, c->stream);
+        if (!reuse) launches += gg_launch_coarse(c->cfg, b, c->stream);
+        else CK(cudaMemsetAsync(&b.bump->fine_cursor[0], 0, sizeof(uint32_t) * GG_FINE_PARTS, c->stream));
         if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
-        CK(cudaMemcpyAsync(c->h_bump, c->bump.p, sizeof(GGBump), cudaMemcpyDeviceToHost, c->stream));
+        if (!reuse) CK(cudaMemcpyAsync(c->h_bump, c->bump.p, sizeof(GGBump), cudaMemcpyDeviceToHost, c->stream));
         // fine is launched optimistically; if a stage overflowed its inputs are in-bounds garbage and the pass is redone
-        const uint32_t band_rows_t = c->band_y1 - c->band_y0;
-        uint32_t parts = (host_dst && band_rows_t >= 4 * GG_FINE_PARTS) ? GG_FINE_PARTS : 1u;
-        for (uint32_t k = 0; k < parts; k++) {
-            uint32_t r0 = (uint32_t)((uint64_t)band_rows_t * k / parts), r1 = (uint32_t)((uint64_t)band_rows_t * (k + 1) / parts);
-            gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, r0, r1, k, c->mirrors);
+        const GGFineRange full = fine_range(c);
+        const uint32_t rows_t = full.row1 - full.row0;
+        uint32_t parts = (host_dst && rows_t >= 4 * GG_FINE_PARTS) ? GG_FINE_PARTS : 1u;
+        const uint32_t col0 = std::min(full.px0 * 2 * GG_TILE_W, c->width), col1 = std::min(full.px1 * 2 * GG_TILE_W, c->width);
+        for (uint32_t k = 0; k < parts && rows_t; k++) {
+            GGFineRange rg = full;
+            rg.row0 = full.row0 + (uint32_t)((uint64_t)rows_t * k / parts); rg.row1 = full.row0 + (uint32_t)((uint64_t)rows_t * (k + 1) / parts);
+            gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, rg, k, c->mirrors);
             if (host_dst) {
-                uint32_t y0 = r0 * GG_TILE_H, y1 = std::min(r1 * GG_TILE_H, std::min(c->band_y1 * GG_TILE_H, c->height) - c->band_y0 * GG_TILE_H);
-                if (y1 > y0) {
+                uint32_t y0 = rg.row0 * GG_TILE_H, y1 = std::min(rg.row1 * GG_TILE_H, std::min(c->band_y1 * GG_TILE_H, c->height) - c->band_y0 * GG_TILE_H);
+                if (y1 > y0 && col1 > col0) {
                     CK(cudaEventRecord(c->ev_part[k], c->stream));
                     CK(cudaStreamWaitEvent(c->copy_stream, c->ev_part[k], 0));
-                    CK(cudaMemcpy2DAsync(host_dst + (size_t)y0 * host_stride, host_stride, dst_device + (size_t)y0 * stride, stride, (size_t)c->width * 4, y1 - y0,
+                    CK(cudaMemcpy2DAsync(host_dst + (size_t)y0 * host_stride + (size_t)col0 * px_bytes, host_stride,
+                                         dst_device + (size_t)y0 * stride + (size_t)col0 * px_bytes, stride, (size_t)(col1 - col0) * px_bytes, y1 - y0,
                                          cudaMemcpyDeviceToHost, c->copy_stream));
                 }
             }
@@ -261,9 +299,13 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
         }
         if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
         c->stats.passes++;
-        c->stats.kernel_launches += 18 + 7 + 5 + parts;   // front (4 scans x 3 + 6) + binning + coarse + fine
+        c->stats.kernel_launches += launches + (rows_t ? parts : 0u);
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
+        if (reuse) {
+            if (c->timing) { c->stats.ms_front = c->stats.ms_binning = c->stats.ms_coarse = 0; cudaEventElapsedTime(&c->stats.ms_fine, c->ev[3], c->ev[4]); }
+            return 0;
+        }
         GGBump bm = *c->h_bump;
         c->last_bump = bm;
         bool grow = false;
@@ -288,6 +330,9 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
                 cudaEventElapsedTime(&s.ms_coarse, c->ev[2], c->ev[3]);
                 cudaEventElapsedTime(&s.ms_fine, c->ev[3], c->ev[4]);
             }
+            // the device now holds this scene's segments and command lists: remember under which key
+            c->resident_valid = c->keyed; c->resident_key = c->pending_key;
+            c->res_w = c->width; c->res_h = c->height; c->res_y0 = c->band_y0; c->res_y1 = c->band_y1;
             return 0;
         }
         if (!grow) return fail(c, GGCUDA_ERR_CUDA, "pipeline reported overflow without a growable buffer (failed mask " + std::to_string(bm.failed) + ")");
@@ -295,7 +340,58 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
     return fail(c, GGCUDA_ERR_NOMEM, "pipeline buffers did not converge");
 }
 
+// After a render: drop the accumulated scene unless the caller keeps it; a dirty rectangle applies to one render only.
+void after_render(Ctx* c, uint32_t flags) {
+    c->dirty_set = false;
+    if (!(flags & GGCUDA_KEEP_SCENE) && !c->reuse) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+}
+
+// ---- NCCL, resolved at run time: the copy already in the process (a host that links NCCL itself, torch's) or libnccl.so.2
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+NcclApi* nccl_api(std::string* why) {
+    static NcclApi api;
+    static bool tried = false;
+    static std::string err;
+    if (!tried) {
+        tried = true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) { err = std::string("NCCL not found: ") + dlerror(); }
+        else {
+            api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+            api.CommInitRank = (decltype(api.CommInitRank))dlsym(h, "ncclCommInitRank");
+            api.CommDestroy = (decltype(api.CommDestroy))dlsym(h, "ncclCommDestroy");
+            api.AllGather = (decltype(api.AllGather))dlsym(h, "ncclAllGather");
+            api.GetErrorString = (decltype(api.GetErrorString))dlsym(h, "ncclGetErrorString");
+            api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.GetErrorString;
+            if (!api.ok) err = "libnccl.so.2 lacks a required symbol";
+        }
+    }
+    if (!api.ok && why) *why = err;
+    return api.ok ? &api : nullptr;
+}
+
+const Ctx::Pinned* find_pinned(const Ctx* c, const uint8_t* p, size_t bytes) {
+    for (const auto& r : c->pinned) if (p >= r.p && p + bytes <= r.p + r.bytes) return &r;
+    return nullptr;
+}
+
 }  // namespace
+
+// No C++ exception may cross the C ABI (cgo would abort the process): every entry point runs inside GG_TRY / GG_CATCH.
+#define GG_TRY try {
+#define GG_CATCH(c)                                                                                                   \
+    } catch (const std::bad_alloc&) { return fail((c), GGCUDA_ERR_NOMEM, "out of host memory"); }                     \
+    catch (const std::exception& e_) { return fail((c), GGCUDA_ERR_INVALID, std::string("internal error: ") + e_.what()); } \
+    catch (...) { return fail((c), GGCUDA_ERR_INVALID, "internal error"); }
 
 extern "C" {
 
@@ -303,6 +399,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
     Ctx* c = nullptr;
     if (!out) return fail(nullptr, GGCUDA_ERR_INVALID, "out is NULL");
     *out = nullptr;
+    try {
     if (device < 0) {   // host-only context (scene packing for tests and the CPU baseline)
         c = new (std::nothrow) Ctx();
         if (!c) return fail(nullptr, GGCUDA_ERR_NOMEM, "out of host memory");
@@ -321,6 +418,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
     c = new (std::nothrow) Ctx();
     if (!c) return fail(nullptr, GGCUDA_ERR_NOMEM, "out of host memory");
     c->device = device;
+    c->sm_count = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : 148;
     c->scene.host_strokes = (flags & GGCUDA_CREATE_HOST_STROKES) != 0;
     if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void**)&c->h_bump, sizeof(GGBump), cudaHostAllocDefault) != cudaSuccess) {
@@ -335,6 +433,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
     cudaEventCreateWithFlags(&c->ev_copied, cudaEventDisableTiming);
     *out = reinterpret_cast<ggcuda_ctx*>(c);
     return 0;
+    } catch (...) { delete c; return fail(nullptr, GGCUDA_ERR_NOMEM, "context creation failed"); }
 }
 
 void ggcuda_destroy(ggcuda_ctx* h) {
@@ -343,7 +442,9 @@ void ggcuda_destroy(ggcuda_ctx* h) {
     if (c->host_only) { delete c; return; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    if (c->dst_registered) cudaHostUnregister(c->last_dst);
+    if (c->comm) { NcclApi* a = nccl_api(nullptr); if (a) a->CommDestroy(c->comm); c->comm = nullptr; }
+    for (auto& r : c->pinned) cudaHostUnregister(r.p);
+    c->pinned.clear();
     free_all(c);
     if (c->h_scene) cudaFreeHost(c->h_scene);
     if (c->h_bump) cudaFreeHost(c->h_bump);
@@ -364,6 +465,7 @@ const char* ggcuda_last_error(ggcuda_ctx* h) {
 long long ggcuda_pack_host(ggcuda_ctx* h, uint32_t* dst, size_t cap_words, uint32_t layout13[13]) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
     if (c->width == 0) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_begin was not called");
     c->scene.close_open_clips();
     size_t words = c->scene.packed_words();
@@ -374,6 +476,7 @@ long long ggcuda_pack_host(ggcuda_ctx* h, uint32_t* dst, size_t cap_words, uint3
     c->scene.pack(dst, &L, ((c->width + GG_TILE_W - 1) / GG_TILE_W) * (y1 > y0 ? y1 - y0 : 0));
     if (layout13) memcpy(layout13, &L, sizeof(uint32_t) * 13);
     return (long long)words;
+    GG_CATCH(c)
 }
 
 int ggcuda_set_stream(ggcuda_ctx* h, void* s) {
@@ -383,13 +486,49 @@ int ggcuda_set_stream(ggcuda_ctx* h, void* s) {
     return 0;
 }
 
-int ggcuda_begin(ggcuda_ctx* h, uint32_t width, uint32_t height) {
-    Ctx* c = reinterpret_cast<Ctx*>(h);
-    if (!c) return GGCUDA_ERR_INVALID;
+static int begin_common(Ctx* c, uint32_t width, uint32_t height) {
     if (width == 0 || height == 0 || width > 65536 || height > 65536) return fail(c, GGCUDA_ERR_INVALID, "bad target size");
     c->width = width; c->height = height;
     c->scene.clear(width, height);
     c->uploaded = false;
+    c->reuse = false; c->keyed = false; c->dirty_set = false;
+    return 0;
+}
+
+int ggcuda_begin(ggcuda_ctx* h, uint32_t width, uint32_t height) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    return begin_common(c, width, height);
+    GG_CATCH(c)
+}
+
+int ggcuda_begin_keyed(ggcuda_ctx* h, uint32_t width, uint32_t height, uint64_t key, int* resident) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !resident) return c ? fail(c, GGCUDA_ERR_INVALID, "resident is NULL") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    *resident = 0;
+    uint32_t ht = (height + GG_TILE_H - 1) / GG_TILE_H;
+    uint32_t y0 = c->band_set ? c->band_y0 : 0, y1 = c->band_set ? std::min(c->band_y1, ht) : ht;
+    if (c->resident_valid && c->resident_key == key && c->res_w == width && c->res_h == height && c->res_y0 == y0 && c->res_y1 == y1 && !c->host_only) {
+        // same scene as the one whose segments and command lists are on the device: nothing to ingest, upload or bin
+        c->width = width; c->height = height;
+        c->reuse = true; c->keyed = true; c->pending_key = key; c->dirty_set = false;
+        *resident = 1;
+        return 0;
+    }
+    int r = begin_common(c, width, height);
+    if (r) return r;
+    c->keyed = true; c->pending_key = key; c->resident_valid = false;
+    return 0;
+    GG_CATCH(c)
+}
+
+int ggcuda_set_dirty_rect(ggcuda_ctx* h, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    if (x1 < x0 || y1 < y0) return fail(c, GGCUDA_ERR_INVALID, "dirty rectangle reversed");
+    c->dirty[0] = x0; c->dirty[1] = y0; c->dirty[2] = x1; c->dirty[3] = y1; c->dirty_set = true;
     return 0;
 }
 
@@ -404,17 +543,23 @@ int ggcuda_set_band(ggcuda_ctx* h, uint32_t y0, uint32_t y1) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
     if (y1 < y0) return fail(c, GGCUDA_ERR_INVALID, "band rows reversed");
+    if (c->scene.n_culled > 0 && !(c->band_set && c->band_y0 == y0 && c->band_y1 == y1))
+        return fail(c, GGCUDA_ERR_INVALID, "ggcuda_set_band: paths outside the previous band were dropped when the scene was added; set the band before adding the scene");
+    if (!(c->band_set && c->band_y0 == y0 && c->band_y1 == y1)) { c->uploaded = false; c->resident_valid = false; c->reuse = false; }
     c->band_y0 = y0; c->band_y1 = y1; c->band_set = true;
-    c->uploaded = false;
+    c->scene.set_cull_band((float)(y0 * GG_TILE_H), (float)(y1 * GG_TILE_H));
     return 0;
 }
 
 static const float ID6[6] = {1, 0, 0, 0, 1, 0};
+#define GG_NO_REUSE(c) if ((c)->reuse) return fail((c), GGCUDA_ERR_INVALID, "the scene is resident (ggcuda_begin_keyed): nothing may be added")
 
 int ggcuda_fill_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
                      const uint8_t rgba[4], int fill_rule) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !rgba) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
     if (n_verbs == 0) return 0;   // vello_accelerator.go:216-219: empty paths are dropped
     c->scene.begin_path(ID6, fill_rule == GGCUDA_FILL_EVENODD);
     c->scene.add_verbs(verbs, n_verbs, coords, n_coords);
@@ -422,12 +567,15 @@ int ggcuda_fill_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, cons
     c->scene.draw_color(gg_pack_color_straight(rgba));
     c->uploaded = false;
     return 0;
+    GG_CATCH(c)
 }
 
 int ggcuda_stroke_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
                        const uint8_t rgba[4], double width, int cap, int join, double miter_limit) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !rgba) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
     if (n_verbs == 0) return 0;
     std::vector<float> cf(n_coords);
     for (uint32_t i = 0; i < n_coords; i++) cf[i] = (float)coords[i];
@@ -445,11 +593,15 @@ int ggcuda_stroke_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, co
     c->scene.draw_color(gg_pack_color_straight(rgba));
     c->uploaded = false;
     return 0;
+    GG_CATCH(c)
 }
 
 int ggcuda_push_clip(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    if ((!verbs && n_verbs) || (!coords && n_coords)) return fail(c, GGCUDA_ERR_INVALID, "null argument");
+    GG_TRY
+    GG_NO_REUSE(c);
     c->scene.begin_path(ID6, false);
     if (n_verbs) c->scene.add_verbs(verbs, n_verbs, coords, n_coords);
     c->scene.end_path();
@@ -458,23 +610,30 @@ int ggcuda_push_clip(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, cons
     c->scene.begin_clip(0x8003u, 1.0f, 0);
     c->uploaded = false;
     return 0;
+    GG_CATCH(c)
 }
 
 int ggcuda_push_layer(ggcuda_ctx* h, uint32_t blend_mode, float alpha) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
     c->scene.begin_layer(gg_blend_word(blend_mode), alpha);
     c->uploaded = false;
     return 0;
+    GG_CATCH(c)
 }
 
 int ggcuda_pop(ggcuda_ctx* h) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
     if (c->scene.clip_stack.empty()) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_pop: nothing to pop");
     c->scene.end_clip(c->scene.clip_kind.back());
     c->uploaded = false;
     return 0;
+    GG_CATCH(c)
 }
 
 int ggcuda_add_encoding(ggcuda_ctx* h, const uint8_t* tags, size_t n_tags, const float* path_data, size_t n_path_data,
@@ -482,92 +641,228 @@ int ggcuda_add_encoding(ggcuda_ctx* h, const uint8_t* tags, size_t n_tags, const
                         const double* brushes, size_t n_brushes) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
     if (c->width == 0) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_begin was not called");
     std::string msg;
     int r = c->scene.add_encoding(tags, n_tags, path_data, n_path_data, draw_data, n_draw_data, transforms, n_transforms / 6, brushes, n_brushes, &msg);
     c->uploaded = false;
     if (r) return fail(c, r, msg);
     return 0;
+    GG_CATCH(c)
 }
 
 int ggcuda_upload(ggcuda_ctx* h) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (c->reuse) return 0;
     return upload(c);
+    GG_CATCH(c)
 }
 
 int ggcuda_render_device(ggcuda_ctx* h, void* dst_device, size_t stride, uint32_t flags) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || !dst_device) return c ? fail(c, GGCUDA_ERR_INVALID, "dst_device is NULL") : GGCUDA_ERR_INVALID;
-    if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
+    GG_TRY
+    if (stride < (size_t)c->width * ((flags & GGCUDA_TARGET_F32) ? 16 : 4)) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
+    if ((flags & GGCUDA_TARGET_F32) && (flags & GGCUDA_COMPOSITE_OVER)) return fail(c, GGCUDA_ERR_INVALID, "composite-over is defined on RGBA8 targets only");
+    if ((flags & GGCUDA_TARGET_F32) && ((reinterpret_cast<uintptr_t>(dst_device) | stride) & 15u)) return fail(c, GGCUDA_ERR_INVALID, "float targets must be 16-byte aligned");
     int r = render(c, (uint8_t*)dst_device, stride, flags);   // one fine launch, no host copy
-    if (r == 0 && !(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+    if (r == 0) after_render(c, flags);
     return r;
+    GG_CATCH(c)
 }
 
 int ggcuda_render_device_multi(ggcuda_ctx* h, void* dst_device, void* const* mirrors, uint32_t n_mirrors, int multicast, size_t stride, uint32_t flags) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c || !dst_device || (n_mirrors && !mirrors)) return c ? fail(c, GGCUDA_ERR_INVALID, "null destination") : GGCUDA_ERR_INVALID;
+    GG_TRY
     if (n_mirrors > GG_MAX_MIRRORS || (multicast && n_mirrors != 1)) return fail(c, GGCUDA_ERR_INVALID, "bad mirror list");
+    if (flags & GGCUDA_TARGET_F32) return fail(c, GGCUDA_ERR_INVALID, "mirrored bands are RGBA8");
     if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
     c->mirrors = GGFineMirrors{};
     for (uint32_t i = 0; i < n_mirrors; i++) c->mirrors.p[i] = (uint8_t*)mirrors[i];
     c->mirrors.n = n_mirrors; c->mirrors.multicast = multicast ? 1u : 0u;
     int r = render(c, (uint8_t*)dst_device, stride, flags);
     c->mirrors = GGFineMirrors{};
-    if (r == 0 && !(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+    if (r == 0) after_render(c, flags);
     return r;
+    GG_CATCH(c)
 }
 
 static double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int ggcuda_register_target(ggcuda_ctx* h, uint8_t* data, size_t bytes) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !data || !bytes) return c ? fail(c, GGCUDA_ERR_INVALID, "null target") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context");
+    if (find_pinned(c, data, bytes)) return 0;
+    CK(cudaSetDevice(c->device));
+    cudaError_t e = cudaHostRegister(data, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(c, GGCUDA_ERR_CUDA, std::string("cudaHostRegister: ") + cudaGetErrorString(e)); }
+    c->pinned.push_back(Ctx::Pinned{data, bytes});
+    return 0;
+    GG_CATCH(c)
+}
+
+int ggcuda_unregister_target(ggcuda_ctx* h, uint8_t* data) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !data) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    for (size_t i = 0; i < c->pinned.size(); i++) {
+        if (c->pinned[i].p != data) continue;
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaHostUnregister(data);
+        c->pinned.erase(c->pinned.begin() + (long)i);
+        return 0;
+    }
+    return fail(c, GGCUDA_ERR_INVALID, "target was not registered");
+    GG_CATCH(c)
+}
 
 int ggcuda_flush(ggcuda_ctx* h, uint8_t* dst, size_t stride, uint32_t flags) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     const bool trace = getenv("GGCUDA_TRACE") != nullptr;
     double t0 = trace ? now_ms() : 0, t1 = 0, t2 = 0;
     if (!c || !dst) return c ? fail(c, GGCUDA_ERR_INVALID, "dst is NULL") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (flags & GGCUDA_TARGET_F32) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_flush reads back RGBA8 (GPURenderTarget.Data); float targets are device targets");
     if (stride < (size_t)c->width * 4) return fail(c, GGCUDA_ERR_INVALID, "stride smaller than a row");
     if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context: no device to render on (there is no CPU fallback)");
     CK(cudaSetDevice(c->device));
-    if (!c->uploaded) { int r = upload(c); if (r) return r; }
+    if (!(c->reuse && c->resident_valid) && !c->uploaded) { int r = upload(c); if (r) return r; }
     if (trace) t1 = now_ms();
     uint32_t row0 = c->band_y0 * GG_TILE_H, row1 = std::min(c->band_y1 * GG_TILE_H, c->height);
-    if (row1 <= row0) return 0;
+    if (row1 <= row0) { after_render(c, flags); return 0; }
     size_t rows = row1 - row0, tight = (size_t)c->width * 4, bytes = rows * tight;
     int r;
     if ((r = ensure(c, c->frame_d, bytes))) return r;
-    if (bytes > c->h_frame_bytes) {
-        if (c->h_frame) { CK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->h_frame); c->h_frame = nullptr; }
+    uint8_t* band_dst = dst + (size_t)row0 * stride;
+    const size_t band_bytes = (rows - 1) * stride + tight;
+    const bool direct = find_pinned(c, band_dst, band_bytes) != nullptr;
+    // rows / columns this flush touches (the whole band unless a dirty rectangle was set)
+    const GGFineRange rg = fine_range(c);
+    const size_t ry0 = (size_t)rg.row0 * GG_TILE_H, ry1 = std::min<size_t>((size_t)rg.row1 * GG_TILE_H, rows);
+    const size_t cx0 = std::min<size_t>((size_t)rg.px0 * 2 * GG_TILE_W, c->width), cx1 = std::min<size_t>((size_t)rg.px1 * 2 * GG_TILE_W, c->width);
+    const bool any = ry1 > ry0 && cx1 > cx0;
+    if (!direct && bytes > c->h_frame_bytes) {
+        if (c->h_frame) { CK(cudaStreamSynchronize(c->stream)); cudaFreeHost(c->h_frame); c->h_frame = nullptr; c->h_frame_bytes = 0; }
         CK(cudaHostAlloc((void**)&c->h_frame, bytes, cudaHostAllocDefault));
         c->h_frame_bytes = bytes;
     }
-    if (flags & GGCUDA_COMPOSITE_OVER) {   // bring the existing target pixels to the device as fine's starting colour
-        for (size_t y = 0; y < rows; y++) memcpy(c->h_frame + y * tight, dst + (row0 + y) * stride, tight);
-        CK(cudaMemcpyAsync(c->frame_d.p, c->h_frame, bytes, cudaMemcpyHostToDevice, c->stream));
-    }
-    uint8_t* band_dst = dst + (size_t)row0 * stride;
-    size_t band_bytes = (rows - 1) * stride + tight;
-    if (band_dst == c->last_dst && band_bytes == c->last_dst_bytes) {
-        if (!c->dst_registered && cudaHostRegister(band_dst, band_bytes, cudaHostRegisterDefault) == cudaSuccess) c->dst_registered = true;
-        else if (!c->dst_registered) cudaGetLastError();
-    } else {
-        if (c->dst_registered) { cudaHostUnregister(c->last_dst); c->dst_registered = false; }
-        c->last_dst = band_dst; c->last_dst_bytes = band_bytes;
+    if ((flags & GGCUDA_COMPOSITE_OVER) && any) {   // the target's pixels go to the device: fine composites the scene over them
+        if (direct) {
+            CK(cudaMemcpy2DAsync((uint8_t*)c->frame_d.p + ry0 * tight + cx0 * 4, tight, band_dst + ry0 * stride + cx0 * 4, stride, (cx1 - cx0) * 4, ry1 - ry0,
+                                 cudaMemcpyHostToDevice, c->stream));
+        } else {
+            for (size_t y = ry0; y < ry1; y++) memcpy(c->h_frame + y * tight + cx0 * 4, band_dst + y * stride + cx0 * 4, (cx1 - cx0) * 4);
+            CK(cudaMemcpy2DAsync((uint8_t*)c->frame_d.p + ry0 * tight + cx0 * 4, tight, c->h_frame + ry0 * tight + cx0 * 4, tight, (cx1 - cx0) * 4, ry1 - ry0,
+                                 cudaMemcpyHostToDevice, c->stream));
+        }
     }
     // a page-locked target is filled slice by slice while fine is still running (render() queues the copies)
-    r = render(c, (uint8_t*)c->frame_d.p, tight, flags, c->dst_registered ? band_dst : nullptr, stride);
+    r = render(c, (uint8_t*)c->frame_d.p, tight, flags, direct ? band_dst : nullptr, stride);
     if (r) return r;
     if (trace) t2 = now_ms();
-    if (!c->dst_registered) {
-        CK(cudaMemcpyAsync(c->h_frame, c->frame_d.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (!direct && any) {
+        CK(cudaMemcpy2DAsync(c->h_frame + ry0 * tight + cx0 * 4, tight, (uint8_t*)c->frame_d.p + ry0 * tight + cx0 * 4, tight, (cx1 - cx0) * 4, ry1 - ry0,
+                             cudaMemcpyDeviceToHost, c->stream));
         CK(cudaStreamSynchronize(c->stream));
-        if (stride == tight) memcpy(band_dst, c->h_frame, bytes);
-        else for (size_t y = 0; y < rows; y++) memcpy(band_dst + y * stride, c->h_frame + y * tight, tight);
+        for (size_t y = ry0; y < ry1; y++) memcpy(band_dst + y * stride + cx0 * 4, c->h_frame + y * tight + cx0 * 4, (cx1 - cx0) * 4);
     }
     if (trace) fprintf(stderr, "[ggcuda] flush: pack+upload %.2f ms, pipeline %s %.2f ms (%u passes), %s %.2f ms\n", t1 - t0,
-                       c->dst_registered ? "+ overlapped read-back" : "", t2 - t1, c->stats.passes, c->dst_registered ? "tail" : "staged read-back", now_ms() - t2);
-    if (!(flags & GGCUDA_KEEP_SCENE)) { c->scene.clear(c->width, c->height); c->uploaded = false; }
+                       direct ? "+ overlapped read-back" : "", t2 - t1, c->stats.passes, direct ? "tail" : "staged read-back", now_ms() - t2);
+    after_render(c, flags);
     return 0;
+    GG_CATCH(c)
+}
+
+// ---- band assembly inside the library: one NCCL all-gather, for hosts without torch (the Go binding)
+int ggcuda_comm_unique_id(uint8_t id[128]) {
+    if (!id) return GGCUDA_ERR_INVALID;
+    try {
+        std::string why;
+        NcclApi* a = nccl_api(&why);
+        if (!a) return fail(nullptr, GGCUDA_ERR_UNSUPPORTED, why);
+        ncclUniqueId u;
+        static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+        ncclResult_t r = a->GetUniqueId(&u);
+        if (r != ncclSuccess) return fail(nullptr, GGCUDA_ERR_CUDA, std::string("ncclGetUniqueId: ") + a->GetErrorString(r));
+        memcpy(id, &u, 128);
+        return 0;
+    } catch (...) { return GGCUDA_ERR_NOMEM; }
+}
+
+int ggcuda_comm_init(ggcuda_ctx* h, int n_ranks, int rank, const uint8_t id[128]) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !id) return c ? fail(c, GGCUDA_ERR_INVALID, "id is NULL") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(c, GGCUDA_ERR_INVALID, "bad rank");
+    std::string why;
+    NcclApi* a = nccl_api(&why);
+    if (!a) return fail(c, GGCUDA_ERR_UNSUPPORTED, why);
+    CK(cudaSetDevice(c->device));
+    if (c->comm) { a->CommDestroy(c->comm); c->comm = nullptr; }
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    ncclResult_t r = a->CommInitRank(&c->comm, n_ranks, u, rank);
+    if (r != ncclSuccess) { c->comm = nullptr; return fail(c, GGCUDA_ERR_CUDA, std::string("ncclCommInitRank: ") + a->GetErrorString(r)); }
+    c->comm_ranks = n_ranks; c->comm_rank = rank;
+    return 0;
+    GG_CATCH(c)
+}
+
+int ggcuda_comm_destroy(ggcuda_ctx* h) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (c->comm) { NcclApi* a = nccl_api(nullptr); if (a) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); a->CommDestroy(c->comm); } c->comm = nullptr; }
+    return 0;
+    GG_CATCH(c)
+}
+
+int ggcuda_all_gather_bands(ggcuda_ctx* h, void* frame_device, size_t band_bytes) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !frame_device) return c ? fail(c, GGCUDA_ERR_INVALID, "frame is NULL") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (!c->comm) return fail(c, GGCUDA_ERR_INVALID, "ggcuda_comm_init was not called");
+    NcclApi* a = nccl_api(nullptr);
+    CK(cudaSetDevice(c->device));
+    // in place: rank r's band already sits at frame + r * band_bytes (fine wrote it there)
+    ncclResult_t r = a->AllGather((const uint8_t*)frame_device + (size_t)c->comm_rank * band_bytes, frame_device, band_bytes, ncclUint8, c->comm, c->stream);
+    if (r != ncclSuccess) return fail(c, GGCUDA_ERR_CUDA, std::string("ncclAllGather: ") + a->GetErrorString(r));
+    return 0;
+    GG_CATCH(c)
+}
+
+int ggcuda_sync(ggcuda_ctx* h) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (c->host_only) return 0;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+    GG_CATCH(c)
+}
+
+// scene.Encoding.Hash (scene/encoding.go:752-802): 64-bit FNV-1a, one step per ELEMENT of the tag, path-data, draw-data and
+// transform streams (text data: none on this path). The reference leaves the brushes out; a key that decides whether pixels
+// may be re-used must not, so the brush colours' bit patterns are folded in behind the reference's value when given.
+uint64_t ggcuda_encoding_hash(const uint8_t* tags, size_t n_tags, const float* path_data, size_t n_path_data, const uint32_t* draw_data, size_t n_draw_data,
+                              const float* transforms, size_t n_transforms, const double* brushes_rgba, size_t n_brushes) {
+    const uint64_t prime = 1099511628211ull;
+    uint64_t hsh = 14695981039346656037ull;
+    for (size_t i = 0; i < n_tags; i++) { hsh ^= tags[i]; hsh *= prime; }
+    for (size_t i = 0; i < n_path_data; i++) { uint32_t b; memcpy(&b, path_data + i, 4); hsh ^= b; hsh *= prime; }
+    for (size_t i = 0; i < n_draw_data; i++) { hsh ^= draw_data[i]; hsh *= prime; }
+    for (size_t i = 0; i < n_transforms; i++) { uint32_t b; memcpy(&b, transforms + i, 4); hsh ^= b; hsh *= prime; }
+    if (brushes_rgba) for (size_t i = 0; i < 4 * n_brushes; i++) { uint64_t b; memcpy(&b, brushes_rgba + i, 8); hsh ^= b; hsh *= prime; }
+    return hsh;
 }
 
 int ggcuda_get_stats(ggcuda_ctx* h, ggcuda_stats* out) {
@@ -587,6 +882,7 @@ int ggcuda_set_timing(ggcuda_ctx* h, int enabled) {
 long long ggcuda_debug_read(ggcuda_ctx* h, int which, void* dst, size_t cap) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
     if (!c) return GGCUDA_ERR_INVALID;
+    GG_TRY
     const GGBump& bm = c->last_bump;
     const HostScene::Layout& L = c->layout;
     uint32_t bt = band_tiles(c);
@@ -625,6 +921,7 @@ long long ggcuda_debug_read(ggcuda_ctx* h, int which, void* dst, size_t cap) {
         for (size_t i = 0; i < t.size(); i++) s[i] -= t[i].seg_count;
     }
     return (long long)bytes;
+    GG_CATCH(c)
 }
 
 }  // extern "C"

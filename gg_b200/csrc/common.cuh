@@ -10,8 +10,7 @@
 
 #define GG_TILE_W 16
 #define GG_TILE_H 16
-#define GG_SM_COUNT 148            // B200: 2 dies x 74 SMs
-#define GG_SCAN_BLOCKS (GG_SM_COUNT * 4)
+#define GG_SCAN_BLOCKS 592         // CTAs of a chunked scan (4 per SM on a 148-SM B200; any device works, the count is only a partition)
 #define GG_SCAN_THREADS 256
 #define GG_SCAN_ITEMS 4
 #define GG_FINE_PARTS 4            // ggcuda_flush runs fine in up to this many row slices so that read-back overlaps it
@@ -104,8 +103,11 @@ struct GGConfig {
     uint32_t n_implicit, imp_words;         // implicit layers; words per implicit layer in the (layer, tile) bitmap; 0 = no de-duplication
     float bg[4];                            // premultiplied background
     uint32_t flags;
+    uint32_t sm_count;                      // multiprocessors of the device (queried at context creation): grids are multiples of it
 };
-#define GG_FLAG_BG_FROM_DST 1u              // fine starts from the destination pixels (composite-over)
+#define GG_FLAG_BG_FROM_DST 1u              // composite-over: the scene is rasterised on transparent and source-overed onto the
+                                            // destination's pixels with the reference's byte formula (vello_accelerator.go:388-442)
+#define GG_FLAG_TARGET_F32 2u               // destination holds premultiplied float4 pixels (16 bytes) instead of RGBA8
 
 // ---------------------------------------------------------------- strict float32 helpers
 // The integer stages must reproduce the Go reference's float32 arithmetic: no FMA

@@ -1,55 +1,31 @@
 // gg_b200/csrc/fine.cu -- fine rasterisation: per-tile PTCL replay with analytic area coverage.
 //
-// Behavioural spec: gg internal/gpu/tilecompute/fine.go:40-289 (fineRasterizeTile, fillPath),
-// the CPU twin of tilecompute/shaders/fine.wgsl. One warp owns one 16x16 tile; a lane owns
-// 8 consecutive pixels of one row (2 lanes per row), so the per-(segment,row) terms are
-// computed twice per row instead of 16 times as in a thread-per-pixel mapping, and every
-// lane finishes with two 16-byte RGBA8 stores. Segments of a fill are fetched 32 at a time
-// (one per lane, coalesced) and broadcast with shuffles; no shared memory, no block barrier.
+// Behavioural spec: gg internal/gpu/tilecompute/fine.go:40-289 (fineRasterizeTile, fillPath), the CPU twin of
+// tilecompute/shaders/fine.wgsl. One warp owns a PAIR of horizontally adjacent 16x16 tiles (so that every row it
+// finally stores is one full 128-byte line); inside a tile a lane owns 8 consecutive pixels of one row (2 lanes per
+// row), colour in registers. Both input streams of a tile reach shared memory through the bulk-copy engine
+// (cp.async.bulk completing on mbarriers, SASS UBLKCP): the command list in 512-byte chunks through a two-slot ring,
+// and the PathSegment slice of every CmdFill in chunks of 32 segments through a second two-slot ring, the slice of the
+// NEXT fill (found by decoding ahead in the command list) in flight while the current one is evaluated.
+//
+// Coverage (fillPath, fine.go:219-289) without a single atomic: a lane only ever accumulates into ITS OWN row half.
+// The 32 segments of a chunk are first looked at in parallel (lane = segment: row span, 1/dy), a 32x32 bit transpose
+// built from warp ballots hands every (row, half) lane the set of segments that cross its row, and the lane walks
+// that set: the reference's trapezoid formula for the few columns the segment passes through, and ONE entry of a
+// per-lane difference table (fixed point: sums independent of the segment order, frames reproducible bit for bit) for
+// everything to its right (where the formula gives exactly dy). A running sum over the table's 8 entries at the end of
+// the fill yields the areas. Round 1 accumulated (segment, row) pairs with
+// shared-memory float atomics -- 15 ATOMS.CAST.SPIN loops in the innermost loop, 64 cycles per warp-wide atomic
+// (profiles/r1c_fine_kernel_ncu.txt); results also depended on the order the atomics landed in.
 #include "pipeline.cuh"
 
 #define FINE_WARPS 4
 #define PX 8
 
-struct Seg { float p0x, p0y, p1x, p1y, y_edge; };
-
 __device__ __forceinline__ float signum32(float x) {   // util.go:118-130
     return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : ((__float_as_uint(x) >> 31) ? -1.0f : 1.0f));
 }
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
-
-// fine.go:219-289 fillPath for one row (yi) and PX pixels starting at column xb.
-__device__ __forceinline__ void fill_row(float* area, const Seg& s, float yi, float xb) {
-    float dx = s.p1x - s.p0x, dy_seg = s.p1y - s.p0y;
-    float y = s.p0y - yi;
-    float y0 = clamp01(y);
-    float y1 = clamp01(y + dy_seg);
-    float dy = y0 - y1;
-    float y_edge = signum32(dx) * clamp01(yi - s.y_edge + 1.0f);
-    if (dy != 0.0f) {
-        float vec_y_recip = 1.0f / dy_seg;
-        float t0 = (y0 - y) * vec_y_recip;
-        float t1 = (y1 - y) * vec_y_recip;
-        float x0 = s.p0x + t0 * dx;
-        float x1 = s.p0x + t1 * dx;
-        float xmin0 = fminf(x0, x1);
-        float xmax0 = fmaxf(x0, x1);
-#pragma unroll
-        for (int i = 0; i < PX; i++) {
-            float i_f = xb + (float)i;   // absolute column in the tile, as fine.go:259
-            float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
-            float xmax = xmax0 - i_f;
-            float b = fminf(xmax, 1.0f);
-            float c = fmaxf(b, 0.0f);
-            float d = fmaxf(xmin, 0.0f);
-            float a = (b + 0.5f * (d * d - c * c) - xmin) / (xmax - xmin);
-            area[i] += y_edge + a * dy;
-        }
-    } else if (y_edge != 0.0f) {
-#pragma unroll
-        for (int i = 0; i < PX; i++) area[i] += y_edge;
-    }
-}
 
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {   // fine.wgsl:305-323
     uint32_t r = (uint32_t)(clamp01(c.x) * 255.0f + 0.5f);
@@ -149,13 +125,19 @@ __constant__ float4 COMPOSE_COEF[14] = {
     {1, 0, 1, 0},    // Plus (clamped)
     {1, 0, 1, -1},   // PlusLighter: not produced by gg, treated as SrcOver
 };
-// ---------------------------------------------------------------- PTCL streaming through shared memory (TMA)
-// Each warp streams its tile's command list through a private two-slot ring in shared memory: 1-D bulk
-// async copies (cp.async.bulk, SASS UBLKCP) complete on a per-slot mbarrier, the next chunk is in flight
-// while the current one is decoded, and every command word is then a broadcast LDS instead of a dependent,
-// L1-missing global load (the top stall of the first version: 14 % of samples on the tag compare).
-#define PTCL_CHUNK 256   // words per ring slot (1 KiB)
-#define FINE_SMEM_PER_WARP 8272
+
+// ---------------------------------------------------------------- shared memory per warp, bulk copies
+#define PTCL_CHUNK 128   // words per command-ring slot (512 B)
+#define SEG_CHUNK 32     // segments per segment-ring slot (640 B)
+// byte offsets inside a warp's slice of dynamic shared memory
+#define SM_STACK 0       // blend stack level 0: float4 [PX][32]                                    4096
+#define SM_PTCL 4096     // command ring: u32 [2][PTCL_CHUNK]                                        1024
+#define SM_SEGS 5120     // segment ring: GGSegment [2][SEG_CHUNK]                                   1280
+#define SM_DER 6400      // per-segment derived values of the chunk being evaluated: float [3][32]   384
+#define SM_D 6784        // per-lane difference table: int [9][32] (then: RGBA8 image of tile B)     1152
+#define SM_IMG_A 7936    // RGBA8 image of the pair's left tile: u32 [16][16]                        1024
+#define SM_BARS 8960     // 4 mbarriers                                                              32
+#define FINE_SMEM_PER_WARP 9088
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -171,6 +153,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
                  ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 
+// A tile's command list, streamed through a two-slot ring.
 struct PtclStream {
     const uint32_t* src;   // tile's PTCL in global memory (16-byte aligned)
     uint32_t* ring;        // [2][PTCL_CHUNK] in shared memory
@@ -208,8 +191,7 @@ struct PtclStream {
     // Called once per command with the index of its first word (the longest command is 4 words). The ring holds
     // the chunk the command starts in and the next one; the slot of the chunk BEHIND the command start is refilled
     // with the chunk after next. A command may straddle a chunk boundary, so nothing is refilled on the strength
-    // of its later words (refilling when word cmd+3 entered a new chunk overwrote words cmd..cmd+2: long lists,
-    // > 1024 hits in a tile, came out wrong).
+    // of its later words.
     __device__ __forceinline__ void ensure(uint32_t cmd) {
         const uint32_t cur = cmd / PTCL_CHUNK;
         while (issued < cur + 2 && issued * PTCL_CHUNK < len) { __syncwarp(); issue(issued); }
@@ -221,320 +203,441 @@ struct PtclStream {
         }
     }
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
+    // The next CmdFill at or after word c, looking only at words that have already arrived (a few commands ahead).
+    __device__ __forceinline__ bool next_fill(uint32_t c, uint32_t* seg_ix, uint32_t* n) const {
+        const uint32_t avail = min(loaded_end, len);
+#pragma unroll 1
+        for (int hop = 0; hop < 6 && c + 2 < avail; hop++) {
+            const uint32_t tag = word(c);
+            if (tag == GG_CMD_FILL) { *n = word(c + 1) >> 1; *seg_ix = word(c + 2); return true; }
+            else if (tag == GG_CMD_COLOR) c += 2;
+            else if (tag == GG_CMD_END_CLIP) c += 3;
+            else if (tag == GG_CMD_SOLID || tag == GG_CMD_BEGIN_CLIP) c += 1;
+            else return false;
+        }
+        return false;
+    }
 };
 
-// Area of one CmdFill (fine.go:219-276 fillPath) for the 8 pixels of this lane.
-//
-// The reference walks every (segment, row, pixel) triple. Here the 32 lanes first take one segment each and
-// count the rows it crosses, then the warp walks the flattened list of (segment, row) pairs 32 at a time, one
-// pair per lane: a lane evaluates the reference's per-pixel trapezoid formula only for the columns its
-// segment passes through in that row and records the constant winding step (a == 1, exactly dy) of every
-// column to the right as one entry of a per-row suffix table. Both tables live in shared memory and are
-// updated with shared-memory float atomics; a prefix sum over the suffix table at the end gives the same
-// sums the reference accumulates pixel by pixel (up to float reassociation and the <= 1e-7 the reference
-// adds to pixels left of a segment).
-__device__ __forceinline__ void fill_area(float* area, float* acc, float* suf, const GGSegment* __restrict__ segs, uint32_t n,
-                                          float backdrop, uint32_t lane) {
-#pragma unroll
-    for (int i = 0; i < PX; i++) acc[lane * PX + i] = 0.0f;
-    for (uint32_t i = lane; i < 16 * 17; i += 32) suf[i] = 0.0f;
-    __syncwarp();
-    for (uint32_t base = 0; base < n; base += 32) {
-        float p0x = 0, p0y = 0, dxs = 0, dys = 0;
-        int r0 = 0, k = 0;
-        if (base + lane < n) {
-            const GGSegment* sp = segs + base + lane;
-            p0x = sp->p0x; p0y = sp->p0y;
-            float p1x = sp->p1x, p1y = sp->p1y, y_edge = sp->y_edge;
-            dxs = p1x - p0x; dys = p1y - p0y;
-            float ymin = fminf(p0y, p1y), ymax = fmaxf(p0y, p1y);
-            r0 = max(0, min(15, (int)floorf(ymin)));
-            int r1 = max(r0, min(16, (int)ceilf(ymax)));
-            k = (dys != 0.0f) ? r1 - r0 : 0;
-            if (y_edge < 16.0f) {   // segment touches the tile's left edge: winding step for the rows below (fine.go:244)
-                float sgn = signum32(dxs);
-                for (int yi = max(0, (int)floorf(y_edge)); yi < 16; yi++) {
-                    float term = sgn * clamp01((float)yi - y_edge + 1.0f);
-                    if (term != 0.0f) atomicAdd(&suf[yi * 17], term);
-                }
-            }
+// PathSegment slices, streamed through a second two-slot ring in chunks of SEG_CHUNK segments. Chunks start at
+// multiples of four segments (80 bytes) so that every copy is 16-byte aligned; the up to three segments before a
+// slice's first one are skipped by the consumer. One chunk may be in flight ahead of the one being evaluated.
+struct SegStream {
+    const GGSegment* segs;
+    float* ring;           // [2][SEG_CHUNK * 5]
+    uint64_t* bars;        // [2]
+    uint32_t issue_seq, wait_seq;   // chunks handed to the copy engine / consumed (slot = seq & 1, parity = (seq >> 1) & 1)
+    uint32_t ahead_first;  // first segment of the newest chunk in flight (meaningful while issue_seq > wait_seq)
+    uint32_t lane;
+    __device__ __forceinline__ void issue(uint32_t first, uint32_t count) {   // count: segments, rounded up to a multiple of 4
+        if (lane == 0) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            bulk_load(ring + (issue_seq & 1u) * (SEG_CHUNK * 5), segs + first, count * (uint32_t)sizeof(GGSegment), bars + (issue_seq & 1u));
         }
-        // exclusive prefix of rows-per-segment across the warp
-        int incl = k;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { int o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)lane >= d) incl += o; }
-        const int excl = incl - k;
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        for (int q0 = 0; q0 < total; q0 += 32) {
-            const int q = q0 + (int)lane;
-            // owner = last lane whose exclusive prefix is <= q
-            int lo = 0;
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1) {
-                int cand = lo + step;
-                int v = __shfl_sync(0xffffffffu, excl, cand & 31);
-                if (v <= q) lo = cand;
-            }
-            const float sx = __shfl_sync(0xffffffffu, p0x, lo), sy = __shfl_sync(0xffffffffu, p0y, lo);
-            const float sdx = __shfl_sync(0xffffffffu, dxs, lo), sdy = __shfl_sync(0xffffffffu, dys, lo);
-            const int sr0 = __shfl_sync(0xffffffffu, r0, lo), sex = __shfl_sync(0xffffffffu, excl, lo);
-            if (q < total) {
-                const int rowq = sr0 + (q - sex);
-                const float yi = (float)rowq;
-                float y = sy - yi;
-                float y0 = clamp01(y);
-                float y1 = clamp01(y + sdy);
-                float dy = y0 - y1;
-                if (dy != 0.0f) {
-                    float vec_y_recip = __frcp_rn(sdy);
-                    float t0 = (y0 - y) * vec_y_recip;
-                    float t1 = (y1 - y) * vec_y_recip;
-                    float x0 = sx + t0 * sdx;
-                    float x1 = sx + t1 * sdx;
-                    float xmin0 = fminf(x0, x1);
-                    float xmax0 = fmaxf(x0, x1);
-                    int c0 = max(0, (int)floorf(xmin0));
-                    int c1 = min(16, (int)ceilf(xmax0));
-                    for (int col = c0; col < c1; col++) {
-                        float i_f = (float)col;
-                        float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
-                        float xmax = xmax0 - i_f;
-                        float b = fminf(xmax, 1.0f);
-                        float c = fmaxf(b, 0.0f);
-                        float d = fmaxf(xmin, 0.0f);
-                        // numerator evaluated exactly as the reference does (it cancels for near-vertical segments);
-                        // the quotient may be 2 ulp off: far below what survives the 8-bit quantisation
-                        float a = __fdividef(b + 0.5f * (d * d - c * c) - xmin, xmax - xmin);
-                        atomicAdd(&acc[rowq * 16 + col], a * dy);
-                    }
-                    if (c1 < 16) atomicAdd(&suf[rowq * 17 + max(c1, 0)], dy);
-                }
-            }
-        }
+        ahead_first = first;
+        issue_seq++;
     }
-    __syncwarp();
-    const uint32_t row = lane >> 1, xb = (lane & 1u) * PX;
-    float run = 0.0f;
-    float pref[PX];
+    __device__ __forceinline__ const float* wait() {
+        const uint32_t slot = wait_seq & 1u;
+        mbar_wait(bars + slot, (wait_seq >> 1) & 1u);
+        wait_seq++;
+        return ring + slot * (SEG_CHUNK * 5);
+    }
+    __device__ __forceinline__ void drain() { while (wait_seq < issue_seq) wait(); }
+};
+
+// fine.go:233-275 for ONE (segment, row): trapezoid areas of the columns the segment passes through inside this lane's
+// 8-pixel window, and the constant winding step dy for everything to the right, recorded as differences in the lane's
+// table D[col][lane] (column 8 = beyond the window). Operation order of the per-pixel formula as in the reference (its
+// numerator cancels for near-vertical segments; this TU is compiled with -fmad=false).
+// The table holds 2^-20 fixed point: integer sums do not depend on the order the segments of a tile arrive in (path_tiling
+// claims their slots with atomics), so a frame is reproducible bit for bit; the quantisation, 5e-7 per term, is the size of
+// float32's own rounding at these magnitudes. (Windings beyond +-2047 would wrap.)
+#define AREA_FIX 1048576.0f
+__device__ __forceinline__ void seg_row(int* D, uint32_t lane, float yi, int xb, float p0x, float p0y, float dx, float dys, float rc) {
+    const float y = p0y - yi;
+    const float y0 = clamp01(y);
+    const float y1 = clamp01(y + dys);
+    const float dy = y0 - y1;
+    if (dy != 0.0f) {
+        const float t0 = (y0 - y) * rc;
+        const float t1 = (y1 - y) * rc;
+        const float x0 = p0x + t0 * dx;
+        const float x1 = p0x + t1 * dx;
+        const float xmin0 = fminf(x0, x1);
+        const float xmax0 = fmaxf(x0, x1);
+        const int c0 = max((int)floorf(xmin0) - xb, 0);
+        const int c1 = min(max((int)ceilf(xmax0) - xb, 0), PX);
+        int vprev = 0;
+        for (int col = c0; col < c1; col++) {
+            const float i_f = (float)(xb + col);   // absolute column in the tile, as fine.go:259
+            const float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
+            const float xmax = xmax0 - i_f;
+            const float b = fminf(xmax, 1.0f);
+            const float c = fmaxf(b, 0.0f);
+            const float d = fmaxf(xmin, 0.0f);
+            // the quotient may be 2 ulp off the reference's IEEE division: far below what survives the 8-bit quantisation
+            const float a = __fdividef(b + 0.5f * (d * d - c * c) - xmin, xmax - xmin);
+            const int v = __float2int_rn(a * dy * AREA_FIX);
+            D[col * 32 + lane] += v - vprev;
+            vprev = v;
+        }
+        D[c1 * 32 + lane] += __float2int_rn(dy * AREA_FIX) - vprev;
+    }
+}
+
+// Area of one CmdFill (fine.go:219-276 fillPath) for the 8 pixels of this lane.
+__device__ __forceinline__ void fill_area(float* area, int* D, float* der, SegStream& ss, const PtclStream& ps, uint32_t next_cmd,
+                                          uint32_t seg_ix, uint32_t n, float backdrop, uint32_t lane) {
+    const uint32_t row = lane >> 1;
+    const int xb = (int)(lane & 1u) * PX;
+    const float yi = (float)row;
 #pragma unroll
-    for (int i = 0; i < PX; i++) { run += suf[row * 17 + xb + i]; pref[i] = run; }
-    float left = __shfl_xor_sync(0xffffffffu, run, 1);
-    if (!(lane & 1u)) left = 0.0f;
+    for (int i = 0; i <= PX; i++) D[i * 32 + lane] = 0;
+    int base = 0;   // the y_edge terms of this row (fine.go:244: the same for every pixel of the row)
+    const uint32_t lead = seg_ix & 3u, first = seg_ix - lead, total = lead + n;
+    for (uint32_t c0s = 0; c0s < total; c0s += SEG_CHUNK) {
+        const uint32_t cnt = min((uint32_t)SEG_CHUNK, total - c0s);
+        // this chunk: already in flight if the previous fill (or chunk) found it by looking ahead
+        if (!(ss.issue_seq > ss.wait_seq && ss.ahead_first == first + c0s)) {
+            ss.drain();
+            __syncwarp();
+            ss.issue(first + c0s, (cnt + 3u) & ~3u);
+        }
+        // next chunk: of this slice, or the first one of the next CmdFill in the command list
+        if (ss.issue_seq == ss.wait_seq + 1) {
+            if (c0s + SEG_CHUNK < total) {
+                __syncwarp();
+                ss.issue(first + c0s + SEG_CHUNK, (min((uint32_t)SEG_CHUNK, total - c0s - SEG_CHUNK) + 3u) & ~3u);
+            } else {
+                uint32_t nseg_ix, nn;
+                if (ps.next_fill(next_cmd, &nseg_ix, &nn)) {
+                    const uint32_t nlead = nseg_ix & 3u;
+                    __syncwarp();
+                    ss.issue(nseg_ix - nlead, (min((uint32_t)SEG_CHUNK, nlead + nn) + 3u) & ~3u);
+                }
+            }
+        }
+        const float* sg = ss.wait();
+        // ---- lane = segment: row span, derived values
+        const uint32_t k = c0s + lane;
+        const bool valid = k >= lead && k < total && lane < cnt;
+        uint32_t rows = 0;
+        bool left = false, edge = false;
+        float ye = 0.0f, sgn = 0.0f;
+        if (valid) {
+            const float p0x = sg[lane * 5 + 0], p0y = sg[lane * 5 + 1], p1x = sg[lane * 5 + 2], p1y = sg[lane * 5 + 3];
+            ye = sg[lane * 5 + 4];
+            const float dx = p1x - p0x, dys = p1y - p0y;
+            der[lane] = dx; der[32 + lane] = dys; der[64 + lane] = __frcp_rn(dys);
+            if (dys != 0.0f) {
+                const float ymin = fminf(p0y, p1y), ymax = fmaxf(p0y, p1y);
+                const int r0 = max(0, min(15, (int)floorf(ymin)));
+                const int r1 = max(r0 + 1, min(16, (int)ceilf(ymax)));
+                rows = (0xffffu >> (16 - (r1 - r0))) << r0;
+            }
+            left = fminf(p0x, p1x) < (float)PX;
+            edge = ye < 16.0f;   // touches the tile's left edge: winding step for the rows from y_edge down (fine.go:244)
+            sgn = signum32(dx);
+        }
+        __syncwarp();
+        uint32_t em = __ballot_sync(0xffffffffu, edge);
+        while (em) {
+            const int j = __ffs((int)em) - 1;
+            em &= em - 1u;
+            const float yej = __shfl_sync(0xffffffffu, ye, j), sj = __shfl_sync(0xffffffffu, sgn, j);
+            base += __float2int_rn(sj * clamp01(yi - yej + 1.0f) * AREA_FIX);
+        }
+        // ---- which segments does my row (half) need? 32 x 32 bit transpose by ballots; tiny chunks: everybody looks at all
+        const uint32_t vm = __ballot_sync(0xffffffffu, rows != 0u);
+        uint32_t mine;
+        if (__popc(vm) <= 3) {
+            mine = vm;
+        } else {
+            mine = 0;
 #pragma unroll
-    for (int i = 0; i < PX; i++) area[i] = backdrop + acc[lane * PX + i] + (pref[i] + left);
-    __syncwarp();
+            for (uint32_t r = 0; r < 16; r++) {
+                const uint32_t m = __ballot_sync(0xffffffffu, (rows >> r) & 1u);
+                if (row == r) mine = m;
+            }
+            const uint32_t lm = __ballot_sync(0xffffffffu, left);
+            if (xb == 0) mine &= lm;   // a segment that stays in the right half leaves the left half's pixels alone
+        }
+        // ---- lane = (row, half): walk the segments that cross the row
+        while (__any_sync(0xffffffffu, mine != 0u)) {
+            if (mine) {
+                const int j = __ffs((int)mine) - 1;
+                mine &= mine - 1u;
+                seg_row(D, lane, yi, xb, sg[j * 5 + 0], sg[j * 5 + 1], der[j], der[32 + j], der[64 + j]);
+            }
+        }
+        __syncwarp();
+    }
+    int run = base;
+#pragma unroll
+    for (int i = 0; i < PX; i++) { run += D[i * 32 + lane]; area[i] = backdrop + (float)run * (1.0f / AREA_FIX); }
+}
+
+// VelloAccelerator.compositeOver (vello_accelerator.go:388-442) for one pixel: the scene was rasterised on transparent,
+// s = its premultiplied RGBA8 pixel, d = the target's; bytes, (d * inv + 127) / 255, uint8 wrap-around as in Go.
+__device__ __forceinline__ uint32_t composite_over_u8(uint32_t s, uint32_t d) {
+    const uint32_t sa = s >> 24;
+    if (sa == 0u) return d;
+    if (sa == 255u) return s;
+    const uint32_t inv = 255u - sa;
+    uint32_t o = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t sc = (s >> (8 * k)) & 0xffu, dc = (d >> (8 * k)) & 0xffu;
+        o |= ((sc + ((dc * inv + 127u) / 255u)) & 0xffu) << (8 * k);
+    }
+    return o;
 }
 
 __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
-                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, uint32_t tile0, uint32_t tile1, uint32_t part, GGFineMirrors mir) {
+                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, GGFineRange rg, uint32_t part, GGFineMirrors mir) {
     // a stage overflowed its buffer: PTCL / segments are incomplete, the host re-runs the pass with larger buffers
     if (bump->failed || bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap || bump->segments > cfg.segments_cap) return;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t row = lane >> 1;
     const uint32_t xb = (lane & 1u) * PX;
-    // per-warp slice of dynamic shared memory (FINE_SMEM_PER_WARP bytes, opt-in above 48 KiB):
-    //   [0, 4096)      blend stack level 0: float4 [1][PX][32]
-    //   [4096, 6144)   PTCL ring: u32 [2][PTCL_CHUNK]
-    //   [6144, 7168)   area accumulators: float [256]
-    //   [7168, 8256)   row suffix table: float [16][17]
-    //   [8256, 8272)   two mbarriers
     extern __shared__ __align__(128) unsigned char fine_smem[];
     unsigned char* wsm = fine_smem + (size_t)(threadIdx.x >> 5) * FINE_SMEM_PER_WARP;
-    float4 (*sstk)[PX][32] = reinterpret_cast<float4 (*)[PX][32]>(wsm);
-    float* acc = reinterpret_cast<float*>(wsm + 6144);
-    float* suf = reinterpret_cast<float*>(wsm + 7168);
+    float4 (*sstk)[PX][32] = reinterpret_cast<float4 (*)[PX][32]>(wsm + SM_STACK);
+    int* D = reinterpret_cast<int*>(wsm + SM_D);
+    float* der = reinterpret_cast<float*>(wsm + SM_DER);
+    uint32_t* img_a = reinterpret_cast<uint32_t*>(wsm + SM_IMG_A);
+    uint32_t* img_b = reinterpret_cast<uint32_t*>(wsm + SM_D);   // the difference table is idle between tiles
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + SM_BARS);
     PtclStream ps;
-    ps.ring = reinterpret_cast<uint32_t*>(wsm + 4096); ps.bars = reinterpret_cast<uint64_t*>(wsm + 8256); ps.parity = 0; ps.issued = 0; ps.loaded_end = 0; ps.lane = threadIdx.x & 31;
-    if ((threadIdx.x & 31) == 0) {
-        mbar_init(ps.bars + 0, 1); mbar_init(ps.bars + 1, 1);
+    ps.ring = reinterpret_cast<uint32_t*>(wsm + SM_PTCL); ps.bars = bars; ps.parity = 0; ps.issued = 0; ps.loaded_end = 0; ps.lane = lane;
+    ps.src = ptcl; ps.len = 0;
+    SegStream ss;
+    ss.segs = segments; ss.ring = reinterpret_cast<float*>(wsm + SM_SEGS); ss.bars = bars + 2; ss.issue_seq = 0; ss.wait_seq = 0; ss.ahead_first = 0; ss.lane = lane;
+    if (lane == 0) {
+        mbar_init(bars + 0, 1); mbar_init(bars + 1, 1); mbar_init(bars + 2, 1); mbar_init(bars + 3, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    // Blend stack (fine.go:58-62 keeps 4 levels "in registers" and spills deeper ones; where a level lives is
-    // invisible in the output). Levels 0-1 live in shared memory ([level][pixel][lane]: conflict-free 128-bit
-    // accesses), deeper levels in the global spill buffer coarse sized for this tile. A local-memory stack
-    // pushed ~10 GB of write-through traffic to L2 per 4K frame of the benchmark scene (73 composites per tile).
-
-    // Tiles are handed out from a shared cursor: their cost varies by orders of magnitude (restart points make most of
-    // them trivial), a static stride left warps idle behind the heavy ones.
+    const bool over = (cfg.flags & GG_FLAG_BG_FROM_DST) != 0u;    // composite the scene over the target's pixels at the end
+    const bool f32_out = (cfg.flags & GG_FLAG_TARGET_F32) != 0u;  // premultiplied float4 per pixel instead of RGBA8
+    const float4 bgc = over ? make_float4(0, 0, 0, 0) : make_float4(cfg.bg[0], cfg.bg[1], cfg.bg[2], cfg.bg[3]);
+    const uint32_t npx = rg.px1 - rg.px0;                         // tile pairs per row of this launch
+    const uint32_t n_pairs = npx * (rg.row1 - rg.row0);
+    // Pairs are handed out from a shared cursor: their cost varies by orders of magnitude (restart points make most
+    // tiles of a scene with opaque content trivial), a static stride left warps idle behind the heavy ones.
     for (;;) {
-        uint32_t T = 0;
-        if (lane == 0) T = tile0 + atomicAdd(&bump->fine_cursor[part], 1u);
-        T = __shfl_sync(0xffffffffu, T, 0);
-        if (T >= tile1) break;
-        const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
-        const uint32_t px = tx * GG_TILE_W + xb, py = ty * GG_TILE_H + row;
+        uint32_t P = 0;
+        if (lane == 0) P = atomicAdd(&bump->fine_cursor[part], 1u);
+        P = __shfl_sync(0xffffffffu, P, 0);
+        if (P >= n_pairs) break;
+        const uint32_t trow = rg.row0 + P / npx;                  // tile row, relative to the band
+        const uint32_t pcol = rg.px0 + P % npx;
+        const uint32_t py = (trow + cfg.band_y0) * GG_TILE_H + row;
         const bool row_in = py < cfg.height;
-        uint8_t* out = dst + (size_t)(py - cfg.band_y0 * GG_TILE_H) * stride + (size_t)px * 4;
-        float4 rgba[PX];
-        float area[PX];
-        // coarse found the last command of this tile that overwrites every pixel whatever came before (an opaque
-        // solid colour or a backdrop-wiping layer at clip depth 0): start right after it, from that colour
-        const uint32_t restart = restart_pt[2 * T];
-        if (restart) {
-            const float4 c0 = unpack_rgba8(restart_pt[2 * T + 1]);
+        for (uint32_t half = 0; half < 2; half++) {
+            const uint32_t tx = pcol * 2 + half;
+            if (tx >= cfg.width_in_tiles) break;
+            const uint32_t T = trow * cfg.width_in_tiles + tx;
+            float4 rgba[PX];
+            float area[PX];
+            // coarse found the last command of this tile that overwrites every pixel whatever came before (an opaque
+            // solid colour or a backdrop-wiping layer at clip depth 0): start right after it, from that colour
+            const uint32_t restart = restart_pt[2 * T];
+            {
+                const float4 c0 = restart ? unpack_rgba8(restart_pt[2 * T + 1]) : bgc;
 #pragma unroll
-            for (int i = 0; i < PX; i++) rgba[i] = c0;
-        } else if (cfg.flags & GG_FLAG_BG_FROM_DST) {
-#pragma unroll
-            for (int i = 0; i < PX; i++) {
-                uint32_t c = 0;
-                if (row_in && px + i < cfg.width) c = reinterpret_cast<const uint32_t*>(out)[i];
-                rgba[i] = unpack_rgba8(c);
+                for (int i = 0; i < PX; i++) { rgba[i] = c0; area[i] = 0.0f; }
             }
-        } else {
+            uint32_t clip_depth = 0;
+            uint32_t cmd = restart ? restart : 1u;   // word 0 = blend offset (ptcl.go:98)
+            ps.begin(ptcl + ptcl_off[T], ptcl_len[T], cmd / PTCL_CHUNK);
+            const uint32_t sp_off = spill_off[T];
+            for (;;) {
+                ps.ensure(cmd);
+                const uint32_t tag = ps.word(cmd);
+                if (tag == GG_CMD_FILL) {
+                    const uint32_t packed = ps.word(cmd + 1), seg_ix = ps.word(cmd + 2);
+                    const float backdrop = (float)(int32_t)ps.word(cmd + 3);
+                    cmd += 4;
+                    fill_area(area, D, der, ss, ps, cmd, seg_ix, packed >> 1, backdrop, lane);
+                    if (packed & 1u) {
 #pragma unroll
-            for (int i = 0; i < PX; i++) rgba[i] = make_float4(cfg.bg[0], cfg.bg[1], cfg.bg[2], cfg.bg[3]);
-        }
-#pragma unroll
-        for (int i = 0; i < PX; i++) area[i] = 0.0f;
-        uint32_t clip_depth = 0;
-        uint32_t cmd = restart ? restart : 1u;   // word 0 = blend offset (ptcl.go:98)
-        ps.begin(ptcl + ptcl_off[T], ptcl_len[T], cmd / PTCL_CHUNK);
-        const uint32_t sp_off = spill_off[T];
-        for (;;) {
-            ps.ensure(cmd);
-            const uint32_t tag = ps.word(cmd);
-            if (tag == GG_CMD_FILL) {
-                const uint32_t packed = ps.word(cmd + 1), seg_ix = ps.word(cmd + 2);
-                const float backdrop = (float)(int32_t)ps.word(cmd + 3);
-                cmd += 4;
-                fill_area(area, acc, suf, segments + seg_ix, packed >> 1, backdrop, lane);
-                const bool even_odd = packed & 1u;
-#pragma unroll
-                for (int i = 0; i < PX; i++) {
-                    float a = area[i];
-                    area[i] = even_odd ? fabsf(a - 2.0f * roundf(0.5f * a))    // fine.go:281
-                                       : fminf(fabsf(a), 1.0f);                // fine.go:286
-                }
-            } else if (tag == GG_CMD_SOLID) {
-                cmd += 1;
-#pragma unroll
-                for (int i = 0; i < PX; i++) area[i] = 1.0f;
-            } else if (tag == GG_CMD_COLOR) {
-                const float4 c = unpack_rgba8(ps.word(cmd + 1));
-                cmd += 2;
-#pragma unroll
-                for (int i = 0; i < PX; i++) {   // fine.go:104-123
-                    float cov = area[i];
-                    float fr = c.x * cov, fg = c.y * cov, fb = c.z * cov, fa = c.w * cov;
-                    float inv = 1.0f - fa;
-                    rgba[i].x = fmaf(rgba[i].x, inv, fr); rgba[i].y = fmaf(rgba[i].y, inv, fg);
-                    rgba[i].z = fmaf(rgba[i].z, inv, fb); rgba[i].w = fmaf(rgba[i].w, inv, fa);
-                }
-            } else if (tag == GG_CMD_BEGIN_CLIP) {   // fine.go:125-138
-                cmd += 1;
-                float4* slot; uint32_t step;
-                if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
-                else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
-                if (clip_depth < GG_BLEND_STACK_SPLIT || sp_off != 0xffffffffu) {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) { slot[i * step] = rgba[i]; }
-                }
-                clip_depth++;
-#pragma unroll
-                for (int i = 0; i < PX; i++) rgba[i] = make_float4(0, 0, 0, 0);
-            } else if (tag == GG_CMD_END_CLIP) {     // fine.go:140-180
-                const uint32_t blend = ps.word(cmd + 1) & 0x3fffffffu;   // bits 30-31 are coarse's layer flags
-                const float alpha = __uint_as_float(ps.word(cmd + 2));
-                cmd += 3;
-                if (clip_depth == 0) continue;
-                clip_depth--;
-                const float4* slot; uint32_t step;
-                if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
-                else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
-                const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
-                // Scaling the source by the coverage (fine.go:152-160) equals out = D + cov (blend(S, D) - D) for every mode
-                // whose backdrop factor is 1 under a transparent source; the six compose modes that wipe their backdrop
-                // are blended at full strength and interpolated instead (a pixel the layer's clip does not cover stays).
-                const bool wipe = mix == 0u && (compose == 0u || compose == 1u || compose == 5u || compose == 6u || compose == 7u || compose == 10u);
-#pragma unroll
-                for (int i = 0; i < PX; i++) {
-                    float scale = wipe ? alpha : area[i] * alpha;   // fg = rgba * area * alpha, in place
-                    rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
-                }
-                if (mix != 0u && mix < 16u) {
-                    // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source); only
-                    // pixels where both are visible take the (un-premultiply, mix, re-compose) path
-#pragma unroll
-                    for (int i = 0; i < PX; i++) {
-                        const float4 sv = slot[i * step];
-                        if (rgba[i].w <= 0.0f) rgba[i] = sv;
-                        else if (sv.w > 0.0f) rgba[i] = blend_mix_px(mix, sv, rgba[i]);
-                    }
-                } else {
-                    // Porter-Duff: Fa * S + Fb * D. Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}.
-                    const float4 k = COMPOSE_COEF[min(compose, 13u)];
-                    const bool plus = compose == 12u;
-#pragma unroll
-                    for (int i = 0; i < PX; i++) {
-                        const float4 sv = slot[i * step];
-                        float fa = k.x + k.y * sv.w, fb = k.z + k.w * rgba[i].w;
-                        float4 o;
-                        o.x = fmaf(fb, sv.x, fa * rgba[i].x); o.y = fmaf(fb, sv.y, fa * rgba[i].y);
-                        o.z = fmaf(fb, sv.z, fa * rgba[i].z); o.w = fmaf(fb, sv.w, fa * rgba[i].w);
-                        if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
-                        if (wipe) { const float cv = area[i]; o.x = sv.x + cv * (o.x - sv.x); o.y = sv.y + cv * (o.y - sv.y); o.z = sv.z + cv * (o.z - sv.z); o.w = sv.w + cv * (o.w - sv.w); }
-                        rgba[i] = o;
-                    }
-                }
-            } else {
-                break;   // CmdEnd, or an unknown command: stop (fine.go:182-185)
-            }
-        }
-        if (row_in) {
-            uint32_t o[PX];
-#pragma unroll
-            for (int i = 0; i < PX; i++) o[i] = pack_rgba8(rgba[i]);
-            const size_t off = (size_t)(py - cfg.band_y0 * GG_TILE_H) * stride + (size_t)px * 4;
-            if (px + PX <= cfg.width && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
-                reinterpret_cast<uint4*>(out)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                reinterpret_cast<uint4*>(out)[1] = make_uint4(o[4], o[5], o[6], o[7]);
-            } else {
-#pragma unroll
-                for (int i = 0; i < PX; i++) if (px + i < cfg.width) reinterpret_cast<uint32_t*>(out)[i] = o[i];
-            }
-            // Multi-GPU: the band also goes straight into the other devices' frames (peer memory over NVLink / NVSwitch) while
-            // the rest of the band is still being rasterised -- the all-gather of bands, fused into the kernel that makes them.
-            if (mir.multicast) {   // one multimem store per 16 bytes: the switch replicates it to every device of the group
-                uint8_t* m = mir.p[0] + off;
-                if (px + PX <= cfg.width && ((reinterpret_cast<uintptr_t>(m) & 15u) == 0)) {
-                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m), "f"(__uint_as_float(o[0])), "f"(__uint_as_float(o[1])),
-                                 "f"(__uint_as_float(o[2])), "f"(__uint_as_float(o[3])) : "memory");
-                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m + 16), "f"(__uint_as_float(o[4])), "f"(__uint_as_float(o[5])),
-                                 "f"(__uint_as_float(o[6])), "f"(__uint_as_float(o[7])) : "memory");
-                } else {
-#pragma unroll
-                    for (int i = 0; i < PX; i++) if (px + i < cfg.width) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(m + 4 * i), "f"(__uint_as_float(o[i])) : "memory");
-                }
-            } else {
-                for (uint32_t k = 0; k < mir.n; k++) {
-                    uint8_t* m = mir.p[k] + off;
-                    if (px + PX <= cfg.width && ((reinterpret_cast<uintptr_t>(m) & 15u) == 0)) {
-                        reinterpret_cast<uint4*>(m)[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        reinterpret_cast<uint4*>(m)[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                        for (int i = 0; i < PX; i++) { const float a = area[i]; area[i] = fabsf(a - 2.0f * roundf(0.5f * a)); }   // fine.go:281
                     } else {
 #pragma unroll
-                        for (int i = 0; i < PX; i++) if (px + i < cfg.width) reinterpret_cast<uint32_t*>(m)[i] = o[i];
+                        for (int i = 0; i < PX; i++) area[i] = fminf(fabsf(area[i]), 1.0f);                                      // fine.go:286
+                    }
+                } else if (tag == GG_CMD_SOLID) {
+                    cmd += 1;
+#pragma unroll
+                    for (int i = 0; i < PX; i++) area[i] = 1.0f;
+                } else if (tag == GG_CMD_COLOR) {
+                    const float4 c = unpack_rgba8(ps.word(cmd + 1));
+                    cmd += 2;
+#pragma unroll
+                    for (int i = 0; i < PX; i++) {   // fine.go:104-123: rgba * (1 - c.a * cov) + c * cov, two FMAs per channel
+                        const float cov = area[i];
+                        rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
+                        rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
+                        rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);
+                        rgba[i].w = fmaf(cov, fmaf(-c.w, rgba[i].w, c.w), rgba[i].w);
+                    }
+                } else if (tag == GG_CMD_BEGIN_CLIP) {   // fine.go:125-138
+                    cmd += 1;
+                    // Blend stack (fine.go:58-62 keeps 4 levels "in registers" and spills deeper ones; where a level lives is
+                    // invisible in the output): level 0 in shared memory ([pixel][lane]: conflict-free 128-bit accesses),
+                    // deeper levels in the global spill buffer coarse sized for this tile.
+                    float4* slot; uint32_t step;
+                    if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
+                    else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
+                    if (clip_depth < GG_BLEND_STACK_SPLIT || sp_off != 0xffffffffu) {
+#pragma unroll
+                        for (int i = 0; i < PX; i++) { slot[i * step] = rgba[i]; }
+                    }
+                    clip_depth++;
+#pragma unroll
+                    for (int i = 0; i < PX; i++) rgba[i] = make_float4(0, 0, 0, 0);
+                } else if (tag == GG_CMD_END_CLIP) {     // fine.go:140-180
+                    const uint32_t blend = ps.word(cmd + 1) & 0x3fffffffu;   // bits 30-31 are coarse's layer flags
+                    const float alpha = __uint_as_float(ps.word(cmd + 2));
+                    cmd += 3;
+                    if (clip_depth == 0) continue;
+                    clip_depth--;
+                    const float4* slot; uint32_t step;
+                    if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
+                    else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
+                    const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
+                    // Scaling the source by the coverage (fine.go:152-160) equals out = D + cov (blend(S, D) - D) for every mode
+                    // whose backdrop factor is 1 under a transparent source; the six compose modes that wipe their backdrop
+                    // are blended at full strength and interpolated instead (a pixel the layer's clip does not cover stays).
+                    const bool wipe = mix == 0u && (compose == 0u || compose == 1u || compose == 5u || compose == 6u || compose == 7u || compose == 10u);
+#pragma unroll
+                    for (int i = 0; i < PX; i++) {
+                        float scale = wipe ? alpha : area[i] * alpha;   // fg = rgba * area * alpha, in place
+                        rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
+                    }
+                    if (mix != 0u && mix < 16u) {
+                        // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source); only
+                        // pixels where both are visible take the (un-premultiply, mix, re-compose) path
+#pragma unroll
+                        for (int i = 0; i < PX; i++) {
+                            const float4 sv = slot[i * step];
+                            if (rgba[i].w <= 0.0f) rgba[i] = sv;
+                            else if (sv.w > 0.0f) rgba[i] = blend_mix_px(mix, sv, rgba[i]);
+                        }
+                    } else {
+                        // Porter-Duff: Fa * S + Fb * D. Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}.
+                        const float4 k = COMPOSE_COEF[min(compose, 13u)];
+                        const bool plus = compose == 12u;
+#pragma unroll
+                        for (int i = 0; i < PX; i++) {
+                            const float4 sv = slot[i * step];
+                            float fa = k.x + k.y * sv.w, fb = k.z + k.w * rgba[i].w;
+                            float4 o;
+                            o.x = fmaf(fb, sv.x, fa * rgba[i].x); o.y = fmaf(fb, sv.y, fa * rgba[i].y);
+                            o.z = fmaf(fb, sv.z, fa * rgba[i].z); o.w = fmaf(fb, sv.w, fa * rgba[i].w);
+                            if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
+                            if (wipe) { const float cv = area[i]; o.x = sv.x + cv * (o.x - sv.x); o.y = sv.y + cv * (o.y - sv.y); o.z = sv.z + cv * (o.z - sv.z); o.w = sv.w + cv * (o.w - sv.w); }
+                            rgba[i] = o;
+                        }
+                    }
+                } else {
+                    break;   // CmdEnd, or an unknown command: stop (fine.go:182-185)
+                }
+            }
+            ss.drain();   // a slice fetched ahead for a fill that never came (cannot happen with a well-formed list)
+            if (f32_out) {
+                // premultiplied float4 per pixel: 8 x 16 bytes, one full 128-byte line per lane
+                const uint32_t px = tx * GG_TILE_W + xb;
+                if (row_in) {
+                    float4* o = reinterpret_cast<float4*>(dst + (size_t)(py - cfg.band_y0 * GG_TILE_H) * stride + (size_t)px * 16);
+#pragma unroll
+                    for (int i = 0; i < PX; i++)
+                        if (px + i < cfg.width) o[i] = make_float4(clamp01(rgba[i].x), clamp01(rgba[i].y), clamp01(rgba[i].z), clamp01(rgba[i].w));
+                }
+            } else {
+                // RGBA8 image of the tile in shared memory: rows of 64 bytes
+                uint32_t o[PX];
+#pragma unroll
+                for (int i = 0; i < PX; i++) o[i] = pack_rgba8(rgba[i]);
+                uint4* im = reinterpret_cast<uint4*>((half ? img_b : img_a) + row * 16 + xb);
+                im[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                im[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            }
+        }
+        if (f32_out) continue;
+        __syncwarp();
+        // ---- store the pair: a lane takes 16 bytes, eight lanes one 128-byte row of the pair, the warp four rows per pass.
+        //      Multi-GPU: the same 128-byte lines also go straight into the other devices' frames (peer memory over NVLink, or
+        //      one multimem store that the NVSwitch replicates to every device of the group) while the rest of the band is
+        //      still being rasterised -- the all-gather of bands, fused into the kernel that makes them.
+#pragma unroll 1
+        for (uint32_t k = 0; k < 4; k++) {
+            const uint32_t r = k * 4 + (lane >> 3), chunk = lane & 7u, half = chunk >> 2, cq = chunk & 3u;
+            uint4 v = *reinterpret_cast<const uint4*>((half ? img_b : img_a) + r * 16 + cq * 4);
+            const uint32_t x = (pcol * 2 + half) * GG_TILE_W + cq * 4;
+            const uint32_t y = (trow + cfg.band_y0) * GG_TILE_H + r;
+            if (y >= cfg.height || x >= cfg.width) continue;
+            const size_t off = (size_t)(y - cfg.band_y0 * GG_TILE_H) * stride + (size_t)x * 4;
+            uint8_t* out = dst + off;
+            const bool full = x + 4 <= cfg.width;
+            if (full && ((reinterpret_cast<uintptr_t>(out) & 15u) == 0)) {
+                if (over) {
+                    const uint4 d = *reinterpret_cast<const uint4*>(out);
+                    v.x = composite_over_u8(v.x, d.x); v.y = composite_over_u8(v.y, d.y); v.z = composite_over_u8(v.z, d.z); v.w = composite_over_u8(v.w, d.w);
+                }
+                *reinterpret_cast<uint4*>(out) = v;
+            } else {
+                uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) if (x + i < cfg.width) {
+                    uint32_t* po = reinterpret_cast<uint32_t*>(out) + i;
+                    if (over) vv[i] = composite_over_u8(vv[i], *po);
+                    *po = vv[i];
+                }
+                v = make_uint4(vv[0], vv[1], vv[2], vv[3]);
+            }
+            if (mir.multicast) {
+                uint8_t* m = mir.p[0] + off;
+                if (full && ((reinterpret_cast<uintptr_t>(m) & 15u) == 0)) {
+                    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(m), "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)),
+                                 "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w)) : "memory");
+                } else {
+                    const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) if (x + i < cfg.width) asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(m + 4 * i), "f"(__uint_as_float(vv[i])) : "memory");
+                }
+            } else {
+                for (uint32_t q = 0; q < mir.n; q++) {
+                    uint8_t* m = mir.p[q] + off;
+                    if (full && ((reinterpret_cast<uintptr_t>(m) & 15u) == 0)) {
+                        *reinterpret_cast<uint4*>(m) = v;
+                    } else {
+                        const uint32_t vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int i = 0; i < 4; i++) if (x + i < cfg.width) reinterpret_cast<uint32_t*>(m)[i] = vv[i];
                     }
                 }
             }
         }
+        __syncwarp();
     }
 }
 
-void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part,
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, const GGFineRange& rg, uint32_t part,
                     const GGFineMirrors& mir) {
-    // tile rows [row0, row1) relative to the band; `part` selects the work cursor (each launch of a frame needs its own)
-    uint32_t n_tiles = cfg.width_in_tiles * (row1 - row0);
-    uint32_t blocks = (n_tiles + FINE_WARPS - 1) / FINE_WARPS;
-    uint32_t max_blocks = GG_SM_COUNT * 16;
+    // tile rows [row0, row1) relative to the band, tile-pair columns [px0, px1); `part` selects the work cursor (each
+    // launch of a frame needs its own)
+    if (rg.row1 <= rg.row0 || rg.px1 <= rg.px0) return;
+    uint32_t n_pairs = (rg.px1 - rg.px0) * (rg.row1 - rg.row0);
+    uint32_t blocks = (n_pairs + FINE_WARPS - 1) / FINE_WARPS;
+    uint32_t max_blocks = cfg.sm_count * 6;   // resident CTAs: 6 per SM (shared memory, registers)
     if (blocks > max_blocks) blocks = max_blocks;
-    if (blocks == 0) return;
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
     fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride,
-                                                      cfg.width_in_tiles * row0, cfg.width_in_tiles * row1, part, mir);
+                                                      rg, part, mir);
 }

@@ -51,8 +51,21 @@ void HostScene::clear(uint32_t w, uint32_t h) {
     tags.clear(); path_data.clear(); draw_tags.clear(); draw_data.clear(); styles.clear(); transforms.clear();
     clip_aux.clear(); clip_stack.clear(); clip_kind.clear(); clip_bb.clear();
     next_clip_bb[0] = next_clip_bb[1] = -3.0e38f; next_clip_bb[2] = next_clip_bb[3] = 3.0e38f;
-    n_paths = n_clips = n_seg_tags = n_implicit = 0;
+    n_paths = n_clips = n_seg_tags = n_implicit = n_culled = 0;
     have_transform = false; in_path = false; has_move = false;
+}
+
+// True if every control point (the curve lies inside their hull), moved by `reach`, misses the band's pixel rows.
+// A pixel of slack covers the flattening tolerance and the float32 rounding of the device-side transform.
+bool HostScene::outside_band(const float t[6], const float* c, size_t n_coords, float reach) const {
+    if (!cull || n_coords < 2) return false;
+    float lo = 3.0e38f, hi = -3.0e38f;
+    for (size_t k = 0; k + 1 < n_coords; k += 2) {
+        float y = t[3] * c[k] + t[4] * c[k + 1] + t[5];
+        if (!(y == y)) return false;
+        lo = y < lo ? y : lo; hi = y > hi ? y : hi;
+    }
+    return hi + reach + 1.0f < cull_lo || lo - reach - 1.0f > cull_hi;
 }
 
 void HostScene::begin_path(const float t[6], bool even_odd) {
@@ -520,14 +533,24 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
             flush_layer();
             uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
-            if (path_active && pt1 > pt0) { fill_verbs(cur_t, style == 1, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, verb_map.m); draw_color(brush_color(brushes, n_brushes, bix)); }
+            if (path_active && pt1 > pt0) {
+                if (outside_band(cur_t, pd + pp0, pi - pp0, 0.0f)) n_culled++;
+                else { fill_verbs(cur_t, style == 1, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, verb_map.m); draw_color(brush_color(brushes, n_brushes, bix)); }
+            }
             path_active = false;
         } break;
         case ST_STROKE: {
             if (di + 5 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
             flush_layer();
             uint32_t bix = dd[di];
-            if (path_active && pt1 > pt0) {
+            float sw = 0, sml = 0;
+            memcpy(&sw, dd + di + 1, 4); memcpy(&sml, dd + di + 2, 4);
+            // reach of the outline beyond the centre line: half the width, miter tips up to miter_limit times that
+            const float reach = 0.5f * (sw > 0 ? sw : 0) * ((dd[di + 4] == 0 && sml > 1.5f) ? sml : 1.5f);
+            if (path_active && pt1 > pt0 && outside_band(cur_t, pd + pp0, pi - pp0, reach)) {
+                n_culled++;
+                if (host_strokes && next_job < jobs.size()) next_job++;
+            } else if (path_active && pt1 > pt0) {
                 if (host_strokes) {
                     if (next_job < jobs.size()) { begin_path(IDENTITY, false); append_stroke(jobs[next_job++].out); end_path(); }
                     else { begin_path(IDENTITY, false); end_path(); }

@@ -38,6 +38,12 @@ struct HostScene {
     void set_next_clip_bounds(const float transform[6], const uint8_t* verbs, size_t n_verbs, const float* coords, size_t n_coords,
                               const uint8_t* verb_map = nullptr);
     uint32_t n_paths = 0, n_clips = 0, n_seg_tags = 0, n_implicit = 0;
+    // Multi-GPU bands: fills and strokes of a scene.Encoding whose control points (plus the stroke's reach) stay outside the
+    // pixel rows [cull_lo, cull_hi) of this device's band are dropped at ingest -- they own no tile there -- so that the
+    // packed scene, its upload and every per-path stage shrink with the band. Clips and layers are always kept.
+    bool cull = false; float cull_lo = 0, cull_hi = 0; uint32_t n_culled = 0;
+    void set_cull_band(float lo, float hi) { cull = true; cull_lo = lo; cull_hi = hi; }
+    bool outside_band(const float t[6], const float* c, size_t n_coords, float reach) const;
     float last_transform[6] = {0, 0, 0, 0, 0, 0};
     bool have_transform = false;
     // current path state

@@ -18,7 +18,7 @@
 #include <cooperative_groups.h>
 namespace cg = cooperative_groups;
 
-#define GG_GRID(blocks_per_sm) (GG_SM_COUNT * (blocks_per_sm))
+#define GG_GRID(blocks_per_sm) (cfg.sm_count * (blocks_per_sm))
 
 // ------------------------------------------------------------------ monoids
 __device__ __forceinline__ GGPathMonoid path_monoid_new(uint32_t tag_word) {   // pathtag.go:26-63
@@ -724,6 +724,10 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
         uint32_t base = path.tiles + y * bw;
         uint32_t gy = path.bbox[1] + y - cfg.band_y0;
         uint32_t tag = scene[cfg.draw_tag_base + p];   // one path marker per draw object: path p <-> draw p
+        // Even-odd fills: a tile without segments is inside only where the winding is odd. (DEVIATION: coarse.go:425
+        // paints every tile with backdrop != 0 solid whatever the rule -- the hole of two nested same-direction
+        // contours, backdrop 2, came out filled. The oracle follows; ot_evenodd_solid_quirk restores the reference.)
+        const bool even_odd = tag == GG_DRAWTAG_COLOR && recs[p].b != 0u;
         // Implicit layers (GG_BLEND_IMPLICIT: no geometry, full coverage) have no tiles of their own: a hit of something
         // they enclose brings their Begin/End pair into that tile's list -- once per (layer, tile): PASS 0 claims the
         // pair with one bit per (layer, tile) and remembers per path tile which ancestors it brought (imp_mask), PASS 1
@@ -759,7 +763,7 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
             }
             if (x < bw) {
                 if (PASS == 0 && v != t.backdrop) tiles[base + x].backdrop = v;
-                if (t.seg_count != 0 || v != 0) {
+                if (t.seg_count != 0 || (even_odd ? (v & 1) != 0 : v != 0)) {
                     uint32_t T = gy * cfg.width_in_tiles + path.bbox[0] + x;
                     if (PASS == 0) {
                         unsigned long long w;
@@ -1289,7 +1293,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
 }
 
 // ------------------------------------------------------------------ launchers
-void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
+uint32_t gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     init_frame_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.path_bbox_ord, b.bump);
     // a3: pathtag scan. n is host-known here; the scan primitive wants it in device memory, so a
     // constant slot at the tail of the scene buffer carries it (word n_scene_words).
@@ -1312,9 +1316,10 @@ void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     // a7: per-path tile bbox + tile / row offsets (one packed scan)
     gg_scan<unsigned long long>(s, n_paths, cfg.n_paths, LoadPathTiles{cfg, b.path_bbox_ord}, StorePath{cfg, b.path_bbox_ord, b.paths, b.path_row_off},
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->path_tiles));
+    return 6 + 4 * 3;
 }
 
-void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
+uint32_t gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     zero_tiles_kernel<<<GG_GRID(4), 256, 0, s>>>(cfg, b.tiles, b.bump);
     uint32_t band_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
     cudaMemsetAsync(b.tile_hits, 0, sizeof(unsigned long long) * band_tiles, s);
@@ -1323,9 +1328,10 @@ void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) 
     tile_rows_kernel<0><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, nullptr, nullptr, nullptr, b.imp_mask, b.imp_seen, b.bump);
     gg_scan<uint32_t>(s, &b.bump->path_tiles, cfg.tiles_cap, LoadTileCount{b.tiles}, StoreU32Ex{b.seg_start}, (uint32_t*)b.scan_partials, &b.bump->segments);
     path_tiling_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.seg_counts, b.lines, b.paths, b.tiles, b.seg_start, b.segments, b.bump);
+    return 4 + 3;
 }
 
-void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
+uint32_t gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     const uint32_t* n_band_tiles = b.scene + cfg.n_scene_words + 4;
     uint32_t band_tiles = cfg.width_in_tiles * (cfg.band_y1 - cfg.band_y0);
     gg_scan<unsigned long long>(s, n_band_tiles, band_tiles, LoadTileHits{b.tile_hits},
@@ -1334,4 +1340,5 @@ void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
     tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.imp_mask, b.imp_seen, b.bump);
     coarse_kernel<<<GG_GRID(8), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
                                                            b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.restart_pt, b.bump);
+    return 2 + 3;
 }

@@ -46,13 +46,17 @@ struct GGBuffers {
 };
 
 // stage launchers (pipeline.cu)
-void gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);   // scans, flatten, path setup
-void gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s); // path_count, backdrop, seg alloc, path_tiling
-void gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  // hit lists + PTCL
+// each returns the number of kernels it launched
+uint32_t gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);   // scans, flatten, path setup
+uint32_t gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s); // path_count, backdrop, seg alloc, path_tiling
+uint32_t gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s);  // hit lists + PTCL
 // fine (fine.cu). dst: RGBA8 premultiplied, row stride in bytes; covers tile rows [band_y0, band_y1).
 // Further destinations of fine's band besides `dst`: the same band inside the frames of the other devices of a
 // multi-GPU group (peer pointers, same row stride), or ONE multicast address that reaches all of them.
 #define GG_MAX_MIRRORS 15
 struct GGFineMirrors { uint8_t* p[GG_MAX_MIRRORS]; uint32_t n; uint32_t multicast; };
-void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, uint32_t row0, uint32_t row1, uint32_t part,
+// What one fine launch covers: tile rows [row0, row1) relative to the band, tile-PAIR columns [px0, px1) (a warp owns two
+// horizontally adjacent tiles). A dirty rectangle (resident scenes) narrows both.
+struct GGFineRange { uint32_t row0, row1, px0, px1; };
+void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, const GGFineRange& rg, uint32_t part,
                     const GGFineMirrors& mir);

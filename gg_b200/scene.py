@@ -97,8 +97,31 @@ class Encoding:
         return self._cache
 
 
+    def Hash(self):
+        """Encoding.Hash (encoding.go:752-802): FNV-1a over tags, path data, draw data and transforms."""
+        return _hash(self, False)
+
+    def CacheKey(self):
+        """Hash continued over the brush colours (the reference's Hash ignores them): the key of a resident scene."""
+        return _hash(self, True)
+
+
+def _hash(enc, with_brushes):
+    from . import _lib
+    s = enc.streams()
+    memo = enc.__dict__.setdefault("_hash_memo", {})
+    k = (id(s[0]), with_brushes)
+    if k not in memo:
+        memo.clear()
+        memo[k] = _lib.encoding_hash(s[0], s[1], s[2], s[3], s[4] if with_brushes else None)
+    return memo[k]
+
+
 class ArrayEncoding:
     """An Encoding held directly as numpy streams (used by the vectorised generators for 10^5-10^6 paths)."""
+
+    Hash = Encoding.Hash
+    CacheKey = Encoding.CacheKey
 
     def __init__(self, tags, path_data, draw_data, transforms, brushes):
         self._s = (np.ascontiguousarray(tags, np.uint8), np.ascontiguousarray(path_data, np.float32),

@@ -41,17 +41,21 @@ def config1(seed=1, w=512, h=512, n=1000):
 _WIPING = (S.BlendClear, S.BlendCopy, S.BlendSourceIn, S.BlendDestinationIn, S.BlendSourceOut, S.BlendDestinationAtop)
 
 
-def _config3_frame(sc, seed, w, h, n, layer_every, y_off, bound=None):
+def _config3_frame(sc, seed, w, h, n, layer_every, y_off, bound=None, nowipe=False):
     rng = np.random.default_rng(seed)
     depth = 0
     mode = 0
     deep_done = False
     for i in range(n):
+        while nowipe and mode % S.NUM_BLEND_MODES in _WIPING:
+            mode += 1
         if i % layer_every == 0:
             while depth > 0 and (depth >= 3 or rng.random() < 0.6):
                 sc.PopLayer(); depth -= 1
             if not deep_done and i >= n // 2:
                 for _ in range(6):   # one 6-deep stack to exercise the blend-stack spill (> 4 levels)
+                    while nowipe and mode % S.NUM_BLEND_MODES in _WIPING:
+                        mode += 1
                     sc.PushLayer(mode % S.NUM_BLEND_MODES, float(rng.uniform(0.3, 1.0)), bound if mode % S.NUM_BLEND_MODES in _WIPING else None)
                     mode += 1; depth += 1
                 deep_done = True
@@ -76,20 +80,23 @@ def _config3_frame(sc, seed, w, h, n, layer_every, y_off, bound=None):
         sc.PopLayer(); depth -= 1
 
 
-def config3(seed=3, w=3840, h=2160, n=10000, layer_every=50, bands=1):
+def config3(seed=3, w=3840, h=2160, n=10000, layer_every=50, bands=1, nowipe=False):
     """10k random filled + stroked paths; every `layer_every` paths wrapped in a PushLayer cycling the 29
     scene.BlendModes, 25 % of layers with a circular clip, nesting depth <= 3 plus one 6-deep case.
     `bands` > 1: the weak-scaling canvas for N GPUs -- that many copies of this frame stacked vertically, one per GPU
     band (the same frame, so that the work per GPU is the same at every N; different random frames differ by +-40 % in
     cost, which would measure the scene generator, not the scaling). A layer without a clip of its own whose blend mode wipes whatever the layer covers gets
-    its frame's rectangle as clip shape, so that it wipes its own frame, as it does on the single 4K canvas."""
+    its frame's rectangle as clip shape, so that it wipes its own frame, as it does on the single 4K canvas.
+    `nowipe`: the layer cycle uses only the 23 blend modes that leave the backdrop alone where the layer is empty -- no tile is
+    ever blanked by a layer, so fine's restart points (which this scene's wiping layers hand out generously) only come from
+    opaque fills: the variant bench.py reports beside the headline scene."""
     sc = S.Scene()
     if bands == 1:
-        _config3_frame(sc, seed, w, h, n, layer_every, 0.0)
+        _config3_frame(sc, seed, w, h, n, layer_every, 0.0, nowipe=nowipe)
         return sc.Encoding(), w, h
     for b in range(bands):
         frame = S.rect_verbs_coords(0.0, float(b * h), float(w), float((b + 1) * h))
-        _config3_frame(sc, seed, w, h, n, layer_every, float(b * h), bound=frame)
+        _config3_frame(sc, seed, w, h, n, layer_every, float(b * h), bound=frame, nowipe=nowipe)
     return sc.Encoding(), w, h * bands
 
 

@@ -52,9 +52,12 @@ enum { GGCUDA_JOIN_MITER = 0, GGCUDA_JOIN_ROUND = 1, GGCUDA_JOIN_BEVEL = 2 };
 
 /* flags for ggcuda_flush / ggcuda_render_device */
 enum {
-    GGCUDA_COMPOSITE_OVER = 1,  /* start from the pixels already in dst (VelloAccelerator.compositeOver,
-                                   vello_accelerator.go:388-442) instead of the background colour */
-    GGCUDA_KEEP_SCENE = 2       /* do not clear the accumulated scene after rendering */
+    GGCUDA_COMPOSITE_OVER = 1,  /* rasterise the scene on transparent and source-over it onto the pixels already in dst with
+                                   VelloAccelerator.compositeOver's byte arithmetic, (d * (255 - sA) + 127) / 255
+                                   (vello_accelerator.go:388-442), instead of starting from the background colour */
+    GGCUDA_KEEP_SCENE = 2,      /* do not clear the accumulated scene after rendering */
+    GGCUDA_TARGET_F32 = 4       /* ggcuda_render_device only: dst holds premultiplied float RGBA, 16 bytes per pixel
+                                   (stride in bytes, 16-byte aligned), instead of RGBA8 */
 };
 
 /* flags for ggcuda_create */
@@ -73,9 +76,24 @@ GGCUDA_API int ggcuda_set_stream(ggcuda_ctx* ctx, void* cuda_stream);
 /* ---- frame set-up ---- */
 /* Start accumulating a scene for a width x height target (GPURenderTarget.Width/Height). */
 GGCUDA_API int ggcuda_begin(ggcuda_ctx* ctx, uint32_t width, uint32_t height);
+/* Resident scenes (scene.Encoding.Hash, scene/encoding.go:752-802; dirty tiles, scene/renderer.go:395-433): like
+ * ggcuda_begin, but the scene accumulated afterwards is remembered under `key` once it has been rendered. If the context
+ * still holds the segments and command lists of a scene with the same key, size and band, *resident is set to 1, NOTHING
+ * may be added, and the next render runs fine rasterisation only (no ingest, no upload, no flatten / binning / coarse). */
+GGCUDA_API int ggcuda_begin_keyed(ggcuda_ctx* ctx, uint32_t width, uint32_t height, uint64_t key, int* resident);
+/* scene.Encoding.Hash (scene/encoding.go:752-802: FNV-1a over the elements of the tag, path-data, draw-data and transform
+ * streams) for hosts that do not have it; with brushes_rgba != NULL the brush colours are folded in behind it (the
+ * reference's hash ignores them; a key for re-using pixels must not). n_transforms counts floats. */
+GGCUDA_API uint64_t ggcuda_encoding_hash(const uint8_t* tags, size_t n_tags, const float* path_data, size_t n_path_data,
+                                         const uint32_t* draw_data, size_t n_draw_data, const float* transforms, size_t n_transforms,
+                                         const double* brushes_rgba, size_t n_brushes);
+/* Restrict the next render (and its read-back) to the 16x16 tiles touching the pixel rectangle [x0, x1) x [y0, y1);
+ * everything else in dst is left as it is. Applies to one render. */
+GGCUDA_API int ggcuda_set_dirty_rect(ggcuda_ctx* ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1);
 /* Background (premultiplied RGBA8) used where GGCUDA_COMPOSITE_OVER is not set. Default transparent. */
 GGCUDA_API int ggcuda_set_background(ggcuda_ctx* ctx, const uint8_t rgba_premul[4]);
-/* Multi-GPU banding: this context renders only tile rows [y0, y1) (16-px rows). Default: whole canvas. */
+/* Multi-GPU banding: this context renders only tile rows [y0, y1) (16-px rows). Default: whole canvas. Set it BEFORE
+ * adding the scene: ggcuda_add_encoding drops fills and strokes that cannot reach the band. */
 GGCUDA_API int ggcuda_set_band(ggcuda_ctx* ctx, uint32_t tile_row0, uint32_t tile_row1);
 
 /* ---- per-draw accumulation: GPUAccelerator.FillPath / StrokePath (accelerator.go:118-128),
@@ -105,9 +123,13 @@ GGCUDA_API int ggcuda_add_encoding(ggcuda_ctx* ctx, const uint8_t* tags, size_t 
 /* Upload the scene, run the pipeline, read the band back into dst (premultiplied RGBA8,
  * GPURenderTarget.Data/Stride). dst addresses row 0 of the CANVAS; only the band's rows are written. */
 GGCUDA_API int ggcuda_flush(ggcuda_ctx* ctx, uint8_t* dst, size_t stride_bytes, uint32_t flags);
-/* Lifetime note: a dst seen on two consecutive flushes is page-locked in place (cudaHostRegister) so that the frame is
- * DMA'd straight into it; it stays registered until a different dst is flushed to or the context is destroyed, and must
- * stay allocated that long (gg keeps one pixmap per Context, so this is the pixmap's natural lifetime). */
+/* By default the frame travels through the library's own page-locked staging buffer and nothing of dst is retained.
+ * A caller that keeps one pixmap alive (gg keeps one per Context) may page-lock it in place: flushes whose destination
+ * lies inside a registered range are DMA'd straight into it, slice by slice while fine rasterisation is still running.
+ * The memory must stay allocated AND at the same address until ggcuda_unregister_target / ggcuda_destroy -- from Go that
+ * means a runtime.Pinner (or C-allocated pixels), see INTEGRATION.md. */
+GGCUDA_API int ggcuda_register_target(ggcuda_ctx* ctx, uint8_t* data, size_t bytes);
+GGCUDA_API int ggcuda_unregister_target(ggcuda_ctx* ctx, uint8_t* data);
 /* Split form used by benchmarks and multi-GPU callers: upload once, render into device memory.
  * dst_device addresses the first row of this context's BAND. */
 GGCUDA_API int ggcuda_upload(ggcuda_ctx* ctx);
@@ -119,6 +141,18 @@ GGCUDA_API int ggcuda_render_device(ggcuda_ctx* ctx, void* dst_device, size_t st
  * all-gather). There is no counterpart in the reference (single device). */
 GGCUDA_API int ggcuda_render_device_multi(ggcuda_ctx* ctx, void* dst_device, void* const* mirrors, uint32_t n_mirrors, int multicast,
                                           size_t stride_bytes, uint32_t flags);
+
+/* Band assembly inside the library ("assembled with one NCCL all-gather"), for hosts that have no
+ * collective library of their own (the Go binding). NCCL is resolved at run time (the copy already loaded in the process,
+ * else libnccl.so.2); libggcuda.so does not link it. One rank calls ggcuda_comm_unique_id and hands the 128 bytes to the
+ * others (any channel); every rank then calls ggcuda_comm_init. ggcuda_all_gather_bands gathers IN PLACE on the context's
+ * stream: every rank's band (band_bytes, equal on all ranks) already lies at frame + rank * band_bytes, where
+ * ggcuda_render_device put it. ggcuda_sync waits for the context's stream. */
+GGCUDA_API int ggcuda_comm_unique_id(uint8_t id[128]);
+GGCUDA_API int ggcuda_comm_init(ggcuda_ctx* ctx, int n_ranks, int rank, const uint8_t id[128]);
+GGCUDA_API int ggcuda_comm_destroy(ggcuda_ctx* ctx);
+GGCUDA_API int ggcuda_all_gather_bands(ggcuda_ctx* ctx, void* frame_device, size_t band_bytes);
+GGCUDA_API int ggcuda_sync(ggcuda_ctx* ctx);
 
 /* ---- introspection ---- */
 typedef struct {

@@ -20,6 +20,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+/* 1 = reproduce coarse.go:425 (even-odd tiles with an even non-zero backdrop painted solid); default 0 = fixed */
+int ot_evenodd_solid_quirk = 0;
+
 #define TILE_W 16
 #define TILE_H 16
 static const float TILE_SCALE = 1.0f / 16.0f;        /* types.go:7-11 */
@@ -622,6 +625,67 @@ static void dm_combine(ot_draw_monoid *a, const ot_draw_monoid *b) {
     a->path_ix += b->path_ix; a->clip_ix += b->clip_ix; a->scene_offset += b->scene_offset; a->info_offset += b->info_offset;
 }
 
+enum { DRAWTAG_COLOR = 0x44, DRAWTAG_BEGIN_CLIP = 0x9, DRAWTAG_END_CLIP = 0x21 };          /* scene_encode.go:70-76 */
+/* The three scan stages on a packed scene (the reference's own layout or ggcuda's, which shares the draw-tag encoding):
+ *   pathtagReduce + pathtagScan (pathtag.go:76-121): exclusive PathMonoid per tag word;
+ *   drawReduce + drawLeafScan (draw_leaf.go:54-151): exclusive DrawMonoid per draw object, info[], ClipInp[];
+ *   clipLeafScan (clip_leaf.go:27-56): every EndClip takes path_ix and scene_offset of its BeginClip.
+ * Any output may be NULL. clip_inps: 2 words per clip {ix, path_ix}. Returns the number of info words. */
+uint32_t ot_scan_stages(const uint32_t *scene, uint32_t n_scene_words, uint32_t path_tag_base, uint32_t n_tag_words,
+                        uint32_t draw_tag_base, uint32_t draw_data_base, uint32_t n_draw, uint32_t n_clips,
+                        ot_path_monoid *tag_monoids, ot_draw_monoid *dm, uint32_t *info, int32_t *clip_inps_out) {
+    if (tag_monoids) {
+        ot_path_monoid m; memset(&m, 0, sizeof m);
+        for (uint32_t i = 0; i < n_tag_words; i++) {
+            tag_monoids[i] = m;
+            ot_path_monoid t; ot_path_monoid_new(scene[path_tag_base + i], &t);
+            pm_combine(&m, &t);
+        }
+    }
+    ot_draw_monoid *own = NULL;
+    if (!dm) dm = own = (ot_draw_monoid *)calloc(n_draw ? n_draw : 1, sizeof(ot_draw_monoid));
+    ot_draw_monoid pre; memset(&pre, 0, sizeof pre);
+    for (uint32_t i = 0; i < n_draw; i++) {
+        dm[i] = pre;
+        ot_draw_monoid t; ot_draw_monoid_new(scene[draw_tag_base + i], &t);
+        dm_combine(&pre, &t);
+    }
+    uint32_t n_info = pre.info_offset;
+    typedef struct { uint32_t ix; int32_t path_ix; } clip_inp;
+    clip_inp *clip_inps = (clip_inp *)calloc(n_clips ? n_clips : 1, sizeof(clip_inp));
+    for (uint32_t i = 0; i < n_draw; i++) {
+        uint32_t tag = scene[draw_tag_base + i];
+        if (tag == DRAWTAG_COLOR) {
+            uint32_t so = draw_data_base + dm[i].scene_offset;
+            if (info && so < n_scene_words && dm[i].info_offset < n_info) info[dm[i].info_offset] = scene[so];
+        } else if (tag == DRAWTAG_BEGIN_CLIP) {
+            if (dm[i].clip_ix < n_clips) { clip_inps[dm[i].clip_ix].ix = i; clip_inps[dm[i].clip_ix].path_ix = (int32_t)dm[i].path_ix; }
+        } else if (tag == DRAWTAG_END_CLIP) {
+            if (dm[i].clip_ix < n_clips) { clip_inps[dm[i].clip_ix].ix = i; clip_inps[dm[i].clip_ix].path_ix = ~(int32_t)i; }
+        }
+    }
+    if (clip_inps_out) memcpy(clip_inps_out, clip_inps, sizeof(clip_inp) * n_clips);
+    if (n_clips > 0) {   /* clipLeafScan */
+        int *stack = (int *)malloc(sizeof(int) * n_clips); int sp = 0;
+        for (uint32_t i = 0; i < n_clips; i++) {
+            if (clip_inps[i].path_ix >= 0) { stack[sp++] = (int)i; }
+            else {
+                if (sp == 0) continue;
+                int parent = stack[--sp];
+                uint32_t end_idx = (uint32_t)(~clip_inps[i].path_ix);
+                if (end_idx < n_draw && clip_inps[parent].ix < n_draw) {
+                    dm[end_idx].path_ix = (uint32_t)clip_inps[parent].path_ix;
+                    dm[end_idx].scene_offset = dm[clip_inps[parent].ix].scene_offset;
+                }
+            }
+        }
+        free(stack);
+    }
+    free(clip_inps);
+    free(own);
+    return n_info;
+}
+
 /* ------------------------------------------------------------------ path_count.go */
 typedef struct {
     vec2 xy0, xy1, s0, s1;
@@ -997,7 +1061,6 @@ static void u32_push(u32vec *v, uint32_t x) {
 static inline uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
 static inline float bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
-enum { DRAWTAG_COLOR = 0x44, DRAWTAG_BEGIN_CLIP = 0x9, DRAWTAG_END_CLIP = 0x21 };          /* scene_encode.go:70-76 */
 enum { PTAG_LINETO = 0x9, PTAG_PATH = 0x10, PTAG_TRANSFORM = 0x20, PTAG_STYLE = 0x40 };      /* scene_encode.go:78-86 */
 enum { CMD_END = 0, CMD_FILL = 1, CMD_SOLID = 3, CMD_COLOR = 5, CMD_BEGIN_CLIP = 10, CMD_END_CLIP = 11 }; /* ptcl.go:17-24 */
 
@@ -1113,58 +1176,14 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
     out->scene = scene; out->n_scene_words = off; out->layout = L;
     free(raw_tags.d); free(path_data.d); free(draw_tags.d); free(draw_data.d); free(transforms.d); free(styles.d);
 
-    /* --- pathtagReduce + pathtagScan (pathtag.go:76-121): exclusive scan per tag word --- */
+    /* --- pathtag / draw / clip-leaf scans (pathtag.go:76-121, draw_leaf.go:54-151, clip_leaf.go:27-56) --- */
     out->n_tag_words = padded;
     out->tag_monoids = (ot_path_monoid *)calloc(padded, sizeof(ot_path_monoid));
-    {
-        ot_path_monoid m; memset(&m, 0, sizeof m);
-        for (uint32_t i = 0; i < padded; i++) {
-            out->tag_monoids[i] = m;
-            ot_path_monoid t; ot_path_monoid_new(scene[L.path_tag_base + i], &t);
-            pm_combine(&m, &t);
-        }
-    }
-    /* --- drawReduce + drawLeafScan (draw_leaf.go:54-151) --- */
     ot_draw_monoid *dm = (ot_draw_monoid *)calloc(n_draw ? n_draw : 1, sizeof(ot_draw_monoid));
-    ot_draw_monoid pre; memset(&pre, 0, sizeof pre);
-    for (uint32_t i = 0; i < n_draw; i++) {
-        dm[i] = pre;
-        ot_draw_monoid t; ot_draw_monoid_new(scene[L.draw_tag_base + i], &t);
-        dm_combine(&pre, &t);
-    }
-    uint32_t n_info = pre.info_offset;
+    uint32_t n_info = ot_scan_stages(scene, off, L.path_tag_base, padded, L.draw_tag_base, L.draw_data_base, n_draw, n_clips,
+                                     out->tag_monoids, dm, NULL, NULL);
     uint32_t *info = (uint32_t *)calloc(n_info ? n_info : 1, sizeof(uint32_t));
-    typedef struct { uint32_t ix; int32_t path_ix; } clip_inp;
-    clip_inp *clip_inps = (clip_inp *)calloc(n_clips ? n_clips : 1, sizeof(clip_inp));
-    for (uint32_t i = 0; i < n_draw; i++) {
-        uint32_t tag = scene[L.draw_tag_base + i];
-        if (tag == DRAWTAG_COLOR) {
-            uint32_t so = L.draw_data_base + dm[i].scene_offset;
-            if (so < off && dm[i].info_offset < n_info) info[dm[i].info_offset] = scene[so];
-        } else if (tag == DRAWTAG_BEGIN_CLIP) {
-            if (dm[i].clip_ix < n_clips) { clip_inps[dm[i].clip_ix].ix = i; clip_inps[dm[i].clip_ix].path_ix = (int32_t)dm[i].path_ix; }
-        } else if (tag == DRAWTAG_END_CLIP) {
-            if (dm[i].clip_ix < n_clips) { clip_inps[dm[i].clip_ix].ix = i; clip_inps[dm[i].clip_ix].path_ix = ~(int32_t)i; }
-        }
-    }
-    /* --- clipLeafScan (clip_leaf.go:27-56) --- */
-    if (n_clips > 0) {
-        int *stack = (int *)malloc(sizeof(int) * n_clips); int sp = 0;
-        for (uint32_t i = 0; i < n_clips; i++) {
-            if (clip_inps[i].path_ix >= 0) { stack[sp++] = (int)i; }
-            else {
-                if (sp == 0) continue;
-                int parent = stack[--sp];
-                uint32_t end_idx = (uint32_t)(~clip_inps[i].path_ix);
-                if (end_idx < n_draw && clip_inps[parent].ix < n_draw) {
-                    dm[end_idx].path_ix = (uint32_t)clip_inps[parent].path_ix;
-                    dm[end_idx].scene_offset = dm[clip_inps[parent].ix].scene_offset;
-                }
-            }
-        }
-        free(stack);
-    }
-    free(clip_inps);
+    ot_scan_stages(scene, off, L.path_tag_base, padded, L.draw_tag_base, L.draw_data_base, n_draw, n_clips, NULL, dm, info, NULL);
     out->draw_monoids = dm; out->info = info; out->n_info = n_info;
 
     /* --- allLines with PathIx (rasterizer.go:363-384) --- */
@@ -1263,7 +1282,11 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                         ptcl_push(&ptcls[g], CMD_FILL); ptcl_push(&ptcls[g], (cnt << 1) | (uint32_t)even_odd);
                         ptcl_push(&ptcls[g], gsb + st); ptcl_push(&ptcls[g], (uint32_t)t.backdrop);
                         ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
-                    } else if (t.backdrop != 0) {
+                    } else if (t.backdrop != 0 && (!even_odd || ot_evenodd_solid_quirk || (t.backdrop & 1))) {
+                        /* DEVIATION from coarse.go:425, which paints every tile with backdrop != 0 solid whatever the
+                         * fill rule: under even-odd a tile without segments is inside only when its winding is odd
+                         * (two nested same-direction contours leave backdrop 2 in the hole). ot_evenodd_solid_quirk = 1
+                         * restores the reference's behaviour. */
                         ptcl_push(&ptcls[g], CMD_SOLID);
                         ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
                     }

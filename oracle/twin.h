@@ -130,4 +130,10 @@ void ot_fine_frame_mt(const ot_coarse *c, const float bg_premul[4], int w, int h
 #ifdef __cplusplus
 }
 #endif
+uint32_t ot_scan_stages(const uint32_t *scene, uint32_t n_scene_words, uint32_t path_tag_base, uint32_t n_tag_words,
+                        uint32_t draw_tag_base, uint32_t draw_data_base, uint32_t n_draw, uint32_t n_clips,
+                        ot_path_monoid *tag_monoids, ot_draw_monoid *dm, uint32_t *info, int32_t *clip_inps_out);
+/* 1 = reproduce coarse.go:425 (even-odd tile with an even non-zero backdrop and no segments is painted solid) */
+extern int ot_evenodd_solid_quirk;
+
 #endif

@@ -265,6 +265,23 @@ def _layout13(layout):
     return np.asarray(layout, dtype=np.uint32)
 
 
+def scan_stages(scene_words, layout):
+    """pathtag scan, draw scan + leaf, clip leaf (pathtag.go:76-121, draw_leaf.go:54-151, clip_leaf.go:27-56) on ggcuda's
+    packed scene -> (tag_monoids, draw_monoids after the clip-leaf fix-up, info, clip_inps)."""
+    L = lib()
+    L.ot_scan_stages.restype = C.c_uint32
+    L.ot_scan_stages.argtypes = [C.c_void_p] + [C.c_uint32] * 7 + [C.c_void_p] * 4
+    sw = np.ascontiguousarray(scene_words, dtype=np.uint32)
+    g = {n: int(layout[n]) for n in layout.dtype.names}
+    tm = np.zeros(g["n_tag_words"], dtype=PATH_MONOID)
+    dm = np.zeros(max(1, g["n_draws"]), dtype=DRAW_MONOID)
+    info = np.zeros(max(1, g["n_draws"]), dtype=np.uint32)
+    ci = np.zeros((max(1, g["n_clips"]), 2), dtype=np.int32)
+    n_info = L.ot_scan_stages(_p(sw), g["n_scene_words"], g["path_tag_base"], g["n_tag_words"], g["draw_tag_base"], g["draw_data_base"],
+                              g["n_draws"], g["n_clips"], _p(tm), _p(dm), _p(info), _p(ci))
+    return tm, dm[:g["n_draws"]], info[:n_info], ci[:g["n_clips"]]
+
+
 def flatten_packed(scene_words, layout):
     L = lib()
     L.ot_flatten_packed.restype = C.c_uint32

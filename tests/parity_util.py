@@ -72,10 +72,28 @@ def sorted_rows(a):
     return a[idx]
 
 
+def compare_scans(ctx):
+    """a3 / a4 / a5: the device's pathtag scan, draw scan + draw leaf (info, clip inputs) and clip-leaf fix-up against the
+    oracle's restatement of pathtag.go:76-121, draw_leaf.go:54-151 and clip_leaf.go:27-56 run on the SAME packed scene."""
+    lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+    words = ctx.debug_read(G.BUF_SCENE, np.uint32)
+    tm, dm, info, ci = T.scan_stages(words, lay)
+    gtm = ctx.debug_read(G.BUF_TAG_MONOIDS, G.PATH_MONOID)
+    assert len(gtm) == len(tm) and gtm.tobytes() == tm.astype(G.PATH_MONOID).tobytes(), "tag monoids differ"
+    gdm = ctx.debug_read(G.BUF_DRAW_MONOIDS, G.DRAW_MONOID)
+    assert len(gdm) == len(dm) and gdm.tobytes() == dm.astype(G.DRAW_MONOID).tobytes(), "draw monoids (after clip leaf) differ"
+    ginfo = ctx.debug_read(G.BUF_INFO, np.uint32)
+    assert (ginfo[:len(info)] == info).all(), "draw info differs"
+    gci = ctx.debug_read(G.BUF_CLIP_INPS, G.CLIP_INP)
+    assert len(gci) == len(ci) and (gci["ix"].astype(np.int64) == ci[:, 0].astype(np.uint32)).all() and (gci["path_ix"] == ci[:, 1]).all(), "clip inputs differ"
+    return {"tag_words": len(tm), "draws": len(dm), "clips": len(ci)}
+
+
 def compare_stages(ctx, oc, elems, w, h, check_ptcl=True):
     """Assert bit-exact equality of every integer stage; returns a dict of counts for reporting."""
     rep = {}
-    # ---- a3/a4: monoids (exclusive scans)
+    # ---- a3 / a4 / a5: monoid scans, draw leaf, clip leaf
+    rep.update(compare_scans(ctx))
     lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
     # ---- a6: lines, per path, as multisets (the reference orders LineTo lines before flattened cubics)
     gl = ctx.debug_read(G.BUF_LINES, G.LINE)
@@ -247,6 +265,7 @@ def compare_stages_fast(ctx, oc, w, h):
     lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
     words = ctx.debug_read(G.BUF_SCENE, np.uint32)
     rep = {}
+    rep.update(compare_scans(ctx))   # a3 / a4 / a5
     # a6
     gl = ctx.debug_read(G.BUF_LINES, G.LINE)
     ol = T.flatten_packed(words, lay).astype(G.LINE)
