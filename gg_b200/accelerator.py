@@ -178,7 +178,7 @@ class CUDAAccelerator:
         self.ctx.unregister_target(target.Data)
 
     # -- scene.EncodingAccelerator (proposed optional interface)
-    def RenderEncoding(self, target, enc, composite_over=False, dirty=None):
+    def RenderEncoding(self, target, enc, composite_over=False, dirty=None, resident=True):
         """Render a whole scene.Encoding (fills, strokes, clips, layers with blend modes). The scene stays resident on the
         device under its key (Encoding.Hash, scene/encoding.go:752-802, continued over the brushes): rendering the same
         encoding again skips ingest, upload, flatten, binning and coarse. dirty = (x0, y0, x1, y1): re-rasterise and read
@@ -187,9 +187,11 @@ class CUDAAccelerator:
             raise ErrFallbackToCPU("accelerator not initialised")
         if self._pending:
             self.Flush(self._target)
-        if self.ctx.begin_keyed(target.Width, target.Height, enc.CacheKey()):
+        if resident and self.ctx.begin_keyed(target.Width, target.Height, enc.CacheKey()):
             self.resident_hits += 1
         else:
+            if not resident:
+                self.ctx.begin(target.Width, target.Height)   # resident=False: always ingest, upload and run every stage
             try:
                 self.ctx.add_encoding(*enc.streams())
             except GGCudaError as e:

@@ -34,9 +34,45 @@ __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {   // fine.wgsl:305-32
     uint32_t a = (uint32_t)(clamp01(c.w) * 255.0f + 0.5f);
     return r | (g << 8) | (b << 16) | (a << 24);
 }
+// (float)byte / 255.0f (fine.go:104-108) as a table: the IEEE division the reference does, done by the compiler; four
+// of them per CmdColor were 8 % of fine's instructions on the 1 M-path scene (ncu r2b). The colour word is the same in
+// every lane, so the look-ups are uniform constant loads.
+__constant__ float U8_TO_UNIT[256] = {
+    0.0f / 255.0f, 1.0f / 255.0f, 2.0f / 255.0f, 3.0f / 255.0f, 4.0f / 255.0f, 5.0f / 255.0f, 6.0f / 255.0f, 7.0f / 255.0f,
+    8.0f / 255.0f, 9.0f / 255.0f, 10.0f / 255.0f, 11.0f / 255.0f, 12.0f / 255.0f, 13.0f / 255.0f, 14.0f / 255.0f, 15.0f / 255.0f,
+    16.0f / 255.0f, 17.0f / 255.0f, 18.0f / 255.0f, 19.0f / 255.0f, 20.0f / 255.0f, 21.0f / 255.0f, 22.0f / 255.0f, 23.0f / 255.0f,
+    24.0f / 255.0f, 25.0f / 255.0f, 26.0f / 255.0f, 27.0f / 255.0f, 28.0f / 255.0f, 29.0f / 255.0f, 30.0f / 255.0f, 31.0f / 255.0f,
+    32.0f / 255.0f, 33.0f / 255.0f, 34.0f / 255.0f, 35.0f / 255.0f, 36.0f / 255.0f, 37.0f / 255.0f, 38.0f / 255.0f, 39.0f / 255.0f,
+    40.0f / 255.0f, 41.0f / 255.0f, 42.0f / 255.0f, 43.0f / 255.0f, 44.0f / 255.0f, 45.0f / 255.0f, 46.0f / 255.0f, 47.0f / 255.0f,
+    48.0f / 255.0f, 49.0f / 255.0f, 50.0f / 255.0f, 51.0f / 255.0f, 52.0f / 255.0f, 53.0f / 255.0f, 54.0f / 255.0f, 55.0f / 255.0f,
+    56.0f / 255.0f, 57.0f / 255.0f, 58.0f / 255.0f, 59.0f / 255.0f, 60.0f / 255.0f, 61.0f / 255.0f, 62.0f / 255.0f, 63.0f / 255.0f,
+    64.0f / 255.0f, 65.0f / 255.0f, 66.0f / 255.0f, 67.0f / 255.0f, 68.0f / 255.0f, 69.0f / 255.0f, 70.0f / 255.0f, 71.0f / 255.0f,
+    72.0f / 255.0f, 73.0f / 255.0f, 74.0f / 255.0f, 75.0f / 255.0f, 76.0f / 255.0f, 77.0f / 255.0f, 78.0f / 255.0f, 79.0f / 255.0f,
+    80.0f / 255.0f, 81.0f / 255.0f, 82.0f / 255.0f, 83.0f / 255.0f, 84.0f / 255.0f, 85.0f / 255.0f, 86.0f / 255.0f, 87.0f / 255.0f,
+    88.0f / 255.0f, 89.0f / 255.0f, 90.0f / 255.0f, 91.0f / 255.0f, 92.0f / 255.0f, 93.0f / 255.0f, 94.0f / 255.0f, 95.0f / 255.0f,
+    96.0f / 255.0f, 97.0f / 255.0f, 98.0f / 255.0f, 99.0f / 255.0f, 100.0f / 255.0f, 101.0f / 255.0f, 102.0f / 255.0f, 103.0f / 255.0f,
+    104.0f / 255.0f, 105.0f / 255.0f, 106.0f / 255.0f, 107.0f / 255.0f, 108.0f / 255.0f, 109.0f / 255.0f, 110.0f / 255.0f, 111.0f / 255.0f,
+    112.0f / 255.0f, 113.0f / 255.0f, 114.0f / 255.0f, 115.0f / 255.0f, 116.0f / 255.0f, 117.0f / 255.0f, 118.0f / 255.0f, 119.0f / 255.0f,
+    120.0f / 255.0f, 121.0f / 255.0f, 122.0f / 255.0f, 123.0f / 255.0f, 124.0f / 255.0f, 125.0f / 255.0f, 126.0f / 255.0f, 127.0f / 255.0f,
+    128.0f / 255.0f, 129.0f / 255.0f, 130.0f / 255.0f, 131.0f / 255.0f, 132.0f / 255.0f, 133.0f / 255.0f, 134.0f / 255.0f, 135.0f / 255.0f,
+    136.0f / 255.0f, 137.0f / 255.0f, 138.0f / 255.0f, 139.0f / 255.0f, 140.0f / 255.0f, 141.0f / 255.0f, 142.0f / 255.0f, 143.0f / 255.0f,
+    144.0f / 255.0f, 145.0f / 255.0f, 146.0f / 255.0f, 147.0f / 255.0f, 148.0f / 255.0f, 149.0f / 255.0f, 150.0f / 255.0f, 151.0f / 255.0f,
+    152.0f / 255.0f, 153.0f / 255.0f, 154.0f / 255.0f, 155.0f / 255.0f, 156.0f / 255.0f, 157.0f / 255.0f, 158.0f / 255.0f, 159.0f / 255.0f,
+    160.0f / 255.0f, 161.0f / 255.0f, 162.0f / 255.0f, 163.0f / 255.0f, 164.0f / 255.0f, 165.0f / 255.0f, 166.0f / 255.0f, 167.0f / 255.0f,
+    168.0f / 255.0f, 169.0f / 255.0f, 170.0f / 255.0f, 171.0f / 255.0f, 172.0f / 255.0f, 173.0f / 255.0f, 174.0f / 255.0f, 175.0f / 255.0f,
+    176.0f / 255.0f, 177.0f / 255.0f, 178.0f / 255.0f, 179.0f / 255.0f, 180.0f / 255.0f, 181.0f / 255.0f, 182.0f / 255.0f, 183.0f / 255.0f,
+    184.0f / 255.0f, 185.0f / 255.0f, 186.0f / 255.0f, 187.0f / 255.0f, 188.0f / 255.0f, 189.0f / 255.0f, 190.0f / 255.0f, 191.0f / 255.0f,
+    192.0f / 255.0f, 193.0f / 255.0f, 194.0f / 255.0f, 195.0f / 255.0f, 196.0f / 255.0f, 197.0f / 255.0f, 198.0f / 255.0f, 199.0f / 255.0f,
+    200.0f / 255.0f, 201.0f / 255.0f, 202.0f / 255.0f, 203.0f / 255.0f, 204.0f / 255.0f, 205.0f / 255.0f, 206.0f / 255.0f, 207.0f / 255.0f,
+    208.0f / 255.0f, 209.0f / 255.0f, 210.0f / 255.0f, 211.0f / 255.0f, 212.0f / 255.0f, 213.0f / 255.0f, 214.0f / 255.0f, 215.0f / 255.0f,
+    216.0f / 255.0f, 217.0f / 255.0f, 218.0f / 255.0f, 219.0f / 255.0f, 220.0f / 255.0f, 221.0f / 255.0f, 222.0f / 255.0f, 223.0f / 255.0f,
+    224.0f / 255.0f, 225.0f / 255.0f, 226.0f / 255.0f, 227.0f / 255.0f, 228.0f / 255.0f, 229.0f / 255.0f, 230.0f / 255.0f, 231.0f / 255.0f,
+    232.0f / 255.0f, 233.0f / 255.0f, 234.0f / 255.0f, 235.0f / 255.0f, 236.0f / 255.0f, 237.0f / 255.0f, 238.0f / 255.0f, 239.0f / 255.0f,
+    240.0f / 255.0f, 241.0f / 255.0f, 242.0f / 255.0f, 243.0f / 255.0f, 244.0f / 255.0f, 245.0f / 255.0f, 246.0f / 255.0f, 247.0f / 255.0f,
+    248.0f / 255.0f, 249.0f / 255.0f, 250.0f / 255.0f, 251.0f / 255.0f, 252.0f / 255.0f, 253.0f / 255.0f, 254.0f / 255.0f, 255.0f / 255.0f,
+};
 __device__ __forceinline__ float4 unpack_rgba8(uint32_t c) {
-    return make_float4((float)(c & 0xffu) / 255.0f, (float)((c >> 8) & 0xffu) / 255.0f,
-                       (float)((c >> 16) & 0xffu) / 255.0f, (float)((c >> 24) & 0xffu) / 255.0f);
+    return make_float4(U8_TO_UNIT[c & 0xffu], U8_TO_UNIT[(c >> 8) & 0xffu], U8_TO_UNIT[(c >> 16) & 0xffu], U8_TO_UNIT[c >> 24]);
 }
 
 // ---------------------------------------------------------------- layer blending at CmdEndClip
@@ -51,20 +87,20 @@ __device__ __forceinline__ float min3f(float a, float b, float c) { return a < b
 __device__ __forceinline__ float max3f(float a, float b, float c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 __device__ __forceinline__ void clip_color(float& r, float& g, float& b) {   // hsl.go:24-43
     float l = lum3(r, g, b), n = min3f(r, g, b), x = max3f(r, g, b);
-    if (n < 0) { r = l + (r - l) * l / (l - n); g = l + (g - l) * l / (l - n); b = l + (b - l) * l / (l - n); }
-    if (x > 1) { r = l + (r - l) * (1 - l) / (x - l); g = l + (g - l) * (1 - l) / (x - l); b = l + (b - l) * (1 - l) / (x - l); }
+    if (n < 0) { const float k = l / (l - n); r = l + (r - l) * k; g = l + (g - l) * k; b = l + (b - l) * k; }
+    if (x > 1) { const float k = (1 - l) / (x - l); r = l + (r - l) * k; g = l + (g - l) * k; b = l + (b - l) * k; }
 }
 __device__ __forceinline__ void set_lum(float& r, float& g, float& b, float l) { float d = l - lum3(r, g, b); r += d; g += d; b += d; clip_color(r, g, b); }
-__device__ __forceinline__ void set_sat(float& r, float& g, float& b, float s) {   // hsl.go:53-88 (same tie-breaking order)
-    float* mn; float* md; float* mx;
-    if (r <= g && g <= b) { mn = &r; md = &g; mx = &b; }
-    else if (r <= b && b <= g) { mn = &r; md = &b; mx = &g; }
-    else if (b <= r && r <= g) { mn = &b; md = &r; mx = &g; }
-    else if (g <= r && r <= b) { mn = &g; md = &r; mx = &b; }
-    else if (g <= b && b <= r) { mn = &g; md = &b; mx = &r; }
-    else { mn = &b; md = &g; mx = &r; }
-    float lo = *mn, mi = *md, hi = *mx;
-    if (hi > lo) { *md = ((mi - lo) * s) / (hi - lo); *mx = s; *mn = 0; }
+// hsl.go:53-88 without the pointer sort: min -> 0, max -> s, mid -> ((mid - min) * s) / (max - min); a component tied with
+// the maximum takes s itself (the reference's quotient there is s up to one rounding)
+__device__ __forceinline__ void set_sat(float& r, float& g, float& b, float s) {
+    const float lo = min3f(r, g, b), hi = max3f(r, g, b);
+    if (hi > lo) {
+        const float d = hi - lo;
+        r = r == hi ? s : ((r - lo) * s) / d;
+        g = g == hi ? s : ((g - lo) * s) / d;
+        b = b == hi ? s : ((b - lo) * s) / d;
+    }
 }
 __device__ __forceinline__ float sep_mix(uint32_t mix, float s, float d) {
     switch (mix) {
@@ -86,26 +122,46 @@ __device__ __forceinline__ float sep_mix(uint32_t mix, float s, float d) {
     default: return s;
     }
 }
-// bg (blend) fg for a mix mode 1..15 (always composed SrcOver)
-__device__ __noinline__ float4 blend_mix_px(uint32_t mix, float4 bg, float4 fg) {
-    float sa = fg.w, da = bg.w;
-    float isa = 1.0f / sa, ida = 1.0f / da;   // callers guarantee sa > 0 and da > 0
-    float csr = fg.x * isa, csg = fg.y * isa, csb = fg.z * isa, cdr = bg.x * ida, cdg = bg.y * ida, cdb = bg.z * ida, br, bgc, bb;
+// bg (blend) fg for a mix mode 1..15 (always composed SrcOver); both visible (sa > 0, da > 0)
+__device__ __forceinline__ float4 blend_mix_px(uint32_t mix, float4 bg, float4 fg) {
+    const float sa = fg.w, da = bg.w;
+    const float isa = 1.0f / sa, ida = 1.0f / da;
+    const float csr = fg.x * isa, csg = fg.y * isa, csb = fg.z * isa, cdr = bg.x * ida, cdg = bg.y * ida, cdb = bg.z * ida;
+    float br, bgc, bb;
     if (mix >= 12) {
-        if (mix == 12) { br = csr; bgc = csg; bb = csb; set_sat(br, bgc, bb, max3f(cdr, cdg, cdb) - min3f(cdr, cdg, cdb)); set_lum(br, bgc, bb, lum3(cdr, cdg, cdb)); }
-        else if (mix == 13) { br = cdr; bgc = cdg; bb = cdb; set_sat(br, bgc, bb, max3f(csr, csg, csb) - min3f(csr, csg, csb)); set_lum(br, bgc, bb, lum3(cdr, cdg, cdb)); }
-        else if (mix == 14) { br = csr; bgc = csg; bb = csb; set_lum(br, bgc, bb, lum3(cdr, cdg, cdb)); }
-        else { br = cdr; bgc = cdg; bb = cdb; set_lum(br, bgc, bb, lum3(csr, csg, csb)); }
+        // Hue 12: SetLum(SetSat(Cs, Sat(Cd)), Lum(Cd)); Saturation 13: SetLum(SetSat(Cd, Sat(Cs)), Lum(Cd));
+        // Color 14: SetLum(Cs, Lum(Cd)); Luminosity 15: SetLum(Cd, Lum(Cs))  -- one copy of SetSat / SetLum for all four
+        const bool from_src = mix == 12u || mix == 14u;
+        br = from_src ? csr : cdr; bgc = from_src ? csg : cdg; bb = from_src ? csb : cdb;
+        const float o_r = from_src ? cdr : csr, o_g = from_src ? cdg : csg, o_b = from_src ? cdb : csb;   // the other colour
+        if (mix <= 13u) set_sat(br, bgc, bb, max3f(o_r, o_g, o_b) - min3f(o_r, o_g, o_b));
+        set_lum(br, bgc, bb, mix == 15u ? lum3(csr, csg, csb) : lum3(cdr, cdg, cdb));
     } else {
         br = sep_mix(mix, csr, cdr); bgc = sep_mix(mix, csg, cdg); bb = sep_mix(mix, csb, cdb);
     }
-    float sada = sa * da;
+    const float sada = sa * da;
     float4 o;
     o.x = (1.0f - da) * fg.x + (1.0f - sa) * bg.x + sada * br;
     o.y = (1.0f - da) * fg.y + (1.0f - sa) * bg.y + sada * bgc;
     o.z = (1.0f - da) * fg.z + (1.0f - sa) * bg.z + sada * bb;
     o.w = sa + da * (1.0f - sa);
     return o;
+}
+// CmdEndClip of a mix mode for FOUR of the lane's pixels, held in shared memory: scr[i * 32] = the layer's pixel
+// (premultiplied, already scaled by coverage and alpha), replaced by the result; slot[i * step] = the backdrop. One rolled
+// loop, one copy of the blend code, one call per four pixels -- with the eight pixels in registers the code was unrolled
+// eight times around a per-pixel call whose register saves were 3 % of fine's instructions and the kernel did not fit the
+// instruction cache (ncu r2b: sm__icc hit rate 69 %, 12.7 cycles of no_instruction stall per issue).
+__device__ __noinline__ void blend_mix4(uint32_t mix, float4* scr, const float4* slot, uint32_t step) {
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        const float4 fg = scr[i * 32], bg = slot[i * step];
+        // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source)
+        float4 o = fg;
+        if (fg.w <= 0.0f) o = bg;
+        else if (bg.w > 0.0f) o = blend_mix_px(mix, bg, fg);
+        scr[i * 32] = o;
+    }
 }
 // Porter-Duff compose (Normal mix): Fa * S + Fb * D with Fa = a0 + a1 * Da and Fb = b0 + b1 * Sa
 // (porter_duff.go:117-216); one table row per compose mode keeps the per-pixel code branch free.
@@ -135,9 +191,10 @@ __constant__ float4 COMPOSE_COEF[14] = {
 #define SM_SEGS 5120     // segment ring: GGSegment [2][SEG_CHUNK]                                   1280
 #define SM_DER 6400      // per-segment derived values of the chunk being evaluated: float [3][32]   384
 #define SM_D 6784        // per-lane difference table: int [9][32] (then: RGBA8 image of tile B)     1152
-#define SM_IMG_A 7936    // RGBA8 image of the pair's left tile: u32 [16][16]                        1024
-#define SM_BARS 8960     // 4 mbarriers                                                              32
-#define FINE_SMEM_PER_WARP 9088
+#define SM_SCR 6400      // CmdEndClip scratch, four pixels per lane: float4 [4][32] (over DER and D) 2048
+#define SM_IMG_A 8448    // RGBA8 image of the pair's left tile: u32 [16][16]                        1024
+#define SM_BARS 9472     // 4 mbarriers                                                              32
+#define FINE_SMEM_PER_WARP 9600
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -162,6 +219,7 @@ struct PtclStream {
     uint32_t loaded_end;   // first word index not yet available
     uint32_t parity;       // bit s = phase parity to wait for on slot s
     uint32_t issued;       // chunks of the current tile handed to the copy engine
+    uint32_t limit;        // ensure(cmd) has nothing to do while cmd < limit
     uint32_t lane;
 
     __device__ __forceinline__ void issue(uint32_t chunk) {
@@ -187,12 +245,16 @@ struct PtclStream {
         __syncwarp();
         issue(first_chunk);
         issue(first_chunk + 1);
+        limit = 0;
     }
     // Called once per command with the index of its first word (the longest command is 4 words). The ring holds
     // the chunk the command starts in and the next one; the slot of the chunk BEHIND the command start is refilled
     // with the chunk after next. A command may straddle a chunk boundary, so nothing is refilled on the strength
-    // of its later words.
+    // of its later words. `limit` = first command index at which there is something to do (one compare per command).
     __device__ __forceinline__ void ensure(uint32_t cmd) {
+        if (cmd >= limit) ensure_slow(cmd);
+    }
+    __device__ __forceinline__ void ensure_slow(uint32_t cmd) {
         const uint32_t cur = cmd / PTCL_CHUNK;
         while (issued < cur + 2 && issued * PTCL_CHUNK < len) { __syncwarp(); issue(issued); }
         while (cmd + 3 >= loaded_end && loaded_end < issued * PTCL_CHUNK) {
@@ -201,6 +263,9 @@ struct PtclStream {
             parity ^= 1u << slot;
             loaded_end += PTCL_CHUNK;
         }
+        const uint32_t a = issued * PTCL_CHUNK >= len ? 0xffffffffu : (issued - 1u) * PTCL_CHUNK;   // next refill
+        const uint32_t b = loaded_end >= issued * PTCL_CHUNK ? 0xffffffffu : loaded_end - 3u;          // next wait
+        limit = min(a, b);
     }
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
     // The next CmdFill at or after word c, looking only at words that have already arrived (a few commands ahead).
@@ -394,7 +459,7 @@ __device__ __forceinline__ uint32_t composite_over_u8(uint32_t s, uint32_t d) {
     return o;
 }
 
-__global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
+__global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
                                                                float4* spill, GGBump* bump, uint8_t* dst, size_t stride, GGFineRange rg, uint32_t part, GGFineMirrors mir) {
@@ -412,7 +477,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
     uint32_t* img_b = reinterpret_cast<uint32_t*>(wsm + SM_D);   // the difference table is idle between tiles
     uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + SM_BARS);
     PtclStream ps;
-    ps.ring = reinterpret_cast<uint32_t*>(wsm + SM_PTCL); ps.bars = bars; ps.parity = 0; ps.issued = 0; ps.loaded_end = 0; ps.lane = lane;
+    ps.ring = reinterpret_cast<uint32_t*>(wsm + SM_PTCL); ps.bars = bars; ps.parity = 0; ps.issued = 0; ps.loaded_end = 0; ps.limit = 0; ps.lane = lane;
     ps.src = ptcl; ps.len = 0;
     SegStream ss;
     ss.segs = segments; ss.ring = reinterpret_cast<float*>(wsm + SM_SEGS); ss.bars = bars + 2; ss.issue_seq = 0; ss.wait_seq = 0; ss.ahead_first = 0; ss.lane = lane;
@@ -457,7 +522,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
             const uint32_t sp_off = spill_off[T];
             for (;;) {
                 ps.ensure(cmd);
-                const uint32_t tag = ps.word(cmd);
+                uint32_t tag = ps.word(cmd);
+                // a coverage command (CmdFill / CmdSolid) is followed by the command that uses it: fall through to it
                 if (tag == GG_CMD_FILL) {
                     const uint32_t packed = ps.word(cmd + 1), seg_ix = ps.word(cmd + 2);
                     const float backdrop = (float)(int32_t)ps.word(cmd + 3);
@@ -470,11 +536,16 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
 #pragma unroll
                         for (int i = 0; i < PX; i++) area[i] = fminf(fabsf(area[i]), 1.0f);                                      // fine.go:286
                     }
+                    ps.ensure(cmd);
+                    tag = ps.word(cmd);
                 } else if (tag == GG_CMD_SOLID) {
                     cmd += 1;
 #pragma unroll
                     for (int i = 0; i < PX; i++) area[i] = 1.0f;
-                } else if (tag == GG_CMD_COLOR) {
+                    ps.ensure(cmd);
+                    tag = ps.word(cmd);
+                }
+                if (tag == GG_CMD_COLOR) {
                     const float4 c = unpack_rgba8(ps.word(cmd + 1));
                     cmd += 2;
 #pragma unroll
@@ -520,13 +591,14 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
                         rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
                     }
                     if (mix != 0u && mix < 16u) {
-                        // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source); only
-                        // pixels where both are visible take the (un-premultiply, mix, re-compose) path
+                        float4* scr = reinterpret_cast<float4*>(wsm + SM_SCR) + lane;
 #pragma unroll
-                        for (int i = 0; i < PX; i++) {
-                            const float4 sv = slot[i * step];
-                            if (rgba[i].w <= 0.0f) rgba[i] = sv;
-                            else if (sv.w > 0.0f) rgba[i] = blend_mix_px(mix, sv, rgba[i]);
+                        for (int hf = 0; hf < 2; hf++) {
+#pragma unroll
+                            for (int i = 0; i < 4; i++) scr[i * 32] = rgba[hf * 4 + i];
+                            blend_mix4(mix, scr, slot + hf * 4 * step, step);
+#pragma unroll
+                            for (int i = 0; i < 4; i++) rgba[hf * 4 + i] = scr[i * 32];
                         }
                     } else {
                         // Porter-Duff: Fa * S + Fb * D. Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}.
@@ -544,7 +616,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 6) fine_kernel(GGConfig cfg, 
                             rgba[i] = o;
                         }
                     }
-                } else {
+                } else if (tag != GG_CMD_FILL && tag != GG_CMD_SOLID) {
                     break;   // CmdEnd, or an unknown command: stop (fine.go:182-185)
                 }
             }
@@ -634,7 +706,7 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     if (rg.row1 <= rg.row0 || rg.px1 <= rg.px0) return;
     uint32_t n_pairs = (rg.px1 - rg.px0) * (rg.row1 - rg.row0);
     uint32_t blocks = (n_pairs + FINE_WARPS - 1) / FINE_WARPS;
-    uint32_t max_blocks = cfg.sm_count * 6;   // resident CTAs: 6 per SM (shared memory, registers)
+    uint32_t max_blocks = cfg.sm_count * 5;   // resident CTAs: 5 per SM (shared memory, registers)
     if (blocks > max_blocks) blocks = max_blocks;
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
