@@ -194,7 +194,7 @@ int size_dynamic(Ctx* c) {
     if ((r = ensure(c, c->seg_counts, sizeof(GGSegCount) * (size_t)c->seg_counts_cap))) return r;
     // + 4: fine fetches segment slices in 16-byte aligned chunks of 4 segments and may read up to 3 past the last one
     if ((r = ensure(c, c->segments, sizeof(GGSegment) * ((size_t)c->segments_cap + 4)))) return r;
-    if ((r = ensure(c, c->hits, 4 * (size_t)c->hits_cap))) return r;
+    if ((r = ensure(c, c->hits, sizeof(GGHit) * (size_t)c->hits_cap))) return r;
     if ((r = ensure(c, c->ptcl, 4 * (size_t)c->ptcl_cap))) return r;
     if ((r = ensure(c, c->spill, sizeof(float4) * 256 * (size_t)std::max<uint32_t>(c->spill_cap, 1)))) return r;
     return 0;
@@ -227,7 +227,7 @@ GGBuffers buffers(Ctx* c) {
     b.path_bbox_ord = (uint32_t*)c->path_bbox.p; b.paths = (GGPath*)c->paths.p; b.path_row_off = (uint32_t*)c->path_row_off.p;
     b.tiles = (GGTile*)c->tiles.p; b.seg_start = (uint32_t*)c->seg_start.p; b.imp_mask = (uint8_t*)c->imp_mask.p; b.imp_seen = (uint32_t*)c->imp_seen.p; b.seg_counts = (GGSegCount*)c->seg_counts.p;
     b.segments = (GGSegment*)c->segments.p; b.tile_hits = (unsigned long long*)c->tile_hits.p; b.hit_off = (uint32_t*)c->hit_off.p;
-    b.hit_cnt = (uint32_t*)c->hit_cnt.p; b.hit_cursor = (uint32_t*)c->hit_cursor.p; b.hits = (uint32_t*)c->hits.p;
+    b.hit_cnt = (uint32_t*)c->hit_cnt.p; b.hit_cursor = (uint32_t*)c->hit_cursor.p; b.hits = (GGHit*)c->hits.p;
     b.ptcl_off = (uint32_t*)c->ptcl_off.p; b.ptcl_len = (uint32_t*)c->ptcl_len.p; b.restart_pt = (uint32_t*)c->restart_pt.p; b.ptcl = (uint32_t*)c->ptcl.p; b.spill_off = (uint32_t*)c->spill_off.p;
     b.spill = (float4*)c->spill.p; b.bump = (GGBump*)c->bump.p; b.scan_partials = c->scan_partials.p;
     return b;

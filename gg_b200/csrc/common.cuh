@@ -29,6 +29,11 @@ struct GGClipInp { uint32_t ix; int32_t path_ix; };                            /
 // EndClip it is the index of its own BeginClip. a/b: Color -> rgba8 premul / even-odd flag;
 // BeginClip -> index of the matching EndClip / unused; EndClip -> blend word / alpha bits.
 struct GGDrawRec { uint32_t tag; int32_t parent; uint32_t a; uint32_t b; };
+// One (draw, tile) hit of coarse's per-tile lists, written by the backdrop pass that already holds the path tile in
+// registers: the draw index (the sort key) and everything coarse needs from the path tile, so that the command writer
+// reads one 16-byte record instead of walking draw monoid -> path -> tile -> segment start (ncu r1c: that chain was
+// coarse's long-scoreboard stall). Hits of layers without geometry: seg_count 0, backdrop 1 (full coverage).
+struct __align__(16) GGHit { uint32_t draw; uint32_t seg_count; uint32_t seg_start; int32_t backdrop; };
 
 // Draw / path tags (scene_encode.go:68-86); 0x0C is our MoveTo: it feeds two floats into the
 // path-data stream and no segment under the unchanged PathMonoid bit tricks.

@@ -710,7 +710,8 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
                                                         const uint32_t* __restrict__ path_row_off, GGTile* tiles,
                                                         const GGDrawRec* __restrict__ recs,
                                                         unsigned long long* tile_hits, const uint32_t* __restrict__ hit_off,
-                                                        uint32_t* hit_cursor, uint32_t* hits, uint8_t* imp_mask, uint32_t* imp_seen, GGBump* bump) {
+                                                        uint32_t* hit_cursor, GGHit* hits, const uint32_t* __restrict__ seg_start,
+                                                        uint8_t* imp_mask, uint32_t* imp_seen, GGBump* bump) {
     cg::thread_block_tile<8> g = cg::tiled_partition<8>(cg::this_thread_block());
     const uint32_t n_rows = min(bump->path_rows, cfg.rows_cap);
     if (bump->failed || bump->path_tiles > cfg.tiles_cap) return;
@@ -791,16 +792,19 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
                         uint32_t own = tag == GG_DRAWTAG_COLOR ? 1u : 2u;
                         uint32_t slot = hit_off[T] + atomicAdd(&hit_cursor[T], own + 2u * n_add);
                         if (slot + own + 2u * n_add <= cfg.hits_cap) {
-                            hits[slot++] = p;
-                            if (own == 2u) hits[slot++] = recs[p].a;
-                            if (mask & 1u) { hits[slot++] = i0; hits[slot++] = e0; }
-                            if (mask & 2u) { hits[slot++] = i1; hits[slot++] = e1; }
-                            if (mask & 4u) { hits[slot++] = i2; hits[slot++] = e2; }
-                            if (mask & 8u) { hits[slot++] = i3; hits[slot++] = e3; }
+                            // path_tiling advanced seg_start[] to the END of the tile's range
+                            GGHit h; h.draw = p; h.seg_count = t.seg_count; h.seg_start = seg_start[base + x] - t.seg_count; h.backdrop = t.backdrop;
+                            hits[slot++] = h;
+                            if (own == 2u) { h.draw = recs[p].a; hits[slot++] = h; }   // the clip's EndClip fills with the same path tile
+                            GGHit li; li.seg_count = 0; li.seg_start = 0; li.backdrop = 1;   // layers without geometry: full coverage
+                            if (mask & 1u) { li.draw = i0; hits[slot++] = li; li.draw = e0; hits[slot++] = li; }
+                            if (mask & 2u) { li.draw = i1; hits[slot++] = li; li.draw = e1; hits[slot++] = li; }
+                            if (mask & 4u) { li.draw = i2; hits[slot++] = li; li.draw = e2; hits[slot++] = li; }
+                            if (mask & 8u) { li.draw = i3; hits[slot++] = li; li.draw = e3; hits[slot++] = li; }
                             if (n_imp > 4) {   // deeper than the cached part of the chain: walk it
                                 uint32_t k = 0;
                                 for (int32_t a = recs[p].parent; a >= 0; a = recs[a].parent)
-                                    if (recs[a].b & GG_BLEND_IMPLICIT) { if (k >= 4) { hits[slot++] = (uint32_t)a; hits[slot++] = recs[a].a; } k++; }
+                                    if (recs[a].b & GG_BLEND_IMPLICIT) { if (k >= 4) { li.draw = (uint32_t)a; hits[slot++] = li; li.draw = recs[a].a; hits[slot++] = li; } k++; }
                             }
                         }
                     }
@@ -916,27 +920,24 @@ __global__ void __launch_bounds__(256) path_tiling_kernel(GGConfig cfg, const GG
 #define COARSE_WARPS 4
 #define COARSE_CAP 1024   // hits per tile handled in shared memory; longer lists are sorted in place by lane 0 and replayed sequentially
 
-__device__ inline void heap_sort_global(uint32_t* a, uint32_t n) {
+__device__ inline void heap_sort_global(GGHit* a, uint32_t n) {   // by draw index; equal keys are identical records
     for (uint32_t start = n / 2; start-- > 0;) {
         uint32_t root = start;
-        for (;;) { uint32_t c = 2 * root + 1; if (c >= n) break; if (c + 1 < n && a[c] < a[c + 1]) c++; if (a[root] >= a[c]) break; uint32_t t = a[root]; a[root] = a[c]; a[c] = t; root = c; }
+        for (;;) { uint32_t c = 2 * root + 1; if (c >= n) break; if (c + 1 < n && a[c].draw < a[c + 1].draw) c++; if (a[root].draw >= a[c].draw) break; GGHit t = a[root]; a[root] = a[c]; a[c] = t; root = c; }
     }
     for (uint32_t end = n; end-- > 1;) {
-        uint32_t t = a[0]; a[0] = a[end]; a[end] = t;
+        GGHit t = a[0]; a[0] = a[end]; a[end] = t;
         uint32_t root = 0;
-        for (;;) { uint32_t c = 2 * root + 1; if (c >= end) break; if (c + 1 < end && a[c] < a[c + 1]) c++; if (a[root] >= a[c]) break; uint32_t t2 = a[root]; a[root] = a[c]; a[c] = t2; root = c; }
+        for (;;) { uint32_t c = 2 * root + 1; if (c >= end) break; if (c + 1 < end && a[c].draw < a[c + 1].draw) c++; if (a[root].draw >= a[c].draw) break; GGHit t2 = a[root]; a[root] = a[c]; a[c] = t2; root = c; }
     }
 }
 
 // Sequential form of the clip state machine (coarse.go:440-625 with lazy layers), one warp, hits in `sorted`:
 // used for tiles with more than COARSE_CAP hits. The shared-memory path below computes the same PTCL in parallel.
-__device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_t T, uint32_t n, const uint32_t* sorted, uint32_t pos,
-                                                    const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
-                                                    const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
-                                                    const GGDrawMonoid* __restrict__ dm, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len,
+__device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_t T, uint32_t n, const GGHit* sorted, uint32_t pos,
+                                                    const GGDrawRec* __restrict__ recs, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len,
                                                     uint32_t* ptcl, uint32_t* spill_off, uint32_t* restart_pt, GGBump* bump) {
     const uint32_t lane = threadIdx.x & 31;
-        const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
         // Layers whose blend word carries GG_BLEND_ELIDE_EMPTY are opened lazily: their BeginClip is only
         // written (just before the first command they enclose in this tile) once something is drawn inside;
         // a layer still pending at its EndClip leaves no trace. `depth` counts logically open clips,
@@ -953,19 +954,11 @@ __device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_
             // parallel gather of everything the state machine and the emitters need
             GGDrawRec r; r.tag = 0; r.parent = -1; r.a = 0; r.b = 0;
             uint32_t d = 0; GGTile t; t.backdrop = 0; t.seg_count = 0; uint32_t sstart = 0; int32_t begin_parent = -1;
-            if (i < n && !(i > 0 && sorted[i] == sorted[i - 1])) {   // implicit-layer hits arrive once per enclosed hit: keep the first
-                d = sorted[i];
+            if (i < n && !(i > 0 && sorted[i].draw == sorted[i - 1].draw)) {   // implicit-layer hits arrive once per enclosed hit: keep the first
+                const GGHit h = sorted[i];
+                d = h.draw;
                 r = recs[d];
-                const bool implicit = (r.tag == GG_DRAWTAG_BEGIN_CLIP && (r.b & GG_BLEND_IMPLICIT)) ||
-                                      (r.tag == GG_DRAWTAG_END_CLIP && (r.a & GG_BLEND_IMPLICIT));
-                if (implicit) {
-                    t.backdrop = 1; t.seg_count = 0;   // full coverage, no geometry: CmdSolid at its EndClip
-                } else {
-                    GGPath path = paths[dm[d].path_ix];
-                    uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
-                    t = tiles[ti];
-                    sstart = seg_start[ti] - t.seg_count;   // path_tiling advanced seg_start[] to the end of the tile's range
-                }
+                t.backdrop = h.backdrop; t.seg_count = h.seg_count; sstart = h.seg_start;
                 if (r.tag == GG_DRAWTAG_END_CLIP) begin_parent = recs[r.parent].parent;
             }
             // per-hit flags for the restart bookkeeping: bit 0 = tile has segments for this path,
@@ -1079,11 +1072,9 @@ __device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_
 // of that BeginClip (an EndClip: to its own BeginClip), liveness is a few rounds of pointer chasing over those links,
 // "this lazily opened layer encloses something" an upward marking, PTCL offsets a warp scan. The first version
 // replayed the state machine hit by hit with seven shuffles per hit: 224 of the kernel's 442 M warp instructions.
-__global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg, const GGPath* __restrict__ paths, const GGTile* __restrict__ tiles,
-                                                                   const uint32_t* __restrict__ seg_start, const GGDrawRec* __restrict__ recs,
-                                                                   const GGDrawMonoid* __restrict__ dm,
+__global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg, const GGDrawRec* __restrict__ recs,
                                                                    const uint32_t* __restrict__ hit_off, const uint32_t* __restrict__ hit_cnt,
-                                                                   uint32_t* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len, uint32_t* ptcl,
+                                                                   GGHit* hits, const uint32_t* __restrict__ ptcl_off, uint32_t* ptcl_len, uint32_t* ptcl,
                                                                    uint32_t* spill_off, uint32_t* restart_pt, GGBump* bump) {
     // per warp: sorted keys (4 KB) | radix ping-pong buffer (4 KB), reused after the sort for lpos (2 KB) + state (1 KB) | histogram (1 KB)
     __shared__ uint32_t sort_buf[COARSE_WARPS][COARSE_CAP];
@@ -1102,26 +1093,27 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
     uint8_t* st = reinterpret_cast<uint8_t*>(tmp) + 2 * COARSE_CAP;
     for (uint32_t T = blockIdx.x * COARSE_WARPS + warp; T < n_tiles; T += gridDim.x * COARSE_WARPS) {
         const uint32_t n = hit_cnt[T];
-        uint32_t* list = hits + hit_off[T];
+        GGHit* list = hits + hit_off[T];
         uint32_t pos = ptcl_off[T];
         if (lane == 0) ptcl[pos] = 0;   // word 0: blend offset, always 0 as in the reference (spill offsets live in spill_off[])
         pos += 1;
         if (n == 0) { if (lane == 0) { ptcl[pos] = GG_CMD_END; ptcl_len[T] = 2; restart_pt[2 * T] = 0; restart_pt[2 * T + 1] = 0; } continue; }
-        if (n > COARSE_CAP) {
+        if (n > COARSE_CAP || key_bits > 22u) {   // (keys pack the draw index above 10 position bits)
             if (lane == 0) heap_sort_global(list, n);
             __syncwarp();
-            coarse_tile_sequential(cfg, T, n, list, pos, paths, tiles, seg_start, recs, dm, ptcl_off, ptcl_len, ptcl, spill_off, restart_pt, bump);
+            coarse_tile_sequential(cfg, T, n, list, pos, recs, ptcl_off, ptcl_len, ptcl, spill_off, restart_pt, bump);
             __syncwarp();
             continue;
         }
-        // ---- sort: stable LSD radix sort on the draw index, 8 bits per pass (2 passes up to 65 536 draws). Per pass a
+        // ---- sort: keys are (draw index << 10) | position in the unsorted list, so that a hit's record can be fetched by
+        //      position afterwards; stable LSD radix sort on the draw-index bits, 8 bits per pass (2 passes up to 65 536 draws). Per pass a
         //      256-bin histogram (shared-memory atomics), an exclusive scan (8 bins per lane) and a stable scatter that
         //      ranks equal digits inside each group of 32 keys with match_any. The bitonic network this replaces cost
         //      ~36-45 passes over the padded list: most of the kernel's instructions (ncu, r1b).
         uint32_t* src = sb;
         uint32_t* dstb = tmp;
-        for (uint32_t i = lane; i < n; i += 32) src[i] = list[i];
-        for (uint32_t shift = 0; shift < key_bits; shift += 8) {
+        for (uint32_t i = lane; i < n; i += 32) src[i] = (list[i].draw << 10) | i;
+        for (uint32_t shift = 10; shift < 10 + key_bits; shift += 8) {
 #pragma unroll
             for (int k = 0; k < 8; k++) hist[lane * 8 + k] = 0;
             __syncwarp();
@@ -1159,8 +1151,8 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         __syncwarp();
         // ---- A: classify every hit, link it to the hit of its enclosing BeginClip
         for (uint32_t i = lane; i < n; i += 32) {
-            const uint32_t d = sb[i];
-            const bool dup = i > 0 && sb[i - 1] == d;   // implicit-layer hits arrive once per enclosed hit: keep the first
+            const uint32_t d = sb[i] >> 10;
+            const bool dup = i > 0 && (sb[i - 1] >> 10) == d;   // implicit-layer hits arrive once per enclosed hit: keep the first
             const GGDrawRec r = recs[d];
             uint32_t s8 = r.tag == GG_DRAWTAG_COLOR ? 0u : (r.tag == GG_DRAWTAG_BEGIN_CLIP ? 1u : 2u);
             if (s8 == 1u && (r.b & GG_BLEND_ELIDE_EMPTY)) s8 |= CH_ELIDE;
@@ -1168,8 +1160,8 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
             if (r.parent >= 0) {
                 const uint32_t key = (uint32_t)r.parent;
                 uint32_t lo = 0, hi = n;   // lower bound
-                while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sb[mid] < key) lo = mid + 1; else hi = mid; }
-                lp = (lo < n && sb[lo] == key) ? lo : CH_MISSING;
+                while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if ((sb[mid] >> 10) < key) lo = mid + 1; else hi = mid; }
+                lp = (lo < n && (sb[lo] >> 10) == key) ? lo : CH_MISSING;
             }
             if (!dup && lp != CH_MISSING) s8 |= CH_VAL;
             st[i] = (uint8_t)s8;
@@ -1199,7 +1191,6 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
         }
         __syncwarp();
         // ---- D: commands, 32 hits at a time in scene order
-        const uint32_t tx = T % cfg.width_in_tiles, ty = T / cfg.width_in_tiles + cfg.band_y0;
         uint32_t pos_u = pos - ptcl_off[T];          // offset of the next command inside this tile's list
         uint32_t restart = 0, restart_rgba = 0, max_depth = 0;
         for (uint32_t base = 0; base < n; base += 32) {
@@ -1218,7 +1209,7 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                 }
             }
             if (emit) {
-                d = sb[i];
+                d = sb[i] >> 10;
                 r = recs[d];
                 const uint32_t tg = s8 & CH_TAG;
                 if (tg == 1u) {
@@ -1227,15 +1218,8 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                     for (uint32_t p = lp; p < CH_MISSING; p = lpos[p]) depth++;
                     max_depth = max(max_depth, depth);
                 } else {
-                    const bool implicit = tg == 2u && (r.a & GG_BLEND_IMPLICIT);
-                    if (implicit) {
-                        t.backdrop = 1;   // full coverage, no geometry: CmdSolid at its EndClip
-                    } else {
-                        GGPath path = paths[dm[d].path_ix];
-                        uint32_t ti = path.tiles + (ty - path.bbox[1]) * (path.bbox[2] - path.bbox[0]) + (tx - path.bbox[0]);
-                        t = tiles[ti];
-                        sstart = seg_start[ti] - t.seg_count;   // path_tiling advanced seg_start[] to the end of the tile's range
-                    }
+                    const GGHit h = list[sb[i] & 1023u];   // the record the backdrop pass wrote for this (draw, tile)
+                    t.backdrop = h.backdrop; t.seg_count = h.seg_count; sstart = h.seg_start;
                     nw = tg == 0u ? (t.seg_count ? 6u : 3u) : (t.seg_count ? 7u : 4u);
                 }
             }
@@ -1325,7 +1309,7 @@ uint32_t gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t
     cudaMemsetAsync(b.tile_hits, 0, sizeof(unsigned long long) * band_tiles, s);
     path_count_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.lines, b.paths, b.tiles, b.seg_counts, b.bump);
     if (cfg.imp_words) cudaMemsetAsync(b.imp_seen, 0, sizeof(uint32_t) * (size_t)cfg.imp_words * cfg.n_implicit, s);
-    tile_rows_kernel<0><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, nullptr, nullptr, nullptr, b.imp_mask, b.imp_seen, b.bump);
+    tile_rows_kernel<0><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, nullptr, nullptr, nullptr, nullptr, b.imp_mask, b.imp_seen, b.bump);
     gg_scan<uint32_t>(s, &b.bump->path_tiles, cfg.tiles_cap, LoadTileCount{b.tiles}, StoreU32Ex{b.seg_start}, (uint32_t*)b.scan_partials, &b.bump->segments);
     path_tiling_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.seg_counts, b.lines, b.paths, b.tiles, b.seg_start, b.segments, b.bump);
     return 4 + 3;
@@ -1337,8 +1321,8 @@ uint32_t gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t 
     gg_scan<unsigned long long>(s, n_band_tiles, band_tiles, LoadTileHits{b.tile_hits},
                                 StoreTileHits{b.hit_off, b.hit_cnt, b.ptcl_off, b.hit_cursor, b.spill_off},
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->hits));
-    tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.imp_mask, b.imp_seen, b.bump);
-    coarse_kernel<<<GG_GRID(8), COARSE_WARPS * 32, 0, s>>>(cfg, b.paths, b.tiles, b.seg_start, b.draw_recs, b.draw_monoids,
+    tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.seg_start, b.imp_mask, b.imp_seen, b.bump);
+    coarse_kernel<<<GG_GRID(8), COARSE_WARPS * 32, 0, s>>>(cfg, b.draw_recs,
                                                            b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.restart_pt, b.bump);
     return 2 + 3;
 }

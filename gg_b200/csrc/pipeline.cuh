@@ -33,7 +33,7 @@ struct GGBuffers {
     uint32_t* hit_off;          // [band_tiles]
     uint32_t* hit_cnt;          // [band_tiles]
     uint32_t* hit_cursor;       // [band_tiles]
-    uint32_t* hits;             // [hits_cap] draw indices
+    GGHit* hits;                // [hits_cap] per-tile hit lists (draw index + path-tile record)
     uint32_t* ptcl_off;         // [band_tiles] (multiples of 4 words: 16-byte aligned lists for bulk copies)
     uint32_t* ptcl_len;         // [band_tiles] words actually written (incl. word 0 and CmdEnd)
     uint32_t* ptcl;             // [ptcl_cap]

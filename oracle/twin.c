@@ -22,6 +22,8 @@
 
 /* 1 = reproduce coarse.go:425 (even-odd tiles with an even non-zero backdrop painted solid); default 0 = fixed */
 int ot_evenodd_solid_quirk = 0;
+/* 1 = fine quantises the running colour like gg's CPU pixmap does: truncated to 8 bits after every CmdColor */
+int ot_truncate_per_draw = 0;
 
 #define TILE_W 16
 #define TILE_H 16
@@ -1447,6 +1449,9 @@ void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment 
                 float inv = 1.0f - fa;
                 rgba[i][0] = rgba[i][0] * inv + fr; rgba[i][1] = rgba[i][1] * inv + fg;
                 rgba[i][2] = rgba[i][2] * inv + fb; rgba[i][3] = rgba[i][3] * inv + fa;
+                if (ot_truncate_per_draw && cov != 0.0f)   /* gg's CPU pixmap: 8 bits, truncated, after every draw that touches the pixel
+                                                             * (software.go:1003-1024, pixmap.go:218-228); 1/512 absorbs the float32 error of k/255*255 */
+                    for (int k = 0; k < 4; k++) { float v = rgba[i][k] * 255.0f + (1.0f / 512.0f); v = v < 0 ? 0 : (v > 255.0f ? 255.0f : v); rgba[i][k] = floorf(v) / 255.0f; }
             }
         } break;
         case CMD_BEGIN_CLIP:

@@ -135,5 +135,7 @@ uint32_t ot_scan_stages(const uint32_t *scene, uint32_t n_scene_words, uint32_t 
                         ot_path_monoid *tag_monoids, ot_draw_monoid *dm, uint32_t *info, int32_t *clip_inps_out);
 /* 1 = reproduce coarse.go:425 (even-odd tile with an even non-zero backdrop and no segments is painted solid) */
 extern int ot_evenodd_solid_quirk;
+/* 1 = fine truncates the running colour to 8 bits after every CmdColor, as gg's CPU pixmap does (pixmap.go:218-228) */
+extern int ot_truncate_per_draw;
 
 #endif
