@@ -138,11 +138,12 @@ __device__ __forceinline__ uint32_t span_u(float a, float b) {                  
 __device__ __forceinline__ uint32_t f_ord(float f) { uint32_t u = __float_as_uint(f); return (u & 0x80000000u) ? ~u : (u | 0x80000000u); }
 __device__ __forceinline__ float f_unord(uint32_t u) { return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u); }
 
-// ---------------------------------------------------------------- chunked three-phase scan
-// n elements are cut into GG_SCAN_BLOCKS contiguous chunks (one per CTA, 4 CTAs per SM):
+// ---------------------------------------------------------------- chunked two-launch scan
+// n elements are cut into GG_SCAN_BLOCKS contiguous chunks (one per CTA):
 //   A) every CTA reduces its chunk              -> partials[b]
-//   B) one CTA scans the partials exclusive     -> partials[b], total
-//   C) every CTA re-reads its chunk and writes the exclusive prefix of each element.
+//   B) every CTA sums the partials before its own (592 values: two or three per thread and a block reduction -- cheaper
+//      than the separate one-CTA launch that scanned them in round 1), re-reads its chunk and writes the exclusive
+//      prefix of each element; CTA 0 also writes the grand total.
 // Traffic: 2 reads + 1 write per element; deterministic, no atomics, no look-back spinning.
 // `n` lives in device memory (it is usually the output of a previous stage).
 template <typename T> struct ScanTraits;
@@ -234,50 +235,24 @@ __global__ void __launch_bounds__(GG_SCAN_THREADS) scan_reduce_kernel(const uint
     if (threadIdx.x == 0) partials[blockIdx.x] = tot;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(1024) scan_partials_kernel(T* partials, int n_partials, T* total_out) {
-    typedef ScanTraits<T> Tr;
-    __shared__ T warp_sums[32];
-    __shared__ T carry_s;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_s = Tr::identity();
-    __syncthreads();
-    for (int base = 0; base < n_partials; base += 1024) {
-        int i = base + threadIdx.x;
-        T v = i < n_partials ? partials[i] : Tr::identity();
-        T inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            T o = shfl_up_t(inc, d);
-            if (lane >= d) inc = Tr::combine(o, inc);
-        }
-        if (lane == 31) warp_sums[warp] = inc;
-        __syncthreads();
-        T pre = carry_s;
-        T tot = Tr::identity();
-        for (int w = 0; w < 32; w++) {
-            T s = warp_sums[w];
-            if (w < warp) pre = Tr::combine(pre, s);
-            tot = Tr::combine(tot, s);
-        }
-        // exclusive = pre + (inc - v)  == pre combined with previous lanes
-        T prev = shfl_up_t(inc, 1);
-        T excl = lane == 0 ? pre : Tr::combine(pre, prev);
-        if (i < n_partials) partials[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == 0) carry_s = Tr::combine(carry_s, tot);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && total_out) *total_out = carry_s;
-}
-
 template <typename T, typename Load, typename Store>
-__global__ void __launch_bounds__(GG_SCAN_THREADS) scan_apply_kernel(const uint32_t* n_ptr, uint32_t n_cap, Load load, Store store, const T* partials) {
+__global__ void __launch_bounds__(GG_SCAN_THREADS) scan_apply_kernel(const uint32_t* n_ptr, uint32_t n_cap, Load load, Store store, const T* partials, T* total_out) {
     typedef ScanTraits<T> Tr;
     __shared__ T warp_sums[GG_SCAN_THREADS / 32];
     uint32_t n = min(*n_ptr, n_cap), b, e;
     scan_chunk_range(n, &b, &e);
-    T carry = partials[blockIdx.x];
+    // exclusive prefix of this CTA's chunk = sum of the partials before it (all monoids here are commutative sums);
+    // CTA 0 sums them all for the grand total
+    T carry;
+    {
+        const uint32_t upto = (blockIdx.x == 0 && total_out) ? gridDim.x : blockIdx.x;
+        T acc = Tr::identity();
+        for (uint32_t i = threadIdx.x; i < upto; i += GG_SCAN_THREADS) acc = Tr::combine(acc, partials[i]);
+        T tot;
+        block_inclusive_scan(acc, warp_sums, &tot);
+        if (blockIdx.x == 0) { if (total_out && threadIdx.x == 0) *total_out = tot; carry = Tr::identity(); }
+        else carry = tot;
+    }
     const uint32_t tile = GG_SCAN_THREADS * GG_SCAN_ITEMS;
     for (uint32_t t0 = b; t0 < e; t0 += tile) {
         // blocked arrangement: thread t owns items [t*ITEMS, t*ITEMS+ITEMS) of the tile
@@ -312,10 +287,9 @@ __global__ void __launch_bounds__(GG_SCAN_THREADS) scan_apply_kernel(const uint3
     }
 }
 
-// Host helper: launches the three phases on `stream`. `partials` must hold GG_SCAN_BLOCKS elements of T.
+// Host helper: launches the two phases on `stream`. `partials` must hold GG_SCAN_BLOCKS elements of T.
 template <typename T, typename Load, typename Store>
 static inline void gg_scan(cudaStream_t stream, const uint32_t* n_ptr, uint32_t n_cap, Load load, Store store, T* partials, T* total_out) {
     scan_reduce_kernel<T, Load><<<GG_SCAN_BLOCKS, GG_SCAN_THREADS, 0, stream>>>(n_ptr, n_cap, load, partials);
-    scan_partials_kernel<T><<<1, 1024, 0, stream>>>(partials, GG_SCAN_BLOCKS, total_out);
-    scan_apply_kernel<T, Load, Store><<<GG_SCAN_BLOCKS, GG_SCAN_THREADS, 0, stream>>>(n_ptr, n_cap, load, store, partials);
+    scan_apply_kernel<T, Load, Store><<<GG_SCAN_BLOCKS, GG_SCAN_THREADS, 0, stream>>>(n_ptr, n_cap, load, store, partials, total_out);
 }

@@ -1300,7 +1300,7 @@ uint32_t gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s
     // a7: per-path tile bbox + tile / row offsets (one packed scan)
     gg_scan<unsigned long long>(s, n_paths, cfg.n_paths, LoadPathTiles{cfg, b.path_bbox_ord}, StorePath{cfg, b.path_bbox_ord, b.paths, b.path_row_off},
                                 (unsigned long long*)b.scan_partials, reinterpret_cast<unsigned long long*>(&b.bump->path_tiles));
-    return 6 + 4 * 3;
+    return 6 + 4 * 2;
 }
 
 uint32_t gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
@@ -1312,7 +1312,7 @@ uint32_t gg_launch_binning(const GGConfig& cfg, const GGBuffers& b, cudaStream_t
     tile_rows_kernel<0><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, nullptr, nullptr, nullptr, nullptr, b.imp_mask, b.imp_seen, b.bump);
     gg_scan<uint32_t>(s, &b.bump->path_tiles, cfg.tiles_cap, LoadTileCount{b.tiles}, StoreU32Ex{b.seg_start}, (uint32_t*)b.scan_partials, &b.bump->segments);
     path_tiling_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.seg_counts, b.lines, b.paths, b.tiles, b.seg_start, b.segments, b.bump);
-    return 4 + 3;
+    return 4 + 2;
 }
 
 uint32_t gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s) {
@@ -1324,5 +1324,5 @@ uint32_t gg_launch_coarse(const GGConfig& cfg, const GGBuffers& b, cudaStream_t 
     tile_rows_kernel<1><<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.paths, b.path_row_off, b.tiles, b.draw_recs, b.tile_hits, b.hit_off, b.hit_cursor, b.hits, b.seg_start, b.imp_mask, b.imp_seen, b.bump);
     coarse_kernel<<<GG_GRID(8), COARSE_WARPS * 32, 0, s>>>(cfg, b.draw_recs,
                                                            b.hit_off, b.hit_cnt, b.hits, b.ptcl_off, b.ptcl_len, b.ptcl, b.spill_off, b.restart_pt, b.bump);
-    return 2 + 3;
+    return 2 + 2;
 }

