@@ -165,7 +165,21 @@ def run_reference(args, rank, world):
                                        "port of internal/gpu/tilecompute (the Go original cannot be built here)",
                              "stage_s": {k: tm.get(k) for k in ("t_flatten", "t_coarse", "t_fine")}},
             "e2e": {"value": val, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line, on the process's real stdout."""
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def checksum_bands(frame, n_bands):
@@ -212,6 +226,12 @@ def main():
     # Watchdog: a wedged collective or driver call must not hold a GPU box until the caller's limit; dump every
     # thread's stack and exit instead.
     faulthandler.dump_traceback_later(int(os.environ.get("GG_BENCH_WATCHDOG_S", "900")), exit=True)
+    # stdout carries exactly ONE line, the JSON: whatever a library prints there meanwhile (NCCL's version banner does) goes
+    # to stderr instead
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
@@ -487,7 +507,7 @@ def main():
                                 "sample": f"{sample} ({cpu_s:.2f} s); own C port of internal/gpu/tilecompute, not gg's Go code",
                                 "stage_s": {k: tm[k] for k in ("t_flatten", "t_coarse", "t_fine")}}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if lib_nccl:
         ctx.comm_destroy()
     ctx.close()
