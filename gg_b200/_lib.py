@@ -20,7 +20,7 @@ SYMBOLS = [
     "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_render_device_multi", "ggcuda_get_stats", "ggcuda_set_timing",
     "ggcuda_debug_read", "ggcuda_pack_host", "ggcuda_begin_keyed", "ggcuda_set_dirty_rect", "ggcuda_register_target",
     "ggcuda_unregister_target", "ggcuda_comm_unique_id", "ggcuda_comm_init", "ggcuda_comm_destroy", "ggcuda_all_gather_bands",
-    "ggcuda_sync", "ggcuda_encoding_hash",
+    "ggcuda_sync", "ggcuda_encoding_hash", "ggcuda_fill_path_gradient",
 ]
 
 LINE = np.dtype([("path_ix", "<u4"), ("p0", "<f4", 2), ("p1", "<f4", 2)])
@@ -78,6 +78,7 @@ def load():
     L.ggcuda_set_band.argtypes = [vp, u32, u32]
     L.ggcuda_fill_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_int]
     L.ggcuda_stroke_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_double, C.c_int, C.c_int, C.c_double]
+    L.ggcuda_fill_path_gradient.argtypes = [vp, vp, u32, vp, u32, C.c_int, vp, vp, u32, C.c_int, C.c_int]
     L.ggcuda_push_clip.argtypes = [vp, vp, u32, vp, u32]
     L.ggcuda_push_layer.argtypes = [vp, u32, C.c_float]
     L.ggcuda_pop.argtypes = [vp]
@@ -208,6 +209,15 @@ class Context:
         col = np.asarray(rgba_straight, dtype=np.uint8)
         self._ck(self.L.ggcuda_fill_path(self.h, _p(v), v.size, _p(c), c.size, _p(col), int(fill_rule)))
 
+    def fill_path_gradient(self, verbs, coords, kind, geom, stops, extend=0, fill_rule=0):
+        """kind 0 linear (x0, y0, x1, y1) / 1 radial (cx, cy, r0, r1); stops: [(offset, r, g, b, a), ...] straight alpha."""
+        v = np.ascontiguousarray(verbs, dtype=np.uint8)
+        c = np.ascontiguousarray(coords, dtype=np.float64).ravel()
+        g = np.zeros(6, dtype=np.float64)
+        g[:len(geom)] = geom
+        st = np.ascontiguousarray(stops, dtype=np.float64).reshape(-1, 5)
+        self._ck(self.L.ggcuda_fill_path_gradient(self.h, _p(v), v.size, _p(c), c.size, int(kind), _p(g), _p(st), len(st), int(extend), int(fill_rule)))
+
     def stroke_path(self, verbs, coords, rgba_straight, width, cap=0, join=0, miter_limit=4.0):
         v = np.ascontiguousarray(verbs, dtype=np.uint8)
         c = np.ascontiguousarray(coords, dtype=np.float64).ravel()
@@ -262,7 +272,7 @@ class Context:
         m = self.L.ggcuda_pack_host(self.h, _p(words), n, _p(lay))
         if m < 0:
             self._ck(int(m))
-        return words[:int(lay[0]["n_scene_words"])], lay[0]
+        return words, lay[0]   # n_scene_words of scene, 8 tail words, the gradient table
 
     def set_timing(self, on):
         self._ck(self.L.ggcuda_set_timing(self.h, int(on)))

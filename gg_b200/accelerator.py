@@ -70,8 +70,9 @@ class Paint:
     """The subset of gg.Paint the accelerator reads (paint.go; path_convert.go:116-128)."""
 
     def __init__(self, color=(0, 0, 0, 1), fill_rule=FillRuleNonZero, line_width=1.0, line_cap=LineCapButt,
-                 line_join=LineJoinMiter, miter_limit=4.0, dashed=False):
+                 line_join=LineJoinMiter, miter_limit=4.0, dashed=False, brush=None):
         self.color = color            # straight RGBA in [0, 1] (gg.RGBA)
+        self.brush = brush            # LinearGradientBrush / RadialGradientBrush, or None for the solid colour
         self.FillRule = fill_rule
         self.line_width = line_width
         self.line_cap = line_cap
@@ -85,6 +86,28 @@ class Paint:
     def color_u8(self):
         """extractColorU8 (path_convert.go:116-140): clampU8(v*255+0.5), straight alpha."""
         return tuple(int(min(255.0, max(0.0, v * 255.0 + 0.5))) for v in self.color)
+
+
+class LinearGradientBrush:
+    """gg.LinearGradientBrush (gradient_linear.go): start / end point, colour stops (offset, RGBA straight), extend mode."""
+
+    kind = 0
+
+    def __init__(self, x0, y0, x1, y1, extend=0):
+        self.geom, self.stops, self.extend = (x0, y0, x1, y1), [], extend
+
+    def AddColorStop(self, offset, rgba):
+        self.stops.append((float(offset), *[float(v) for v in rgba]))
+        return self
+
+
+class RadialGradientBrush(LinearGradientBrush):
+    """gg.RadialGradientBrush (gradient_radial.go) with the focus at the centre."""
+
+    kind = 1
+
+    def __init__(self, cx, cy, r0, r1, extend=0):
+        self.geom, self.stops, self.extend = (cx, cy, r0, r1), [], extend
 
 
 class GPURenderTarget:
@@ -122,7 +145,7 @@ class CUDAAccelerator:
 
     def CanAccelerate(self, op):
         # False for the SDF shape ops so that gg offers the exact original path (shape routing)
-        return bool(op & (AccelFill | AccelStroke | AccelScene))
+        return bool(op & (AccelFill | AccelStroke | AccelScene | AccelGradient))
 
     def CanCompute(self):   # ComputePipelineAware, accelerator.go:444-447
         return self.ctx is not None
@@ -140,7 +163,11 @@ class CUDAAccelerator:
         if path is None or path.NumVerbs() == 0:
             return
         self._bind(target)
-        self.ctx.fill_path(path.verbs, path.coords, paint.color_u8(), paint.FillRule)
+        if paint.brush is not None:
+            b = paint.brush
+            self.ctx.fill_path_gradient(path.verbs, path.coords, b.kind, b.geom, b.stops, b.extend, paint.FillRule)
+        else:
+            self.ctx.fill_path(path.verbs, path.coords, paint.color_u8(), paint.FillRule)
         self._pending += 1
 
     def StrokePath(self, target, path, paint):

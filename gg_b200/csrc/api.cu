@@ -56,6 +56,7 @@ struct Ctx {
         tiles, seg_start, imp_mask, imp_seen, seg_counts, segments, tile_hits, hit_off, hit_cnt, hit_cursor, hits, ptcl_off, ptcl_len, ptcl, restart_pt, spill_off, spill, bump,
         scan_partials, frame_d;
     uint32_t imp_words = 0;
+    size_t uploaded_words = 0;   // packed scene + tail + gradient table, as last uploaded
     uint32_t lines_cap = 0, tiles_cap = 0, rows_cap = 0, seg_counts_cap = 0, segments_cap = 0, hits_cap = 0, ptcl_cap = 0, spill_cap = 0, esegs_cap = 0;
     // Read-back targets the caller asked to page-lock (ggcuda_register_target): a flush whose destination lies inside
     // one is DMA'd straight into it, slice by slice while fine is still running; any other goes through the staging buffer.
@@ -144,6 +145,7 @@ int upload(Ctx* c) {
     if ((r = ensure(c, c->scene_d, words * 4))) return r;
     CK(cudaMemcpyAsync(c->scene_d.p, c->h_scene, words * 4, cudaMemcpyHostToDevice, c->stream));
     c->stats.scene_bytes = words * 4;
+    c->uploaded_words = words;
     size_t nd = std::max<size_t>(L.n_draws, 1), np = std::max<size_t>(L.n_paths, 1), bt = std::max<size_t>(band_tiles(c), 1);
     if ((r = ensure(c, c->tag_monoids, sizeof(GGPathMonoid) * L.n_tag_words))) return r;
     if ((r = ensure(c, c->draw_monoids, sizeof(GGDrawMonoid) * nd))) return r;
@@ -217,6 +219,7 @@ void fill_config(Ctx* c, uint32_t flags) {
     for (int i = 0; i < 4; i++) g.bg[i] = (float)c->bg[i] / 255.0f;
     g.flags = ((flags & GGCUDA_COMPOSITE_OVER) ? GG_FLAG_BG_FROM_DST : 0u) | ((flags & GGCUDA_TARGET_F32) ? GG_FLAG_TARGET_F32 : 0u);
     g.sm_count = (uint32_t)c->sm_count;
+    g.grad_base = L.n_scene_words + 8; g.n_grads = c->scene.n_gradients;
 }
 
 GGBuffers buffers(Ctx* c) {
@@ -570,6 +573,24 @@ int ggcuda_fill_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, cons
     GG_CATCH(c)
 }
 
+int ggcuda_fill_path_gradient(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
+                              int kind, const double geom[6], const double* stops, uint32_t n_stops, int extend, int fill_rule) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !geom || (!stops && n_stops)) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
+    if (kind != GGCUDA_GRADIENT_LINEAR && kind != GGCUDA_GRADIENT_RADIAL) return fail(c, GGCUDA_ERR_UNSUPPORTED, "gradient kind not supported by the CUDA path (sweep and focal radial gradients fall back)");
+    if (extend < 0 || extend > 2 || n_stops > 64) return fail(c, GGCUDA_ERR_INVALID, "bad gradient");
+    if (n_verbs == 0) return 0;
+    c->scene.begin_path(ID6, fill_rule == GGCUDA_FILL_EVENODD);
+    c->scene.add_verbs(verbs, n_verbs, coords, n_coords);
+    c->scene.end_path();
+    c->scene.draw_gradient(kind, geom, stops, n_stops, extend);
+    c->uploaded = false;
+    return 0;
+    GG_CATCH(c)
+}
+
 int ggcuda_stroke_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
                        const uint8_t rgba[4], double width, int cap, int join, double miter_limit) {
     Ctx* c = reinterpret_cast<Ctx*>(h);
@@ -888,7 +909,7 @@ long long ggcuda_debug_read(ggcuda_ctx* h, int which, void* dst, size_t cap) {
     uint32_t bt = band_tiles(c);
     const void* src = nullptr; size_t bytes = 0;
     switch (which) {
-    case GGCUDA_BUF_SCENE: src = c->scene_d.p; bytes = 4 * (size_t)L.n_scene_words; break;
+    case GGCUDA_BUF_SCENE: src = c->scene_d.p; bytes = 4 * std::max<size_t>(c->uploaded_words, L.n_scene_words); break;   // + tail + gradient table
     case GGCUDA_BUF_TAG_MONOIDS: src = c->tag_monoids.p; bytes = sizeof(GGPathMonoid) * (size_t)L.n_tag_words; break;
     case GGCUDA_BUF_DRAW_MONOIDS: src = c->draw_monoids.p; bytes = sizeof(GGDrawMonoid) * (size_t)L.n_draws; break;
     case GGCUDA_BUF_INFO: src = c->info.p; bytes = 4 * (size_t)L.n_draws; break;

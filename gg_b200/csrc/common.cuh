@@ -26,7 +26,7 @@ struct GGClipInp { uint32_t ix; int32_t path_ix; };                            /
 
 // Per-draw record produced by draw_leaf for coarse (our "info" superset).
 // tag: draw tag. parent: draw index of the innermost enclosing BeginClip (-1 = none); for an
-// EndClip it is the index of its own BeginClip. a/b: Color -> rgba8 premul / even-odd flag;
+// EndClip it is the index of its own BeginClip. a/b: Color -> rgba8 premul (gradient: its index) / bit 0 even-odd, bit 1 gradient;
 // BeginClip -> index of the matching EndClip / unused; EndClip -> blend word / alpha bits.
 struct GGDrawRec { uint32_t tag; int32_t parent; uint32_t a; uint32_t b; };
 // One (draw, tile) hit of coarse's per-tile lists, written by the backdrop pass that already holds the path tile in
@@ -41,6 +41,7 @@ struct __align__(16) GGHit { uint32_t draw; uint32_t seg_count; uint32_t seg_sta
 #define GG_DRAWTAG_COLOR 0x44u
 #define GG_DRAWTAG_BEGIN_CLIP 0x9u
 #define GG_DRAWTAG_END_CLIP 0x21u
+#define GG_DRAWTAG_GRADIENT 0x444u   // DrawTagColor's monoid increments + bit 10: the scene word is a gradient index (ours)
 #define GG_PTAG_LINETO 0x09u
 #define GG_PTAG_QUADTO 0x0Au
 #define GG_PTAG_CUBICTO 0x0Bu
@@ -54,6 +55,7 @@ struct __align__(16) GGHit { uint32_t draw; uint32_t seg_count; uint32_t seg_sta
 #define GG_CMD_FILL 1u
 #define GG_CMD_SOLID 3u
 #define GG_CMD_COLOR 5u
+#define GG_CMD_GRAD 6u               // {tag, gradient index}: CmdColor with a per-pixel colour (Vello's CmdLinGrad slot; ours)
 #define GG_CMD_BEGIN_CLIP 10u
 #define GG_CMD_END_CLIP 11u
 #define GG_BLEND_STACK_SPLIT 1   // clip levels kept on chip by fine (the reference's BlendStackSplit is 4, ptcl.go:31; not observable)
@@ -109,7 +111,9 @@ struct GGConfig {
     float bg[4];                            // premultiplied background
     uint32_t flags;
     uint32_t sm_count;                      // multiprocessors of the device (queried at context creation): grids are multiples of it
+    uint32_t grad_base, n_grads;            // gradient table (word offset in the scene buffer): 16-word records | stops | ramps
 };
+#define GG_RAMP_N 256                       // entries of a gradient's colour ramp (premultiplied float4)
 #define GG_FLAG_BG_FROM_DST 1u              // composite-over: the scene is rasterised on transparent and source-overed onto the
                                             // destination's pixels with the reference's byte formula (vello_accelerator.go:388-442)
 #define GG_FLAG_TARGET_F32 2u               // destination holds premultiplied float4 pixels (16 bytes) instead of RGBA8

@@ -275,7 +275,7 @@ struct PtclStream {
         for (int hop = 0; hop < 6 && c + 2 < avail; hop++) {
             const uint32_t tag = word(c);
             if (tag == GG_CMD_FILL) { *n = word(c + 1) >> 1; *seg_ix = word(c + 2); return true; }
-            else if (tag == GG_CMD_COLOR) c += 2;
+            else if (tag == GG_CMD_COLOR || tag == GG_CMD_GRAD) c += 2;
             else if (tag == GG_CMD_END_CLIP) c += 3;
             else if (tag == GG_CMD_SOLID || tag == GG_CMD_BEGIN_CLIP) c += 1;
             else return false;
@@ -462,7 +462,8 @@ __device__ __forceinline__ uint32_t composite_over_u8(uint32_t s, uint32_t d) {
 __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
-                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, GGFineRange rg, uint32_t part, GGFineMirrors mir) {
+                                                               float4* spill, GGBump* bump, uint8_t* dst, size_t stride, GGFineRange rg, uint32_t part, GGFineMirrors mir,
+                                                               const uint32_t* __restrict__ gtab) {
     // a stage overflowed its buffer: PTCL / segments are incomplete, the host re-runs the pass with larger buffers
     if (bump->failed || bump->hits > cfg.hits_cap || bump->ptcl_words > cfg.ptcl_cap || bump->segments > cfg.segments_cap) return;
     const uint32_t lane = threadIdx.x & 31;
@@ -550,6 +551,38 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     cmd += 2;
 #pragma unroll
                     for (int i = 0; i < PX; i++) {   // fine.go:104-123: rgba * (1 - c.a * cov) + c * cov, two FMAs per channel
+                        const float cov = area[i];
+                        rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
+                        rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
+                        rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);
+                        rgba[i].w = fmaf(cov, fmaf(-c.w, rgba[i].w, c.w), rgba[i].w);
+                    }
+                } else if (tag == GG_CMD_GRAD) {
+                    // Gradient brush (gg.LinearGradientBrush / RadialGradientBrush.ColorAt at the pixel centre, software.go:1086-1090):
+                    // t from the record's coefficients, extend mode (gradient.go:42-60), colour from the gradient's 256-entry
+                    // premultiplied ramp (built on the host with gg's linear-light interpolation), linear between entries.
+                    const uint32_t* g = gtab + 16u * ps.word(cmd + 1);
+                    cmd += 2;
+                    const uint32_t kind = g[0], extend = g[1];
+                    const float4* ramp = reinterpret_cast<const float4*>(gtab + g[4]);
+                    const float k0 = __uint_as_float(g[11]), k1 = __uint_as_float(g[12]), k2 = __uint_as_float(g[13]), ok = __uint_as_float(g[14]);
+                    const float gcx = __uint_as_float(g[5]), gcy = __uint_as_float(g[6]);
+                    const float fy = (float)py + 0.5f;
+#pragma unroll
+                    for (int i = 0; i < PX; i++) {
+                        const float fx = (float)(tx * GG_TILE_W + xb + i) + 0.5f;
+                        float t;
+                        if (kind == 0u) t = fx * k0 + fy * k1 + k2;
+                        else { const float ddx = fx - gcx, ddy = fy - gcy; t = sqrtf(ddx * ddx + ddy * ddy) * k0 + k1; }
+                        if (extend == 1u) { t -= floorf(t); }
+                        else if (extend == 2u) { t = fabsf(t); const float per = floorf(t); t -= per; if (((int)per) & 1) t = 1.0f - t; }
+                        else t = clamp01(t);
+                        if (ok == 0.0f) t = 0.0f;   // degenerate geometry: the first stop everywhere
+                        const float u = t * (float)(GG_RAMP_N - 1);
+                        const int i0 = min((int)u, GG_RAMP_N - 2);
+                        const float fr = u - (float)i0;
+                        const float4 c0 = ramp[i0], c1 = ramp[i0 + 1];
+                        const float4 c = make_float4(c0.x + fr * (c1.x - c0.x), c0.y + fr * (c1.y - c0.y), c0.z + fr * (c1.z - c0.z), c0.w + fr * (c1.w - c0.w));
                         const float cov = area[i];
                         rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
                         rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
@@ -711,5 +744,5 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
     fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride,
-                                                      rg, part, mir);
+                                                      rg, part, mir, b.scene + cfg.grad_base);
 }

@@ -73,6 +73,15 @@ struct HostScene {
 
     void append_stroke(const StrokeSink& k);               // outline loops of an expanded stroke into the current path
     void draw_color(uint32_t rgba_premul);                 // DrawTagColor for the path just ended
+    // Gradient brush for the path just ended (gg.LinearGradientBrush / RadialGradientBrush, gradient_linear.go,
+    // gradient_radial.go, gradient.go). kind 0 linear: geom = x0, y0, x1, y1; kind 1 radial: geom = cx, cy, r0, r1 (device
+    // space). stops: 5 floats each {offset, r, g, b, a} straight alpha. The table travels behind the packed scene (see pack()).
+    void draw_gradient(int kind, const double geom[6], const double* stops, uint32_t n_stops, int extend);
+    // gradient table words: per gradient a 16-word record {kind, extend, n_stops, stops offset, ramp offset, 6 raw geometry
+    // floats, 4 derived coefficients, pad}, then all stops (5 floats each), then all ramps (GG_RAMP_N premultiplied float4)
+    std::vector<uint32_t> grad_recs; std::vector<float> grad_stops, grad_ramps;
+    uint32_t n_gradients = 0;
+    size_t gradient_words() const { return grad_recs.size() + grad_stops.size() + grad_ramps.size(); }
     void begin_clip(uint32_t blend_word, float alpha, uint8_t kind);   // DrawTagBeginClip for the path just ended
     void begin_layer(uint32_t blend_word, float alpha);   // PushLayer: clip rectangle carrying blend + alpha
     bool end_clip(uint8_t kind);                           // DrawTagEndClip (+ dummy path); false if nothing to pop

@@ -72,13 +72,14 @@ __global__ void draw_leaf_kernel(GGConfig cfg, const uint32_t* __restrict__ scen
         int32_t parent = (int32_t)scene[cfg.clip_parent_base + 2 * d];
         uint32_t link = scene[cfg.clip_parent_base + 2 * d + 1];
         GGDrawRec r; r.tag = tag; r.parent = parent; r.a = 0; r.b = 0;
-        if (tag == GG_DRAWTAG_COLOR) {
-            uint32_t rgba = scene[cfg.draw_data_base + m.scene_offset];
+        if (tag == GG_DRAWTAG_COLOR || tag == GG_DRAWTAG_GRADIENT) {
+            uint32_t rgba = scene[cfg.draw_data_base + m.scene_offset];   // gradient: its index in the gradient table
             info[m.info_offset] = rgba;
             r.a = rgba;
             // fill rule: style word of this path (coarse.go:683-705 indexes styles by path_ix;
             // our encoder emits one style per path marker so the lookup is exact)
-            r.b = (scene[cfg.style_base + GG_STYLE_WORDS * m.path_ix] & 0x02u) ? 1u : 0u;
+            r.b = ((scene[cfg.style_base + GG_STYLE_WORDS * m.path_ix] & 0x02u) ? 1u : 0u) | (tag == GG_DRAWTAG_GRADIENT ? 2u : 0u);
+            r.tag = GG_DRAWTAG_COLOR;   // a gradient fill is a colour draw everywhere downstream; coarse reads bit 1 of b
         } else if (tag == GG_DRAWTAG_BEGIN_CLIP) {
             if (m.clip_ix < cfg.n_clips) { clip_inps[m.clip_ix].ix = d; clip_inps[m.clip_ix].path_ix = (int32_t)m.path_ix; }
             r.a = link;
@@ -725,10 +726,11 @@ __global__ void __launch_bounds__(256) tile_rows_kernel(GGConfig cfg, const uint
         uint32_t base = path.tiles + y * bw;
         uint32_t gy = path.bbox[1] + y - cfg.band_y0;
         uint32_t tag = scene[cfg.draw_tag_base + p];   // one path marker per draw object: path p <-> draw p
+        if (tag == GG_DRAWTAG_GRADIENT) tag = GG_DRAWTAG_COLOR;
         // Even-odd fills: a tile without segments is inside only where the winding is odd. (DEVIATION: coarse.go:425
         // paints every tile with backdrop != 0 solid whatever the rule -- the hole of two nested same-direction
         // contours, backdrop 2, came out filled. The oracle follows; ot_evenodd_solid_quirk restores the reference.)
-        const bool even_odd = tag == GG_DRAWTAG_COLOR && recs[p].b != 0u;
+        const bool even_odd = tag == GG_DRAWTAG_COLOR && (recs[p].b & 1u) != 0u;
         // Implicit layers (GG_BLEND_IMPLICIT: no geometry, full coverage) have no tiles of their own: a hit of something
         // they enclose brings their Begin/End pair into that tile's list -- once per (layer, tile): PASS 0 claims the
         // pair with one bit per (layer, tile) and remembers per path tile which ancestors it brought (imp_mask), PASS 1
@@ -964,7 +966,7 @@ __device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_
             // per-hit flags for the restart bookkeeping: bit 0 = tile has segments for this path,
             // bits 1-2: 1 = opaque colour, 2 = End of a wiping layer (if empty), 3 = End of a Clear layer
             uint32_t hflags = t.seg_count ? 1u : 0u;
-            if (r.tag == GG_DRAWTAG_COLOR) { if ((r.a >> 24) == 255u) hflags |= 1u << 1; }
+            if (r.tag == GG_DRAWTAG_COLOR) { if ((r.a >> 24) == 255u && !(r.b & 2u)) hflags |= 1u << 1; }
             else if (r.tag == GG_DRAWTAG_END_CLIP) {
                 uint32_t mixm = (r.a >> 8) & 0xffu, comp = r.a & 0xffu;
                 if (mixm == 0u && comp == 0u) hflags |= 3u << 1;
@@ -1032,9 +1034,9 @@ __device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_
             if (emit) {
                 for (uint32_t k = 0; k < pre; k++) ptcl[o++] = GG_CMD_BEGIN_CLIP;
                 if (r.tag == GG_DRAWTAG_COLOR) {
-                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | r.b; ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
+                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | (r.b & 1u); ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
                     else ptcl[o++] = GG_CMD_SOLID;
-                    ptcl[o++] = GG_CMD_COLOR; ptcl[o++] = r.a;
+                    ptcl[o++] = (r.b & 2u) ? GG_CMD_GRAD : GG_CMD_COLOR; ptcl[o++] = r.a;
                 } else if (r.tag == GG_DRAWTAG_BEGIN_CLIP) {
                     ptcl[o++] = GG_CMD_BEGIN_CLIP;
                 } else {
@@ -1231,11 +1233,11 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
                 const uint32_t tg = s8 & CH_TAG;
                 const uint32_t after = pos_u + inc;   // list offset right after this command
                 if (tg == 0u) {
-                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | r.b; ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
+                    if (t.seg_count) { ptcl[o++] = GG_CMD_FILL; ptcl[o++] = (t.seg_count << 1) | (r.b & 1u); ptcl[o++] = sstart; ptcl[o++] = (uint32_t)t.backdrop; }
                     else ptcl[o++] = GG_CMD_SOLID;
-                    ptcl[o++] = GG_CMD_COLOR; ptcl[o++] = r.a;
+                    ptcl[o++] = (r.b & 2u) ? GG_CMD_GRAD : GG_CMD_COLOR; ptcl[o++] = r.a;
                     // restart point for fine: an opaque colour over the whole tile outside every clip
-                    if (lp == CH_NONE && !t.seg_count && (r.a >> 24) == 255u && after > restart) { restart = after; restart_rgba = r.a; }
+                    if (lp == CH_NONE && !t.seg_count && (r.a >> 24) == 255u && !(r.b & 2u) && after > restart) { restart = after; restart_rgba = r.a; }
                 } else if (tg == 1u) {
                     ptcl[o++] = GG_CMD_BEGIN_CLIP;
                 } else {

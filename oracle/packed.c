@@ -96,7 +96,8 @@ static void *fine_worker(void *arg) {
     float px[256 * 4];
     for (int t = j->t0; t < j->t1; t++) {
         int tx = t % c->width_in_tiles, ty = t / c->width_in_tiles;
-        ot_fine_tile(c->ptcl_words + c->ptcl_offsets[t], c->ptcl_offsets[t + 1] - c->ptcl_offsets[t], c->segments, c->n_segments, j->bg, px);
+        ot_fine_tile_at(c->ptcl_words + c->ptcl_offsets[t], c->ptcl_offsets[t + 1] - c->ptcl_offsets[t], c->segments, c->n_segments, j->bg, px,
+                        tx * 16, ty * 16, c->gtab);
         for (int ly = 0; ly < 16; ly++) {
             int py = ty * 16 + ly; if (py >= j->h) break;
             for (int lx = 0; lx < 16; lx++) {
@@ -158,7 +159,10 @@ static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, i
     const uint32_t *dtags = scene + L[L_DRAW_TAG_BASE], *ddata = scene + L[L_DRAW_DATA_BASE], *styles = scene + L[L_STYLE_BASE];
     for (uint32_t d = 0; d < n_draws; d++) {
         el[d].line_start = start[d]; el[d].line_count = start[d + 1] - start[d];
-        if (dtags[d] == 0x44) { el[d].type = OT_ELEM_DRAW | OT_ELEM_PACKED; el[d].packed_rgba = ddata[dd]; el[d].even_odd = (styles[3 * d] & 2u) ? 1 : 0; dd += 1; }
+        if (dtags[d] == 0x44 || dtags[d] == 0x444) {
+            el[d].type = OT_ELEM_DRAW | OT_ELEM_PACKED | (dtags[d] == 0x444 ? OT_ELEM_GRADIENT : 0u);
+            el[d].packed_rgba = ddata[dd]; el[d].even_odd = (styles[3 * d] & 2u) ? 1 : 0; dd += 1;
+        }
         else if (dtags[d] == 0x9) { el[d].type = OT_ELEM_BEGIN_CLIP; el[d].blend = ddata[dd]; el[d].alpha = bits_f(ddata[dd + 1]); dd += 2; }
         else { el[d].type = OT_ELEM_END_CLIP; el[d].line_count = 0; }
     }
@@ -167,6 +171,22 @@ static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, i
     ot_style_per_path = 1;
     ot_coarse *c = ot_coarse_run(el, n_draws, lines, w, h);
     ot_style_per_path = saved;
+    {   /* the gradient table behind the packed scene's 8 tail words: tail[5] = its word offset, tail[6] = number of gradients */
+        const uint32_t *tail = scene + L[L_N_SCENE_WORDS];
+        uint32_t ng = tail[6];
+        if (ng) {
+            const uint32_t *gt = scene + tail[5];
+            uint32_t words = 16 * ng;
+            for (uint32_t g = 0; g < ng; g++) {
+                uint32_t e1 = gt[16 * g + 3] + 5 * gt[16 * g + 2], e2 = gt[16 * g + 4] + 256 * 4;
+                if (e1 > words) words = e1;
+                if (e2 > words) words = e2;
+            }
+            c->gtab = (uint32_t *)malloc(4 * (size_t)words);
+            memcpy(c->gtab, gt, 4 * (size_t)words);
+            c->n_gtab_words = words;
+        }
+    }
     if (t_flatten) *t_flatten = t1 - t0;
     if (n_lines_out) *n_lines_out = n;
     free(el); free(start); free(lines);

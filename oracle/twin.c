@@ -627,7 +627,8 @@ static void dm_combine(ot_draw_monoid *a, const ot_draw_monoid *b) {
     a->path_ix += b->path_ix; a->clip_ix += b->clip_ix; a->scene_offset += b->scene_offset; a->info_offset += b->info_offset;
 }
 
-enum { DRAWTAG_COLOR = 0x44, DRAWTAG_BEGIN_CLIP = 0x9, DRAWTAG_END_CLIP = 0x21 };          /* scene_encode.go:70-76 */
+enum { DRAWTAG_COLOR = 0x44, DRAWTAG_BEGIN_CLIP = 0x9, DRAWTAG_END_CLIP = 0x21,             /* scene_encode.go:70-76 */
+       DRAWTAG_GRADIENT = 0x444 };   /* ggcuda: DrawTagColor's monoid increments, the scene word is a gradient index */
 /* The three scan stages on a packed scene (the reference's own layout or ggcuda's, which shares the draw-tag encoding):
  *   pathtagReduce + pathtagScan (pathtag.go:76-121): exclusive PathMonoid per tag word;
  *   drawReduce + drawLeafScan (draw_leaf.go:54-151): exclusive DrawMonoid per draw object, info[], ClipInp[];
@@ -657,7 +658,7 @@ uint32_t ot_scan_stages(const uint32_t *scene, uint32_t n_scene_words, uint32_t 
     clip_inp *clip_inps = (clip_inp *)calloc(n_clips ? n_clips : 1, sizeof(clip_inp));
     for (uint32_t i = 0; i < n_draw; i++) {
         uint32_t tag = scene[draw_tag_base + i];
-        if (tag == DRAWTAG_COLOR) {
+        if (tag == DRAWTAG_COLOR || tag == DRAWTAG_GRADIENT) {
             uint32_t so = draw_data_base + dm[i].scene_offset;
             if (info && so < n_scene_words && dm[i].info_offset < n_info) info[dm[i].info_offset] = scene[so];
         } else if (tag == DRAWTAG_BEGIN_CLIP) {
@@ -1064,7 +1065,8 @@ static inline uint32_t f32_bits(float f) { uint32_t u; memcpy(&u, &f, 4); return
 static inline float bits_f32(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
 
 enum { PTAG_LINETO = 0x9, PTAG_PATH = 0x10, PTAG_TRANSFORM = 0x20, PTAG_STYLE = 0x40 };      /* scene_encode.go:78-86 */
-enum { CMD_END = 0, CMD_FILL = 1, CMD_SOLID = 3, CMD_COLOR = 5, CMD_BEGIN_CLIP = 10, CMD_END_CLIP = 11 }; /* ptcl.go:17-24 */
+enum { CMD_END = 0, CMD_FILL = 1, CMD_SOLID = 3, CMD_COLOR = 5, CMD_BEGIN_CLIP = 10, CMD_END_CLIP = 11, /* ptcl.go:17-24 */
+       CMD_GRAD = 6 };   /* ggcuda: {tag, gradient index} */
 
 /* scene_encode.go:312-347 encodePath */
 static void encode_path(u32vec *raw_tags, u32vec *path_data, u32vec *transforms, u32vec *styles,
@@ -1135,7 +1137,7 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
         switch (OT_ELEM_TYPE(el->type)) {
         case OT_ELEM_DRAW:
             encode_path(&raw_tags, &path_data, &transforms, &styles, lines_in + el->line_start, el->line_count, (int)el->even_odd);
-            u32_push(&draw_tags, DRAWTAG_COLOR);
+            u32_push(&draw_tags, (el->type & OT_ELEM_GRADIENT) ? DRAWTAG_GRADIENT : DRAWTAG_COLOR);
             u32_push(&draw_data, (el->type & OT_ELEM_PACKED) ? el->packed_rgba : pack_color(el->color));
             n_paths++; n_draw++;
             break;
@@ -1263,7 +1265,8 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
             if (pix >= n_paths) continue;
             ot_path path = out->paths[pix];
             int bw = (int)(path.bbox[2] - path.bbox[0]), bh = (int)(path.bbox[3] - path.bbox[1]);
-            if (tag == DRAWTAG_COLOR) {
+            if (tag == DRAWTAG_COLOR || tag == DRAWTAG_GRADIENT) {
+                const uint32_t cmd_paint = tag == DRAWTAG_GRADIENT ? CMD_GRAD : CMD_COLOR;
                 uint32_t rgba = m.info_offset < n_info ? info[m.info_offset] : 0;
                 int even_odd = 0;
                 if (pix < style_count && L.style_base + pix < off) even_odd = (scene[L.style_base + pix] & 0x02) != 0;
@@ -1283,14 +1286,14 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
                     if (cnt > 0) {
                         ptcl_push(&ptcls[g], CMD_FILL); ptcl_push(&ptcls[g], (cnt << 1) | (uint32_t)even_odd);
                         ptcl_push(&ptcls[g], gsb + st); ptcl_push(&ptcls[g], (uint32_t)t.backdrop);
-                        ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
+                        ptcl_push(&ptcls[g], cmd_paint); ptcl_push(&ptcls[g], rgba);
                     } else if (t.backdrop != 0 && (!even_odd || ot_evenodd_solid_quirk || (t.backdrop & 1))) {
                         /* DEVIATION from coarse.go:425, which paints every tile with backdrop != 0 solid whatever the
                          * fill rule: under even-odd a tile without segments is inside only when its winding is odd
                          * (two nested same-direction contours leave backdrop 2 in the hole). ot_evenodd_solid_quirk = 1
                          * restores the reference's behaviour. */
                         ptcl_push(&ptcls[g], CMD_SOLID);
-                        ptcl_push(&ptcls[g], CMD_COLOR); ptcl_push(&ptcls[g], rgba);
+                        ptcl_push(&ptcls[g], cmd_paint); ptcl_push(&ptcls[g], rgba);
                     }
                 }
             } else if (tag == DRAWTAG_BEGIN_CLIP && (scene[L.draw_data_base + m.scene_offset] & OT_BLEND_IMPLICIT)) {
@@ -1406,13 +1409,54 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems, const ot_lin
 void ot_coarse_free(ot_coarse *c) {
     if (!c) return;
     free(c->paths); free(c->tiles); free(c->segments); free(c->path_seg_base); free(c->path_total_segs);
-    free(c->ptcl_offsets); free(c->ptcl_words); free(c->scene); free(c->tag_monoids); free(c->draw_monoids); free(c->info);
+    free(c->ptcl_offsets); free(c->ptcl_words); free(c->scene); free(c->tag_monoids); free(c->draw_monoids); free(c->info); free(c->gtab);
     free(c);
 }
 
 /* ------------------------------------------------------------------ fine.go:40-187 */
+/* gg's gradient colour at a point (gradient_linear.go:52-66, gradient_radial.go computeTSimple, gradient.go:42-131), from a
+ * record of ggcuda's gradient table: the raw geometry and the sorted stops, evaluated like the Go code (float64 geometry,
+ * float32 linear-light interpolation) -- NOT from the device's colour ramp. Straight RGBA out. */
+static float og_srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : (float)pow((double)((s + 0.055f) / 1.055f), 2.4); }
+static float og_linear_to_srgb(float l) { return l <= 0.0031308f ? l * 12.92f : 1.055f * (float)pow((double)l, 1.0 / 2.4) - 0.055f; }
+static void og_color_at(const uint32_t *gtab, uint32_t idx, double x, double y, float out[4]) {
+    const uint32_t *g = gtab + 16 * idx;
+    uint32_t kind = g[0], extend = g[1], n = g[2];
+    const uint32_t *st = gtab + g[3];   /* 5 floats per stop */
+    double t = 0; int first_only = 0;
+    double g0 = bits_f32(g[5]), g1 = bits_f32(g[6]), g2 = bits_f32(g[7]), g3 = bits_f32(g[8]);
+    if (kind == 0) {
+        double dx = g2 - g0, dy = g3 - g1, l2 = dx * dx + dy * dy;
+        if (l2 == 0) first_only = 1; else t = ((x - g0) * dx + (y - g1) * dy) / l2;
+    } else {
+        double dx = x - g0, dy = y - g1, rd = g3 - g2;
+        if (rd == 0) first_only = 1; else t = (sqrt(dx * dx + dy * dy) - g2) / rd;
+    }
+    if (n == 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
+    if (first_only || n == 1) { for (int k = 0; k < 4; k++) out[k] = bits_f32(st[1 + k]); return; }
+    if (extend == 1) { t -= floor(t); if (t < 0) t += 1; }
+    else if (extend == 2) { t = fabs(t); double per = floor(t); t -= per; if (((long long)per) % 2 == 1) t = 1 - t; }
+    else t = t < 0 ? 0 : (t > 1 ? 1 : t);
+    uint32_t i = 0;
+    while (i < n && !((double)bits_f32(st[5 * i]) >= t)) i++;
+    const uint32_t *a = NULL;
+    if (i == 0) a = st; else if (i >= n) a = st + 5 * (n - 1); else if (bits_f32(st[5 * i]) == bits_f32(st[5 * (i - 1)])) a = st + 5 * (i - 1);
+    if (a) { for (int k = 0; k < 4; k++) out[k] = bits_f32(a[1 + k]); return; }
+    const uint32_t *s1 = st + 5 * (i - 1), *s2 = st + 5 * i;
+    float lt = (float)((t - (double)bits_f32(s1[0])) / ((double)bits_f32(s2[0]) - (double)bits_f32(s1[0])));
+    for (int k = 0; k < 3; k++) {
+        float l1 = og_srgb_to_linear(bits_f32(s1[1 + k])), l2v = og_srgb_to_linear(bits_f32(s2[1 + k]));
+        out[k] = og_linear_to_srgb(l1 + lt * (l2v - l1));
+    }
+    out[3] = bits_f32(s1[4]) + lt * (bits_f32(s2[4]) - bits_f32(s1[4]));
+}
+
 void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment *segs, uint32_t n_segs,
                   const float bg[4], float *rgba_out) {
+    ot_fine_tile_at(cmds, n_words, segs, n_segs, bg, rgba_out, 0, 0, NULL);
+}
+void ot_fine_tile_at(const uint32_t *cmds, uint32_t n_words, const ot_path_segment *segs, uint32_t n_segs,
+                     const float bg[4], float *rgba_out, int origin_x, int origin_y, const uint32_t *gtab) {
     enum { PC = TILE_W * TILE_H, SPLIT = 4 };
     float (*rgba)[4] = (float (*)[4])rgba_out;
     for (int i = 0; i < PC; i++) memcpy(rgba[i], bg, 16);
@@ -1452,6 +1496,17 @@ void ot_fine_tile(const uint32_t *cmds, uint32_t n_words, const ot_path_segment 
                 if (ot_truncate_per_draw && cov != 0.0f)   /* gg's CPU pixmap: 8 bits, truncated, after every draw that touches the pixel
                                                              * (software.go:1003-1024, pixmap.go:218-228); 1/512 absorbs the float32 error of k/255*255 */
                     for (int k = 0; k < 4; k++) { float v = rgba[i][k] * 255.0f + (1.0f / 512.0f); v = v < 0 ? 0 : (v > 255.0f ? 255.0f : v); rgba[i][k] = floorf(v) / 255.0f; }
+            }
+        } break;
+        case CMD_GRAD: {   /* CmdColor with the brush's colour at the pixel centre (software.go:1086-1090) */
+            uint32_t gi = cmds[off++];
+            for (int i = 0; i < PC; i++) {
+                float c[4] = {0, 0, 0, 0};
+                if (gtab) og_color_at(gtab, gi, (double)(origin_x + i % TILE_W) + 0.5, (double)(origin_y + i / TILE_W) + 0.5, c);
+                float cov = area[i];
+                float fa = c[3] * cov, inv = 1.0f - fa;
+                rgba[i][0] = rgba[i][0] * inv + c[0] * c[3] * cov; rgba[i][1] = rgba[i][1] * inv + c[1] * c[3] * cov;
+                rgba[i][2] = rgba[i][2] * inv + c[2] * c[3] * cov; rgba[i][3] = rgba[i][3] * inv + fa;
             }
         } break;
         case CMD_BEGIN_CLIP:
@@ -1511,8 +1566,8 @@ void ot_fine_frame(const ot_coarse *c, const uint8_t bg[4], int w, int h, uint8_
     float px[TILE_W * TILE_H * 4];
     for (int ty = 0; ty < c->height_in_tiles; ty++) for (int tx = 0; tx < c->width_in_tiles; tx++) {
         int t = ty * c->width_in_tiles + tx;
-        ot_fine_tile(c->ptcl_words + c->ptcl_offsets[t], c->ptcl_offsets[t + 1] - c->ptcl_offsets[t],
-                     c->segments, c->n_segments, bgf, px);
+        ot_fine_tile_at(c->ptcl_words + c->ptcl_offsets[t], c->ptcl_offsets[t + 1] - c->ptcl_offsets[t],
+                        c->segments, c->n_segments, bgf, px, tx * TILE_W, ty * TILE_H, c->gtab);
         for (int ly = 0; ly < TILE_H; ly++) {
             int py = ty * TILE_H + ly; if (py >= h) break;
             for (int lx = 0; lx < TILE_W; lx++) {

@@ -39,6 +39,7 @@ typedef struct {
     uint32_t packed_rgba; /* draw: premultiplied packed colour, used instead of `color` when OT_ELEM_PACKED is set in type */
 } ot_element;
 #define OT_ELEM_PACKED 0x100u
+#define OT_ELEM_GRADIENT 0x200u   /* draw: packed_rgba is an index into the gradient table (ggcuda's DrawTag 0x444) */
 #define OT_ELEM_TYPE(t) ((t) & 0xffu)
 
 /* scene_encode.go:52-62 */
@@ -61,6 +62,8 @@ typedef struct {
     uint32_t n_tag_words;    ot_path_monoid *tag_monoids;
     ot_draw_monoid *draw_monoids;
     uint32_t n_info;         uint32_t *info;
+    /* ggcuda's gradient table (16-word records | stops | ramps), copied from behind the packed scene; NULL without gradients */
+    uint32_t n_gtab_words;   uint32_t *gtab;
 } ot_coarse;
 
 /* ---- flatten (flatten.go, euler.go, path_convert.go) ---- */
@@ -92,6 +95,9 @@ ot_coarse *ot_coarse_run(const ot_element *elems, uint32_t n_elems,
                          const ot_line_soup *lines, int w, int h);
 void ot_coarse_free(ot_coarse *c);
 /* fine for one tile -> 256 x 4 premultiplied float32 (fine.go:40-187) */
+/* the same with the tile's pixel origin and the gradient table (CmdGrad evaluates gg's ColorAt at pixel centres) */
+void ot_fine_tile_at(const uint32_t *ptcl, uint32_t n_words, const ot_path_segment *segs, uint32_t n_segs,
+                     const float bg[4], float *rgba_out, int origin_x, int origin_y, const uint32_t *gtab);
 void ot_fine_tile(const uint32_t *ptcl, uint32_t n_words, const ot_path_segment *segs, uint32_t n_segs,
                   const float bg[4], float *rgba_out);
 /* whole frame: out_straight (w*h*4, premulToStraightU8 as rasterizer.go:405-414) and/or

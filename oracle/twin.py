@@ -40,7 +40,8 @@ class _Coarse(C.Structure):
                 ("n_scene_words", C.c_uint32), ("scene", C.c_void_p), ("layout", _Layout),
                 ("n_tag_words", C.c_uint32), ("tag_monoids", C.c_void_p),
                 ("draw_monoids", C.c_void_p),
-                ("n_info", C.c_uint32), ("info", C.c_void_p)]
+                ("n_info", C.c_uint32), ("info", C.c_void_p),
+                ("n_gtab_words", C.c_uint32), ("gtab", C.c_void_p)]
 
 
 def build(force=False):

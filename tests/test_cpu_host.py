@@ -407,7 +407,7 @@ def test_ingest_survives_malformed_encodings():
             err += 1
             continue
         words, lay = c.pack_host()
-        assert lay["n_scene_words"] == len(words) and lay["n_draws"] == lay["n_paths"]     # one path marker per draw object
+        assert lay["n_scene_words"] + 8 == len(words) and lay["n_draws"] == lay["n_paths"]     # one path marker per draw object (+ 8 tail words)
         ok += 1
     assert ok > 100 and err > 100
 

@@ -459,3 +459,58 @@ def test_exact_area_vs_gg_cpu_multicontour_folder():
         g = np.array(Image.open(os.path.join(HERE, "golden", "skia-aaa", name + ".png")).convert("RGBA"))[..., :3].astype(int)
         d = np.abs(out - g).max(-1)
         assert d.mean() <= 1.5 and (d <= 2).mean() >= 0.85 and d.max() <= max_allowed, (name, d.mean(), d.max(), (d <= 2).mean())
+
+
+# ---- gradient brushes: the oracle's CmdGrad against gg's formulas restated independently in numpy ----
+def _gg_color_at(stops, t, extend):
+    """gradient.go:42-131 (applyExtendMode, colorAtOffset, interpolateColorLinear) + internal/color/convert.go:8-23."""
+    f = np.float32
+    if extend == 1:
+        t = t - np.floor(t)
+    elif extend == 2:
+        t = abs(t); per = np.floor(t); t -= per
+        if int(per) % 2 == 1:
+            t = 1 - t
+    else:
+        t = min(1.0, max(0.0, t))
+    stops = sorted(stops, key=lambda s: s[0])
+    idx = next((i for i, s in enumerate(stops) if s[0] >= t), len(stops))
+    if idx == 0:
+        return list(stops[0][1:])
+    if idx >= len(stops):
+        return list(stops[-1][1:])
+    a, b = stops[idx - 1], stops[idx]
+    if a[0] == b[0]:
+        return list(a[1:])
+    lt = f((t - a[0]) / (b[0] - a[0]))
+    s2l = lambda s: f(s) / f(12.92) if f(s) <= f(0.04045) else f(((float(f(s)) + 0.055) / 1.055) ** 2.4)   # noqa: E731
+    l2s = lambda l: f(l) * f(12.92) if f(l) <= f(0.0031308) else f(1.055) * f(float(l) ** (1 / 2.4)) - f(0.055)   # noqa: E731
+    rgb = [float(l2s(s2l(a[1 + k]) + lt * (s2l(b[1 + k]) - s2l(a[1 + k])))) for k in range(3)]
+    return rgb + [float(f(a[4]) + lt * (f(b[4]) - f(a[4])))]
+
+
+@pytest.mark.parametrize("kind,geom,extend", [(0, (10, 5, 80, 40), 0), (0, (30, 0, 50, 0), 1), (0, (30, 10, 50, 30), 2),
+                                              (1, (48, 32, 4, 40), 0), (1, (20, 20, 0, 12), 2), (0, (5, 5, 5, 5), 0)])
+def test_gradient_fill_matches_gg_formulas(kind, geom, extend):
+    from gg_b200 import _lib
+    w, h = 96, 64
+    stops = [(1.0, 0.1, 0.2, 0.9, 1.0), (0.0, 1.0, 0.0, 0.0, 1.0), (0.4, 0.0, 1.0, 0.0, 0.5)]    # unsorted on purpose
+    c = _lib.Context(-1)
+    c.begin(w, h)
+    c.fill_path_gradient([0, 1, 1, 1, 4], [0, 0, w, 0, w, h, 0, h], kind, geom, stops, extend)
+    words, lay = c.pack_host()
+    c.close()
+    out, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 1)
+    rng = np.random.default_rng(1)
+    for _ in range(60):
+        x, y = int(rng.integers(0, w)), int(rng.integers(0, h))
+        fx, fy = x + 0.5, y + 0.5
+        g = [float(np.float32(v)) for v in geom]
+        if kind == 0:
+            dx, dy = g[2] - g[0], g[3] - g[1]
+            l2 = dx * dx + dy * dy
+            col = sorted(stops)[0][1:] if l2 == 0 else _gg_color_at(stops, ((fx - g[0]) * dx + (fy - g[1]) * dy) / l2, extend)
+        else:
+            col = _gg_color_at(stops, (np.hypot(fx - g[0], fy - g[1]) - g[2]) / (g[3] - g[2]), extend)
+        want = [int(min(1.0, max(0.0, col[k] * col[3])) * 255 + 0.5) for k in range(3)] + [int(col[3] * 255 + 0.5)]
+        assert np.abs(out[y, x].astype(int) - np.array(want)).max() <= 1, (x, y, out[y, x], want)

@@ -765,3 +765,42 @@ def test_config1_cuda_vs_gg_cpu_path(ctx):
     d1 = np.abs(out1.astype(int) - cpu1.astype(int))
     print(f"one circle r=200: mean |d| = {d1.mean():.4f}/255, max = {d1.max()}, {(d1.max(axis=2) > 2).mean() * 100:.3f}% beyond 2/255")
     assert d1.mean() < 0.3 and (d1.max(axis=2) > 2).mean() < 0.01
+
+
+def test_gradient_brushes(ctx):
+    """linear / radial gradient fills (pad, repeat, reflect) through the per-draw entry, mixed with solid fills and
+    clips: PTCL word for word (CmdGrad where the oracle has it), pixels within 2/255 of the oracle, which evaluates gg's
+    ColorAt exactly (the device samples a 256-entry ramp)."""
+    w, h = 400, 300
+    rng = np.random.default_rng(8)
+    ctx.begin(w, h)
+    ctx.set_background((0, 0, 0, 0))
+    ctx.set_band(0, (h + 15) // 16)
+    n_grad = 0
+    for i in range(60):
+        v, c = U.circle_path(np.float32(rng.uniform(0, w)), np.float32(rng.uniform(0, h)), np.float32(rng.uniform(10, 90)))
+        if i % 7 == 3:
+            ctx.push_clip(v, c)
+            continue
+        if i % 7 == 6:
+            ctx.pop()
+        if i % 2:
+            stops = [(float(o), *rng.uniform(0, 1, 3), float(rng.uniform(0.3, 1.0))) for o in sorted(rng.uniform(0, 1, int(rng.integers(2, 5))))]
+            if i % 4 == 1:
+                ctx.fill_path_gradient(v, c, 0, tuple(rng.uniform(0, w, 4)), stops, extend=i % 3, fill_rule=0)
+            else:
+                ctx.fill_path_gradient(v, c, 1, (float(rng.uniform(0, w)), float(rng.uniform(0, h)), 0.0, float(rng.uniform(20, 150))), stops, extend=i % 3)
+            n_grad += 1
+        else:
+            ctx.fill_path(v, c, tuple(int(x) for x in rng.integers(0, 256, 4)), 0)
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    ctx.flush(out, flags=G.KEEP_SCENE)
+    oc = U.oracle_from_ctx(ctx, w, h)
+    rep = U.compare_stages_fast(ctx, oc, w, h)
+    assert n_grad > 20 and (oc.ptcl_words == 6).sum() > 0 and rep["ptcl_words"] > 0
+    words = ctx.debug_read(G.BUF_SCENE, np.uint32)
+    lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+    from oracle import twin as T
+    ref, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 4)
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert d.max() <= 2 and (d.max(axis=2) > 1).mean() < 0.002, (d.max(), (d.max(axis=2) > 1).mean())
