@@ -9,6 +9,10 @@
 
 #include <algorithm>
 #include <chrono>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "../../include/ggcuda.h"
@@ -139,14 +143,11 @@ void HostScene::add_verbs(const uint8_t* verbs, uint32_t n_verbs, const double* 
 // Fill path straight from verb bytes + float coordinates: the hot loop of scene ingest. Tags and coordinates are
 // written through raw pointers into space reserved for the worst case (every MoveTo / Close / the path end may add a
 // closing LineTo); the rules are those of move_to / line_to / close / end_path above.
-void HostScene::fill_verbs(const float t[6], bool even_odd, const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords,
-                           const uint8_t* verb_map) {
-    begin_path(t, even_odd);
-    const size_t t0 = tags.size(), d0 = path_data.size();
-    tags.resize(t0 + 2 * n_verbs + 3);
-    path_data.resize(d0 + n_coords + 2 * (n_verbs + 2));
-    uint8_t* tp = tags.data() + t0;
-    float* dp = path_data.data() + d0;
+// Geometry of a fill path: tags and coordinates written through raw pointers into space the caller reserved for the worst
+// case (2 * n_verbs + 3 tags, n_coords + 2 * (n_verbs + 2) floats). A pure function of its inputs: the ingest threads run it
+// side by side. Returns the number of segment tags.
+static uint32_t build_fill_geometry(const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const uint8_t* verb_map,
+                                    uint8_t*& tp, float*& dp) {
     bool have = false;
     float sx = 0, sy = 0, cx = 0, cy = 0;
     uint32_t nseg = 0;
@@ -180,6 +181,20 @@ void HostScene::fill_verbs(const float t[6], bool even_odd, const uint8_t* verbs
     }
     GG_CLOSE_SUBPATH();
 #undef GG_CLOSE_SUBPATH
+    return nseg;
+}
+static inline size_t fill_tag_bound(size_t n_verbs) { return 2 * n_verbs + 3; }
+static inline size_t fill_data_bound(size_t n_verbs, size_t n_coords) { return n_coords + 2 * (n_verbs + 2); }
+
+void HostScene::fill_verbs(const float t[6], bool even_odd, const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords,
+                           const uint8_t* verb_map) {
+    begin_path(t, even_odd);
+    const size_t t0 = tags.size(), d0 = path_data.size();
+    tags.resize(t0 + fill_tag_bound(n_verbs));
+    path_data.resize(d0 + fill_data_bound(n_verbs, n_coords));
+    uint8_t* tp = tags.data() + t0;
+    float* dp = path_data.data() + d0;
+    uint32_t nseg = build_fill_geometry(verbs, n_verbs, c, n_coords, verb_map, tp, dp);
     *tp++ = PT_PATH;
     tags.resize((size_t)(tp - tags.data()));
     path_data.resize((size_t)(dp - path_data.data()));
@@ -192,20 +207,10 @@ void HostScene::fill_verbs(const float t[6], bool even_odd, const uint8_t* verbs
 // all coincide are dropped, so every segment has a tangent), then a marker: a copy of the first segment flagged
 // PT_MARKER -- the last segment reads the tangent of its join from it when the subpath is closed; for an open
 // subpath a PT_MARKER_MOVE back to the first point precedes it and the marker segment draws the start cap.
-void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const StrokeStyleHost& st,
-                            const uint8_t* verb_map) {
-    begin_path(t, false);
-    float w = (float)st.width, ml = (float)st.miter_limit;
-    if (!(w > 0.0f)) { end_path(); return; }
-    uint32_t fl = STYLE_STROKE | ((uint32_t)(st.join & 3) << 2) | ((uint32_t)(st.cap & 3) << 4);
-    uint32_t wb, mb; memcpy(&wb, &w, 4); memcpy(&mb, &ml, 4);
-    styles[styles.size() - 3] = fl; styles[styles.size() - 2] = wb; styles[styles.size() - 1] = mb;
-    // worst case per verb: its own tag + (at a subpath end) closing line, marker MoveTo and marker copy
-    const size_t t0 = tags.size(), d0 = path_data.size();
-    tags.resize(t0 + 4 * n_verbs + 8);
-    path_data.resize(d0 + n_coords + 12 * (n_verbs + 2));
-    uint8_t* tp = tags.data() + t0;
-    float* dp = path_data.data() + d0;
+// Geometry of a stroke's centre line (see above); same contract as build_fill_geometry, bounds 4 * n_verbs + 8 tags and
+// n_coords + 12 * (n_verbs + 2) floats.
+static uint32_t build_stroke_geometry(const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const StrokeStyleHost& st,
+                                      const uint8_t* verb_map, uint8_t*& tp, float*& dp) {
     bool have = false, implicit = false;   // implicit: current point left behind by a Close, not set by a MoveTo
     float sx = 0, sy = 0, cx = 0, cy = 0;
     uint8_t* sub_t = nullptr; float* sub_d = nullptr;   // where the open subpath's MoveTo was written
@@ -261,6 +266,25 @@ void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_ver
         }
     }
     flush(false);
+    return nseg;
+}
+static inline size_t stroke_tag_bound(size_t n_verbs) { return 4 * n_verbs + 8; }
+static inline size_t stroke_data_bound(size_t n_verbs, size_t n_coords) { return n_coords + 12 * (n_verbs + 2); }
+static inline uint32_t stroke_style_flags(const StrokeStyleHost& st) { return STYLE_STROKE | ((uint32_t)(st.join & 3) << 2) | ((uint32_t)(st.cap & 3) << 4); }
+
+void HostScene::stroke_path(const float t[6], const uint8_t* verbs, size_t n_verbs, const float* c, size_t n_coords, const StrokeStyleHost& st,
+                            const uint8_t* verb_map) {
+    begin_path(t, false);
+    float w = (float)st.width, ml = (float)st.miter_limit;
+    if (!(w > 0.0f)) { end_path(); return; }
+    uint32_t wb, mb; memcpy(&wb, &w, 4); memcpy(&mb, &ml, 4);
+    styles[styles.size() - 3] = stroke_style_flags(st); styles[styles.size() - 2] = wb; styles[styles.size() - 1] = mb;
+    const size_t t0 = tags.size(), d0 = path_data.size();
+    tags.resize(t0 + stroke_tag_bound(n_verbs));
+    path_data.resize(d0 + stroke_data_bound(n_verbs, n_coords));
+    uint8_t* tp = tags.data() + t0;
+    float* dp = path_data.data() + d0;
+    uint32_t nseg = build_stroke_geometry(verbs, n_verbs, c, n_coords, st, verb_map, tp, dp);
     tags.resize((size_t)(tp - tags.data()));
     path_data.resize((size_t)(dp - path_data.data()));
     n_seg_tags += nseg;
@@ -501,6 +525,81 @@ static uint32_t brush_color(const double* brushes, size_t n_brushes, uint32_t ix
     return gg_pack_color_straight(c);
 }
 
+// ---- two-pass ingest: path geometry on a small persistent thread pool
+// A scene.Encoding is consumed in three steps: (A) one light walk over the tags finds every Fill / Stroke with the slices of
+// the tag and coordinate streams its path occupies and the transform in force; (B) the pool builds the packed geometry of
+// those paths side by side into per-chunk arenas (a pure function per path: band culling, verb translation, auto-close,
+// stroke markers); (C) the ordinary sequential walk does the order-dependent bookkeeping -- transforms, styles, draw
+// objects, layers, clips -- and copies each finished slice in place. The packed scene is byte for byte what the
+// one-thread walk produces. Round 1: 0.73 ms for the 96 k-tag benchmark encoding on one thread, 24 % of the end-to-end frame.
+namespace {
+class IngestPool {
+public:
+    static IngestPool& get() { static IngestPool p; return p; }
+    unsigned workers() const { return (unsigned)th_.size() + 1; }
+    // fn(chunk) for chunk in [0, n): the caller works too; returns when all chunks are done
+    void run(unsigned n, const std::function<void(unsigned)>& fn) {
+        if (n == 0) return;
+        if (th_.empty() || n == 1) { for (unsigned c = 0; c < n; c++) fn(c); return; }
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn; n_ = n; next_.store(0); done_ = 0; gen_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        cv_done_.wait(lk, [&] { return done_ == n_; });
+        fn_ = nullptr;
+    }
+private:
+    IngestPool() {
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned want = std::min(hw, 8u);
+        if (const char* e = getenv("GGCUDA_INGEST_THREADS")) want = (unsigned)std::max(1, atoi(e));
+        for (unsigned i = 1; i < want; i++) th_.emplace_back([this] { loop(); });
+    }
+    ~IngestPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; gen_++; }
+        cv_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    void work() {
+        for (;;) {
+            unsigned c = next_.fetch_add(1);
+            if (c >= n_) break;
+            (*fn_)(c);
+            std::lock_guard<std::mutex> lk(m_);
+            if (++done_ == n_) cv_done_.notify_all();
+        }
+    }
+    void loop() {
+        unsigned seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+            }
+            work();
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(unsigned)>* fn_ = nullptr;
+    unsigned n_ = 0, done_ = 0, gen_ = 0;
+    std::atomic<unsigned> next_{0};
+    bool stop_ = false;
+};
+struct IngestJob {
+    const uint8_t* tg; const float* pd; uint32_t nt, npd;
+    float t[6]; StrokeStyleHost st; float reach; bool stroke;
+    uint32_t chunk, t_off, n_t, d_off, n_d, nseg; bool culled;   // results
+};
+struct IngestArena { std::vector<uint8_t> tags; std::vector<float> data; };
+}  // namespace
+
 int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, size_t n_pd, const uint32_t* dd, size_t n_dd,
                             const float* tr, size_t n_tr, const double* brushes, size_t n_brushes, std::string* msg) {
     // Strokes are expanded on the host (the reference's stroke expander is host code too).
@@ -565,6 +664,86 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
         }
     }
     size_t next_job = 0;
+    static const struct VerbMap { uint8_t m[256]; VerbMap() { memset(m, 0xff, sizeof m); m[ST_MOVE_TO] = GGCUDA_VERB_MOVE; m[ST_LINE_TO] = GGCUDA_VERB_LINE;
+                                  m[ST_QUAD_TO] = GGCUDA_VERB_QUAD; m[ST_CUBIC_TO] = GGCUDA_VERB_CUBIC; m[ST_CLOSE_PATH] = GGCUDA_VERB_CLOSE; } } verb_map;
+    // ---- (A) find the paths of Fill / Stroke tags, (B) build their geometry on the pool
+    std::vector<IngestJob> mt_jobs;
+    std::vector<IngestArena> arenas;
+    size_t next_mt = 0;
+    const bool mt = !host_strokes && n_tags >= 16384 && IngestPool::get().workers() > 1;
+    if (mt) {
+        size_t pi = 0, di = 0, ti = 0, pt0 = 0, pt1 = 0, pp0 = 0;
+        float t[6]; memcpy(t, IDENTITY, sizeof t);
+        bool active = false, ok = true;
+        mt_jobs.reserve(n_tags / 8 + 16);
+        for (size_t i = 0; i < n_tags && ok; i++) {
+            switch (tg[i]) {
+            case ST_TRANSFORM: if (ti + 1 > n_tr) ok = false; else { memcpy(t, tr + 6 * ti, sizeof t); ti++; } break;
+            case ST_SET_AA: di += 1; break;
+            case ST_BEGIN_PATH: pt0 = pt1 = i + 1; pp0 = pi; active = true; break;
+            case ST_MOVE_TO: case ST_LINE_TO: if (pi + 2 > n_pd) ok = false; else { pi += 2; if (active) pt1 = i + 1; } break;
+            case ST_QUAD_TO: if (pi + 4 > n_pd) ok = false; else { pi += 4; if (active) pt1 = i + 1; } break;
+            case ST_CUBIC_TO: if (pi + 6 > n_pd) ok = false; else { pi += 6; if (active) pt1 = i + 1; } break;
+            case ST_CLOSE_PATH: if (active) pt1 = i + 1; break;
+            case ST_END_PATH: break;
+            case ST_FILL: case ST_STROKE: {
+                const bool stroke = tg[i] == ST_STROKE;
+                if (di + (stroke ? 5 : 2) > n_dd) { ok = false; break; }
+                if (active && pt1 > pt0) {
+                    IngestJob j; memset(&j, 0, sizeof j);
+                    j.tg = tg + pt0; j.nt = (uint32_t)(pt1 - pt0); j.pd = pd + pp0; j.npd = (uint32_t)(pi - pp0);
+                    memcpy(j.t, t, sizeof t); j.stroke = stroke;
+                    if (stroke) {
+                        float w, ml; memcpy(&w, dd + di + 1, 4); memcpy(&ml, dd + di + 2, 4);
+                        j.st = {(double)w, (double)ml, (int)dd[di + 3], (int)dd[di + 4]};
+                        j.reach = 0.5f * (w > 0 ? w : 0) * ((dd[di + 4] == 0 && ml > 1.5f) ? ml : 1.5f);
+                    }
+                    mt_jobs.push_back(j);
+                }
+                di += stroke ? 5 : 2; active = false;
+            } break;
+            case ST_FILL_ROUND_RECT: if (di + 2 > n_dd || pi + 6 > n_pd) ok = false; else { di += 2; pi += 6; } break;
+            case ST_PUSH_LAYER: if (di + 2 > n_dd) ok = false; else di += 2; break;
+            case ST_POP_LAYER: case ST_END_CLIP: break;
+            case ST_BEGIN_CLIP: active = false; break;
+            case ST_BRUSH: pi += 4; break;
+            default: ok = false; break;   // TagImage / TagText / unknown: the sequential walk reports it
+            }
+        }
+        const unsigned n_chunks = (unsigned)std::min<size_t>(4 * IngestPool::get().workers(), mt_jobs.size() / 64 + 1);
+        arenas.resize(n_chunks);
+        const size_t nj = mt_jobs.size();
+        IngestPool::get().run(n_chunks, [&](unsigned c) {
+            const size_t j0 = nj * c / n_chunks, j1 = nj * (c + 1) / n_chunks;
+            size_t tb = 0, db = 0;
+            for (size_t k = j0; k < j1; k++) {
+                const IngestJob& j = mt_jobs[k];
+                tb += j.stroke ? stroke_tag_bound(j.nt) : fill_tag_bound(j.nt);
+                db += j.stroke ? stroke_data_bound(j.nt, j.npd) : fill_data_bound(j.nt, j.npd);
+            }
+            IngestArena& a = arenas[c];
+            a.tags.resize(tb); a.data.resize(db);
+            uint8_t* tp = a.tags.data(); float* dp = a.data.data();
+            for (size_t k = j0; k < j1; k++) {
+                IngestJob& j = mt_jobs[k];
+                j.chunk = c;
+                j.culled = outside_band(j.t, j.pd, j.npd, j.reach);
+                if (j.culled || (j.stroke && !((float)j.st.width > 0.0f))) { j.n_t = j.n_d = j.nseg = 0; continue; }
+                uint8_t* t0p = tp; float* d0p = dp;
+                j.nseg = j.stroke ? build_stroke_geometry(j.tg, j.nt, j.pd, j.npd, j.st, verb_map.m, tp, dp)
+                                  : build_fill_geometry(j.tg, j.nt, j.pd, j.npd, verb_map.m, tp, dp);
+                j.t_off = (uint32_t)(t0p - a.tags.data()); j.n_t = (uint32_t)(tp - t0p);
+                j.d_off = (uint32_t)(d0p - a.data.data()); j.n_d = (uint32_t)(dp - d0p);
+            }
+        });
+    }
+    // (C) the sequential walk; with `mt` the geometry of Fill / Stroke paths comes finished from mt_jobs, in order
+    auto append_job = [&](const IngestJob& j) {
+        const IngestArena& a = arenas[j.chunk];
+        tags.insert(tags.end(), a.tags.begin() + j.t_off, a.tags.begin() + j.t_off + j.n_t);
+        path_data.insert(path_data.end(), a.data.begin() + j.d_off, a.data.begin() + j.d_off + j.n_d);
+        n_seg_tags += j.nseg;
+    };
     size_t pi = 0, di = 0, ti = 0;
     float cur_t[6]; memcpy(cur_t, IDENTITY, sizeof cur_t);
     // current path: a view into the input streams (tags [pt0, pt1), coordinates from pp0), consumed by the Fill / Stroke /
@@ -573,8 +752,6 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
     bool path_active = false;
     tags.reserve(tags.size() + 2 * n_tags + 64);
     path_data.reserve(path_data.size() + 2 * n_pd + 64);
-    static const struct VerbMap { uint8_t m[256]; VerbMap() { memset(m, 0xff, sizeof m); m[ST_MOVE_TO] = GGCUDA_VERB_MOVE; m[ST_LINE_TO] = GGCUDA_VERB_LINE;
-                                  m[ST_QUAD_TO] = GGCUDA_VERB_QUAD; m[ST_CUBIC_TO] = GGCUDA_VERB_CUBIC; m[ST_CLOSE_PATH] = GGCUDA_VERB_CLOSE; } } verb_map;
     bool pend_layer = false; uint32_t pend_blend = 0; float pend_alpha = 1.0f;
     auto flush_layer = [&]() { if (pend_layer) { pend_layer = false; begin_layer(pend_blend, pend_alpha); } };
     for (size_t i = 0; i < n_tags; i++) {
@@ -601,7 +778,16 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             flush_layer();
             uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
             if (path_active && pt1 > pt0) {
-                if (outside_band(cur_t, pd + pp0, pi - pp0, 0.0f)) n_culled++;
+                if (mt && next_mt < mt_jobs.size()) {
+                    const IngestJob& j = mt_jobs[next_mt++];
+                    if (j.culled) n_culled++;
+                    else {   // fill_verbs with the geometry already built
+                        begin_path(cur_t, style == 1);
+                        append_job(j);
+                        tags.push_back(PT_PATH); n_paths++; in_path = false; has_move = false;
+                        draw_color(brush_color(brushes, n_brushes, bix));
+                    }
+                } else if (outside_band(cur_t, pd + pp0, pi - pp0, 0.0f)) n_culled++;
                 else { fill_verbs(cur_t, style == 1, tg + pt0, pt1 - pt0, pd + pp0, pi - pp0, verb_map.m); draw_color(brush_color(brushes, n_brushes, bix)); }
             }
             path_active = false;
@@ -614,7 +800,22 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             memcpy(&sw, dd + di + 1, 4); memcpy(&sml, dd + di + 2, 4);
             // reach of the outline beyond the centre line: half the width, miter tips up to miter_limit times that
             const float reach = 0.5f * (sw > 0 ? sw : 0) * ((dd[di + 4] == 0 && sml > 1.5f) ? sml : 1.5f);
-            if (path_active && pt1 > pt0 && outside_band(cur_t, pd + pp0, pi - pp0, reach)) {
+            if (mt && path_active && pt1 > pt0 && next_mt < mt_jobs.size()) {
+                const IngestJob& j = mt_jobs[next_mt++];
+                if (j.culled) n_culled++;
+                else {   // stroke_path with the geometry already built
+                    begin_path(cur_t, false);
+                    if ((float)j.st.width > 0.0f) {
+                        float w = (float)j.st.width, ml = (float)j.st.miter_limit;
+                        uint32_t wb, mb; memcpy(&wb, &w, 4); memcpy(&mb, &ml, 4);
+                        styles[styles.size() - 3] = stroke_style_flags(j.st); styles[styles.size() - 2] = wb; styles[styles.size() - 1] = mb;
+                        append_job(j);
+                        has_move = false;
+                    }
+                    end_path();
+                    draw_color(brush_color(brushes, n_brushes, bix));
+                }
+            } else if (path_active && pt1 > pt0 && outside_band(cur_t, pd + pp0, pi - pp0, reach)) {
                 n_culled++;
                 if (host_strokes && next_job < jobs.size()) next_job++;
             } else if (path_active && pt1 > pt0) {
