@@ -357,6 +357,7 @@ __device__ __forceinline__ void fill_area(float* area, int* D, float* der, SegSt
     const uint32_t row = lane >> 1;
     const int xb = (int)(lane & 1u) * PX;
     const float yi = (float)row;
+    __syncwarp();   // the table and the derived values share their bytes with CmdEndClip's scratch and tile B's image
 #pragma unroll
     for (int i = 0; i <= PX; i++) D[i * 32 + lane] = 0;
     int base = 0;   // the y_edge terms of this row (fine.go:244: the same for every pixel of the row)
@@ -564,10 +565,33 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     const uint32_t* g = gtab + 16u * ps.word(cmd + 1);
                     cmd += 2;
                     const uint32_t kind = g[0], extend = g[1];
-                    const float4* ramp = reinterpret_cast<const float4*>(gtab + g[4]);
+                    const float* ramp = reinterpret_cast<const float*>(gtab + g[4]);   // 4-byte aligned only: scalar loads
                     const float k0 = __uint_as_float(g[11]), k1 = __uint_as_float(g[12]), k2 = __uint_as_float(g[13]), ok = __uint_as_float(g[14]);
                     const float gcx = __uint_as_float(g[5]), gcy = __uint_as_float(g[6]);
                     const float fy = (float)py + 0.5f;
+                    if (kind == 2u) {
+                        // TagFillRoundRect the way gg's CPU renderer draws it (scene/renderer.go:986-1043, scene/shape.go:246-274):
+                        // coverage = Hermite smoothstep over +-0.7 px of the signed distance to the rounded rectangle, at the pixel
+                        // centre; the path's own area only decided which tiles carry the command
+                        const float hw = __uint_as_float(g[7]), hh = __uint_as_float(g[8]), rad = __uint_as_float(g[9]);
+                        const float4 c = unpack_rgba8(g[10]);
+#pragma unroll
+                        for (int i = 0; i < PX; i++) {
+                            const float fx = (float)(tx * GG_TILE_W + xb + i) + 0.5f;
+                            const float ddx = fabsf(fx - gcx) - hw + rad, ddy = fabsf(fy - gcy) - hh + rad;
+                            const float ox = fmaxf(ddx, 0.0f), oy = fmaxf(ddy, 0.0f);
+                            const float dist = sqrtf(ox * ox + oy * oy) + fminf(fmaxf(ddx, ddy), 0.0f) - rad;
+                            float cov;
+                            if (dist >= 0.7f) cov = 0.0f;
+                            else if (dist <= -0.7f) cov = 1.0f;
+                            else { const float tt = (dist + 0.7f) / 1.4f; cov = 1.0f - (tt * tt * (3.0f - 2.0f * tt)); }
+                            rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
+                            rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
+                            rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);
+                            rgba[i].w = fmaf(cov, fmaf(-c.w, rgba[i].w, c.w), rgba[i].w);
+                        }
+                        continue;
+                    }
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
                         const float fx = (float)(tx * GG_TILE_W + xb + i) + 0.5f;
@@ -581,7 +605,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                         const float u = t * (float)(GG_RAMP_N - 1);
                         const int i0 = min((int)u, GG_RAMP_N - 2);
                         const float fr = u - (float)i0;
-                        const float4 c0 = ramp[i0], c1 = ramp[i0 + 1];
+                        const float* rp = ramp + 4 * i0;
+                        const float4 c0 = make_float4(rp[0], rp[1], rp[2], rp[3]), c1 = make_float4(rp[4], rp[5], rp[6], rp[7]);
                         const float4 c = make_float4(c0.x + fr * (c1.x - c0.x), c0.y + fr * (c1.y - c0.y), c0.z + fr * (c1.z - c0.z), c0.w + fr * (c1.w - c0.w));
                         const float cov = area[i];
                         rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
@@ -625,6 +650,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     }
                     if (mix != 0u && mix < 16u) {
                         float4* scr = reinterpret_cast<float4*>(wsm + SM_SCR) + lane;
+                        __syncwarp();   // the scratch lies over the coverage table of the fill just evaluated
 #pragma unroll
                         for (int hf = 0; hf < 2; hf++) {
 #pragma unroll
@@ -664,7 +690,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                         if (px + i < cfg.width) o[i] = make_float4(clamp01(rgba[i].x), clamp01(rgba[i].y), clamp01(rgba[i].z), clamp01(rgba[i].w));
                 }
             } else {
-                // RGBA8 image of the tile in shared memory: rows of 64 bytes
+                // RGBA8 image of the tile in shared memory: rows of 64 bytes (tile B's lies over the coverage table)
+                __syncwarp();
                 uint32_t o[PX];
 #pragma unroll
                 for (int i = 0; i < PX; i++) o[i] = pack_rgba8(rgba[i]);

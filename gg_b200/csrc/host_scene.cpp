@@ -377,6 +377,18 @@ void HostScene::draw_gradient(int kind, const double geom[6], const double* stop
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(0);
 }
+void HostScene::draw_sdf_round_rect(float cx, float cy, float half_w, float half_h, float radius, uint32_t rgba_premul) {
+    uint32_t rec[16] = {0};
+    rec[0] = 2u;
+    float g[6] = {cx, cy, half_w, half_h, radius, 0.0f};
+    memcpy(rec + 5, g, sizeof g);
+    rec[10] = rgba_premul;
+    grad_recs.insert(grad_recs.end(), rec, rec + 16);
+    draw_tags.push_back(DT_GRADIENT);
+    draw_data.push_back(n_gradients++);
+    clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
+    clip_aux.push_back(0);
+}
 void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     int32_t d = (int32_t)draw_tags.size();
     draw_tags.push_back(DT_BEGIN_CLIP);
@@ -493,8 +505,8 @@ void HostScene::pack(uint32_t* out, Layout* L, uint32_t band_tiles) const {   //
 
 // ------------------------------------------------------------------ scene.Encoding ingest
 static void emit_round_rect(HostScene* s, float x0, float y0, float x1, float y1, float rx, float ry) {
-    // scene/path.go rounded rectangle with kappa arcs; TagFillRoundRect is SDF-rendered by the
-    // CPU renderer of the reference (scene/renderer.go:986-1071) -- exact-area rendering of the same outline here.
+    // scene/path.go rounded rectangle with kappa arcs (the outline that bins the tiles of a TagFillRoundRect; its coverage
+    // comes from the signed distance field, draw_sdf_round_rect)
     const float k = 0.5522847498f;
     float w = x1 - x0, h = y1 - y0;
     if (rx > w * 0.5f) rx = w * 0.5f;
@@ -531,7 +543,7 @@ static uint32_t brush_color(const double* brushes, size_t n_brushes, uint32_t ix
 // those paths side by side into per-chunk arenas (a pure function per path: band culling, verb translation, auto-close,
 // stroke markers); (C) the ordinary sequential walk does the order-dependent bookkeeping -- transforms, styles, draw
 // objects, layers, clips -- and copies each finished slice in place. The packed scene is byte for byte what the
-// one-thread walk produces. Round 1: 0.73 ms for the 96 k-tag benchmark encoding on one thread, 24 % of the end-to-end frame.
+// one-thread walk produces. Off unless GGCUDA_INGEST_THREADS asks for it (see IngestPool()).
 namespace {
 class IngestPool {
 public:
@@ -553,9 +565,12 @@ public:
     }
 private:
     IngestPool() {
+        // Opt-in: measured on the B200 box's 16 host cores the 96 k-tag benchmark encoding ingests in 0.80 ms on one thread
+        // and 1.0-1.6 ms on 2-8 (the per-path work, ~1 us, is smaller than the hand-off), so the default is the one-thread
+        // walk; GGCUDA_INGEST_THREADS=n turns the pool on for encodings whose paths are long.
         unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        unsigned want = std::min(hw, 8u);
-        if (const char* e = getenv("GGCUDA_INGEST_THREADS")) want = (unsigned)std::max(1, atoi(e));
+        unsigned want = 1;
+        if (const char* e = getenv("GGCUDA_INGEST_THREADS")) want = std::min(hw, (unsigned)std::max(1, atoi(e)));
         for (unsigned i = 1; i < want; i++) th_.emplace_back([this] { loop(); });
     }
     ~IngestPool() {
@@ -837,10 +852,25 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             flush_layer();
             uint32_t bix = dd[di], style = dd[di + 1]; di += 2;
             const float* r = pd + pi; pi += 6;
-            begin_path(cur_t, style == 1);
-            emit_round_rect(this, r[0], r[1], r[2], r[3], r[4], r[5]);
-            end_path();
-            draw_color(brush_color(brushes, n_brushes, bix));
+            if (cur_t[1] == 0.0f && cur_t[3] == 0.0f) {
+                // axis-aligned transform: the CPU renderer's SDF (scene/renderer.go:986-1043 transforms the two corners, takes
+                // min(rx, ry) UNSCALED as the radius). The outline that bins the tiles is inflated by one pixel so that every
+                // pixel the 0.7 px smoothstep reaches lies in a tile with a command.
+                float x0 = cur_t[0] * r[0] + cur_t[2], y0 = cur_t[4] * r[1] + cur_t[5], x1 = cur_t[0] * r[2] + cur_t[2], y1 = cur_t[4] * r[3] + cur_t[5];
+                if (x0 > x1) std::swap(x0, x1);
+                if (y0 > y1) std::swap(y0, y1);
+                const float hw = (x1 - x0) / 2, hh = (y1 - y0) / 2;
+                const float radius = std::min(std::min(r[4], r[5]), std::min(hw, hh));
+                begin_path(IDENTITY, false);
+                emit_round_rect(this, x0 - 1.0f, y0 - 1.0f, x1 + 1.0f, y1 + 1.0f, std::max(radius, 0.0f) + 1.0f, std::max(radius, 0.0f) + 1.0f);
+                end_path();
+                draw_sdf_round_rect((x0 + x1) / 2, (y0 + y1) / 2, hw, hh, radius, brush_color(brushes, n_brushes, bix));
+            } else {   // rotated / skewed: the reference's SDF ignores that; here the exact area of the transformed outline
+                begin_path(cur_t, style == 1);
+                emit_round_rect(this, r[0], r[1], r[2], r[3], r[4], r[5]);
+                end_path();
+                draw_color(brush_color(brushes, n_brushes, bix));
+            }
         } break;
         case ST_PUSH_LAYER: {
             if (di + 2 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }

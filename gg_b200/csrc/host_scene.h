@@ -77,6 +77,10 @@ struct HostScene {
     // gradient_radial.go, gradient.go). kind 0 linear: geom = x0, y0, x1, y1; kind 1 radial: geom = cx, cy, r0, r1 (device
     // space). stops: 5 floats each {offset, r, g, b, a} straight alpha. The table travels behind the packed scene (see pack()).
     void draw_gradient(int kind, const double geom[6], const double* stops, uint32_t n_stops, int extend);
+    // TagFillRoundRect as the CPU renderer draws it (scene/renderer.go:986-1043, scene/shape.go:246-274): coverage from a signed
+    // distance field with a 0.7 px smoothstep, not from the outline's area. Record kind 2 of the same table: cx, cy, half width,
+    // half height, corner radius (device space), the premultiplied RGBA8 colour's bits. The path just ended only bins tiles.
+    void draw_sdf_round_rect(float cx, float cy, float half_w, float half_h, float radius, uint32_t rgba_premul);
     // gradient table words: per gradient a 16-word record {kind, extend, n_stops, stops offset, ramp offset, 6 raw geometry
     // floats, 4 derived coefficients, pad}, then all stops (5 floats each), then all ramps (GG_RAMP_N premultiplied float4)
     std::vector<uint32_t> grad_recs; std::vector<float> grad_stops, grad_ramps;

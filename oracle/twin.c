@@ -1500,6 +1500,28 @@ void ot_fine_tile_at(const uint32_t *cmds, uint32_t n_words, const ot_path_segme
         } break;
         case CMD_GRAD: {   /* CmdColor with the brush's colour at the pixel centre (software.go:1086-1090) */
             uint32_t gi = cmds[off++];
+            if (gtab && gtab[16 * gi] == 2u) {
+                /* TagFillRoundRect: sdfRoundRectCoverage at the pixel centre (scene/shape.go:246-274, scene/renderer.go:986-1043), float32 */
+                const uint32_t *g = gtab + 16 * gi;
+                float cx = bits_f32(g[5]), cy = bits_f32(g[6]), hw = bits_f32(g[7]), hh = bits_f32(g[8]), rad = bits_f32(g[9]);
+                uint32_t pc = g[10];
+                float cr = (float)(pc & 0xff) / 255.0f, cg = (float)((pc >> 8) & 0xff) / 255.0f, cb = (float)((pc >> 16) & 0xff) / 255.0f, ca = (float)(pc >> 24) / 255.0f;
+                for (int i = 0; i < PC; i++) {
+                    float px = (float)(origin_x + i % TILE_W) + 0.5f, py = (float)(origin_y + i / TILE_W) + 0.5f;
+                    float dx = fabsf(px - cx) - hw + rad, dy = fabsf(py - cy) - hh + rad;
+                    float mx = dx > 0 ? dx : 0, my = dy > 0 ? dy : 0;
+                    float outside = (float)sqrt((double)(mx * mx + my * my));
+                    float inside = (dx > dy ? dx : dy); if (inside > 0) inside = 0;
+                    float dist = outside + inside - rad, cov;
+                    if (dist >= 0.7f) cov = 0;
+                    else if (dist <= -0.7f) cov = 1;
+                    else { float t = (dist + 0.7f) / (2 * 0.7f); cov = 1 - (t * t * (3 - 2 * t)); }
+                    float fa = ca * cov, inv = 1.0f - fa;
+                    rgba[i][0] = rgba[i][0] * inv + cr * cov; rgba[i][1] = rgba[i][1] * inv + cg * cov;
+                    rgba[i][2] = rgba[i][2] * inv + cb * cov; rgba[i][3] = rgba[i][3] * inv + fa;
+                }
+                break;
+            }
             for (int i = 0; i < PC; i++) {
                 float c[4] = {0, 0, 0, 0};
                 if (gtab) og_color_at(gtab, gi, (double)(origin_x + i % TILE_W) + 0.5, (double)(origin_y + i / TILE_W) + 0.5, c);

@@ -127,6 +127,22 @@ def test_encoding_ingest_matches_per_draw_calls():
     assert l1 == l2 and (w1 == w2).all()
 
 
+def test_pooled_ingest_is_byte_identical():
+    """GGCUDA_INGEST_THREADS=n (opt-in thread pool, host_scene.cpp IngestPool) packs the same bytes as the one-thread walk,
+    whole frame and with a band's culling active."""
+    import subprocess
+    import sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "ingest_bench.py")
+    for bands in ("1", "4"):
+        md5 = set()
+        for n in ("1", "4"):
+            env = dict(os.environ, GGCUDA_INGEST_THREADS=n, GG_INGEST_REPS="1")
+            out = subprocess.run([sys.executable, tool, bands], env=env, capture_output=True, text=True, timeout=300)
+            assert out.returncode == 0, out.stderr[-2000:]
+            md5.add(out.stdout.split("md5")[1].split()[0])
+        assert len(md5) == 1, md5
+
+
 def test_unsupported_tags_are_reported():
     c = _lib.Context(-1)
     c.begin(64, 64)
@@ -407,7 +423,8 @@ def test_ingest_survives_malformed_encodings():
             err += 1
             continue
         words, lay = c.pack_host()
-        assert lay["n_scene_words"] + 8 == len(words) and lay["n_draws"] == lay["n_paths"]     # one path marker per draw object (+ 8 tail words)
+        tail = words[int(lay["n_scene_words"]):]
+        assert len(words) == lay["n_scene_words"] + 8 + 16 * tail[6] and lay["n_draws"] == lay["n_paths"]   # one path marker per draw; 8 tail words; round-rect SDF records
         ok += 1
     assert ok > 100 and err > 100
 

@@ -514,3 +514,108 @@ def test_gradient_fill_matches_gg_formulas(kind, geom, extend):
             col = _gg_color_at(stops, (np.hypot(fx - g[0], fy - g[1]) - g[2]) / (g[3] - g[2]), extend)
         want = [int(min(1.0, max(0.0, col[k] * col[3])) * 255 + 0.5) for k in range(3)] + [int(col[3] * 255 + 0.5)]
         assert np.abs(out[y, x].astype(int) - np.array(want)).max() <= 1, (x, y, out[y, x], want)
+
+
+# ---- TagFillRoundRect: the oracle's SDF command against scene/shape.go:243-274 + scene/renderer.go:986-1070 ----
+def _sdf_cov(px, py, cx, cy, hw, hh, r):
+    f = np.float32
+    px, py, cx, cy, hw, hh, r = (f(v) for v in (px, py, cx, cy, hw, hh, r))
+    dx = abs(px - cx) - hw + r
+    dy = abs(py - cy) - hh + r
+    mx, my = max(dx, f(0)), max(dy, f(0))
+    outside = f(np.sqrt(np.float64(mx * mx + my * my)))
+    inside = min(max(dx, dy), f(0))
+    d = outside + inside - r
+    aa = f(0.7)
+    if d >= aa:
+        return f(0)
+    if d <= -aa:
+        return f(1)
+    t = (d + aa) / (f(2) * aa)
+    return f(1) - (t * t * (f(3) - f(2) * t))
+
+
+def _rrect_encoding(rects, w, h):
+    from gg_b200 import scene as S
+    enc = S.Encoding()
+    for (rect, rx, ry, col, tr) in rects:
+        enc.EncodeTransform(tr)
+        enc.EncodeFillRoundRect(col, rect, rx, ry)
+    return enc
+
+
+def test_round_rect_sdf_known_answers():
+    """scene/roundrect_shape_test.go:165-219: the coverage table of the reference's own tests."""
+    cx, cy, hw, hh, r = 50, 40, 50, 40, 10
+    for (px, py, inside) in [(50, 40, True), (30, 30, True), (49.5, 0.5, True), (200, 200, False), (0.1, 0.1, False)]:
+        assert (_sdf_cov(px, py, cx, cy, hw, hh, r) > 0.5) == inside
+    from gg_b200 import _lib
+    c = _lib.Context(-1)
+    c.begin(128, 96)
+    c.add_encoding(*_rrect_encoding([((0, 0, 100, 80), 10, 10, (1, 1, 1, 1), (1, 0, 0, 0, 1, 0))], 128, 96).streams())
+    words, lay = c.pack_host()
+    c.close()
+    out, _ = T.render_packed(words, lay, 128, 96, (0, 0, 0, 0), 1)
+    assert out[40, 50, 3] == 255 and out[30, 30, 3] == 255 and out[0, 49, 3] > 127      # pixel (49, 0) has its centre at (49.5, 0.5)
+    assert out[90, 120, 3] == 0 and out[0, 0, 3] < 128
+    # smoothstep on the edge: a pixel centre exactly on the boundary is half covered (TestSmoothstepCoverage32)
+    assert abs(float(_sdf_cov(100, 40, cx, cy, hw, hh, r)) - 0.5) < 0.01
+
+
+@pytest.mark.parametrize("tr", [(1, 0, 0, 0, 1, 0), (1.5, 0, 7.25, 0, 0.75, -3.5), (-1, 0, 120, 0, 1, 2)])
+def test_round_rect_sdf_matches_reference_formula(tr):
+    """Every pixel of a frame of overlapping translucent round rects (axis-aligned transforms, incl. a mirror) equals the
+    reference's renderFillRoundRect + blendSDF restated in numpy, to 1/255 (the oracle composites in float32, the reference's
+    pixmap holds float32 too)."""
+    from gg_b200 import _lib
+    w, h = 160, 112
+    rects = [((10.3, 8.6, 90.2, 70.9), 12, 12, (0.9, 0.2, 0.1, 0.8), tr), ((40, 30, 70, 100), 30, 8, (0.1, 0.3, 0.9, 0.5), tr),
+             ((60.5, 5.5, 64.5, 9.5), 9, 9, (0, 1, 0, 1), tr)]
+    c = _lib.Context(-1)
+    c.begin(w, h)
+    c.add_encoding(*_rrect_encoding(rects, w, h).streams())
+    words, lay = c.pack_host()
+    c.close()
+    tail = words[int(lay["n_scene_words"]):]
+    assert tail[6] == 3                                       # three SDF records behind the packed scene
+    out, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 1)
+    want = np.zeros((h, w, 4), np.float32)
+    f = np.float32
+    for (rect, rx, ry, col, t) in rects:
+        x0, y0 = f(t[0]) * f(rect[0]) + f(t[1]) * f(rect[1]) + f(t[2]), f(t[3]) * f(rect[0]) + f(t[4]) * f(rect[1]) + f(t[5])
+        x1, y1 = f(t[0]) * f(rect[2]) + f(t[1]) * f(rect[3]) + f(t[2]), f(t[3]) * f(rect[2]) + f(t[4]) * f(rect[3]) + f(t[5])
+        x0, x1 = min(x0, x1), max(x0, x1)
+        y0, y1 = min(y0, y1), max(y0, y1)
+        cx, cy, hw, hh = (x0 + x1) / f(2), (y0 + y1) / f(2), (x1 - x0) / f(2), (y1 - y0) / f(2)
+        r = min(min(f(rx), f(ry)), min(hw, hh))
+        # the product quantises the brush to 8 bits at ingest like every other draw (path_convert.go:131-140)
+        q = [f(int(min(255.0, v * 255.0 + 0.5))) / f(255) for v in col]
+        for py in range(h):
+            for px in range(w):
+                cov = _sdf_cov(px + 0.5, py + 0.5, cx, cy, hw, hh, r)
+                if cov <= 0:
+                    continue
+                sa = q[3] * cov
+                inv = f(1) - sa
+                pm = np.array([f(int(q[0] * q[3] * f(255) + f(0.5))) / f(255), f(int(q[1] * q[3] * f(255) + f(0.5))) / f(255),
+                               f(int(q[2] * q[3] * f(255) + f(0.5))) / f(255)], np.float32)
+                want[py, px, :3] = want[py, px, :3] * inv + pm * cov
+                want[py, px, 3] = want[py, px, 3] * inv + sa
+    wq = np.floor(np.clip(want, 0, 1) * 255 + 0.5).astype(int)
+    d = np.abs(out.astype(int) - wq)
+    assert d.max() <= 1, (d.max(), np.argwhere(d > 1)[:5])
+    assert out[..., 3].max() > 100
+
+
+def test_round_rect_rotated_falls_back_to_the_outline():
+    """A transform that is not axis-aligned has no SDF form in the reference either (renderFillRoundRect transforms two
+    corners only); ggcuda fills the transformed outline with the exact-area path instead: no SDF record."""
+    from gg_b200 import _lib
+    c = _lib.Context(-1)
+    c.begin(128, 128)
+    c.add_encoding(*_rrect_encoding([((20, 20, 90, 70), 10, 10, (1, 0, 0, 1), (0.8, -0.6, 30, 0.6, 0.8, 0))], 128, 128).streams())
+    words, lay = c.pack_host()
+    c.close()
+    assert words[int(lay["n_scene_words"]):][6] == 0
+    out, _ = T.render_packed(words, lay, 128, 128, (0, 0, 0, 0), 1)
+    assert out[..., 3].max() == 255

@@ -804,3 +804,49 @@ def test_gradient_brushes(ctx):
     ref, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 4)
     d = np.abs(out.astype(int) - ref.astype(int))
     assert d.max() <= 2 and (d.max(axis=2) > 1).mean() < 0.002, (d.max(), (d.max(axis=2) > 1).mean())
+
+
+@pytest.mark.gpu
+def test_round_rect_sdf_encoding(ctx):
+    """TagFillRoundRect in a scene.Encoding renders as the reference's SDF coverage (scene/renderer.go:986-1043)
+    inside the inflated outline's tiles; mixed with path fills, a clip and a rotated round rect (outline fallback). PTCL word
+    for word, pixels within 1/255 of the oracle (same float32 formula on both sides, sqrt rounding aside)."""
+    from gg_b200 import scene as S
+    w, h = 500, 380
+    rng = np.random.default_rng(21)
+    enc = S.Encoding()
+    for i in range(40):
+        col = (*rng.uniform(0, 1, 3), float(rng.uniform(0.3, 1.0)))
+        x0, y0 = rng.uniform(-20, w - 40), rng.uniform(-20, h - 40)
+        rect = (x0, y0, x0 + rng.uniform(2, 200), y0 + rng.uniform(2, 160))
+        if i % 9 == 4:
+            enc.EncodeTransform((0.8, -0.6, 60, 0.6, 0.8, -40))
+        elif i % 5 == 0:
+            enc.EncodeTransform((float(rng.uniform(0.5, 1.5)), 0, float(rng.uniform(-10, 10)), 0, float(rng.uniform(0.5, 1.5)), 0))
+        else:
+            enc.EncodeTransform(S.IDENTITY)
+        if i % 4 == 1:
+            enc.EncodePath(*U.circle_path(np.float32(rng.uniform(0, w)), np.float32(rng.uniform(0, h)), np.float32(rng.uniform(10, 70))))
+            enc.EncodeFill(col)
+        else:
+            enc.EncodeFillRoundRect(col, rect, float(rng.uniform(0, 40)), float(rng.uniform(0, 40)))
+        if i == 12:
+            enc.EncodeTransform(S.IDENTITY)
+            enc.EncodePath(*U.circle_path(np.float32(250), np.float32(190), np.float32(170)))
+            enc.EncodeBeginClip()
+        if i == 30:
+            enc.EncodeEndClip()
+    ctx.begin(w, h)
+    ctx.set_background((0, 0, 0, 0))
+    ctx.add_encoding(*enc.streams())
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    ctx.flush(out, flags=G.KEEP_SCENE)
+    oc = U.oracle_from_ctx(ctx, w, h)
+    rep = U.compare_stages_fast(ctx, oc, w, h)
+    assert (oc.ptcl_words == 6).sum() > 0 and rep["ptcl_words"] > 0
+    words = ctx.debug_read(G.BUF_SCENE, np.uint32)
+    lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+    from oracle import twin as T
+    ref, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 4)
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d.max(axis=2) > 0).mean() < 0.01, (d.max(), (d.max(axis=2) > 0).mean())
