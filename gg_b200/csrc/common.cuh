@@ -113,7 +113,6 @@ struct GGConfig {
     uint32_t sm_count;                      // multiprocessors of the device (queried at context creation): grids are multiples of it
     uint32_t grad_base, n_grads;            // gradient table (word offset in the scene buffer): 16-word records | stops | ramps
 };
-#define GG_RAMP_N 256                       // entries of a gradient's colour ramp (premultiplied float4)
 #define GG_FLAG_BG_FROM_DST 1u              // composite-over: the scene is rasterised on transparent and source-overed onto the
                                             // destination's pixels with the reference's byte formula (vello_accelerator.go:388-442)
 #define GG_FLAG_TARGET_F32 2u               // destination holds premultiplied float4 pixels (16 bytes) instead of RGBA8

@@ -460,6 +460,59 @@ __device__ __forceinline__ uint32_t composite_over_u8(uint32_t s, uint32_t d) {
     return o;
 }
 
+// gg's brush colour at a pixel centre (gradient_linear.go:52-66, gradient_radial.go computeTSimple, gradient.go:42-131), in gg's
+// own arithmetic: float64 geometry and stop search, float32 interpolation in linear light, sRGB on the way out; only the last
+// step differs from the Go code (powf instead of float64 math.Pow: < 1e-6 on a colour in [0, 1]). The stops carry their
+// linear-light values from the host. Out of line: gradients are rare commands and this is a lot of code.
+// Returns the premultiplied colour.
+__device__ __noinline__ float4 grad_color(const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ g, float fx, float fy) {
+    const uint32_t kind = g[0], extend = g[1], n = g[2];
+    const float* st = reinterpret_cast<const float*>(gtab + g[3]);   // 8 floats per stop: offset, r g b a, linear-light r g b
+    if (n == 0u) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    const double g0 = (double)__uint_as_float(g[5]), g1 = (double)__uint_as_float(g[6]);
+    const double g2 = (double)__uint_as_float(g[7]), g3 = (double)__uint_as_float(g[8]);
+    const double x = (double)fx, y = (double)fy;
+    double t = 0.0;
+    bool first_only = n == 1u;
+    if (kind == 0u) {
+        const double dx = g2 - g0, dy = g3 - g1, l2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        if (l2 == 0.0) first_only = true;
+        else t = __ddiv_rn(__dadd_rn(__dmul_rn(x - g0, dx), __dmul_rn(y - g1, dy)), l2);
+    } else {
+        const double dx = x - g0, dy = y - g1, rd = g3 - g2;
+        if (rd == 0.0) first_only = true;
+        else t = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) - g2, rd);
+    }
+    const float* a = nullptr;
+    uint32_t i = 0;
+    if (first_only) a = st;
+    else {
+        if (extend == 1u) { t -= floor(t); if (t < 0.0) t += 1.0; }
+        else if (extend == 2u) { t = fabs(t); const double per = floor(t); t -= per; if (((long long)per) & 1ll) t = 1.0 - t; }
+        else t = t < 0.0 ? 0.0 : (t > 1.0 ? 1.0 : t);
+        while (i < n && !((double)st[8u * i] >= t)) i++;   // sort.Search: first stop with offset >= t
+        if (i == 0u) a = st;
+        else if (i >= n) a = st + 8u * (n - 1u);
+        else if (st[8u * i] == st[8u * (i - 1u)]) a = st + 8u * (i - 1u);
+    }
+    float r, gg, b, al;
+    if (a) { r = a[1]; gg = a[2]; b = a[3]; al = a[4]; }
+    else {
+        const float* s1 = st + 8u * (i - 1u);
+        const float* s2 = st + 8u * i;
+        const float lt = (float)__ddiv_rn(t - (double)s1[0], (double)s2[0] - (double)s1[0]);
+        float c[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const float l = s1[5 + k] + lt * (s2[5 + k] - s1[5 + k]);
+            c[k] = l <= 0.0031308f ? l * 12.92f : 1.055f * powf(l, 1.0f / 2.4f) - 0.055f;
+        }
+        r = c[0]; gg = c[1]; b = c[2];
+        al = s1[4] + lt * (s2[4] - s1[4]);
+    }
+    return make_float4(r * al, gg * al, b * al, al);
+}
+
 __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
@@ -560,19 +613,16 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     }
                 } else if (tag == GG_CMD_GRAD) {
                     // Gradient brush (gg.LinearGradientBrush / RadialGradientBrush.ColorAt at the pixel centre, software.go:1086-1090):
-                    // t from the record's coefficients, extend mode (gradient.go:42-60), colour from the gradient's 256-entry
-                    // premultiplied ramp (built on the host with gg's linear-light interpolation), linear between entries.
+                    // evaluated per pixel by grad_color, gg's own arithmetic.
                     const uint32_t* g = gtab + 16u * ps.word(cmd + 1);
                     cmd += 2;
-                    const uint32_t kind = g[0], extend = g[1];
-                    const float* ramp = reinterpret_cast<const float*>(gtab + g[4]);   // 4-byte aligned only: scalar loads
-                    const float k0 = __uint_as_float(g[11]), k1 = __uint_as_float(g[12]), k2 = __uint_as_float(g[13]), ok = __uint_as_float(g[14]);
-                    const float gcx = __uint_as_float(g[5]), gcy = __uint_as_float(g[6]);
+                    const uint32_t kind = g[0];
                     const float fy = (float)py + 0.5f;
                     if (kind == 2u) {
                         // TagFillRoundRect the way gg's CPU renderer draws it (scene/renderer.go:986-1043, scene/shape.go:246-274):
                         // coverage = Hermite smoothstep over +-0.7 px of the signed distance to the rounded rectangle, at the pixel
                         // centre; the path's own area only decided which tiles carry the command
+                        const float gcx = __uint_as_float(g[5]), gcy = __uint_as_float(g[6]);
                         const float hw = __uint_as_float(g[7]), hh = __uint_as_float(g[8]), rad = __uint_as_float(g[9]);
                         const float4 c = unpack_rgba8(g[10]);
 #pragma unroll
@@ -594,20 +644,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     }
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
-                        const float fx = (float)(tx * GG_TILE_W + xb + i) + 0.5f;
-                        float t;
-                        if (kind == 0u) t = fx * k0 + fy * k1 + k2;
-                        else { const float ddx = fx - gcx, ddy = fy - gcy; t = sqrtf(ddx * ddx + ddy * ddy) * k0 + k1; }
-                        if (extend == 1u) { t -= floorf(t); }
-                        else if (extend == 2u) { t = fabsf(t); const float per = floorf(t); t -= per; if (((int)per) & 1) t = 1.0f - t; }
-                        else t = clamp01(t);
-                        if (ok == 0.0f) t = 0.0f;   // degenerate geometry: the first stop everywhere
-                        const float u = t * (float)(GG_RAMP_N - 1);
-                        const int i0 = min((int)u, GG_RAMP_N - 2);
-                        const float fr = u - (float)i0;
-                        const float* rp = ramp + 4 * i0;
-                        const float4 c0 = make_float4(rp[0], rp[1], rp[2], rp[3]), c1 = make_float4(rp[4], rp[5], rp[6], rp[7]);
-                        const float4 c = make_float4(c0.x + fr * (c1.x - c0.x), c0.y + fr * (c1.y - c0.y), c0.z + fr * (c1.z - c0.z), c0.w + fr * (c1.w - c0.w));
+                        const float4 c = grad_color(gtab, g, (float)(tx * GG_TILE_W + xb + i) + 0.5f, fy);   // premultiplied
                         const float cov = area[i];
                         rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
                         rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);

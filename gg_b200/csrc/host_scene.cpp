@@ -22,7 +22,6 @@ enum { PT_LINETO = 0x09, PT_QUADTO = 0x0A, PT_CUBICTO = 0x0B, PT_MOVETO = 0x0C, 
 enum { STYLE_STROKE = 0x01, STYLE_EVEN_ODD = 0x02 };
 enum { DT_COLOR = 0x44, DT_BEGIN_CLIP = 0x9, DT_END_CLIP = 0x21,
        DT_GRADIENT = 0x444 };   // DrawTagColor's monoid increments (one scene word, one info word) + bit 10: the word is a gradient index
-#define GG_RAMP_N 256
 
 // scene.Tag values, scene/tag.go:25-110
 enum {
@@ -58,7 +57,7 @@ void HostScene::clear(uint32_t w, uint32_t h) {
     clip_aux.clear(); clip_stack.clear(); clip_kind.clear(); clip_bb.clear();
     next_clip_bb[0] = next_clip_bb[1] = -3.0e38f; next_clip_bb[2] = next_clip_bb[3] = 3.0e38f;
     n_paths = n_clips = n_seg_tags = n_implicit = n_culled = 0;
-    grad_recs.clear(); grad_stops.clear(); grad_ramps.clear(); n_gradients = 0;
+    grad_recs.clear(); grad_stops.clear(); n_gradients = 0;
     have_transform = false; in_path = false; has_move = false;
 }
 
@@ -323,26 +322,9 @@ void HostScene::draw_color(uint32_t rgba_premul) {
     clip_aux.push_back(0);
 }
 // gg's colour stops interpolate in linear light: sRGB -> linear, lerp, linear -> sRGB, float32 (gradient.go:62-101,
-// internal/color/convert.go:8-23); alpha is linear.
+// internal/color/convert.go:8-23); alpha is linear. The device does the lerp and the way back per pixel (fine.cu grad_color);
+// the linear-light value of every stop is computed here, once.
 static float srgb_to_linear(float s) { return s <= 0.04045f ? s / 12.92f : (float)pow((double)((s + 0.055f) / 1.055f), 2.4); }
-static float linear_to_srgb(float l) { return l <= 0.0031308f ? l * 12.92f : 1.055f * (float)pow((double)l, 1.0 / 2.4) - 0.055f; }
-// colorAtOffset (gradient.go:104-131) on stops already sorted by offset, t in [0, 1]
-static void color_at_offset(const double* stops, uint32_t n, double t, float out[4]) {
-    if (n == 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
-    uint32_t idx = 0;
-    while (idx < n && !(stops[5 * idx] >= t)) idx++;   // sort.Search: first stop with offset >= t
-    const double* a = nullptr;
-    if (n == 1 || idx == 0) a = stops; else if (idx >= n) a = stops + 5 * (n - 1);
-    else if (stops[5 * idx] == stops[5 * (idx - 1)]) a = stops + 5 * (idx - 1);
-    if (a) { for (int k = 0; k < 4; k++) out[k] = (float)a[1 + k]; return; }
-    const double *s1 = stops + 5 * (idx - 1), *s2 = stops + 5 * idx;
-    float lt = (float)((t - s1[0]) / (s2[0] - s1[0]));
-    for (int k = 0; k < 3; k++) {
-        float l1 = srgb_to_linear((float)s1[1 + k]), l2 = srgb_to_linear((float)s2[1 + k]);
-        out[k] = linear_to_srgb(l1 + lt * (l2 - l1));
-    }
-    out[3] = (float)s1[4] + lt * ((float)s2[4] - (float)s1[4]);
-}
 void HostScene::draw_gradient(int kind, const double geom[6], const double* stops_in, uint32_t n_stops, int extend) {
     // sortStops (gradient.go:29-40): by offset (insertion sort: stable; sort.Slice makes no promise for equal offsets)
     std::vector<double> st(stops_in, stops_in + 5 * (size_t)n_stops);
@@ -354,23 +336,14 @@ void HostScene::draw_gradient(int kind, const double geom[6], const double* stop
     }
     uint32_t rec[16] = {0};
     rec[0] = (uint32_t)kind; rec[1] = (uint32_t)extend; rec[2] = n_stops;
-    rec[3] = (uint32_t)grad_stops.size(); rec[4] = (uint32_t)grad_ramps.size();
-    float g[6], d[4] = {0, 0, 0, 0};
+    rec[3] = (uint32_t)grad_stops.size(); rec[4] = 0;
+    float g[6];
     for (int k = 0; k < 6; k++) g[k] = (float)geom[k];
-    if (kind == 0) {   // t = ((x - x0) dx + (y - y0) dy) / |d|^2 = a x + b y + c (gradient_linear.go:52-66)
-        double dx = geom[2] - geom[0], dy = geom[3] - geom[1], l2 = dx * dx + dy * dy;
-        if (l2 > 0) { d[0] = (float)(dx / l2); d[1] = (float)(dy / l2); d[2] = (float)(-(geom[0] * dx + geom[1] * dy) / l2); d[3] = 1.0f; }
-    } else {           // t = (|p - c| - r0) / (r1 - r0) (gradient_radial.go computeTSimple)
-        double rd = geom[3] - geom[2];
-        if (rd != 0) { d[0] = (float)(1.0 / rd); d[1] = (float)(-geom[2] / rd); d[3] = 1.0f; }
-    }
-    memcpy(rec + 5, g, sizeof g); memcpy(rec + 11, d, sizeof d);
+    memcpy(rec + 5, g, sizeof g);
     grad_recs.insert(grad_recs.end(), rec, rec + 16);
-    for (size_t i = 0; i < st.size(); i++) grad_stops.push_back((float)st[i]);
-    for (int i = 0; i < GG_RAMP_N; i++) {   // premultiplied ramp for the device: entry i is the colour at t = i / (N - 1)
-        float c[4];
-        color_at_offset(st.data(), n_stops, d[3] != 0.0f ? (double)i / (GG_RAMP_N - 1) : 0.0, c);   // degenerate geometry: first stop
-        grad_ramps.push_back(c[0] * c[3]); grad_ramps.push_back(c[1] * c[3]); grad_ramps.push_back(c[2] * c[3]); grad_ramps.push_back(c[3]);
+    for (uint32_t i = 0; i < n_stops; i++) {   // 8 floats per stop: offset, straight sRGB r g b, a, linear-light r g b
+        for (int k = 0; k < 5; k++) grad_stops.push_back((float)st[5 * i + k]);
+        for (int k = 0; k < 3; k++) grad_stops.push_back(srgb_to_linear((float)st[5 * i + 1 + k]));
     }
     draw_tags.push_back(DT_GRADIENT);
     draw_data.push_back(n_gradients++);
@@ -491,15 +464,14 @@ void HostScene::pack(uint32_t* out, Layout* L, uint32_t band_tiles) const {   //
     if (!clip_aux.empty()) memcpy(out + L->clip_aux_base, clip_aux.data(), 4 * clip_aux.size());
     uint32_t* tail = out + off;   // device-resident element counts for the scan primitive
     tail[0] = padded; tail[1] = L->n_draws; tail[2] = L->n_tag_bytes; tail[3] = n_paths; tail[4] = band_tiles;
-    // gradient table behind the tail: records | stops | ramps; tail[5] = its word offset, tail[6] = number of gradients
+    // gradient table behind the tail: records | stops; tail[5] = its word offset, tail[6] = number of gradients
     tail[5] = off + 8; tail[6] = n_gradients; tail[7] = 0;
     uint32_t* gt = out + off + 8;
     if (!grad_recs.empty()) {
-        const uint32_t stops_base = (uint32_t)grad_recs.size(), ramps_base = stops_base + (uint32_t)grad_stops.size();
+        const uint32_t stops_base = (uint32_t)grad_recs.size();
         memcpy(gt, grad_recs.data(), 4 * grad_recs.size());
-        for (uint32_t g = 0; g < n_gradients; g++) { gt[16 * g + 3] += stops_base; gt[16 * g + 4] += ramps_base; }   // offsets relative to the table
+        for (uint32_t g = 0; g < n_gradients; g++) gt[16 * g + 3] += stops_base;   // offsets relative to the table
         memcpy(gt + stops_base, grad_stops.data(), 4 * grad_stops.size());
-        memcpy(gt + ramps_base, grad_ramps.data(), 4 * grad_ramps.size());
     }
 }
 

@@ -81,11 +81,11 @@ struct HostScene {
     // distance field with a 0.7 px smoothstep, not from the outline's area. Record kind 2 of the same table: cx, cy, half width,
     // half height, corner radius (device space), the premultiplied RGBA8 colour's bits. The path just ended only bins tiles.
     void draw_sdf_round_rect(float cx, float cy, float half_w, float half_h, float radius, uint32_t rgba_premul);
-    // gradient table words: per gradient a 16-word record {kind, extend, n_stops, stops offset, ramp offset, 6 raw geometry
-    // floats, 4 derived coefficients, pad}, then all stops (5 floats each), then all ramps (GG_RAMP_N premultiplied float4)
-    std::vector<uint32_t> grad_recs; std::vector<float> grad_stops, grad_ramps;
+    // gradient table words: per gradient a 16-word record {kind, extend, n_stops, stops offset, 0, 6 raw geometry floats, pad},
+    // then all stops, sorted per gradient, 8 floats each {offset, r, g, b, a (straight sRGB), linear-light r, g, b}
+    std::vector<uint32_t> grad_recs; std::vector<float> grad_stops;
     uint32_t n_gradients = 0;
-    size_t gradient_words() const { return grad_recs.size() + grad_stops.size() + grad_ramps.size(); }
+    size_t gradient_words() const { return grad_recs.size() + grad_stops.size(); }
     void begin_clip(uint32_t blend_word, float alpha, uint8_t kind);   // DrawTagBeginClip for the path just ended
     void begin_layer(uint32_t blend_word, float alpha);   // PushLayer: clip rectangle carrying blend + alpha
     bool end_clip(uint8_t kind);                           // DrawTagEndClip (+ dummy path); false if nothing to pop

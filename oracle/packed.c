@@ -178,9 +178,8 @@ static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, i
             const uint32_t *gt = scene + tail[5];
             uint32_t words = 16 * ng;
             for (uint32_t g = 0; g < ng; g++) {
-                uint32_t e1 = gt[16 * g + 3] + 5 * gt[16 * g + 2], e2 = gt[16 * g + 4] + 256 * 4;
+                uint32_t e1 = gt[16 * g] == 2u ? 0 : gt[16 * g + 3] + 8 * gt[16 * g + 2];   /* 8 floats per stop; SDF records have none */
                 if (e1 > words) words = e1;
-                if (e2 > words) words = e2;
             }
             c->gtab = (uint32_t *)malloc(4 * (size_t)words);
             memcpy(c->gtab, gt, 4 * (size_t)words);

@@ -1422,7 +1422,7 @@ static float og_linear_to_srgb(float l) { return l <= 0.0031308f ? l * 12.92f : 
 static void og_color_at(const uint32_t *gtab, uint32_t idx, double x, double y, float out[4]) {
     const uint32_t *g = gtab + 16 * idx;
     uint32_t kind = g[0], extend = g[1], n = g[2];
-    const uint32_t *st = gtab + g[3];   /* 5 floats per stop */
+    const uint32_t *st = gtab + g[3];   /* 8 floats per stop: offset, r g b a, (linear-light r g b: the device's, unused here) */
     double t = 0; int first_only = 0;
     double g0 = bits_f32(g[5]), g1 = bits_f32(g[6]), g2 = bits_f32(g[7]), g3 = bits_f32(g[8]);
     if (kind == 0) {
@@ -1438,11 +1438,11 @@ static void og_color_at(const uint32_t *gtab, uint32_t idx, double x, double y, 
     else if (extend == 2) { t = fabs(t); double per = floor(t); t -= per; if (((long long)per) % 2 == 1) t = 1 - t; }
     else t = t < 0 ? 0 : (t > 1 ? 1 : t);
     uint32_t i = 0;
-    while (i < n && !((double)bits_f32(st[5 * i]) >= t)) i++;
+    while (i < n && !((double)bits_f32(st[8 * i]) >= t)) i++;
     const uint32_t *a = NULL;
-    if (i == 0) a = st; else if (i >= n) a = st + 5 * (n - 1); else if (bits_f32(st[5 * i]) == bits_f32(st[5 * (i - 1)])) a = st + 5 * (i - 1);
+    if (i == 0) a = st; else if (i >= n) a = st + 8 * (n - 1); else if (bits_f32(st[8 * i]) == bits_f32(st[8 * (i - 1)])) a = st + 8 * (i - 1);
     if (a) { for (int k = 0; k < 4; k++) out[k] = bits_f32(a[1 + k]); return; }
-    const uint32_t *s1 = st + 5 * (i - 1), *s2 = st + 5 * i;
+    const uint32_t *s1 = st + 8 * (i - 1), *s2 = st + 8 * i;
     float lt = (float)((t - (double)bits_f32(s1[0])) / ((double)bits_f32(s2[0]) - (double)bits_f32(s1[0])));
     for (int k = 0; k < 3; k++) {
         float l1 = og_srgb_to_linear(bits_f32(s1[1 + k])), l2v = og_srgb_to_linear(bits_f32(s2[1 + k]));

@@ -769,8 +769,8 @@ def test_config1_cuda_vs_gg_cpu_path(ctx):
 
 def test_gradient_brushes(ctx):
     """linear / radial gradient fills (pad, repeat, reflect) through the per-draw entry, mixed with solid fills and
-    clips: PTCL word for word (CmdGrad where the oracle has it), pixels within 2/255 of the oracle, which evaluates gg's
-    ColorAt exactly (the device samples a 256-entry ramp)."""
+    clips: PTCL word for word (CmdGrad where the oracle has it), pixels within 1/255 of the oracle, which evaluates gg's
+    ColorAt exactly (the device does the same arithmetic but for powf in the linear -> sRGB step)."""
     w, h = 400, 300
     rng = np.random.default_rng(8)
     ctx.begin(w, h)
@@ -803,7 +803,7 @@ def test_gradient_brushes(ctx):
     from oracle import twin as T
     ref, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 4)
     d = np.abs(out.astype(int) - ref.astype(int))
-    assert d.max() <= 2 and (d.max(axis=2) > 1).mean() < 0.002, (d.max(), (d.max(axis=2) > 1).mean())
+    assert d.max() <= 2 and (d.max(axis=2) > 1).mean() < 1e-4, (d.max(), (d.max(axis=2) > 1).mean(), (d.max(axis=2) > 0).mean())
 
 
 @pytest.mark.gpu
