@@ -102,7 +102,8 @@ __device__ __forceinline__ void set_sat(float& r, float& g, float& b, float s) {
         b = b == hi ? s : ((b - lo) * s) / d;
     }
 }
-__device__ __forceinline__ float sep_mix(uint32_t mix, float s, float d) {
+// out of line: one copy for the three channels (the kernel has to fit the instruction cache, see blend_mix4)
+__device__ __noinline__ float sep_mix(uint32_t mix, float s, float d) {
     switch (mix) {
     case 1: return s * d;
     case 2: return 1.0f - (1.0f - s) * (1.0f - d);
@@ -148,14 +149,14 @@ __device__ __forceinline__ float4 blend_mix_px(uint32_t mix, float4 bg, float4 f
     return o;
 }
 // CmdEndClip of a mix mode for FOUR of the lane's pixels, held in shared memory: scr[i * 32] = the layer's pixel
-// (premultiplied, already scaled by coverage and alpha), replaced by the result; slot[i * step] = the backdrop. One rolled
+// (premultiplied, already scaled by coverage and alpha), replaced by the result; slot[i * 32] = the backdrop. One rolled
 // loop, one copy of the blend code, one call per four pixels -- with the eight pixels in registers the code was unrolled
 // eight times around a per-pixel call whose register saves were 3 % of fine's instructions and the kernel did not fit the
 // instruction cache (ncu r2b: sm__icc hit rate 69 %, 12.7 cycles of no_instruction stall per issue).
-__device__ __noinline__ void blend_mix4(uint32_t mix, float4* scr, const float4* slot, uint32_t step) {
+__device__ __noinline__ void blend_mix4(uint32_t mix, float4* scr, const float4* slot) {
 #pragma unroll 1
     for (int i = 0; i < 4; i++) {
-        const float4 fg = scr[i * 32], bg = slot[i * step];
+        const float4 fg = scr[i * 32], bg = slot[i * 32];
         // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source)
         float4 o = fg;
         if (fg.w <= 0.0f) o = bg;
@@ -189,8 +190,8 @@ __constant__ float4 COMPOSE_COEF[14] = {
 #define SM_STACK 0       // blend stack level 0: float4 [PX][32]                                    4096
 #define SM_PTCL 4096     // command ring: u32 [2][PTCL_CHUNK]                                        1024
 #define SM_SEGS 5120     // segment ring: GGSegment [2][SEG_CHUNK]                                   1280
-#define SM_DER 6400      // per-segment derived values of the chunk being evaluated: float [3][32]   384
-#define SM_D 6784        // per-lane difference table: int [9][32] (then: RGBA8 image of tile B)     1152
+#define SM_DER 6400      // 1/dy of the segments of the chunk being evaluated: float [32] (384 reserved)      384
+#define SM_D 6784        // coverage difference table: int [8][32] (then: RGBA8 image of tile B)     1152
 #define SM_SCR 6400      // CmdEndClip scratch, four pixels per lane: float4 [4][32] (over DER and D) 2048
 #define SM_IMG_A 8448    // RGBA8 image of the pair's left tile: u32 [16][16]                        1024
 #define SM_BARS 9472     // 4 mbarriers                                                              32
@@ -247,38 +248,41 @@ struct PtclStream {
         issue(first_chunk + 1);
         limit = 0;
     }
-    // Called once per command with the index of its first word (the longest command is 4 words). The ring holds
-    // the chunk the command starts in and the next one; the slot of the chunk BEHIND the command start is refilled
-    // with the chunk after next. A command may straddle a chunk boundary, so nothing is refilled on the strength
-    // of its later words. `limit` = first command index at which there is something to do (one compare per command).
+    // Called once per loop iteration with the index of a command's first word; makes that command AND the one after it
+    // readable (a coverage command -- CmdFill, 4 words -- is dispatched together with the command that uses it, at most
+    // 3 words: 7 words). The ring holds the chunk the command starts in and the next one; the slot of the chunk BEHIND the
+    // command start is refilled with the chunk after next. `limit` = first command index at which there is something to do
+    // (one compare per iteration).
     __device__ __forceinline__ void ensure(uint32_t cmd) {
         if (cmd >= limit) ensure_slow(cmd);
     }
     __device__ __forceinline__ void ensure_slow(uint32_t cmd) {
         const uint32_t cur = cmd / PTCL_CHUNK;
         while (issued < cur + 2 && issued * PTCL_CHUNK < len) { __syncwarp(); issue(issued); }
-        while (cmd + 3 >= loaded_end && loaded_end < issued * PTCL_CHUNK) {
+        while (cmd + 7 >= loaded_end && loaded_end < issued * PTCL_CHUNK) {
             uint32_t slot = (loaded_end / PTCL_CHUNK) & 1u;
             mbar_wait(bars + slot, (parity >> slot) & 1u);
             parity ^= 1u << slot;
             loaded_end += PTCL_CHUNK;
         }
         const uint32_t a = issued * PTCL_CHUNK >= len ? 0xffffffffu : (issued - 1u) * PTCL_CHUNK;   // next refill
-        const uint32_t b = loaded_end >= issued * PTCL_CHUNK ? 0xffffffffu : loaded_end - 3u;          // next wait
+        const uint32_t b = loaded_end >= issued * PTCL_CHUNK ? 0xffffffffu : loaded_end - 7u;          // next wait
         limit = min(a, b);
     }
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
     // The next CmdFill at or after word c, looking only at words that have already arrived (a few commands ahead).
+    // Command lengths from a nibble table indexed by the tag (0 = stop: CmdEnd or unknown).
     __device__ __forceinline__ bool next_fill(uint32_t c, uint32_t* seg_ix, uint32_t* n) const {
         const uint32_t avail = min(loaded_end, len);
+        constexpr uint32_t LEN_LO = (1u << (4 * GG_CMD_SOLID)) | (2u << (4 * GG_CMD_COLOR)) | (2u << (4 * GG_CMD_GRAD));     // tags 0..7
+        constexpr uint32_t LEN_HI = (1u << (4 * (GG_CMD_BEGIN_CLIP - 8))) | (3u << (4 * (GG_CMD_END_CLIP - 8)));              // tags 8..15
 #pragma unroll 1
-        for (int hop = 0; hop < 6 && c + 2 < avail; hop++) {
+        for (int hop = 0; hop < 4 && c + 2 < avail; hop++) {
             const uint32_t tag = word(c);
             if (tag == GG_CMD_FILL) { *n = word(c + 1) >> 1; *seg_ix = word(c + 2); return true; }
-            else if (tag == GG_CMD_COLOR || tag == GG_CMD_GRAD) c += 2;
-            else if (tag == GG_CMD_END_CLIP) c += 3;
-            else if (tag == GG_CMD_SOLID || tag == GG_CMD_BEGIN_CLIP) c += 1;
-            else return false;
+            const uint32_t l = tag > 15u ? 0u : (((tag & 8u) ? LEN_HI : LEN_LO) >> ((tag & 7u) * 4u)) & 15u;
+            if (l == 0u) return false;
+            c += l;
         }
         return false;
     }
@@ -311,16 +315,18 @@ struct SegStream {
     __device__ __forceinline__ void drain() { while (wait_seq < issue_seq) wait(); }
 };
 
-// fine.go:233-275 for ONE (segment, row): trapezoid areas of the columns the segment passes through inside this lane's
-// 8-pixel window, and the constant winding step dy for everything to the right, recorded as differences in the lane's
-// table D[col][lane] (column 8 = beyond the window). Operation order of the per-pixel formula as in the reference (its
-// numerator cancels for near-vertical segments; this TU is compiled with -fmad=false).
-// The table holds 2^-20 fixed point: integer sums do not depend on the order the segments of a tile arrive in (path_tiling
-// claims their slots with atomics), so a frame is reproducible bit for bit; the quantisation, 5e-7 per term, is the size of
-// float32's own rounding at these magnitudes. (Windings beyond +-2047 would wrap.)
+// fine.go:233-275 for ONE (segment, row) pair: trapezoid areas of the columns the segment passes through in this row of
+// the tile, and the constant winding step dy for everything to the right, recorded as differences in the row's table.
+// The table is laid out for its readers -- lane (row, half) owns entries D[i * 32 + lane], i = column inside its 8-pixel
+// half -- and written with shared-memory INTEGER atomics (native ATOMS.ADD, not the compare-and-swap loops of float
+// atomics): 2^-20 fixed point, so the sums do not depend on the order the segments of a tile arrive in (path_tiling claims
+// their slots with atomics) and a frame is reproducible bit for bit; the quantisation, 5e-7 per term, is the size of
+// float32's own rounding at these magnitudes. (Windings beyond +-2047 would wrap.) Operation order of the per-pixel formula
+// as in the reference (its numerator cancels for near-vertical segments; this TU is compiled with -fmad=false).
 #define AREA_FIX 1048576.0f
-__device__ __forceinline__ void seg_row(int* D, uint32_t lane, float yi, int xb, float p0x, float p0y, float dx, float dys, float rc) {
-    const float y = p0y - yi;
+__device__ __forceinline__ int d_slot(int row, int col) { return (col & 7) * 32 + row * 2 + (col >> 3); }   // col 0..15
+__device__ __forceinline__ void seg_item(int* D, int row, float p0x, float p0y, float dx, float dys, float rc) {
+    const float y = p0y - (float)row;
     const float y0 = clamp01(y);
     const float y1 = clamp01(y + dys);
     const float dy = y0 - y1;
@@ -331,11 +337,11 @@ __device__ __forceinline__ void seg_row(int* D, uint32_t lane, float yi, int xb,
         const float x1 = p0x + t1 * dx;
         const float xmin0 = fminf(x0, x1);
         const float xmax0 = fmaxf(x0, x1);
-        const int c0 = max((int)floorf(xmin0) - xb, 0);
-        const int c1 = min(max((int)ceilf(xmax0) - xb, 0), PX);
+        const int c0 = max((int)floorf(xmin0), 0);
+        const int c1 = min(max((int)ceilf(xmax0), 0), GG_TILE_W);
         int vprev = 0;
         for (int col = c0; col < c1; col++) {
-            const float i_f = (float)(xb + col);   // absolute column in the tile, as fine.go:259
+            const float i_f = (float)col;   // column in the tile, as fine.go:259
             const float xmin = fminf(xmin0 - i_f, 1.0f) - 1.0e-6f;
             const float xmax = xmax0 - i_f;
             const float b = fminf(xmax, 1.0f);
@@ -344,22 +350,25 @@ __device__ __forceinline__ void seg_row(int* D, uint32_t lane, float yi, int xb,
             // the quotient may be 2 ulp off the reference's IEEE division: far below what survives the 8-bit quantisation
             const float a = __fdividef(b + 0.5f * (d * d - c * c) - xmin, xmax - xmin);
             const int v = __float2int_rn(a * dy * AREA_FIX);
-            D[col * 32 + lane] += v - vprev;
+            atomicAdd(&D[d_slot(row, col)], v - vprev);
             vprev = v;
         }
-        D[c1 * 32 + lane] += __float2int_rn(dy * AREA_FIX) - vprev;
+        if (c1 < GG_TILE_W) atomicAdd(&D[d_slot(row, c1)], __float2int_rn(dy * AREA_FIX) - vprev);
     }
 }
 
 // Area of one CmdFill (fine.go:219-276 fillPath) for the 8 pixels of this lane.
+// The segments of a chunk are first looked at in parallel (lane = segment: rows crossed, 1/dy); the (segment, row) pairs
+// of the chunk -- the unit of work of fillPath's two loops -- are then dealt to the lanes 32 at a time through a prefix
+// sum of the row counts, whatever the shape of the slice: one tall edge (16 pairs of one segment) and a dozen short
+// segments of a small path both fill one pass.
 __device__ __forceinline__ void fill_area(float* area, int* D, float* der, SegStream& ss, const PtclStream& ps, uint32_t next_cmd,
                                           uint32_t seg_ix, uint32_t n, float backdrop, uint32_t lane) {
     const uint32_t row = lane >> 1;
-    const int xb = (int)(lane & 1u) * PX;
     const float yi = (float)row;
     __syncwarp();   // the table and the derived values share their bytes with CmdEndClip's scratch and tile B's image
 #pragma unroll
-    for (int i = 0; i <= PX; i++) D[i * 32 + lane] = 0;
+    for (int i = 0; i < PX; i++) D[i * 32 + lane] = 0;
     int base = 0;   // the y_edge terms of this row (fine.go:244: the same for every pixel of the row)
     const uint32_t lead = seg_ix & 3u, first = seg_ix - lead, total = lead + n;
     for (uint32_t c0s = 0; c0s < total; c0s += SEG_CHUNK) {
@@ -372,41 +381,37 @@ __device__ __forceinline__ void fill_area(float* area, int* D, float* der, SegSt
         }
         // next chunk: of this slice, or the first one of the next CmdFill in the command list
         if (ss.issue_seq == ss.wait_seq + 1) {
-            if (c0s + SEG_CHUNK < total) {
-                __syncwarp();
-                ss.issue(first + c0s + SEG_CHUNK, (min((uint32_t)SEG_CHUNK, total - c0s - SEG_CHUNK) + 3u) & ~3u);
-            } else {
+            uint32_t nfirst = first + c0s + SEG_CHUNK, ncnt = total - c0s - SEG_CHUNK;
+            bool more = c0s + SEG_CHUNK < total;
+            if (!more) {
                 uint32_t nseg_ix, nn;
-                if (ps.next_fill(next_cmd, &nseg_ix, &nn)) {
-                    const uint32_t nlead = nseg_ix & 3u;
-                    __syncwarp();
-                    ss.issue(nseg_ix - nlead, (min((uint32_t)SEG_CHUNK, nlead + nn) + 3u) & ~3u);
-                }
+                if (ps.next_fill(next_cmd, &nseg_ix, &nn)) { more = true; nfirst = nseg_ix & ~3u; ncnt = (nseg_ix & 3u) + nn; }
+            }
+            if (more) {
+                __syncwarp();
+                ss.issue(nfirst, (min((uint32_t)SEG_CHUNK, ncnt) + 3u) & ~3u);
             }
         }
         const float* sg = ss.wait();
-        // ---- lane = segment: row span, derived values
+        // ---- lane = segment: rows crossed, derived values
         const uint32_t k = c0s + lane;
         const bool valid = k >= lead && k < total && lane < cnt;
-        uint32_t rows = 0;
-        bool left = false, edge = false;
+        uint32_t r0 = 0, nrows = 0;
+        bool edge = false;
         float ye = 0.0f, sgn = 0.0f;
         if (valid) {
             const float p0x = sg[lane * 5 + 0], p0y = sg[lane * 5 + 1], p1x = sg[lane * 5 + 2], p1y = sg[lane * 5 + 3];
             ye = sg[lane * 5 + 4];
-            const float dx = p1x - p0x, dys = p1y - p0y;
-            der[lane] = dx; der[32 + lane] = dys; der[64 + lane] = __frcp_rn(dys);
+            const float dys = p1y - p0y;
+            der[lane] = __frcp_rn(dys);
             if (dys != 0.0f) {
                 const float ymin = fminf(p0y, p1y), ymax = fmaxf(p0y, p1y);
-                const int r0 = max(0, min(15, (int)floorf(ymin)));
-                const int r1 = max(r0 + 1, min(16, (int)ceilf(ymax)));
-                rows = (0xffffu >> (16 - (r1 - r0))) << r0;
+                r0 = (uint32_t)max(0, min(15, (int)floorf(ymin)));
+                nrows = (uint32_t)max((int)r0 + 1, min(16, (int)ceilf(ymax))) - r0;
             }
-            left = fminf(p0x, p1x) < (float)PX;
             edge = ye < 16.0f;   // touches the tile's left edge: winding step for the rows from y_edge down (fine.go:244)
-            sgn = signum32(dx);
+            sgn = signum32(p1x - p0x);
         }
-        __syncwarp();
         uint32_t em = __ballot_sync(0xffffffffu, edge);
         while (em) {
             const int j = __ffs((int)em) - 1;
@@ -414,34 +419,33 @@ __device__ __forceinline__ void fill_area(float* area, int* D, float* der, SegSt
             const float yej = __shfl_sync(0xffffffffu, ye, j), sj = __shfl_sync(0xffffffffu, sgn, j);
             base += __float2int_rn(sj * clamp01(yi - yej + 1.0f) * AREA_FIX);
         }
-        // ---- which segments does my row (half) need? 32 x 32 bit transpose by ballots; tiny chunks: everybody looks at all
-        const uint32_t vm = __ballot_sync(0xffffffffu, rows != 0u);
-        uint32_t mine;
-        if (__popc(vm) <= 3) {
-            mine = vm;
-        } else {
-            mine = 0;
+        // ---- inclusive prefix sum of the row counts: pair t of the chunk belongs to the first segment with incl > t
+        uint32_t incl = nrows;
 #pragma unroll
-            for (uint32_t r = 0; r < 16; r++) {
-                const uint32_t m = __ballot_sync(0xffffffffu, (rows >> r) & 1u);
-                if (row == r) mine = m;
-            }
-            const uint32_t lm = __ballot_sync(0xffffffffu, left);
-            if (xb == 0) mine &= lm;   // a segment that stays in the right half leaves the left half's pixels alone
-        }
-        // ---- lane = (row, half): walk the segments that cross the row
-        while (__any_sync(0xffffffffu, mine != 0u)) {
-            if (mine) {
-                const int j = __ffs((int)mine) - 1;
-                mine &= mine - 1u;
-                seg_row(D, lane, yi, xb, sg[j * 5 + 0], sg[j * 5 + 1], der[j], der[32 + j], der[64 + j]);
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o); if ((int)lane >= o) incl += v; }
+        const uint32_t n_pairs = __shfl_sync(0xffffffffu, incl, 31);
+        const uint32_t start = (incl - nrows) | (r0 << 16);   // first pair of my segment | its first row
+        __syncwarp();   // der[] written above, the table zeroed: visible to every lane
+        for (uint32_t t = lane; t - lane < n_pairs; t += 32) {
+            uint32_t j = 0;
+#pragma unroll
+            for (uint32_t s2 = 16; s2; s2 >>= 1) { if (__shfl_sync(0xffffffffu, incl, j + s2 - 1u) <= t) j += s2; }
+            const uint32_t st = __shfl_sync(0xffffffffu, start, j & 31u);
+            if (t < n_pairs) {
+                const float p0x = sg[j * 5 + 0], p0y = sg[j * 5 + 1];
+                seg_item(D, (int)((st >> 16) + t - (st & 0xffffu)), p0x, p0y, sg[j * 5 + 2] - p0x, sg[j * 5 + 3] - p0y, der[j]);
             }
         }
         __syncwarp();
     }
-    int run = base;
+    int run = 0;
+    int dv[PX];
 #pragma unroll
-    for (int i = 0; i < PX; i++) { run += D[i * 32 + lane]; area[i] = backdrop + (float)run * (1.0f / AREA_FIX); }
+    for (int i = 0; i < PX; i++) { run += D[i * 32 + lane]; dv[i] = run; }
+    const int left = __shfl_sync(0xffffffffu, run, lane & ~1u);   // the row's left half carries into its right half
+    base += (lane & 1u) ? left : 0;
+#pragma unroll
+    for (int i = 0; i < PX; i++) area[i] = backdrop + (float)(dv[i] + base) * (1.0f / AREA_FIX);
 }
 
 // VelloAccelerator.compositeOver (vello_accelerator.go:388-442) for one pixel: the scene was rasterised on transparent,
@@ -591,13 +595,11 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
 #pragma unroll
                         for (int i = 0; i < PX; i++) area[i] = fminf(fabsf(area[i]), 1.0f);                                      // fine.go:286
                     }
-                    ps.ensure(cmd);
                     tag = ps.word(cmd);
                 } else if (tag == GG_CMD_SOLID) {
                     cmd += 1;
 #pragma unroll
                     for (int i = 0; i < PX; i++) area[i] = 1.0f;
-                    ps.ensure(cmd);
                     tag = ps.word(cmd);
                 }
                 if (tag == GG_CMD_COLOR) {
@@ -656,12 +658,12 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     // Blend stack (fine.go:58-62 keeps 4 levels "in registers" and spills deeper ones; where a level lives is
                     // invisible in the output): level 0 in shared memory ([pixel][lane]: conflict-free 128-bit accesses),
                     // deeper levels in the global spill buffer coarse sized for this tile.
-                    float4* slot; uint32_t step;
-                    if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
-                    else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
+                    // Both as [pixel][lane]: a warp-wide access is 512 contiguous bytes either way.
+                    float4* slot = clip_depth < GG_BLEND_STACK_SPLIT ? &sstk[clip_depth][0][lane]
+                                                                     : spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane);
                     if (clip_depth < GG_BLEND_STACK_SPLIT || sp_off != 0xffffffffu) {
 #pragma unroll
-                        for (int i = 0; i < PX; i++) { slot[i * step] = rgba[i]; }
+                        for (int i = 0; i < PX; i++) { slot[i * 32] = rgba[i]; }
                     }
                     clip_depth++;
 #pragma unroll
@@ -672,9 +674,8 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     cmd += 3;
                     if (clip_depth == 0) continue;
                     clip_depth--;
-                    const float4* slot; uint32_t step;
-                    if (clip_depth < GG_BLEND_STACK_SPLIT) { slot = &sstk[clip_depth][0][lane]; step = 32; }
-                    else { slot = spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane * PX); step = 1; }
+                    const float4* slot = clip_depth < GG_BLEND_STACK_SPLIT ? &sstk[clip_depth][0][lane]
+                                                                           : spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane);
                     const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
                     // Scaling the source by the coverage (fine.go:152-160) equals out = D + cov (blend(S, D) - D) for every mode
                     // whose backdrop factor is 1 under a transparent source; the six compose modes that wipe their backdrop
@@ -692,7 +693,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                         for (int hf = 0; hf < 2; hf++) {
 #pragma unroll
                             for (int i = 0; i < 4; i++) scr[i * 32] = rgba[hf * 4 + i];
-                            blend_mix4(mix, scr, slot + hf * 4 * step, step);
+                            blend_mix4(mix, scr, slot + hf * 4 * 32);
 #pragma unroll
                             for (int i = 0; i < 4; i++) rgba[hf * 4 + i] = scr[i * 32];
                         }
@@ -702,7 +703,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                         const bool plus = compose == 12u;
 #pragma unroll
                         for (int i = 0; i < PX; i++) {
-                            const float4 sv = slot[i * step];
+                            const float4 sv = slot[i * 32];
                             float fa = k.x + k.y * sv.w, fb = k.z + k.w * rgba[i].w;
                             float4 o;
                             o.x = fmaf(fb, sv.x, fa * rgba[i].x); o.y = fmaf(fb, sv.y, fa * rgba[i].y);
