@@ -27,6 +27,11 @@ __device__ __forceinline__ float signum32(float x) {   // util.go:118-130
 }
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 
+// two float32 FMAs in one instruction (FFMA2, sm_100): each half rounds exactly like fmaf
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
 __device__ __forceinline__ uint32_t pack_rgba8(float4 c) {   // fine.wgsl:305-323
     uint32_t r = (uint32_t)(clamp01(c.x) * 255.0f + 0.5f);
     uint32_t g = (uint32_t)(clamp01(c.y) * 255.0f + 0.5f);
@@ -148,22 +153,6 @@ __device__ __forceinline__ float4 blend_mix_px(uint32_t mix, float4 bg, float4 f
     o.w = sa + da * (1.0f - sa);
     return o;
 }
-// CmdEndClip of a mix mode for FOUR of the lane's pixels, held in shared memory: scr[i * 32] = the layer's pixel
-// (premultiplied, already scaled by coverage and alpha), replaced by the result; slot[i * 32] = the backdrop. One rolled
-// loop, one copy of the blend code, one call per four pixels -- with the eight pixels in registers the code was unrolled
-// eight times around a per-pixel call whose register saves were 3 % of fine's instructions and the kernel did not fit the
-// instruction cache (ncu r2b: sm__icc hit rate 69 %, 12.7 cycles of no_instruction stall per issue).
-__device__ __noinline__ void blend_mix4(uint32_t mix, float4* scr, const float4* slot) {
-#pragma unroll 1
-    for (int i = 0; i < 4; i++) {
-        const float4 fg = scr[i * 32], bg = slot[i * 32];
-        // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source)
-        float4 o = fg;
-        if (fg.w <= 0.0f) o = bg;
-        else if (bg.w > 0.0f) o = blend_mix_px(mix, bg, fg);
-        scr[i * 32] = o;
-    }
-}
 // Porter-Duff compose (Normal mix): Fa * S + Fb * D with Fa = a0 + a1 * Da and Fb = b0 + b1 * Sa
 // (porter_duff.go:117-216); one table row per compose mode keeps the per-pixel code branch free.
 __constant__ float4 COMPOSE_COEF[14] = {
@@ -182,6 +171,43 @@ __constant__ float4 COMPOSE_COEF[14] = {
     {1, 0, 1, 0},    // Plus (clamped)
     {1, 0, 1, -1},   // PlusLighter: not produced by gg, treated as SrcOver
 };
+// CmdEndClip (fine.go:140-180) for FOUR of the lane's pixels, held in shared memory: scr[i * 32] = the layer's pixel
+// (premultiplied), replaced by the result; cov[i * 32] = the clip's coverage there; slot[i * 32] = the backdrop saved by
+// CmdBeginClip. One rolled loop, one copy of the blend code, two calls per CmdEndClip -- with the eight pixels in
+// registers the code was unrolled eight times and the kernel did not fit the 32 KB instruction cache of an SM (ncu r2b /
+// r2f: sm__icc hit rate 69-74 %, 9-13 cycles of no_instruction stall per issue, the GPC's instruction cache 95 % busy).
+// Scaling the source by the coverage (fine.go:152-160) equals out = D + cov (blend(S, D) - D) for every mode whose
+// backdrop factor is 1 under a transparent source; the six compose modes that wipe their backdrop are blended at full
+// strength and interpolated instead (a pixel the layer's clip does not cover stays).
+__device__ __noinline__ void end_clip4(uint32_t blend, float alpha, float4* scr, const float* cov, const float4* slot) {
+    const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
+    const bool wipe = mix == 0u && (compose == 0u || compose == 1u || compose == 5u || compose == 6u || compose == 7u || compose == 10u);
+    const bool mixed = mix != 0u && mix < 16u;
+    const float4 k = COMPOSE_COEF[min(compose, 13u)];   // Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}
+    const bool plus = compose == 12u;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        float4 fg = scr[i * 32];
+        const float4 bg = slot[i * 32];
+        const float cv = cov[i * 32];
+        const float scale = wipe ? alpha : cv * alpha;
+        fg.x *= scale; fg.y *= scale; fg.z *= scale; fg.w *= scale;
+        float4 o;
+        if (mixed) {
+            // trivial pixels first (transparent source -> backdrop, transparent backdrop -> source)
+            o = fg;
+            if (fg.w <= 0.0f) o = bg;
+            else if (bg.w > 0.0f) o = blend_mix_px(mix, bg, fg);
+        } else {
+            const float fa = k.x + k.y * bg.w, fb = k.z + k.w * fg.w;
+            o.x = fmaf(fb, bg.x, fa * fg.x); o.y = fmaf(fb, bg.y, fa * fg.y);
+            o.z = fmaf(fb, bg.z, fa * fg.z); o.w = fmaf(fb, bg.w, fa * fg.w);
+            if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
+            if (wipe) { o.x = bg.x + cv * (o.x - bg.x); o.y = bg.y + cv * (o.y - bg.y); o.z = bg.z + cv * (o.z - bg.z); o.w = bg.w + cv * (o.w - bg.w); }
+        }
+        scr[i * 32] = o;
+    }
+}
 
 // ---------------------------------------------------------------- shared memory per warp, bulk copies
 #define PTCL_CHUNK 128   // words per command-ring slot (512 B)
@@ -195,7 +221,8 @@ __constant__ float4 COMPOSE_COEF[14] = {
 #define SM_SCR 6400      // CmdEndClip scratch, four pixels per lane: float4 [4][32] (over DER and D) 2048
 #define SM_IMG_A 8448    // RGBA8 image of the pair's left tile: u32 [16][16]                        1024
 #define SM_BARS 9472     // 4 mbarriers                                                              32
-#define FINE_SMEM_PER_WARP 9600
+#define SM_COV 9600      // CmdEndClip scratch: coverage of the four pixels, float [4][32]           512
+#define FINE_SMEM_PER_WARP 10112
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -270,21 +297,16 @@ struct PtclStream {
         limit = min(a, b);
     }
     __device__ __forceinline__ uint32_t word(uint32_t i) const { return ring[i & (2 * PTCL_CHUNK - 1)]; }
-    // The next CmdFill at or after word c, looking only at words that have already arrived (a few commands ahead).
-    // Command lengths from a nibble table indexed by the tag (0 = stop: CmdEnd or unknown).
+    // The CmdFill that follows the command at word c (the user of the fill being evaluated: CmdColor / CmdGrad, 2 words, or
+    // CmdEndClip, 3 words), if both have already arrived. Other shapes are simply not prefetched.
     __device__ __forceinline__ bool next_fill(uint32_t c, uint32_t* seg_ix, uint32_t* n) const {
-        const uint32_t avail = min(loaded_end, len);
-        constexpr uint32_t LEN_LO = (1u << (4 * GG_CMD_SOLID)) | (2u << (4 * GG_CMD_COLOR)) | (2u << (4 * GG_CMD_GRAD));     // tags 0..7
-        constexpr uint32_t LEN_HI = (1u << (4 * (GG_CMD_BEGIN_CLIP - 8))) | (3u << (4 * (GG_CMD_END_CLIP - 8)));              // tags 8..15
-#pragma unroll 1
-        for (int hop = 0; hop < 4 && c + 2 < avail; hop++) {
-            const uint32_t tag = word(c);
-            if (tag == GG_CMD_FILL) { *n = word(c + 1) >> 1; *seg_ix = word(c + 2); return true; }
-            const uint32_t l = tag > 15u ? 0u : (((tag & 8u) ? LEN_HI : LEN_LO) >> ((tag & 7u) * 4u)) & 15u;
-            if (l == 0u) return false;
-            c += l;
-        }
-        return false;
+        if (c + 6 >= min(loaded_end, len)) return false;
+        const uint32_t t0 = word(c);
+        if (t0 != GG_CMD_COLOR && t0 != GG_CMD_END_CLIP && t0 != GG_CMD_GRAD) return false;
+        c += t0 == GG_CMD_END_CLIP ? 3u : 2u;
+        if (word(c) != GG_CMD_FILL) return false;
+        *n = word(c + 1) >> 1; *seg_ix = word(c + 2);
+        return true;
     }
 };
 
@@ -605,13 +627,14 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                 if (tag == GG_CMD_COLOR) {
                     const float4 c = unpack_rgba8(ps.word(cmd + 1));
                     cmd += 2;
+                    // fine.go:104-123: rgba * (1 - c.a * cov) + c * cov, two FMAs per channel, two channels per instruction
+                    const uint64_t nw2 = pack2(-c.w, -c.w), cxy = pack2(c.x, c.y), czw = pack2(c.z, c.w);
 #pragma unroll
-                    for (int i = 0; i < PX; i++) {   // fine.go:104-123: rgba * (1 - c.a * cov) + c * cov, two FMAs per channel
-                        const float cov = area[i];
-                        rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
-                        rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
-                        rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);
-                        rgba[i].w = fmaf(cov, fmaf(-c.w, rgba[i].w, c.w), rgba[i].w);
+                    for (int i = 0; i < PX; i++) {
+                        const uint64_t cov2 = pack2(area[i], area[i]);
+                        const uint64_t xy = pack2(rgba[i].x, rgba[i].y), zw = pack2(rgba[i].z, rgba[i].w);
+                        unpack2(fma2(cov2, fma2(nw2, xy, cxy), xy), rgba[i].x, rgba[i].y);
+                        unpack2(fma2(cov2, fma2(nw2, zw, czw), zw), rgba[i].z, rgba[i].w);
                     }
                 } else if (tag == GG_CMD_GRAD) {
                     // Gradient brush (gg.LinearGradientBrush / RadialGradientBrush.ColorAt at the pixel centre, software.go:1086-1090):
@@ -676,42 +699,16 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     clip_depth--;
                     const float4* slot = clip_depth < GG_BLEND_STACK_SPLIT ? &sstk[clip_depth][0][lane]
                                                                            : spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane);
-                    const uint32_t mix = (blend >> 8) & 0xffu, compose = blend & 0xffu;
-                    // Scaling the source by the coverage (fine.go:152-160) equals out = D + cov (blend(S, D) - D) for every mode
-                    // whose backdrop factor is 1 under a transparent source; the six compose modes that wipe their backdrop
-                    // are blended at full strength and interpolated instead (a pixel the layer's clip does not cover stays).
-                    const bool wipe = mix == 0u && (compose == 0u || compose == 1u || compose == 5u || compose == 6u || compose == 7u || compose == 10u);
+                    float4* scr = reinterpret_cast<float4*>(wsm + SM_SCR) + lane;
+                    float* cvs = reinterpret_cast<float*>(wsm + SM_COV) + lane;
+                    __syncwarp();   // the scratch lies over the coverage table of the fill just evaluated
 #pragma unroll
-                    for (int i = 0; i < PX; i++) {
-                        float scale = wipe ? alpha : area[i] * alpha;   // fg = rgba * area * alpha, in place
-                        rgba[i].x *= scale; rgba[i].y *= scale; rgba[i].z *= scale; rgba[i].w *= scale;
-                    }
-                    if (mix != 0u && mix < 16u) {
-                        float4* scr = reinterpret_cast<float4*>(wsm + SM_SCR) + lane;
-                        __syncwarp();   // the scratch lies over the coverage table of the fill just evaluated
+                    for (int hf = 0; hf < 2; hf++) {
 #pragma unroll
-                        for (int hf = 0; hf < 2; hf++) {
+                        for (int i = 0; i < 4; i++) { scr[i * 32] = rgba[hf * 4 + i]; cvs[i * 32] = area[hf * 4 + i]; }
+                        end_clip4(blend, alpha, scr, cvs, slot + hf * 4 * 32);
 #pragma unroll
-                            for (int i = 0; i < 4; i++) scr[i * 32] = rgba[hf * 4 + i];
-                            blend_mix4(mix, scr, slot + hf * 4 * 32);
-#pragma unroll
-                            for (int i = 0; i < 4; i++) rgba[hf * 4 + i] = scr[i * 32];
-                        }
-                    } else {
-                        // Porter-Duff: Fa * S + Fb * D. Normal / clip SrcOver (fine.go:168-179) is the row {1, 0, 1, -1}.
-                        const float4 k = COMPOSE_COEF[min(compose, 13u)];
-                        const bool plus = compose == 12u;
-#pragma unroll
-                        for (int i = 0; i < PX; i++) {
-                            const float4 sv = slot[i * 32];
-                            float fa = k.x + k.y * sv.w, fb = k.z + k.w * rgba[i].w;
-                            float4 o;
-                            o.x = fmaf(fb, sv.x, fa * rgba[i].x); o.y = fmaf(fb, sv.y, fa * rgba[i].y);
-                            o.z = fmaf(fb, sv.z, fa * rgba[i].z); o.w = fmaf(fb, sv.w, fa * rgba[i].w);
-                            if (plus) { o.x = fminf(o.x, 1.0f); o.y = fminf(o.y, 1.0f); o.z = fminf(o.z, 1.0f); o.w = fminf(o.w, 1.0f); }
-                            if (wipe) { const float cv = area[i]; o.x = sv.x + cv * (o.x - sv.x); o.y = sv.y + cv * (o.y - sv.y); o.z = sv.z + cv * (o.z - sv.z); o.w = sv.w + cv * (o.w - sv.w); }
-                            rgba[i] = o;
-                        }
+                        for (int i = 0; i < 4; i++) rgba[hf * 4 + i] = scr[i * 32];
                     }
                 } else if (tag != GG_CMD_FILL && tag != GG_CMD_SOLID) {
                     break;   // CmdEnd, or an unknown command: stop (fine.go:182-185)
