@@ -110,7 +110,7 @@ def fine_bytes_fast(ptcl_off, ptcl, w, h):
     words = len(pos)
     segs = 0
     size = np.zeros(16, dtype=np.int64)
-    size[[0, 1, 3, 5, 10, 11]] = [1, 4, 1, 2, 1, 3]
+    size[[0, 1, 3, 5, 6, 10, 11]] = [1, 4, 1, 2, 2, 1, 3]
     while active.any():
         idx = np.nonzero(active)[0]
         tags = ptcl[pos[idx]]

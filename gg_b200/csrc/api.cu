@@ -165,7 +165,7 @@ int upload(Ctx* c) {
     if ((r = ensure(c, c->ptcl_off, 4 * bt))) return r;
     if ((r = ensure(c, c->ptcl_len, 4 * bt))) return r;
     if ((r = ensure(c, c->restart_pt, 8 * bt))) return r;
-    if ((r = ensure(c, c->spill_off, 4 * bt))) return r;
+    if ((r = ensure(c, c->spill_off, 8 * bt))) return r;   // + the list of heavy tiles (GG_FINE_HEAVY_WORDS)
     if ((r = ensure(c, c->bump, sizeof(GGBump)))) return r;
     if ((r = ensure(c, c->scan_partials, 32 * GG_SCAN_BLOCKS))) return r;
     // first guesses for the data-dependent buffers; the retry loop corrects them

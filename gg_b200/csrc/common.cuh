@@ -83,10 +83,14 @@ struct GGBump {
     uint32_t esegs;        // 40: Euler-segment records written by flatten_subdivide
     uint32_t sub_cursor;   // 44: next work-list entry flatten_subdivide hands to a lane
     uint32_t emit_cursor;  // 48: next Euler-segment record flatten_eseg_emit hands to a lane
-    uint32_t pad[3];       // 52
+    uint32_t heavy;        // 52: tiles whose command list (after the restart point) is long: fine starts those first, one warp each
+    uint32_t pad[2];       // 56
     uint32_t fine_cursor[GG_FINE_PARTS];   // 64: next tile (relative to the part's first) fine hands to a warp, one per launch of a frame
     uint32_t pad2[8 - GG_FINE_PARTS];
 };
+// A tile with more than this many PTCL words left to execute is `heavy`: coarse lists it (behind spill_off[]), fine hands the
+// listed tiles out first and singly instead of in pairs (a frame ends when its slowest warp does).
+#define GG_FINE_HEAVY_WORDS 96u
 #define GG_FAIL_LINES 1u
 #define GG_FAIL_TILES 2u
 #define GG_FAIL_SEGCOUNTS 4u

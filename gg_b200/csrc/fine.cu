@@ -572,26 +572,47 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
     const float4 bgc = over ? make_float4(0, 0, 0, 0) : make_float4(cfg.bg[0], cfg.bg[1], cfg.bg[2], cfg.bg[3]);
     const uint32_t npx = rg.px1 - rg.px0;                         // tile pairs per row of this launch
     const uint32_t n_pairs = npx * (rg.row1 - rg.row0);
-    // Pairs are handed out from a shared cursor: their cost varies by orders of magnitude (restart points make most
-    // tiles of a scene with opaque content trivial), a static stride left warps idle behind the heavy ones.
+    // Work is handed out from a shared cursor: costs vary by orders of magnitude (restart points make most tiles of a scene
+    // with opaque content trivial; a static stride left warps idle behind the heavy ones). First the tiles coarse listed as
+    // heavy, ONE per warp -- the frame ends when its slowest warp does, so the long lists start first and are not chained
+    // two to a warp --, then the pairs, skipping the heavy tiles in them. (If an eighth of the tiles are heavy there is no
+    // tail to speak of: everything goes by pairs.)
+    const uint32_t band_tiles = (cfg.band_y1 - cfg.band_y0) * cfg.width_in_tiles;
+    const uint32_t* heavy_list = spill_off + band_tiles;
+    const uint32_t n_heavy = bump->heavy * 8u <= band_tiles ? bump->heavy : 0u;
     for (;;) {
         uint32_t P = 0;
         if (lane == 0) P = atomicAdd(&bump->fine_cursor[part], 1u);
         P = __shfl_sync(0xffffffffu, P, 0);
-        if (P >= n_pairs) break;
-        const uint32_t trow = rg.row0 + P / npx;                  // tile row, relative to the band
-        const uint32_t pcol = rg.px0 + P % npx;
+        uint32_t trow, pcol, only = 2u;   // only: the half to render (2 = both)
+        if (P < n_heavy) {
+            const uint32_t T = heavy_list[P];
+            trow = T / cfg.width_in_tiles;
+            const uint32_t tx = T - trow * cfg.width_in_tiles;
+            pcol = tx >> 1; only = tx & 1u;
+            if (trow < rg.row0 || trow >= rg.row1 || pcol < rg.px0 || pcol >= rg.px1) continue;   // another launch's tile
+        } else {
+            P -= n_heavy;
+            if (P >= n_pairs) break;
+            trow = rg.row0 + P / npx;                  // tile row, relative to the band
+            pcol = rg.px0 + P % npx;
+        }
         const uint32_t py = (trow + cfg.band_y0) * GG_TILE_H + row;
         const bool row_in = py < cfg.height;
+        uint32_t done = 0;   // bit h: half h was rendered by this warp
         for (uint32_t half = 0; half < 2; half++) {
             const uint32_t tx = pcol * 2 + half;
             if (tx >= cfg.width_in_tiles) break;
+            if (only != 2u && only != half) continue;
             const uint32_t T = trow * cfg.width_in_tiles + tx;
-            float4 rgba[PX];
-            float area[PX];
             // coarse found the last command of this tile that overwrites every pixel whatever came before (an opaque
             // solid colour or a backdrop-wiping layer at clip depth 0): start right after it, from that colour
             const uint32_t restart = restart_pt[2 * T];
+            const uint32_t tlen = ptcl_len[T];
+            if (only == 2u && n_heavy && tlen - max(restart, 1u) > GG_FINE_HEAVY_WORDS) continue;   // listed: rendered on its own
+            done |= 1u << half;
+            float4 rgba[PX];
+            float area[PX];
             {
                 const float4 c0 = restart ? unpack_rgba8(restart_pt[2 * T + 1]) : bgc;
 #pragma unroll
@@ -599,7 +620,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
             }
             uint32_t clip_depth = 0;
             uint32_t cmd = restart ? restart : 1u;   // word 0 = blend offset (ptcl.go:98)
-            ps.begin(ptcl + ptcl_off[T], ptcl_len[T], cmd / PTCL_CHUNK);
+            ps.begin(ptcl + ptcl_off[T], tlen, cmd / PTCL_CHUNK);
             const uint32_t sp_off = spill_off[T];
             for (;;) {
                 ps.ensure(cmd);
@@ -744,6 +765,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
 #pragma unroll 1
         for (uint32_t k = 0; k < 4; k++) {
             const uint32_t r = k * 4 + (lane >> 3), chunk = lane & 7u, half = chunk >> 2, cq = chunk & 3u;
+            if (!((done >> half) & 1u)) continue;
             uint4 v = *reinterpret_cast<const uint4*>((half ? img_b : img_a) + r * 16 + cq * 4);
             const uint32_t x = (pcol * 2 + half) * GG_TILE_W + cq * 4;
             const uint32_t y = (trow + cfg.band_y0) * GG_TILE_H + r;

@@ -1051,6 +1051,8 @@ __device__ __noinline__ void coarse_tile_sequential(const GGConfig& cfg, uint32_
             ptcl[pos] = GG_CMD_END;
             ptcl_len[T] = pos + 1 - ptcl_off[T];
             restart_pt[2 * T] = restart; restart_pt[2 * T + 1] = restart_rgba;
+            if (pos + 1 - ptcl_off[T] - max(restart, 1u) > GG_FINE_HEAVY_WORDS)
+                spill_off[(cfg.band_y1 - cfg.band_y0) * cfg.width_in_tiles + atomicAdd(&bump->heavy, 1u)] = T;
             if (max_depth > GG_BLEND_STACK_SPLIT) {
                 uint32_t lv = max_depth - GG_BLEND_STACK_SPLIT;
                 uint32_t so = atomicAdd(&bump->spill, lv);
@@ -1268,6 +1270,8 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
             ptcl[pos] = GG_CMD_END;
             ptcl_len[T] = pos + 1 - ptcl_off[T];
             restart_pt[2 * T] = restart; restart_pt[2 * T + 1] = restart_rgba;
+            if (pos + 1 - ptcl_off[T] - max(restart, 1u) > GG_FINE_HEAVY_WORDS)
+                spill_off[(cfg.band_y1 - cfg.band_y0) * cfg.width_in_tiles + atomicAdd(&bump->heavy, 1u)] = T;
             if (max_depth > GG_BLEND_STACK_SPLIT) {
                 uint32_t lv = max_depth - GG_BLEND_STACK_SPLIT;
                 uint32_t so = atomicAdd(&bump->spill, lv);

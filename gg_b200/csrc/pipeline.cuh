@@ -38,7 +38,7 @@ struct GGBuffers {
     uint32_t* ptcl_len;         // [band_tiles] words actually written (incl. word 0 and CmdEnd)
     uint32_t* ptcl;             // [ptcl_cap]
     uint32_t* restart_pt;       // [2 * band_tiles] {PTCL word offset fine may start from (0 = list start), RGBA8 all pixels hold there}
-    uint32_t* spill_off;        // [band_tiles] blend spill offsets (tile-levels), 0xffffffff = none
+    uint32_t* spill_off;        // [band_tiles] blend spill offsets (tile-levels), 0xffffffff = none; then [band_tiles] heavy tile list (bump->heavy)
     float4* spill;              // [spill_cap * 256]
     // misc
     GGBump* bump;
