@@ -84,7 +84,8 @@ struct GGBump {
     uint32_t sub_cursor;   // 44: next work-list entry flatten_subdivide hands to a lane
     uint32_t emit_cursor;  // 48: next Euler-segment record flatten_eseg_emit hands to a lane
     uint32_t heavy;        // 52: tiles whose command list (after the restart point) is long: fine starts those first, one warp each
-    uint32_t pad[2];       // 56
+    uint32_t coarse_cursor; // 56: next tile coarse hands to a warp (tile costs differ by orders of magnitude)
+    uint32_t pad[1];       // 60
     uint32_t fine_cursor[GG_FINE_PARTS];   // 64: next tile (relative to the part's first) fine hands to a warp, one per launch of a frame
     uint32_t pad2[8 - GG_FINE_PARTS];
 };

@@ -1095,7 +1095,11 @@ __global__ void __launch_bounds__(COARSE_WARPS * 32) coarse_kernel(GGConfig cfg,
     const uint32_t key_bits = 32u - (uint32_t)__clz((int)max(cfg.n_draws, 2u) - 1);   // draw indices are < n_draws
     uint16_t* lpos = reinterpret_cast<uint16_t*>(tmp);
     uint8_t* st = reinterpret_cast<uint8_t*>(tmp) + 2 * COARSE_CAP;
-    for (uint32_t T = blockIdx.x * COARSE_WARPS + warp; T < n_tiles; T += gridDim.x * COARSE_WARPS) {
+    for (;;) {
+        uint32_t T = 0;
+        if (lane == 0) T = atomicAdd(&bump->coarse_cursor, 1u);
+        T = __shfl_sync(0xffffffffu, T, 0);
+        if (T >= n_tiles) break;
         const uint32_t n = hit_cnt[T];
         GGHit* list = hits + hit_off[T];
         uint32_t pos = ptcl_off[T];
