@@ -250,7 +250,7 @@ __device__ inline void stroke_tail(LineOut& o, const GGConfig& cfg, const uint32
         stroke_cap<EMIT>(o, c.p3, ne, st);
 }
 
-__global__ void __launch_bounds__(128) flatten_subdivide_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
+__global__ void __launch_bounds__(128, 6) flatten_subdivide_kernel(GGConfig cfg, const uint32_t* __restrict__ scene,
                                                                 const GGPathMonoid* __restrict__ tag_monoids,
                                                                 const uint32_t* __restrict__ curve_list, uint32_t* line_count,
                                                                 GGESeg* esegs, GGBump* bump) {
@@ -1303,7 +1303,7 @@ uint32_t gg_launch_front(const GGConfig& cfg, const GGBuffers& b, cudaStream_t s
     draw_leaf_kernel<<<GG_GRID(2), 256, 0, s>>>(cfg, b.scene, b.draw_monoids, b.info, b.clip_inps, b.draw_recs);
     // a6: flatten (count, scan, emit)
     flatten_classify_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.curve_list, b.bump);
-    flatten_subdivide_kernel<<<GG_GRID(2), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.esegs, b.bump);
+    flatten_subdivide_kernel<<<GG_GRID(6), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.curve_list, b.line_count, b.esegs, b.bump);
     gg_scan<uint32_t>(s, n_tag_bytes, cfg.n_tag_bytes, LoadU32{b.line_count}, StoreU32Ex{b.line_off}, (uint32_t*)b.scan_partials, &b.bump->lines);
     flatten_line_emit_kernel<<<GG_GRID(8), 256, 0, s>>>(cfg, b.scene, b.tag_monoids, b.line_count, b.line_off, b.lines, b.path_bbox_ord, b.bump);
     flatten_eseg_emit_kernel<<<GG_GRID(8), 128, 0, s>>>(cfg, b.scene, b.tag_monoids, b.esegs, b.line_off, b.lines, b.path_bbox_ord, b.bump);
