@@ -190,7 +190,7 @@ def checksum_bands(frame, n_bands):
     return (v * wgt).sum(dim=1)
 
 
-def time_pipeline(ctx, torch, stream, steps, warmup, step_fn, flush_buf, dist=None):
+def time_pipeline(ctx, torch, stream, steps, warmup, step_fn, flush_buf, dist=None, stages=True):
     """(ms per step summed, per-stage ms summed, own-pipeline ms summed) over `steps` timed iterations, L2 flushed between."""
     for _ in range(warmup):
         step_fn()
@@ -205,8 +205,9 @@ def time_pipeline(ctx, torch, stream, steps, warmup, step_fn, flush_buf, dist=No
         torch.cuda.synchronize()
         total_ms += e0.elapsed_time(e1)
         own_ms += e0.elapsed_time(e_mid)
-        s = ctx.stats()
-        stage_ms += [s["ms_front"], s["ms_binning"], s["ms_coarse"], s["ms_fine"]]
+        if stages:
+            s = ctx.stats()
+            stage_ms += [s["ms_front"], s["ms_binning"], s["ms_coarse"], s["ms_fine"]]
     return total_ms, stage_ms, own_ms
 
 
@@ -322,6 +323,9 @@ def main():
         return step
 
     step = make_step(ctx, band)
+    # The timed region runs without per-stage events: a pass into a device target is then one CUDA-graph replay
+    # (GGCUDA_NO_GRAPH=1 turns that off). The per-stage times come from a second, untimed set of passes below.
+    ctx.set_timing(False)
     for _ in range(args.warmup):
         step()
     torch.cuda.synchronize()
@@ -334,11 +338,14 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    total_ms, stage_ms, own_ms = time_pipeline(ctx, torch, stream, args.steps, 0, step, flush_buf)
+    total_ms, _, own_ms = time_pipeline(ctx, torch, stream, args.steps, 0, step, flush_buf, stages=False)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     clocks = sampler.stop() if sampler else None
+    ctx.set_timing(True)     # stage breakdown: the same passes again with CUDA events between the stages (stream launches)
+    staged_total_ms, stage_ms, _ = time_pipeline(ctx, torch, stream, args.steps, 2, step, flush_buf)
+    ctx.set_timing(False)
     t = torch.tensor([total_ms, own_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -469,6 +476,8 @@ def main():
                        "frames_per_s": 1e3 / ms_per_step,
                        "stage_ms": {k: float(v / args.steps) for k, v in zip(("front", "binning", "coarse", "fine"), stage_ms)},
                        "counts": {k: counts[k] for k in ("n_lines", "n_path_tiles", "n_segments", "n_hits", "n_ptcl_words")},
+                       "stage_ms_note": "from a second set of passes with events between the stages (%.3f ms/step there); the timed passes replay one CUDA graph" % (staged_total_ms / args.steps),
+                       "cuda_graph": os.environ.get("GGCUDA_NO_GRAPH", "0") in ("", "0"),
                        "fine": fine_info, "launches_per_step": int(launches_per_step)},
             "roofline": {"bound": "hbm", "kernel": dom_kernel, "stage": dom, "achieved": stages[dom]["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": stages[dom]["frac"], "traffic": traffic, "peak_source": peak_src,

@@ -74,6 +74,13 @@ struct Ctx {
     ggcuda_stats stats{};
     bool timing = false;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    // One pass into a device target, captured as a CUDA graph and replayed while nothing it was built from changes (kernel
+    // arguments are baked into the nodes: configuration, buffer addresses, target, fine ranges). 25 dependent launches cost
+    // ~5 us each through the stream; a 512 x 512 frame spent half its time there.
+    struct PassKey { GGConfig cfg; GGBuffers b; uint8_t* dst; size_t stride; GGFineRange rg; GGFineMirrors mir; uint32_t reuse; } graph_key{};
+    cudaGraphExec_t graph_exec = nullptr;
+    uint32_t graph_launches = 0;
+    bool graphs = true;       // GGCUDA_NO_GRAPH=1 turns them off; so does a failed capture
     GGConfig cfg{};
     GGBump last_bump{};
 };
@@ -266,41 +273,67 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
         if (!reuse) { int r = size_dynamic(c); if (r) return r; }
         fill_config(c, flags);
         GGBuffers b = buffers(c);
-        if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
-        uint32_t launches = 0;
-        if (!reuse) launches += gg_launch_front(c->cfg, b, c->stream);
-        if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
-        if (!reuse) launches += gg_launch_binning(c->cfg, b, c->stream);
-        if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
-        if (!reuse) launches += gg_launch_coarse(c->cfg, b, c->stream);
-        else CK(cudaMemsetAsync(&b.bump->fine_cursor[0], 0, sizeof(uint32_t) * GG_FINE_PARTS, c->stream));
-        if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
-        if (!reuse) CK(cudaMemcpyAsync(c->h_bump, c->bump.p, sizeof(GGBump), cudaMemcpyDeviceToHost, c->stream));
-        // fine is launched optimistically; if a stage overflowed its inputs are in-bounds garbage and the pass is redone
         const GGFineRange full = fine_range(c);
         const uint32_t rows_t = full.row1 - full.row0;
-        uint32_t parts = (host_dst && rows_t >= 4 * GG_FINE_PARTS) ? GG_FINE_PARTS : 1u;
-        const uint32_t col0 = std::min(full.px0 * 2 * GG_TILE_W, c->width), col1 = std::min(full.px1 * 2 * GG_TILE_W, c->width);
-        for (uint32_t k = 0; k < parts && rows_t; k++) {
-            GGFineRange rg = full;
-            rg.row0 = full.row0 + (uint32_t)((uint64_t)rows_t * k / parts); rg.row1 = full.row0 + (uint32_t)((uint64_t)rows_t * (k + 1) / parts);
-            gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, rg, k, c->mirrors);
-            if (host_dst) {
-                uint32_t y0 = rg.row0 * GG_TILE_H, y1 = std::min(rg.row1 * GG_TILE_H, std::min(c->band_y1 * GG_TILE_H, c->height) - c->band_y0 * GG_TILE_H);
-                if (y1 > y0 && col1 > col0) {
-                    CK(cudaEventRecord(c->ev_part[k], c->stream));
-                    CK(cudaStreamWaitEvent(c->copy_stream, c->ev_part[k], 0));
-                    CK(cudaMemcpy2DAsync(host_dst + (size_t)y0 * host_stride + (size_t)col0 * px_bytes, host_stride,
-                                         dst_device + (size_t)y0 * stride + (size_t)col0 * px_bytes, stride, (size_t)(col1 - col0) * px_bytes, y1 - y0,
-                                         cudaMemcpyDeviceToHost, c->copy_stream));
+        const uint32_t parts = (host_dst && rows_t >= 4 * GG_FINE_PARTS) ? GG_FINE_PARTS : 1u;
+        uint32_t launches = 0;
+        // everything one pass puts on the stream
+        auto enqueue = [&]() -> int {
+            launches = 0;
+            if (c->timing) CK(cudaEventRecord(c->ev[0], c->stream));
+            if (!reuse) launches += gg_launch_front(c->cfg, b, c->stream);
+            if (c->timing) CK(cudaEventRecord(c->ev[1], c->stream));
+            if (!reuse) launches += gg_launch_binning(c->cfg, b, c->stream);
+            if (c->timing) CK(cudaEventRecord(c->ev[2], c->stream));
+            if (!reuse) launches += gg_launch_coarse(c->cfg, b, c->stream);
+            else CK(cudaMemsetAsync(&b.bump->fine_cursor[0], 0, sizeof(uint32_t) * GG_FINE_PARTS, c->stream));
+            if (c->timing) CK(cudaEventRecord(c->ev[3], c->stream));
+            if (!reuse) CK(cudaMemcpyAsync(c->h_bump, c->bump.p, sizeof(GGBump), cudaMemcpyDeviceToHost, c->stream));
+            // fine is launched optimistically; if a stage overflowed its inputs are in-bounds garbage and the pass is redone
+            const uint32_t col0 = std::min(full.px0 * 2 * GG_TILE_W, c->width), col1 = std::min(full.px1 * 2 * GG_TILE_W, c->width);
+            for (uint32_t k = 0; k < parts && rows_t; k++) {
+                GGFineRange rg = full;
+                rg.row0 = full.row0 + (uint32_t)((uint64_t)rows_t * k / parts); rg.row1 = full.row0 + (uint32_t)((uint64_t)rows_t * (k + 1) / parts);
+                gg_launch_fine(c->cfg, b, dst_device, stride, c->stream, rg, k, c->mirrors);
+                if (host_dst) {
+                    uint32_t y0 = rg.row0 * GG_TILE_H, y1 = std::min(rg.row1 * GG_TILE_H, std::min(c->band_y1 * GG_TILE_H, c->height) - c->band_y0 * GG_TILE_H);
+                    if (y1 > y0 && col1 > col0) {
+                        CK(cudaEventRecord(c->ev_part[k], c->stream));
+                        CK(cudaStreamWaitEvent(c->copy_stream, c->ev_part[k], 0));
+                        CK(cudaMemcpy2DAsync(host_dst + (size_t)y0 * host_stride + (size_t)col0 * px_bytes, host_stride,
+                                             dst_device + (size_t)y0 * stride + (size_t)col0 * px_bytes, stride, (size_t)(col1 - col0) * px_bytes, y1 - y0,
+                                             cudaMemcpyDeviceToHost, c->copy_stream));
+                    }
                 }
             }
+            if (host_dst) {   // the main stream owns the frame buffer again only after the copies
+                CK(cudaEventRecord(c->ev_copied, c->copy_stream));
+                CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
+            }
+            if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
+            return 0;
+        };
+        bool replayed = false;
+        if (c->graphs && !c->timing && !host_dst) {
+            Ctx::PassKey key;
+            memset(&key, 0, sizeof key);   // padding bytes take part in the comparison
+            key.cfg = c->cfg; key.b = b; key.dst = dst_device; key.stride = stride; key.rg = full; key.mir = c->mirrors; key.reuse = reuse ? 1u : 0u;
+            if (c->graph_exec && memcmp(&key, &c->graph_key, sizeof key) != 0) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+            if (!c->graph_exec) {
+                cudaGraph_t g = nullptr;
+                bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+                if (ok) {
+                    const int r = enqueue();
+                    ok = cudaStreamEndCapture(c->stream, &g) == cudaSuccess && r == 0 && g;
+                }
+                if (ok) ok = cudaGraphInstantiate(&c->graph_exec, g, 0) == cudaSuccess;
+                if (g) cudaGraphDestroy(g);
+                if (!ok) { cudaGetLastError(); c->graph_exec = nullptr; c->graphs = false; }   // this context goes on without graphs
+                else { memcpy(&c->graph_key, &key, sizeof key); c->graph_launches = launches; }
+            }
+            if (c->graph_exec) { CK(cudaGraphLaunch(c->graph_exec, c->stream)); replayed = true; launches = c->graph_launches; }
         }
-        if (host_dst) {   // the main stream owns the frame buffer again only after the copies
-            CK(cudaEventRecord(c->ev_copied, c->copy_stream));
-            CK(cudaStreamWaitEvent(c->stream, c->ev_copied, 0));
-        }
-        if (c->timing) CK(cudaEventRecord(c->ev[4], c->stream));
+        if (!replayed) { int r = enqueue(); if (r) return r; }
         c->stats.passes++;
         c->stats.kernel_launches += launches + (rows_t ? parts : 0u);
         CK(cudaStreamSynchronize(c->stream));
@@ -430,6 +463,7 @@ int ggcuda_create(int device, uint32_t flags, ggcuda_ctx** out) {
         return GGCUDA_ERR_CUDA;
     }
     c->stream = c->own_stream;
+    if (const char* ng = getenv("GGCUDA_NO_GRAPH")) c->graphs = !(ng[0] && ng[0] != '0');
     cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking);
     for (auto& ev : c->ev) cudaEventCreate(&ev);
     for (auto& ev : c->ev_part) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
@@ -450,6 +484,7 @@ void ggcuda_destroy(ggcuda_ctx* h) {
     c->pinned.clear();
     free_all(c);
     if (c->h_scene) cudaFreeHost(c->h_scene);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     if (c->h_bump) cudaFreeHost(c->h_bump);
     if (c->h_frame) cudaFreeHost(c->h_frame);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
