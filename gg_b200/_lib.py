@@ -20,7 +20,7 @@ SYMBOLS = [
     "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_render_device_multi", "ggcuda_get_stats", "ggcuda_set_timing",
     "ggcuda_debug_read", "ggcuda_pack_host", "ggcuda_begin_keyed", "ggcuda_set_dirty_rect", "ggcuda_register_target",
     "ggcuda_unregister_target", "ggcuda_comm_unique_id", "ggcuda_comm_init", "ggcuda_comm_destroy", "ggcuda_all_gather_bands",
-    "ggcuda_sync", "ggcuda_encoding_hash", "ggcuda_fill_path_gradient",
+    "ggcuda_sync", "ggcuda_encoding_hash", "ggcuda_fill_path_gradient", "ggcuda_add_image",
 ]
 
 LINE = np.dtype([("path_ix", "<u4"), ("p0", "<f4", 2), ("p1", "<f4", 2)])
@@ -79,6 +79,7 @@ def load():
     L.ggcuda_fill_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_int]
     L.ggcuda_stroke_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_double, C.c_int, C.c_int, C.c_double]
     L.ggcuda_fill_path_gradient.argtypes = [vp, vp, u32, vp, u32, C.c_int, vp, vp, u32, C.c_int, C.c_int]
+    L.ggcuda_add_image.argtypes = [vp, u32, u32, vp, vp]
     L.ggcuda_push_clip.argtypes = [vp, vp, u32, vp, u32]
     L.ggcuda_push_layer.argtypes = [vp, u32, C.c_float]
     L.ggcuda_pop.argtypes = [vp]
@@ -217,6 +218,14 @@ class Context:
         g[:len(geom)] = geom
         st = np.ascontiguousarray(stops, dtype=np.float64).reshape(-1, 5)
         self._ck(self.L.ggcuda_fill_path_gradient(self.h, _p(v), v.size, _p(c), c.size, int(kind), _p(g), _p(st), len(st), int(extend), int(fill_rule)))
+
+    def add_image(self, pixels):
+        """Register an image of this frame: (h, w, 4) uint8, premultiplied RGBA. Returns its index (TagImage refers to it)."""
+        a = np.ascontiguousarray(pixels, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[2] == 4
+        ix = C.c_uint32(0)
+        self._ck(self.L.ggcuda_add_image(self.h, a.shape[1], a.shape[0], _p(a), C.byref(ix)))
+        return int(ix.value)
 
     def stroke_path(self, verbs, coords, rgba_straight, width, cap=0, join=0, miter_limit=4.0):
         v = np.ascontiguousarray(verbs, dtype=np.uint8)

@@ -220,6 +220,8 @@ class CUDAAccelerator:
             if not resident:
                 self.ctx.begin(target.Width, target.Height)   # resident=False: always ingest, upload and run every stage
             try:
+                for im in getattr(enc, "images", ()):
+                    self.ctx.add_image(im)
                 self.ctx.add_encoding(*enc.streams())
             except GGCudaError as e:
                 if e.code == _lib.ERR_UNSUPPORTED:

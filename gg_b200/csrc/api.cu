@@ -608,6 +608,19 @@ int ggcuda_fill_path(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, cons
     GG_CATCH(c)
 }
 
+int ggcuda_add_image(ggcuda_ctx* h, uint32_t width, uint32_t height, const uint8_t* premul_rgba, uint32_t* index_out) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !premul_rgba) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    GG_NO_REUSE(c);
+    const int ix = c->scene.add_image(width, height, premul_rgba);
+    if (ix < 0) return fail(c, GGCUDA_ERR_INVALID, "bad image size (1..16384 per side)");
+    if (index_out) *index_out = (uint32_t)ix;
+    c->uploaded = false;
+    return 0;
+    GG_CATCH(c)
+}
+
 int ggcuda_fill_path_gradient(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
                               int kind, const double geom[6], const double* stops, uint32_t n_stops, int extend, int fill_rule) {
     Ctx* c = reinterpret_cast<Ctx*>(h);

@@ -486,6 +486,52 @@ __device__ __forceinline__ uint32_t composite_over_u8(uint32_t s, uint32_t d) {
     return o;
 }
 
+// TagImage at a pixel centre (scene/renderer.go:1093-1243 blitImageToTile + blitBilinearPixel / blitNearestPixel), float32
+// in the reference's order of operations: map the centre back into the image (the record holds the inverse affine), move
+// by half a texel, skip unless the 2 x 2 neighbourhood touches the image; on a texel centre take that texel (and only if
+// it is inside), otherwise blend four clamp-to-edge texels in premultiplied space. Returns the premultiplied colour in
+// [0, 1]; *cov = 1 where the reference draws, 0 where it leaves the pixel alone. Out of line like grad_color.
+__device__ __noinline__ float4 image_color(const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ g, float fx, float fy, int px, int py, float* cov) {
+    *cov = 0.0f;
+    const float4 none = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    if (px < (int)g[11] || py < (int)g[12] || px > (int)g[13] || py > (int)g[14]) return none;   // the box the reference iterates over
+    const int w = (int)g[1], h = (int)g[2];
+    const uint32_t* tex = gtab + g[3];
+    float sx = __uint_as_float(g[5]) * fx + __uint_as_float(g[6]) * fy + __uint_as_float(g[7]);
+    float sy = __uint_as_float(g[8]) * fx + __uint_as_float(g[9]) * fy + __uint_as_float(g[10]);
+    sx -= 0.5f; sy -= 0.5f;
+    const float flx = floorf(sx), fly = floorf(sy);
+    if (!(fabsf(flx) < 1.0e9f) || !(fabsf(fly) < 1.0e9f)) return none;
+    const int ix0 = (int)flx, iy0 = (int)fly;
+    if (ix0 + 1 < 0 || iy0 + 1 < 0 || ix0 >= w || iy0 >= h) return none;
+    const float wx = sx - flx, wy = sy - fly;
+    if (wx == 0.0f && wy == 0.0f) {
+        if (ix0 < 0 || iy0 < 0) return none;
+        const uint32_t t = tex[iy0 * w + ix0];
+        if ((t >> 24) == 0u) return none;
+        *cov = 1.0f;
+        return unpack_rgba8(t);
+    }
+    const int cx0 = min(max(ix0, 0), w - 1), cx1 = min(max(ix0 + 1, 0), w - 1), cy0 = min(max(iy0, 0), h - 1), cy1 = min(max(iy0 + 1, 0), h - 1);
+    uint32_t t00 = tex[cy0 * w + cx0], t10 = tex[cy0 * w + cx1], t01 = tex[cy1 * w + cx0], t11 = tex[cy1 * w + cx1];
+    if ((t00 >> 24) == 0u) t00 = 0u;   // fetchPremul: a texel without alpha counts as (0, 0, 0, 0)
+    if ((t10 >> 24) == 0u) t10 = 0u;
+    if ((t01 >> 24) == 0u) t01 = 0u;
+    if ((t11 >> 24) == 0u) t11 = 0u;
+    const float ifx = 1.0f - wx, ify = 1.0f - wy;
+    const float w00 = ifx * ify, w10 = wx * ify, w01 = ifx * wy, w11 = wx * wy;
+    float s[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float p00 = (float)((t00 >> (8 * k)) & 0xffu), p10 = (float)((t10 >> (8 * k)) & 0xffu);
+        const float p01 = (float)((t01 >> (8 * k)) & 0xffu), p11 = (float)((t11 >> (8 * k)) & 0xffu);
+        s[k] = p00 * w00 + p10 * w10 + p01 * w01 + p11 * w11;
+    }
+    if (s[3] < 0.5f / 255.0f) return none;
+    *cov = 1.0f;
+    return make_float4(s[0] / 255.0f, s[1] / 255.0f, s[2] / 255.0f, s[3] / 255.0f);
+}
+
 // gg's brush colour at a pixel centre (gradient_linear.go:52-66, gradient_radial.go computeTSimple, gradient.go:42-131), in gg's
 // own arithmetic: float64 geometry and stop search, float32 interpolation in linear light, sRGB on the way out; only the last
 // step differs from the Go code (powf instead of float64 math.Pow: < 1e-6 on a colour in [0, 1]). The stops carry their
@@ -690,8 +736,10 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                     }
 #pragma unroll
                     for (int i = 0; i < PX; i++) {
-                        const float4 c = grad_color(gtab, g, (float)(tx * GG_TILE_W + xb + i) + 0.5f, fy);   // premultiplied
-                        const float cov = area[i];
+                        float cov = area[i];
+                        const int ipx = (int)(tx * GG_TILE_W + xb) + i;
+                        const float4 c = kind == 3u ? image_color(gtab, g, (float)ipx + 0.5f, fy, ipx, (int)py, &cov)    // TagImage: its own coverage
+                                                    : grad_color(gtab, g, (float)ipx + 0.5f, fy);                       // premultiplied
                         rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
                         rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
                         rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);

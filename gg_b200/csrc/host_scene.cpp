@@ -57,7 +57,7 @@ void HostScene::clear(uint32_t w, uint32_t h) {
     clip_aux.clear(); clip_stack.clear(); clip_kind.clear(); clip_bb.clear();
     next_clip_bb[0] = next_clip_bb[1] = -3.0e38f; next_clip_bb[2] = next_clip_bb[3] = 3.0e38f;
     n_paths = n_clips = n_seg_tags = n_implicit = n_culled = 0;
-    grad_recs.clear(); grad_stops.clear(); n_gradients = 0;
+    grad_recs.clear(); grad_stops.clear(); images.clear(); image_words.clear(); n_gradients = 0;
     have_transform = false; in_path = false; has_move = false;
 }
 
@@ -362,6 +362,54 @@ void HostScene::draw_sdf_round_rect(float cx, float cy, float half_w, float half
     clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
     clip_aux.push_back(0);
 }
+int HostScene::add_image(uint32_t w, uint32_t h, const uint8_t* premul_rgba) {
+    if (w == 0 || h == 0 || w > 16384 || h > 16384 || !premul_rgba) return -1;
+    HostImage im = {w, h, image_words.size()};
+    image_words.resize(im.off + (size_t)w * h);
+    memcpy(image_words.data() + im.off, premul_rgba, (size_t)w * h * 4);
+    images.push_back(im);
+    return (int)images.size() - 1;
+}
+bool HostScene::draw_image(uint32_t index, const float t[6]) {
+    if (index >= images.size()) return false;
+    const HostImage& im = images[index];
+    // inverse affine and the canvas-space box of the image, in float32 and in the reference's order of operations
+    // (renderer.go:1104-1137); a degenerate transform draws nothing
+    const float A = t[0], B = t[1], C = t[2], D = t[3], E = t[4], F = t[5];
+    const float det = A * E - B * D;
+    if (det == 0.0f || !(det == det)) return true;
+    const float inv_det = 1.0f / det;
+    const float inv[6] = {E * inv_det, -B * inv_det, (B * F - E * C) * inv_det, -D * inv_det, A * inv_det, (D * C - A * F) * inv_det};
+    const float cw = (float)im.w, ch = (float)im.h;
+    const float cx[4] = {0, cw, cw, 0}, cy[4] = {0, 0, ch, ch};
+    float x0 = 0, y0 = 0, x1 = 0, y1 = 0;   // the reference seeds the box with the UNtransformed corner (0, 0)
+    for (int k = 0; k < 4; k++) {
+        const float px = A * cx[k] + B * cy[k] + C, py = D * cx[k] + E * cy[k] + F;
+        x0 = std::min(x0, px); y0 = std::min(y0, py); x1 = std::max(x1, px); y1 = std::max(y1, py);
+    }
+    auto trunc_i = [](float v) { return v >= 2147483520.0f ? 2147483647 : (v <= -2147483520.0f ? -2147483647 : (int32_t)v); };
+    const int32_t bx0 = trunc_i(x0), by0 = trunc_i(y0), bx1 = trunc_i(x1), by1 = trunc_i(y1);
+    // pixels [bx0, bx1] x [by0, by1], clamped to the canvas: the rectangle that bins the tiles
+    const float rx0 = (float)std::max(bx0, 0), ry0 = (float)std::max(by0, 0);
+    const float rx1 = (float)std::min<int64_t>((int64_t)bx1 + 1, width), ry1 = (float)std::min<int64_t>((int64_t)by1 + 1, height);
+    begin_path(IDENTITY, false);
+    if (rx1 > rx0 && ry1 > ry0) {
+        const uint8_t v[5] = {GGCUDA_VERB_MOVE, GGCUDA_VERB_LINE, GGCUDA_VERB_LINE, GGCUDA_VERB_LINE, GGCUDA_VERB_CLOSE};
+        const double c[8] = {rx0, ry0, rx1, ry0, rx1, ry1, rx0, ry1};
+        add_verbs(v, 5, c, 8);
+    }
+    end_path();
+    uint32_t rec[16] = {0};
+    rec[0] = 3u; rec[1] = im.w; rec[2] = im.h; rec[3] = (uint32_t)im.off;
+    memcpy(rec + 5, inv, sizeof inv);
+    rec[11] = (uint32_t)bx0; rec[12] = (uint32_t)by0; rec[13] = (uint32_t)bx1; rec[14] = (uint32_t)by1;
+    grad_recs.insert(grad_recs.end(), rec, rec + 16);
+    draw_tags.push_back(DT_GRADIENT);
+    draw_data.push_back(n_gradients++);
+    clip_aux.push_back(clip_stack.empty() ? -1 : clip_stack.back());
+    clip_aux.push_back(0);
+    return true;
+}
 void HostScene::begin_clip(uint32_t blend_word, float alpha, uint8_t kind) {
     int32_t d = (int32_t)draw_tags.size();
     draw_tags.push_back(DT_BEGIN_CLIP);
@@ -464,14 +512,16 @@ void HostScene::pack(uint32_t* out, Layout* L, uint32_t band_tiles) const {   //
     if (!clip_aux.empty()) memcpy(out + L->clip_aux_base, clip_aux.data(), 4 * clip_aux.size());
     uint32_t* tail = out + off;   // device-resident element counts for the scan primitive
     tail[0] = padded; tail[1] = L->n_draws; tail[2] = L->n_tag_bytes; tail[3] = n_paths; tail[4] = band_tiles;
-    // gradient table behind the tail: records | stops; tail[5] = its word offset, tail[6] = number of gradients
-    tail[5] = off + 8; tail[6] = n_gradients; tail[7] = 0;
+    // gradient table behind the tail: records | stops | image pixels; tail[5] = its word offset, tail[6] = number of records, tail[7] = its words
+    tail[5] = off + 8; tail[6] = n_gradients; tail[7] = (uint32_t)gradient_words();
     uint32_t* gt = out + off + 8;
     if (!grad_recs.empty()) {
         const uint32_t stops_base = (uint32_t)grad_recs.size();
         memcpy(gt, grad_recs.data(), 4 * grad_recs.size());
-        for (uint32_t g = 0; g < n_gradients; g++) gt[16 * g + 3] += stops_base;   // offsets relative to the table
-        memcpy(gt + stops_base, grad_stops.data(), 4 * grad_stops.size());
+        const uint32_t images_base = stops_base + (uint32_t)grad_stops.size();
+        for (uint32_t g = 0; g < n_gradients; g++) gt[16 * g + 3] += gt[16 * g] == 3u ? images_base : stops_base;   // offsets relative to the table
+        if (!grad_stops.empty()) memcpy(gt + stops_base, grad_stops.data(), 4 * grad_stops.size());
+        if (!image_words.empty()) memcpy(gt + images_base, image_words.data(), 4 * image_words.size());
     }
 }
 
@@ -629,6 +679,7 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             case ST_PUSH_LAYER: di += 2; break;
             case ST_BEGIN_CLIP: active = false; break;
             case ST_BRUSH: pi += 4; break;
+            case ST_IMAGE: di += 1; ti++; break;
             default: break;
             }
         }
@@ -694,7 +745,8 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             case ST_POP_LAYER: case ST_END_CLIP: break;
             case ST_BEGIN_CLIP: active = false; break;
             case ST_BRUSH: pi += 4; break;
-            default: ok = false; break;   // TagImage / TagText / unknown: the sequential walk reports it
+            case ST_IMAGE: if (di + 1 > n_dd) ok = false; else { di += 1; ti++; } break;
+            default: ok = false; break;   // TagText / unknown: the sequential walk reports it
             }
         }
         const unsigned n_chunks = (unsigned)std::min<size_t>(4 * IngestPool::get().workers(), mt_jobs.size() / 64 + 1);
@@ -877,7 +929,17 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             end_clip(0);
             break;
         case ST_BRUSH: pi += 4; break;
-        case ST_IMAGE: *msg = "encoding: TagImage is not supported by the CUDA path"; return GGCUDA_ERR_UNSUPPORTED;
+        case ST_IMAGE: {
+            // the image's affine is the next entry of the transform stream (EncodeImage appends one without a TagTransform,
+            // decoder.go:318-335); it does not become the current transform
+            if (di + 1 > n_dd) { *msg = "encoding: draw stream underrun"; return GGCUDA_ERR_INVALID; }
+            flush_layer();
+            const uint32_t index = dd[di]; di += 1;
+            const float* it = ti + 1 <= n_tr ? tr + 6 * ti : IDENTITY;
+            ti++;
+            if (index < images.size()) draw_image(index, it);   // an unknown index draws nothing (renderer.go:773)
+            path_active = false;
+        } break;
         case ST_TEXT: *msg = "encoding: TagText must be resolved to outlines before the CUDA path"; return GGCUDA_ERR_UNSUPPORTED;
         default: *msg = "encoding: unknown tag"; return GGCUDA_ERR_INVALID;
         }

@@ -81,11 +81,21 @@ struct HostScene {
     // distance field with a 0.7 px smoothstep, not from the outline's area. Record kind 2 of the same table: cx, cy, half width,
     // half height, corner radius (device space), the premultiplied RGBA8 colour's bits. The path just ended only bins tiles.
     void draw_sdf_round_rect(float cx, float cy, float half_w, float half_h, float radius, uint32_t rgba_premul);
+    // TagImage (scene/renderer.go:1093-1243 blitImageToTile): images are registered per frame (premultiplied RGBA8, the
+    // bytes scene.Image.Data holds), drawn by index under their own affine. Record kind 3 of the same table: width, height,
+    // word offset of the pixels (behind the stops), the INVERSE affine (float32, computed as the reference does), the
+    // truncated device-space bounding box the reference iterates over. The path just ended (that box) only bins tiles.
+    struct HostImage { uint32_t w, h; size_t off; };
+    std::vector<HostImage> images;
+    std::vector<uint32_t> image_words;
+    int add_image(uint32_t w, uint32_t h, const uint8_t* premul_rgba);   // index of the image, -1 if the size is unusable
+    bool draw_image(uint32_t index, const float t[6]);                   // false: no such image
     // gradient table words: per gradient a 16-word record {kind, extend, n_stops, stops offset, 0, 6 raw geometry floats, pad},
-    // then all stops, sorted per gradient, 8 floats each {offset, r, g, b, a (straight sRGB), linear-light r, g, b}
+    // then all stops, sorted per gradient, 8 floats each {offset, r, g, b, a (straight sRGB), linear-light r, g, b}, then the
+    // pixels of the frame's images (one word per pixel)
     std::vector<uint32_t> grad_recs; std::vector<float> grad_stops;
     uint32_t n_gradients = 0;
-    size_t gradient_words() const { return grad_recs.size() + grad_stops.size(); }
+    size_t gradient_words() const { return grad_recs.size() + grad_stops.size() + image_words.size(); }
     void begin_clip(uint32_t blend_word, float alpha, uint8_t kind);   // DrawTagBeginClip for the path just ended
     void begin_layer(uint32_t blend_word, float alpha);   // PushLayer: clip rectangle carrying blend + alpha
     bool end_clip(uint8_t kind);                           // DrawTagEndClip (+ dummy path); false if nothing to pop

@@ -42,6 +42,7 @@ class Encoding:
         self.transforms = []     # 6-tuples
         self.brushes = []        # (r, g, b, a) float64 straight alpha (solid brushes only)
         self._chunks = []        # pre-built numpy chunks appended by the bulk encoders
+        self.images = []         # (h, w, 4) uint8 arrays, premultiplied RGBA (scene.Image.Data), referenced by TagImage
 
     def EncodeTransform(self, t):
         self.tags.append(TagTransform)
@@ -71,6 +72,17 @@ class Encoding:
         self.draw_data += [len(self.brushes), int(style)]
         self.brushes.append(tuple(color))
         self.path_data += [float(np.float32(v)) for v in (*rect, rx, ry)]
+
+    def EncodeImage(self, image_index, transform):
+        """EncodeImage (encoding.go:656-661): the image's affine goes to the transform stream WITHOUT a TagTransform."""
+        self.tags.append(TagImage)
+        self.draw_data.append(int(image_index))
+        self.transforms.append(tuple(float(x) for x in transform))
+
+    def AddImage(self, pixels):
+        """Register premultiplied RGBA8 pixels (h, w, 4); returns the index EncodeImage takes."""
+        self.images.append(np.ascontiguousarray(pixels, dtype=np.uint8))
+        return len(self.images) - 1
 
     def EncodePushLayer(self, blend, alpha):
         self.tags.append(TagPushLayer)
@@ -113,7 +125,11 @@ def _hash(enc, with_brushes):
     k = (id(s[0]), with_brushes)
     if k not in memo:
         memo.clear()
-        memo[k] = _lib.encoding_hash(s[0], s[1], s[2], s[3], s[4] if with_brushes else None)
+        hv = _lib.encoding_hash(s[0], s[1], s[2], s[3], s[4] if with_brushes else None)
+        if with_brushes:   # ... and over the pixels of the images the encoding refers to
+            for im in getattr(enc, "images", ()):
+                hv = (hv * 0x100000001B3 ^ _lib.encoding_hash(im.reshape(-1), np.asarray(im.shape[:2], np.float32), [], [], None)) & 0xFFFFFFFFFFFFFFFF
+        memo[k] = hv
     return memo[k]
 
 

@@ -87,6 +87,12 @@ GGCUDA_API int ggcuda_begin_keyed(ggcuda_ctx* ctx, uint32_t width, uint32_t heig
 GGCUDA_API uint64_t ggcuda_encoding_hash(const uint8_t* tags, size_t n_tags, const float* path_data, size_t n_path_data,
                                          const uint32_t* draw_data, size_t n_draw_data, const float* transforms, size_t n_transforms,
                                          const double* brushes_rgba, size_t n_brushes);
+/* Register an image of the frame being built (scene.Image, scene/scene.go:769-779: premultiplied RGBA8, row-major, the bytes
+ * gg.Pixmap.ToImage() produces). Images are numbered from 0 in the order they are added after ggcuda_begin; TagImage entries
+ * of an encoding added afterwards refer to them by that number (scene/encoding.go:656-661) and are drawn as the CPU tile
+ * renderer draws them (scene/renderer.go:1093-1243: inverse affine, bilinear in premultiplied space with clamp-to-edge,
+ * the nearest texel when the sample falls on a texel centre, source-over). The pixels are copied. */
+GGCUDA_API int ggcuda_add_image(ggcuda_ctx* ctx, uint32_t width, uint32_t height, const uint8_t* premul_rgba, uint32_t* index_out);
 /* Restrict the next render (and its read-back) to the 16x16 tiles touching the pixel rectangle [x0, x1) x [y0, y1);
  * everything else in dst is left as it is. Applies to one render. */
 GGCUDA_API int ggcuda_set_dirty_rect(ggcuda_ctx* ctx, uint32_t x0, uint32_t y0, uint32_t x1, uint32_t y1);

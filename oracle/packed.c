@@ -177,8 +177,9 @@ static ot_coarse *coarse_from_packed(const uint32_t *scene, const uint32_t *L, i
         if (ng) {
             const uint32_t *gt = scene + tail[5];
             uint32_t words = 16 * ng;
+            if (tail[7] > words) words = tail[7];   /* the table's size: records | stops | image pixels */
             for (uint32_t g = 0; g < ng; g++) {
-                uint32_t e1 = gt[16 * g] == 2u ? 0 : gt[16 * g + 3] + 8 * gt[16 * g + 2];   /* 8 floats per stop; SDF records have none */
+                uint32_t e1 = gt[16 * g] >= 2u ? 0 : gt[16 * g + 3] + 8 * gt[16 * g + 2];   /* 8 floats per stop; SDF records have none */
                 if (e1 > words) words = e1;
             }
             c->gtab = (uint32_t *)malloc(4 * (size_t)words);

@@ -1522,6 +1522,52 @@ void ot_fine_tile_at(const uint32_t *cmds, uint32_t n_words, const ot_path_segme
                 }
                 break;
             }
+            if (gtab && gtab[16 * gi] == 3u) {
+                /* TagImage: blitImageToTile (scene/renderer.go:1093-1243), float32 in its order of operations; the pixmap of the
+                 * reference holds bytes and rounds after every draw, this one composites in float32 like every other command */
+                const uint32_t *g = gtab + 16 * gi;
+                const int iw = (int)g[1], ih = (int)g[2];
+                const uint32_t *tex = gtab + g[3];
+                const float iA = bits_f32(g[5]), iB = bits_f32(g[6]), iC = bits_f32(g[7]), iD = bits_f32(g[8]), iE = bits_f32(g[9]), iF = bits_f32(g[10]);
+                for (int i = 0; i < PC; i++) {
+                    const int px = origin_x + i % TILE_W, py = origin_y + i / TILE_W;
+                    if (px < (int32_t)g[11] || py < (int32_t)g[12] || px > (int32_t)g[13] || py > (int32_t)g[14]) continue;
+                    const float cxp = (float)px + 0.5f, cyp = (float)py + 0.5f;
+                    float sx = iA * cxp + iB * cyp + iC, sy = iD * cxp + iE * cyp + iF;
+                    sx -= 0.5f; sy -= 0.5f;
+                    const float flx = floorf(sx), fly = floorf(sy);
+                    if (!(fabsf(flx) < 1.0e9f) || !(fabsf(fly) < 1.0e9f)) continue;
+                    const int ix0 = (int)flx, iy0 = (int)fly;
+                    if (ix0 + 1 < 0 || iy0 + 1 < 0 || ix0 >= iw || iy0 >= ih) continue;
+                    const float wx = sx - flx, wy = sy - fly;
+                    float s4[4];
+                    if (wx == 0.0f && wy == 0.0f) {
+                        if (ix0 < 0 || iy0 < 0) continue;
+                        const uint32_t t = tex[iy0 * iw + ix0];
+                        if ((t >> 24) == 0u) continue;
+                        for (int k = 0; k < 4; k++) s4[k] = (float)((t >> (8 * k)) & 0xffu) / 255.0f;
+                    } else {
+                        const int cx0 = ix0 < 0 ? 0 : (ix0 > iw - 1 ? iw - 1 : ix0), cx1 = ix0 + 1 < 0 ? 0 : (ix0 + 1 > iw - 1 ? iw - 1 : ix0 + 1);
+                        const int cy0 = iy0 < 0 ? 0 : (iy0 > ih - 1 ? ih - 1 : iy0), cy1 = iy0 + 1 < 0 ? 0 : (iy0 + 1 > ih - 1 ? ih - 1 : iy0 + 1);
+                        uint32_t t00 = tex[cy0 * iw + cx0], t10 = tex[cy0 * iw + cx1], t01 = tex[cy1 * iw + cx0], t11 = tex[cy1 * iw + cx1];
+                        if ((t00 >> 24) == 0u) t00 = 0u;
+                        if ((t10 >> 24) == 0u) t10 = 0u;
+                        if ((t01 >> 24) == 0u) t01 = 0u;
+                        if ((t11 >> 24) == 0u) t11 = 0u;
+                        const float ifx = 1.0f - wx, ify = 1.0f - wy;
+                        const float w00 = ifx * ify, w10 = wx * ify, w01 = ifx * wy, w11 = wx * wy;
+                        for (int k = 0; k < 4; k++)
+                            s4[k] = (float)((t00 >> (8 * k)) & 0xffu) * w00 + (float)((t10 >> (8 * k)) & 0xffu) * w10 +
+                                    (float)((t01 >> (8 * k)) & 0xffu) * w01 + (float)((t11 >> (8 * k)) & 0xffu) * w11;
+                        if (s4[3] < 0.5f / 255.0f) continue;
+                        for (int k = 0; k < 4; k++) s4[k] = s4[k] / 255.0f;
+                    }
+                    const float inv = 1.0f - s4[3];
+                    rgba[i][0] = rgba[i][0] * inv + s4[0]; rgba[i][1] = rgba[i][1] * inv + s4[1];
+                    rgba[i][2] = rgba[i][2] * inv + s4[2]; rgba[i][3] = rgba[i][3] * inv + s4[3];
+                }
+                break;
+            }
             for (int i = 0; i < PC; i++) {
                 float c[4] = {0, 0, 0, 0};
                 if (gtab) og_color_at(gtab, gi, (double)(origin_x + i % TILE_W) + 0.5, (double)(origin_y + i / TILE_W) + 0.5, c);

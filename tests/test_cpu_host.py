@@ -147,8 +147,11 @@ def test_unsupported_tags_are_reported():
     c = _lib.Context(-1)
     c.begin(64, 64)
     with pytest.raises(_lib.GGCudaError) as e:
-        c.add_encoding(np.array([S.TagImage], np.uint8), [], [0], [1, 0, 0, 0, 1, 0], [])
+        c.add_encoding(np.array([S.TagText], np.uint8), [], [0], [1, 0, 0, 0, 1, 0], [])
     assert e.value.code == _lib.ERR_UNSUPPORTED     # the Go binding maps this to gg.ErrFallbackToCPU
+    c.begin(64, 64)
+    c.add_encoding(np.array([S.TagImage], np.uint8), [], [0], [1, 0, 0, 0, 1, 0], [])   # an image that was never registered: nothing drawn
+    assert c.pack_host()[1]["n_draws"] == 0
     with pytest.raises(_lib.GGCudaError) as e:
         c.add_encoding(np.array([S.TagFill], np.uint8), [], [], [], [])
     assert e.value.code == _lib.ERR_INVALID         # stream underrun

@@ -619,3 +619,146 @@ def test_round_rect_rotated_falls_back_to_the_outline():
     assert words[int(lay["n_scene_words"]):][6] == 0
     out, _ = T.render_packed(words, lay, 128, 128, (0, 0, 0, 0), 1)
     assert out[..., 3].max() == 255
+
+
+# ---- TagImage: the oracle's image command against scene/renderer.go:1093-1243 restated in numpy, bytes and all ----
+def _ref_blit_image(pm, img, t):
+    """blitImageToTile + blitBilinearPixel + blitNearestPixel on a whole-canvas premultiplied RGBA8 pixmap (tile = canvas)."""
+    f = np.float32
+    H, W = pm.shape[:2]
+    ih, iw = img.shape[:2]
+    A, B, C_, D, E, F = (f(v) for v in t)
+    det = A * E - B * D
+    if det == 0:
+        return
+    inv_det = f(1.0) / det
+    iA, iB, iC = E * inv_det, -B * inv_det, (B * F - E * C_) * inv_det
+    iD, iE, iF = -D * inv_det, A * inv_det, (D * C_ - A * F) * inv_det
+    xs, ys = [f(0)], [f(0)]                                  # the box is seeded with the untransformed (0, 0)
+    for cx, cy in ((0, 0), (iw, 0), (iw, ih), (0, ih)):
+        xs.append(A * f(cx) + B * f(cy) + C_)
+        ys.append(D * f(cx) + E * f(cy) + F)
+    sx0, sy0 = max(int(min(xs)), 0), max(int(min(ys)), 0)
+    ex, ey = min(int(max(xs)) + 1, W), min(int(max(ys)) + 1, H)
+    cb = lambda v: 0 if v <= 0 else (255 if v >= 255 else int(f(v) + f(0.5)))   # noqa: E731  clampByte
+    for py in range(sy0, ey):
+        cyp = f(py) + f(0.5)
+        for px in range(sx0, ex):
+            cxp = f(px) + f(0.5)
+            sx = iA * cxp + iB * cyp + iC - f(0.5)
+            sy = iD * cxp + iE * cyp + iF - f(0.5)
+            flx, fly = np.floor(sx), np.floor(sy)
+            ix0, iy0 = int(flx), int(fly)
+            if ix0 + 1 < 0 or iy0 + 1 < 0 or ix0 >= iw or iy0 >= ih:
+                continue
+            wx, wy = sx - flx, sy - fly
+            d = pm[py, px]
+            if wx == 0 and wy == 0:
+                if 0 <= ix0 < iw and 0 <= iy0 < ih:
+                    s = img[iy0, ix0]
+                    sa = int(s[3])
+                    if sa == 0:
+                        continue
+                    if sa == 255:
+                        d[:3] = s[:3]; d[3] = 255
+                    else:
+                        inv = 255 - sa
+                        for k in range(4):
+                            d[k] = (int(s[k]) + (int(d[k]) * inv + 127) // 255) & 0xFF
+                continue
+            cx0, cx1 = min(max(ix0, 0), iw - 1), min(max(ix0 + 1, 0), iw - 1)
+            cy0, cy1 = min(max(iy0, 0), ih - 1), min(max(iy0 + 1, 0), ih - 1)
+            tex = [img[cy0, cx0], img[cy0, cx1], img[cy1, cx0], img[cy1, cx1]]
+            tex = [np.zeros(4, f) if p[3] == 0 else p.astype(f) for p in tex]
+            ifx, ify = f(1) - wx, f(1) - wy
+            wts = [ifx * ify, wx * ify, ifx * wy, wx * wy]
+            s = [tex[0][k] * wts[0] + tex[1][k] * wts[1] + tex[2][k] * wts[2] + tex[3][k] * wts[3] for k in range(4)]
+            if s[3] < f(0.5 / 255.0):
+                continue
+            inv = f(1) - s[3] / f(255)
+            for k in range(4):
+                d[k] = cb(s[k] + f(d[k]) * inv)
+
+
+def _test_image(h, w, seed):
+    rng = np.random.default_rng(seed)
+    a = rng.integers(0, 256, (h, w, 1)).astype(np.float32)
+    a[rng.random((h, w, 1)) < 0.15] = 0          # transparent holes (fetchPremul's special case)
+    a[rng.random((h, w, 1)) < 0.3] = 255
+    rgb = rng.integers(0, 256, (h, w, 3)).astype(np.float32)
+    return np.concatenate([np.floor(rgb * a / 255.0), a], axis=2).astype(np.uint8)   # premultiplied: colour <= alpha
+
+
+@pytest.mark.parametrize("t", [(1, 0, 10, 0, 1, 7), (1, 0, 10.5, 0, 1, 7.25), (2.5, 0, 3, 0, 1.75, 2), (0.8, -0.6, 30, 0.6, 0.8, 5),
+                               (-1, 0, 60, 0, 1, 4), (0.3, 0, 20, 0, 0.4, 20), (1, 0, -6, 0, 1, -5)])
+def test_image_matches_reference_blit(t):
+    """One image over an opaque and a translucent fill: every pixel within 1/255 of the reference's byte arithmetic (the
+    nearest-texel path on integer translations, bilinear with clamp-to-edge otherwise, the half-texel border, holes)."""
+    from gg_b200 import _lib, scene as S
+    W, H = 96, 64
+    img = _test_image(14, 20, 5)
+    enc = S.Encoding()
+    enc.EncodeTransform(S.IDENTITY)
+    enc.EncodePath(*S.rect_verbs_coords(0, 0, 50, 64)); enc.EncodeFill((0.2, 0.4, 0.6, 1.0))
+    enc.EncodePath(*S.rect_verbs_coords(40, 10, 96, 50)); enc.EncodeFill((1.0, 0.5, 0.0, 0.5))
+    ix = enc.AddImage(img)
+    enc.EncodeImage(ix, t)
+    enc.EncodeTransform((1, 0, 0, 0, 1, 0))     # the image's affine must not have become the current transform ...
+    enc.EncodePath(*S.rect_verbs_coords(90, 60, 96, 64)); enc.EncodeFill((0.0, 1.0, 0.0, 1.0))
+    c = _lib.Context(-1)
+    c.begin(W, H)
+    c.add_image(img)
+    c.add_encoding(*enc.streams())
+    words, lay = c.pack_host()
+    c.close()
+    out, _ = T.render_packed(words, lay, W, H, (0, 0, 0, 0), 1)
+    pm = np.zeros((H, W, 4), np.uint8)
+    pm[:, :50] = (51, 102, 153, 255)
+    q = lambda v: int(min(255.0, v * 255.0 + 0.5))   # noqa: E731
+    src = np.array([q(1.0) * q(0.5) / 255.0, q(0.5) * q(0.5) / 255.0, 0, q(0.5)], np.float32)   # premultiplied translucent orange
+    reg = pm[10:50, 40:96].astype(np.float32)
+    pm[10:50, 40:96] = np.floor(src + reg * (1 - src[3] / 255.0) + 0.5).astype(np.uint8)
+    base = pm.copy()
+    _ref_blit_image(pm, img, t)
+    pm[60:64, 90:96] = (0, 255, 0, 255)
+    base[60:64, 90:96] = (0, 255, 0, 255)
+    d = np.abs(out.astype(int) - pm.astype(int))
+    assert (pm != base).any(), "the reference drew nothing: bad test transform"
+    assert d.max() <= 1, (d.max(), np.argwhere(d.max(axis=2) > 1)[:5], out[tuple(np.argwhere(d.max(axis=2) > 1)[0])], pm[tuple(np.argwhere(d.max(axis=2) > 1)[0])])
+    # exactly the pixels the reference touches are touched
+    touched_ref = (pm != base).any(axis=2)
+    out0, _ = T.render_packed(*_pack_without_image(enc, W, H), W, H, (0, 0, 0, 0), 1)
+    touched = (out != out0).any(axis=2)
+    assert (touched & ~touched_ref).sum() <= touched_ref.sum() * 0.02 + 2 and (touched_ref & ~touched).sum() <= touched_ref.sum() * 0.02 + 2
+
+
+def _pack_without_image(enc, W, H):
+    from gg_b200 import _lib
+    c = _lib.Context(-1)
+    c.begin(W, H)
+    c.add_encoding(*enc.streams())     # no image registered: TagImage draws nothing (renderer.go:773)
+    words, lay = c.pack_host()
+    c.close()
+    return words, lay
+
+
+def test_image_stream_consumption_and_degenerates():
+    """TagImage consumes one drawData word and one transform; a singular affine, an unknown index draw nothing."""
+    from gg_b200 import _lib, scene as S
+    img = _test_image(4, 4, 1)
+    enc = S.Encoding()
+    enc.AddImage(img)
+    enc.EncodeImage(0, (0, 0, 5, 0, 0, 5))          # det == 0
+    enc.EncodeImage(7, (1, 0, 5, 0, 1, 5))          # no such image
+    enc.EncodeTransform((1, 0, 2, 0, 1, 3))
+    enc.EncodePath(*S.rect_verbs_coords(0, 0, 4, 4)); enc.EncodeFill((1, 1, 1, 1))
+    c = _lib.Context(-1)
+    c.begin(32, 32)
+    c.add_image(img)
+    c.add_encoding(*enc.streams())
+    words, lay = c.pack_host()
+    c.close()
+    out, _ = T.render_packed(words, lay, 32, 32, (0, 0, 0, 0), 1)
+    want = np.zeros((32, 32, 4), np.uint8)
+    want[3:7, 2:6] = 255                             # the rectangle under ITS transform, nothing else
+    assert (out == want).all()

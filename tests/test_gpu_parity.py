@@ -851,3 +851,60 @@ def test_round_rect_sdf_encoding(ctx):
     ref, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 4)
     d = np.abs(out.astype(int) - ref.astype(int))
     assert d.max() <= 1 and (d.max(axis=2) > 0).mean() < 0.01, (d.max(), (d.max(axis=2) > 0).mean())
+
+
+@pytest.mark.gpu
+def test_images_in_encoding(ctx):
+    """TagImage (scene/renderer.go:1093-1243) through the encoding entry: translated (nearest texel), scaled,
+    rotated and mirrored images over fills, inside a clip, under a later fill. PTCL word for word, pixels within 1/255 of the
+    oracle (the same float32 arithmetic on both sides)."""
+    from gg_b200 import scene as S
+    w, h = 420, 300
+    rng = np.random.default_rng(33)
+    enc = S.Encoding()
+    imgs = []
+    for k, (ih, iw) in enumerate([(24, 40), (64, 64), (7, 5), (120, 90)]):
+        a = rng.integers(0, 256, (ih, iw, 1)).astype(np.float32)
+        a[rng.random((ih, iw, 1)) < 0.2] = 0
+        a[rng.random((ih, iw, 1)) < 0.3] = 255
+        rgb = rng.integers(0, 256, (ih, iw, 3)).astype(np.float32)
+        imgs.append(np.concatenate([np.floor(rgb * a / 255.0), a], axis=2).astype(np.uint8))
+        enc.AddImage(imgs[-1])
+    enc.EncodeTransform(S.IDENTITY)
+    enc.EncodePath(*S.rect_verbs_coords(0, 0, w, h)); enc.EncodeFill((0.9, 0.9, 0.8, 1.0))
+    enc.EncodeImage(0, (1, 0, 30, 0, 1, 20))
+    enc.EncodeImage(1, (2.25, 0, 100.5, 0, 1.5, 10.25))
+    enc.EncodePath(*U.circle_path(np.float32(260), np.float32(170), np.float32(90)))
+    enc.EncodeBeginClip()
+    enc.EncodeImage(3, (0.8, -0.6, 200, 0.6, 0.8, 60))
+    enc.EncodeImage(2, (20, 0, 180, 0, 20, 120))
+    enc.EncodePath(*U.circle_path(np.float32(300), np.float32(200), np.float32(40))); enc.EncodeFill((0.1, 0.2, 0.9, 0.6))
+    enc.EncodeEndClip()
+    enc.EncodeImage(1, (-1, 0, 90, 0, 1, 200))
+    enc.EncodeImage(0, (1, 0, -20, 0, 1, 280))          # partly off the canvas
+    ctx.begin(w, h)
+    ctx.set_background((0, 0, 0, 0))
+    ctx.set_band(0, (h + 15) // 16)
+    for im in imgs:
+        ctx.add_image(im)
+    ctx.add_encoding(*enc.streams())
+    out = np.zeros((h, w, 4), dtype=np.uint8)
+    ctx.flush(out, flags=G.KEEP_SCENE)
+    oc = U.oracle_from_ctx(ctx, w, h)
+    rep = U.compare_stages_fast(ctx, oc, w, h)
+    assert (oc.ptcl_words == 6).sum() > 0 and rep["ptcl_words"] > 0
+    words = ctx.debug_read(G.BUF_SCENE, np.uint32)
+    lay = ctx.debug_read(G.BUF_LAYOUT, G.LAYOUT)[0]
+    from oracle import twin as T
+    ref, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), 4)
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d.max(axis=2) > 0).mean() < 0.01, (d.max(), (d.max(axis=2) > 0).mean())
+    assert (out[20:44, 30:70] != np.array([230, 230, 204, 255])).any()      # image 0 is there
+    # through the accelerator mirror (RenderEncoding registers the encoding's images), resident on the second call
+    from gg_b200 import accelerator as A
+    acc = A.CUDAAccelerator(); acc.Init()
+    tgt = A.GPURenderTarget(w, h)
+    acc.RenderEncoding(tgt, enc)
+    acc.RenderEncoding(tgt, enc)
+    assert acc.resident_hits == 1 and (tgt.Data == out).all()
+    acc.Close()
