@@ -110,6 +110,24 @@ class RadialGradientBrush(LinearGradientBrush):
         self.geom, self.stops, self.extend = (cx, cy, r0, r1), [], extend
 
 
+class SweepGradientBrush(LinearGradientBrush):
+    """gg.SweepGradientBrush (gradient_sweep.go): centre, start / end angle in radians."""
+
+    kind = 2
+
+    def __init__(self, cx, cy, start_angle, end_angle, extend=0):
+        self.geom, self.stops, self.extend = (cx, cy, start_angle, end_angle), [], extend
+
+
+class FocalRadialGradientBrush(LinearGradientBrush):
+    """gg.RadialGradientBrush with Focus != Center (gradient_radial.go:131-196)."""
+
+    kind = 3
+
+    def __init__(self, cx, cy, r0, r1, fx, fy, extend=0):
+        self.geom, self.stops, self.extend = (cx, cy, r0, r1, fx, fy), [], extend
+
+
 class GPURenderTarget:
     """accelerator.go:61-92, CPU read-back mode: Data is premultiplied RGBA8, Stride bytes per row."""
 

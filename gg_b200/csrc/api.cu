@@ -627,7 +627,7 @@ int ggcuda_fill_path_gradient(ggcuda_ctx* h, const uint8_t* verbs, uint32_t n_ve
     if (!c || (!verbs && n_verbs) || (!coords && n_coords) || !geom || (!stops && n_stops)) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
     GG_TRY
     GG_NO_REUSE(c);
-    if (kind != GGCUDA_GRADIENT_LINEAR && kind != GGCUDA_GRADIENT_RADIAL) return fail(c, GGCUDA_ERR_UNSUPPORTED, "gradient kind not supported by the CUDA path (sweep and focal radial gradients fall back)");
+    if (kind < GGCUDA_GRADIENT_LINEAR || kind > GGCUDA_GRADIENT_RADIAL_FOCAL) return fail(c, GGCUDA_ERR_UNSUPPORTED, "unknown gradient kind");
     if (extend < 0 || extend > 2 || n_stops > 64) return fail(c, GGCUDA_ERR_INVALID, "bad gradient");
     if (n_verbs == 0) return 0;
     c->scene.begin_path(ID6, fill_rule == GGCUDA_FILL_EVENODD);

@@ -550,10 +550,43 @@ __device__ __noinline__ float4 grad_color(const uint32_t* __restrict__ gtab, con
         const double dx = g2 - g0, dy = g3 - g1, l2 = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         if (l2 == 0.0) first_only = true;
         else t = __ddiv_rn(__dadd_rn(__dmul_rn(x - g0, dx), __dmul_rn(y - g1, dy)), l2);
-    } else {
+    } else if (kind == 1u) {
         const double dx = x - g0, dy = y - g1, rd = g3 - g2;
         if (rd == 0.0) first_only = true;
         else t = __ddiv_rn(__dsqrt_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy))) - g2, rd);
+    } else if (kind == 4u) {   // sweep (gradient_sweep.go:79-150): the angle from the centre, relative to the start angle, over the sweep
+        const double dx = x - g0, dy = y - g1, sweep = g3 - g2;
+        if (dx == 0.0 && dy == 0.0) first_only = true;
+        else if (sweep != 0.0) {
+            const double two_pi = 6.283185307179586;
+            double rel = atan2(dy, dx) - g2;
+            if (sweep > 0.0) { for (int k = 0; k < 64 && rel < 0.0; k++) rel += two_pi; for (int k = 0; k < 64 && rel >= two_pi; k++) rel -= two_pi; }
+            else { for (int k = 0; k < 64 && rel > 0.0; k++) rel -= two_pi; for (int k = 0; k < 64 && rel <= -two_pi; k++) rel += two_pi; }
+            t = __ddiv_rn(rel, sweep);
+        }
+    } else {                   // radial with the focus off the centre (gradient_radial.go:131-196): ray from the focus against the end circle
+        const double fx0 = (double)__uint_as_float(g[9]), fy0 = (double)__uint_as_float(g[10]);
+        if (g3 - g2 == 0.0) first_only = true;
+        else {
+            const double dx = x - fx0, dy = y - fy0, fx = g0 - fx0, fy = g1 - fy0;
+            const double a = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+            const double b = __dmul_rn(-2.0, __dadd_rn(__dmul_rn(dx, fx), __dmul_rn(dy, fy)));
+            const double c = __dadd_rn(__dmul_rn(fx, fx), __dmul_rn(fy, fy)) - __dmul_rn(g3, g3);
+            if (a != 0.0) {
+                const double disc = __dmul_rn(b, b) - __dmul_rn(__dmul_rn(4.0, a), c);
+                if (disc < 0.0) t = 1.0;
+                else {
+                    const double sq = __dsqrt_rn(disc), t1 = __ddiv_rn(-b - sq, __dmul_rn(2.0, a)), t2 = __ddiv_rn(-b + sq, __dmul_rn(2.0, a));
+                    double tt = 0.0;
+                    bool hit = true;
+                    if (t1 > 0.0 && t2 > 0.0) tt = fmin(t1, t2); else if (t1 > 0.0) tt = t1; else if (t2 > 0.0) tt = t2; else hit = false;
+                    if (hit) {
+                        const double pd = __dsqrt_rn(a), idist = __dmul_rn(tt, pd);
+                        if (idist != 0.0) t = __ddiv_rn(pd, idist);
+                    }
+                }
+            }
+        }
     }
     const float* a = nullptr;
     uint32_t i = 0;

@@ -335,7 +335,8 @@ void HostScene::draw_gradient(int kind, const double geom[6], const double* stop
         memcpy(&st[5 * (j + 1)], key, sizeof key);
     }
     uint32_t rec[16] = {0};
-    rec[0] = (uint32_t)kind; rec[1] = (uint32_t)extend; rec[2] = n_stops;
+    rec[0] = kind <= 1 ? (uint32_t)kind : (uint32_t)kind + 2u;   // table kinds: 0 linear, 1 radial, 4 sweep, 5 focal radial (2 / 3: SDF round rect / image)
+    rec[1] = (uint32_t)extend; rec[2] = n_stops;
     rec[3] = (uint32_t)grad_stops.size(); rec[4] = 0;
     float g[6];
     for (int k = 0; k < 6; k++) g[k] = (float)geom[k];

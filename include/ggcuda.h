@@ -111,8 +111,9 @@ GGCUDA_API int ggcuda_fill_path(ggcuda_ctx* ctx, const uint8_t* verbs, uint32_t 
 /* Gradient brushes (gg.LinearGradientBrush, gradient_linear.go:52-66; gg.RadialGradientBrush without focus,
  * gradient_radial.go computeTSimple; colour stops interpolated in linear light, gradient.go:62-131; sampled at pixel centres,
  * software.go:1086-1090). geom: linear x0, y0, x1, y1; radial cx, cy, r0, r1 (device space, two unused). stops: 5 doubles each
- * {offset, r, g, b, a}, straight alpha, any order. extend: gg.ExtendMode. Sweep / focal gradients: GGCUDA_ERR_UNSUPPORTED. */
-enum { GGCUDA_GRADIENT_LINEAR = 0, GGCUDA_GRADIENT_RADIAL = 1 };
+ * {offset, r, g, b, a}, straight alpha, any order. extend: gg.ExtendMode. Sweep (gg.SweepGradientBrush, gradient_sweep.go:79-150):
+ * cx, cy, start angle, end angle (radians). Radial with a focus off the centre (gradient_radial.go:131-196): cx, cy, r0, r1, fx, fy. */
+enum { GGCUDA_GRADIENT_LINEAR = 0, GGCUDA_GRADIENT_RADIAL = 1, GGCUDA_GRADIENT_SWEEP = 2, GGCUDA_GRADIENT_RADIAL_FOCAL = 3 };
 enum { GGCUDA_EXTEND_PAD = 0, GGCUDA_EXTEND_REPEAT = 1, GGCUDA_EXTEND_REFLECT = 2 };
 GGCUDA_API int ggcuda_fill_path_gradient(ggcuda_ctx* ctx, const uint8_t* verbs, uint32_t n_verbs, const double* coords, uint32_t n_coords,
                                          int kind, const double geom[6], const double* stops, uint32_t n_stops, int extend, int fill_rule);

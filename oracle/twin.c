@@ -1428,9 +1428,36 @@ static void og_color_at(const uint32_t *gtab, uint32_t idx, double x, double y, 
     if (kind == 0) {
         double dx = g2 - g0, dy = g3 - g1, l2 = dx * dx + dy * dy;
         if (l2 == 0) first_only = 1; else t = ((x - g0) * dx + (y - g1) * dy) / l2;
-    } else {
+    } else if (kind == 1) {
         double dx = x - g0, dy = y - g1, rd = g3 - g2;
         if (rd == 0) first_only = 1; else t = (sqrt(dx * dx + dy * dy) - g2) / rd;
+    } else if (kind == 4) {   /* gradient_sweep.go:79-150 */
+        double dx = x - g0, dy = y - g1, sweep = g3 - g2;
+        if (dx == 0 && dy == 0) first_only = 1;
+        else if (sweep != 0) {
+            const double two_pi = 2 * 3.14159265358979323846;
+            double rel = atan2(dy, dx) - g2;
+            if (sweep > 0) { for (int k = 0; k < 64 && rel < 0; k++) rel += two_pi; for (int k = 0; k < 64 && rel >= two_pi; k++) rel -= two_pi; }
+            else { for (int k = 0; k < 64 && rel > 0; k++) rel -= two_pi; for (int k = 0; k < 64 && rel <= -two_pi; k++) rel += two_pi; }
+            t = rel / sweep;
+        }
+    } else {                  /* gradient_radial.go:84-196, focus off the centre */
+        double fx0 = bits_f32(g[9]), fy0 = bits_f32(g[10]);
+        if (g3 - g2 == 0) first_only = 1;
+        else {
+            double dx = x - fx0, dy = y - fy0, fx = g0 - fx0, fy = g1 - fy0;
+            double a = dx * dx + dy * dy, b = -2 * (dx * fx + dy * fy), c = fx * fx + fy * fy - g3 * g3;
+            if (a != 0) {
+                double disc = b * b - 4 * a * c;
+                if (disc < 0) t = 1;
+                else {
+                    double sq = sqrt(disc), t1 = (-b - sq) / (2 * a), t2 = (-b + sq) / (2 * a), tt = 0;
+                    int hit = 1;
+                    if (t1 > 0 && t2 > 0) tt = t1 < t2 ? t1 : t2; else if (t1 > 0) tt = t1; else if (t2 > 0) tt = t2; else hit = 0;
+                    if (hit) { double pd = sqrt(a), idist = tt * pd; if (idist != 0) t = pd / idist; }
+                }
+            }
+        }
     }
     if (n == 0) { out[0] = out[1] = out[2] = out[3] = 0; return; }
     if (first_only || n == 1) { for (int k = 0; k < 4; k++) out[k] = bits_f32(st[1 + k]); return; }

@@ -489,8 +489,47 @@ def _gg_color_at(stops, t, extend):
     return rgb + [float(f(a[4]) + lt * (f(b[4]) - f(a[4])))]
 
 
+def _gg_focal_t(x, y, cx, cy, r1, fx0, fy0):
+    """gradient_radial.go:131-196 computeTFocal."""
+    dx, dy, fx, fy = x - fx0, y - fy0, cx - fx0, cy - fy0
+    a, b, c = dx * dx + dy * dy, -2 * (dx * fx + dy * fy), fx * fx + fy * fy - r1 * r1
+    if a == 0:
+        return 0.0
+    disc = b * b - 4 * a * c
+    if disc < 0:
+        return 1.0
+    t1, t2 = (-b - np.sqrt(disc)) / (2 * a), (-b + np.sqrt(disc)) / (2 * a)
+    pos = [v for v in (t1, t2) if v > 0]
+    if not pos:
+        return 0.0
+    idist = min(pos) * np.sqrt(a)
+    return 0.0 if idist == 0 else float(np.sqrt(a) / idist)
+
+
+def _gg_sweep_t(x, y, cx, cy, a0, a1):
+    """gradient_sweep.go:79-150."""
+    sweep = a1 - a0
+    if sweep == 0:
+        return 0.0
+    rel = float(np.arctan2(y - cy, x - cx)) - a0
+    two_pi = 2 * np.pi
+    if sweep > 0:
+        while rel < 0:
+            rel += two_pi
+        while rel >= two_pi:
+            rel -= two_pi
+    else:
+        while rel > 0:
+            rel -= two_pi
+        while rel <= -two_pi:
+            rel += two_pi
+    return rel / sweep
+
+
 @pytest.mark.parametrize("kind,geom,extend", [(0, (10, 5, 80, 40), 0), (0, (30, 0, 50, 0), 1), (0, (30, 10, 50, 30), 2),
-                                              (1, (48, 32, 4, 40), 0), (1, (20, 20, 0, 12), 2), (0, (5, 5, 5, 5), 0)])
+                                              (1, (48, 32, 4, 40), 0), (1, (20, 20, 0, 12), 2), (0, (5, 5, 5, 5), 0),
+                                              (2, (48, 32, 0.0, 6.283185307179586), 0), (2, (40.5, 20.5, 1.0, -2.5), 1), (2, (10, 60, 0.5, 0.5), 0),
+                                              (3, (48, 32, 0, 40, 60, 40), 0), (3, (30, 30, 5, 25, 20, 22), 2), (3, (30, 30, 7, 7, 20, 22), 0)])
 def test_gradient_fill_matches_gg_formulas(kind, geom, extend):
     from gg_b200 import _lib
     w, h = 96, 64
@@ -510,8 +549,12 @@ def test_gradient_fill_matches_gg_formulas(kind, geom, extend):
             dx, dy = g[2] - g[0], g[3] - g[1]
             l2 = dx * dx + dy * dy
             col = sorted(stops)[0][1:] if l2 == 0 else _gg_color_at(stops, ((fx - g[0]) * dx + (fy - g[1]) * dy) / l2, extend)
-        else:
+        elif kind == 1:
             col = _gg_color_at(stops, (np.hypot(fx - g[0], fy - g[1]) - g[2]) / (g[3] - g[2]), extend)
+        elif kind == 2:
+            col = sorted(stops)[0][1:] if (fx == g[0] and fy == g[1]) else _gg_color_at(stops, _gg_sweep_t(fx, fy, *g[:4]), extend)
+        else:
+            col = sorted(stops)[0][1:] if g[3] - g[2] == 0 else _gg_color_at(stops, _gg_focal_t(fx, fy, g[0], g[1], g[3], g[4], g[5]), extend)
         want = [int(min(1.0, max(0.0, col[k] * col[3])) * 255 + 0.5) for k in range(3)] + [int(col[3] * 255 + 0.5)]
         assert np.abs(out[y, x].astype(int) - np.array(want)).max() <= 1, (x, y, out[y, x], want)
 

@@ -768,7 +768,7 @@ def test_config1_cuda_vs_gg_cpu_path(ctx):
 
 
 def test_gradient_brushes(ctx):
-    """linear / radial gradient fills (pad, repeat, reflect) through the per-draw entry, mixed with solid fills and
+    """linear / radial / sweep / focal-radial gradient fills (pad, repeat, reflect) through the per-draw entry, mixed with solid fills and
     clips: PTCL word for word (CmdGrad where the oracle has it), pixels within 1/255 of the oracle, which evaluates gg's
     ColorAt exactly (the device does the same arithmetic but for powf in the linear -> sRGB step)."""
     w, h = 400, 300
@@ -786,10 +786,15 @@ def test_gradient_brushes(ctx):
             ctx.pop()
         if i % 2:
             stops = [(float(o), *rng.uniform(0, 1, 3), float(rng.uniform(0.3, 1.0))) for o in sorted(rng.uniform(0, 1, int(rng.integers(2, 5))))]
-            if i % 4 == 1:
+            if i % 8 == 1:
                 ctx.fill_path_gradient(v, c, 0, tuple(rng.uniform(0, w, 4)), stops, extend=i % 3, fill_rule=0)
-            else:
+            elif i % 8 == 3:
                 ctx.fill_path_gradient(v, c, 1, (float(rng.uniform(0, w)), float(rng.uniform(0, h)), 0.0, float(rng.uniform(20, 150))), stops, extend=i % 3)
+            elif i % 8 == 5:     # sweep: centre, start / end angle
+                ctx.fill_path_gradient(v, c, 2, (float(rng.uniform(0, w)), float(rng.uniform(0, h)), float(rng.uniform(-3, 3)), float(rng.uniform(-6, 6))), stops, extend=i % 3)
+            else:                # radial with the focus off the centre
+                gx, gy, r1 = float(rng.uniform(0, w)), float(rng.uniform(0, h)), float(rng.uniform(40, 150))
+                ctx.fill_path_gradient(v, c, 3, (gx, gy, 5.0, r1, gx + 0.4 * r1, gy - 0.3 * r1), stops, extend=i % 3)
             n_grad += 1
         else:
             ctx.fill_path(v, c, tuple(int(x) for x in rng.integers(0, 256, 4)), 0)
