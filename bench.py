@@ -267,15 +267,34 @@ def main():
     # symmetric memory cannot be set up on this box.
     sym, assemble_kind = None, "single"
     band_mode = os.environ.get("GG_BANDS", "auto")
-    if band_mode == "auto":   # measured on 8 x B200 (round 2): fused stores 1.70 ms / step, NCCL all-gather 2.14 ms
+    if band_mode == "auto":
+        # Fused stores (fine writes its band into every frame) unless the receivers' NVLink ingress -- (N - 1) bands per
+        # device and frame -- takes longer than half of fine itself: then fine would be stretched to the ingress time, and
+        # the band is broadcast afterwards on a side stream, behind the next frame's front stages. Measured on 8 x B200,
+        # round 2, config3: fused 1.47 ms / step, deferred 1.41 (L2 flush inside), NCCL all-gather 2.14; config5 (fine
+        # 3.6 ms, ingress 1.3 ms): fused 6.0, deferred 6.5.
         band_mode = "p2p"
-    if world > 1 and band_mode in ("p2p", "p2p_nomc"):
+        if world > 1:
+            ctx.set_timing(True)
+            probe = torch.zeros((max(1, min(y1 * 16, h) - y0 * 16), w, 4), dtype=torch.uint8, device="cuda")
+            for _ in range(3):
+                ctx.render_device(probe.data_ptr(), w * 4, _lib.KEEP_SCENE)
+            fine_ms = torch.tensor([ctx.stats()["ms_fine"]], dtype=torch.float64, device="cuda")
+            dist.all_reduce(fine_ms, op=dist.ReduceOp.MAX)
+            ingress_ms = (world - 1) * probe.numel() / 700e9 * 1e3      # ~700 GB/s of the 900 GB/s a direction offers
+            if ingress_ms > 0.5 * float(fine_ms.item()):
+                band_mode = "p2p_async"
+            del probe
+            ctx.set_timing(False)
+    deferred = band_mode in ("p2p_async", "p2p_async_nomc")   # bands broadcast on a side stream, behind the next frame's front stages
+    if world > 1 and band_mode in ("p2p", "p2p_nomc", "p2p_async", "p2p_async_nomc"):
         try:
             sym = bands.SymmetricFrame(w, h, world, rank, f"cuda:{local_rank}")
-            if band_mode == "p2p_nomc":
+            if band_mode in ("p2p_nomc", "p2p_async_nomc"):
                 sym.multicast = False
-            assemble_kind = "fine stores into all frames (multimem.st over NVSwitch multicast) + barrier" if sym.multicast else \
-                "fine stores into all frames (peer memory over NVLink) + barrier"
+            via = "multimem.st over NVSwitch multicast" if sym.multicast else "peer memory over NVLink"
+            assemble_kind = (f"band broadcast into all frames ({via}) on a side stream while the next frame is rasterised (ggcuda_broadcast_band) + barrier"
+                             if deferred else f"fine stores into all frames ({via}) + barrier")
         except Exception as e:   # noqa: BLE001
             if rank == 0:
                 print(f"symmetric memory unavailable ({type(e).__name__}: {e}); using the NCCL all-gather", file=sys.stderr)
@@ -300,12 +319,29 @@ def main():
             assemble_kind = "NCCL all_gather_into_tensor (torch)"
     stride = w * 4
     band_bytes = band.numel()
-    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    flush_buf = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # 1.5 x the 126 MB L2
     e_mid = torch.cuda.Event(enable_timing=True)
+
+    side = torch.cuda.Stream() if (sym is not None and deferred) else None
+    scratch = [torch.empty_like(band), torch.empty_like(band)] if side is not None else None
+    step_no = [0]
 
     def make_step(c, band_t):
         def step():
-            if sym is not None:
+            if side is not None:
+                # render into one of two private bands; a small kernel on the side stream copies it into every rank's frame
+                # (this rank's too) and the barrier follows it there, while this stream goes on with the next frame
+                sb = scratch[step_no[0] & 1]
+                step_no[0] += 1
+                c.render_device(sb.data_ptr(), stride, _lib.KEEP_SCENE | _lib.NO_WAIT)   # the host queues frames ahead of the device
+                e_mid.record(stream)
+                if sym.multicast:
+                    c.broadcast_band(sb.data_ptr(), [sym.multicast_band], band_bytes, side.cuda_stream, multicast=True)
+                else:
+                    c.broadcast_band(sb.data_ptr(), sym.peer_bands + [band_t.data_ptr()], band_bytes, side.cuda_stream)
+                with torch.cuda.stream(side):
+                    sym.barrier()
+            elif sym is not None:
                 if sym.multicast:
                     c.render_device_multi(band_t.data_ptr(), [sym.multicast_band], stride, _lib.KEEP_SCENE, multicast=True)
                 else:
@@ -338,7 +374,20 @@ def main():
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    total_ms, _, own_ms = time_pipeline(ctx, torch, stream, args.steps, 0, step, flush_buf, stages=False)
+    if side is not None:
+        # pipelined across frames: one event pair around all K steps (the L2 flushes between them are inside it and counted),
+        # closed only after the side stream has delivered the last band everywhere
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            step()
+        stream.wait_stream(side)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        total_ms, own_ms = e0.elapsed_time(e1), 0.0
+    else:
+        total_ms, _, own_ms = time_pipeline(ctx, torch, stream, args.steps, 0, step, flush_buf, stages=False)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -350,6 +399,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     own_max_ms = float(t[1].item()) / args.steps   # slowest rank's own pipeline, before it waits for the others
+    if side is not None:
+        own_max_ms = None                          # frames overlap in this mode: there is no per-frame boundary to time
     ms_per_step = float(t[0].item()) / args.steps
     value = w * h / 1e6 / (ms_per_step / 1e3)
 
@@ -471,8 +522,8 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling if world > 1 else "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": WORKLOADS[args.workload], "width": w, "height": h, "bands": world,
-                       "band_assembly": assemble_kind, "rank_pipeline_ms_max": own_max_ms, "rank0_pipeline_ms": own_ms / args.steps,
-                       "paths": int(st["n_draws"]), "l2": "flushed between timed iterations (256 MiB write)",
+                       "band_assembly": assemble_kind, "rank_pipeline_ms_max": own_max_ms, "rank0_pipeline_ms": (own_ms / args.steps if side is None else None),
+                       "paths": int(st["n_draws"]), "l2": "flushed between timed iterations (192 MiB write)" + (", inside the timed region in this mode" if side is not None else ""),
                        "frames_per_s": 1e3 / ms_per_step,
                        "stage_ms": {k: float(v / args.steps) for k, v in zip(("front", "binning", "coarse", "fine"), stage_ms)},
                        "counts": {k: counts[k] for k in ("n_lines", "n_path_tiles", "n_segments", "n_hits", "n_ptcl_words")},

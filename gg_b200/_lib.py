@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libggcuda.so")
 
 OK, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4
-COMPOSITE_OVER, KEEP_SCENE, TARGET_F32 = 1, 2, 4
+COMPOSITE_OVER, KEEP_SCENE, TARGET_F32, NO_WAIT = 1, 2, 4, 8
 (BUF_SCENE, BUF_TAG_MONOIDS, BUF_DRAW_MONOIDS, BUF_INFO, BUF_CLIP_INPS, BUF_LINES, BUF_PATHS, BUF_TILES,
  BUF_SEG_START, BUF_SEGMENTS, BUF_PTCL_OFF, BUF_PTCL, BUF_HIT_CNT, BUF_LAYOUT, BUF_RESTART) = range(15)
 
@@ -20,7 +20,7 @@ SYMBOLS = [
     "ggcuda_add_encoding", "ggcuda_flush", "ggcuda_upload", "ggcuda_render_device", "ggcuda_render_device_multi", "ggcuda_get_stats", "ggcuda_set_timing",
     "ggcuda_debug_read", "ggcuda_pack_host", "ggcuda_begin_keyed", "ggcuda_set_dirty_rect", "ggcuda_register_target",
     "ggcuda_unregister_target", "ggcuda_comm_unique_id", "ggcuda_comm_init", "ggcuda_comm_destroy", "ggcuda_all_gather_bands",
-    "ggcuda_sync", "ggcuda_encoding_hash", "ggcuda_fill_path_gradient", "ggcuda_add_image",
+    "ggcuda_sync", "ggcuda_encoding_hash", "ggcuda_fill_path_gradient", "ggcuda_add_image", "ggcuda_broadcast_band",
 ]
 
 LINE = np.dtype([("path_ix", "<u4"), ("p0", "<f4", 2), ("p1", "<f4", 2)])
@@ -80,6 +80,7 @@ def load():
     L.ggcuda_stroke_path.argtypes = [vp, vp, u32, vp, u32, vp, C.c_double, C.c_int, C.c_int, C.c_double]
     L.ggcuda_fill_path_gradient.argtypes = [vp, vp, u32, vp, u32, C.c_int, vp, vp, u32, C.c_int, C.c_int]
     L.ggcuda_add_image.argtypes = [vp, u32, u32, vp, vp]
+    L.ggcuda_broadcast_band.argtypes = [vp, vp, vp, u32, C.c_int, C.c_size_t, vp]
     L.ggcuda_push_clip.argtypes = [vp, vp, u32, vp, u32]
     L.ggcuda_push_layer.argtypes = [vp, u32, C.c_float]
     L.ggcuda_pop.argtypes = [vp]
@@ -270,6 +271,11 @@ class Context:
         """Band to `dptr` and to every address in `mirrors` (peer pointers, or one multicast address)."""
         arr = (C.c_void_p * max(1, len(mirrors)))(*[C.c_void_p(int(m)) for m in mirrors])
         self._ck(self.L.ggcuda_render_device_multi(self.h, C.c_void_p(dptr), arr, len(mirrors), 1 if multicast else 0, stride, flags))
+
+    def broadcast_band(self, band_ptr, mirrors, nbytes, stream, multicast=False):
+        """Copy the band of the last render into every address of `mirrors` on `stream` (a CUDA stream handle of the caller's)."""
+        arr = (C.c_void_p * len(mirrors))(*[C.c_void_p(int(m)) for m in mirrors])
+        self._ck(self.L.ggcuda_broadcast_band(self.h, C.c_void_p(band_ptr), arr, len(mirrors), 1 if multicast else 0, nbytes, C.c_void_p(stream)))
 
     def pack_host(self):
         """(packed scene words, LAYOUT record) exactly as ggcuda_upload would send them; works on host-only contexts."""

@@ -77,10 +77,14 @@ struct Ctx {
     // One pass into a device target, captured as a CUDA graph and replayed while nothing it was built from changes (kernel
     // arguments are baked into the nodes: configuration, buffer addresses, target, fine ranges). 25 dependent launches cost
     // ~5 us each through the stream; a 512 x 512 frame spent half its time there.
-    struct PassKey { GGConfig cfg; GGBuffers b; uint8_t* dst; size_t stride; GGFineRange rg; GGFineMirrors mir; uint32_t reuse; } graph_key{};
-    cudaGraphExec_t graph_exec = nullptr;
-    uint32_t graph_launches = 0;
+    struct PassKey { GGConfig cfg; GGBuffers b; uint8_t* dst; size_t stride; GGFineRange rg; GGFineMirrors mir; uint32_t reuse; };
+    struct PassGraph { PassKey key; cudaGraphExec_t exec = nullptr; uint32_t launches = 0; } graph[2];   // two: a double-buffered target alternates
+    uint32_t graph_next = 0;
+    // Deferred band broadcast (ggcuda_broadcast_band): the band a broadcast is still reading must not be rendered into
+    struct Bcast { const void* band = nullptr; cudaEvent_t done = nullptr; } bcast[2];
+    cudaEvent_t ev_rendered = nullptr;
     bool graphs = true;       // GGCUDA_NO_GRAPH=1 turns them off; so does a failed capture
+    bool steady = false;      // the uploaded scene has been rendered to completion with the current buffers (GGCUDA_NO_WAIT)
     GGConfig cfg{};
     GGBump last_bump{};
 };
@@ -185,6 +189,7 @@ int upload(Ctx* c) {
     c->hits_cap = std::max<uint32_t>(c->hits_cap, c->tiles_cap);
     c->ptcl_cap = std::max<uint32_t>(c->ptcl_cap, 6u * c->hits_cap + 8u * (uint32_t)bt);
     c->uploaded = true;
+    c->steady = false;
     return 0;
 }
 
@@ -268,6 +273,7 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
     const bool reuse = c->reuse && c->resident_valid;
     if (!reuse && !c->uploaded) { int r = upload(c); if (r) return r; }
     c->stats.passes = 0; c->stats.kernel_launches = 0;
+    for (auto& e : c->bcast) if (e.band == dst_device && e.done) { CK(cudaStreamWaitEvent(c->stream, e.done, 0)); e.band = nullptr; }
     const size_t px_bytes = (flags & GGCUDA_TARGET_F32) ? 16 : 4;
     for (int attempt = 0; attempt < 12; attempt++) {
         if (!reuse) { int r = size_dynamic(c); if (r) return r; }
@@ -318,24 +324,29 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
             Ctx::PassKey key;
             memset(&key, 0, sizeof key);   // padding bytes take part in the comparison
             key.cfg = c->cfg; key.b = b; key.dst = dst_device; key.stride = stride; key.rg = full; key.mir = c->mirrors; key.reuse = reuse ? 1u : 0u;
-            if (c->graph_exec && memcmp(&key, &c->graph_key, sizeof key) != 0) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
-            if (!c->graph_exec) {
+            Ctx::PassGraph* pg = nullptr;
+            for (auto& e : c->graph) if (e.exec && memcmp(&key, &e.key, sizeof key) == 0) pg = &e;
+            if (!pg) {
+                pg = &c->graph[c->graph_next]; c->graph_next ^= 1u;
+                if (pg->exec) { cudaGraphExecDestroy(pg->exec); pg->exec = nullptr; }
                 cudaGraph_t g = nullptr;
                 bool ok = cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
                 if (ok) {
                     const int r = enqueue();
                     ok = cudaStreamEndCapture(c->stream, &g) == cudaSuccess && r == 0 && g;
                 }
-                if (ok) ok = cudaGraphInstantiate(&c->graph_exec, g, 0) == cudaSuccess;
+                if (ok) ok = cudaGraphInstantiate(&pg->exec, g, 0) == cudaSuccess;
                 if (g) cudaGraphDestroy(g);
-                if (!ok) { cudaGetLastError(); c->graph_exec = nullptr; c->graphs = false; }   // this context goes on without graphs
-                else { memcpy(&c->graph_key, &key, sizeof key); c->graph_launches = launches; }
+                if (!ok) { cudaGetLastError(); pg->exec = nullptr; c->graphs = false; }   // this context goes on without graphs
+                else { memcpy(&pg->key, &key, sizeof key); pg->launches = launches; }
             }
-            if (c->graph_exec) { CK(cudaGraphLaunch(c->graph_exec, c->stream)); replayed = true; launches = c->graph_launches; }
+            if (pg->exec) { CK(cudaGraphLaunch(pg->exec, c->stream)); replayed = true; launches = pg->launches; }
         }
         if (!replayed) { int r = enqueue(); if (r) return r; }
         c->stats.passes++;
         c->stats.kernel_launches += launches + (rows_t ? parts : 0u);
+        // the same scene went through these buffers before: every count is known to fit, the caller may run ahead
+        if ((flags & GGCUDA_NO_WAIT) && c->steady && !c->timing && !host_dst) return 0;
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaGetLastError());
         if (reuse) {
@@ -367,6 +378,7 @@ int render(Ctx* c, uint8_t* dst_device, size_t stride, uint32_t flags, uint8_t* 
                 cudaEventElapsedTime(&s.ms_fine, c->ev[3], c->ev[4]);
             }
             // the device now holds this scene's segments and command lists: remember under which key
+            c->steady = true;
             c->resident_valid = c->keyed; c->resident_key = c->pending_key;
             c->res_w = c->width; c->res_h = c->height; c->res_y0 = c->band_y0; c->res_y1 = c->band_y1;
             return 0;
@@ -484,7 +496,9 @@ void ggcuda_destroy(ggcuda_ctx* h) {
     c->pinned.clear();
     free_all(c);
     if (c->h_scene) cudaFreeHost(c->h_scene);
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (auto& e : c->graph) if (e.exec) cudaGraphExecDestroy(e.exec);
+    for (auto& e : c->bcast) if (e.done) cudaEventDestroy(e.done);
+    if (c->ev_rendered) cudaEventDestroy(c->ev_rendered);
     if (c->h_bump) cudaFreeHost(c->h_bump);
     if (c->h_frame) cudaFreeHost(c->h_frame);
     for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
@@ -757,6 +771,43 @@ int ggcuda_render_device_multi(ggcuda_ctx* h, void* dst_device, void* const* mir
     c->mirrors = GGFineMirrors{};
     if (r == 0) after_render(c, flags);
     return r;
+    GG_CATCH(c)
+}
+
+// Deferred multi-GPU assembly: the band of the LAST render, copied into every device's frame by a small kernel on `stream`
+// (a stream of the caller's, not the context's) while the context's own stream already rasterises the next frame. The
+// ingress of an N-way exchange -- (N - 1) bands per device and frame, 232 MB at N = 8 for 4K RGBA8, a quarter of a
+// millisecond of NVLink time -- then hides behind flatten, binning and coarse instead of stretching fine (which it does
+// when fine stores into the peers itself, ggcuda_render_device_multi). Render into two bands alternately: a band is not
+// rendered into again before its broadcast has read it (the context waits if it has to).
+int ggcuda_broadcast_band(ggcuda_ctx* h, const void* band_device, void* const* mirrors, uint32_t n_mirrors, int multicast, size_t bytes, void* stream) {
+    Ctx* c = reinterpret_cast<Ctx*>(h);
+    if (!c || !band_device || !mirrors || !n_mirrors || !stream) return c ? fail(c, GGCUDA_ERR_INVALID, "null argument") : GGCUDA_ERR_INVALID;
+    GG_TRY
+    if (c->host_only) return fail(c, GGCUDA_ERR_UNSUPPORTED, "host-only context");
+    if (n_mirrors > GG_MAX_MIRRORS || (multicast && n_mirrors != 1)) return fail(c, GGCUDA_ERR_INVALID, "bad mirror list");
+    if ((reinterpret_cast<uintptr_t>(band_device) & 15u) || (bytes & 15u)) return fail(c, GGCUDA_ERR_INVALID, "band must be 16-byte aligned and sized");
+    GGFineMirrors mir{};
+    for (uint32_t i = 0; i < n_mirrors; i++) {
+        if (reinterpret_cast<uintptr_t>(mirrors[i]) & 15u) return fail(c, GGCUDA_ERR_INVALID, "mirror must be 16-byte aligned");
+        mir.p[i] = (uint8_t*)mirrors[i];
+    }
+    mir.n = n_mirrors; mir.multicast = multicast ? 1u : 0u;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (!c->ev_rendered) CK(cudaEventCreateWithFlags(&c->ev_rendered, cudaEventDisableTiming));
+    CK(cudaEventRecord(c->ev_rendered, c->stream));
+    CK(cudaStreamWaitEvent(s, c->ev_rendered, 0));
+    gg_launch_band_bcast(band_device, mir, bytes, c->sm_count, s);
+    CK(cudaGetLastError());
+    Ctx::Bcast* slot = nullptr;
+    for (auto& e : c->bcast) if (e.band == band_device) slot = &e;            // this band again
+    if (!slot) for (auto& e : c->bcast) if (!slot && !e.band) slot = &e;      // a free entry
+    if (!slot) { slot = &c->bcast[0]; CK(cudaEventSynchronize(slot->done)); }  // a third band in flight: let the oldest finish
+    if (!slot->done) CK(cudaEventCreateWithFlags(&slot->done, cudaEventDisableTiming));
+    CK(cudaEventRecord(slot->done, s));
+    slot->band = band_device;
+    return 0;
     GG_CATCH(c)
 }
 

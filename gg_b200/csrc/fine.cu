@@ -911,3 +911,33 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     fine_kernel<<<blocks, FINE_WARPS * 32, smem, s>>>(cfg, b.ptcl_off, b.ptcl_len, b.ptcl, b.restart_pt, b.segments, b.spill_off, b.spill, b.bump, dst, stride,
                                                       rg, part, mir, b.scene + cfg.grad_base);
 }
+
+// ---------------------------------------------------------------- deferred band broadcast (ggcuda_broadcast_band)
+// Copies a finished band into the frames of the other devices: 16 bytes per thread and store, four loads in flight per
+// thread, a grid of a few CTAs -- the copy is bound by the NVLink ingress of the receivers (every device takes in N - 1
+// bands), not by this device, and it runs beside the next frame's kernels.
+__global__ void __launch_bounds__(256) band_bcast_kernel(const uint4* __restrict__ src, GGFineMirrors mir, size_t n16) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n16; i0 += 4 * stride) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const size_t i = i0 + k * stride; if (i < n16) v[k] = __ldg(src + i); }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const size_t i = i0 + k * stride;
+            if (i >= n16) continue;
+            if (mir.multicast) {
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mir.p[0] + 16 * i), "f"(__uint_as_float(v[k].x)), "f"(__uint_as_float(v[k].y)),
+                             "f"(__uint_as_float(v[k].z)), "f"(__uint_as_float(v[k].w)) : "memory");
+            } else {
+                for (uint32_t q = 0; q < mir.n; q++) reinterpret_cast<uint4*>(mir.p[q])[i] = v[k];
+            }
+        }
+    }
+}
+void gg_launch_band_bcast(const void* band, const GGFineMirrors& mir, size_t bytes, uint32_t sm_count, cudaStream_t s) {
+    const size_t n16 = bytes / 16;
+    if (!n16) return;
+    const uint32_t blocks = (uint32_t)std::min<size_t>((n16 + 1023) / 1024, std::max(8u, sm_count / 4));
+    band_bcast_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const uint4*>(band), mir, n16);
+}

@@ -58,5 +58,6 @@ struct GGFineMirrors { uint8_t* p[GG_MAX_MIRRORS]; uint32_t n; uint32_t multicas
 // What one fine launch covers: tile rows [row0, row1) relative to the band, tile-PAIR columns [px0, px1) (a warp owns two
 // horizontally adjacent tiles). A dirty rectangle (resident scenes) narrows both.
 struct GGFineRange { uint32_t row0, row1, px0, px1; };
+void gg_launch_band_bcast(const void* band, const GGFineMirrors& mir, size_t bytes, uint32_t sm_count, cudaStream_t s);
 void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_t stride, cudaStream_t s, const GGFineRange& rg, uint32_t part,
                     const GGFineMirrors& mir);

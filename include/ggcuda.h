@@ -56,8 +56,12 @@ enum {
                                    VelloAccelerator.compositeOver's byte arithmetic, (d * (255 - sA) + 127) / 255
                                    (vello_accelerator.go:388-442), instead of starting from the background colour */
     GGCUDA_KEEP_SCENE = 2,      /* do not clear the accumulated scene after rendering */
-    GGCUDA_TARGET_F32 = 4       /* ggcuda_render_device only: dst holds premultiplied float RGBA, 16 bytes per pixel
+    GGCUDA_TARGET_F32 = 4,      /* ggcuda_render_device only: dst holds premultiplied float RGBA, 16 bytes per pixel
                                    (stride in bytes, 16-byte aligned), instead of RGBA8 */
+    GGCUDA_NO_WAIT = 8          /* ggcuda_render_device[_multi] only: return as soon as the pass is on the stream when the same
+                                   scene has already been rendered once by this context with the buffers it has now (its
+                                   element counts are known to fit: nothing to check). The host can then queue frames ahead
+                                   of the device; ggcuda_sync waits for them. Ignored (the call waits) in every other case. */
 };
 
 /* flags for ggcuda_create */
@@ -156,6 +160,14 @@ GGCUDA_API int ggcuda_render_device(ggcuda_ctx* ctx, void* dst_device, size_t st
  * all-gather). There is no counterpart in the reference (single device). */
 GGCUDA_API int ggcuda_render_device_multi(ggcuda_ctx* ctx, void* dst_device, void* const* mirrors, uint32_t n_mirrors, int multicast,
                                           size_t stride_bytes, uint32_t flags);
+/* Deferred assembly: copy the band the last render produced (band_device, `bytes` long, 16-byte aligned) into every address of
+ * `mirrors` (the band's place in each device's frame -- this device's own frame included --, or ONE NVSwitch multicast address)
+ * on `stream`, a stream of the caller's: the copy runs beside the context's next renders, so the receivers' NVLink ingress
+ * ((N - 1) bands per frame) is hidden behind the next frame's flatten / binning / coarse. Render into two bands alternately;
+ * the context waits before rendering into a band whose broadcast is still reading it. Synchronise `stream` (and the other
+ * devices) before reading the assembled frame. */
+GGCUDA_API int ggcuda_broadcast_band(ggcuda_ctx* ctx, const void* band_device, void* const* mirrors, uint32_t n_mirrors, int multicast,
+                                     size_t bytes, void* stream);
 
 /* Band assembly inside the library ("assembled with one NCCL all-gather"), for hosts that have no
  * collective library of their own (the Go binding). NCCL is resolved at run time (the copy already loaded in the process,

@@ -3,7 +3,8 @@ renders the WHOLE frame alone. Against it, bit for bit, on every rank:
   * bands (ingest-time culling active) assembled by the library's own NCCL all-gather (ggcuda_comm_init / ggcuda_all_gather_bands),
   * bands assembled by torch's all_gather_into_tensor,
   * bands stored by the fine kernel itself into every rank's frame: NVSwitch multicast (multimem.st), then peer pointers,
-    each followed by the symmetric-memory barrier only."""
+    each followed by the symmetric-memory barrier only,
+  * bands rendered privately and broadcast afterwards on a side stream (ggcuda_broadcast_band), multicast and peer."""
 import os
 import sys
 
@@ -79,6 +80,28 @@ if sym is not None:
         else:
             ctx.render_device_multi(sym.band().data_ptr(), sym.peer_bands, w * 4, _lib.KEEP_SCENE)
         sym.barrier()
+        torch.cuda.synchronize()
+        results[mode] = bool((sym.frame == truth).all().item())
+        dist.barrier()
+    # 4. deferred broadcast: three frames rendered alternately into two private bands, each copied into every rank's frame
+    #    on a side stream (ggcuda_broadcast_band) while the next one is rasterised; barrier on the side stream
+    side = torch.cuda.Stream()
+    scratch = [torch.empty_like(sym.band()), torch.empty_like(sym.band())]
+    nbytes = scratch[0].numel()
+    for mode in (["bcast_multicast"] if sym.multicast else []) + ["bcast_peer"]:
+        sym.frame.zero_()
+        torch.cuda.synchronize()
+        dist.barrier()
+        for k in range(3):
+            sb = scratch[k & 1]
+            sb.zero_()
+            ctx.render_device(sb.data_ptr(), w * 4, _lib.KEEP_SCENE | _lib.NO_WAIT)   # queued behind one another, no host wait
+            if mode == "bcast_multicast":
+                ctx.broadcast_band(sb.data_ptr(), [sym.multicast_band], nbytes, side.cuda_stream, multicast=True)
+            else:
+                ctx.broadcast_band(sb.data_ptr(), sym.peer_bands + [sym.band().data_ptr()], nbytes, side.cuda_stream)
+            with torch.cuda.stream(side):
+                sym.barrier()
         torch.cuda.synchronize()
         results[mode] = bool((sym.frame == truth).all().item())
         dist.barrier()
