@@ -269,10 +269,10 @@ def main():
     band_mode = os.environ.get("GG_BANDS", "auto")
     if band_mode == "auto":
         # Fused stores (fine writes its band into every frame) unless the receivers' NVLink ingress -- (N - 1) bands per
-        # device and frame -- takes longer than half of fine itself: then fine would be stretched to the ingress time, and
-        # the band is broadcast afterwards on a side stream, behind the next frame's front stages. Measured on 8 x B200,
-        # round 2, config3: fused 1.47 ms / step, deferred 1.41 (L2 flush inside), NCCL all-gather 2.14; config5 (fine
-        # 3.6 ms, ingress 1.3 ms): fused 6.0, deferred 6.5.
+        # device and frame -- takes longer than fine itself: then fine would be stretched to the ingress time, and the band
+        # is broadcast afterwards on a side stream, behind the next frame's front stages. Measured on B200s, round 2,
+        # config3: N = 8 fused 1.47 ms / step, deferred 1.41 (L2 flush inside), NCCL all-gather 2.14; N = 4 fused 1.31,
+        # deferred 1.32; config5 at N = 8 (fine 3.6 ms, ingress 1.3 ms): fused 6.0, deferred 6.5.
         band_mode = "p2p"
         if world > 1:
             ctx.set_timing(True)
@@ -282,7 +282,7 @@ def main():
             fine_ms = torch.tensor([ctx.stats()["ms_fine"]], dtype=torch.float64, device="cuda")
             dist.all_reduce(fine_ms, op=dist.ReduceOp.MAX)
             ingress_ms = (world - 1) * probe.numel() / 700e9 * 1e3      # ~700 GB/s of the 900 GB/s a direction offers
-            if ingress_ms > 0.5 * float(fine_ms.item()):
+            if ingress_ms > float(fine_ms.item()):
                 band_mode = "p2p_async"
             del probe
             ctx.set_timing(False)

@@ -30,5 +30,25 @@ assert ctx.begin_keyed(w2, h2, key)
 ctx.set_dirty_rect(40, 30, 120, 90)
 ctx.flush(buf)
 c = U.gpu_encoding(ctx, enc, w2, h2, band=(2, 7))
-print("sanitizer scene ok", int(a.sum()), int(b.sum()), int(buf.sum()), int(c.sum()), "launches", ctx.stats()["kernel_launches"])
+# brushes beyond solid colours: the four gradient kinds, an SDF round rect, images (nearest and bilinear)
+from gg_b200 import scene as S  # noqa: E402
+e2 = S.Encoding()
+rng = np.random.default_rng(3)
+img = rng.integers(0, 256, (9, 13, 4)).astype(np.uint8)
+img[..., :3] = np.minimum(img[..., :3], img[..., 3:])
+e2.AddImage(img)
+e2.EncodeTransform(S.IDENTITY)
+e2.EncodeFillRoundRect((0.9, 0.2, 0.1, 0.8), (10.5, 8.5, 150.0, 90.0), 12.0, 12.0)
+e2.EncodeImage(0, (1, 0, 20, 0, 1, 30))
+e2.EncodeImage(0, (6.5, 1.0, 60, -1.0, 5.0, 40))
+ctx.begin(w2, h2)
+ctx.add_image(img)
+ctx.add_encoding(*e2.streams())
+stops = [(0.0, 1, 0, 0, 1), (0.5, 0, 1, 0, 0.5), (1.0, 0, 0, 1, 1)]
+sq = ([0, 1, 1, 1, 4], [5, 5, 220, 5, 220, 140, 5, 140])
+for kind, geom in ((0, (0, 0, 200, 100)), (1, (100, 70, 5, 80)), (2, (100, 70, 0.3, 5.0)), (3, (100, 70, 5, 80, 120, 60))):
+    ctx.fill_path_gradient(*sq, kind, geom, stops, extend=kind % 3)
+g = np.zeros((h2, w2, 4), dtype=np.uint8)
+ctx.flush(g)
+print("sanitizer scene ok", int(a.sum()), int(b.sum()), int(buf.sum()), int(c.sum()), int(g.sum()), "launches", ctx.stats()["kernel_launches"])
 ctx.close()
