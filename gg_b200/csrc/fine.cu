@@ -618,7 +618,46 @@ __device__ __noinline__ float4 grad_color(const uint32_t* __restrict__ gtab, con
     return make_float4(r * al, gg * al, b * al, al);
 }
 
-__global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
+// CmdGrad for FOUR of the lane's pixels held in shared memory (scr[i * 32], coverage of the fill in cov[i * 32]), starting at
+// pixel (px0, py): the brush's premultiplied colour and coverage at each pixel centre, source-over.
+//   kind 0 / 1 / 4 / 5  gradients: gg's ColorAt (grad_color), coverage = the fill's area
+//   kind 2  TagFillRoundRect the way gg's CPU renderer draws it (scene/renderer.go:986-1043, scene/shape.go:246-274): coverage =
+//           Hermite smoothstep over +-0.7 px of the signed distance to the rounded rectangle; the path only binned the tiles
+//   kind 3  TagImage (image_color): its own coverage too
+__device__ __noinline__ void brush4(const uint32_t* __restrict__ gtab, const uint32_t* __restrict__ g, float4* scr, const float* cov, int px0, int py) {
+    const uint32_t kind = g[0];
+    const float fy = (float)py + 0.5f;
+#pragma unroll 1
+    for (int i = 0; i < 4; i++) {
+        const int ipx = px0 + i;
+        const float fx = (float)ipx + 0.5f;
+        float cv = cov[i * 32];
+        float4 c;
+        if (kind == 2u) {
+            const float gcx = __uint_as_float(g[5]), gcy = __uint_as_float(g[6]);
+            const float hw = __uint_as_float(g[7]), hh = __uint_as_float(g[8]), rad = __uint_as_float(g[9]);
+            c = unpack_rgba8(g[10]);
+            const float ddx = fabsf(fx - gcx) - hw + rad, ddy = fabsf(fy - gcy) - hh + rad;
+            const float ox = fmaxf(ddx, 0.0f), oy = fmaxf(ddy, 0.0f);
+            const float dist = sqrtf(ox * ox + oy * oy) + fminf(fmaxf(ddx, ddy), 0.0f) - rad;
+            if (dist >= 0.7f) cv = 0.0f;
+            else if (dist <= -0.7f) cv = 1.0f;
+            else { const float tt = (dist + 0.7f) / 1.4f; cv = 1.0f - (tt * tt * (3.0f - 2.0f * tt)); }
+        } else if (kind == 3u) {
+            c = image_color(gtab, g, fx, fy, ipx, py, &cv);
+        } else {
+            c = grad_color(gtab, g, fx, fy);
+        }
+        float4 d = scr[i * 32];
+        d.x = fmaf(cv, fmaf(-c.w, d.x, c.x), d.x);
+        d.y = fmaf(cv, fmaf(-c.w, d.y, c.y), d.y);
+        d.z = fmaf(cv, fmaf(-c.w, d.z, c.z), d.z);
+        d.w = fmaf(cv, fmaf(-c.w, d.w, c.w), d.w);
+        scr[i * 32] = d;
+    }
+}
+
+__global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, const uint32_t* __restrict__ ptcl_off, const uint32_t* __restrict__ ptcl_len,
                                                                const uint32_t* __restrict__ ptcl, const uint32_t* __restrict__ restart_pt,
                                                                const GGSegment* __restrict__ segments, const uint32_t* __restrict__ spill_off,
                                                                float4* spill, GGBump* bump, uint8_t* dst, size_t stride, GGFineRange rg, uint32_t part, GGFineMirrors mir,
@@ -737,46 +776,20 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 5) fine_kernel(GGConfig cfg, 
                         unpack2(fma2(cov2, fma2(nw2, zw, czw), zw), rgba[i].z, rgba[i].w);
                     }
                 } else if (tag == GG_CMD_GRAD) {
-                    // Gradient brush (gg.LinearGradientBrush / RadialGradientBrush.ColorAt at the pixel centre, software.go:1086-1090):
-                    // evaluated per pixel by grad_color, gg's own arithmetic.
+                    // A brush evaluated per pixel (gradient, SDF round rect, image): out of line, over the same shared scratch
+                    // as CmdEndClip -- rare commands with a lot of code, kept out of the command loop's instruction footprint.
                     const uint32_t* g = gtab + 16u * ps.word(cmd + 1);
                     cmd += 2;
-                    const uint32_t kind = g[0];
-                    const float fy = (float)py + 0.5f;
-                    if (kind == 2u) {
-                        // TagFillRoundRect the way gg's CPU renderer draws it (scene/renderer.go:986-1043, scene/shape.go:246-274):
-                        // coverage = Hermite smoothstep over +-0.7 px of the signed distance to the rounded rectangle, at the pixel
-                        // centre; the path's own area only decided which tiles carry the command
-                        const float gcx = __uint_as_float(g[5]), gcy = __uint_as_float(g[6]);
-                        const float hw = __uint_as_float(g[7]), hh = __uint_as_float(g[8]), rad = __uint_as_float(g[9]);
-                        const float4 c = unpack_rgba8(g[10]);
+                    float4* scr = reinterpret_cast<float4*>(wsm + SM_SCR) + lane;
+                    float* cvs = reinterpret_cast<float*>(wsm + SM_COV) + lane;
+                    __syncwarp();   // the scratch lies over the coverage table of the fill just evaluated
 #pragma unroll
-                        for (int i = 0; i < PX; i++) {
-                            const float fx = (float)(tx * GG_TILE_W + xb + i) + 0.5f;
-                            const float ddx = fabsf(fx - gcx) - hw + rad, ddy = fabsf(fy - gcy) - hh + rad;
-                            const float ox = fmaxf(ddx, 0.0f), oy = fmaxf(ddy, 0.0f);
-                            const float dist = sqrtf(ox * ox + oy * oy) + fminf(fmaxf(ddx, ddy), 0.0f) - rad;
-                            float cov;
-                            if (dist >= 0.7f) cov = 0.0f;
-                            else if (dist <= -0.7f) cov = 1.0f;
-                            else { const float tt = (dist + 0.7f) / 1.4f; cov = 1.0f - (tt * tt * (3.0f - 2.0f * tt)); }
-                            rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
-                            rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
-                            rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);
-                            rgba[i].w = fmaf(cov, fmaf(-c.w, rgba[i].w, c.w), rgba[i].w);
-                        }
-                        continue;
-                    }
+                    for (int hf = 0; hf < 2; hf++) {
 #pragma unroll
-                    for (int i = 0; i < PX; i++) {
-                        float cov = area[i];
-                        const int ipx = (int)(tx * GG_TILE_W + xb) + i;
-                        const float4 c = kind == 3u ? image_color(gtab, g, (float)ipx + 0.5f, fy, ipx, (int)py, &cov)    // TagImage: its own coverage
-                                                    : grad_color(gtab, g, (float)ipx + 0.5f, fy);                       // premultiplied
-                        rgba[i].x = fmaf(cov, fmaf(-c.w, rgba[i].x, c.x), rgba[i].x);
-                        rgba[i].y = fmaf(cov, fmaf(-c.w, rgba[i].y, c.y), rgba[i].y);
-                        rgba[i].z = fmaf(cov, fmaf(-c.w, rgba[i].z, c.z), rgba[i].z);
-                        rgba[i].w = fmaf(cov, fmaf(-c.w, rgba[i].w, c.w), rgba[i].w);
+                        for (int i = 0; i < 4; i++) { scr[i * 32] = rgba[hf * 4 + i]; cvs[i * 32] = area[hf * 4 + i]; }
+                        brush4(gtab, g, scr, cvs, (int)(tx * GG_TILE_W + xb) + hf * 4, (int)py);
+#pragma unroll
+                        for (int i = 0; i < 4; i++) rgba[hf * 4 + i] = scr[i * 32];
                     }
                 } else if (tag == GG_CMD_BEGIN_CLIP) {   // fine.go:125-138
                     cmd += 1;
@@ -904,7 +917,9 @@ void gg_launch_fine(const GGConfig& cfg, const GGBuffers& b, uint8_t* dst, size_
     if (rg.row1 <= rg.row0 || rg.px1 <= rg.px0) return;
     uint32_t n_pairs = (rg.px1 - rg.px0) * (rg.row1 - rg.row0);
     uint32_t blocks = (n_pairs + FINE_WARPS - 1) / FINE_WARPS;
-    uint32_t max_blocks = cfg.sm_count * 5;   // resident CTAs: 5 per SM (shared memory, registers)
+    // resident CTAs: 4 per SM at 128 registers. (5 at 96 registers spilled in the command loop: 10 % more instructions; the
+    // benchmark scene's fine stage, bound by single-warp latency, went 0.258 -> 0.215 ms with the wider budget.)
+    uint32_t max_blocks = cfg.sm_count * 4;
     if (blocks > max_blocks) blocks = max_blocks;
     const int smem = FINE_WARPS * FINE_SMEM_PER_WARP;
     cudaFuncSetAttribute(fine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);   // per device; cheap
