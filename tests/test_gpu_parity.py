@@ -913,3 +913,59 @@ def test_images_in_encoding(ctx):
     acc.RenderEncoding(tgt, enc)
     assert acc.resident_hits == 1 and (tgt.Data == out).all()
     acc.Close()
+
+
+@pytest.mark.gpu
+def test_graph_replay_no_wait_and_band_broadcast(ctx):
+    """The steady-state conveniences of round 2 on one device: a pass into a device target is replayed as a CUDA graph (two
+    cached, for a double-buffered target), GGCUDA_NO_WAIT returns before the device is done once the scene's counts are known
+    to fit, and ggcuda_broadcast_band copies a finished band on a side stream (here into two 'frames' of the same device) while
+    the next frame is rasterised. Every frame must equal the plain render bit for bit; changing what a graph was built from
+    (background, target, dirty rectangle) must not replay a stale one."""
+    import torch
+    from gg_b200 import scenes
+    w, h = 640, 400
+    enc, _, _ = scenes.config3(n=300, w=w, h=h, layer_every=5, nowipe=True)   # no wiping layers: the background shows
+    stream = torch.cuda.Stream()
+    side = torch.cuda.Stream()
+    ctx.set_stream(stream.cuda_stream)
+    try:
+        ctx.begin(w, h)
+        ctx.set_background((10, 20, 30, 255))
+        ctx.set_band(0, (h + 15) // 16)
+        ctx.add_encoding(*enc.streams())
+        truth = torch.zeros((h, w, 4), dtype=torch.uint8, device="cuda")
+        ctx.set_timing(True)                                   # events between the stages: the stream path, no graph
+        ctx.render_device(truth.data_ptr(), w * 4, G.KEEP_SCENE)
+        ctx.set_timing(False)
+        assert int(truth.sum().item()) > 0
+        bands_ = [torch.zeros_like(truth), torch.zeros_like(truth)]
+        frames = [torch.zeros_like(truth), torch.zeros_like(truth)]
+        for k in range(6):                                     # queued behind one another
+            b = bands_[k & 1]
+            ctx.render_device(b.data_ptr(), w * 4, G.KEEP_SCENE | G.NO_WAIT)
+            ctx.broadcast_band(b.data_ptr(), [f.data_ptr() for f in frames], b.numel(), side.cuda_stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+        for t in bands_ + frames:
+            assert bool((t == truth).all().item())
+        # a different background: same buffers, same target -> the configuration differs, the graph must be rebuilt
+        ctx.set_background((200, 0, 0, 255))
+        other = torch.zeros_like(truth)
+        ctx.render_device(other.data_ptr(), w * 4, G.KEEP_SCENE)
+        ctx.render_device(bands_[0].data_ptr(), w * 4, G.KEEP_SCENE)
+        torch.cuda.synchronize()
+        assert bool((bands_[0] == other).all().item()) and not bool((other == truth).all().item())
+        # a dirty rectangle applies to one render and is part of what a graph is keyed by
+        ctx.set_background((10, 20, 30, 255))
+        ctx.set_dirty_rect(64, 48, 200, 120)
+        ctx.render_device(other.data_ptr(), w * 4, G.KEEP_SCENE)
+        torch.cuda.synchronize()
+        inside = other[48:112, 64:192]
+        assert bool((inside == truth[48:112, 64:192]).all().item()) and not bool((other == truth).all().item())
+        ctx.render_device(other.data_ptr(), w * 4, G.KEEP_SCENE)
+        torch.cuda.synchronize()
+        assert bool((other == truth).all().item())
+    finally:
+        ctx.sync()
+        ctx.set_stream(0)
