@@ -702,15 +702,19 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
         uint32_t P = 0;
         if (lane == 0) P = atomicAdd(&bump->fine_cursor[part], 1u);
         P = __shfl_sync(0xffffffffu, P, 0);
-        uint32_t trow, pcol, only = 2u;   // only: the half to render (2 = both)
-        if (P < n_heavy) {
-            const uint32_t T = heavy_list[P];
+        uint32_t trow, pcol, only = 2u;   // only: the tile of the pair to render (2 = both)
+        uint32_t psel = 2u;               // heavy tiles: which four of a lane's eight pixels this warp is responsible for (2 = all)
+        if (P < 2u * n_heavy) {
+            // A listed tile goes to TWO warps: both replay the whole list, each blends the layers (the bulk of such a list) for
+            // four of every lane's eight pixels only and stores those -- the frame ends when the slowest warp does.
+            const uint32_t T = heavy_list[P >> 1];
+            psel = P & 1u;
             trow = T / cfg.width_in_tiles;
             const uint32_t tx = T - trow * cfg.width_in_tiles;
             pcol = tx >> 1; only = tx & 1u;
             if (trow < rg.row0 || trow >= rg.row1 || pcol < rg.px0 || pcol >= rg.px1) continue;   // another launch's tile
         } else {
-            P -= n_heavy;
+            P -= 2u * n_heavy;
             if (P >= n_pairs) break;
             trow = rg.row0 + P / npx;                  // tile row, relative to the band
             pcol = rg.px0 + P % npx;
@@ -785,6 +789,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                     __syncwarp();   // the scratch lies over the coverage table of the fill just evaluated
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) {
+                        if (psel != 2u && psel != (uint32_t)hf) continue;
 #pragma unroll
                         for (int i = 0; i < 4; i++) { scr[i * 32] = rgba[hf * 4 + i]; cvs[i * 32] = area[hf * 4 + i]; }
                         brush4(gtab, g, scr, cvs, (int)(tx * GG_TILE_W + xb) + hf * 4, (int)py);
@@ -801,7 +806,9 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                                                                      : spill + ((size_t)(sp_off + clip_depth - GG_BLEND_STACK_SPLIT) * 256 + lane);
                     if (clip_depth < GG_BLEND_STACK_SPLIT || sp_off != 0xffffffffu) {
 #pragma unroll
-                        for (int i = 0; i < PX; i++) { slot[i * 32] = rgba[i]; }
+                        for (int i = 0; i < PX; i++) {   // (a heavy tile's two warps share its spill slots: each saves its own four pixels)
+                            if (psel == 2u || psel == (uint32_t)(i >> 2)) slot[i * 32] = rgba[i];
+                        }
                     }
                     clip_depth++;
 #pragma unroll
@@ -819,6 +826,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                     __syncwarp();   // the scratch lies over the coverage table of the fill just evaluated
 #pragma unroll
                     for (int hf = 0; hf < 2; hf++) {
+                        if (psel != 2u && psel != (uint32_t)hf) continue;   // the other warp of this heavy tile does those
 #pragma unroll
                         for (int i = 0; i < 4; i++) { scr[i * 32] = rgba[hf * 4 + i]; cvs[i * 32] = area[hf * 4 + i]; }
                         end_clip4(blend, alpha, scr, cvs, slot + hf * 4 * 32);
@@ -837,7 +845,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
                     float4* o = reinterpret_cast<float4*>(dst + (size_t)(py - cfg.band_y0 * GG_TILE_H) * stride + (size_t)px * 16);
 #pragma unroll
                     for (int i = 0; i < PX; i++)
-                        if (px + i < cfg.width) o[i] = make_float4(clamp01(rgba[i].x), clamp01(rgba[i].y), clamp01(rgba[i].z), clamp01(rgba[i].w));
+                        if (px + i < cfg.width && (psel == 2u || psel == (uint32_t)(i >> 2))) o[i] = make_float4(clamp01(rgba[i].x), clamp01(rgba[i].y), clamp01(rgba[i].z), clamp01(rgba[i].w));
                 }
             } else {
                 // RGBA8 image of the tile in shared memory: rows of 64 bytes (tile B's lies over the coverage table)
@@ -860,6 +868,7 @@ __global__ void __launch_bounds__(FINE_WARPS * 32, 4) fine_kernel(GGConfig cfg, 
         for (uint32_t k = 0; k < 4; k++) {
             const uint32_t r = k * 4 + (lane >> 3), chunk = lane & 7u, half = chunk >> 2, cq = chunk & 3u;
             if (!((done >> half) & 1u)) continue;
+            if (psel != 2u && (cq & 1u) != psel) continue;   // a heavy tile's other warp stores the other four pixels of every lane
             uint4 v = *reinterpret_cast<const uint4*>((half ? img_b : img_a) + r * 16 + cq * 4);
             const uint32_t x = (pcol * 2 + half) * GG_TILE_W + cq * 4;
             const uint32_t y = (trow + cfg.band_y0) * GG_TILE_H + r;
