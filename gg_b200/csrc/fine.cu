@@ -8,15 +8,18 @@
 // and the PathSegment slice of every CmdFill in chunks of 32 segments through a second two-slot ring, the slice of the
 // NEXT fill (found by decoding ahead in the command list) in flight while the current one is evaluated.
 //
-// Coverage (fillPath, fine.go:219-289) without a single atomic: a lane only ever accumulates into ITS OWN row half.
-// The 32 segments of a chunk are first looked at in parallel (lane = segment: row span, 1/dy), a 32x32 bit transpose
-// built from warp ballots hands every (row, half) lane the set of segments that cross its row, and the lane walks
-// that set: the reference's trapezoid formula for the few columns the segment passes through, and ONE entry of a
-// per-lane difference table (fixed point: sums independent of the segment order, frames reproducible bit for bit) for
-// everything to its right (where the formula gives exactly dy). A running sum over the table's 8 entries at the end of
-// the fill yields the areas. Round 1 accumulated (segment, row) pairs with
-// shared-memory float atomics -- 15 ATOMS.CAST.SPIN loops in the innermost loop, 64 cycles per warp-wide atomic
-// (profiles/r1c_fine_kernel_ncu.txt); results also depended on the order the atomics landed in.
+// Coverage (fillPath, fine.go:219-289): the 32 segments of a chunk are first looked at in parallel (lane = segment: rows
+// crossed, 1/dy); a prefix sum of the row counts then deals the chunk's (segment, row) pairs to the lanes, 32 at a time.
+// A pair evaluates the reference's trapezoid formula for the few columns its segment passes through in that row and
+// records ONE difference for everything to the right (where the formula gives exactly dy) in the row's table, with
+// integer shared-memory atomics (native ATOMS.ADD; 2^-20 fixed point: sums independent of the order the segments arrive
+// in, frames reproducible bit for bit). A running sum over a lane's 8 entries at the end of the fill yields its areas.
+// Round 1 accumulated with shared-memory FLOAT atomics -- 15 ATOMS.CAST.SPIN compare-and-swap loops in the innermost
+// loop (profiles/r1c_fine_kernel_ncu.txt) -- and its results depended on the order the atomics landed in.
+//
+// Everything that is not on the path of a plain fill -- layer blending (29 modes), brushes (gradients, SDF round rects,
+// images) -- lives in out-of-line functions working on four pixels at a time through shared memory: the command loop has
+// to fit the 32 KB instruction cache of an SM (profiles/r2_summary.md).
 #include "pipeline.cuh"
 
 #define FINE_WARPS 4
