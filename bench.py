@@ -11,11 +11,15 @@ Workloads (BASELINE.json configs): config1 (512^2, 1 000 fills), config2 (1920x1
 config3_nowipe (the same with the 23 blend modes that never blank a tile), config4 (4K, 50 000 glyph outlines), config5
 (16384^2, 1 M paths). N GPUs: config3 is WEAK scaling -- N copies of the 4K frame stacked vertically, one band of 135 tile
 rows per GPU; every other workload is STRONG scaling -- the one canvas cut into N bands. A rank ingests only the paths
-that can reach its band. Band assembly: the fine kernel stores its band into every rank's frame itself (symmetric memory:
-one multimem.st per 16 bytes through the NVSwitch, or peer stores) followed by a barrier, or one NCCL all-gather issued by
-the library (GG_BANDS=p2p|p2p_nomc|nccl|torch_nccl; default p2p, NCCL if symmetric memory cannot be set up). `value` is device time (CUDA
-events, max over ranks); `e2e` is the same frame through the public host API with host buffers (scene ingest + H2D +
-pipeline + D2H inside the timed region). At N > 1 every rank's assembled frame is checked against the bands the ranks
+that can reach its band. Band assembly (GG_BANDS): `p2p` -- the fine kernel stores its band into every rank's frame itself
+(symmetric memory: one multimem.st per 16 bytes through the NVSwitch, `p2p_nomc`: peer stores) followed by a barrier;
+`p2p_async` -- the band is rendered privately and broadcast on a side stream while the next frame is rasterised
+(ggcuda_broadcast_band); `nccl` / `torch_nccl` -- one all-gather issued by the library / by torch. Default `auto`: p2p, or
+p2p_async when the receivers' ingress ((N - 1) bands per frame) would take longer than fine itself; NCCL if symmetric memory
+cannot be set up. A pass into device memory is replayed as one CUDA graph (GGCUDA_NO_GRAPH=1: through the stream). `value` is
+device time (CUDA events, max over ranks; in p2p_async ONE event pair around all K steps, L2 flushes included); the per-stage
+times come from a second set of passes with events between the stages. `e2e` is the same frame through the public host API
+with host buffers (scene ingest + H2D + pipeline + D2H inside the timed region). At N > 1 every rank's assembled frame is checked against the bands the ranks
 rendered (`frame_ok`). `--impl reference` times the CPU restatement of the reference's pipeline on the host cores.
 """
 import argparse
