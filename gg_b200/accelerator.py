@@ -248,3 +248,35 @@ class CUDAAccelerator:
         if dirty is not None:
             self.ctx.set_dirty_rect(*dirty)
         self.ctx.flush(target.Data, target.Stride, _lib.COMPOSITE_OVER if composite_over else 0)
+
+
+class PipelinedRenderer:
+    """Several frames in flight on one device: `depth` accelerators (each its own context, stream and buffers), one host
+    thread each. While one frame's pipeline and read-back occupy the device and the PCIe link, the next frame's encoding is
+    ingested and packed on another host thread (the library releases nothing it shares: a context is used by one thread at a
+    time, entry points set the device themselves; ctypes drops the GIL for the duration of a call). In Go this is `depth`
+    Accelerator values and goroutines. submit() returns a concurrent.futures.Future; frames complete in submission order per
+    slot, not globally -- wait on the future of the frame you need."""
+
+    def __init__(self, device=0, depth=2, band=None, background=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.accs = [CUDAAccelerator(device) for _ in range(depth)]
+        for a in self.accs:
+            a.Init()
+            if band is not None:
+                a.ctx.set_band(*band)
+            if background is not None:
+                a.ctx.set_background(background)
+        self.pools = [ThreadPoolExecutor(max_workers=1) for _ in range(depth)]
+        self.n = 0
+
+    def submit(self, target, enc, **kw):
+        i = self.n % len(self.accs)
+        self.n += 1
+        return self.pools[i].submit(self.accs[i].RenderEncoding, target, enc, **kw)
+
+    def Close(self):
+        for p in self.pools:
+            p.shutdown(wait=True)
+        for a in self.accs:
+            a.Close()

@@ -969,3 +969,28 @@ def test_graph_replay_no_wait_and_band_broadcast(ctx):
     finally:
         ctx.sync()
         ctx.set_stream(0)
+
+
+@pytest.mark.gpu
+def test_pipelined_renderer_frames_in_flight():
+    """Two contexts, two host threads (accelerator.PipelinedRenderer): different encodings submitted back to back come out as
+    the same pixels as the one-at-a-time accelerator renders them."""
+    from gg_b200 import accelerator as A, scenes
+    w, h = 320, 240
+    encs = [scenes.config3(n=150, w=w, h=h, layer_every=4, seed=s)[0] for s in (1, 2, 3, 4, 5)]
+    acc = A.CUDAAccelerator(); acc.Init()
+    want = []
+    for e in encs:
+        t = A.GPURenderTarget(w, h)
+        acc.RenderEncoding(t, e, resident=False)
+        want.append(t.Data.copy())
+    acc.Close()
+    pr = A.PipelinedRenderer(0, depth=2)
+    tgts = [A.GPURenderTarget(w, h) for _ in encs]
+    futs = [pr.submit(t, e, resident=False) for t, e in zip(tgts, encs)]
+    for f in futs:
+        f.result()
+    pr.Close()
+    for t, wnt in zip(tgts, want):
+        assert (t.Data == wnt).all()
+    assert not (want[0] == want[1]).all()
