@@ -65,6 +65,24 @@ void HostScene::clear(uint32_t w, uint32_t h) {
 // A pixel of slack covers the flattening tolerance and the float32 rounding of the device-side transform.
 bool HostScene::outside_band(const float t[6], const float* c, size_t n_coords, float reach) const {
     if (!cull || n_coords < 2) return false;
+    if (t[3] == 0.0f) {
+        // No shear into y (every transform of an axis-aligned scene): y' = fl(fl(t4 * y) + t5) is monotone in y, so the extremes
+        // of the raw ordinates map to the extremes of the transformed ones, bit for bit what the general loop below computes --
+        // two compares per point instead of two multiplies, two adds and two compares. A non-finite x makes the general
+        // form's 0 * x a NaN (never culled): kept.
+        float lo = 3.0e38f, hi = -3.0e38f, bad = 0.0f;
+        for (size_t k = 0; k + 1 < n_coords; k += 2) {
+            const float x = c[k], y = c[k + 1];
+            bad += x - x;                       // 0 for finite x, NaN otherwise
+            if (!(y == y)) return false;
+            lo = y < lo ? y : lo; hi = y > hi ? y : hi;
+        }
+        if (!(bad == 0.0f)) return false;
+        float a = t[4] * lo + t[5], b = t[4] * hi + t[5];
+        if (!(a == a) || !(b == b)) return false;
+        if (a > b) { const float sw = a; a = b; b = sw; }
+        return b + reach + 1.0f < cull_lo || a - reach - 1.0f > cull_hi;
+    }
     float lo = 3.0e38f, hi = -3.0e38f;
     for (size_t k = 0; k + 1 < n_coords; k += 2) {
         float y = t[3] * c[k] + t[4] * c[k + 1] + t[5];
@@ -801,7 +819,16 @@ int HostScene::add_encoding(const uint8_t* tg, size_t n_tags, const float* pd, s
             memcpy(cur_t, tr + 6 * ti, sizeof cur_t); ti++;
             break;
         case ST_SET_AA: di += 1; break;   // anti-aliasing is always on in this path
-        case ST_BEGIN_PATH: pt0 = pt1 = i + 1; pp0 = pi; path_active = true; break;
+        case ST_BEGIN_PATH: {
+            pt0 = pt1 = i + 1; pp0 = pi; path_active = true;
+            // the path's own element tags in one tight loop (most of an encoding's tags): coordinate counts from a table
+            static const struct NCoord { uint8_t n[256]; NCoord() { memset(n, 0xff, sizeof n); n[ST_MOVE_TO] = 2; n[ST_LINE_TO] = 2; n[ST_QUAD_TO] = 4;
+                                                                     n[ST_CUBIC_TO] = 6; n[ST_CLOSE_PATH] = 0; } } ncoord;
+            size_t j = i + 1;
+            for (; j < n_tags; j++) { const uint8_t nc = ncoord.n[tg[j]]; if (nc == 0xff) break; pi += nc; }
+            if (pi > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
+            pt1 = j; i = j - 1;
+        } break;
         case ST_MOVE_TO: case ST_LINE_TO:
             if (pi + 2 > n_pd) { *msg = "encoding: path stream underrun"; return GGCUDA_ERR_INVALID; }
             pi += 2; if (path_active) pt1 = i + 1; break;
