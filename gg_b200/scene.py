@@ -122,7 +122,7 @@ def _hash(enc, with_brushes):
     from . import _lib
     s = enc.streams()
     memo = enc.__dict__.setdefault("_hash_memo", {})
-    k = (id(s[0]), with_brushes)
+    k = (id(s[0]), with_brushes, tuple(id(im) for im in getattr(enc, "images", ())))   # (image arrays are treated as immutable once added)
     if k not in memo:
         memo.clear()
         hv = _lib.encoding_hash(s[0], s[1], s[2], s[3], s[4] if with_brushes else None)
