@@ -220,7 +220,9 @@ static vec2 es_eval_with_offset(vec2 p0, vec2 p1, const euler_params *ep, float 
 }
 
 /* ------------------------------------------------------------------ flatten.go */
-static const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f, FLATTEN_TOL = 0.25f;
+static const float DERIV_THRESH = 1e-6f, DERIV_EPS = 1e-6f, SUBDIV_LIMIT = 1.0f / 65536.0f;
+float ot_flatten_tol = 0.25f;   /* flatten.go:19; a test may tighten it to measure what the tolerance costs against gg's CPU path */
+#define FLATTEN_TOL ot_flatten_tol
 
 static void eval_cubic_and_deriv(vec2 p0, vec2 p1, vec2 p2, vec2 p3, float t, vec2 *po, vec2 *qo) { /* flatten.go:46-56 */
     float m = 1.0f - t;

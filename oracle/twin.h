@@ -139,6 +139,8 @@ void ot_fine_frame_mt(const ot_coarse *c, const float bg_premul[4], int w, int h
 uint32_t ot_scan_stages(const uint32_t *scene, uint32_t n_scene_words, uint32_t path_tag_base, uint32_t n_tag_words,
                         uint32_t draw_tag_base, uint32_t draw_data_base, uint32_t n_draw, uint32_t n_clips,
                         ot_path_monoid *tag_monoids, ot_draw_monoid *dm, uint32_t *info, int32_t *clip_inps_out);
+/* flatten.go:19 (0.25 px); a test may tighten it to measure what the tolerance costs against gg's CPU path */
+extern float ot_flatten_tol;
 /* 1 = reproduce coarse.go:425 (even-odd tile with an even non-zero backdrop and no segments is painted solid) */
 extern int ot_evenodd_solid_quirk;
 /* 1 = fine truncates the running colour to 8 bits after every CmdColor, as gg's CPU pixmap does (pixmap.go:218-228) */

@@ -158,6 +158,18 @@ def test_exact_area_twin_vs_gg_cpu_on_config1():
     assert res[0][0] < 2.0 and res[0][2] < 0.2
     assert abs(res[1][3]) < abs(res[0][3])      # the truncation bias shrinks in the quantising mode
     assert res[1][0] < res[0][0]
+    # ... and the flattening tolerance (flatten.go:19: 0.25 px; gg's CPU edges subdivide to ~0.1 px): tightened 50-fold in the oracle
+    # the mean drops by a third and the rest stays -- exact area is not Skia's AAA, whatever the polyline
+    tol = ctypes.c_float.in_dll(T.lib(), "ot_flatten_tol")
+    try:
+        tol.value = 0.005
+        exact, _ = T.render_packed(words, lay, w, h, (0, 0, 0, 0), os.cpu_count() or 1)
+    finally:
+        tol.value = 0.25
+    d = np.abs(exact.astype(int) - cpu.astype(int))
+    fine_tol = (float(d.mean()), int(d.max()), float((d.max(axis=2) > 2).mean()))
+    print(f"config1 (300 paths), flatten tolerance 0.005 px: mean |d| = {fine_tol[0]:.3f}/255, max = {fine_tol[1]}, {fine_tol[2] * 100:.2f}% beyond 2/255")
+    assert fine_tol[0] < res[0][0] and fine_tol[0] > 0.25 and fine_tol[1] > 2      # better, and still outside the north star's bounds
 
 
 def gg_cpu_render(enc, w, h):
